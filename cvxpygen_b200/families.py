@@ -1,0 +1,249 @@
+"""cvxpy-free builders of the problem families named by BASELINE.json.
+
+cvxpy is not installable in the build container, so the families the benchmark
+and the tests need are canonicalised by hand here into the same IR
+(``cvxpygen_b200.ir.CanonFamily``) that the reference's ``Canonicalizer`` would
+feed the solver plugin with (reference: cvxpygen/canonicalizer.py:86-122).
+The hand-derived forms are the compact ones of SURVEY Appendix D: they have fewer
+auxiliary variables than cvxpy's own canonicalisation, but the user-level
+variables and constraint duals coincide at the optimum.  Row signs follow
+cvxpy's convention (``lhs - rhs == 0`` for equalities, ``expr <= 0`` for
+inequalities) so that dual signs match the reference's.
+
+Families:
+  nonneg_ls(m, n)      README example (reference: examples/main.py:16-26)
+  mpc(nx, nu, N)       MPC QP (reference: tests/test_E2E_QP.py:44-73,127-146; BASELINE config 2)
+"""
+from typing import Optional
+
+import numpy as np
+import scipy.sparse as sp
+
+from .ir import CanonFamily, UserParam, UserVar, UserDual
+
+INF = 1e30  # OSQP_INFTY (reference: osqp_sources/include/constants.h:100; cvxpygen/utils.py:213-228 replace_inf)
+
+
+class _MapBuilder:
+    """Collects (entry, theta-column, coefficient) triplets of one affine map."""
+
+    def __init__(self, n_rows, n_theta):
+        self.n_rows, self.n_theta = n_rows, n_theta
+        self.r, self.c, self.v = [], [], []
+
+    def add(self, row, col, val):
+        self.r.append(row); self.c.append(col); self.v.append(val)
+
+    def const(self, row, val):
+        self.add(row, self.n_theta - 1, val)
+
+    def csr(self):
+        M = sp.coo_matrix((self.v, (self.r, self.c)), shape=(self.n_rows, self.n_theta)).tocsr()
+        M.sum_duplicates()
+        return M
+
+
+def _layout_params(specs):
+    """specs: list of (name, shape, default_flat) -> list of UserParam with running columns."""
+    params, col = [], 0
+    for name, shape, default in specs:
+        default = np.atleast_1d(np.asarray(default, dtype=float)).ravel()
+        params.append(UserParam(name, tuple(shape), default.size, col, default))
+        col += default.size
+    return params
+
+
+def _csc_pattern(M):
+    M = sp.csc_matrix(M)
+    M.sort_indices()
+    return M.indices.astype(np.int32), M.indptr.astype(np.int32), M.shape
+
+
+def default_mpc_dynamics(nx=12, nu=4, seed=0, dt=0.1):
+    """The survey-probe plant: nx/2 positions + nx/2 damped
+    velocities, nu force inputs.  Same construction and seed as BASELINE.md section 2."""
+    h = nx // 2
+    rs = np.random.RandomState(seed)
+    Ad = np.eye(nx)
+    Ad[:h, h:] = dt * np.eye(h)
+    Ad[h:, h:] *= 0.98
+    M = rs.randn(h, nu)
+    Bd = np.zeros((nx, nu))
+    Bd[h:, :] = dt * M
+    Bd[:h, :] = 0.5 * dt * dt * M
+    return Ad, Bd
+
+
+def mpc(nx=12, nu=4, N=10, Ad=None, Bd=None, Q=None, QN=None, R=None, umax=1.0,
+        x_init=None, d_const=0.0, name=None) -> CanonFamily:
+    """MPC QP, compact sparse stacking:
+
+        min  sum_{k<N} x_k'Q x_k + x_N'QN x_N + sum_{k<N} u_k'R u_k  (+ d_const)
+        s.t. x_{k+1} = Ad x_k + Bd u_k,  x_0 = x_init,  |u_k|_inf <= umax
+
+    canonical x = [X(:) ; U(:)]  (X is nx x (N+1), U is nu x N, Fortran order).
+    P = 2*blkdiag(Q.., QN, R..) because the reference objective has no 1/2
+    (reference: tests/test_E2E_QP.py:63-64).
+    rows:  [0, nx)            x_0 = x_init                          (user constraint d2)
+           [nx, (N+1)nx)      x_{k+1} - Ad x_k - Bd u_k = 0         (user constraint d0)
+           [(N+1)nx, +N*nu)   -umax <= u <= umax                    (user constraint d1)
+    Only ``x_init`` is a user parameter: it enters l and u of the first nx rows.
+    """
+    if Ad is None or Bd is None:
+        Ad, Bd = default_mpc_dynamics(nx, nu)
+    Q = np.eye(nx) if Q is None else np.asarray(Q, float)
+    QN = Q if QN is None else np.asarray(QN, float)
+    R = 0.1 * np.eye(nu) if R is None else np.asarray(R, float)
+    if x_init is None:
+        x_init = np.zeros(nx)
+    nX, nU = (N + 1) * nx, N * nu
+    n, n_eq, n_ineq = nX + nU, nX, nU
+    m = n_eq + n_ineq
+    params = _layout_params([('x_init', (nx,), x_init)])
+    n_theta = nx + 1
+
+    # --- P (upper triangle, CSC) and A (CSC): constants of the family
+    P = sp.block_diag([2 * Q] * N + [2 * QN] + [2 * R] * N, format='csc')
+    Pu = sp.triu(P, format='csc'); Pu.eliminate_zeros(); Pu.sort_indices()
+    Ax_blocks = sp.eye(nX, format='csc') - sp.kron(sp.eye(N + 1, k=-1), sp.csc_matrix(Ad), format='csc')
+    Au_blocks = -sp.kron(sp.vstack([sp.csc_matrix((1, N)), sp.eye(N)]), sp.csc_matrix(Bd), format='csc')
+    A = sp.vstack([sp.hstack([Ax_blocks, Au_blocks]),
+                   sp.hstack([sp.csc_matrix((nU, nX)), sp.eye(nU)])], format='csc')
+    A.eliminate_zeros(); A.sort_indices()
+
+    maps = {}
+    mb = _MapBuilder(Pu.nnz, n_theta)
+    for k, v in enumerate(Pu.data):
+        mb.const(k, v)
+    maps['P'] = mb.csr()
+    mb = _MapBuilder(A.nnz, n_theta)
+    for k, v in enumerate(A.data):
+        mb.const(k, v)
+    maps['A'] = mb.csr()
+    maps['q'] = sp.csr_matrix((n, n_theta))
+    mb = _MapBuilder(1, n_theta); mb.const(0, d_const); maps['d'] = mb.csr()
+    ml, mu = _MapBuilder(m, n_theta), _MapBuilder(m, n_theta)
+    for i in range(nx):                      # x_0 = x_init
+        ml.add(i, i, 1.0); mu.add(i, i, 1.0)
+    for i in range(n_ineq):                  # input box
+        ml.const(n_eq + i, -umax); mu.const(n_eq + i, umax)
+    maps['l'], maps['u'] = ml.csr(), mu.csr()
+
+    variables = [UserVar('U', (nu, N), nX + np.arange(nU)),
+                 UserVar('X', (nx, N + 1), np.arange(nX))]
+    duals = [UserDual('d0', 'y', (nx, N), nx + np.arange(N * nx)),
+             UserDual('d1', 'y', (nu, N), n_eq + np.arange(nU)),
+             UserDual('d2', 'y', (nx,), np.arange(nx))]
+    return CanonFamily(name or f'mpc_{nx}_{nu}_{N}', 'quadratic', n, n_eq, n_ineq, params, maps,
+                       {'P': _csc_pattern(Pu), 'A': _csc_pattern(A)}, variables, duals)
+
+
+def nonneg_ls(m=3, n=2, A_pattern=None, A_data=None, b=None, seed=1, name=None) -> CanonFamily:
+    """README example  min ||A x - b||^2  s.t. x >= 0  (reference: examples/main.py:16-26).
+
+    canonical x = [x(n) ; t(m)] with t = A x - b (the epigraph-free part of what cvxpy's
+    sum_squares canonicalisation introduces), P = 2 I on t.
+    rows:  [0, m)      A x - t = b          (no user dual)
+           [m, m+n)    -x <= 0              (user constraint d0, dual >= 0)
+    User parameters: ``A`` (sparse, stored entries in column order -- reference README.md:140-143)
+    enters the canonical matrix A; ``b`` enters l and u.
+    """
+    rs = np.random.RandomState(seed)
+    if A_pattern is None:
+        A_pattern = ((0, 0, 1), (0, 1, 1)) if (m, n) == (3, 2) else tuple(np.nonzero(np.ones((m, n))))
+    rows, cols = np.asarray(A_pattern[0]), np.asarray(A_pattern[1])
+    order = np.lexsort((rows, cols))            # column-major order of the stored entries
+    rows, cols = rows[order], cols[order]
+    nnzA = rows.size
+    if A_data is None:
+        A_data = rs.randn(nnzA)
+    if b is None:
+        b = rs.randn(m)
+    params = _layout_params([('A', (m, n), A_data), ('b', (m,), b)])
+    colA, colb = params[0].col, params[1].col
+    n_theta = nnzA + m + 1
+    nv, n_eq, n_ineq = n + m, m, n
+    mtot = n_eq + n_ineq
+
+    Pu = sp.csc_matrix((2 * np.ones(m), (n + np.arange(m), n + np.arange(m))), shape=(nv, nv))
+    # canonical A pattern: [A_user, -I ; -I, 0]; tag each stored entry with its source
+    ent = [(r, c, ('A', k)) for k, (r, c) in enumerate(zip(rows, cols))]
+    ent += [(i, n + i, ('c', -1.0)) for i in range(m)]
+    ent += [(m + j, j, ('c', -1.0)) for j in range(n)]
+    ent.sort(key=lambda e: (e[1], e[0]))
+    Ar = np.array([e[0] for e in ent]); Ac = np.array([e[1] for e in ent])
+    indptr = np.zeros(nv + 1, dtype=np.int32)
+    np.add.at(indptr, Ac + 1, 1); indptr = np.cumsum(indptr).astype(np.int32)
+    mbA = _MapBuilder(len(ent), n_theta)
+    for k, e in enumerate(ent):
+        if e[2][0] == 'A':
+            mbA.add(k, colA + e[2][1], 1.0)
+        else:
+            mbA.const(k, e[2][1])
+    maps = {'A': mbA.csr()}
+    mb = _MapBuilder(Pu.nnz, n_theta)
+    for k in range(Pu.nnz):
+        mb.const(k, 2.0)
+    maps['P'] = mb.csr()
+    maps['q'] = sp.csr_matrix((nv, n_theta))
+    maps['d'] = sp.csr_matrix((1, n_theta))
+    ml, mu = _MapBuilder(mtot, n_theta), _MapBuilder(mtot, n_theta)
+    for i in range(m):
+        ml.add(i, colb + i, 1.0); mu.add(i, colb + i, 1.0)
+    for j in range(n):
+        ml.const(m + j, -INF)
+    maps['l'], maps['u'] = ml.csr(), mu.csr()
+    variables = [UserVar('x', (n,), np.arange(n))]
+    duals = [UserDual('d0', 'y', (n,), m + np.arange(n))]
+    return CanonFamily(name or f'nonneg_LS_{m}_{n}', 'quadratic', nv, n_eq, n_ineq, params, maps,
+                       {'P': _csc_pattern(Pu), 'A': (Ar.astype(np.int32), indptr, (mtot, nv))},
+                       variables, duals)
+
+
+def random_qp(n=20, m_eq=5, m_ineq=15, density=0.3, seed=0, name=None) -> CanonFamily:
+    """Generic sparse QP family with unstructured sparsity -- exercises the generic level scheduler.
+    User parameters: ``q`` (linear cost), ``b`` (equality rhs), ``h`` (inequality upper bounds)."""
+    rs = np.random.RandomState(seed)
+    Mh = sp.random(n, n, density=density, random_state=rs, data_rvs=rs.randn).toarray()
+    Pfull = Mh @ Mh.T * 0.5 + 0.1 * np.eye(n)
+    Pfull[np.abs(Pfull) < 0.05] = 0.0
+    Pfull = 0.5 * (Pfull + Pfull.T) + np.eye(n) * (np.abs(Pfull).sum(1).max())  # diagonally dominant => PSD
+    Pu = sp.triu(sp.csc_matrix(Pfull), format='csc'); Pu.sort_indices()
+    Aeq = sp.random(m_eq, n, density=density, random_state=rs, data_rvs=rs.randn).toarray()
+    for i in range(m_eq):
+        if not Aeq[i].any():
+            Aeq[i, rs.randint(n)] = 1.0
+    Ain = sp.random(m_ineq, n, density=density, random_state=rs, data_rvs=rs.randn).toarray()
+    for i in range(m_ineq):
+        if not Ain[i].any():
+            Ain[i, rs.randint(n)] = 1.0
+    A = sp.csc_matrix(np.vstack([Aeq, Ain])); A.sort_indices()
+    x0 = rs.randn(n)
+    params = _layout_params([('q', (n,), rs.randn(n)), ('b', (m_eq,), Aeq @ x0),
+                             ('h', (m_ineq,), Ain @ x0 + rs.rand(m_ineq))])
+    n_theta = n + m_eq + m_ineq + 1
+    m = m_eq + m_ineq
+    maps = {}
+    mb = _MapBuilder(Pu.nnz, n_theta)
+    for k, v in enumerate(Pu.data):
+        mb.const(k, v)
+    maps['P'] = mb.csr()
+    mb = _MapBuilder(A.nnz, n_theta)
+    for k, v in enumerate(A.data):
+        mb.const(k, v)
+    maps['A'] = mb.csr()
+    mb = _MapBuilder(n, n_theta)
+    for i in range(n):
+        mb.add(i, params[0].col + i, 1.0)
+    maps['q'] = mb.csr()
+    maps['d'] = sp.csr_matrix((1, n_theta))
+    ml, mu = _MapBuilder(m, n_theta), _MapBuilder(m, n_theta)
+    for i in range(m_eq):
+        ml.add(i, params[1].col + i, 1.0); mu.add(i, params[1].col + i, 1.0)
+    for i in range(m_ineq):
+        ml.const(m_eq + i, -INF); mu.add(m_eq + i, params[2].col + i, 1.0)
+    maps['l'], maps['u'] = ml.csr(), mu.csr()
+    variables = [UserVar('x', (n,), np.arange(n))]
+    duals = [UserDual('d0', 'y', (m_eq,), np.arange(m_eq)), UserDual('d1', 'y', (m_ineq,), m_eq + np.arange(m_ineq))]
+    return CanonFamily(name or f'random_qp_{n}_{m_eq}_{m_ineq}', 'quadratic', n, m_eq, m_ineq, params, maps,
+                       {'P': _csc_pattern(Pu), 'A': _csc_pattern(A)}, variables, duals)

@@ -1,0 +1,149 @@
+"""Solver-independent intermediate representation of one DPP problem family.
+
+This is the cvxpy-independent hand-off between canonicalisation and the CUDA
+code generator.  It carries the same information the reference keeps in its
+``Canon`` bundle (reference: cvxpygen/mappings.py:34-145 -- ParameterCanon,
+ParameterInfo, PrimalVariableInfo, DualVariableInfo) but organised per object
+instead of per attribute, so that a family can be built either
+
+  * by hand, without cvxpy (``cvxpygen_b200.families``), or
+  * from the reference's own ``Canonicalizer`` output when cvxpy is installed
+    (``CanonFamily.from_reference_canon``).
+
+Conventions (reference: SURVEY Appendix B; cvxpygen/canonicalizer.py:226-332):
+
+  theta = [user parameters flattened in user sparsity, Fortran order ; 1.0]
+  canonical object ``id``  =  maps[id] @ theta            (CSR, one row per stored entry)
+
+QP form   (reference: cvxpygen/solvers/_interface.py:18-79):
+      min 1/2 x'Px + q'x + d   s.t.  l <= Ax <= u,  rows = [equalities ; inequalities]
+      P is the upper-triangular CSC, A is CSC; the maps produce their ``.data``.
+Conic form (reference: cvxpygen/solvers/_interface.py:132-173):
+      min c'x + d  s.t.  Ax = b,  h - Gx in K.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import scipy.sparse as sp
+
+
+@dataclass
+class UserParam:
+    """One user-level parameter (reference: ParameterInfo, cvxpygen/mappings.py:51-68)."""
+    name: str
+    shape: Tuple[int, ...]
+    size: int            # number of stored entries (user sparsity: diag / sparse params store fewer)
+    col: int             # first column of this parameter in theta
+    default: np.ndarray  # flat default value, length ``size``
+
+
+@dataclass
+class UserVar:
+    """One user-level primal variable: a gather from the canonical solution
+    (reference: PrimalVariableInfo.name_to_indices, cvxpygen/canonicalizer.py:124-158)."""
+    name: str
+    shape: Tuple[int, ...]
+    indices: np.ndarray  # positions in canonical x, Fortran order of the variable
+
+
+@dataclass
+class UserDual:
+    """One user-level constraint dual (reference: DualVariableInfo.name_to_indices,
+    cvxpygen/canonicalizer.py:160-224).  ``vec`` is 'y' for the QP form, 'y'/'z' for conic."""
+    name: str
+    vec: str
+    shape: Optional[Tuple[int, ...]]
+    indices: np.ndarray
+
+
+@dataclass
+class CanonFamily:
+    name: str
+    solver_type: str                      # 'quadratic' | 'conic'
+    n_var: int
+    n_eq: int
+    n_ineq: int
+    params: List[UserParam]
+    maps: Dict[str, sp.csr_matrix]        # canonical id -> CSR (entries x n_theta)
+    patterns: Dict[str, Tuple[np.ndarray, np.ndarray, Tuple[int, int]]]  # 'P','A','G' -> (indices, indptr, shape) CSC
+    variables: List[UserVar]
+    duals: List[UserDual]
+    is_maximization: bool = False
+    cone_dims: Dict[str, object] = field(default_factory=dict)   # conic: {'l': int, 'q': [int,...]}
+
+    # ---- parameter vector ---------------------------------------------------
+    @property
+    def n_theta(self) -> int:
+        return sum(p.size for p in self.params) + 1
+
+    def param(self, name: str) -> UserParam:
+        for p in self.params:
+            if p.name == name:
+                return p
+        raise AttributeError(f'{name} is not a parameter.')   # same error text as TPL/cpg_solver.py.jinja2:50-51
+
+    def theta_default(self) -> np.ndarray:
+        th = np.ones(self.n_theta)
+        for p in self.params:
+            th[p.col:p.col + p.size] = np.asarray(p.default, dtype=float).ravel()
+        return th
+
+    # ---- canonical data -----------------------------------------------------
+    def canon_data(self, p_id: str, theta: Optional[np.ndarray] = None) -> np.ndarray:
+        """Stored entries of canonical object ``p_id`` for one theta (a2: cpg_canonicalize_<id>,
+        reference emitter cvxpygen/utils.py:279-294)."""
+        th = self.theta_default() if theta is None else theta
+        return np.asarray(self.maps[p_id] @ th).ravel()
+
+    def canon_matrix(self, p_id: str, theta: Optional[np.ndarray] = None) -> sp.csc_matrix:
+        idx, ptr, shape = self.patterns[p_id]
+        return sp.csc_matrix((self.canon_data(p_id, theta), idx.copy(), ptr.copy()), shape=shape)
+
+    def changes(self, p_id: str, names: Optional[List[str]] = None) -> bool:
+        """Does canonical object p_id depend on (the given subset of) user parameters?
+        (reference: p_id_to_changes, cvxpygen/canonicalizer.py:324)."""
+        M = self.maps.get(p_id)
+        if M is None:
+            return False
+        cols = self.param_columns(names)
+        return M[:, cols].nnz > 0 if len(cols) else False
+
+    def param_columns(self, names: Optional[List[str]] = None) -> np.ndarray:
+        ps = self.params if names is None else [self.param(n) for n in names]
+        if not ps:
+            return np.zeros(0, dtype=int)
+        return np.concatenate([np.arange(p.col, p.col + p.size) for p in ps])
+
+    def outdated_by(self, name: str) -> List[str]:
+        """canonical ids touched by one user parameter (adjacency, cvxpygen/canonicalizer.py:117-120)."""
+        return [k for k in self.maps if self.changes(k, [name])]
+
+    # ---- bridge from the reference's own canonicaliser (needs cvxpy; untested here) ----
+    @classmethod
+    def from_reference_canon(cls, name, canon, solver_interface) -> 'CanonFamily':
+        """Build the IR from (Canon, SolverInterface) as returned by the reference's
+        ``Canonicalizer.canonicalize`` (cvxpygen/canonicalizer.py:47-52).  Only attribute
+        reads -- nothing of cvxpygen is imported here."""
+        pi, pc = canon.parameter_info, canon.parameter_canon
+        pv, dv = canon.prim_variable_info, canon.dual_variable_info
+        params = []
+        for col in sorted(pi.col_to_name_usp):
+            nm = pi.col_to_name_usp[col]
+            sz = pi.name_to_size_usp[nm]
+            params.append(UserParam(nm, tuple(pi.name_to_shape[nm]), sz, col,
+                                    np.asarray(pi.flat_usp[col:col + sz], dtype=float)))
+        maps = {k: sp.csr_matrix(v) for k, v in pc.p_id_to_mapping.items() if v is not None}
+        patterns = {}
+        for k, M in pc.p.items():
+            if sp.issparse(M):
+                M = sp.csc_matrix(M)
+                patterns[k] = (M.indices.copy(), M.indptr.copy(), M.shape)
+        variables = [UserVar(n, tuple(pv.name_to_shape[n]), np.asarray(pv.name_to_indices[n]))
+                     for n in pv.name_to_indices]
+        duals = [UserDual(n, v, dv.name_to_shape[n], np.asarray(ix))
+                 for n, (v, ix) in dv.name_to_indices.items()]
+        fam = cls(name, solver_interface.solver_type, solver_interface.n_var, solver_interface.n_eq,
+                  solver_interface.n_ineq, params, maps, patterns, variables, duals,
+                  is_maximization=pc.is_maximization)
+        return fam
