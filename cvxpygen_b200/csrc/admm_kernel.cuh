@@ -1,0 +1,586 @@
+// admm_kernel.cuh -- batched ADMM (OSQP-style) QP solver for sm_100a, one problem instance per warp.
+//
+// Hand-written device code shared by every generated problem family; the generator emits
+// only compile-time sizes (cpg_family.h), the blob-header struct (cpg_blob_layout.h) and the
+// constants blob.  What it replaces, per instance, is the reference's generated
+//   cpg_canonicalize_<id>()                       cvxpygen/utils.py:279-294      (a2)
+//   osqp_update_data_vec / update bounds          osqp_sources/src/osqp.c:752-827 (a3)
+//   osqp_solve main loop                          src/osqp.c:288-645              (a4)
+//     compute_rhs / update_xz_tilde               src/auxil.c:161-183             (a5)
+//     solve_linsys_qdldl -> QDLDL_solve           qdldl_interface.c:341-376, qdldl.c:236-281 (a6)
+//     update_x / update_z+project / update_y      src/auxil.c:185-225, src/proj.c:4-14      (a7)
+//     update_info, residuals, check_termination   src/auxil.c:240-359, 361-512, 564-629, 681-786 (a8)
+//     compute_rho_estimate / adapt_rho            src/auxil.c:13-74               (a9, decision only)
+//   store_solution / unscale_solution / obj       src/auxil.c:524-562, src/scaling.c:177-192 (a11)
+//   cpg_retrieve_prim / dual / info               cvxpygen/utils.py:950-985       (a12)
+//
+// Data layout
+//   * constants blob (factor schedule, scaled A/P for the residuals, scalings, maps) staged ONCE per
+//     CTA global->shared with TMA bulk copies (cp.async.bulk + mbarrier complete_tx);
+//   * per-instance ADMM state x, z, y, q, l, u lives in REGISTERS, element i of a vector on lane i%32;
+//   * the only per-warp shared memory is the (n+m)-double work vector w of the KKT solve;
+//   * HBM is touched only to read the instance's parameters and to write its solution rows
+//     (coalesced: a warp writes consecutive doubles of one row).
+//   * persistent CTAs: warps pull instance indices from a global counter, so instances that stop
+//     at iteration 25 do not leave lanes idle while a neighbour runs to 100.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "cpg_blob_layout.h"
+
+namespace cpgb200 {
+
+constexpr int LANES = 32;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr double OSQP_INFTY = 1e30;
+constexpr double MIN_SCALING = 1e-4;
+constexpr double RHO_MIN = 1e-6, RHO_MAX = 1e6, RHO_TOL = 1e-4, RHO_EQ_FACTOR = 1e3;
+constexpr double DIVISION_TOL = 1.0 / OSQP_INFTY;
+
+// status codes = OSQP's (osqp_sources/include/constants.h:18-30) plus one internal hand-off code
+enum : int { ST_SOLVED = 1, ST_SOLVED_INACC = 2, ST_PINF_INACC = 3, ST_DINF_INACC = 4, ST_MAXITER = -2,
+             ST_PINF = -3, ST_DINF = -4, ST_NONCVX = -7, ST_UNSOLVED = -10, ST_HANDOFF = -100 };
+
+struct Settings {          // cvxpygen's OSQP settings table, cvxpygen/solvers/osqp.py:102-115
+  int max_iter, check_termination, scaled_termination, warm_start;
+  int adaptive_rho, adaptive_rho_interval, scaling, pad;
+  double eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, alpha, adaptive_rho_tolerance;
+};
+
+struct BatchIO {
+  const double* params;    // (B, npb) row-major: the batched user parameters of each instance
+  const double* x0;        // optional warm start, canonical, UNscaled: (B, n) / (B, m)
+  const double* y0;
+  double* prim;            // (B, n_prim) user-level primal variables, concatenated in declaration order
+  double* dual;            // (B, n_dual) user-level constraint duals
+  double* sol_x;           // optional canonical solution (B, n) / (B, m)   (gradient path needs it)
+  double* sol_y;
+  double* obj_val; int* iter; int* status; double* pri_res; double* dua_res;   // CPG_Info, SoA
+  unsigned int* work_counter;   // persistent-CTA instance queue
+  int* tail_count;              // instances handed to the refactorisation kernel
+  int* tail_ids;
+  double* tail_state;           // per handed-off instance: x(n) z(m) y(m) rho_new iter   (scaled iterates)
+  int B;
+  int tail_capacity;
+};
+
+// ---------------------------------------------------------------- TMA bulk copy + mbarrier helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ---------------------------------------------------------------- warp reductions
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------- ELL sparse dot products
+// row-blocked ELL: table entry = {K, f64 offset, u16 offset}; entry k of lane's row at [k*32 + lane]
+__device__ __forceinline__ double ell_dot(const int* tab, const double* F64, const uint16_t* U16,
+                                          const double* vec, int lane) {
+  const int K = tab[0];
+  const double* v = F64 + tab[1] + lane;
+  const uint16_t* c = U16 + tab[2] + lane;
+  double a0 = 0.0, a1 = 0.0;
+  int k = 0;
+  for (; k + 1 < K; k += 2) {
+    a0 = fma(v[k * LANES], vec[c[k * LANES]], a0);
+    a1 = fma(v[(k + 1) * LANES], vec[c[(k + 1) * LANES]], a1);
+  }
+  if (k < K) a0 = fma(v[k * LANES], vec[c[k * LANES]], a0);
+  return a0 + a1;
+}
+
+// one schedule tile: every lane accumulates its slice of a row, rows spread over 32/r_pad lanes
+__device__ __forceinline__ double tile_acc(const int4 h0, const double* F64, const uint16_t* U16,
+                                           const double* w, int lane) {
+  const double* v = F64 + h0.x + lane;
+  const uint16_t* c = U16 + h0.y + lane;
+  const int K = h0.z;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int k = 0;
+  for (; k + 3 < K; k += 4) {
+    a0 = fma(v[(k + 0) * LANES], w[c[(k + 0) * LANES]], a0);
+    a1 = fma(v[(k + 1) * LANES], w[c[(k + 1) * LANES]], a1);
+    a2 = fma(v[(k + 2) * LANES], w[c[(k + 2) * LANES]], a2);
+    a3 = fma(v[(k + 3) * LANES], w[c[(k + 3) * LANES]], a3);
+  }
+  for (; k < K; ++k) a0 = fma(v[k * LANES], w[c[k * LANES]], a0);
+  double acc = (a0 + a1) + (a2 + a3);
+  for (int o = 16; o >= h0.w; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+  return acc;
+}
+
+// K x = b in pivot order, in place in w (a6).  Forward tiles, dense trailing block, backward tiles.
+template <int TRAIL>
+__device__ __forceinline__ void kkt_solve(const CpgBlobHeader* H, const int* I32, const double* F64,
+                                          const uint16_t* U16, double* w, int lane) {
+  const int4* T = reinterpret_cast<const int4*>(I32 + H->i_tiles);
+  const int nf = H->n_fwd_tiles, nt = H->n_tiles;
+  int t = 0;
+  for (; t < nf; ++t) {
+    const int4 h0 = T[2 * t], h1 = T[2 * t + 1];
+    const double acc = tile_acc(h0, F64, U16, w, lane);
+    __syncwarp();
+    if (lane < h1.x) w[U16[h1.y + lane]] = acc;
+    __syncwarp();
+  }
+  if (TRAIL > 0) {           // all trailing tiles read the whole block: gather everything, then write
+    double tacc[TRAIL > 0 ? TRAIL : 1];
+#pragma unroll
+    for (int j = 0; j < TRAIL; ++j) tacc[j] = (j < H->n_trail_tiles) ? tile_acc(T[2 * (t + j)], F64, U16, w, lane) : 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < TRAIL; ++j) {
+      if (j < H->n_trail_tiles) {
+        const int4 h1 = T[2 * (t + j) + 1];
+        if (lane < h1.x) w[U16[h1.y + lane]] = tacc[j];
+      }
+    }
+    __syncwarp();
+    t += H->n_trail_tiles;
+  }
+  for (; t < nt; ++t) {
+    const int4 h0 = T[2 * t], h1 = T[2 * t + 1];
+    const double acc = tile_acc(h0, F64, U16, w, lane);
+    __syncwarp();
+    if (lane < h1.x) w[U16[h1.y + lane]] = acc;
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- per-instance solver
+template <class Fam>
+struct Instance {
+  static constexpr int N = Fam::N, M = Fam::M, NXL = (N + 31) / 32, NZL = (M + 31) / 32;
+  static constexpr int NZLs = NZL > 0 ? NZL : 1;
+
+  double x[NXL], q[NXL];
+  double z[NZLs], y[NZLs], l[NZLs], u[NZLs];
+  double dx[NXL], dy[NZLs];
+  unsigned eqmask, loosemask;     // bit k: constraint row lane+32k is an equality / a loose row
+
+  // residual bookkeeping of the last update_info
+  double pri_res, dua_res, xPx, qx;
+  double nrm_z, nrm_Ax, nrm_q, nrm_Aty, nrm_Px;                 // termination norms (unscaled unless scaled_termination)
+  double s_rp, s_rd, s_z, s_Ax, s_q, s_Aty, s_Px;               // SCALED norms for compute_rho_estimate
+
+  __device__ __forceinline__ double rho_of(int k, double rho_in, double rho_eq) const {
+    return ((loosemask >> k) & 1u) ? RHO_MIN : (((eqmask >> k) & 1u) ? rho_eq : rho_in);
+  }
+};
+
+template <class Fam>
+__device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* __restrict__ I32,
+                               const double* __restrict__ F64, const uint16_t* __restrict__ U16,
+                               double* __restrict__ w, const int lane, const int b,
+                               const BatchIO& io, const Settings& st) {
+  using I = Instance<Fam>;
+  constexpr int N = I::N, M = I::M, NXL = I::NXL, NZL = I::NZL;
+  I s;
+  const double* Dv = F64 + H->f_D;  const double* Dinv = F64 + H->f_Dinv;
+  const double* Ev = F64 + H->f_E;  const double* Einv = F64 + H->f_Einv;
+  const double c = H->c, cinv = H->cinv, sigma = H->sigma, alpha = st.alpha;
+  const bool unscale = st.scaling && !st.scaled_termination;
+
+  // ---- a1/a2/a3: canonicalise the instance's vectors and scale them (q <- c D q ; l,u <- E l, E u)
+  const double* th = io.params + (size_t)b * H->npb;
+  int px[NXL], pz[I::NZLs];
+  bool type_mismatch = false;
+  s.eqmask = 0u; s.loosemask = 0u;
+#pragma unroll
+  for (int k = 0; k < NXL; ++k) {
+    const int i = lane + 32 * k;
+    s.q[k] = 0.0; s.x[k] = 0.0; s.dx[k] = 0.0; px[k] = 0;
+    if (i < N) {
+      const int* tab = I32 + H->i_ellMq + 3 * k;
+      double acc = F64[H->f_qbase + i];
+      const int K = tab[0];
+      for (int kk = 0; kk < K; ++kk)
+        acc = fma(F64[tab[1] + kk * LANES + lane], __ldg(th + U16[tab[2] + kk * LANES + lane]), acc);
+      s.q[k] = (Dv[i] * acc) * c;
+      px[k] = U16[H->h_pinvx + i];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NZL; ++k) {
+    const int j = lane + 32 * k;
+    s.l[k] = 0.0; s.u[k] = 0.0; s.z[k] = 0.0; s.y[k] = 0.0; s.dy[k] = 0.0; pz[k] = 0;
+    if (j < M) {
+      const int* tl = I32 + H->i_ellMl + 3 * k;
+      const int* tu = I32 + H->i_ellMu + 3 * k;
+      double al = F64[H->f_lbase + j], au = F64[H->f_ubase + j];
+      for (int kk = 0; kk < tl[0]; ++kk)
+        al = fma(F64[tl[1] + kk * LANES + lane], __ldg(th + U16[tl[2] + kk * LANES + lane]), al);
+      for (int kk = 0; kk < tu[0]; ++kk)
+        au = fma(F64[tu[1] + kk * LANES + lane], __ldg(th + U16[tu[2] + kk * LANES + lane]), au);
+      al = fmin(fmax(al, -OSQP_INFTY), OSQP_INFTY);
+      au = fmin(fmax(au, -OSQP_INFTY), OSQP_INFTY);
+      s.l[k] = Ev[j] * al; s.u[k] = Ev[j] * au;
+      pz[k] = U16[H->h_pinvz + j];
+      // constraint type on the scaled bounds (set_rho_vec / update_rho_vec, auxil.c:76-142)
+      const bool loose = (s.l[k] < -OSQP_INFTY * MIN_SCALING) && (s.u[k] > OSQP_INFTY * MIN_SCALING);
+      const bool eq = !loose && (s.u[k] - s.l[k] < RHO_TOL);
+      const int ct = loose ? 0 : (eq ? 2 : 1);
+      type_mismatch |= (ct != (int)U16[H->h_ctype + j]);
+      if (eq) s.eqmask |= 1u << k;
+      if (loose) s.loosemask |= 1u << k;
+    }
+  }
+  type_mismatch = __any_sync(FULL, type_mismatch);
+
+  const double rho_in = H->rho, rho_eq = RHO_EQ_FACTOR * H->rho;
+  const double rinv_in = 1.0 / rho_in, rinv_eq = 1.0 / rho_eq, rinv_loose = 1.0 / RHO_MIN;
+  auto rinv_of = [&](int k) -> double {
+    return ((s.loosemask >> k) & 1u) ? rinv_loose : (((s.eqmask >> k) & 1u) ? rinv_eq : rinv_in);
+  };
+
+  // ---- cold start (auxil.c:155-159) or warm start (osqp.c:929-953: x <- Dinv x, y <- c Einv y, z <- A x)
+  if (st.warm_start && io.x0 != nullptr && io.y0 != nullptr) {
+#pragma unroll
+    for (int k = 0; k < NXL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < N) { s.x[k] = Dinv[i] * io.x0[(size_t)b * N + i]; w[i] = s.x[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < NZL; ++k) {
+      const int j = lane + 32 * k;
+      if (j < M) s.y[k] = (Einv[j] * io.y0[(size_t)b * M + j]) * c;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < NZL; ++k) {
+      const int j = lane + 32 * k;
+      if (j < M) s.z[k] = ell_dot(I32 + H->i_ellA + 3 * k, F64, U16, w, lane);
+    }
+    __syncwarp();
+  }
+
+  int status = ST_UNSOLVED;
+  int it = 0;
+  double rho_new = rho_in;
+  bool handoff = type_mismatch;     // a constraint changed type: this instance needs its own KKT factor
+
+  // ---- residuals + norms of the current iterate (update_info, auxil.c:564-629)
+  auto update_info = [&]() {
+#pragma unroll
+    for (int k = 0; k < NXL; ++k) { const int i = lane + 32 * k; if (i < N) w[i] = s.x[k]; }
+#pragma unroll
+    for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) w[N + j] = s.y[k]; }
+    __syncwarp();
+    double m_rp = 0, m_z = 0, m_Ax = 0, ms_rp = 0, ms_z = 0, ms_Ax = 0;
+#pragma unroll
+    for (int k = 0; k < NZL; ++k) {
+      const int j = lane + 32 * k;
+      if (j < M) {
+        const double Ax = ell_dot(I32 + H->i_ellA + 3 * k, F64, U16, w, lane);
+        const double rp = Ax - s.z[k];
+        const double e = unscale ? Einv[j] : 1.0;
+        m_rp = fmax(m_rp, fabs(e * rp)); m_z = fmax(m_z, fabs(e * s.z[k])); m_Ax = fmax(m_Ax, fabs(e * Ax));
+        ms_rp = fmax(ms_rp, fabs(rp)); ms_z = fmax(ms_z, fabs(s.z[k])); ms_Ax = fmax(ms_Ax, fabs(Ax));
+      }
+    }
+    double m_rd = 0, m_q = 0, m_Aty = 0, m_Px = 0, ms_rd = 0, ms_q = 0, ms_Aty = 0, ms_Px = 0, a_xPx = 0, a_qx = 0;
+#pragma unroll
+    for (int k = 0; k < NXL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < N) {
+        const double Px = ell_dot(I32 + H->i_ellP + 3 * k, F64, U16, w, lane);
+        const double Aty = (M > 0) ? ell_dot(I32 + H->i_ellAt + 3 * k, F64, U16, w, lane) : 0.0;
+        const double rd = s.q[k] + Px + Aty;
+        const double d = unscale ? Dinv[i] : 1.0;
+        m_rd = fmax(m_rd, fabs(d * rd)); m_q = fmax(m_q, fabs(d * s.q[k]));
+        m_Aty = fmax(m_Aty, fabs(d * Aty)); m_Px = fmax(m_Px, fabs(d * Px));
+        ms_rd = fmax(ms_rd, fabs(rd)); ms_q = fmax(ms_q, fabs(s.q[k]));
+        ms_Aty = fmax(ms_Aty, fabs(Aty)); ms_Px = fmax(ms_Px, fabs(Px));
+        a_xPx = fma(s.x[k], Px, a_xPx); a_qx = fma(s.q[k], s.x[k], a_qx);
+      }
+    }
+    __syncwarp();
+    const double cs = unscale ? cinv : 1.0;
+    s.pri_res = (M > 0) ? warp_max(m_rp) : 0.0;
+    s.nrm_z = warp_max(m_z); s.nrm_Ax = warp_max(m_Ax);
+    s.dua_res = cs * warp_max(m_rd);
+    s.nrm_q = warp_max(m_q); s.nrm_Aty = warp_max(m_Aty); s.nrm_Px = warp_max(m_Px);
+    s.s_rp = warp_max(ms_rp); s.s_z = warp_max(ms_z); s.s_Ax = warp_max(ms_Ax);
+    s.s_rd = warp_max(ms_rd); s.s_q = warp_max(ms_q); s.s_Aty = warp_max(ms_Aty); s.s_Px = warp_max(ms_Px);
+    s.xPx = warp_sum(a_xPx); s.qx = warp_sum(a_qx);
+  };
+
+  // ---- check_termination (auxil.c:681-786); returns the new status (ST_UNSOLVED = continue)
+  auto check_termination = [&](bool approximate) -> int {
+    double ea = st.eps_abs, er = st.eps_rel, epi = st.eps_prim_inf, edi = st.eps_dual_inf;
+    if (approximate) { ea *= 10; er *= 10; epi *= 10; edi *= 10; }
+    if (s.pri_res > OSQP_INFTY || s.dua_res > OSQP_INFTY) return ST_NONCVX;
+    const double cs = unscale ? cinv : 1.0;
+    bool prim_ok, prim_inf = false, dual_inf = false;
+    if (M == 0) prim_ok = true;
+    else {
+      const double eps_prim = ea + er * fmax(s.nrm_z, s.nrm_Ax);
+      prim_ok = s.pri_res < eps_prim;
+      if (!prim_ok) {               // is_primal_infeasible, auxil.c:361-424
+        double dproj[I::NZLs];
+        double nd = 0, lhs = 0;
+#pragma unroll
+        for (int k = 0; k < NZL; ++k) {
+          const int j = lane + 32 * k;
+          double d = s.dy[k];
+          const bool up_inf = s.u[k] > OSQP_INFTY * MIN_SCALING, lo_inf = s.l[k] < -OSQP_INFTY * MIN_SCALING;
+          if (up_inf) d = lo_inf ? 0.0 : fmin(d, 0.0);
+          else if (lo_inf) d = fmax(d, 0.0);
+          if (j >= M) d = 0.0;
+          dproj[k] = d;
+          nd = fmax(nd, fabs((unscale && j < M) ? Ev[j] * d : d));
+          lhs += s.u[k] * fmax(d, 0.0) + s.l[k] * fmin(d, 0.0);
+        }
+        nd = warp_max(nd);
+        if (nd > DIVISION_TOL) {
+          lhs = warp_sum(lhs);
+          if (lhs < epi * nd) {
+#pragma unroll
+            for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) w[N + j] = dproj[k]; }
+            __syncwarp();
+            double mx = 0;
+#pragma unroll
+            for (int k = 0; k < NXL; ++k) {
+              const int i = lane + 32 * k;
+              if (i < N) {
+                double v = ell_dot(I32 + H->i_ellAt + 3 * k, F64, U16, w, lane);
+                if (unscale) v *= Dinv[i];
+                mx = fmax(mx, fabs(v));
+              }
+            }
+            __syncwarp();
+            prim_inf = warp_max(mx) < epi * nd;
+          }
+        }
+      }
+    }
+    const double eps_dual = ea + er * cs * fmax(fmax(s.nrm_q, s.nrm_Aty), s.nrm_Px);
+    const bool dual_ok = s.dua_res < eps_dual;
+    if (!dual_ok) {                 // is_dual_infeasible, auxil.c:426-512
+      double nd = 0, qd = 0;
+#pragma unroll
+      for (int k = 0; k < NXL; ++k) {
+        const int i = lane + 32 * k;
+        if (i < N) { nd = fmax(nd, fabs(unscale ? Dv[i] * s.dx[k] : s.dx[k])); qd = fma(s.q[k], s.dx[k], qd); }
+      }
+      nd = warp_max(nd);
+      const double cost_scaling = unscale ? c : 1.0;
+      if (nd > DIVISION_TOL) {
+        qd = warp_sum(qd);
+        if (qd < cost_scaling * edi * nd) {
+#pragma unroll
+          for (int k = 0; k < NXL; ++k) { const int i = lane + 32 * k; if (i < N) w[i] = s.dx[k]; }
+          __syncwarp();
+          double mx = 0;
+#pragma unroll
+          for (int k = 0; k < NXL; ++k) {
+            const int i = lane + 32 * k;
+            if (i < N) {
+              double v = ell_dot(I32 + H->i_ellP + 3 * k, F64, U16, w, lane);
+              if (unscale) v *= Dinv[i];
+              mx = fmax(mx, fabs(v));
+            }
+          }
+          if (warp_max(mx) < cost_scaling * edi * nd) {
+            bool bad = false;
+#pragma unroll
+            for (int k = 0; k < NZL; ++k) {
+              const int j = lane + 32 * k;
+              if (j < M) {
+                double v = ell_dot(I32 + H->i_ellA + 3 * k, F64, U16, w, lane);
+                if (unscale) v *= Einv[j];
+                bad |= ((s.u[k] < OSQP_INFTY * MIN_SCALING) && (v > edi * nd)) ||
+                       ((s.l[k] > -OSQP_INFTY * MIN_SCALING) && (v < -edi * nd));
+              }
+            }
+            dual_inf = !__any_sync(FULL, bad);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (prim_ok && dual_ok) return approximate ? ST_SOLVED_INACC : ST_SOLVED;
+    if (prim_inf) return approximate ? ST_PINF_INACC : ST_PINF;
+    if (dual_inf) return approximate ? ST_DINF_INACC : ST_DINF;
+    return ST_UNSOLVED;
+  };
+
+  // ---- main ADMM loop (osqp.c:354-527)
+  if (!handoff) {
+    for (it = 1; it <= st.max_iter; ++it) {
+      // compute_rhs (auxil.c:161-175), written straight into pivot order
+#pragma unroll
+      for (int k = 0; k < NXL; ++k) { const int i = lane + 32 * k; if (i < N) w[px[k]] = sigma * s.x[k] - s.q[k]; }
+#pragma unroll
+      for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) w[pz[k]] = s.z[k] - rinv_of(k) * s.y[k]; }
+      __syncwarp();
+      kkt_solve<Fam::TRAIL>(H, I32, F64, U16, w, lane);
+      // update_x, update_z (+project), update_y (auxil.c:185-225)
+#pragma unroll
+      for (int k = 0; k < NXL; ++k) {
+        const int i = lane + 32 * k;
+        if (i < N) {
+          const double xn = alpha * w[px[k]] + (1.0 - alpha) * s.x[k];
+          s.dx[k] = xn - s.x[k];
+          s.x[k] = xn;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NZL; ++k) {
+        const int j = lane + 32 * k;
+        if (j < M) {
+          const double ri = rinv_of(k);
+          const double zt = (s.z[k] - ri * s.y[k]) + ri * w[pz[k]];     // z~ = rhs_z + rho^-1 nu (qdldl_interface.c:368-370)
+          const double v = alpha * zt + (1.0 - alpha) * s.z[k];
+          const double zn = fmin(fmax(v + ri * s.y[k], s.l[k]), s.u[k]);
+          const double r = ((s.loosemask >> k) & 1u) ? RHO_MIN : (((s.eqmask >> k) & 1u) ? rho_eq : rho_in);
+          s.dy[k] = r * (v - zn);
+          s.y[k] += s.dy[k];
+          s.z[k] = zn;
+        }
+      }
+      __syncwarp();
+      const bool can_check = st.check_termination && (it % st.check_termination == 0);
+      const bool can_adapt = st.adaptive_rho && st.adaptive_rho_interval && (it % st.adaptive_rho_interval == 0);
+      if (can_check || can_adapt || it == st.max_iter) {
+        update_info();
+        if (can_check || it == st.max_iter) {
+          status = check_termination(false);
+          if (status != ST_UNSOLVED) break;
+        }
+        if (can_adapt) {            // compute_rho_estimate + adapt_rho decision (auxil.c:13-74)
+          const double pn = s.s_rp / (fmax(s.s_z, s.s_Ax) + DIVISION_TOL);
+          const double dn = s.s_rd / (fmax(fmax(s.s_q, s.s_Aty), s.s_Px) + DIVISION_TOL);
+          double r = rho_in * sqrt(pn / dn);
+          r = fmin(fmax(r, RHO_MIN), RHO_MAX);
+          if (r > rho_in * st.adaptive_rho_tolerance || r < rho_in / st.adaptive_rho_tolerance) {
+            rho_new = r; handoff = true; break;   // needs a per-instance refactorisation: tail kernel
+          }
+        }
+      }
+    }
+    if (it > st.max_iter) it = st.max_iter;
+    if (!handoff && status == ST_UNSOLVED) {      // osqp.c:563-568
+      status = check_termination(true);
+      if (status == ST_UNSOLVED) status = ST_MAXITER;
+    }
+  }
+
+  if (handoff) {
+    int slot = -1;
+    if (lane == 0) slot = atomicAdd(io.tail_count, 1);
+    slot = __shfl_sync(FULL, slot, 0);
+    if (lane == 0) { io.status[b] = ST_HANDOFF; io.iter[b] = it; }
+    if (slot < io.tail_capacity) {
+      double* ts = io.tail_state + (size_t)slot * (N + 2 * M + 2);
+#pragma unroll
+      for (int k = 0; k < NXL; ++k) { const int i = lane + 32 * k; if (i < N) ts[i] = s.x[k]; }
+#pragma unroll
+      for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) { ts[N + j] = s.z[k]; ts[N + M + j] = s.y[k]; } }
+      if (lane == 0) { ts[N + 2 * M] = rho_new; ts[N + 2 * M + 1] = (double)it; io.tail_ids[slot] = b; }
+    }
+    return;
+  }
+
+  // ---- store_solution / unscale_solution (auxil.c:524-562, scaling.c:177-192) + retrieval (a11, a12)
+  const bool has_sol = !(status == ST_PINF || status == ST_PINF_INACC || status == ST_DINF ||
+                         status == ST_DINF_INACC || status == ST_NONCVX);
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+  for (int k = 0; k < NXL; ++k) {
+    const int i = lane + 32 * k;
+    if (i < N) {
+      const double xv = has_sol ? Dv[i] * s.x[k] : qnan;
+      w[i] = xv;
+      if (io.sol_x) io.sol_x[(size_t)b * N + i] = xv;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NZL; ++k) {
+    const int j = lane + 32 * k;
+    if (j < M) {
+      const double yv = has_sol ? (Ev[j] * s.y[k]) * cinv : qnan;
+      w[N + j] = yv;
+      if (io.sol_y) io.sol_y[(size_t)b * M + j] = yv;
+    }
+  }
+  __syncwarp();
+  if (io.prim) {
+    const int np = H->n_prim;
+    for (int k = lane; k < np; k += LANES) io.prim[(size_t)b * np + k] = w[U16[H->h_prim + k]];
+  }
+  if (io.dual) {
+    const int nd = H->n_dual;
+    for (int k = lane; k < nd; k += LANES) io.dual[(size_t)b * nd + k] = w[N + U16[H->h_dual + k]];
+  }
+  __syncwarp();
+  if (lane == 0) {
+    double obj = (0.5 * s.xPx + s.qx);                          // compute_obj_val, auxil.c:227-238
+    if (st.scaling) obj *= cinv;
+    if (status == ST_PINF || status == ST_PINF_INACC) obj = OSQP_INFTY;
+    else if (status == ST_DINF || status == ST_DINF_INACC) obj = -OSQP_INFTY;
+    else if (status == ST_NONCVX) obj = qnan;
+    else obj = (H->is_max ? -1.0 : 1.0) * (obj + H->d_const);   // cpg_retrieve_info, cvxpygen/utils.py:980
+    io.obj_val[b] = obj; io.iter[b] = it; io.status[b] = status;
+    io.pri_res[b] = s.pri_res; io.dua_res[b] = s.dua_res;
+  }
+}
+
+// ---------------------------------------------------------------- persistent kernel
+template <class Fam>
+__global__ void __launch_bounds__(Fam::WARPS * 32, 1)
+admm_batch_kernel(const uint8_t* __restrict__ blob_g, const BatchIO io, const Settings st) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t total = reinterpret_cast<const CpgBlobHeader*>(blob_g)->total_bytes;
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {                      // stage the constants blob with TMA bulk copies
+    mbar_expect_tx(&bar, total);
+    constexpr uint32_t CHUNK = 32768;
+    for (uint32_t off = 0; off < total; off += CHUNK)
+      tma_bulk_g2s(smem + off, blob_g + off, (total - off < CHUNK) ? (total - off) : CHUNK, &bar);
+  }
+  mbar_wait(&bar, 0);
+  const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(smem);
+  const int* I32 = reinterpret_cast<const int*>(smem + H->off_i32);
+  const double* F64 = reinterpret_cast<const double*>(smem + H->off_f64);
+  const uint16_t* U16 = reinterpret_cast<const uint16_t*>(smem + H->off_u16);
+  double* w = reinterpret_cast<double*>(smem + Fam::BLOB_BYTES_PAD) + (size_t)warp * Fam::W_STRIDE;
+  for (;;) {
+    unsigned b = 0;
+    if (lane == 0) b = atomicAdd(io.work_counter, 1u);
+    b = __shfl_sync(FULL, b, 0);
+    if (b >= (unsigned)io.B) break;
+    solve_instance<Fam>(H, I32, F64, U16, w, lane, (int)b, io, st);
+    __syncwarp();
+  }
+}
+
+}  // namespace cpgb200

@@ -1,0 +1,232 @@
+// cpg_b200_module.cu -- C-ABI runtime of one generated ADMM-CUDA solver library.
+// Compiled once per problem family together with the generated cpg_family.h (compile-time sizes),
+// cpg_blob_layout.h (blob header struct) and cpg_blob.c (the constants blob).
+// Implements include/cpg_b200.h; see that header for the reference interfaces it stands beside.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "cpg_family.h"
+#include "cpg_b200.h"
+#include "cpg_blob_layout.h"
+#include "admm_kernel.cuh"
+
+extern "C" const unsigned long long CPG_B200_FN(cpg_blob_words)[];
+extern "C" const unsigned int CPG_B200_FN(cpg_blob_nbytes);
+
+namespace {
+
+struct Fam {
+  static constexpr int N = CPG_FAM_N, M = CPG_FAM_M;
+  static constexpr int TRAIL = CPG_FAM_TRAIL_TILES;
+  static constexpr int WARPS = CPG_FAM_WARPS;
+  static constexpr int BLOB_BYTES_PAD = CPG_FAM_BLOB_BYTES_PAD;
+  static constexpr int W_STRIDE = CPG_FAM_W_STRIDE;       // doubles per warp work vector
+};
+constexpr int SMEM_BYTES = Fam::BLOB_BYTES_PAD + Fam::WARPS * Fam::W_STRIDE * 8;
+constexpr int TAIL_WORDS = Fam::N + 2 * Fam::M + 2;
+
+struct Ctx {
+  bool ready = false;
+  int device = -1, n_sm = 0;
+  uint8_t* d_blob = nullptr;
+  unsigned int* d_counter = nullptr;
+  int* d_tail_count = nullptr;
+  int* d_tail_ids = nullptr;
+  double* d_tail_state = nullptr;
+  int tail_cap = 0;
+  // staging for the host-buffer entry point
+  int cap_B = 0;
+  double *d_params = nullptr, *d_x0 = nullptr, *d_y0 = nullptr, *d_prim = nullptr, *d_dual = nullptr;
+  double *d_solx = nullptr, *d_soly = nullptr, *d_obj = nullptr, *d_pri = nullptr, *d_dua = nullptr;
+  int *d_iter = nullptr, *d_status = nullptr;
+  int launches = 0;
+  char err[256] = {0};
+} g;
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      snprintf(g.err, sizeof(g.err), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return CPG_B200_ERR_CUDA;                                                                   \
+    }                                                                                             \
+  } while (0)
+
+int ensure_tail(int B) {
+  if (B <= g.tail_cap) return CPG_B200_OK;
+  if (g.d_tail_ids) cudaFree(g.d_tail_ids);
+  if (g.d_tail_state) cudaFree(g.d_tail_state);
+  g.d_tail_ids = nullptr; g.d_tail_state = nullptr; g.tail_cap = 0;
+  CK(cudaMalloc(&g.d_tail_ids, sizeof(int) * (size_t)B));
+  CK(cudaMalloc(&g.d_tail_state, sizeof(double) * (size_t)B * TAIL_WORDS));
+  g.tail_cap = B;
+  return CPG_B200_OK;
+}
+
+template <class T>
+int grow(T** p, size_t count) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  CK(cudaMalloc(p, sizeof(T) * count));
+  return CPG_B200_OK;
+}
+
+int ensure_staging(int B) {
+  if (B <= g.cap_B) return CPG_B200_OK;
+  int rc;
+  const int np = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words))->npb;
+  const int npr = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words))->n_prim;
+  const int ndu = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words))->n_dual;
+  if ((rc = grow(&g.d_params, (size_t)B * (np > 0 ? np : 1)))) return rc;
+  if ((rc = grow(&g.d_x0, (size_t)B * Fam::N))) return rc;
+  if ((rc = grow(&g.d_y0, (size_t)B * (Fam::M > 0 ? Fam::M : 1)))) return rc;
+  if ((rc = grow(&g.d_prim, (size_t)B * (npr > 0 ? npr : 1)))) return rc;
+  if ((rc = grow(&g.d_dual, (size_t)B * (ndu > 0 ? ndu : 1)))) return rc;
+  if ((rc = grow(&g.d_solx, (size_t)B * Fam::N))) return rc;
+  if ((rc = grow(&g.d_soly, (size_t)B * (Fam::M > 0 ? Fam::M : 1)))) return rc;
+  if ((rc = grow(&g.d_obj, (size_t)B))) return rc;
+  if ((rc = grow(&g.d_pri, (size_t)B))) return rc;
+  if ((rc = grow(&g.d_dua, (size_t)B))) return rc;
+  if ((rc = grow(&g.d_iter, (size_t)B))) return rc;
+  if ((rc = grow(&g.d_status, (size_t)B))) return rc;
+  g.cap_B = B;
+  return CPG_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* CPG_B200_FN(cpg_b200_last_error)(void) { return g.err; }
+int CPG_B200_FN(cpg_b200_launch_count)(void) { return g.launches; }
+
+void CPG_B200_FN(cpg_b200_default_settings)(CpgB200Settings* s) {
+  if (!s) return;
+  s->max_iter = 4000; s->check_termination = 25; s->scaled_termination = 0; s->warm_start = 0;
+  s->adaptive_rho = 1; s->adaptive_rho_interval = 0; s->scaling = CPG_FAM_SCALING; s->pad_ = 0;
+  s->eps_abs = 1e-3; s->eps_rel = 1e-3; s->eps_prim_inf = 1e-4; s->eps_dual_inf = 1e-4;
+  s->alpha = 1.6; s->adaptive_rho_tolerance = 5.0;
+}
+
+int CPG_B200_FN(cpg_b200_dims)(CpgB200Dims* out) {
+  if (!out) return CPG_B200_ERR_BAD_ARG;
+  const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words));
+  out->n_var = H->n; out->n_con = H->m; out->n_param = H->npb; out->n_prim = H->n_prim; out->n_dual = H->n_dual;
+  out->blob_bytes = H->total_bytes; out->warps_per_cta = Fam::WARPS; out->smem_bytes = SMEM_BYTES;
+  return CPG_B200_OK;
+}
+
+int CPG_B200_FN(cpg_b200_load_constants)(const void* blob, int nbytes) {
+  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+  if (!blob || nbytes <= 0 || nbytes > Fam::BLOB_BYTES_PAD) return CPG_B200_ERR_BAD_ARG;
+  const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(blob);
+  if (H->n != Fam::N || H->m != Fam::M || (int)H->total_bytes != nbytes || H->n_trail_tiles > Fam::TRAIL)
+    return CPG_B200_ERR_BAD_ARG;
+  CK(cudaMemcpy(g.d_blob, blob, nbytes, cudaMemcpyHostToDevice));
+  return CPG_B200_OK;
+}
+
+int CPG_B200_FN(cpg_b200_init)(int device) {
+  g.err[0] = 0;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    snprintf(g.err, sizeof(g.err), "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return CPG_B200_ERR_CUDA;
+  }
+  g.device = device; g.n_sm = prop.multiProcessorCount;
+  if (!g.d_blob) CK(cudaMalloc(&g.d_blob, Fam::BLOB_BYTES_PAD));
+  CK(cudaMemcpy(g.d_blob, CPG_B200_FN(cpg_blob_words), CPG_B200_FN(cpg_blob_nbytes), cudaMemcpyHostToDevice));
+  if (!g.d_counter) CK(cudaMalloc(&g.d_counter, sizeof(unsigned int)));
+  if (!g.d_tail_count) CK(cudaMalloc(&g.d_tail_count, sizeof(int)));
+  CK(cudaFuncSetAttribute(cpgb200::admm_batch_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  g.ready = true;
+  return CPG_B200_OK;
+}
+
+int CPG_B200_FN(cpg_b200_free)(void) {
+  void* ptrs[] = {g.d_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0,
+                  g.d_prim, g.d_dual, g.d_solx, g.d_soly, g.d_obj, g.d_pri, g.d_dua, g.d_iter, g.d_status};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  g = Ctx();
+  return CPG_B200_OK;
+}
+
+int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const double* x0, const double* y0,
+                                        double* prim, double* dual, double* sol_x, double* sol_y,
+                                        double* obj_val, int* iter, int* status, double* pri_res, double* dua_res,
+                                        const CpgB200Settings* settings, void* stream_) {
+  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+  if (B < 0 || !obj_val || !iter || !status || !pri_res || !dua_res) return CPG_B200_ERR_BAD_ARG;
+  g.launches = 0;
+  if (B == 0) return CPG_B200_OK;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CpgB200Settings s;
+  if (settings) s = *settings; else CPG_B200_FN(cpg_b200_default_settings)(&s);
+  int rc = ensure_tail(B);
+  if (rc) return rc;
+  cpgb200::Settings st;
+  st.max_iter = s.max_iter; st.check_termination = s.check_termination; st.scaled_termination = s.scaled_termination;
+  st.warm_start = s.warm_start && x0 && y0; st.adaptive_rho = s.adaptive_rho;
+  st.adaptive_rho_interval = s.adaptive_rho_interval;
+  if (st.adaptive_rho && !st.adaptive_rho_interval)        // osqp.c:267-279 (no profiling timer)
+    st.adaptive_rho_interval = s.check_termination ? 4 * s.check_termination : 100;
+  st.scaling = CPG_FAM_SCALING; st.pad = 0;
+  st.eps_abs = s.eps_abs; st.eps_rel = s.eps_rel; st.eps_prim_inf = s.eps_prim_inf; st.eps_dual_inf = s.eps_dual_inf;
+  st.alpha = s.alpha; st.adaptive_rho_tolerance = s.adaptive_rho_tolerance;
+  cpgb200::BatchIO io;
+  io.params = params; io.x0 = x0; io.y0 = y0; io.prim = prim; io.dual = dual; io.sol_x = sol_x; io.sol_y = sol_y;
+  io.obj_val = obj_val; io.iter = iter; io.status = status; io.pri_res = pri_res; io.dua_res = dua_res;
+  io.work_counter = g.d_counter; io.tail_count = g.d_tail_count; io.tail_ids = g.d_tail_ids;
+  io.tail_state = g.d_tail_state; io.B = B; io.tail_capacity = g.tail_cap;
+  CK(cudaMemsetAsync(g.d_counter, 0, sizeof(unsigned int), stream));
+  CK(cudaMemsetAsync(g.d_tail_count, 0, sizeof(int), stream));
+  int grid = g.n_sm;
+  const int need = (B + Fam::WARPS - 1) / Fam::WARPS;
+  if (grid > need) grid = need;
+  cpgb200::admm_batch_kernel<Fam><<<grid, Fam::WARPS * 32, SMEM_BYTES, stream>>>(g.d_blob, io, st);
+  g.launches += 1;
+  CK(cudaGetLastError());
+  return CPG_B200_OK;
+}
+
+int CPG_B200_FN(cpg_solve_batch_host)(int B, const double* params, const double* x0, const double* y0,
+                                      double* prim, double* dual, double* sol_x, double* sol_y,
+                                      double* obj_val, int* iter, int* status, double* pri_res, double* dua_res,
+                                      const CpgB200Settings* settings) {
+  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+  if (B < 0 || !obj_val || !iter || !status || !pri_res || !dua_res) return CPG_B200_ERR_BAD_ARG;
+  if (B == 0) { g.launches = 0; return CPG_B200_OK; }
+  const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words));
+  if (H->npb > 0 && !params) return CPG_B200_ERR_BAD_ARG;
+  int rc = ensure_staging(B);
+  if (rc) return rc;
+  cudaStream_t st = 0;
+  if (H->npb > 0) CK(cudaMemcpyAsync(g.d_params, params, sizeof(double) * (size_t)B * H->npb, cudaMemcpyHostToDevice, st));
+  const bool warm = x0 && y0;
+  if (warm) {
+    CK(cudaMemcpyAsync(g.d_x0, x0, sizeof(double) * (size_t)B * Fam::N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(g.d_y0, y0, sizeof(double) * (size_t)B * Fam::M, cudaMemcpyHostToDevice, st));
+  }
+  rc = CPG_B200_FN(cpg_solve_batch_device)(B, g.d_params, warm ? g.d_x0 : nullptr, warm ? g.d_y0 : nullptr,
+                                           prim ? g.d_prim : nullptr, dual ? g.d_dual : nullptr,
+                                           sol_x ? g.d_solx : nullptr, sol_y ? g.d_soly : nullptr,
+                                           g.d_obj, g.d_iter, g.d_status, g.d_pri, g.d_dua, settings, st);
+  if (rc) return rc;
+  if (prim) CK(cudaMemcpyAsync(prim, g.d_prim, sizeof(double) * (size_t)B * H->n_prim, cudaMemcpyDeviceToHost, st));
+  if (dual) CK(cudaMemcpyAsync(dual, g.d_dual, sizeof(double) * (size_t)B * H->n_dual, cudaMemcpyDeviceToHost, st));
+  if (sol_x) CK(cudaMemcpyAsync(sol_x, g.d_solx, sizeof(double) * (size_t)B * Fam::N, cudaMemcpyDeviceToHost, st));
+  if (sol_y) CK(cudaMemcpyAsync(sol_y, g.d_soly, sizeof(double) * (size_t)B * Fam::M, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(obj_val, g.d_obj, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(pri_res, g.d_pri, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(dua_res, g.d_dua, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(iter, g.d_iter, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(status, g.d_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return CPG_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+"""Constants blob of one ADMM-CUDA problem family.
+
+Everything a CTA needs besides the per-instance parameters is packed offline into ONE
+contiguous, 16-byte aligned byte string which the kernel stages global -> shared with
+TMA bulk copies (cp.async.bulk) once per CTA.  This is the role `workspace.c` plays for
+the reference's embedded OSQP (data, scaling, L, Dinv, P, rho_inv_vec, ... --
+osqp-python/module/codegen/utils.py:66-254 as listed in SURVEY Appendix A), re-laid-out
+for a warp: lane-interleaved ELL tiles instead of CSC columns.
+
+Layout:  [ header | int32 area | float64 area | uint16 area ]
+The header field list below is the single source of truth; `header_struct_c()` emits the
+matching C struct into the generated code, so host packer and kernel cannot drift apart.
+"""
+import struct
+from typing import Dict, List, Tuple
+
+import numpy as np
+import scipy.sparse as sp
+
+MAGIC = 0x42323030   # 'B200'
+LANES = 32
+
+# (ctype, name) -- ints first, then doubles; total kept a multiple of 16 bytes
+HEADER_FIELDS: List[Tuple[str, str]] = [
+    ('int', 'magic'), ('int', 'total_bytes'), ('int', 'n'), ('int', 'm'),
+    ('int', 'nk'), ('int', 'npb'), ('int', 'n_prim'), ('int', 'n_dual'),
+    ('int', 'n_tiles'), ('int', 'n_fwd_tiles'), ('int', 'n_trail_tiles'), ('int', 'is_max'),
+    ('int', 'off_i32'), ('int', 'off_f64'), ('int', 'off_u16'), ('int', 'n_theta_shared'),
+    # int32-area indices
+    ('int', 'i_tiles'), ('int', 'i_ellA'), ('int', 'i_ellAt'), ('int', 'i_ellP'),
+    ('int', 'i_ellMq'), ('int', 'i_ellMl'), ('int', 'i_ellMu'), ('int', 'pad_i0'),
+    # float64-area indices (in doubles)
+    ('int', 'f_D'), ('int', 'f_Dinv'), ('int', 'f_E'), ('int', 'f_Einv'),
+    ('int', 'f_qbase'), ('int', 'f_lbase'), ('int', 'f_ubase'), ('int', 'pad_f0'),
+    # uint16-area indices
+    ('int', 'h_pinvx'), ('int', 'h_pinvz'), ('int', 'h_ctype'), ('int', 'h_prim'),
+    ('int', 'h_dual'), ('int', 'pad_h0'), ('int', 'pad_h1'), ('int', 'pad_h2'),
+    ('double', 'sigma'), ('double', 'rho'), ('double', 'c'), ('double', 'cinv'),
+    ('double', 'd_const'), ('double', 'reserved0'),
+]
+
+
+def header_struct_c(name='CpgBlobHeader') -> str:
+    lines = [f'struct {name} {{']
+    for t, n in HEADER_FIELDS:
+        lines.append(f'  {t} {n};')
+    lines.append('};')
+    return '\n'.join(lines) + '\n'
+
+
+def _pack_header(vals: Dict[str, float]) -> bytes:
+    fmt = '<' + ''.join('i' if t == 'int' else 'd' for t, _ in HEADER_FIELDS)
+    data = struct.pack(fmt, *[(int(vals.get(n, 0)) if t == 'int' else float(vals.get(n, 0.0))) for t, n in HEADER_FIELDS])
+    assert len(data) % 16 == 0, len(data)
+    return data
+
+
+class _Areas:
+    def __init__(self):
+        self.i32: List[int] = []
+        self.f64: List[float] = []
+        self.u16: List[int] = []
+
+    def add_i32(self, arr) -> int:
+        off = len(self.i32); self.i32.extend(int(v) for v in np.asarray(arr).ravel()); return off
+
+    def add_f64(self, arr) -> int:
+        off = len(self.f64); self.f64.extend(float(v) for v in np.asarray(arr, dtype=float).ravel()); return off
+
+    def add_u16(self, arr) -> int:
+        a = np.asarray(arr).ravel()
+        assert a.size == 0 or (a.min() >= 0 and a.max() < 65536)
+        off = len(self.u16); self.u16.extend(int(v) for v in a); return off
+
+
+def ell_row_blocks(Mcsr: sp.csr_matrix, n_rows: int):
+    """Row-blocked ELL of a CSR matrix: block rb holds rows 32*rb .. 32*rb+31 (row = lane + 32*rb),
+    K_rb = longest row in the block; entry k of a row sits at [k*32 + lane].
+    Returns list of (K, vals(K,32), cols(K,32))."""
+    Mcsr = sp.csr_matrix(Mcsr); Mcsr.sort_indices()
+    blocks = []
+    for r0 in range(0, n_rows, LANES):
+        rows = range(r0, min(r0 + LANES, n_rows))
+        lens = [Mcsr.indptr[r + 1] - Mcsr.indptr[r] for r in rows]
+        K = max(lens) if lens else 0
+        vals = np.zeros((K, LANES)); cols = np.zeros((K, LANES), dtype=np.int64)
+        for lane, r in enumerate(rows):
+            s, e = Mcsr.indptr[r], Mcsr.indptr[r + 1]
+            vals[:e - s, lane] = Mcsr.data[s:e]
+            cols[:e - s, lane] = Mcsr.indices[s:e]
+        blocks.append((K, vals, cols))
+    return blocks
+
+
+def _add_ell(ar: _Areas, blocks) -> int:
+    """int32 table: per block [K, f64 offset, u16 offset]; returns table index."""
+    table = []
+    for K, vals, cols in blocks:
+        table += [K, ar.add_f64(vals), ar.add_u16(cols)]
+    return ar.add_i32(table) if table else ar.add_i32([0, 0, 0])
+
+
+def pack_blob(*, n, m, perm, schedule, Ps_upper, As, D, E, c, sigma, rho, ctype,
+              q_base, l_base, u_base, Mq_b, Ml_b, Mu_b, npb, prim_idx, dual_idx,
+              d_const, is_max) -> bytes:
+    """All vectors are in natural (unpermuted) canonical order.  q/l/u_base are the UNSCALED
+    canonical vectors with the batched parameters set to zero (shared parameters and constants
+    folded in); M*_b are the CSR maps restricted to the batched-parameter columns."""
+    nk = n + m
+    ar = _Areas()
+    pinv = np.empty(nk, dtype=np.int64); pinv[np.asarray(perm)] = np.arange(nk)
+    # --- tiles
+    tile_tab = []
+    for t in schedule.tiles:
+        f = ar.add_f64(t.vals)
+        h = ar.add_u16(t.cols)
+        hr = ar.add_u16(np.concatenate([t.rows, np.zeros(LANES - len(t.rows), dtype=np.uint16)]))
+        tile_tab += [f, h, t.K, t.r_pad, len(t.rows), hr, 0, 0]
+    i_tiles = ar.add_i32(tile_tab)
+    # --- residual operators (scaled data): A (rows), A' (rows = variables), full symmetric P
+    As = sp.csr_matrix(As)
+    Pfull = sp.csr_matrix(Ps_upper + sp.triu(Ps_upper, 1).T)
+    i_A = _add_ell(ar, ell_row_blocks(As, m))
+    # A' gathers y from w[n + j]
+    At = sp.csr_matrix(As.T)
+    At_blocks = [(K, v, cidx + n) for K, v, cidx in ell_row_blocks(At, n)]
+    i_At = _add_ell(ar, At_blocks)
+    i_P = _add_ell(ar, ell_row_blocks(Pfull, n))
+    i_Mq = _add_ell(ar, ell_row_blocks(Mq_b, n))
+    i_Ml = _add_ell(ar, ell_row_blocks(Ml_b, m))
+    i_Mu = _add_ell(ar, ell_row_blocks(Mu_b, m))
+    hv = dict(magic=MAGIC, n=n, m=m, nk=nk, npb=npb, n_prim=len(prim_idx), n_dual=len(dual_idx),
+              n_tiles=len(schedule.tiles), n_fwd_tiles=schedule.n_fwd_tiles,
+              n_trail_tiles=schedule.n_trailing_tiles, is_max=int(is_max),
+              i_tiles=i_tiles, i_ellA=i_A, i_ellAt=i_At, i_ellP=i_P, i_ellMq=i_Mq, i_ellMl=i_Ml, i_ellMu=i_Mu,
+              f_D=ar.add_f64(D), f_Dinv=ar.add_f64(1.0 / np.asarray(D)), f_E=ar.add_f64(E),
+              f_Einv=ar.add_f64(1.0 / np.asarray(E)),
+              f_qbase=ar.add_f64(q_base), f_lbase=ar.add_f64(l_base), f_ubase=ar.add_f64(u_base),
+              h_pinvx=ar.add_u16(pinv[:n]), h_pinvz=ar.add_u16(pinv[n:]),
+              h_ctype=ar.add_u16(np.asarray(ctype) + 1),      # stored as 0 loose / 1 ineq / 2 eq
+              h_prim=ar.add_u16(prim_idx), h_dual=ar.add_u16(dual_idx),
+              sigma=sigma, rho=rho, c=c, cinv=1.0 / c, d_const=d_const)
+    hdr_len = len(_pack_header(hv))
+
+    def pad16(b: bytes) -> bytes:
+        return b + b'\0' * ((-len(b)) % 16)
+    i32b = pad16(np.asarray(ar.i32, dtype='<i4').tobytes())
+    f64b = pad16(np.asarray(ar.f64, dtype='<f8').tobytes())
+    u16b = pad16(np.asarray(ar.u16, dtype='<u2').tobytes())
+    hv['off_i32'] = hdr_len
+    hv['off_f64'] = hdr_len + len(i32b)
+    hv['off_u16'] = hv['off_f64'] + len(f64b)
+    hv['total_bytes'] = hv['off_u16'] + len(u16b)
+    blob = _pack_header(hv) + i32b + f64b + u16b
+    assert len(blob) == hv['total_bytes'] and len(blob) % 16 == 0
+    return blob

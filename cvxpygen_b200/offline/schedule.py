@@ -1,0 +1,246 @@
+"""Warp-level schedule for the KKT solve  K x = b  with  P K P' = L D L'.
+
+The reference runs `QDLDL_Lsolve`, a diagonal scale and `QDLDL_Ltsolve`
+(qdldl_sources/src/qdldl.c:236-281) column by column on one core: 2*(n+m)
+dependent steps per ADMM iteration (a6 -- the dominant cost of the hot path).
+One warp per instance cannot afford a dependent step per column, so the factor is
+re-expressed offline as a short sequence of *tiles*, each an independent set of
+sparse dot products executed by the 32 lanes of the warp:
+
+    forward  groups g=[a,b):  w_g <- T^{-1} w_g - (T^{-1} L[g,:a]) w_{:a}        T = I + L[g,g]
+    trailing block  t=[s,n):  w_t <- S^{-1} (w_t - L[t,:s] w_{:s}),  S = L_tt D_tt L_tt'   (optional, dense)
+    backward groups g=[a,b):  w_g <- T^{-T} D_g^{-1} w_g - (T^{-T} L[b:,g]') w_{b:}
+
+A group is a union of consecutive elimination-tree levels.  Where a level is wide
+(leaves of the tree) T = I and this is classic level scheduling; where the tree
+degenerates into a chain (the banded Schur complement of an MPC problem) merging k
+levels -- with the small triangular block inverted explicitly offline -- trades a
+little fill for k-fold fewer dependent steps.  Rows of a group are cut into tiles of
+<= 32 rows; a tile with r <= 16 rows spreads every row over p = 32/r_pad lanes and
+finishes with log2(p) shuffle-adds, so short-and-fat blocks still use the whole warp.
+Group boundaries, and the start s of the trailing dense block, are chosen by dynamic
+programming on a cost model that counts warp-level loop iterations.
+
+Hazard rule that lets the kernel write a tile's rows immediately (no double
+buffering): inside a forward group row i only reads rows j <= i of the group, so
+tiles are emitted in DEcreasing row order; backward groups read j >= i and are
+emitted in INcreasing order.  Within a tile all lanes read before any lane writes.
+Rows whose update is the identity (forward leaves) are dropped.
+"""
+from dataclasses import dataclass, field
+from typing import List, Tuple
+
+import numpy as np
+
+from .kkt import LDLFactor
+
+LANES = 32
+TILE_OVERHEAD = 3.0       # header decode + sync + store, in units of one inner-loop iteration
+REDUCE_COST = 0.75        # one shuffle-add stage
+
+
+def _pad_pow2(r: int) -> int:
+    p = 1
+    while p < r:
+        p *= 2
+    return p
+
+
+@dataclass
+class Tile:
+    rows: np.ndarray      # (nrows,) pivot positions written by lanes 0..nrows-1
+    r_pad: int            # power of two >= nrows; lane -> (row = lane % r_pad, part = lane // r_pad)
+    cols: np.ndarray      # (K, 32) uint16 column positions (padding points at a harmless address, coeff 0)
+    vals: np.ndarray      # (K, 32) float64
+
+    @property
+    def K(self):
+        return self.cols.shape[0]
+
+    @property
+    def parts(self):
+        return LANES // self.r_pad
+
+
+def _tile_cost(nrows: int, kmax: int) -> float:
+    r_pad = _pad_pow2(nrows)
+    p = LANES // r_pad
+    return -(-kmax // p) + REDUCE_COST * np.log2(p) + TILE_OVERHEAD
+
+
+def _group_cost(lens_in_emit_order: np.ndarray) -> float:
+    c = 0.0
+    for t0 in range(0, len(lens_in_emit_order), LANES):
+        sel = lens_in_emit_order[t0:t0 + LANES]
+        c += _tile_cost(len(sel), int(max(1, sel.max())))
+    return c
+
+
+def _make_tiles(rows: np.ndarray, M: np.ndarray, col_pos: np.ndarray, decreasing: bool) -> List[Tile]:
+    """rows: pivot positions (ascending); M: dense operator (len(rows) x len(col_pos))."""
+    idx = np.arange(len(rows))
+    if decreasing:
+        idx = idx[::-1]
+    tiles = []
+    for t0 in range(0, len(idx), LANES):
+        sel = idx[t0:t0 + LANES]
+        nr = len(sel)
+        r_pad = _pad_pow2(nr)
+        p = LANES // r_pad
+        nz = [np.nonzero(M[i])[0] for i in sel]
+        kmax = max(1, max(len(c) for c in nz))
+        K = -(-kmax // p)
+        cols = np.zeros((K, LANES), dtype=np.uint16)
+        vals = np.zeros((K, LANES))
+        for lane in range(LANES):
+            r, part = lane % r_pad, lane // r_pad
+            if r >= nr:
+                cols[:, lane] = rows[sel[0]]
+                continue
+            c = nz[r][part::p]                      # interleave the row's entries over its p lanes
+            cols[:len(c), lane] = col_pos[c]
+            vals[:len(c), lane] = M[sel[r], c]
+            cols[len(c):, lane] = rows[sel[r]]
+        tiles.append(Tile(rows=np.asarray(rows)[sel].astype(np.uint16), r_pad=r_pad, cols=cols, vals=vals))
+    return tiles
+
+
+def _forward_group(F: LDLFactor, a: int, b: int):
+    g = b - a
+    Tinv = np.linalg.solve(np.eye(g) + F.L[a:b, a:b], np.eye(g)) if g > 1 else np.ones((1, 1))
+    Tinv[np.triu_indices(g, 1)] = 0.0
+    M = np.zeros((g, b))
+    M[:, a:b] = Tinv
+    if a:
+        M[:, :a] = -Tinv @ F.L[a:b, :a]
+    ident = np.array([np.count_nonzero(M[i]) == 1 and M[i, a + i] == 1.0 for i in range(g)], dtype=bool)
+    return np.arange(a, b)[~ident], M[~ident], np.arange(0, b)
+
+
+def _backward_group(F: LDLFactor, a: int, b: int):
+    n = F.L.shape[0]
+    g = b - a
+    TinvT = np.linalg.solve((np.eye(g) + F.L[a:b, a:b]).T, np.eye(g)) if g > 1 else np.ones((1, 1))
+    TinvT[np.tril_indices(g, -1)] = 0.0
+    M = np.zeros((g, n - a))
+    M[:, :g] = TinvT / F.D[a:b][None, :]
+    if b < n:
+        M[:, g:] = -TinvT @ F.L[b:, a:b].T
+    return np.arange(a, b), M, np.arange(a, n)
+
+
+def _trailing_block(F: LDLFactor, s: int):
+    n = F.L.shape[0]
+    Ltt = np.eye(n - s) + F.L[s:, s:]
+    Sinv = np.linalg.inv(Ltt @ np.diag(F.D[s:]) @ Ltt.T)
+    Sinv = 0.5 * (Sinv + Sinv.T)
+    M = np.zeros((n - s, n))
+    M[:, s:] = Sinv
+    if s:
+        M[:, :s] = -Sinv @ F.L[s:, :s]      # pull the forward-solved leading part into the block's rhs
+    return np.arange(s, n), M, np.arange(0, n)
+
+
+@dataclass
+class SolveSchedule:
+    tiles: List[Tile]              # in execution order
+    n: int
+    n_fwd_tiles: int = 0
+    n_trailing_tiles: int = 0      # tiles of the dense trailing block: ALL are computed before any is written
+    trailing_start: int = -1       # pivot position where the dense trailing block starts (-1: none)
+    model_cost: float = 0.0
+
+    @property
+    def n_entries(self):
+        return sum(t.cols.size for t in self.tiles)
+
+    def apply(self, w: np.ndarray) -> np.ndarray:
+        """Host emulation of the kernel's tile executor (w in pivot positions; batch on leading axes)."""
+        w = np.array(w, dtype=float, copy=True)
+        deferred = []
+        for it, t in enumerate(self.tiles):
+            acc = np.zeros(w.shape[:-1] + (LANES,))
+            for k in range(t.K):
+                acc = acc + t.vals[k] * w[..., t.cols[k].astype(int)]
+            off = LANES // 2
+            while off >= t.r_pad:                           # shuffle-xor reduction over the row's lanes
+                acc = acc + acc[..., np.arange(LANES) ^ off]
+                off //= 2
+            if self.n_fwd_tiles <= it < self.n_fwd_tiles + self.n_trailing_tiles:
+                deferred.append((t, acc))
+                if it == self.n_fwd_tiles + self.n_trailing_tiles - 1:
+                    for td, ad in deferred:
+                        w[..., td.rows.astype(int)] = ad[..., :len(td.rows)]
+                continue
+            w[..., t.rows.astype(int)] = acc[..., :len(t.rows)]
+        return w
+
+
+def build_schedule(F: LDLFactor, max_group_rows: int = 64, allow_trailing: bool = True) -> SolveSchedule:
+    level = F.level
+    n = len(level)
+    bounds = [0] + [k for k in range(1, n) if level[k] != level[k - 1]] + [n]
+    nb = len(bounds)
+
+    def cost_f(i, j):
+        rows, M, _ = _forward_group(F, bounds[i], bounds[j])
+        if not len(rows):
+            return 0.0
+        return _group_cost(np.count_nonzero(M, axis=1)[::-1])
+
+    def cost_b(i, j):
+        rows, M, _ = _backward_group(F, bounds[i], bounds[j])
+        return _group_cost(np.count_nonzero(M, axis=1))
+
+    INF = float('inf')
+    Ff, Pf = [INF] * nb, [-1] * nb
+    Bb, Pb = [INF] * nb, [-1] * nb
+    Ff[0] = Bb[0] = 0.0
+    for j in range(1, nb):
+        for i in range(j - 1, -1, -1):
+            if bounds[j] - bounds[i] > max_group_rows and i != j - 1:
+                break
+            cf = Ff[i] + cost_f(i, j)
+            if cf < Ff[j]:
+                Ff[j], Pf[j] = cf, i
+            cb = Bb[i] + cost_b(i, j)
+            if cb < Bb[j]:
+                Bb[j], Pb[j] = cb, i
+    best_j, best = nb - 1, Ff[nb - 1] + Bb[nb - 1]
+    if allow_trailing:
+        for j in range(1, nb - 1):
+            r = n - bounds[j]
+            if r > 160:
+                continue
+            _, Mt, _ = _trailing_block(F, bounds[j])
+            dense = _group_cost(np.count_nonzero(Mt, axis=1))
+            tot = Ff[j] + Bb[j] + dense
+            if tot < best:
+                best, best_j = tot, j
+
+    def backtrack(prev, j):
+        out = []
+        while j > 0:
+            out.append((bounds[prev[j]], bounds[j]))
+            j = prev[j]
+        return out[::-1]
+
+    tiles: List[Tile] = []
+    for a, b in backtrack(Pf, best_j):
+        rows, M, cp = _forward_group(F, a, b)
+        if len(rows):
+            tiles += _make_tiles(rows, M, cp, decreasing=True)
+    n_fwd = len(tiles)
+    s = -1
+    if best_j != nb - 1:
+        s = bounds[best_j]
+        rows, M, cp = _trailing_block(F, s)
+        # the trailing block reads every row of the block: emit as ONE hazard unit -> handled by the
+        # kernel as a multi-tile "gather-then-write" step (flagged through SolveSchedule.trailing_start)
+        tiles += _make_tiles(rows, M, cp, decreasing=False)
+    n_trail = len(tiles) - n_fwd
+    for a, b in reversed(backtrack(Pb, best_j)):
+        rows, M, cp = _backward_group(F, a, b)
+        tiles += _make_tiles(rows, M, cp, decreasing=False)
+    return SolveSchedule(tiles=tiles, n=n, n_fwd_tiles=n_fwd, n_trailing_tiles=n_trail,
+                         trailing_start=s, model_cost=best)

@@ -1,0 +1,255 @@
+"""ctypes binding of a generated ADMM-CUDA solver library (libcpg_b200.so).
+
+This file is copied verbatim into every generated code directory as ``cpg_module.py``; it plays
+the role of the reference's pybind11 module ``cpg_module`` (emitter cvxpygen/utils.py:1331-1412,
+structs TPL/cpg_module.hpp.jinja2:10-76):
+
+  reference                               here
+  --------------------------------------  ------------------------------------------------------
+  cpg_module.solve(upd, par) -> result    Module.solve(upd, par) -> result      (batch of one)
+  cpg_module.set_solver_default_settings  Module.set_solver_default_settings()
+  cpg_module.set_solver_<name>(v)         Module.set_solver_<name>(v)   (AttributeError if unknown)
+  <prefix>cpg_params / cpg_updated / ...  Module.cpg_params() / cpg_updated() ... plain attribute bags
+  (none)                                  Module.solve_batch(params)            NEW: host arrays
+  (none)                                  Module.solve_batch_device(tensor)     NEW: torch CUDA tensors
+
+There is no CPU fallback: if the library or a CUDA device is missing, construction raises.
+"""
+import ctypes as C
+import json
+import os
+import time
+from types import SimpleNamespace
+
+import numpy as np
+
+STATUS_STRINGS = {1: 'solved', 2: 'solved inaccurate', 3: 'primal infeasible inaccurate',
+                  4: 'dual infeasible inaccurate', -2: 'maximum iterations reached',
+                  -3: 'primal infeasible', -4: 'dual infeasible', -7: 'problem non convex',
+                  -10: 'unsolved', -100: 'handed off'}   # osqp_sources/src/auxil.c:655-679
+
+
+class CpgB200Settings(C.Structure):
+    _fields_ = [('max_iter', C.c_int), ('check_termination', C.c_int), ('scaled_termination', C.c_int),
+                ('warm_start', C.c_int), ('adaptive_rho', C.c_int), ('adaptive_rho_interval', C.c_int),
+                ('scaling', C.c_int), ('pad_', C.c_int),
+                ('eps_abs', C.c_double), ('eps_rel', C.c_double), ('eps_prim_inf', C.c_double),
+                ('eps_dual_inf', C.c_double), ('alpha', C.c_double), ('adaptive_rho_tolerance', C.c_double)]
+
+
+class CpgB200Dims(C.Structure):
+    _fields_ = [('n_var', C.c_int), ('n_con', C.c_int), ('n_param', C.c_int), ('n_prim', C.c_int),
+                ('n_dual', C.c_int), ('blob_bytes', C.c_int), ('warps_per_cta', C.c_int), ('smem_bytes', C.c_int)]
+
+
+# settings the reference exposes for OSQP and their cvxpy aliases (cvxpygen/solvers/osqp.py:102-115)
+SETTING_ALIASES = {'warm_starting': 'warm_start'}
+READONLY_SETTINGS = ('scaling', 'pad_')
+
+
+class Module:
+    """One loaded solver library bound to one CUDA device."""
+
+    def __init__(self, code_dir, device=0):
+        self.code_dir = os.path.abspath(code_dir)
+        with open(os.path.join(self.code_dir, 'cpg_meta.json')) as f:
+            self.meta = json.load(f)
+        self.prefix = self.meta['prefix']
+        path = os.path.join(self.code_dir, 'libcpg_b200.so')
+        if not os.path.exists(path):
+            raise RuntimeError(f'{path} is missing: run cvxpygen_b200.codegen.compile_code (nvcc, sm_100a) first; '
+                               'there is no CPU fallback')
+        self.lib = C.CDLL(path)
+        self._fn('cpg_b200_last_error').restype = C.c_char_p
+        self.dims = CpgB200Dims()
+        self._check(self._fn('cpg_b200_dims')(C.byref(self.dims)))
+        self.settings = CpgB200Settings()
+        self.set_solver_default_settings()
+        self.device = device
+        self._initialised = False
+
+    # ---- plumbing
+    def _fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._fn('cpg_b200_last_error')()
+            raise RuntimeError(f'cpg_b200 error {rc}: {msg.decode() if msg else ""}')
+
+    def init(self):
+        if not self._initialised:
+            self._check(self._fn('cpg_b200_init')(C.c_int(self.device)))
+            self._initialised = True
+        return self
+
+    def load_constants(self, blob: bytes):
+        self.init()
+        self._check(self._fn('cpg_b200_load_constants')(C.c_char_p(blob), C.c_int(len(blob))))
+
+    def launch_count(self):
+        return int(self._fn('cpg_b200_launch_count')())
+
+    # ---- settings (b2: cpg_set_solver_default_settings / cpg_set_solver_<name>)
+    def set_solver_default_settings(self):
+        self._fn('cpg_b200_default_settings')(C.byref(self.settings))
+
+    def set_solver_setting(self, name, value):
+        name = SETTING_ALIASES.get(name, name)
+        if name in READONLY_SETTINGS or name not in dict(CpgB200Settings._fields_):
+            raise AttributeError(f'Solver setting "{name}" not available.')   # TPL/cpg_solver.py.jinja2:59-60
+        setattr(self.settings, name, value)
+
+    def __getattr__(self, item):
+        if item.startswith('set_solver_'):
+            name = item[len('set_solver_'):]
+            return lambda v: self.set_solver_setting(name, v)
+        raise AttributeError(item)
+
+    # ---- attribute bags mirroring the pybind classes
+    def cpg_params(self):
+        return SimpleNamespace(**{p['name']: list(p['default']) if p['size'] > 1 else p['default'][0]
+                                  for p in self.meta['params']})
+
+    def cpg_updated(self):
+        return SimpleNamespace(**{p['name']: False for p in self.meta['params']})
+
+    # ---- packing helpers
+    def pack_params(self, params, B=None):
+        """dict name -> (B, size) | (B, *shape) | (size,) broadcast  ->  (B, n_param) float64, batched params only.
+        Matrices are flattened in Fortran order like the reference (TPL/cpg_solver.py.jinja2:26-34)."""
+        bp = [p for p in self.meta['params'] if p['batched']]
+        unknown = set(params) - {p['name'] for p in self.meta['params']}
+        if unknown:
+            raise AttributeError(f'{sorted(unknown)[0]} is not a parameter.')
+        shared_given = [n for n in params if n not in {p['name'] for p in bp}]
+        if shared_given:
+            raise ValueError(f'parameters {shared_given} are shared by the whole batch in this generated code; '
+                             'update them with update_shared_params (host re-setup), not per instance')
+        flat = {}
+        for p in bp:
+            if p['name'] not in params:
+                continue
+            a = np.asarray(params[p['name']], dtype=np.float64)
+            shp, sz = tuple(p['shape']), p['size']
+            if a.shape == shp or a.shape == (sz,) or a.size == 1 == sz and a.ndim == 0:
+                a = a.flatten(order='F').reshape(1, sz)                 # one value, broadcast over the batch
+            elif a.shape[1:] == shp and len(shp) > 1:
+                a = a.transpose([0] + list(range(a.ndim - 1, 0, -1))).reshape(a.shape[0], sz)   # per-instance F-order
+            elif a.ndim == 2 and a.shape[1] == sz:
+                pass
+            elif a.ndim == 1 and sz == 1:
+                a = a.reshape(-1, 1)
+            else:
+                raise ValueError(f"parameter {p['name']}: cannot interpret shape {a.shape} for size {sz}")
+            flat[p['name']] = a
+            if a.shape[0] > 1:
+                if B is not None and B != a.shape[0]:
+                    raise ValueError('inconsistent batch sizes')
+                B = a.shape[0]
+        B = 1 if B is None else B
+        out = np.empty((B, self.dims.n_param), dtype=np.float64)
+        col = 0
+        for p in bp:
+            sz = p['size']
+            a = flat.get(p['name'], np.asarray(p['default'], dtype=np.float64).reshape(1, sz))
+            out[:, col:col + sz] = np.broadcast_to(a, (B, sz))
+            col += sz
+        return out
+
+    def unpack(self, prim, dual):
+        res_p, res_d = {}, {}
+        for v in self.meta['variables']:
+            a = prim[:, v['offset']:v['offset'] + v['size']]
+            res_p[v['name']] = a.reshape((a.shape[0],) + tuple(v['shape']), order='F') if len(v['shape']) > 1 else a
+        for d in self.meta['duals']:
+            a = dual[:, d['offset']:d['offset'] + d['size']]
+            res_d[d['name']] = a
+        return res_p, res_d
+
+    # ---- NEW: batched solve, host arrays (goes through cpg_solve_batch_host: H2D + kernel + D2H)
+    def solve_batch(self, params, x0=None, y0=None, return_canonical=False, **settings):
+        self.init()
+        for k, v in settings.items():
+            self.set_solver_setting(k, v)
+        P = params if isinstance(params, np.ndarray) else self.pack_params(params)
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        B = P.shape[0]
+        d = self.dims
+        prim = np.empty((B, d.n_prim)); dual = np.empty((B, d.n_dual))
+        solx = np.empty((B, d.n_var)) if return_canonical else None
+        soly = np.empty((B, d.n_con)) if return_canonical else None
+        obj = np.empty(B); pri = np.empty(B); dua = np.empty(B)
+        it = np.empty(B, dtype=np.int32); st = np.empty(B, dtype=np.int32)
+        s = self.settings
+        if x0 is not None and y0 is not None:
+            x0 = np.ascontiguousarray(x0, dtype=np.float64); y0 = np.ascontiguousarray(y0, dtype=np.float64)
+            s = CpgB200Settings.from_buffer_copy(bytes(self.settings)); s.warm_start = 1
+
+        def p(a, t=C.c_double):
+            return None if a is None else a.ctypes.data_as(C.POINTER(t))
+        t0 = time.perf_counter()
+        self._check(self._fn('cpg_solve_batch_host')(C.c_int(B), p(P), p(x0), p(y0), p(prim), p(dual), p(solx), p(soly),
+                                                     p(obj), p(it, C.c_int), p(st, C.c_int), p(pri), p(dua), C.byref(s)))
+        t1 = time.perf_counter()
+        pr, du = self.unpack(prim, dual)
+        info = SimpleNamespace(obj_val=obj, iter=it, status=st, pri_res=pri, dua_res=dua, time=t1 - t0)
+        return SimpleNamespace(cpg_prim=pr, cpg_dual=du, cpg_info=info, prim=prim, dual=dual, sol_x=solx, sol_y=soly)
+
+    # ---- NEW: batched solve on torch CUDA tensors already resident in HBM (asynchronous on the current stream)
+    def solve_batch_device(self, params, x0=None, y0=None, out=None, return_canonical=False):
+        import torch
+        self.init()
+        assert params.is_cuda and params.dtype == torch.float64 and params.is_contiguous()
+        B = params.shape[0]
+        d = self.dims
+        dev = params.device
+        if out is None:
+            out = SimpleNamespace(
+                prim=torch.empty((B, d.n_prim), dtype=torch.float64, device=dev),
+                dual=torch.empty((B, d.n_dual), dtype=torch.float64, device=dev),
+                sol_x=torch.empty((B, d.n_var), dtype=torch.float64, device=dev) if return_canonical else None,
+                sol_y=torch.empty((B, d.n_con), dtype=torch.float64, device=dev) if return_canonical else None,
+                obj_val=torch.empty(B, dtype=torch.float64, device=dev),
+                pri_res=torch.empty(B, dtype=torch.float64, device=dev),
+                dua_res=torch.empty(B, dtype=torch.float64, device=dev),
+                iter=torch.empty(B, dtype=torch.int32, device=dev),
+                status=torch.empty(B, dtype=torch.int32, device=dev))
+        s = self.settings
+        if x0 is not None and y0 is not None:
+            s = CpgB200Settings.from_buffer_copy(bytes(self.settings)); s.warm_start = 1
+        ptr = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        self._check(self._fn('cpg_solve_batch_device')(C.c_int(B), ptr(params), ptr(x0), ptr(y0), ptr(out.prim), ptr(out.dual),
+                                                       ptr(out.sol_x), ptr(out.sol_y), ptr(out.obj_val), ptr(out.iter),
+                                                       ptr(out.status), ptr(out.pri_res), ptr(out.dua_res), C.byref(s), stream))
+        return out
+
+    # ---- reference-compatible single-instance entry: cpg_module.solve(upd, par)
+    def solve(self, upd, par):
+        vals = {}
+        for p in self.meta['params']:
+            if p['batched']:
+                vals[p['name']] = np.atleast_1d(np.asarray(getattr(par, p['name']), dtype=np.float64)).reshape(1, -1)
+            elif getattr(upd, p['name'], False):
+                raise ValueError(f"parameter {p['name']} is shared in this generated code; regenerate or use update_shared_params")
+        r = self.solve_batch(vals)
+        prim = SimpleNamespace(**{k: (v[0].flatten(order='F').tolist() if v[0].size > 1 else float(v[0].ravel()[0]))
+                                  for k, v in r.cpg_prim.items()})
+        dual = SimpleNamespace(**{k: (v[0].tolist() if v[0].size > 1 else float(v[0].ravel()[0])) for k, v in r.cpg_dual.items()})
+        info = SimpleNamespace(obj_val=float(r.cpg_info.obj_val[0]), iter=int(r.cpg_info.iter[0]),
+                               status=STATUS_STRINGS.get(int(r.cpg_info.status[0]), 'unknown'),
+                               pri_res=float(r.cpg_info.pri_res[0]), dua_res=float(r.cpg_info.dua_res[0]),
+                               time=r.cpg_info.time)
+        return SimpleNamespace(cpg_prim=prim, cpg_dual=dual, cpg_info=info)
+
+
+_modules = {}
+
+
+def load(code_dir=None, device=0) -> Module:
+    code_dir = os.path.dirname(os.path.abspath(__file__)) if code_dir is None else os.path.abspath(code_dir)
+    key = (code_dir, device)
+    if key not in _modules:
+        _modules[key] = Module(code_dir, device)
+    return _modules[key]

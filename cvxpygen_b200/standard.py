@@ -1,0 +1,43 @@
+"""The problem families this repository builds ahead of time (BASELINE.json `configs`).
+
+`build_all()` is what `__graft_entry__.build()` runs: generate + nvcc-compile every family into
+cvxpygen_b200/_generated/<name>/ (in-tree, so the .so files travel to the GPU box).
+"""
+import os
+from typing import Dict, Tuple, Callable, List
+
+from . import families
+from .cpg import generate_code
+
+GENERATED_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_generated')
+
+# name -> (family builder, batched parameters)
+STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
+    'mpc_12_4_10': (lambda: families.mpc(12, 4, 10), ['x_init']),          # BASELINE config 2 / 5 (headline)
+    'mpc_6_3_10': (lambda: families.mpc(6, 3, 10), ['x_init']),             # the reference test's MPC size
+    'nonneg_LS_3_2': (lambda: families.nonneg_ls(3, 2), ['b']),             # BASELINE config 1 (README example)
+    'random_qp_20_5_15': (lambda: families.random_qp(20, 5, 15), ['q', 'b', 'h']),  # unstructured sparsity, q/l/u all batched
+}
+
+
+def code_dir(name: str) -> str:
+    return os.path.join(GENERATED_DIR, name)
+
+
+def build(name: str, force: bool = False, verbose: bool = False) -> str:
+    d = code_dir(name)
+    if not force and os.path.exists(os.path.join(d, 'libcpg_b200.so')):
+        return d
+    fam_fn, batch = STANDARD[name]
+    os.makedirs(GENERATED_DIR, exist_ok=True)
+    generate_code(fam_fn(), code_dir=d, solver='ADMM-CUDA', batch_params=batch, prefix='', wrapper=True, verbose=verbose)
+    return d
+
+
+def build_all(force: bool = False, verbose: bool = False):
+    return {name: build(name, force, verbose) for name in STANDARD}
+
+
+def load(name: str, device: int = 0):
+    from . import runtime
+    return runtime.load(build(name), device)

@@ -1,0 +1,109 @@
+/* cpg_b200.h -- C ABI of one generated ADMM-CUDA solver library (libcpg_b200_<name>.so).
+ *
+ * Drop-in boundary of the batched-solve hot path.  Plain pointers and sizes only -- no
+ * torch / CUDA types in the signatures (`stream` is an opaque cudaStream_t handle, 0 = default).
+ * Every function name is prefixed with the code-generation prefix exactly like the reference's
+ * generated C (`<prefix>cpg_solve`, cvxpygen/utils.py:1087-1141); CPG_B200_PREFIX is empty by default.
+ *
+ * Part A keeps the reference's generated single-instance interface (what its pybind module
+ * binds, cvxpygen/utils.py:1194-1270, 1331-1412):
+ *     void <p>cpg_update_<param>(cpg_int idx, cpg_float val)      cvxpygen/utils.py:904-935
+ *     void <p>cpg_solve()                                         cvxpygen/utils.py:1009-1052
+ *     void <p>cpg_set_solver_default_settings()                   cvxpygen/utils.py:1069-1076
+ *     void <p>cpg_set_solver_<setting>(value)                     cvxpygen/utils.py:1077-1084
+ *     globals  <p>CPG_Prim, <p>CPG_Dual, <p>CPG_Info, <p>CPG_Result   cvxpygen/utils.py:745-798
+ *   These are emitted per family into c/include/cpg_solve.h + c/include/cpg_workspace.h because
+ *   their names depend on the user's parameter / variable names; they run a batch of one.
+ *
+ * Part B (this header) is the NEW batched entry the reference lacks (SURVEY section 8b, row "new").
+ * All functions return 0 on success or a CPG_B200_ERR_* code; nothing aborts, nothing falls back to
+ * a CPU path: without a CUDA device cpg_b200_init fails with CPG_B200_ERR_CUDA.
+ */
+#ifndef CPG_B200_H
+#define CPG_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef CPG_B200_PREFIX
+#define CPG_B200_PREFIX
+#endif
+#define CPG_B200_CAT_(a, b) a##b
+#define CPG_B200_CAT(a, b) CPG_B200_CAT_(a, b)
+#define CPG_B200_FN(name) CPG_B200_CAT(CPG_B200_PREFIX, name)
+
+enum {
+  CPG_B200_OK = 0,
+  CPG_B200_ERR_CUDA = 1,        /* a CUDA runtime call failed: see cpg_b200_last_error() */
+  CPG_B200_ERR_NOT_INIT = 2,    /* cpg_b200_init() has not been called */
+  CPG_B200_ERR_BAD_ARG = 3,     /* null pointer / negative size */
+  CPG_B200_ERR_TAIL_OVERFLOW = 4 /* more hand-offs to the refactorisation kernel than its queue holds */
+};
+
+/* OSQP status values reported per instance in `status` (osqp_sources/include/constants.h:18-30) */
+enum {
+  CPG_B200_SOLVED = 1, CPG_B200_SOLVED_INACCURATE = 2,
+  CPG_B200_PRIMAL_INFEASIBLE_INACCURATE = 3, CPG_B200_DUAL_INFEASIBLE_INACCURATE = 4,
+  CPG_B200_MAX_ITER_REACHED = -2, CPG_B200_PRIMAL_INFEASIBLE = -3, CPG_B200_DUAL_INFEASIBLE = -4,
+  CPG_B200_NON_CVX = -7, CPG_B200_UNSOLVED = -10
+};
+
+/* Solver settings: the table cvxpygen exposes for OSQP (cvxpygen/solvers/osqp.py:102-115) plus the
+ * OSQP defaults that shape the iteration (osqp_sources/include/constants.h:59-114).
+ * rho and sigma are NOT here: they are baked into the KKT factor at generation time. */
+typedef struct {
+  int max_iter;               /* 4000 */
+  int check_termination;      /* 25   */
+  int scaled_termination;     /* 0    */
+  int warm_start;             /* 0 for batches (cold start); 1 uses x0/y0 */
+  int adaptive_rho;           /* 1    */
+  int adaptive_rho_interval;  /* 0 = 4*check_termination, as OSQP without a timer (osqp.c:267-279) */
+  int scaling;                /* read-only: number of Ruiz iterations used at generation time */
+  int pad_;
+  double eps_abs, eps_rel;            /* 1e-3 */
+  double eps_prim_inf, eps_dual_inf;  /* 1e-4 */
+  double alpha;                       /* 1.6  */
+  double adaptive_rho_tolerance;      /* 5    */
+} CpgB200Settings;
+
+/* Problem-family dimensions baked into the library. */
+typedef struct {
+  int n_var, n_con;        /* canonical QP: x in R^n_var, l <= A x <= u in R^n_con            */
+  int n_param;             /* doubles per instance in `params` (batched user parameters only)  */
+  int n_prim, n_dual;      /* doubles per instance in `prim` / `dual`                          */
+  int blob_bytes;          /* shared-memory constants blob                                     */
+  int warps_per_cta, smem_bytes;
+} CpgB200Dims;
+
+int  CPG_B200_FN(cpg_b200_init)(int device);                 /* upload constants, allocate queues  */
+int  CPG_B200_FN(cpg_b200_free)(void);
+int  CPG_B200_FN(cpg_b200_dims)(CpgB200Dims* out);
+void CPG_B200_FN(cpg_b200_default_settings)(CpgB200Settings* s);
+const char* CPG_B200_FN(cpg_b200_last_error)(void);
+int  CPG_B200_FN(cpg_b200_launch_count)(void);               /* kernels launched by the last solve call */
+/* Replace the constants blob (shared parameters changed => host re-ran the offline setup). */
+int  CPG_B200_FN(cpg_b200_load_constants)(const void* blob, int nbytes);
+
+/* Batched solve, DEVICE buffers (row-major, one instance per row), asynchronous on `stream`.
+ *   params (B, n_param) in        x0 (B, n_var) / y0 (B, n_con) optional warm start (NULL = cold)
+ *   prim (B, n_prim), dual (B, n_dual) out; sol_x (B, n_var), sol_y (B, n_con) optional (NULL = skip)
+ *   obj_val, pri_res, dua_res: (B) double;  iter, status: (B) int                               */
+int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const double* x0, const double* y0,
+                                        double* prim, double* dual, double* sol_x, double* sol_y,
+                                        double* obj_val, int* iter, int* status,
+                                        double* pri_res, double* dua_res,
+                                        const CpgB200Settings* settings, void* stream);
+
+/* Same with HOST buffers: H2D of params, solve, D2H of the results, synchronous.  This is what the
+ * generated cpg_solve()/cpg_module.solve_batch call. */
+int CPG_B200_FN(cpg_solve_batch_host)(int B, const double* params, const double* x0, const double* y0,
+                                      double* prim, double* dual, double* sol_x, double* sol_y,
+                                      double* obj_val, int* iter, int* status,
+                                      double* pri_res, double* dua_res,
+                                      const CpgB200Settings* settings);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPG_B200_H */
