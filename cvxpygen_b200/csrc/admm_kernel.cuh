@@ -172,6 +172,89 @@ __device__ __forceinline__ void kkt_solve(const CpgBlobHeader* H, const int* I32
   }
 }
 
+
+// ---------------------------------------------------------------- tail path: per-instance numeric LDL' (a9)
+// Tables built by offline/refactor.py; they live in GLOBAL memory (L2-resident, shared by all tail warps).
+struct TailView {
+  const CpgTailHeader* H;
+  const int* I32;
+  const double* F64;
+  const uint16_t* U16;
+};
+__device__ __forceinline__ TailView make_tail_view(const uint8_t* blob) {
+  TailView tv;
+  tv.H = reinterpret_cast<const CpgTailHeader*>(blob);
+  tv.I32 = reinterpret_cast<const int*>(blob + tv.H->off_i32);
+  tv.F64 = reinterpret_cast<const double*>(blob + tv.H->off_f64);
+  tv.U16 = reinterpret_cast<const uint16_t*>(blob + tv.H->off_u16);
+  return tv;
+}
+
+// Numeric factorisation of K(rho_vec) on the family's symbolic pattern (role of QDLDL_factor, qdldl.c:72-233,
+// after update_KKT_param2, kkt.c:214-222).  S holds K's lower triangle in slot order with -1/rho_vec already
+// written; on exit S[j] = 1/D_j and the other slots hold L.  Right-looking, one elimination-tree level at a time.
+__device__ __forceinline__ void tail_factor(const TailView& tv, double* S, int lane) {
+  const int nl = tv.H->n_levels;
+  const int* lp = tv.I32 + tv.H->i_level_ptr;
+  const int* op = tv.I32 + tv.H->i_op_ptr;
+  const int* sp = tv.I32 + tv.H->i_scale_ptr;
+  const uint16_t* lc = tv.U16 + tv.H->h_level_cols;
+  const ushort4* ops = reinterpret_cast<const ushort4*>(tv.U16 + tv.H->h_ops);
+  const ushort2* scl = reinterpret_cast<const ushort2*>(tv.U16 + tv.H->h_scale);
+  for (int lv = 0; lv < nl; ++lv) {
+    for (int c = lp[lv] + lane; c < lp[lv + 1]; c += LANES) { const int j = lc[c]; S[j] = 1.0 / S[j]; }
+    __syncwarp();
+    for (int o = op[lv] + lane; o < op[lv + 1]; o += LANES) {
+      const ushort4 q = __ldg(ops + o);
+      atomicAdd(&S[q.x], -(S[q.y] * S[q.z] * S[q.w]));
+    }
+    __syncwarp();
+    for (int o = sp[lv] + lane; o < sp[lv + 1]; o += LANES) { const ushort2 q = __ldg(scl + o); S[q.x] *= S[q.y]; }
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ double slot_tile_acc(const int* h, const uint16_t* U16, const double* S,
+                                                const double* w, int lane) {
+  const uint16_t* sl = U16 + h[0] + lane;
+  const uint16_t* c = U16 + h[1] + lane;
+  const int K = h[2];
+  double a0 = 0.0, a1 = 0.0;
+  int k = 0;
+  for (; k + 1 < K; k += 2) {
+    a0 = fma(S[sl[k * LANES]], w[c[k * LANES]], a0);
+    a1 = fma(S[sl[(k + 1) * LANES]], w[c[(k + 1) * LANES]], a1);
+  }
+  if (k < K) a0 = fma(S[sl[k * LANES]], w[c[k * LANES]], a0);
+  double acc = a0 + a1;
+  for (int o = 16; o >= h[3]; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+  return acc;
+}
+
+// K x = b with the per-instance factor: level-scheduled L solve, D^{-1}, L' solve (QDLDL_solve, qdldl.c:269-281)
+__device__ __forceinline__ void tail_solve(const TailView& tv, const double* S, double* w, int lane) {
+  const int* T = tv.I32 + tv.H->i_tiles;
+  const int nf = tv.H->n_fwd_tiles, nt = nf + tv.H->n_bwd_tiles, nk = tv.H->nk;
+  for (int t = 0; t < nt; ++t) {
+    if (t == nf) {
+      for (int i = lane; i < nk; i += LANES) w[i] *= S[i];
+      __syncwarp();
+    }
+    const int* h = T + 8 * t;
+    const double acc = slot_tile_acc(h, tv.U16, S, w, lane);
+    __syncwarp();
+    if (lane < h[4]) { const int r = tv.U16[h[5] + lane]; w[r] -= acc; }
+    __syncwarp();
+  }
+  if (nt == nf) { for (int i = lane; i < nk; i += LANES) w[i] *= S[i]; __syncwarp(); }
+}
+
+struct TailArgs {
+  TailView tv;
+  double* S;              // per-warp shared memory, n_slots doubles
+  const double* state;    // x(n) z(m) y(m) rho iter of the handed-off instance
+};
+
 // ---------------------------------------------------------------- per-instance solver
 template <class Fam>
 struct Instance {
@@ -193,11 +276,11 @@ struct Instance {
   }
 };
 
-template <class Fam>
+template <class Fam, bool TAIL>
 __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* __restrict__ I32,
                                const double* __restrict__ F64, const uint16_t* __restrict__ U16,
                                double* __restrict__ w, const int lane, const int b,
-                               const BatchIO& io, const Settings& st) {
+                               const BatchIO& io, const Settings& st, const TailArgs* ta) {
   using I = Instance<Fam>;
   constexpr int N = I::N, M = I::M, NXL = I::NXL, NZL = I::NZL;
   I s;
@@ -252,14 +335,41 @@ __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* _
   }
   type_mismatch = __any_sync(FULL, type_mismatch);
 
-  const double rho_in = H->rho, rho_eq = RHO_EQ_FACTOR * H->rho;
-  const double rinv_in = 1.0 / rho_in, rinv_eq = 1.0 / rho_eq, rinv_loose = 1.0 / RHO_MIN;
+  double rho_in = H->rho, rho_eq = RHO_EQ_FACTOR * H->rho;
+  double rinv_in = 1.0 / rho_in, rinv_eq = 1.0 / rho_eq;
+  const double rinv_loose = 1.0 / RHO_MIN;
   auto rinv_of = [&](int k) -> double {
     return ((s.loosemask >> k) & 1u) ? rinv_loose : (((s.eqmask >> k) & 1u) ? rinv_eq : rinv_in);
   };
 
   // ---- cold start (auxil.c:155-159) or warm start (osqp.c:929-953: x <- Dinv x, y <- c Einv y, z <- A x)
-  if (st.warm_start && io.x0 != nullptr && io.y0 != nullptr) {
+  int it0 = 0;
+  // (TAIL) build this instance's own factor: S <- K(rho_vec) on the symbolic pattern, then numeric LDL'
+  auto refactor = [&]() {
+    if (TAIL) {
+      const TailView& tv = ta->tv;
+      double* S = ta->S;
+      for (int i = lane; i < tv.H->n_slots; i += LANES) S[i] = tv.F64[tv.H->f_S0 + i];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < NZL; ++k) {
+        const int j = lane + 32 * k;
+        if (j < M) S[tv.U16[tv.H->h_rho_slot + j]] = -rinv_of(k);
+      }
+      __syncwarp();
+      tail_factor(tv, S, lane);
+    }
+  };
+  if (TAIL) {
+    const double* ts = ta->state;
+#pragma unroll
+    for (int k = 0; k < NXL; ++k) { const int i = lane + 32 * k; if (i < N) s.x[k] = ts[i]; }
+#pragma unroll
+    for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) { s.z[k] = ts[N + j]; s.y[k] = ts[N + M + j]; } }
+    rho_in = ts[N + 2 * M]; rho_eq = RHO_EQ_FACTOR * rho_in; rinv_in = 1.0 / rho_in; rinv_eq = 1.0 / rho_eq;
+    it0 = (int)ts[N + 2 * M + 1];
+    refactor();
+  } else if (st.warm_start && io.x0 != nullptr && io.y0 != nullptr) {
 #pragma unroll
     for (int k = 0; k < NXL; ++k) {
       const int i = lane + 32 * k;
@@ -282,7 +392,7 @@ __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* _
   int status = ST_UNSOLVED;
   int it = 0;
   double rho_new = rho_in;
-  bool handoff = type_mismatch;     // a constraint changed type: this instance needs its own KKT factor
+  bool handoff = !TAIL && type_mismatch;     // a constraint changed type: this instance needs its own KKT factor
 
   // ---- residuals + norms of the current iterate (update_info, auxil.c:564-629)
   auto update_info = [&]() {
@@ -432,14 +542,15 @@ __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* _
 
   // ---- main ADMM loop (osqp.c:354-527)
   if (!handoff) {
-    for (it = 1; it <= st.max_iter; ++it) {
+    for (it = it0 + 1; it <= st.max_iter; ++it) {
       // compute_rhs (auxil.c:161-175), written straight into pivot order
 #pragma unroll
       for (int k = 0; k < NXL; ++k) { const int i = lane + 32 * k; if (i < N) w[px[k]] = sigma * s.x[k] - s.q[k]; }
 #pragma unroll
       for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) w[pz[k]] = s.z[k] - rinv_of(k) * s.y[k]; }
       __syncwarp();
-      kkt_solve<Fam::TRAIL>(H, I32, F64, U16, w, lane);
+      if (TAIL) tail_solve(ta->tv, ta->S, w, lane);
+      else kkt_solve<Fam::TRAIL>(H, I32, F64, U16, w, lane);
       // update_x, update_z (+project), update_y (auxil.c:185-225)
 #pragma unroll
       for (int k = 0; k < NXL; ++k) {
@@ -479,7 +590,12 @@ __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* _
           double r = rho_in * sqrt(pn / dn);
           r = fmin(fmax(r, RHO_MIN), RHO_MAX);
           if (r > rho_in * st.adaptive_rho_tolerance || r < rho_in / st.adaptive_rho_tolerance) {
-            rho_new = r; handoff = true; break;   // needs a per-instance refactorisation: tail kernel
+            if (TAIL) {                              // osqp_update_rho (osqp.c:1268-1325) + refactor
+              rho_in = r; rho_eq = RHO_EQ_FACTOR * r; rinv_in = 1.0 / rho_in; rinv_eq = 1.0 / rho_eq;
+              refactor();
+            } else {
+              rho_new = r; handoff = true; break;   // needs a per-instance refactorisation: tail kernel
+            }
           }
         }
       }
@@ -578,7 +694,44 @@ admm_batch_kernel(const uint8_t* __restrict__ blob_g, const BatchIO io, const Se
     if (lane == 0) b = atomicAdd(io.work_counter, 1u);
     b = __shfl_sync(FULL, b, 0);
     if (b >= (unsigned)io.B) break;
-    solve_instance<Fam>(H, I32, F64, U16, w, lane, (int)b, io, st);
+    solve_instance<Fam, false>(H, I32, F64, U16, w, lane, (int)b, io, st, nullptr);
+    __syncwarp();
+  }
+}
+
+// Tail kernel: instances whose rho changed (or whose bounds changed a constraint type) continue here with their
+// own numeric factor.  One warp per instance; reads the hand-off queue written by admm_batch_kernel.
+template <class Fam>
+__global__ void __launch_bounds__(Fam::TAIL_WARPS * 32, 1)
+admm_tail_kernel(const uint8_t* __restrict__ blob_g, const uint8_t* __restrict__ tail_blob_g,
+                 const BatchIO io, const Settings st) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const int n_tail = min(*io.tail_count, io.tail_capacity);
+  if (n_tail == 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t total = reinterpret_cast<const CpgBlobHeader*>(blob_g)->total_bytes;
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, total);
+    constexpr uint32_t CHUNK = 32768;
+    for (uint32_t off = 0; off < total; off += CHUNK)
+      tma_bulk_g2s(smem + off, blob_g + off, (total - off < CHUNK) ? (total - off) : CHUNK, &bar);
+  }
+  mbar_wait(&bar, 0);
+  const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(smem);
+  const int* I32 = reinterpret_cast<const int*>(smem + H->off_i32);
+  const double* F64 = reinterpret_cast<const double*>(smem + H->off_f64);
+  const uint16_t* U16 = reinterpret_cast<const uint16_t*>(smem + H->off_u16);
+  double* wbase = reinterpret_cast<double*>(smem + Fam::BLOB_BYTES_PAD) + (size_t)warp * (Fam::W_STRIDE + Fam::S_STRIDE);
+  TailArgs ta;
+  ta.tv = make_tail_view(tail_blob_g);
+  ta.S = wbase + Fam::W_STRIDE;
+  for (int slot = blockIdx.x * Fam::TAIL_WARPS + warp; slot < n_tail; slot += gridDim.x * Fam::TAIL_WARPS) {
+    ta.state = io.tail_state + (size_t)slot * (Fam::N + 2 * Fam::M + 2);
+    const int b = io.tail_ids[slot];
+    solve_instance<Fam, true>(H, I32, F64, U16, wbase, lane, b, io, st, &ta);
     __syncwarp();
   }
 }

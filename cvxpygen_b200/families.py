@@ -103,7 +103,7 @@ def mpc(nx=12, nu=4, N=10, Ad=None, Bd=None, Q=None, QN=None, R=None, umax=1.0,
     n_theta = nx + 1
 
     # --- P (upper triangle, CSC) and A (CSC): constants of the family
-    P = sp.block_diag([2 * Q] * N + [2 * QN] + [2 * R] * N, format='csc')
+    P = sp.block_diag([sp.csc_matrix(2 * Q)] * N + [sp.csc_matrix(2 * QN)] + [sp.csc_matrix(2 * R)] * N, format='csc')
     Pu = sp.triu(P, format='csc'); Pu.eliminate_zeros(); Pu.sort_indices()
     Ax_blocks = sp.eye(nX, format='csc') - sp.kron(sp.eye(N + 1, k=-1), sp.csc_matrix(Ad), format='csc')
     Au_blocks = -sp.kron(sp.vstack([sp.csc_matrix((1, N)), sp.eye(N)]), sp.csc_matrix(Bd), format='csc')

@@ -116,6 +116,8 @@ def pack_blob(*, n, m, perm, schedule, Ps_upper, As, D, E, c, sigma, rho, ctype,
         h = ar.add_u16(t.cols)
         hr = ar.add_u16(np.concatenate([t.rows, np.zeros(LANES - len(t.rows), dtype=np.uint16)]))
         tile_tab += [f, h, t.K, t.r_pad, len(t.rows), hr, 0, 0]
+    while len(ar.i32) % 4:
+        ar.i32.append(0)
     i_tiles = ar.add_i32(tile_tab)
     # --- residual operators (scaled data): A (rows), A' (rows = variables), full symmetric P
     As = sp.csr_matrix(As)
@@ -154,3 +156,63 @@ def pack_blob(*, n, m, perm, schedule, Ps_upper, As, D, E, c, sigma, rho, ctype,
     blob = _pack_header(hv) + i32b + f64b + u16b
     assert len(blob) == hv['total_bytes'] and len(blob) % 16 == 0
     return blob
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Tail blob: tables of offline/refactor.py for the in-kernel numeric re-factorisation.  Lives in GLOBAL memory.
+TAIL_HEADER_FIELDS: List[Tuple[str, str]] = [
+    ('int', 'magic'), ('int', 'total_bytes'), ('int', 'nk'), ('int', 'n_slots'),
+    ('int', 'n_levels'), ('int', 'n_fwd_tiles'), ('int', 'n_bwd_tiles'), ('int', 'n_ops'),
+    ('int', 'off_i32'), ('int', 'off_f64'), ('int', 'off_u16'), ('int', 'pad0'),
+    ('int', 'i_level_ptr'), ('int', 'i_op_ptr'), ('int', 'i_scale_ptr'), ('int', 'i_tiles'),
+    ('int', 'f_S0'), ('int', 'h_rho_slot'), ('int', 'h_level_cols'), ('int', 'h_ops'),
+    ('int', 'h_scale'), ('int', 'pad1'), ('int', 'pad2'), ('int', 'pad3'),
+]
+
+
+def tail_header_struct_c(name='CpgTailHeader') -> str:
+    return 'struct %s {\n%s};\n' % (name, ''.join(f'  {t} {n};\n' for t, n in TAIL_HEADER_FIELDS))
+
+
+def pack_tail_blob(T) -> bytes:
+    """T: offline.refactor.RefactorTables"""
+    ar = _Areas()
+
+    def align_u16(mult):
+        while len(ar.u16) % mult:
+            ar.u16.append(0)
+    hv = dict(magic=MAGIC + 1, nk=T.nk, n_slots=T.n_slots, n_levels=len(T.level_ptr) - 1,
+              n_fwd_tiles=len(T.fwd_tiles), n_bwd_tiles=len(T.bwd_tiles), n_ops=len(T.ops))
+    hv['i_level_ptr'] = ar.add_i32(T.level_ptr)
+    hv['i_op_ptr'] = ar.add_i32(T.op_ptr)
+    hv['i_scale_ptr'] = ar.add_i32(T.scale_ptr)
+    hv['f_S0'] = ar.add_f64(T.S0)
+    hv['h_rho_slot'] = ar.add_u16(T.rho_slot)
+    hv['h_level_cols'] = ar.add_u16(T.level_cols)
+    align_u16(4)
+    hv['h_ops'] = ar.add_u16(T.ops)
+    align_u16(2)
+    hv['h_scale'] = ar.add_u16(T.scale)
+    tab = []
+    for t in list(T.fwd_tiles) + list(T.bwd_tiles):
+        hs = ar.add_u16(t.slots)
+        hc = ar.add_u16(t.cols)
+        hr = ar.add_u16(np.concatenate([t.rows, np.zeros(LANES - len(t.rows), dtype=np.uint16)]))
+        tab += [hs, hc, t.slots.shape[0], t.r_pad, len(t.rows), hr, 0, 0]
+    hv['i_tiles'] = ar.add_i32(tab if tab else [0] * 8)
+    fmt = '<' + 'i' * len(TAIL_HEADER_FIELDS)
+
+    def hdr():
+        return struct.pack(fmt, *[int(hv.get(n, 0)) for _, n in TAIL_HEADER_FIELDS])
+    assert len(hdr()) % 16 == 0
+
+    def pad16(b: bytes) -> bytes:
+        return b + b'\0' * ((-len(b)) % 16)
+    i32b = pad16(np.asarray(ar.i32, dtype='<i4').tobytes())
+    f64b = pad16(np.asarray(ar.f64, dtype='<f8').tobytes())
+    u16b = pad16(np.asarray(ar.u16, dtype='<u2').tobytes())
+    hv['off_i32'] = len(hdr())
+    hv['off_f64'] = hv['off_i32'] + len(i32b)
+    hv['off_u16'] = hv['off_f64'] + len(f64b)
+    hv['total_bytes'] = hv['off_u16'] + len(u16b)
+    return hdr() + i32b + f64b + u16b

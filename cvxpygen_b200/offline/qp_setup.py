@@ -12,7 +12,8 @@ import scipy.sparse as sp
 
 from ..ir import CanonFamily
 from . import kkt as _kkt
-from .blob import pack_blob
+from .blob import pack_blob, pack_tail_blob
+from .refactor import build_refactor_tables, RefactorTables
 from .equilibrate import ruiz_equilibrate
 from .schedule import SolveSchedule, build_schedule
 
@@ -40,6 +41,8 @@ class QPSetup:
     prim_idx: np.ndarray
     dual_idx: np.ndarray
     blob: bytes = b''
+    tail_blob: bytes = b''
+    refactor: Optional[RefactorTables] = None
     theta_shared: Optional[np.ndarray] = None
     batch_cols: Optional[np.ndarray] = None
     stats: Dict[str, float] = field(default_factory=dict)
@@ -101,9 +104,11 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
                      c=sc['c'], sigma=sigma, rho=rho, ctype=ctype, q_base=q_base, l_base=l_base, u_base=u_base,
                      Mq_b=Mq_b, Ml_b=Ml_b, Mu_b=Mu_b, npb=npb, prim_idx=prim_idx, dual_idx=dual_idx,
                      d_const=d_const, is_max=fam.is_maximization)
-    st = dict(nnz_L=F.nnz, n_levels=int(F.level.max()) + 1, n_tiles=len(S.tiles), schedule_cost=S.model_cost,
+    RT = build_refactor_tables(F, K, n)
+    tail_blob = pack_tail_blob(RT)
+    st = dict(nnz_L=F.nnz, tail_blob_bytes=len(tail_blob), refactor_ops=len(RT.ops), n_levels=int(F.level.max()) + 1, n_tiles=len(S.tiles), schedule_cost=S.model_cost,
               schedule_entries=S.n_entries, blob_bytes=len(blob))
     return QPSetup(family=fam, batch_params=list(batch_params), n=n, m=m, npb=npb, rho=rho, sigma=sigma,
                    scaling=scaling, D=sc['D'], E=sc['E'], c=sc['c'], ctype=ctype, P_scaled=sc['P'],
-                   A_scaled=sc['A'], factor=F, schedule=S, prim_idx=prim_idx, dual_idx=dual_idx, blob=blob,
+                   A_scaled=sc['A'], factor=F, schedule=S, prim_idx=prim_idx, dual_idx=dual_idx, blob=blob, tail_blob=tail_blob, refactor=RT,
                    theta_shared=theta0, batch_cols=bcols, stats=st)

@@ -1,0 +1,187 @@
+"""Tables for the in-kernel numeric LDL' re-factorisation (the "tail" path).
+
+When OSQP adapts rho (`adapt_rho`, osqp_sources/src/auxil.c:54-74 ->
+`osqp_update_rho`, src/osqp.c:1268-1325 -> `update_KKT_param2`, src/kkt.c:214-222 ->
+`QDLDL_factor`, qdldl.c:72-233) or when an instance's bounds change a constraint's type
+(`update_rho_vec`, auxil.c:100-142), that instance needs its OWN factor of
+K(rho_vec) = [[P+sigma I, A'],[A, -diag(1/rho_vec)]].  The symbolic structure (ordering,
+elimination tree, pattern of L) is the family's; only values change.  QDLDL does an
+up-looking, row-by-row numeric factorisation -- sequential.  For a warp we pre-compute:
+
+  * S layout: value slot of every entry of the lower triangle of P K P' inside the pattern of L
+    (slots [0,nk) = diagonal, then the strictly-lower entries column by column);
+  * S0: slot values of K without the -1/rho diagonal;  rho_slot[j] = diagonal slot of constraint j;
+  * per elimination-tree level (columns of a level are independent):
+      - the columns of the level                          -> D_j = S[j], S[j] <- 1/D_j
+      - update ops (t, a, b, j):  S[t] -= S[a] * S[b] * Dinv_j   (right-looking; atomics resolve
+        different columns of the level hitting the same target)
+      - scale list (slot):         S[slot] *= Dinv_{col(slot)}   (Y -> L)
+  * triangular-solve tiles over per-instance values: like offline/schedule.py tiles but each entry
+    carries a SLOT into S instead of an inlined coefficient; one set of tiles per level, rows of thin
+    levels are spread over several lanes (p-split) so that a chain level costs ~1 FMA + shuffles.
+
+`emulate()` runs the exact op sequence in numpy; tests pin it against a dense solve.
+"""
+from dataclasses import dataclass
+from typing import List
+
+import numpy as np
+import scipy.sparse as sp
+
+from .kkt import LDLFactor
+from .schedule import LANES, _pad_pow2
+
+
+@dataclass
+class SlotTile:
+    rows: np.ndarray     # (nrows,) pivot positions written
+    r_pad: int
+    slots: np.ndarray    # (K, 32) uint16 slot into S   (padding: slot of a zero entry, see zero_slot)
+    cols: np.ndarray     # (K, 32) uint16 position in w
+
+
+@dataclass
+class RefactorTables:
+    nk: int
+    n_slots: int                  # nk + nnz(L) + 1 (last slot is a constant zero for padding)
+    S0: np.ndarray                # (n_slots,) base values
+    rho_slot: np.ndarray          # (m,) diagonal slot of constraint row j
+    level_ptr: np.ndarray         # (n_levels+1,) into level_cols
+    level_cols: np.ndarray        # columns (pivot positions) level by level
+    op_ptr: np.ndarray            # (n_levels+1,) into ops
+    ops: np.ndarray               # (n_ops, 4) uint16: t, a, b, j
+    scale_ptr: np.ndarray         # (n_levels+1,) into scale
+    scale: np.ndarray             # (n_scale, 2) uint16: slot, j
+    fwd_tiles: List[SlotTile]
+    bwd_tiles: List[SlotTile]
+
+    @property
+    def zero_slot(self):
+        return self.n_slots - 1
+
+
+def _slot_tiles(rows, entries, zero_slot) -> List[SlotTile]:
+    """rows: positions; entries[i] = list of (slot, col) for row rows[i]."""
+    tiles = []
+    for t0 in range(0, len(rows), LANES):
+        sel = list(range(t0, min(t0 + LANES, len(rows))))
+        nr = len(sel)
+        r_pad = _pad_pow2(nr)
+        p = LANES // r_pad
+        kmax = max(1, max(len(entries[i]) for i in sel))
+        K = -(-kmax // p)
+        slots = np.full((K, LANES), zero_slot, dtype=np.uint16)
+        cols = np.zeros((K, LANES), dtype=np.uint16)
+        for lane in range(LANES):
+            r, part = lane % r_pad, lane // r_pad
+            if r >= nr:
+                cols[:, lane] = rows[sel[0]]
+                continue
+            e = entries[sel[r]][part::p]
+            cols[:, lane] = rows[sel[r]]
+            for k, (s, c) in enumerate(e):
+                slots[k, lane] = s
+                cols[k, lane] = c
+        tiles.append(SlotTile(rows=np.asarray(rows)[sel].astype(np.uint16), r_pad=r_pad, slots=slots, cols=cols))
+    return tiles
+
+
+def build_refactor_tables(F: LDLFactor, K: sp.csc_matrix, n_var: int) -> RefactorTables:
+    nk = K.shape[0]
+    m = nk - n_var
+    perm = F.perm
+    pinv = np.empty(nk, dtype=np.int64); pinv[perm] = np.arange(nk)
+    patt = F.Lpattern
+    # slots of strictly-lower entries, column by column
+    slot = -np.ones((nk, nk), dtype=np.int64)
+    s = nk
+    for j in range(nk):
+        rows = np.nonzero(patt[:, j])[0]
+        slot[rows, j] = np.arange(s, s + len(rows))
+        s += len(rows)
+    n_slots = s + 1
+    assert n_slots < 65536
+    Kp = K.toarray()[np.ix_(perm, perm)]
+    S0 = np.zeros(n_slots)
+    S0[:nk] = np.diag(Kp)
+    ii, jj = np.nonzero(np.tril(Kp, -1))
+    assert (slot[ii, jj] >= 0).all(), 'KKT entry outside the symbolic pattern'
+    S0[slot[ii, jj]] = Kp[ii, jj]
+    rho_slot = pinv[n_var:]
+    S0[rho_slot] = 0.0
+    level = F.level
+    n_levels = int(level.max()) + 1
+    level_ptr, level_cols = [0], []
+    op_ptr, ops = [0], []
+    scale_ptr, scale = [0], []
+    for lv in range(n_levels):
+        cols = np.nonzero(level == lv)[0]
+        level_cols += cols.tolist()
+        level_ptr.append(len(level_cols))
+        for j in cols:
+            rows = np.nonzero(patt[:, j])[0]
+            for a_i, i in enumerate(rows):
+                for k in rows[:a_i + 1]:
+                    t = i if i == k else slot[i, k]          # diagonal slot = position
+                    assert t >= 0
+                    ops.append((t, slot[i, j], slot[k, j], j))
+                scale.append((slot[i, j], j))
+        op_ptr.append(len(ops))
+        scale_ptr.append(len(scale))
+    # triangular solves, one hazard-free group of tiles per level
+    fwd, bwd = [], []
+    for lv in range(1, n_levels):
+        rows = np.nonzero(level == lv)[0]
+        ent = [[(slot[i, j], j) for j in np.nonzero(patt[i, :])[0]] for i in rows]
+        fwd += _slot_tiles(rows, ent, n_slots - 1)
+    for lv in range(n_levels - 1, -1, -1):
+        rows = np.nonzero(level == lv)[0]
+        ent = [[(slot[k, i], k) for k in np.nonzero(patt[:, i])[0]] for i in rows]
+        rows_nz = [r for r, e in zip(rows, ent) if e]
+        ent_nz = [e for e in ent if e]
+        if rows_nz:
+            bwd += _slot_tiles(np.asarray(rows_nz), ent_nz, n_slots - 1)
+    return RefactorTables(nk=nk, n_slots=n_slots, S0=S0, rho_slot=rho_slot.astype(np.int64),
+                          level_ptr=np.asarray(level_ptr), level_cols=np.asarray(level_cols),
+                          op_ptr=np.asarray(op_ptr), ops=np.asarray(ops, dtype=np.int64).reshape(-1, 4),
+                          scale_ptr=np.asarray(scale_ptr), scale=np.asarray(scale, dtype=np.int64).reshape(-1, 2),
+                          fwd_tiles=fwd, bwd_tiles=bwd)
+
+
+def emulate_factor(T: RefactorTables, rho_vec: np.ndarray) -> np.ndarray:
+    """numpy emulation of the kernel's numeric factorisation; returns S with Dinv on the diagonal slots."""
+    S = T.S0.copy()
+    S[T.rho_slot] = -1.0 / rho_vec
+    for lv in range(len(T.level_ptr) - 1):
+        cols = T.level_cols[T.level_ptr[lv]:T.level_ptr[lv + 1]]
+        S[cols] = 1.0 / S[cols]
+        o = T.ops[T.op_ptr[lv]:T.op_ptr[lv + 1]]
+        if len(o):
+            np.subtract.at(S, o[:, 0], S[o[:, 1]] * S[o[:, 2]] * S[o[:, 3]])
+        sc = T.scale[T.scale_ptr[lv]:T.scale_ptr[lv + 1]]
+        if len(sc):
+            S[sc[:, 0]] *= S[sc[:, 1]]
+    return S
+
+
+def emulate_solve(T: RefactorTables, S: np.ndarray, w: np.ndarray) -> np.ndarray:
+    """w in pivot positions -> K^{-1} w (pivot positions), using the slot tiles."""
+    w = np.array(w, dtype=float, copy=True)
+
+    def run(tile, sign_update):
+        acc = np.zeros(LANES)
+        for k in range(tile.slots.shape[0]):
+            acc += S[tile.slots[k].astype(int)] * w[tile.cols[k].astype(int)]
+        off = LANES // 2
+        while off >= tile.r_pad:
+            acc = acc + acc[np.arange(LANES) ^ off]
+            off //= 2
+        return acc[:len(tile.rows)]
+    for t in T.fwd_tiles:                         # w_i -= sum_j L_ij w_j
+        r = t.rows.astype(int)
+        w[r] = w[r] - run(t, -1)
+    w[:T.nk] *= S[:T.nk]                          # D^{-1}
+    for t in T.bwd_tiles:                         # w_i -= sum_k L_ki w_k
+        r = t.rows.astype(int)
+        w[r] = w[r] - run(t, -1)
+    return w

@@ -196,6 +196,21 @@ class Module:
         info = SimpleNamespace(obj_val=obj, iter=it, status=st, pri_res=pri, dua_res=dua, time=t1 - t0)
         return SimpleNamespace(cpg_prim=pr, cpg_dual=du, cpg_info=info, prim=prim, dual=dual, sol_x=solx, sol_y=soly)
 
+    def solve_batch_pinned(self, params, out, x0=None, y0=None):
+        """Host-buffer entry on caller-owned (ideally pinned) torch CPU tensors: no allocation, no copies on the
+        Python side.  out: dict with prim, dual, obj, pri, dua (float64) and it, st (int32) tensors."""
+        self.init()
+        B = params.shape[0]
+        ptr = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+        s = self.settings
+        if x0 is not None and y0 is not None:
+            s = CpgB200Settings.from_buffer_copy(bytes(self.settings)); s.warm_start = 1
+        self._check(self._fn('cpg_solve_batch_host')(C.c_int(B), ptr(params), ptr(x0), ptr(y0), ptr(out.get('prim')),
+                                                     ptr(out.get('dual')), ptr(out.get('sol_x')), ptr(out.get('sol_y')),
+                                                     ptr(out['obj']), ptr(out['it']), ptr(out['st']), ptr(out['pri']),
+                                                     ptr(out['dua']), C.byref(s)))
+        return out
+
     # ---- NEW: batched solve on torch CUDA tensors already resident in HBM (asynchronous on the current stream)
     def solve_batch_device(self, params, x0=None, y0=None, out=None, return_canonical=False):
         import torch
