@@ -1,4 +1,5 @@
-// admm_kernel.cuh -- batched ADMM (OSQP-style) QP solver for sm_100a, one problem instance per warp.
+// admm_kernel.cuh -- shared device helpers + the one-instance-per-warp ADMM solver used by the TAIL kernel
+// (per-instance KKT factor).  The main kernel (two instances per warp) is admm_pair_kernel.cuh.
 //
 // Hand-written device code shared by every generated problem family; the generator emits
 // only compile-time sizes (cpg_family.h), the blob-header struct (cpg_blob_layout.h) and the
@@ -113,65 +114,6 @@ __device__ __forceinline__ double ell_dot(const int* tab, const double* F64, con
   if (k < K) a0 = fma(v[k * LANES], vec[c[k * LANES]], a0);
   return a0 + a1;
 }
-
-// one schedule tile: every lane accumulates its slice of a row, rows spread over 32/r_pad lanes
-__device__ __forceinline__ double tile_acc(const int4 h0, const double* F64, const uint16_t* U16,
-                                           const double* w, int lane) {
-  const double* v = F64 + h0.x + lane;
-  const uint16_t* c = U16 + h0.y + lane;
-  const int K = h0.z;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int k = 0;
-  for (; k + 3 < K; k += 4) {
-    a0 = fma(v[(k + 0) * LANES], w[c[(k + 0) * LANES]], a0);
-    a1 = fma(v[(k + 1) * LANES], w[c[(k + 1) * LANES]], a1);
-    a2 = fma(v[(k + 2) * LANES], w[c[(k + 2) * LANES]], a2);
-    a3 = fma(v[(k + 3) * LANES], w[c[(k + 3) * LANES]], a3);
-  }
-  for (; k < K; ++k) a0 = fma(v[k * LANES], w[c[k * LANES]], a0);
-  double acc = (a0 + a1) + (a2 + a3);
-  for (int o = 16; o >= h0.w; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-  return acc;
-}
-
-// K x = b in pivot order, in place in w (a6).  Forward tiles, dense trailing block, backward tiles.
-template <int TRAIL>
-__device__ __forceinline__ void kkt_solve(const CpgBlobHeader* H, const int* I32, const double* F64,
-                                          const uint16_t* U16, double* w, int lane) {
-  const int4* T = reinterpret_cast<const int4*>(I32 + H->i_tiles);
-  const int nf = H->n_fwd_tiles, nt = H->n_tiles;
-  int t = 0;
-  for (; t < nf; ++t) {
-    const int4 h0 = T[2 * t], h1 = T[2 * t + 1];
-    const double acc = tile_acc(h0, F64, U16, w, lane);
-    __syncwarp();
-    if (lane < h1.x) w[U16[h1.y + lane]] = acc;
-    __syncwarp();
-  }
-  if (TRAIL > 0) {           // all trailing tiles read the whole block: gather everything, then write
-    double tacc[TRAIL > 0 ? TRAIL : 1];
-#pragma unroll
-    for (int j = 0; j < TRAIL; ++j) tacc[j] = (j < H->n_trail_tiles) ? tile_acc(T[2 * (t + j)], F64, U16, w, lane) : 0.0;
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < TRAIL; ++j) {
-      if (j < H->n_trail_tiles) {
-        const int4 h1 = T[2 * (t + j) + 1];
-        if (lane < h1.x) w[U16[h1.y + lane]] = tacc[j];
-      }
-    }
-    __syncwarp();
-    t += H->n_trail_tiles;
-  }
-  for (; t < nt; ++t) {
-    const int4 h0 = T[2 * t], h1 = T[2 * t + 1];
-    const double acc = tile_acc(h0, F64, U16, w, lane);
-    __syncwarp();
-    if (lane < h1.x) w[U16[h1.y + lane]] = acc;
-    __syncwarp();
-  }
-}
-
 
 // ---------------------------------------------------------------- tail path: per-instance numeric LDL' (a9)
 // Tables built by offline/refactor.py; they live in GLOBAL memory (L2-resident, shared by all tail warps).
@@ -549,8 +491,7 @@ __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* _
 #pragma unroll
       for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) w[pz[k]] = s.z[k] - rinv_of(k) * s.y[k]; }
       __syncwarp();
-      if (TAIL) tail_solve(ta->tv, ta->S, w, lane);
-      else kkt_solve<Fam::TRAIL>(H, I32, F64, U16, w, lane);
+      tail_solve(ta->tv, ta->S, w, lane);
       // update_x, update_z (+project), update_y (auxil.c:185-225)
 #pragma unroll
       for (int k = 0; k < NXL; ++k) {
@@ -664,38 +605,6 @@ __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* _
     else obj = (H->is_max ? -1.0 : 1.0) * (obj + H->d_const);   // cpg_retrieve_info, cvxpygen/utils.py:980
     io.obj_val[b] = obj; io.iter[b] = it; io.status[b] = status;
     io.pri_res[b] = s.pri_res; io.dua_res[b] = s.dua_res;
-  }
-}
-
-// ---------------------------------------------------------------- persistent kernel
-template <class Fam>
-__global__ void __launch_bounds__(Fam::WARPS * 32, 1)
-admm_batch_kernel(const uint8_t* __restrict__ blob_g, const BatchIO io, const Settings st) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t total = reinterpret_cast<const CpgBlobHeader*>(blob_g)->total_bytes;
-  if (tid == 0) mbar_init(&bar, 1);
-  __syncthreads();
-  if (tid == 0) {                      // stage the constants blob with TMA bulk copies
-    mbar_expect_tx(&bar, total);
-    constexpr uint32_t CHUNK = 32768;
-    for (uint32_t off = 0; off < total; off += CHUNK)
-      tma_bulk_g2s(smem + off, blob_g + off, (total - off < CHUNK) ? (total - off) : CHUNK, &bar);
-  }
-  mbar_wait(&bar, 0);
-  const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(smem);
-  const int* I32 = reinterpret_cast<const int*>(smem + H->off_i32);
-  const double* F64 = reinterpret_cast<const double*>(smem + H->off_f64);
-  const uint16_t* U16 = reinterpret_cast<const uint16_t*>(smem + H->off_u16);
-  double* w = reinterpret_cast<double*>(smem + Fam::BLOB_BYTES_PAD) + (size_t)warp * Fam::W_STRIDE;
-  for (;;) {
-    unsigned b = 0;
-    if (lane == 0) b = atomicAdd(io.work_counter, 1u);
-    b = __shfl_sync(FULL, b, 0);
-    if (b >= (unsigned)io.B) break;
-    solve_instance<Fam, false>(H, I32, F64, U16, w, lane, (int)b, io, st, nullptr);
-    __syncwarp();
   }
 }
 

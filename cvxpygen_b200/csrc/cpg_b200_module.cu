@@ -10,7 +10,7 @@
 #include "cpg_family.h"
 #include "cpg_b200.h"
 #include "cpg_blob_layout.h"
-#include "admm_kernel.cuh"
+#include "admm_pair_kernel.cuh"
 
 extern "C" const unsigned long long CPG_B200_FN(cpg_blob_words)[];
 extern "C" const unsigned int CPG_B200_FN(cpg_blob_nbytes);
@@ -27,8 +27,9 @@ struct Fam {
   static constexpr int W_STRIDE = CPG_FAM_W_STRIDE;       // doubles per warp work vector
   static constexpr int S_STRIDE = CPG_FAM_S_STRIDE;       // doubles per warp factor storage (tail kernel)
   static constexpr int TAIL_WARPS = CPG_FAM_TAIL_WARPS;
+  static constexpr int PAIR_STRIDE = CPG_FAM_PAIR_STRIDE; // doubles per warp in the pair kernel: interleaved w + batched-row slots
 };
-constexpr int SMEM_BYTES = Fam::BLOB_BYTES_PAD + Fam::WARPS * Fam::W_STRIDE * 8;
+constexpr int SMEM_BYTES = Fam::BLOB_BYTES_PAD + Fam::WARPS * Fam::PAIR_STRIDE * 8;
 constexpr int TAIL_SMEM_BYTES = Fam::BLOB_BYTES_PAD + Fam::TAIL_WARPS * (Fam::W_STRIDE + Fam::S_STRIDE) * 8;
 constexpr int TAIL_WORDS = Fam::N + 2 * Fam::M + 2;
 
@@ -151,7 +152,7 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
   CK(cudaFuncSetAttribute(cpgb200::admm_tail_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM_BYTES));
   if (!g.d_counter) CK(cudaMalloc(&g.d_counter, sizeof(unsigned int)));
   if (!g.d_tail_count) CK(cudaMalloc(&g.d_tail_count, sizeof(int)));
-  CK(cudaFuncSetAttribute(cpgb200::admm_batch_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CK(cudaFuncSetAttribute(cpgb200::admm_pair_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   g.ready = true;
   return CPG_B200_OK;
 }
@@ -194,9 +195,9 @@ int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const doubl
   CK(cudaMemsetAsync(g.d_counter, 0, sizeof(unsigned int), stream));
   CK(cudaMemsetAsync(g.d_tail_count, 0, sizeof(int), stream));
   int grid = g.n_sm;
-  const int need = (B + Fam::WARPS - 1) / Fam::WARPS;
+  const int need = (B + 2 * Fam::WARPS - 1) / (2 * Fam::WARPS);
   if (grid > need) grid = need;
-  cpgb200::admm_batch_kernel<Fam><<<grid, Fam::WARPS * 32, SMEM_BYTES, stream>>>(g.d_blob, io, st);
+  cpgb200::admm_pair_kernel<Fam><<<grid, Fam::WARPS * 32, SMEM_BYTES, stream>>>(g.d_blob, io, st);
   g.launches += 1;
   CK(cudaGetLastError());
   // instances that changed rho (or a constraint type) continue with their own factor; the kernel exits at once

@@ -34,7 +34,13 @@ HEADER_FIELDS: List[Tuple[str, str]] = [
     ('int', 'f_qbase'), ('int', 'f_lbase'), ('int', 'f_ubase'), ('int', 'pad_f0'),
     # uint16-area indices
     ('int', 'h_pinvx'), ('int', 'h_pinvz'), ('int', 'h_ctype'), ('int', 'h_prim'),
-    ('int', 'h_dual'), ('int', 'pad_h0'), ('int', 'pad_h1'), ('int', 'pad_h2'),
+    ('int', 'h_dual'), ('int', 'n_bq'), ('int', 'n_bc'), ('int', 'nb_slots'),
+    # two-instances-per-warp kernel: encoded tiles, scaled base vectors, accessor tables, batched-row maps
+    ('int', 'i_tiles2'), ('int', 'f_qs'), ('int', 'f_ls'), ('int', 'f_us'),
+    ('int', 'i_addr_q'), ('int', 'i_addr_l'), ('int', 'i_addr_u'), ('int', 'h_bq_row'),
+    ('int', 'h_bc_row'), ('int', 'i_bq_ptr'), ('int', 'i_bl_ptr'), ('int', 'i_bu_ptr'),
+    ('int', 'h_bq_col'), ('int', 'h_bl_col'), ('int', 'h_bu_col'), ('int', 'f_bq_val'),
+    ('int', 'f_bl_val'), ('int', 'f_bu_val'), ('int', 'pad_v0'), ('int', 'pad_v1'),
     ('double', 'sigma'), ('double', 'rho'), ('double', 'c'), ('double', 'cinv'),
     ('double', 'd_const'), ('double', 'reserved0'),
 ]
@@ -109,16 +115,30 @@ def pack_blob(*, n, m, perm, schedule, Ps_upper, As, D, E, c, sigma, rho, ctype,
     nk = n + m
     ar = _Areas()
     pinv = np.empty(nk, dtype=np.int64); pinv[np.asarray(perm)] = np.arange(nk)
-    # --- tiles
+    # --- KKT-solve tiles, encoded for the pair kernel (sparse gather / dense broadcast; offline/schedule.py)
+    from .schedule import encode_best
     tile_tab = []
+    tile_info, encodings = [], []
     for t in schedule.tiles:
-        f = ar.add_f64(t.vals)
-        h = ar.add_u16(t.cols)
+        e = encode_best(t, nk)
+        encodings.append(e)
+        f = ar.add_f64(e['vals'])
         hr = ar.add_u16(np.concatenate([t.rows, np.zeros(LANES - len(t.rows), dtype=np.uint16)]))
-        tile_tab += [f, h, t.K, t.r_pad, len(t.rows), hr, 0, 0]
+        if e['kind'] == 0:
+            # packed words hold BYTE offsets into the interleaved pair vector (pos * 16 < 65536)
+            words = np.asarray(e['cols32'], dtype=np.uint32)
+            words = ((words & 0xffff) * 16) | (((words >> 16) * 16) << 16)
+            assert nk * 16 < 65536
+            aux = ar.add_i32(words.astype(np.uint32).view(np.int32))
+            tile_tab += [0, f, aux, e['K'], t.r_pad, len(t.rows), hr, 0]
+        else:
+            aux = ar.add_i32(np.asarray(e['segs'], dtype=np.int64).ravel())
+            tile_tab += [1, f, aux, e['K'], t.r_pad, len(t.rows), hr, len(e['segs'])]
+        tile_info.append(dict(f64=f, aux=aux, rows=hr))
     while len(ar.i32) % 4:
         ar.i32.append(0)
-    i_tiles = ar.add_i32(tile_tab)
+    i_tiles2 = ar.add_i32(tile_tab if tile_tab else [0] * 8)
+    i_tiles = i_tiles2
     # --- residual operators (scaled data): A (rows), A' (rows = variables), full symmetric P
     As = sp.csr_matrix(As)
     Pfull = sp.csr_matrix(Ps_upper + sp.triu(Ps_upper, 1).T)
@@ -131,6 +151,40 @@ def pack_blob(*, n, m, perm, schedule, Ps_upper, As, D, E, c, sigma, rho, ctype,
     i_Mq = _add_ell(ar, ell_row_blocks(Mq_b, n))
     i_Ml = _add_ell(ar, ell_row_blocks(Ml_b, m))
     i_Mu = _add_ell(ar, ell_row_blocks(Mu_b, m))
+    D = np.asarray(D, dtype=float); E = np.asarray(E, dtype=float)
+    Mq_c, Ml_c, Mu_c = sp.csr_matrix(Mq_b), sp.csr_matrix(Ml_b), sp.csr_matrix(Mu_b)
+    bq_rows = np.nonzero(np.diff(Mq_c.indptr))[0] if npb else np.zeros(0, dtype=int)
+    bc_rows = np.nonzero(np.diff(Ml_c.indptr) + np.diff(Mu_c.indptr))[0] if npb else np.zeros(0, dtype=int)
+    n_bq, n_bc = len(bq_rows), len(bc_rows)
+    f_qs = ar.add_f64((D * np.asarray(q_base)) * c)
+    f_ls = ar.add_f64(E * np.clip(l_base, -1e30, 1e30))
+    f_us = ar.add_f64(E * np.clip(u_base, -1e30, 1e30))
+
+    def addr_table(f_base, nrows, brow, slot0, stride):
+        tab = np.array([f_base + r for r in range(nrows)], dtype=np.int64)          # >= 0: index into the f64 area
+        for k, r in enumerate(brow):
+            tab[r] = -(slot0 + stride * k) - 1                                      # < 0: per-warp slot of a batched row
+        return tab
+    # per-warp slots: [q rows][l rows][u rows], each slot holds the value for the two instances of the warp
+    addr_q = addr_table(f_qs, n, bq_rows, 0, 1)
+    addr_l = addr_table(f_ls, m, bc_rows, n_bq, 1)
+    addr_u = addr_table(f_us, m, bc_rows, n_bq + n_bc, 1)
+
+    def csr_rows(M, rows):
+        ptr, cols, vals = [0], [], []
+        for r in rows:
+            s_, e_ = M.indptr[r], M.indptr[r + 1]
+            cols += M.indices[s_:e_].tolist(); vals += M.data[s_:e_].tolist(); ptr.append(len(cols))
+        return ptr, cols, vals
+    pq, cq, vq = csr_rows(Mq_c, bq_rows)
+    pl, cl, vl = csr_rows(Ml_c, bc_rows)
+    pu, cu, vu = csr_rows(Mu_c, bc_rows)
+    v2 = dict(i_tiles2=i_tiles2, n_bq=n_bq, n_bc=n_bc, nb_slots=n_bq + 2 * n_bc, f_qs=f_qs, f_ls=f_ls, f_us=f_us,
+              i_addr_q=ar.add_i32(addr_q), i_addr_l=ar.add_i32(addr_l), i_addr_u=ar.add_i32(addr_u),
+              h_bq_row=ar.add_u16(bq_rows), h_bc_row=ar.add_u16(bc_rows),
+              i_bq_ptr=ar.add_i32(pq), i_bl_ptr=ar.add_i32(pl), i_bu_ptr=ar.add_i32(pu),
+              h_bq_col=ar.add_u16(cq), h_bl_col=ar.add_u16(cl), h_bu_col=ar.add_u16(cu),
+              f_bq_val=ar.add_f64(vq), f_bl_val=ar.add_f64(vl), f_bu_val=ar.add_f64(vu))
     hv = dict(magic=MAGIC, n=n, m=m, nk=nk, npb=npb, n_prim=len(prim_idx), n_dual=len(dual_idx),
               n_tiles=len(schedule.tiles), n_fwd_tiles=schedule.n_fwd_tiles,
               n_trail_tiles=schedule.n_trailing_tiles, is_max=int(is_max),
@@ -142,6 +196,7 @@ def pack_blob(*, n, m, perm, schedule, Ps_upper, As, D, E, c, sigma, rho, ctype,
               h_ctype=ar.add_u16(np.asarray(ctype) + 1),      # stored as 0 loose / 1 ineq / 2 eq
               h_prim=ar.add_u16(prim_idx), h_dual=ar.add_u16(dual_idx),
               sigma=sigma, rho=rho, c=c, cinv=1.0 / c, d_const=d_const)
+    hv.update(v2)
     hdr_len = len(_pack_header(hv))
 
     def pad16(b: bytes) -> bytes:
@@ -155,6 +210,9 @@ def pack_blob(*, n, m, perm, schedule, Ps_upper, As, D, E, c, sigma, rho, ctype,
     hv['total_bytes'] = hv['off_u16'] + len(u16b)
     blob = _pack_header(hv) + i32b + f64b + u16b
     assert len(blob) == hv['total_bytes'] and len(blob) % 16 == 0
+    from .emit_solve import emit_kkt_solve
+    pack_blob.last_solve_source = emit_kkt_solve(schedule, encodings, tile_info)
+    pack_blob.last_header = dict(hv)
     return blob
 
 

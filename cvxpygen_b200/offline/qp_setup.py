@@ -43,6 +43,7 @@ class QPSetup:
     blob: bytes = b''
     tail_blob: bytes = b''
     refactor: Optional[RefactorTables] = None
+    solve_source: str = ''
     theta_shared: Optional[np.ndarray] = None
     batch_cols: Optional[np.ndarray] = None
     stats: Dict[str, float] = field(default_factory=dict)
@@ -104,11 +105,16 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
                      c=sc['c'], sigma=sigma, rho=rho, ctype=ctype, q_base=q_base, l_base=l_base, u_base=u_base,
                      Mq_b=Mq_b, Ml_b=Ml_b, Mu_b=Mu_b, npb=npb, prim_idx=prim_idx, dual_idx=dual_idx,
                      d_const=d_const, is_max=fam.is_maximization)
+    solve_source = pack_blob.last_solve_source
     RT = build_refactor_tables(F, K, n)
     tail_blob = pack_tail_blob(RT)
-    st = dict(nnz_L=F.nnz, tail_blob_bytes=len(tail_blob), refactor_ops=len(RT.ops), n_levels=int(F.level.max()) + 1, n_tiles=len(S.tiles), schedule_cost=S.model_cost,
+    import struct as _struct
+    from .blob import HEADER_FIELDS as _HF
+    _hdr = dict(zip([n_ for _, n_ in _HF], _struct.unpack('<' + ''.join('i' if t_ == 'int' else 'd' for t_, _ in _HF),
+                                                            blob[:_struct.calcsize('<' + ''.join('i' if t_ == 'int' else 'd' for t_, _ in _HF))])))
+    st = dict(nb_slots=int(_hdr['nb_slots']), nnz_L=F.nnz, tail_blob_bytes=len(tail_blob), refactor_ops=len(RT.ops), n_levels=int(F.level.max()) + 1, n_tiles=len(S.tiles), schedule_cost=S.model_cost,
               schedule_entries=S.n_entries, blob_bytes=len(blob))
     return QPSetup(family=fam, batch_params=list(batch_params), n=n, m=m, npb=npb, rho=rho, sigma=sigma,
                    scaling=scaling, D=sc['D'], E=sc['E'], c=sc['c'], ctype=ctype, P_scaled=sc['P'],
-                   A_scaled=sc['A'], factor=F, schedule=S, prim_idx=prim_idx, dual_idx=dual_idx, blob=blob, tail_blob=tail_blob, refactor=RT,
+                   A_scaled=sc['A'], factor=F, schedule=S, prim_idx=prim_idx, dual_idx=dual_idx, blob=blob, tail_blob=tail_blob, refactor=RT, solve_source=solve_source,
                    theta_shared=theta0, batch_cols=bcols, stats=st)

@@ -52,6 +52,8 @@ class Tile:
     r_pad: int            # power of two >= nrows; lane -> (row = lane % r_pad, part = lane // r_pad)
     cols: np.ndarray      # (K, 32) uint16 column positions (padding points at a harmless address, coeff 0)
     vals: np.ndarray      # (K, 32) float64
+    row_cols: list = None # per row: sorted column positions of the non-zero coefficients
+    row_vals: list = None # per row: the coefficients
 
     @property
     def K(self):
@@ -101,7 +103,9 @@ def _make_tiles(rows: np.ndarray, M: np.ndarray, col_pos: np.ndarray, decreasing
             cols[:len(c), lane] = col_pos[c]
             vals[:len(c), lane] = M[sel[r], c]
             cols[len(c):, lane] = rows[sel[r]]
-        tiles.append(Tile(rows=np.asarray(rows)[sel].astype(np.uint16), r_pad=r_pad, cols=cols, vals=vals))
+        tiles.append(Tile(rows=np.asarray(rows)[sel].astype(np.uint16), r_pad=r_pad, cols=cols, vals=vals,
+                          row_cols=[np.asarray(col_pos)[c].astype(np.int64) for c in nz],
+                          row_vals=[M[i, c].copy() for i, c in zip(sel, nz)]))
     return tiles
 
 
@@ -244,3 +248,109 @@ def build_schedule(F: LDLFactor, max_group_rows: int = 64, allow_trailing: bool 
         tiles += _make_tiles(rows, M, cp, decreasing=False)
     return SolveSchedule(tiles=tiles, n=n, n_fwd_tiles=n_fwd, n_trailing_tiles=n_trail,
                          trailing_start=s, model_cost=best)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Device encodings of a tile for the two-instances-per-warp kernel (admm_pair_kernel.cuh)
+#   sparse: lane-interleaved ELL, column indices packed two per 32-bit word; every lane gathers its own w entry
+#   dense : the union of the rows' columns is covered by a few contiguous column segments; all lanes of a
+#           row-part read the SAME w address at each step (shared-memory broadcast), no index loads at all.
+SPARSE_STEP_WF = 9.0     # shared-memory wavefronts per inner step (2 val + 0.5 idx + ~6.5 gather of 16-byte pairs)
+DENSE_STEP_WF = 3.0      # 2 val + 1 broadcast
+DENSE_SEG_OVERHEAD = 1.0
+
+
+def encode_sparse(t: Tile):
+    p = LANES // t.r_pad
+    nr = len(t.rows)
+    kmax = max(1, max(len(c) for c in t.row_cols))
+    K = -(-kmax // p)
+    K += K % 2                                     # pairs of steps share one packed index word
+    cols = np.zeros((K, LANES), dtype=np.int64)
+    vals = np.zeros((K, LANES))
+    for lane in range(LANES):
+        r, part = lane % t.r_pad, lane // t.r_pad
+        if r >= nr:
+            continue
+        c = t.row_cols[r][part::p]; v = t.row_vals[r][part::p]
+        cols[:len(c), lane] = c; vals[:len(c), lane] = v
+    # padding entries (coefficient 0) copy the address of another lane of the same step: a broadcast, never a conflict
+    for k in range(K):
+        used = cols[k][vals[k] != 0]
+        fill = used[0] if len(used) else int(t.rows[0])
+        cols[k][vals[k] == 0] = fill
+    packed = (cols[0::2] | (cols[1::2] << 16)).astype(np.uint32)
+    return dict(kind=0, K=K, vals=vals, cols32=packed, cost=K * SPARSE_STEP_WF)
+
+
+def encode_dense(t: Tile, max_gap: int = 3):
+    p = LANES // t.r_pad
+    nr = len(t.rows)
+    used = np.unique(np.concatenate([c for c in t.row_cols if len(c)])) if any(len(c) for c in t.row_cols) else np.array([int(t.rows[0])])
+    segs = []                                      # (c0, width)
+    c0 = prev = int(used[0])
+    for c in used[1:]:
+        c = int(c)
+        if c - prev > max_gap * p:
+            segs.append((c0, prev - c0 + 1)); c0 = c
+        prev = c
+    segs.append((c0, prev - c0 + 1))
+    dense = {}
+    for r in range(nr):
+        for c, v in zip(t.row_cols[r], t.row_vals[r]):
+            dense[(r, int(c))] = v
+    seg_tab, blocks, steps = [], [], 0
+    for c0, W in segs:
+        Kp = -(-W // p)
+        vals = np.zeros((Kp, LANES))
+        for lane in range(LANES):
+            r, part = lane % t.r_pad, lane // t.r_pad
+            if r >= nr:
+                continue
+            for k in range(Kp):
+                vals[k, lane] = dense.get((r, c0 + part + p * k), 0.0)
+        seg_tab.append((c0, Kp)); blocks.append(vals); steps += Kp
+    return dict(kind=1, segs=seg_tab, vals=np.concatenate(blocks, axis=0), K=steps,
+                cost=steps * DENSE_STEP_WF + len(segs) * DENSE_SEG_OVERHEAD, n_addr=int(used.max()) + p)
+
+
+def encode_best(t: Tile, nk: int):
+    sp_, de = encode_sparse(t), encode_dense(t)
+    # a dense segment may read up to p-1 addresses past its last used column: they must exist
+    if de['cost'] < sp_['cost'] and max(c0 + (LANES // t.r_pad) * Kp for c0, Kp in de['segs']) <= nk:
+        return de
+    return sp_
+
+
+def apply_encoded(sched: 'SolveSchedule', enc: list, w: np.ndarray) -> np.ndarray:
+    """Host emulation of the pair kernel's tile executor on the ENCODED tiles (single right-hand side)."""
+    w = np.array(w, dtype=float, copy=True)
+    deferred = []
+    lanes = np.arange(LANES)
+    for it, (t, e) in enumerate(zip(sched.tiles, enc)):
+        p = LANES // t.r_pad
+        acc = np.zeros(LANES)
+        if e['kind'] == 0:
+            for k in range(e['K']):
+                cc = e['cols32'][k // 2]
+                c = (cc & 0xffff) if k % 2 == 0 else (cc >> 16)
+                acc += e['vals'][k] * w[c.astype(int)]
+        else:
+            row0 = 0
+            part = lanes // t.r_pad
+            for c0, Kp in e['segs']:
+                for k in range(Kp):
+                    acc += e['vals'][row0 + k] * w[c0 + part + p * k]
+                row0 += Kp
+        off = LANES // 2
+        while off >= t.r_pad:
+            acc = acc + acc[lanes ^ off]
+            off //= 2
+        if sched.n_fwd_tiles <= it < sched.n_fwd_tiles + sched.n_trailing_tiles:
+            deferred.append((t, acc))
+            if it == sched.n_fwd_tiles + sched.n_trailing_tiles - 1:
+                for td, ad in deferred:
+                    w[td.rows.astype(int)] = ad[:len(td.rows)]
+            continue
+        w[t.rows.astype(int)] = acc[:len(t.rows)]
+    return w
