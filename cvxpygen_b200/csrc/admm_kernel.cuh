@@ -633,7 +633,7 @@ admm_tail_kernel(const uint8_t* __restrict__ blob_g, const uint8_t* __restrict__
   const int* I32 = reinterpret_cast<const int*>(smem + H->off_i32);
   const double* F64 = reinterpret_cast<const double*>(smem + H->off_f64);
   const uint16_t* U16 = reinterpret_cast<const uint16_t*>(smem + H->off_u16);
-  double* wbase = reinterpret_cast<double*>(smem + Fam::BLOB_BYTES_PAD) + (size_t)warp * (Fam::W_STRIDE + Fam::S_STRIDE);
+  double* wbase = reinterpret_cast<double*>(smem + Fam::CBLOB_BYTES_PAD) + (size_t)warp * (Fam::W_STRIDE + Fam::S_STRIDE);
   TailArgs ta;
   ta.tv = make_tail_view(tail_blob_g);
   ta.S = wbase + Fam::W_STRIDE;

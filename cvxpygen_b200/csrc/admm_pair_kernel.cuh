@@ -151,38 +151,31 @@ __device__ void solve_pairs(const CpgBlobHeader* __restrict__ H, const int* __re
   const double rinv_in = 1.0 / rho_in, rinv_eq = 1.0 / rho_eq, rinv_loose = 1.0 / RHO_MIN;
 
   // ---- per-lane constants of the family (identical for every instance)
-  int px[NXL], pz[NZLs];
-  int qa[NXL], la[NZLs], ua[NZLs];   // index (in doubles, relative to F64) of q_i / l_j / u_j of slot 0
-  const int bvi = (int)(bv - F64);   // the per-warp batched-row table lives in the same shared-memory array
-  unsigned qb = 0u, cb = 0u;                                               // bit k: the row is a batched one (slot 1 at +8 bytes)
+  // Pivot positions and the q/l/u accessor tables are read from the blob when needed (they would cost 30 registers).
+  // addr tables: >= 0 index into the F64 area (row constant over the batch); < 0 -(slot+1) in the per-warp table bv.
+  const uint16_t* PX = U16 + H->h_pinvx + lane;
+  const uint16_t* PZ = U16 + H->h_pinvz + lane;
+  const int* AQ = I32 + H->i_addr_q + lane;
+  const int* AL = I32 + H->i_addr_l + lane;
+  const int* AU = I32 + H->i_addr_u + lane;
   unsigned eqmask = 0u, loosemask = 0u;
-#pragma unroll
-  for (int k = 0; k < NXL; ++k) {
-    const int i = lane + 32 * k;
-    px[k] = 0; qa[k] = 0;
-    if (i < N) {
-      px[k] = U16[H->h_pinvx + i];
-      const int a = I32[H->i_addr_q + i];
-      if (a >= 0) qa[k] = a; else { qa[k] = bvi + 2 * (-a - 1); qb |= 1u << k; }
-    }
-  }
 #pragma unroll
   for (int k = 0; k < NZL; ++k) {
     const int j = lane + 32 * k;
-    pz[k] = 0; la[k] = 0; ua[k] = 0;
     if (j < M) {
-      pz[k] = U16[H->h_pinvz + j];
-      const int al = I32[H->i_addr_l + j], au = I32[H->i_addr_u + j];
-      if (al >= 0) la[k] = al; else { la[k] = bvi + 2 * (-al - 1); cb |= 1u << k; }
-      if (au >= 0) ua[k] = au; else { ua[k] = bvi + 2 * (-au - 1); }
       const int ct = U16[H->h_ctype + j];
       if (ct == 2) eqmask |= 1u << k;
       if (ct == 0) loosemask |= 1u << k;
     }
   }
-  auto q_of = [&](int k, int s) __attribute__((always_inline)) -> double { return F64[qa[k] + (((qb >> k) & 1u) ? s : 0)]; };
-  auto l_of = [&](int k, int s) __attribute__((always_inline)) -> double { return F64[la[k] + (((cb >> k) & 1u) ? s : 0)]; };
-  auto u_of = [&](int k, int s) __attribute__((always_inline)) -> double { return F64[ua[k] + (((cb >> k) & 1u) ? s : 0)]; };
+  auto tab2 = [&](const int* T, int k) __attribute__((always_inline)) -> double2 {   // value of slots 0 and 1
+    const int a = T[32 * k];
+    if (a >= 0) { const double v = F64[a]; return make_double2(v, v); }
+    return lds2(bv + 2 * (-a - 1));
+  };
+  auto q_of = [&](int k, int s) __attribute__((always_inline)) -> double { return sel(tab2(AQ, k), s); };
+  auto l_of = [&](int k, int s) __attribute__((always_inline)) -> double { return sel(tab2(AL, k), s); };
+  auto u_of = [&](int k, int s) __attribute__((always_inline)) -> double { return sel(tab2(AU, k), s); };
   auto rinv_of = [&](int k) __attribute__((always_inline)) -> double { return ((loosemask >> k) & 1u) ? rinv_loose : (((eqmask >> k) & 1u) ? rinv_eq : rinv_in); };
   auto rho_of = [&](int k) __attribute__((always_inline)) -> double { return ((loosemask >> k) & 1u) ? RHO_MIN : (((eqmask >> k) & 1u) ? rho_eq : rho_in); };
 
@@ -307,17 +300,17 @@ __device__ void solve_pairs(const CpgBlobHeader* __restrict__ H, const int* __re
 #pragma unroll
         for (int k = 0; k < NZL; ++k) {
           const int j = lane + 32 * k;
-          double d = dy[s][k];
-          const double lv = l_of(k, s), uv = u_of(k, s);
-          const bool up_inf = uv > OSQP_INFTY * MIN_SCALING, lo_inf = lv < -OSQP_INFTY * MIN_SCALING;
-          if (up_inf) d = lo_inf ? 0.0 : fmin(d, 0.0);
-          else if (lo_inf) d = fmax(d, 0.0);
-          if (j >= M) d = 0.0;
-          dproj[k] = d;
+          double d = 0.0;
           if (j < M) {
+            d = dy[s][k];
+            const double lv = l_of(k, s), uv = u_of(k, s);
+            const bool up_inf = uv > OSQP_INFTY * MIN_SCALING, lo_inf = lv < -OSQP_INFTY * MIN_SCALING;
+            if (up_inf) d = lo_inf ? 0.0 : fmin(d, 0.0);
+            else if (lo_inf) d = fmax(d, 0.0);
             nd = fmax(nd, fabs(unscale ? Ev[j] * d : d));
             lhs += uv * fmax(d, 0.0) + lv * fmin(d, 0.0);
           }
+          dproj[k] = d;
         }
         nd = warp_max(nd);
         if (nd > DIVISION_TOL) {
@@ -456,6 +449,10 @@ __device__ void solve_pairs(const CpgBlobHeader* __restrict__ H, const int* __re
   };
 
   for (;;) {
+    // All warps of the CTA run the same ~50 KB of straight-line code per iteration; without this barrier they drift
+    // apart and every warp misses the instruction cache on its own (ncu: stall_no_instruction 4.4 cycles/issue).
+    // Iteration counts are multiples of check_termination for every instance, so the warps' check iterations coincide.
+    if (!__syncthreads_or((int)(!exhausted || active[0] || active[1]))) break;
     // ---- refill empty slots from the global queue
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
@@ -496,7 +493,7 @@ __device__ void solve_pairs(const CpgBlobHeader* __restrict__ H, const int* __re
         active[s] = true;
       }
     }
-    if (!active[0] && !active[1]) break;
+    if (!active[0] && !active[1]) continue;    // nothing left for this warp: keep meeting the others at the barrier
 
     // which slots evaluate their residuals after this iteration
     bool chk[2], adp[2];
@@ -514,12 +511,12 @@ __device__ void solve_pairs(const CpgBlobHeader* __restrict__ H, const int* __re
 #pragma unroll
     for (int k = 0; k < NXL; ++k) {
       const int i = lane + 32 * k;
-      if (i < N) sts2(w2 + 2 * px[k], sigma * x[0][k] - q_of(k, 0), sigma * x[1][k] - q_of(k, 1));
+      if (i < N) { const double2 qv = tab2(AQ, k); sts2(w2 + 2 * PX[32 * k], sigma * x[0][k] - qv.x, sigma * x[1][k] - qv.y); }
     }
 #pragma unroll
     for (int k = 0; k < NZL; ++k) {
       const int j = lane + 32 * k;
-      if (j < M) { const double ri = rinv_of(k); sts2(w2 + 2 * pz[k], z[0][k] - ri * y[0][k], z[1][k] - ri * y[1][k]); }
+      if (j < M) { const double ri = rinv_of(k); sts2(w2 + 2 * PZ[32 * k], z[0][k] - ri * y[0][k], z[1][k] - ri * y[1][k]); }
     }
     __syncwarp();
 #ifdef CPG_FAM_GENERATED_SOLVE
@@ -531,7 +528,7 @@ __device__ void solve_pairs(const CpgBlobHeader* __restrict__ H, const int* __re
     for (int k = 0; k < NXL; ++k) {
       const int i = lane + 32 * k;
       if (i < N) {
-        const double2 xt = lds2(w2 + 2 * px[k]);
+        const double2 xt = lds2(w2 + 2 * PX[32 * k]);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           const double xn = alpha * sel(xt, s) + (1.0 - alpha) * x[s][k];
@@ -545,12 +542,13 @@ __device__ void solve_pairs(const CpgBlobHeader* __restrict__ H, const int* __re
       const int j = lane + 32 * k;
       if (j < M) {
         const double ri = rinv_of(k), r = rho_of(k);
-        const double2 nu = lds2(w2 + 2 * pz[k]);
+        const double2 nu = lds2(w2 + 2 * PZ[32 * k]);
+        const double2 lv = tab2(AL, k), uv = tab2(AU, k);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           const double zt = (z[s][k] - ri * y[s][k]) + ri * sel(nu, s);
           const double v = alpha * zt + (1.0 - alpha) * z[s][k];
-          const double zn = fmin(fmax(v + ri * y[s][k], l_of(k, s)), u_of(k, s));
+          const double zn = fmin(fmax(v + ri * y[s][k], sel(lv, s)), sel(uv, s));
           const double d = r * (v - zn);
           dy[s][k] = d;
           y[s][k] += d;

@@ -16,6 +16,8 @@ extern "C" const unsigned long long CPG_B200_FN(cpg_blob_words)[];
 extern "C" const unsigned int CPG_B200_FN(cpg_blob_nbytes);
 extern "C" const unsigned long long CPG_B200_FN(cpg_tail_blob_words)[];
 extern "C" const unsigned int CPG_B200_FN(cpg_tail_blob_nbytes);
+extern "C" const unsigned long long CPG_B200_FN(cpg_cblob_words)[];     // main blob without the tile schedule (tail kernel)
+extern "C" const unsigned int CPG_B200_FN(cpg_cblob_nbytes);
 
 namespace {
 
@@ -24,13 +26,14 @@ struct Fam {
   static constexpr int TRAIL = CPG_FAM_TRAIL_TILES;
   static constexpr int WARPS = CPG_FAM_WARPS;
   static constexpr int BLOB_BYTES_PAD = CPG_FAM_BLOB_BYTES_PAD;
+  static constexpr int CBLOB_BYTES_PAD = CPG_FAM_CBLOB_BYTES_PAD;
   static constexpr int W_STRIDE = CPG_FAM_W_STRIDE;       // doubles per warp work vector
   static constexpr int S_STRIDE = CPG_FAM_S_STRIDE;       // doubles per warp factor storage (tail kernel)
   static constexpr int TAIL_WARPS = CPG_FAM_TAIL_WARPS;
   static constexpr int PAIR_STRIDE = CPG_FAM_PAIR_STRIDE; // doubles per warp in the pair kernel: interleaved w + batched-row slots
 };
 constexpr int SMEM_BYTES = Fam::BLOB_BYTES_PAD + Fam::WARPS * Fam::PAIR_STRIDE * 8;
-constexpr int TAIL_SMEM_BYTES = Fam::BLOB_BYTES_PAD + Fam::TAIL_WARPS * (Fam::W_STRIDE + Fam::S_STRIDE) * 8;
+constexpr int TAIL_SMEM_BYTES = Fam::CBLOB_BYTES_PAD + Fam::TAIL_WARPS * (Fam::W_STRIDE + Fam::S_STRIDE) * 8;
 constexpr int TAIL_WORDS = Fam::N + 2 * Fam::M + 2;
 
 struct Ctx {
@@ -38,6 +41,7 @@ struct Ctx {
   int device = -1, n_sm = 0;
   uint8_t* d_blob = nullptr;
   uint8_t* d_tail_blob = nullptr;
+  uint8_t* d_cblob = nullptr;
   unsigned int* d_counter = nullptr;
   int* d_tail_count = nullptr;
   int* d_tail_ids = nullptr;
@@ -147,6 +151,8 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
   g.device = device; g.n_sm = prop.multiProcessorCount;
   if (!g.d_blob) CK(cudaMalloc(&g.d_blob, Fam::BLOB_BYTES_PAD));
   CK(cudaMemcpy(g.d_blob, CPG_B200_FN(cpg_blob_words), CPG_B200_FN(cpg_blob_nbytes), cudaMemcpyHostToDevice));
+  if (!g.d_cblob) CK(cudaMalloc(&g.d_cblob, Fam::CBLOB_BYTES_PAD));
+  CK(cudaMemcpy(g.d_cblob, CPG_B200_FN(cpg_cblob_words), CPG_B200_FN(cpg_cblob_nbytes), cudaMemcpyHostToDevice));
   if (!g.d_tail_blob) CK(cudaMalloc(&g.d_tail_blob, CPG_B200_FN(cpg_tail_blob_nbytes)));
   CK(cudaMemcpy(g.d_tail_blob, CPG_B200_FN(cpg_tail_blob_words), CPG_B200_FN(cpg_tail_blob_nbytes), cudaMemcpyHostToDevice));
   CK(cudaFuncSetAttribute(cpgb200::admm_tail_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM_BYTES));
@@ -158,7 +164,7 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
 }
 
 int CPG_B200_FN(cpg_b200_free)(void) {
-  void* ptrs[] = {g.d_blob, g.d_tail_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0,
+  void* ptrs[] = {g.d_blob, g.d_cblob, g.d_tail_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0,
                   g.d_prim, g.d_dual, g.d_solx, g.d_soly, g.d_obj, g.d_pri, g.d_dua, g.d_iter, g.d_status};
   for (void* p : ptrs) if (p) cudaFree(p);
   g = Ctx();
@@ -202,7 +208,7 @@ int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const doubl
   CK(cudaGetLastError());
   // instances that changed rho (or a constraint type) continue with their own factor; the kernel exits at once
   // when the hand-off queue is empty (no host round trip to find out)
-  cpgb200::admm_tail_kernel<Fam><<<g.n_sm, Fam::TAIL_WARPS * 32, TAIL_SMEM_BYTES, stream>>>(g.d_blob, g.d_tail_blob, io, st);
+  cpgb200::admm_tail_kernel<Fam><<<g.n_sm, Fam::TAIL_WARPS * 32, TAIL_SMEM_BYTES, stream>>>(g.d_cblob, g.d_tail_blob, io, st);
   g.launches += 1;
   CK(cudaGetLastError());
   return CPG_B200_OK;

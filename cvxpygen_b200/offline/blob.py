@@ -108,7 +108,7 @@ def _add_ell(ar: _Areas, blocks) -> int:
 
 def pack_blob(*, n, m, perm, schedule, Ps_upper, As, D, E, c, sigma, rho, ctype,
               q_base, l_base, u_base, Mq_b, Ml_b, Mu_b, npb, prim_idx, dual_idx,
-              d_const, is_max) -> bytes:
+              d_const, is_max, with_tiles=True) -> bytes:
     """All vectors are in natural (unpermuted) canonical order.  q/l/u_base are the UNSCALED
     canonical vectors with the batched parameters set to zero (shared parameters and constants
     folded in); M*_b are the CSR maps restricted to the batched-parameter columns."""
@@ -119,7 +119,7 @@ def pack_blob(*, n, m, perm, schedule, Ps_upper, As, D, E, c, sigma, rho, ctype,
     from .schedule import encode_best
     tile_tab = []
     tile_info, encodings = [], []
-    for t in schedule.tiles:
+    for t in (schedule.tiles if with_tiles else []):
         e = encode_best(t, nk)
         encodings.append(e)
         f = ar.add_f64(e['vals'])
@@ -210,9 +210,10 @@ def pack_blob(*, n, m, perm, schedule, Ps_upper, As, D, E, c, sigma, rho, ctype,
     hv['total_bytes'] = hv['off_u16'] + len(u16b)
     blob = _pack_header(hv) + i32b + f64b + u16b
     assert len(blob) == hv['total_bytes'] and len(blob) % 16 == 0
-    from .emit_solve import emit_kkt_solve
-    pack_blob.last_solve_source = emit_kkt_solve(schedule, encodings, tile_info)
-    pack_blob.last_header = dict(hv)
+    if with_tiles:
+        from .emit_solve import emit_kkt_solve
+        pack_blob.last_solve_source = emit_kkt_solve(schedule, encodings, tile_info)
+        pack_blob.last_header = dict(hv)
     return blob
 
 

@@ -42,6 +42,7 @@ class QPSetup:
     dual_idx: np.ndarray
     blob: bytes = b''
     tail_blob: bytes = b''
+    blob_compact: bytes = b''
     refactor: Optional[RefactorTables] = None
     solve_source: str = ''
     theta_shared: Optional[np.ndarray] = None
@@ -106,6 +107,11 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
                      Mq_b=Mq_b, Ml_b=Ml_b, Mu_b=Mu_b, npb=npb, prim_idx=prim_idx, dual_idx=dual_idx,
                      d_const=d_const, is_max=fam.is_maximization)
     solve_source = pack_blob.last_solve_source
+    # the tail kernel needs everything but the (large) tile schedule: a compact copy leaves room for more warps
+    blob_compact = pack_blob(n=n, m=m, perm=F.perm, schedule=S, Ps_upper=sc['P'], As=sc['A'], D=sc['D'], E=sc['E'],
+                             c=sc['c'], sigma=sigma, rho=rho, ctype=ctype, q_base=q_base, l_base=l_base, u_base=u_base,
+                             Mq_b=Mq_b, Ml_b=Ml_b, Mu_b=Mu_b, npb=npb, prim_idx=prim_idx, dual_idx=dual_idx,
+                             d_const=d_const, is_max=fam.is_maximization, with_tiles=False)
     RT = build_refactor_tables(F, K, n)
     tail_blob = pack_tail_blob(RT)
     import struct as _struct
@@ -116,5 +122,5 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
               schedule_entries=S.n_entries, blob_bytes=len(blob))
     return QPSetup(family=fam, batch_params=list(batch_params), n=n, m=m, npb=npb, rho=rho, sigma=sigma,
                    scaling=scaling, D=sc['D'], E=sc['E'], c=sc['c'], ctype=ctype, P_scaled=sc['P'],
-                   A_scaled=sc['A'], factor=F, schedule=S, prim_idx=prim_idx, dual_idx=dual_idx, blob=blob, tail_blob=tail_blob, refactor=RT, solve_source=solve_source,
+                   A_scaled=sc['A'], factor=F, schedule=S, prim_idx=prim_idx, dual_idx=dual_idx, blob=blob, tail_blob=tail_blob, blob_compact=blob_compact, refactor=RT, solve_source=solve_source,
                    theta_shared=theta0, batch_cols=bcols, stats=st)
