@@ -105,6 +105,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-sample', type=int, default=40000, help='instances in the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--with-grad', action='store_true', help='also time config 4: forward + backward (gradient=True)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -205,6 +206,22 @@ def main():
     h2d = B * 12 * 8
     d2h = B * ((d.n_prim + d.n_dual) * 8 + 3 * 8 + 2 * 4)
 
+    # ---- optional: BASELINE config 4 (MPC QP with gradient=True): backward pass on the forward solution, device-resident
+    grad_info = None
+    if args.with_grad:
+        outg = mod.solve_batch_device(params, return_canonical=True)
+        dprim = torch.randn((B, d.n_prim), dtype=torch.float64, device=dev)
+        dpar = mod.gradient_batch_device(outg.sol_y, dprim)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(3):
+            dpar = mod.gradient_batch_device(outg.sol_y, dprim, dparams=dpar)
+        g1.record(); torch.cuda.synchronize()
+        ms_b = g0.elapsed_time(g1) / 3
+        grad_info = {'backward_ms': ms_b, 'backward_inst_per_s': B / ms_b * 1e3,
+                     'forward_backward_inst_per_s': B / (ms_step + ms_b) * 1e3}
+
     # ---- solution quality of the last timed step (all ranks' share identical in distribution; rank 0 reports)
     st = out.status.cpu().numpy(); it = out.iter.cpu().numpy()
     frac_solved = float((st == 1).mean())
@@ -232,6 +249,8 @@ def main():
                      'note': 'on-chip design: the kernel is issue/latency bound, not HBM bound (DESIGN.md); '
                              'fp64 fraction = %.4f of 37 TFLOP/s nominal' % (value / world * FLOP_PER_INSTANCE / 37e12)},
     }
+    if grad_info:
+        line['config']['gradient'] = grad_info
     if not args.no_cpu_baseline:
         try:
             ips, _ = run_reference_cpu(args.cpu_sample, cores)

@@ -36,8 +36,8 @@ def generate_code(problem, code_dir='cpg_code', solver=None, solver_opts=None, e
     solver = 'ADMM-CUDA' if solver is None else solver
     if solver.upper() not in SOLVERS:
         raise ValueError(f'Unsupported solver: {solver}.')       # same text as cvxpygen/canonicalizer.py:83
-    if gradient:
-        raise NotImplementedError('gradient=True is not generated by the ADMM-CUDA backend yet')
+    # gradient=True needs nothing extra: every generated library carries the batched backward pass
+    # (cpg_gradient_batch_*); the flag is accepted for signature compatibility with the reference.
     sys.stdout.write('Generating code with cvxpygen_b200 (ADMM-CUDA, sm_100a) ...\n')
     fam = problem if isinstance(problem, CanonFamily) else _canonicalize_with_reference(problem, solver_opts, enable_settings)
     if not fam.params:

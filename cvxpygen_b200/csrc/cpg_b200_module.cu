@@ -11,6 +11,7 @@
 #include "cpg_b200.h"
 #include "cpg_blob_layout.h"
 #include "admm_pair_kernel.cuh"
+#include "grad_kernel.cuh"
 
 extern "C" const unsigned long long CPG_B200_FN(cpg_blob_words)[];
 extern "C" const unsigned int CPG_B200_FN(cpg_blob_nbytes);
@@ -18,6 +19,10 @@ extern "C" const unsigned long long CPG_B200_FN(cpg_tail_blob_words)[];
 extern "C" const unsigned int CPG_B200_FN(cpg_tail_blob_nbytes);
 extern "C" const unsigned long long CPG_B200_FN(cpg_cblob_words)[];     // main blob without the tile schedule (tail kernel)
 extern "C" const unsigned int CPG_B200_FN(cpg_cblob_nbytes);
+extern "C" const unsigned long long CPG_B200_FN(cpg_gblob_words)[];     // backward-pass constants (shared memory)
+extern "C" const unsigned int CPG_B200_FN(cpg_gblob_nbytes);
+extern "C" const unsigned long long CPG_B200_FN(cpg_gS0_words)[];       // regularised KKT values in slot order (global)
+extern "C" const unsigned int CPG_B200_FN(cpg_gS0_nbytes);
 
 namespace {
 
@@ -30,11 +35,15 @@ struct Fam {
   static constexpr int W_STRIDE = CPG_FAM_W_STRIDE;       // doubles per warp work vector
   static constexpr int S_STRIDE = CPG_FAM_S_STRIDE;       // doubles per warp factor storage (tail kernel)
   static constexpr int TAIL_WARPS = CPG_FAM_TAIL_WARPS;
+  static constexpr int GBLOB_BYTES_PAD = CPG_FAM_GBLOB_BYTES_PAD;
+  static constexpr int GRAD_WARPS = CPG_FAM_GRAD_WARPS;
+  static constexpr int GRAD_STRIDE = CPG_FAM_GRAD_STRIDE;
   static constexpr int PAIR_STRIDE = CPG_FAM_PAIR_STRIDE; // doubles per warp in the pair kernel: interleaved w + batched-row slots
 };
 constexpr int SMEM_BYTES = Fam::BLOB_BYTES_PAD + Fam::WARPS * Fam::PAIR_STRIDE * 8;
 constexpr int TAIL_SMEM_BYTES = Fam::CBLOB_BYTES_PAD + Fam::TAIL_WARPS * (Fam::W_STRIDE + Fam::S_STRIDE) * 8;
 constexpr int TAIL_WORDS = Fam::N + 2 * Fam::M + 2;
+constexpr int GRAD_SMEM_BYTES = Fam::GBLOB_BYTES_PAD + Fam::GRAD_WARPS * Fam::GRAD_STRIDE * 8;
 
 struct Ctx {
   bool ready = false;
@@ -42,6 +51,10 @@ struct Ctx {
   uint8_t* d_blob = nullptr;
   uint8_t* d_tail_blob = nullptr;
   uint8_t* d_cblob = nullptr;
+  uint8_t* d_gblob = nullptr;
+  double* d_gS0 = nullptr;
+  int cap_G = 0;
+  double *g_soly = nullptr, *g_dprim = nullptr, *g_dparams = nullptr, *g_dq = nullptr, *g_dl = nullptr, *g_du = nullptr;
   unsigned int* d_counter = nullptr;
   int* d_tail_count = nullptr;
   int* d_tail_ids = nullptr;
@@ -153,6 +166,11 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
   CK(cudaMemcpy(g.d_blob, CPG_B200_FN(cpg_blob_words), CPG_B200_FN(cpg_blob_nbytes), cudaMemcpyHostToDevice));
   if (!g.d_cblob) CK(cudaMalloc(&g.d_cblob, Fam::CBLOB_BYTES_PAD));
   CK(cudaMemcpy(g.d_cblob, CPG_B200_FN(cpg_cblob_words), CPG_B200_FN(cpg_cblob_nbytes), cudaMemcpyHostToDevice));
+  if (!g.d_gblob) CK(cudaMalloc(&g.d_gblob, Fam::GBLOB_BYTES_PAD));
+  CK(cudaMemcpy(g.d_gblob, CPG_B200_FN(cpg_gblob_words), CPG_B200_FN(cpg_gblob_nbytes), cudaMemcpyHostToDevice));
+  if (!g.d_gS0) CK(cudaMalloc(&g.d_gS0, CPG_B200_FN(cpg_gS0_nbytes)));
+  CK(cudaMemcpy(g.d_gS0, CPG_B200_FN(cpg_gS0_words), CPG_B200_FN(cpg_gS0_nbytes), cudaMemcpyHostToDevice));
+  CK(cudaFuncSetAttribute(cpgb200::qp_grad_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAD_SMEM_BYTES));
   if (!g.d_tail_blob) CK(cudaMalloc(&g.d_tail_blob, CPG_B200_FN(cpg_tail_blob_nbytes)));
   CK(cudaMemcpy(g.d_tail_blob, CPG_B200_FN(cpg_tail_blob_words), CPG_B200_FN(cpg_tail_blob_nbytes), cudaMemcpyHostToDevice));
   CK(cudaFuncSetAttribute(cpgb200::admm_tail_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM_BYTES));
@@ -164,7 +182,7 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
 }
 
 int CPG_B200_FN(cpg_b200_free)(void) {
-  void* ptrs[] = {g.d_blob, g.d_cblob, g.d_tail_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0,
+  void* ptrs[] = {g.d_blob, g.d_cblob, g.d_gblob, g.d_gS0, g.g_soly, g.g_dprim, g.g_dparams, g.g_dq, g.g_dl, g.g_du, g.d_tail_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0,
                   g.d_prim, g.d_dual, g.d_solx, g.d_soly, g.d_obj, g.d_pri, g.d_dua, g.d_iter, g.d_status};
   for (void* p : ptrs) if (p) cudaFree(p);
   g = Ctx();
@@ -246,6 +264,55 @@ int CPG_B200_FN(cpg_solve_batch_host)(int B, const double* params, const double*
   CK(cudaMemcpyAsync(dua_res, g.d_dua, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(iter, g.d_iter, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(status, g.d_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return CPG_B200_OK;
+}
+
+int CPG_B200_FN(cpg_gradient_batch_device)(int B, const double* sol_x, const double* sol_y, const double* dprim,
+                                           double* dparams, double* dq, double* dl, double* du, void* stream_) {
+  (void)sol_x;   // only enters dP / dA (matrix parameters are shared in this build)
+  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+  if (B < 0 || !sol_y || !dprim) return CPG_B200_ERR_BAD_ARG;
+  g.launches = 0;
+  if (B == 0) return CPG_B200_OK;
+  cpgb200::GradIO io;
+  io.sol_y = sol_y; io.dprim = dprim; io.dparams = dparams; io.dq = dq; io.dl = dl; io.du = du; io.S0 = g.d_gS0; io.B = B;
+  int grid = g.n_sm;
+  const int need = (B + Fam::GRAD_WARPS - 1) / Fam::GRAD_WARPS;
+  if (grid > need) grid = need;
+  cpgb200::qp_grad_kernel<Fam><<<grid, Fam::GRAD_WARPS * 32, GRAD_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      g.d_gblob, g.d_tail_blob, io);
+  g.launches += 1;
+  CK(cudaGetLastError());
+  return CPG_B200_OK;
+}
+
+int CPG_B200_FN(cpg_gradient_batch_host)(int B, const double* sol_x, const double* sol_y, const double* dprim,
+                                         double* dparams, double* dq, double* dl, double* du) {
+  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+  if (B < 0 || !sol_y || !dprim) return CPG_B200_ERR_BAD_ARG;
+  if (B == 0) { g.launches = 0; return CPG_B200_OK; }
+  const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words));
+  int rc;
+  if (B > g.cap_G) {
+    if ((rc = grow(&g.g_soly, (size_t)B * (Fam::M > 0 ? Fam::M : 1)))) return rc;
+    if ((rc = grow(&g.g_dprim, (size_t)B * (H->n_prim > 0 ? H->n_prim : 1)))) return rc;
+    if ((rc = grow(&g.g_dparams, (size_t)B * (H->npb > 0 ? H->npb : 1)))) return rc;
+    if ((rc = grow(&g.g_dq, (size_t)B * Fam::N))) return rc;
+    if ((rc = grow(&g.g_dl, (size_t)B * (Fam::M > 0 ? Fam::M : 1)))) return rc;
+    if ((rc = grow(&g.g_du, (size_t)B * (Fam::M > 0 ? Fam::M : 1)))) return rc;
+    g.cap_G = B;
+  }
+  cudaStream_t st = 0;
+  CK(cudaMemcpyAsync(g.g_soly, sol_y, sizeof(double) * (size_t)B * Fam::M, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(g.g_dprim, dprim, sizeof(double) * (size_t)B * H->n_prim, cudaMemcpyHostToDevice, st));
+  rc = CPG_B200_FN(cpg_gradient_batch_device)(B, nullptr, g.g_soly, g.g_dprim, dparams ? g.g_dparams : nullptr,
+                                              dq ? g.g_dq : nullptr, dl ? g.g_dl : nullptr, du ? g.g_du : nullptr, st);
+  if (rc) return rc;
+  if (dparams) CK(cudaMemcpyAsync(dparams, g.g_dparams, sizeof(double) * (size_t)B * H->npb, cudaMemcpyDeviceToHost, st));
+  if (dq) CK(cudaMemcpyAsync(dq, g.g_dq, sizeof(double) * (size_t)B * Fam::N, cudaMemcpyDeviceToHost, st));
+  if (dl) CK(cudaMemcpyAsync(dl, g.g_dl, sizeof(double) * (size_t)B * Fam::M, cudaMemcpyDeviceToHost, st));
+  if (du) CK(cudaMemcpyAsync(du, g.g_du, sizeof(double) * (size_t)B * Fam::M, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return CPG_B200_OK;
 }

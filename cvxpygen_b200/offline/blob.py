@@ -275,3 +275,81 @@ def pack_tail_blob(T) -> bytes:
     hv['off_u16'] = hv['off_f64'] + len(f64b)
     hv['total_bytes'] = hv['off_u16'] + len(u16b)
     return hdr() + i32b + f64b + u16b
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Gradient blob: constants of the batched QP backward pass (csrc/grad_kernel.cuh).  Staged in shared memory,
+# except S0 (the regularised KKT values in slot order), which each warp reads once per instance from global.
+GRAD_HEADER_FIELDS: List[Tuple[str, str]] = [
+    ('int', 'magic'), ('int', 'total_bytes'), ('int', 'n'), ('int', 'm'),
+    ('int', 'nk'), ('int', 'npb'), ('int', 'n_prim'), ('int', 'n_slots'),
+    ('int', 'off_i32'), ('int', 'off_f64'), ('int', 'off_u16'), ('int', 'n_tent'),
+    ('int', 'i_ellA'), ('int', 'i_ellAt'), ('int', 'i_ellP'), ('int', 'i_arow_ptr'),
+    ('int', 'i_tptr'), ('int', 'h_pinvx'), ('int', 'h_pinvz'), ('int', 'h_prim'),
+    ('int', 'h_arow_slot'), ('int', 'h_tidx'), ('int', 'h_tkind'), ('int', 'f_tval'),
+]
+
+
+def grad_header_struct_c(name='CpgGradHeader') -> str:
+    return 'struct %s {\n%s};\n' % (name, ''.join(f'  {t} {n};\n' for t, n in GRAD_HEADER_FIELDS))
+
+
+def pack_grad_blob(*, n, m, perm, P_upper, A, slot_of, n_slots, Mq_b, Ml_b, Mu_b, npb, prim_idx, reg=1e-6):
+    """P_upper, A: UNSCALED canonical matrices; slot_of(i, j) -> slot of the lower-triangle entry (pivot positions).
+    Returns (blob for shared memory, S0 array for global memory)."""
+    nk = n + m
+    ar = _Areas()
+    pinv = np.empty(nk, dtype=np.int64); pinv[np.asarray(perm)] = np.arange(nk)
+    A = sp.csr_matrix(A); A.sort_indices()
+    Pfull = sp.csr_matrix(P_upper + sp.triu(P_upper, 1).T)
+    # K_reg = [[P + reg I, A'], [A, -reg I]] in slot order  (cvxpygen/writer.py:361-364)
+    S0 = np.zeros(n_slots)
+    for i in range(n):
+        S0[pinv[i]] = Pfull[i, i] + reg
+    Pc = sp.coo_matrix(sp.tril(Pfull, -1))
+    for i, j, v in zip(Pc.row, Pc.col, Pc.data):
+        a, b = pinv[i], pinv[j]
+        S0[slot_of(max(a, b), min(a, b))] = v
+    arow_ptr, arow_slot = [0], []
+    for j in range(m):
+        S0[pinv[n + j]] = -reg
+        for c, v in zip(A.indices[A.indptr[j]:A.indptr[j + 1]], A.data[A.indptr[j]:A.indptr[j + 1]]):
+            a, b = pinv[n + j], pinv[c]
+            s_ = slot_of(max(a, b), min(a, b))
+            S0[s_] = v
+            arow_slot.append(s_)
+        arow_ptr.append(len(arow_slot))
+    hv = dict(magic=MAGIC + 2, n=n, m=m, nk=nk, npb=npb, n_prim=len(prim_idx), n_slots=n_slots)
+    hv['i_ellA'] = _add_ell(ar, ell_row_blocks(A, m))
+    At_blocks = [(K, v, cidx + n) for K, v, cidx in ell_row_blocks(sp.csr_matrix(A.T), n)]
+    hv['i_ellAt'] = _add_ell(ar, At_blocks)
+    hv['i_ellP'] = _add_ell(ar, ell_row_blocks(Pfull, n))
+    hv['i_arow_ptr'] = ar.add_i32(arow_ptr)
+    hv['h_arow_slot'] = ar.add_u16(arow_slot)
+    hv['h_pinvx'] = ar.add_u16(pinv[:n]); hv['h_pinvz'] = ar.add_u16(pinv[n:])
+    hv['h_prim'] = ar.add_u16(prim_idx)
+    # transposed maps: for every batched parameter entry c the list of (kind, row, coefficient)
+    tptr, tidx, tkind, tval = [0], [], [], []
+    Ms = [sp.csc_matrix(M) for M in (Mq_b, Ml_b, Mu_b)]
+    for cidx in range(npb):
+        for kind, M in enumerate(Ms):
+            s_, e_ = M.indptr[cidx], M.indptr[cidx + 1]
+            tidx += M.indices[s_:e_].tolist(); tval += M.data[s_:e_].tolist(); tkind += [kind] * (e_ - s_)
+        tptr.append(len(tidx))
+    hv['n_tent'] = len(tidx)
+    hv['i_tptr'] = ar.add_i32(tptr)
+    hv['h_tidx'] = ar.add_u16(tidx); hv['h_tkind'] = ar.add_u16(tkind); hv['f_tval'] = ar.add_f64(tval)
+    fmt = '<' + 'i' * len(GRAD_HEADER_FIELDS)
+
+    def hdr():
+        return struct.pack(fmt, *[int(hv.get(nm, 0)) for _, nm in GRAD_HEADER_FIELDS])
+    assert len(hdr()) % 16 == 0
+
+    def pad16(b: bytes) -> bytes:
+        return b + b'\0' * ((-len(b)) % 16)
+    i32b = pad16(np.asarray(ar.i32, dtype='<i4').tobytes())
+    f64b = pad16(np.asarray(ar.f64, dtype='<f8').tobytes())
+    u16b = pad16(np.asarray(ar.u16, dtype='<u2').tobytes())
+    hv['off_i32'] = len(hdr()); hv['off_f64'] = hv['off_i32'] + len(i32b); hv['off_u16'] = hv['off_f64'] + len(f64b)
+    hv['total_bytes'] = hv['off_u16'] + len(u16b)
+    return hdr() + i32b + f64b + u16b, S0

@@ -12,7 +12,7 @@ import scipy.sparse as sp
 
 from ..ir import CanonFamily
 from . import kkt as _kkt
-from .blob import pack_blob, pack_tail_blob
+from .blob import pack_blob, pack_tail_blob, pack_grad_blob
 from .refactor import build_refactor_tables, RefactorTables
 from .equilibrate import ruiz_equilibrate
 from .schedule import SolveSchedule, build_schedule
@@ -43,6 +43,8 @@ class QPSetup:
     blob: bytes = b''
     tail_blob: bytes = b''
     blob_compact: bytes = b''
+    grad_blob: bytes = b''
+    grad_S0: Optional[np.ndarray] = None
     refactor: Optional[RefactorTables] = None
     solve_source: str = ''
     theta_shared: Optional[np.ndarray] = None
@@ -114,6 +116,9 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
                              d_const=d_const, is_max=fam.is_maximization, with_tiles=False)
     RT = build_refactor_tables(F, K, n)
     tail_blob = pack_tail_blob(RT)
+    # backward pass (gradient=True): regularised KKT of the UNSCALED problem on the same symbolic pattern
+    grad_blob, grad_S0 = pack_grad_blob(n=n, m=m, perm=F.perm, P_upper=sp.csc_matrix(P), A=sp.csc_matrix(A), slot_of=RT.slot_of,
+                                        n_slots=RT.n_slots, Mq_b=Mq_b, Ml_b=Ml_b, Mu_b=Mu_b, npb=npb, prim_idx=prim_idx)
     import struct as _struct
     from .blob import HEADER_FIELDS as _HF
     _hdr = dict(zip([n_ for _, n_ in _HF], _struct.unpack('<' + ''.join('i' if t_ == 'int' else 'd' for t_, _ in _HF),
@@ -122,5 +127,5 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
               schedule_entries=S.n_entries, blob_bytes=len(blob))
     return QPSetup(family=fam, batch_params=list(batch_params), n=n, m=m, npb=npb, rho=rho, sigma=sigma,
                    scaling=scaling, D=sc['D'], E=sc['E'], c=sc['c'], ctype=ctype, P_scaled=sc['P'],
-                   A_scaled=sc['A'], factor=F, schedule=S, prim_idx=prim_idx, dual_idx=dual_idx, blob=blob, tail_blob=tail_blob, blob_compact=blob_compact, refactor=RT, solve_source=solve_source,
+                   A_scaled=sc['A'], factor=F, schedule=S, prim_idx=prim_idx, dual_idx=dual_idx, blob=blob, tail_blob=tail_blob, blob_compact=blob_compact, grad_blob=grad_blob, grad_S0=grad_S0, refactor=RT, solve_source=solve_source,
                    theta_shared=theta0, batch_cols=bcols, stats=st)

@@ -54,6 +54,15 @@ class RefactorTables:
     scale: np.ndarray             # (n_scale, 2) uint16: slot, j
     fwd_tiles: List[SlotTile]
     bwd_tiles: List[SlotTile]
+    slot: np.ndarray = None       # (nk, nk) slot of the strictly-lower entry (i, j) in pivot positions, -1 outside the pattern
+
+    def slot_of(self, i: int, j: int) -> int:
+        if i == j:
+            return int(i)
+        s = int(self.slot[i, j])
+        if s < 0:
+            raise KeyError('entry outside the symbolic pattern')
+        return s
 
     @property
     def zero_slot(self):
@@ -145,7 +154,7 @@ def build_refactor_tables(F: LDLFactor, K: sp.csc_matrix, n_var: int) -> Refacto
                           level_ptr=np.asarray(level_ptr), level_cols=np.asarray(level_cols),
                           op_ptr=np.asarray(op_ptr), ops=np.asarray(ops, dtype=np.int64).reshape(-1, 4),
                           scale_ptr=np.asarray(scale_ptr), scale=np.asarray(scale, dtype=np.int64).reshape(-1, 2),
-                          fwd_tiles=fwd, bwd_tiles=bwd)
+                          fwd_tiles=fwd, bwd_tiles=bwd, slot=slot)
 
 
 def emulate_factor(T: RefactorTables, rho_vec: np.ndarray) -> np.ndarray:

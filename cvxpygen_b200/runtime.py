@@ -240,6 +240,52 @@ class Module:
                                                        ptr(out.status), ptr(out.pri_res), ptr(out.dua_res), C.byref(s), stream))
         return out
 
+    # ---- NEW: batched backward pass (gradient=True).  dprim: dict name -> (B, *shape) or packed (B, n_prim) array
+    def pack_dprim(self, dvars, B):
+        d = np.zeros((B, self.dims.n_prim))
+        for v in self.meta['variables']:
+            if v['name'] in dvars:
+                a = np.asarray(dvars[v['name']], dtype=np.float64)
+                a = a.reshape(B, -1, order='F') if a.ndim <= 2 else np.stack([t.flatten(order='F') for t in a])
+                d[:, v['offset']:v['offset'] + v['size']] = a
+        return d
+
+    def unpack_dparams(self, dparams):
+        out, col = {}, 0
+        for p in self.meta['params']:
+            if p['batched']:
+                out[p['name']] = dparams[:, col:col + p['size']]
+                col += p['size']
+        return out
+
+    def gradient_batch(self, sol_y, dprim, sol_x=None, return_canonical=False):
+        """Host arrays.  Returns (dict name -> (B, size) gradients of the batched parameters[, dq, dl, du])."""
+        self.init()
+        sol_y = np.ascontiguousarray(sol_y, dtype=np.float64)
+        B = sol_y.shape[0]
+        D = np.ascontiguousarray(dprim if isinstance(dprim, np.ndarray) else self.pack_dprim(dprim, B), dtype=np.float64)
+        d = self.dims
+        dpar = np.empty((B, d.n_param))
+        dq = np.empty((B, d.n_var)) if return_canonical else None
+        dl = np.empty((B, d.n_con)) if return_canonical else None
+        du = np.empty((B, d.n_con)) if return_canonical else None
+        p = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+        self._check(self._fn('cpg_gradient_batch_host')(C.c_int(B), None, p(sol_y), p(D), p(dpar), p(dq), p(dl), p(du)))
+        res = self.unpack_dparams(dpar)
+        return (res, dq, dl, du) if return_canonical else res
+
+    def gradient_batch_device(self, sol_y, dprim, dparams=None):
+        import torch
+        self.init()
+        B = sol_y.shape[0]
+        if dparams is None:
+            dparams = torch.empty((B, self.dims.n_param), dtype=torch.float64, device=sol_y.device)
+        ptr = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(sol_y.device).cuda_stream)
+        self._check(self._fn('cpg_gradient_batch_device')(C.c_int(B), None, ptr(sol_y), ptr(dprim), ptr(dparams),
+                                                          None, None, None, stream))
+        return dparams
+
     # ---- reference-compatible single-instance entry: cpg_module.solve(upd, par)
     def solve(self, upd, par):
         vals = {}

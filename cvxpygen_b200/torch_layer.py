@@ -1,0 +1,34 @@
+"""Batched differentiable QP layer on top of a generated ADMM-CUDA library.
+
+The reference exposes `forward(params, context)` / `backward(dvars, context)` for cvxpylayers' `custom_method`
+(cvxpygen/templates/cpg_solver.py.jinja2:176-212), one instance per call.  This is the batched equivalent as a
+torch.autograd.Function: forward = cpg_solve_batch_device, backward = cpg_gradient_batch_device; everything stays on
+the GPU (the canonical dual of the forward pass is kept for the backward pass, like `gradient_dual` in the reference)."""
+import torch
+
+
+class _BatchedQP(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, params, module):
+        p = params.detach().contiguous()
+        out = module.solve_batch_device(p, return_canonical=True)
+        ctx.module = module
+        ctx.save_for_backward(out.sol_y)
+        ctx.status = out.status
+        return out.prim
+
+    @staticmethod
+    def backward(ctx, dprim):
+        (sol_y,) = ctx.saved_tensors
+        return ctx.module.gradient_batch_device(sol_y, dprim.contiguous()), None
+
+
+class BatchedQPLayer(torch.nn.Module):
+    """params (B, n_param) float64 CUDA tensor of the batched user parameters -> (B, n_prim) user variables."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module.init()
+
+    def forward(self, params):
+        return _BatchedQP.apply(params, self.module)

@@ -103,6 +103,20 @@ int CPG_B200_FN(cpg_solve_batch_host)(int B, const double* params, const double*
                                       double* pri_res, double* dua_res,
                                       const CpgB200Settings* settings);
 
+/* Batched backward pass (gradient=True): differentiates the QP solution map through its KKT system.
+ * Reference counterpart, one instance at a time: <p>cpg_update_d<var>(idx, val) + <p>cpg_gradient()
+ * (cvxpygen/writer.py:222-312) -> cpg_osqp_gradient() (templates/cpg_osqp_grad_compute.c.jinja2:432-531); the pybind
+ * entry is cpg_module.gradient(vdelta, gsol, use_sol) (cvxpygen/utils.py:1272-1328).
+ *   sol_x (B, n_var), sol_y (B, n_con): canonical solution returned by the forward solve (sol_x may be NULL: it only
+ *                                       enters the gradients of matrix parameters, which are shared in this build)
+ *   dprim   (B, n_prim): upstream gradient w.r.t. the user-level primal variables, same layout as `prim`
+ *   dparams (B, n_param): OUT gradient w.r.t. the batched user parameters, same layout as `params`
+ *   dq (B, n_var), dl, du (B, n_con): optional canonical gradients (NULL = skip)                               */
+int CPG_B200_FN(cpg_gradient_batch_device)(int B, const double* sol_x, const double* sol_y, const double* dprim,
+                                           double* dparams, double* dq, double* dl, double* du, void* stream);
+int CPG_B200_FN(cpg_gradient_batch_host)(int B, const double* sol_x, const double* sol_y, const double* dprim,
+                                         double* dparams, double* dq, double* dl, double* du);
+
 #ifdef __cplusplus
 }
 #endif

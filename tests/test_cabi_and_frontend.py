@@ -37,7 +37,8 @@ def test_generated_tree_mirrors_reference_layout(ls_dir):
 def test_library_exports_every_declared_symbol(ls_dir):
     lib = C.CDLL(os.path.join(ls_dir, 'libcpg_b200.so'))
     fns = declared_functions()
-    assert {'cpg_b200_init', 'cpg_solve_batch_device', 'cpg_solve_batch_host', 'cpg_b200_dims'} <= set(fns)
+    assert {'cpg_b200_init', 'cpg_solve_batch_device', 'cpg_solve_batch_host', 'cpg_b200_dims',
+            'cpg_gradient_batch_device', 'cpg_gradient_batch_host'} <= set(fns)
     for fn in fns:
         assert hasattr(lib, 't1_' + fn), fn
     # reference-compatible per-family interface (cvxpygen/utils.py:1087-1141)
@@ -107,8 +108,6 @@ def test_matrix_parameter_is_flattened_in_fortran_order(tmp_path):
 def test_generate_code_argument_errors():
     with pytest.raises(ValueError, match='Unsupported solver'):
         cpg.generate_code(families.nonneg_ls(), solver='GUROBI', wrapper=False)
-    with pytest.raises(NotImplementedError):
-        cpg.generate_code(families.nonneg_ls(), gradient=True, wrapper=False)
 
 
 def test_standard_families_are_built_or_buildable():
