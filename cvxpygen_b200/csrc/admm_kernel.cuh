@@ -173,7 +173,37 @@ __device__ __forceinline__ double slot_tile_acc(const int* h, const uint16_t* U1
   return acc;
 }
 
-// K x = b with the per-instance factor: level-scheduled L solve, D^{-1}, L' solve (QDLDL_solve, qdldl.c:269-281)
+// Resolve the dependencies INSIDE a group tile in registers: lane t holds the value of row t of the tile; rows are
+// finalised one after the other (ascending for L, descending for L'), each broadcast with one shuffle and applied with
+// one FMA by the lanes that depend on it.  Coefficients are fetched eight rows ahead so that their shared-memory
+// latency overlaps the sweep.  inside[j*32 + t] = slot of the coefficient coupling row t to row j (zero slot if none).
+template <bool ASCENDING>
+__device__ __forceinline__ double group_sweep(double val, const uint16_t* __restrict__ inside, const double* __restrict__ S,
+                                              const int nrows, const int lane) {
+  const int nblk = (nrows + 7) >> 3;
+  for (int blk = 0; blk < nblk; ++blk) {
+    double cf[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int jj = blk * 8 + u;
+      const int j = ASCENDING ? jj : nrows - 1 - jj;
+      cf[u] = (jj < nrows) ? S[inside[j * LANES + lane]] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int jj = blk * 8 + u;
+      if (jj < nrows) {
+        const int j = ASCENDING ? jj : nrows - 1 - jj;
+        const double vj = __shfl_sync(FULL, val, j);
+        const bool dep = ASCENDING ? (lane > j) : (lane < j);
+        if (dep) val = fma(-cf[u], vj, val);
+      }
+    }
+  }
+  return val;
+}
+
+// K x = b with the per-instance factor: grouped level-scheduled L solve, D^{-1}, L' solve (QDLDL_solve, qdldl.c:269-281)
 __device__ __forceinline__ void tail_solve(const TailView& tv, const double* S, double* w, int lane) {
   const int* T = tv.I32 + tv.H->i_tiles;
   const int nf = tv.H->n_fwd_tiles, nt = nf + tv.H->n_bwd_tiles, nk = tv.H->nk;
@@ -184,8 +214,13 @@ __device__ __forceinline__ void tail_solve(const TailView& tv, const double* S, 
     }
     const int* h = T + 8 * t;
     const double acc = slot_tile_acc(h, tv.U16, S, w, lane);
+    const int nrows = h[4];
+    const int row = tv.U16[h[5] + lane];
+    double val = w[row] - acc;
+    if (h[7]) val = (t < nf) ? group_sweep<true>(val, tv.U16 + h[6], S, nrows, lane)
+                             : group_sweep<false>(val, tv.U16 + h[6], S, nrows, lane);
     __syncwarp();
-    if (lane < h[4]) { const int r = tv.U16[h[5] + lane]; w[r] -= acc; }
+    if (lane < nrows) w[row] = val;
     __syncwarp();
   }
   if (nt == nf) { for (int i = lane; i < nk; i += LANES) w[i] *= S[i]; __syncwarp(); }

@@ -257,7 +257,8 @@ def pack_tail_blob(T) -> bytes:
         hs = ar.add_u16(t.slots)
         hc = ar.add_u16(t.cols)
         hr = ar.add_u16(np.concatenate([t.rows, np.zeros(LANES - len(t.rows), dtype=np.uint16)]))
-        tab += [hs, hc, t.slots.shape[0], t.r_pad, len(t.rows), hr, 0, 0]
+        hin = ar.add_u16(t.inside) if t.inside is not None else 0
+        tab += [hs, hc, t.slots.shape[0], t.r_pad, len(t.rows), hr, hin, 1 if t.inside is not None else 0]
     hv['i_tiles'] = ar.add_i32(tab if tab else [0] * 8)
     fmt = '<' + 'i' * len(TAIL_HEADER_FIELDS)
 

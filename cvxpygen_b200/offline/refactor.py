@@ -38,6 +38,10 @@ class SlotTile:
     r_pad: int
     slots: np.ndarray    # (K, 32) uint16 slot into S   (padding: slot of a zero entry, see zero_slot)
     cols: np.ndarray     # (K, 32) uint16 position in w
+    inside: np.ndarray = None   # group tiles only: (nrows, 32) uint16, inside[j, t] = slot of the coefficient that
+    #                             couples row t to row j of the SAME tile (zero_slot if none).  The kernel resolves these
+    #                             dependencies with an in-register sweep (one shuffle + FMA per row) instead of one
+    #                             shared-memory round trip per elimination-tree level.
 
 
 @dataclass
@@ -95,6 +99,40 @@ def _slot_tiles(rows, entries, zero_slot) -> List[SlotTile]:
     return tiles
 
 
+def _level_groups(level: np.ndarray, lo_level: int):
+    """Consecutive levels >= lo_level packed into groups of <= 32 rows; a level wider than 32 rows stays alone."""
+    n_levels = int(level.max()) + 1
+    groups, cur = [], []
+    for lv in range(lo_level, n_levels):
+        rows = np.nonzero(level == lv)[0].tolist()
+        if len(rows) > LANES:
+            if cur:
+                groups.append(cur); cur = []
+            groups.append(rows)
+        elif len(cur) + len(rows) > LANES:
+            groups.append(cur); cur = rows
+        else:
+            cur = cur + rows
+    if cur:
+        groups.append(cur)
+    return groups
+
+
+def _group_tiles(rows, outside, inside_pairs, zero_slot):
+    """rows sorted ascending; outside[i] = [(slot, col)] entries outside the group; inside_pairs[(t, j)] = slot coupling
+    row index t to row index j (both indices into `rows`).  One tile per <= 32 rows; only single-tile groups carry
+    inside couplings (wide levels have none)."""
+    tiles = _slot_tiles(np.asarray(rows), outside, zero_slot)
+    if inside_pairs:
+        assert len(tiles) == 1
+        g = len(rows)
+        ins = np.full((g, LANES), zero_slot, dtype=np.uint16)
+        for (t, j), sl in inside_pairs.items():
+            ins[j, t] = sl
+        tiles[0].inside = ins
+    return tiles
+
+
 def build_refactor_tables(F: LDLFactor, K: sp.csc_matrix, n_var: int) -> RefactorTables:
     nk = K.shape[0]
     m = nk - n_var
@@ -137,19 +175,35 @@ def build_refactor_tables(F: LDLFactor, K: sp.csc_matrix, n_var: int) -> Refacto
                 scale.append((slot[i, j], j))
         op_ptr.append(len(ops))
         scale_ptr.append(len(scale))
-    # triangular solves, one hazard-free group of tiles per level
+    # triangular solves: groups of consecutive levels (<= 32 rows) resolve their internal dependencies in registers
     fwd, bwd = [], []
-    for lv in range(1, n_levels):
-        rows = np.nonzero(level == lv)[0]
-        ent = [[(slot[i, j], j) for j in np.nonzero(patt[i, :])[0]] for i in rows]
-        fwd += _slot_tiles(rows, ent, n_slots - 1)
-    for lv in range(n_levels - 1, -1, -1):
-        rows = np.nonzero(level == lv)[0]
-        ent = [[(slot[k, i], k) for k in np.nonzero(patt[:, i])[0]] for i in rows]
-        rows_nz = [r for r, e in zip(rows, ent) if e]
-        ent_nz = [e for e in ent if e]
-        if rows_nz:
-            bwd += _slot_tiles(np.asarray(rows_nz), ent_nz, n_slots - 1)
+    pos_in = {}
+    for rows in _level_groups(level, 1):
+        rset = {r: t for t, r in enumerate(rows)}
+        outside, inside = [], {}
+        for t, i in enumerate(rows):
+            ent = []
+            for j in np.nonzero(patt[i, :])[0]:
+                if j in rset:
+                    inside[(t, rset[j])] = slot[i, j]
+                else:
+                    ent.append((slot[i, j], j))
+            outside.append(ent)
+        fwd += _group_tiles(rows, outside, inside if len(rows) <= LANES else {}, n_slots - 1)
+    for rows in reversed(_level_groups(level, 0)):
+        rset = {r: t for t, r in enumerate(rows)}
+        outside, inside = [], {}
+        for t, i in enumerate(rows):
+            ent = []
+            for k in np.nonzero(patt[:, i])[0]:
+                if k in rset:
+                    inside[(t, rset[k])] = slot[k, i]
+                else:
+                    ent.append((slot[k, i], k))
+            outside.append(ent)
+        if len(rows) > LANES:
+            assert not inside
+        bwd += _group_tiles(rows, outside, inside, n_slots - 1)
     return RefactorTables(nk=nk, n_slots=n_slots, S0=S0, rho_slot=rho_slot.astype(np.int64),
                           level_ptr=np.asarray(level_ptr), level_cols=np.asarray(level_cols),
                           op_ptr=np.asarray(op_ptr), ops=np.asarray(ops, dtype=np.int64).reshape(-1, 4),
@@ -174,10 +228,10 @@ def emulate_factor(T: RefactorTables, rho_vec: np.ndarray) -> np.ndarray:
 
 
 def emulate_solve(T: RefactorTables, S: np.ndarray, w: np.ndarray) -> np.ndarray:
-    """w in pivot positions -> K^{-1} w (pivot positions), using the slot tiles."""
+    """w in pivot positions -> K^{-1} w (pivot positions), using the slot tiles exactly like the kernel."""
     w = np.array(w, dtype=float, copy=True)
 
-    def run(tile, sign_update):
+    def outside_acc(tile):
         acc = np.zeros(LANES)
         for k in range(tile.slots.shape[0]):
             acc += S[tile.slots[k].astype(int)] * w[tile.cols[k].astype(int)]
@@ -185,12 +239,23 @@ def emulate_solve(T: RefactorTables, S: np.ndarray, w: np.ndarray) -> np.ndarray
         while off >= tile.r_pad:
             acc = acc + acc[np.arange(LANES) ^ off]
             off //= 2
-        return acc[:len(tile.rows)]
-    for t in T.fwd_tiles:                         # w_i -= sum_j L_ij w_j
-        r = t.rows.astype(int)
-        w[r] = w[r] - run(t, -1)
+        return acc
+
+    def run(tile, ascending):
+        g = len(tile.rows)
+        r = tile.rows.astype(int)
+        val = w[r] - outside_acc(tile)[:g]
+        if tile.inside is not None:
+            order = range(g) if ascending else range(g - 1, -1, -1)
+            for j in order:
+                vj = val[j]
+                coef = S[tile.inside[j, :g].astype(int)]
+                mask = (np.arange(g) > j) if ascending else (np.arange(g) < j)
+                val = np.where(mask, val - coef * vj, val)
+        w[r] = val
+    for t in T.fwd_tiles:
+        run(t, True)
     w[:T.nk] *= S[:T.nk]                          # D^{-1}
-    for t in T.bwd_tiles:                         # w_i -= sum_k L_ki w_k
-        r = t.rows.astype(int)
-        w[r] = w[r] - run(t, -1)
+    for t in T.bwd_tiles:
+        run(t, False)
     return w
