@@ -247,3 +247,91 @@ def random_qp(n=20, m_eq=5, m_ineq=15, density=0.3, seed=0, name=None) -> CanonF
     duals = [UserDual('d0', 'y', (m_eq,), np.arange(m_eq)), UserDual('d1', 'y', (m_ineq,), m_eq + np.arange(m_ineq))]
     return CanonFamily(name or f'random_qp_{n}_{m_eq}_{m_ineq}', 'quadratic', n, m_eq, m_ineq, params, maps,
                        {'P': _csc_pattern(Pu), 'A': _csc_pattern(A)}, variables, duals)
+
+
+def portfolio_socp(n=100, m=10, seed=1, k_tc=0.01, k_sh=0.05, Lmax=1.6, name=None) -> CanonFamily:
+    """Portfolio optimisation as an SOCP in ECOS form (reference problem:
+    examples/portfolio.ipynb / tests/test_E2E_QP.py:76-110,148-162):
+
+        maximise a'w - ||Sig_f^1/2 f||^2 - ||d o w||^2 - k_tc'|dw| + k_sh' min(0, w)
+        s.t.     f = F'w,  1'w = 1,  ||w||_1 <= L,  dw = w - w_prev
+
+    canonical x = [w(n), dw(n), f(m), t_tc(n), t_sh(n), t_l1(n), r1, r2];   min c'x  s.t.  A x = b,  h - G x in K
+      equalities (p = m + 1 + n):  f - F'w = 0 ;  1'w = 1 ;  dw - w = -w_prev
+      LP cone (l = 6n + 1):        t_tc -/+ dw >= 0 ; t_sh + w >= 0, t_sh >= 0 ; t_l1 -/+ w >= 0 ; L - 1't_l1 >= 0
+      SOC(m+2): (1 + r1, 1 - r1, 2 Sig_f^1/2 f) ;  SOC(n+2): (1 + r2, 1 - r2, 2 d o w)      (||v||^2 <= r)
+    User parameters: ``a`` (enters c), ``w_prev`` (enters b); F, Sig_f_sqrt, d_sqrt, k_tc, k_sh, L are constants here.
+    Maximisation: obj_val is negated at retrieval (cvxpygen/utils.py:980)."""
+    rs = np.random.RandomState(seed)
+    alpha = rs.randn(n)
+    F = np.round(rs.randn(n, m))
+    sig = rs.rand(m)
+    d = rs.rand(n)
+    nv = 5 * n + m + 2
+    iw, idw, if_, itc, ish, il1, ir1, ir2 = 0, n, 2 * n, 2 * n + m, 3 * n + m, 4 * n + m, 5 * n + m, 5 * n + m + 1
+    p = m + 1 + n
+    params = _layout_params([('a', (n,), alpha), ('w_prev', (n,), np.zeros(n))])
+    col_a, col_wp = params[0].col, params[1].col
+    n_theta = 2 * n + 1
+    # ---- A x = b
+    Ar, Ac, Av = [], [], []
+    for j in range(m):
+        Ar.append(j); Ac.append(if_ + j); Av.append(1.0)
+        for i in range(n):
+            if F[i, j] != 0:
+                Ar.append(j); Ac.append(iw + i); Av.append(-F[i, j])
+    for i in range(n):
+        Ar.append(m); Ac.append(iw + i); Av.append(1.0)
+    for i in range(n):
+        Ar += [m + 1 + i, m + 1 + i]; Ac += [idw + i, iw + i]; Av += [1.0, -1.0]
+    A = sp.csc_matrix((Av, (Ar, Ac)), shape=(p, nv)); A.sort_indices()
+    # ---- h - G x in K
+    Gr, Gc, Gv, hv = [], [], [], []
+    row = 0
+
+    def ge(terms, const=0.0):      # sum coef*x + const >= 0   ->  G row = -coef, h = const
+        nonlocal row
+        for cidx, coef in terms:
+            Gr.append(row); Gc.append(cidx); Gv.append(-coef)
+        hv.append(const); row += 1
+    for i in range(n): ge([(itc + i, 1.0), (idw + i, -1.0)])
+    for i in range(n): ge([(itc + i, 1.0), (idw + i, 1.0)])
+    for i in range(n): ge([(ish + i, 1.0), (iw + i, 1.0)])
+    for i in range(n): ge([(ish + i, 1.0)])
+    for i in range(n): ge([(il1 + i, 1.0), (iw + i, -1.0)])
+    for i in range(n): ge([(il1 + i, 1.0), (iw + i, 1.0)])
+    ge([(il1 + i, -1.0) for i in range(n)], Lmax)
+    n_lp = row
+    ge([(ir1, 1.0)], 1.0); ge([(ir1, -1.0)], 1.0)
+    for j in range(m): ge([(if_ + j, 2.0 * sig[j])])
+    ge([(ir2, 1.0)], 1.0); ge([(ir2, -1.0)], 1.0)
+    for i in range(n): ge([(iw + i, 2.0 * d[i])])
+    mc = row
+    G = sp.csc_matrix((Gv, (Gr, Gc)), shape=(mc, nv)); G.sort_indices()
+    maps = {}
+    mb = _MapBuilder(nv, n_theta)
+    for i in range(n):
+        mb.add(iw + i, col_a + i, -1.0); mb.const(itc + i, k_tc); mb.const(ish + i, k_sh)
+    mb.const(ir1, 1.0); mb.const(ir2, 1.0)
+    maps['c'] = mb.csr()
+    maps['d'] = sp.csr_matrix((1, n_theta))
+    mbA = _MapBuilder(A.nnz, n_theta)
+    for k, v in enumerate(A.data): mbA.const(k, v)
+    maps['A'] = mbA.csr()
+    mbG = _MapBuilder(G.nnz, n_theta)
+    for k, v in enumerate(G.data): mbG.const(k, v)
+    maps['G'] = mbG.csr()
+    mbb = _MapBuilder(p, n_theta); mbb.const(m, 1.0)
+    for i in range(n): mbb.add(m + 1 + i, col_wp + i, -1.0)
+    maps['b'] = mbb.csr()
+    mbh = _MapBuilder(mc, n_theta)
+    for k, v in enumerate(hv):
+        if v != 0.0: mbh.const(k, v)
+    maps['h'] = mbh.csr()
+    variables = [UserVar('w', (n,), iw + np.arange(n)), UserVar('delta_w', (n,), idw + np.arange(n)),
+                 UserVar('f', (m,), if_ + np.arange(m))]
+    duals = [UserDual('d0', 'y', (m,), np.arange(m)), UserDual('d1', 'y', (1,), np.array([m])),
+             UserDual('d2', 'z', (1,), np.array([n_lp - 1])), UserDual('d3', 'y', (n,), m + 1 + np.arange(n))]
+    return CanonFamily(name or f'portfolio_socp_{n}_{m}', 'conic', nv, p, mc, params, maps,
+                       {'A': _csc_pattern(A), 'G': _csc_pattern(G)}, variables, duals, is_maximization=True,
+                       cone_dims={'l': n_lp, 'q': [m + 2, n + 2]})

@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Golden vectors for BASELINE config 3 (portfolio SOCP, n=100 assets) produced by the UNMODIFIED vendored ECOS 2.0.8
+(oracle/_ref/libecos_ref.so, built by `make -C oracle ref`) with cvxpygen's settings (feastol=abstol=reltol=1e-8).
+The IPM-CUDA kernel is not built yet; these fixtures pin its oracle for the next round."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from cvxpygen_b200 import families          # noqa: E402
+from oracle.ref_ecos import RefECOS         # noqa: E402
+
+fam = families.portfolio_socp()
+c, b, h = fam.canon_data('c'), fam.canon_data('b'), fam.canon_data('h')
+A, G = fam.canon_matrix('A'), fam.canon_matrix('G')
+r = RefECOS(c, A, b, G, h, fam.cone_dims['l'], fam.cone_dims['q'])
+B = 24
+rng = np.random.default_rng(2024)
+a = rng.standard_normal((B, 100)); wp = 1 / 100 + 0.01 * rng.standard_normal((B, 100))
+Cb = np.tile(c, (B, 1)); Cb[:, :100] = -a
+Bb = np.tile(b, (B, 1)); Bb[:, 11:111] = -wp
+out = r.solve_batch(c=Cb, b=Bb)
+np.savez_compressed(os.path.join(HERE, 'socp_portfolio_100_10.npz'), param_a=a, param_w_prev=wp,
+                    x=out['x'], y=out['y'], z=out['z'], s=out['s'], pcost=out['pcost'], iter=out['iter'], exitflag=out['exitflag'])
+print('iters', out['iter'].mean(), 'exit', np.unique(out['exitflag']), 'us/solve', out['seconds'] / B * 1e6)
