@@ -335,3 +335,46 @@ def portfolio_socp(n=100, m=10, seed=1, k_tc=0.01, k_sh=0.05, Lmax=1.6, name=Non
     return CanonFamily(name or f'portfolio_socp_{n}_{m}', 'conic', nv, p, mc, params, maps,
                        {'A': _csc_pattern(A), 'G': _csc_pattern(G)}, variables, duals, is_maximization=True,
                        cone_dims={'l': n_lp, 'q': [m + 2, n + 2]})
+
+
+def box_qp(n=6, m=8, seed=4, name=None) -> CanonFamily:
+    """Small QP with two-sided constraints  l <= A x <= u  whose bounds are user parameters, built to exercise the
+    per-instance corner cases of the path: a bound pair collapsing to an equality or opening to (-inf, inf) changes the
+    constraint's TYPE (and hence rho_vec and the KKT factor: update_rho_vec, osqp_sources/src/auxil.c:100-142); two
+    parallel rows with crossing bounds are primal infeasible; variable n-1 has no curvature and no constraint, so a
+    non-zero cost on it is dual infeasible (unbounded).  User parameters: q (n), l (m), u (m)."""
+    rs = np.random.RandomState(seed)
+    Pd = np.concatenate([1.0 + rs.rand(n - 1), [0.0]])
+    Pu = sp.csc_matrix(sp.diags(Pd))
+    Ad = rs.randn(m, n) * (rs.rand(m, n) < 0.6)
+    Ad[:, n - 1] = 0.0
+    Ad[1] = Ad[0]                                   # rows 0 and 1 are parallel
+    for i in range(m):
+        if not Ad[i].any():
+            Ad[i, rs.randint(n - 1)] = 1.0
+    A = sp.csc_matrix(Ad); A.sort_indices()
+    x0 = rs.randn(n)
+    q0 = np.concatenate([rs.randn(n - 1), [0.0]])
+    l0 = Ad @ x0 - 0.5 - rs.rand(m); u0 = Ad @ x0 + 0.5 + rs.rand(m)
+    params = _layout_params([('q', (n,), q0), ('l', (m,), l0), ('u', (m,), u0)])
+    n_theta = n + 2 * m + 1
+    maps = {}
+    mb = _MapBuilder(Pu.nnz, n_theta)
+    Pu.sort_indices()
+    for k, v in enumerate(Pu.data):
+        mb.const(k, v)
+    maps['P'] = mb.csr()
+    mb = _MapBuilder(A.nnz, n_theta)
+    for k, v in enumerate(A.data):
+        mb.const(k, v)
+    maps['A'] = mb.csr()
+    mq, ml, mu = _MapBuilder(n, n_theta), _MapBuilder(m, n_theta), _MapBuilder(m, n_theta)
+    for i in range(n):
+        mq.add(i, params[0].col + i, 1.0)
+    for j in range(m):
+        ml.add(j, params[1].col + j, 1.0); mu.add(j, params[2].col + j, 1.0)
+    maps['q'], maps['l'], maps['u'] = mq.csr(), ml.csr(), mu.csr()
+    maps['d'] = sp.csr_matrix((1, n_theta))
+    return CanonFamily(name or f'box_qp_{n}_{m}', 'quadratic', n, 0, m, params, maps,
+                       {'P': _csc_pattern(Pu), 'A': _csc_pattern(A)}, [UserVar('x', (n,), np.arange(n))],
+                       [UserDual('d0', 'y', (m,), np.arange(m))])

@@ -17,6 +17,7 @@ STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
     'mpc_6_3_10': (lambda: families.mpc(6, 3, 10), ['x_init']),             # the reference test's MPC size
     'nonneg_LS_3_2': (lambda: families.nonneg_ls(3, 2), ['b']),             # BASELINE config 1 (README example)
     'random_qp_20_5_15': (lambda: families.random_qp(20, 5, 15), ['q', 'b', 'h']),  # unstructured sparsity, q/l/u all batched
+    'box_qp_6_8': (lambda: families.box_qp(6, 8), ['q', 'l', 'u']),          # corner cases: type changes, infeasibility
 }
 
 

@@ -65,13 +65,18 @@ def rel_err(a, b):
     return np.linalg.norm(a - b, axis=1) / np.maximum(nb, 1e-12)
 
 
-def assert_batch_parity(got_x, got_y, got_info, ora, tol, eps_abs=1e-3):
-    """got_info: object with status, iter, obj_val, pri_res, dua_res arrays."""
+def assert_batch_parity(got_x, got_y, got_info, ora, tol, eps_abs=1e-3, stable=None):
+    """got_info: object with status, iter, obj_val, pri_res, dua_res arrays.
+    stable: optional boolean mask of the instances on which the comparison is meaningful (see rounding_stable)."""
     st = np.asarray(got_info.status)
     assert (st != -100).all(), 'instances left in the hand-off state: the tail kernel did not run'
-    assert (st == ora['status']).all(), f"status mismatch at {np.nonzero(st != ora['status'])[0][:5]}"
-    assert (np.asarray(got_info.iter) == ora['iter']).all(), f"iter mismatch at {np.nonzero(got_info.iter != ora['iter'])[0][:5]}"
-    sol = np.isin(st, [1, 2, -2])
+    if stable is None:
+        stable = np.ones(len(st), bool)
+    bad = stable & (st != ora['status'])
+    assert not bad.any(), f"status mismatch at {np.nonzero(bad)[0][:5]}"
+    bad = stable & (np.asarray(got_info.iter) != ora['iter'])
+    assert not bad.any(), f"iter mismatch at {np.nonzero(bad)[0][:5]}"
+    sol = np.isin(st, [1, 2, -2]) & stable
     if sol.any():
         assert rel_err(got_x[sol], ora['x'][sol]).max() < tol
         assert rel_err(got_y[sol], ora['y'][sol]).max() < tol
@@ -79,7 +84,16 @@ def assert_batch_parity(got_x, got_y, got_info, ora, tol, eps_abs=1e-3):
         # residuals are differences of O(1) numbers: compare on the scale of the stopping tolerance
         assert np.allclose(got_info.pri_res[sol], ora['pri_res'][sol], rtol=1e-5, atol=1e-3 * eps_abs)
         assert np.allclose(got_info.dua_res[sol], ora['dua_res'][sol], rtol=1e-5, atol=1e-3 * eps_abs)
-    nos = ~sol
+    nos = ~np.isin(st, [1, 2, -2]) & stable
     if nos.any():
         assert np.isnan(got_x[nos]).all() and np.isnan(got_y[nos]).all()
     return sol
+
+
+def rounding_stable(fam, q, l, u, ora, **settings):
+    """Instances on which the compiled reference and the numpy restatement -- the same algorithm with a different, equally
+    exact KKT solve -- stop at the same iteration.  A handful of ill-conditioned instances (e.g. loose rows, rho = 1e-6,
+    several rho updates, hundreds of iterations) amplify rounding differences into different stopping iterations; for
+    those "the reference's result" is itself not defined to 1e-5 and they are excluded from the comparison."""
+    o2 = oracle_for(fam, **settings).solve_batch(q=q, l=l, u=u)
+    return (o2['iter'] == ora['iter']) & (o2['status'] == ora['status'])

@@ -126,3 +126,46 @@ def test_full_size_properties():
     res2 = mod.solve_batch({'x_init': params['x_init'][perm]}, return_canonical=True)
     assert np.array_equal(res2.sol_x, res.sol_x[perm]) or np.allclose(res2.sol_x, res.sol_x[perm], rtol=0, atol=1e-9)
     assert np.array_equal(res2.cpg_info.iter, res.cpg_info.iter[perm])
+
+
+def corner_case_batch(fam, B, seed=13):
+    """box_qp instances: regular, equality-collapsed rows, loose rows, primal infeasible, dual infeasible."""
+    rng = np.random.default_rng(seed)
+    pq, pl, pu = (fam.param(k) for k in ('q', 'l', 'u'))
+    q = np.asarray(pq.default)[None] + 0.3 * rng.standard_normal((B, pq.size)); q[:, -1] = 0.0
+    mid = 0.5 * (np.asarray(pl.default) + np.asarray(pu.default))[None] + 0.2 * rng.standard_normal((B, pl.size))
+    half = 0.3 + rng.random((B, pl.size))
+    l, u = mid - half, mid + half
+    kind = np.arange(B) % 5
+    for b in range(B):
+        if kind[b] == 1:                       # some rows become equalities (u - l < 1e-4)
+            rows = rng.choice(np.arange(2, pl.size), 2, replace=False); l[b, rows] = u[b, rows] = mid[b, rows]
+        elif kind[b] == 2:                     # some rows become loose
+            rows = rng.choice(np.arange(2, pl.size), 2, replace=False); l[b, rows] = -1e30; u[b, rows] = 1e30
+        elif kind[b] == 3:                     # parallel rows 0, 1 with crossing bounds: primal infeasible
+            l[b, 0] = 2.0; u[b, 0] = 3.0; l[b, 1] = -1.0; u[b, 1] = 1.0
+        elif kind[b] == 4:                     # cost on the free, curvature-less variable: dual infeasible
+            q[b, -1] = 1.0 + rng.random()
+    return {'q': q, 'l': l, 'u': u}, kind
+
+
+@pytest.mark.gpu
+def test_corner_cases_type_changes_and_infeasibility():
+    """Per-instance constraint-type changes (routed to the tail kernel with their own KKT factor), primal and dual
+    infeasibility certificates (NaN solution, +-1e30 objective): statuses, iteration counts and solutions vs the oracle."""
+    from helpers import canon_batches
+    name, B = 'box_qp_6_8', 320
+    fam = standard.STANDARD[name][0]()
+    params, kind = corner_case_batch(fam, B)
+    q, l, u = canon_batches(fam, params, B)
+    mod = standard.load(name)
+    res = mod.solve_batch(params, return_canonical=True)
+    ora = oracle_solve(fam, q, l, u)
+    assert set(np.unique(ora['status'])) >= {1, -3, -4}
+    assert (ora['status'][kind == 3] == -3).all() and (ora['status'][kind == 4] == -4).all()
+    from helpers import rounding_stable
+    stable = rounding_stable(fam, q, l, u, ora)
+    assert stable.mean() > 0.98
+    assert_batch_parity(res.sol_x, res.sol_y, res.cpg_info, ora, TOL, stable=stable)
+    assert (res.cpg_info.status == ora['status']).all()          # statuses agree even on the unstable ones
+    assert (res.cpg_info.obj_val[kind == 3] == 1e30).all() and (res.cpg_info.obj_val[kind == 4] == -1e30).all()
