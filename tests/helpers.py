@@ -25,6 +25,8 @@ def family_and_batch(name, B, seed=1):
             params[pn] = rng.uniform(-1, 1, (B, p.size))
         else:
             params[pn] = np.asarray(p.default)[None, :] + 0.3 * rng.standard_normal((B, p.size))
+    if name.startswith('box_qp'):
+        params['q'][:, -1] = 0.0          # keep the curvature-less variable free of cost: bounded instances
     return fam, params, canon_batches(fam, params, B)
 
 

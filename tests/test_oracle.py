@@ -90,9 +90,11 @@ def test_numpy_oracle_matches_golden(name, tag, kw):
     assert (r['status'] == g[f'{tag}_status'][:B]).all()
     assert (r['iter'] == g[f'{tag}_iter'][:B]).all()
     assert (r['rho_updates'] == g[f'{tag}_rho_updates'][:B]).all()
-    assert rel_err(r['x'], g[f'{tag}_x'][:B]).max() < 1e-9
-    assert rel_err(r['y'], g[f'{tag}_y'][:B]).max() < 1e-8
-    assert np.allclose(r['obj'], g[f'{tag}_obj'][:B], rtol=1e-9, atol=1e-11)
+    ok = np.isin(r['status'], [1, 2, -2])      # no-solution statuses: OSQP 0.6.2 stores (c_float)0x7fc00000UL = 2143289344.0
+    assert ok.any()                            # (include/constants.h:96), the restatement and the kernel store an IEEE NaN
+    assert rel_err(r['x'][ok], g[f'{tag}_x'][:B][ok]).max() < 1e-9
+    assert rel_err(r['y'][ok], g[f'{tag}_y'][:B][ok]).max() < 1e-8
+    assert np.allclose(r['obj'][ok], g[f'{tag}_obj'][:B][ok], rtol=1e-9, atol=1e-11)
 
 
 @pytest.mark.skipif(not ref_available(), reason='oracle/_ref/libosqp_ref.so not built')
