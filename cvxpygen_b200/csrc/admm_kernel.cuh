@@ -1,5 +1,5 @@
 // admm_kernel.cuh -- shared device helpers + the one-instance-per-warp ADMM solver used by the TAIL kernel
-// (per-instance KKT factor).  The main kernel (two instances per warp) is admm_pair_kernel.cuh.
+// (per-instance KKT factor).  The main kernel (NI instances per warp) is admm_multi_kernel.cuh.
 //
 // Hand-written device code shared by every generated problem family; the generator emits
 // only compile-time sizes (cpg_family.h), the blob-header struct (cpg_blob_layout.h) and the

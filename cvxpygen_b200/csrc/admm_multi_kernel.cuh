@@ -1,0 +1,646 @@
+// admm_multi_kernel.cuh -- main batched ADMM kernel for sm_100a: NI problem instances per warp (NI = 2 or 4).
+//
+// Why several instances per warp: ncu on the one-instance-per-warp version showed the kernel bound by shared-memory
+// bandwidth (71 % of peak wavefronts; profiles/r1_v1_ncu_summary.md): every inner step of the KKT-solve schedule loads
+// one 8-byte coefficient per lane and uses it once.  Register-blocking NI instances makes every coefficient (and index)
+// loaded from shared memory feed NI FMAs; the instances' work vectors are interleaved (wN[pos * NI + s]) so that one or
+// two LDS.128 fetch all operands.  The chain part of the schedule is encoded as DENSE tiles whose lanes read the same
+// wN address (a shared-memory broadcast) and load no index at all; the whole schedule is emitted as straight-line
+// code with immediate offsets (cpg_kkt_solve_gen.cuh, offline/emit_solve.py).
+//
+// The NI slots of a warp are independent instances: each has its own iteration counter, termination check and
+// epilogue; when one terminates its slot is refilled from the global instance queue at once.
+// State per slot in registers: x, z, y (lane i%32 owns element i).  q, l, u are NOT kept in registers: rows that do
+// not depend on a batched parameter are read from the constants blob (already scaled), rows that do are read from a
+// small per-warp table written by the slot's prologue.
+// Everything that happens once per instance or once per check_termination iterations (prologue, residuals,
+// termination + infeasibility tests, hand-off, epilogue) is written for SLOT 0 only; the slots are brought to
+// position 0 one after the other by rotating the register state.  That keeps the cold code NI times smaller (the hot
+// loop shares the instruction cache with it) at the cost of ~100 register moves per rotation.
+//
+// Reference functions restated: same list as admm_kernel.cuh (a1-a12); the per-instance arithmetic and its order are
+// those of the single-instance path, so iterates agree with it bit for bit.
+#pragma once
+#include "admm_kernel.cuh"
+
+namespace cpgb200 {
+
+template <int NI> struct MultiOps;
+template <> struct MultiOps<2> {
+  static __device__ __forceinline__ void ld(const double* p, double (&o)[2]) {
+    const double2 a = *reinterpret_cast<const double2*>(p); o[0] = a.x; o[1] = a.y;
+  }
+  static __device__ __forceinline__ void st(double* p, const double (&v)[2]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+  }
+};
+template <> struct MultiOps<4> {
+  static __device__ __forceinline__ void ld(const double* p, double (&o)[4]) {
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+  }
+  static __device__ __forceinline__ void st(double* p, const double (&v)[4]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+  }
+};
+
+}  // namespace cpgb200
+#include "cpg_kkt_solve_gen.cuh"     // straight-line schedule of this family, template <int NI>
+namespace cpgb200 {
+
+// row-blocked ELL sparse mat-vec on an interleaved multi-vector; returns the result for column 0 only
+template <int NI>
+__device__ __forceinline__ double ell_dot_col0(const int* tab, const double* F64, const uint16_t* U16,
+                                               const double* vecN, int lane) {
+  const int K = tab[0];
+  const double* v = F64 + tab[1] + lane;
+  const uint16_t* c = U16 + tab[2] + lane;
+  double a = 0.0;
+  for (int k = 0; k < K; ++k) a = fma(v[k * LANES], vecN[NI * c[k * LANES]], a);
+  return a;
+}
+
+template <class Fam, int NI>
+__device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __restrict__ I32,
+                            const double* __restrict__ F64, const uint16_t* __restrict__ U16,
+                            double* __restrict__ wN, double* __restrict__ bv, const int lane,
+                            const BatchIO& io, const Settings& st) {
+  constexpr int N = Fam::N, M = Fam::M, NXL = (N + 31) / 32, NZL = (M + 31) / 32, NZLs = NZL > 0 ? NZL : 1;
+  using MO = MultiOps<NI>;
+  const double* Dv = F64 + H->f_D;  const double* Dinv = F64 + H->f_Dinv;
+  const double* Ev = F64 + H->f_E;  const double* Einv = F64 + H->f_Einv;
+  const double c = H->c, cinv = H->cinv, sigma = H->sigma, alpha = st.alpha;
+  const bool unscale = st.scaling && !st.scaled_termination;
+  const double rho_in = H->rho, rho_eq = RHO_EQ_FACTOR * H->rho;
+  const double rinv_in = 1.0 / rho_in, rinv_eq = 1.0 / rho_eq, rinv_loose = 1.0 / RHO_MIN;
+
+  // ---- per-lane constants of the family (identical for every instance), read from the blob when needed
+  // addr tables: >= 0 index into the F64 area (row constant over the batch); < 0 -(slot+1) in the per-warp table bv.
+  const uint16_t* PX = U16 + H->h_pinvx + lane;
+  const uint16_t* PZ = U16 + H->h_pinvz + lane;
+  const int* AQ = I32 + H->i_addr_q + lane;
+  const int* AL = I32 + H->i_addr_l + lane;
+  const int* AU = I32 + H->i_addr_u + lane;
+  unsigned eqmask = 0u, loosemask = 0u;
+#pragma unroll
+  for (int k = 0; k < NZL; ++k) {
+    const int j = lane + 32 * k;
+    if (j < M) {
+      const int ct = U16[H->h_ctype + j];
+      if (ct == 2) eqmask |= 1u << k;
+      if (ct == 0) loosemask |= 1u << k;
+    }
+  }
+  auto tabN = [&](const int* T, int k, double (&o)[NI]) __attribute__((always_inline)) {
+    const int a = T[32 * k];
+    if (a >= 0) {
+      const double v = F64[a];
+#pragma unroll
+      for (int s = 0; s < NI; ++s) o[s] = v;
+    } else MO::ld(bv + NI * (-a - 1), o);
+  };
+  auto tab0 = [&](const int* T, int k) __attribute__((always_inline)) -> double {       // slot 0 only
+    const int a = T[32 * k];
+    return (a >= 0) ? F64[a] : bv[NI * (-a - 1)];
+  };
+  auto rinv_of = [&](int k) __attribute__((always_inline)) -> double {
+    return ((loosemask >> k) & 1u) ? rinv_loose : (((eqmask >> k) & 1u) ? rinv_eq : rinv_in); };
+  auto rho_of = [&](int k) __attribute__((always_inline)) -> double {
+    return ((loosemask >> k) & 1u) ? RHO_MIN : (((eqmask >> k) & 1u) ? rho_eq : rho_in); };
+
+  // ---- per-slot state
+  double x[NI][NXL], z[NI][NZLs], y[NI][NZLs];
+  int inst[NI], it[NI];
+  bool active[NI];
+  bool exhausted = false;
+#pragma unroll
+  for (int s = 0; s < NI; ++s) {
+    inst[s] = -1; it[s] = 0; active[s] = false;
+#pragma unroll
+    for (int k = 0; k < NXL; ++k) x[s][k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NZLs; ++k) { z[s][k] = 0.0; y[s][k] = 0.0; }
+  }
+
+  // bring slot s+1 to position s (cyclically) -- registers and the per-warp batched-row table
+  auto rotate_state = [&]() __attribute__((always_inline)) {
+#pragma unroll
+    for (int k = 0; k < NXL; ++k) { const double t = x[0][k];
+#pragma unroll
+      for (int s = 0; s + 1 < NI; ++s) x[s][k] = x[s + 1][k];
+      x[NI - 1][k] = t; }
+#pragma unroll
+    for (int k = 0; k < NZLs; ++k) { const double t = z[0][k], u = y[0][k];
+#pragma unroll
+      for (int s = 0; s + 1 < NI; ++s) { z[s][k] = z[s + 1][k]; y[s][k] = y[s + 1][k]; }
+      z[NI - 1][k] = t; y[NI - 1][k] = u; }
+    { const int t = inst[0], u = it[0]; const bool a = active[0];
+#pragma unroll
+      for (int s = 0; s + 1 < NI; ++s) { inst[s] = inst[s + 1]; it[s] = it[s + 1]; active[s] = active[s + 1]; }
+      inst[NI - 1] = t; it[NI - 1] = u; active[NI - 1] = a; }
+    const int nb = H->nb_slots;
+    for (int r = lane; r < nb; r += LANES) {
+      double v[NI], w[NI];
+      MO::ld(bv + NI * r, v);
+#pragma unroll
+      for (int s = 0; s < NI; ++s) w[s] = v[(s + 1) % NI];
+      MO::st(bv + NI * r, w);
+    }
+    __syncwarp();
+  };
+
+  // ================================================================ slot-0 routines (cold path)
+  // a1-a3: canonicalise the batched rows of slot 0, scale them, detect constraint-type changes
+  auto load_instance0 = [&](int b) __attribute__((always_inline)) -> bool {
+    const double* th = io.params + (size_t)b * H->npb;
+    const int nbq = H->n_bq, nbc = H->n_bc;
+    for (int r = lane; r < nbq; r += LANES) {
+      const int i = U16[H->h_bq_row + r];
+      double acc = F64[H->f_qbase + i];
+      for (int e = I32[H->i_bq_ptr + r]; e < I32[H->i_bq_ptr + r + 1]; ++e)
+        acc = fma(F64[H->f_bq_val + e], __ldg(th + U16[H->h_bq_col + e]), acc);
+      bv[NI * r] = (Dv[i] * acc) * c;
+    }
+    bool mismatch = false;
+    for (int r = lane; r < nbc; r += LANES) {
+      const int j = U16[H->h_bc_row + r];
+      double al = F64[H->f_lbase + j], au = F64[H->f_ubase + j];
+      for (int e = I32[H->i_bl_ptr + r]; e < I32[H->i_bl_ptr + r + 1]; ++e)
+        al = fma(F64[H->f_bl_val + e], __ldg(th + U16[H->h_bl_col + e]), al);
+      for (int e = I32[H->i_bu_ptr + r]; e < I32[H->i_bu_ptr + r + 1]; ++e)
+        au = fma(F64[H->f_bu_val + e], __ldg(th + U16[H->h_bu_col + e]), au);
+      al = Ev[j] * fmin(fmax(al, -OSQP_INFTY), OSQP_INFTY);
+      au = Ev[j] * fmin(fmax(au, -OSQP_INFTY), OSQP_INFTY);
+      bv[NI * (nbq + r)] = al;
+      bv[NI * (nbq + nbc + r)] = au;
+      const bool loose = (al < -OSQP_INFTY * MIN_SCALING) && (au > OSQP_INFTY * MIN_SCALING);
+      const bool eq = !loose && (au - al < RHO_TOL);
+      mismatch |= ((loose ? 0 : (eq ? 2 : 1)) != (int)U16[H->h_ctype + j]);
+    }
+    __syncwarp();
+    return __any_sync(FULL, mismatch);
+  };
+
+  // residuals + norms of slot 0's current iterate (update_info, auxil.c:564-629)
+  double pri_res, dua_res, xPx, qx, nrm_z, nrm_Ax, nrm_q, nrm_Aty, nrm_Px, s_rp, s_rd, s_z, s_Ax, s_q, s_Aty, s_Px;
+  auto update_info0 = [&]() __attribute__((always_inline)) {
+#pragma unroll
+    for (int k = 0; k < NXL; ++k) { const int i = lane + 32 * k; if (i < N) wN[NI * i] = x[0][k]; }
+#pragma unroll
+    for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) wN[NI * (N + j)] = y[0][k]; }
+    __syncwarp();
+    double m_rp = 0, m_z = 0, m_Ax = 0, ms_rp = 0, ms_z = 0, ms_Ax = 0;
+#pragma unroll
+    for (int k = 0; k < NZL; ++k) {
+      const int j = lane + 32 * k;
+      if (j < M) {
+        const double Ax = ell_dot_col0<NI>(I32 + H->i_ellA + 3 * k, F64, U16, wN, lane);
+        const double rp = Ax - z[0][k];
+        const double e = unscale ? Einv[j] : 1.0;
+        m_rp = fmax(m_rp, fabs(e * rp)); m_z = fmax(m_z, fabs(e * z[0][k])); m_Ax = fmax(m_Ax, fabs(e * Ax));
+        ms_rp = fmax(ms_rp, fabs(rp)); ms_z = fmax(ms_z, fabs(z[0][k])); ms_Ax = fmax(ms_Ax, fabs(Ax));
+      }
+    }
+    double m_rd = 0, m_q = 0, m_Aty = 0, m_Px = 0, ms_rd = 0, ms_q = 0, ms_Aty = 0, ms_Px = 0, a_xPx = 0, a_qx = 0;
+#pragma unroll
+    for (int k = 0; k < NXL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < N) {
+        const double Px = ell_dot_col0<NI>(I32 + H->i_ellP + 3 * k, F64, U16, wN, lane);
+        const double Aty = (M > 0) ? ell_dot_col0<NI>(I32 + H->i_ellAt + 3 * k, F64, U16, wN, lane) : 0.0;
+        const double qv = tab0(AQ, k);
+        const double rd = qv + Px + Aty;
+        const double d = unscale ? Dinv[i] : 1.0;
+        m_rd = fmax(m_rd, fabs(d * rd)); m_q = fmax(m_q, fabs(d * qv));
+        m_Aty = fmax(m_Aty, fabs(d * Aty)); m_Px = fmax(m_Px, fabs(d * Px));
+        ms_rd = fmax(ms_rd, fabs(rd)); ms_q = fmax(ms_q, fabs(qv));
+        ms_Aty = fmax(ms_Aty, fabs(Aty)); ms_Px = fmax(ms_Px, fabs(Px));
+        a_xPx = fma(x[0][k], Px, a_xPx); a_qx = fma(qv, x[0][k], a_qx);
+      }
+    }
+    __syncwarp();
+    const double cs = unscale ? cinv : 1.0;
+    pri_res = (M > 0) ? warp_max(m_rp) : 0.0;
+    nrm_z = warp_max(m_z); nrm_Ax = warp_max(m_Ax);
+    dua_res = cs * warp_max(m_rd);
+    nrm_q = warp_max(m_q); nrm_Aty = warp_max(m_Aty); nrm_Px = warp_max(m_Px);
+    s_rp = warp_max(ms_rp); s_z = warp_max(ms_z); s_Ax = warp_max(ms_Ax);
+    s_rd = warp_max(ms_rd); s_q = warp_max(ms_q); s_Aty = warp_max(ms_Aty); s_Px = warp_max(ms_Px);
+    xPx = warp_sum(a_xPx); qx = warp_sum(a_qx);
+  };
+
+  // check_termination for slot 0 (auxil.c:681-786); dx0, dy0 = last step of slot 0
+  auto check_termination0 = [&](const double (&dx0)[NXL], const double (&dy0)[NZLs], bool approximate)
+      __attribute__((always_inline)) -> int {
+    double ea = st.eps_abs, er = st.eps_rel, epi = st.eps_prim_inf, edi = st.eps_dual_inf;
+    if (approximate) { ea *= 10; er *= 10; epi *= 10; edi *= 10; }
+    if (pri_res > OSQP_INFTY || dua_res > OSQP_INFTY) return ST_NONCVX;
+    const double cs = unscale ? cinv : 1.0;
+    bool prim_ok, prim_inf = false, dual_inf = false;
+    if (M == 0) prim_ok = true;
+    else {
+      prim_ok = pri_res < ea + er * fmax(nrm_z, nrm_Ax);
+      if (!prim_ok) {               // is_primal_infeasible, auxil.c:361-424
+        double dproj[NZLs];
+        double nd = 0, lhs = 0;
+#pragma unroll
+        for (int k = 0; k < NZL; ++k) {
+          const int j = lane + 32 * k;
+          double d = 0.0;
+          if (j < M) {
+            d = dy0[k];
+            const double lv = tab0(AL, k), uv = tab0(AU, k);
+            const bool up_inf = uv > OSQP_INFTY * MIN_SCALING, lo_inf = lv < -OSQP_INFTY * MIN_SCALING;
+            if (up_inf) d = lo_inf ? 0.0 : fmin(d, 0.0);
+            else if (lo_inf) d = fmax(d, 0.0);
+            nd = fmax(nd, fabs(unscale ? Ev[j] * d : d));
+            lhs += uv * fmax(d, 0.0) + lv * fmin(d, 0.0);
+          }
+          dproj[k] = d;
+        }
+        nd = warp_max(nd);
+        if (nd > DIVISION_TOL) {
+          lhs = warp_sum(lhs);
+          if (lhs < epi * nd) {
+#pragma unroll
+            for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) wN[NI * (N + j)] = dproj[k]; }
+            __syncwarp();
+            double mx = 0;
+#pragma unroll
+            for (int k = 0; k < NXL; ++k) {
+              const int i = lane + 32 * k;
+              if (i < N) {
+                double v = ell_dot_col0<NI>(I32 + H->i_ellAt + 3 * k, F64, U16, wN, lane);
+                if (unscale) v *= Dinv[i];
+                mx = fmax(mx, fabs(v));
+              }
+            }
+            __syncwarp();
+            prim_inf = warp_max(mx) < epi * nd;
+          }
+        }
+      }
+    }
+    const bool dual_ok = dua_res < ea + er * cs * fmax(fmax(nrm_q, nrm_Aty), nrm_Px);
+    if (!dual_ok) {                 // is_dual_infeasible, auxil.c:426-512
+      double nd = 0, qd = 0;
+#pragma unroll
+      for (int k = 0; k < NXL; ++k) {
+        const int i = lane + 32 * k;
+        if (i < N) { nd = fmax(nd, fabs(unscale ? Dv[i] * dx0[k] : dx0[k])); qd = fma(tab0(AQ, k), dx0[k], qd); }
+      }
+      nd = warp_max(nd);
+      const double cost_scaling = unscale ? c : 1.0;
+      if (nd > DIVISION_TOL) {
+        qd = warp_sum(qd);
+        if (qd < cost_scaling * edi * nd) {
+#pragma unroll
+          for (int k = 0; k < NXL; ++k) { const int i = lane + 32 * k; if (i < N) wN[NI * i] = dx0[k]; }
+          __syncwarp();
+          double mx = 0;
+#pragma unroll
+          for (int k = 0; k < NXL; ++k) {
+            const int i = lane + 32 * k;
+            if (i < N) {
+              double v = ell_dot_col0<NI>(I32 + H->i_ellP + 3 * k, F64, U16, wN, lane);
+              if (unscale) v *= Dinv[i];
+              mx = fmax(mx, fabs(v));
+            }
+          }
+          if (warp_max(mx) < cost_scaling * edi * nd) {
+            bool bad = false;
+#pragma unroll
+            for (int k = 0; k < NZL; ++k) {
+              const int j = lane + 32 * k;
+              if (j < M) {
+                double v = ell_dot_col0<NI>(I32 + H->i_ellA + 3 * k, F64, U16, wN, lane);
+                if (unscale) v *= Einv[j];
+                bad |= ((tab0(AU, k) < OSQP_INFTY * MIN_SCALING) && (v > edi * nd)) ||
+                       ((tab0(AL, k) > -OSQP_INFTY * MIN_SCALING) && (v < -edi * nd));
+              }
+            }
+            dual_inf = !__any_sync(FULL, bad);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (prim_ok && dual_ok) return approximate ? ST_SOLVED_INACC : ST_SOLVED;
+    if (prim_inf) return approximate ? ST_PINF_INACC : ST_PINF;
+    if (dual_inf) return approximate ? ST_DINF_INACC : ST_DINF;
+    return ST_UNSOLVED;
+  };
+
+  // hand slot 0 to the tail kernel (own KKT factor needed)
+  auto hand_off0 = [&](double rho_new) __attribute__((always_inline)) {
+    const int b = inst[0];
+    int slot = -1;
+    if (lane == 0) slot = atomicAdd(io.tail_count, 1);
+    slot = __shfl_sync(FULL, slot, 0);
+    if (lane == 0) { io.status[b] = ST_HANDOFF; io.iter[b] = it[0]; }
+    if (slot < io.tail_capacity) {
+      double* ts = io.tail_state + (size_t)slot * (N + 2 * M + 2);
+#pragma unroll
+      for (int k = 0; k < NXL; ++k) { const int i = lane + 32 * k; if (i < N) ts[i] = x[0][k]; }
+#pragma unroll
+      for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) { ts[N + j] = z[0][k]; ts[N + M + j] = y[0][k]; } }
+      if (lane == 0) { ts[N + 2 * M] = rho_new; ts[N + 2 * M + 1] = (double)it[0]; io.tail_ids[slot] = b; }
+    }
+  };
+
+  // store_solution / unscale / retrieval for slot 0 (a11, a12)
+  auto finish0 = [&](int status) __attribute__((always_inline)) {
+    const int b = inst[0];
+    const bool has_sol = !(status == ST_PINF || status == ST_PINF_INACC || status == ST_DINF ||
+                           status == ST_DINF_INACC || status == ST_NONCVX);
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+    for (int k = 0; k < NXL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < N) {
+        const double xv = has_sol ? Dv[i] * x[0][k] : qnan;
+        wN[NI * i] = xv;
+        if (io.sol_x) io.sol_x[(size_t)b * N + i] = xv;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NZL; ++k) {
+      const int j = lane + 32 * k;
+      if (j < M) {
+        const double yv = has_sol ? (Ev[j] * y[0][k]) * cinv : qnan;
+        wN[NI * (N + j)] = yv;
+        if (io.sol_y) io.sol_y[(size_t)b * M + j] = yv;
+      }
+    }
+    __syncwarp();
+    if (io.prim) {
+      const int np = H->n_prim;
+      for (int k = lane; k < np; k += LANES) io.prim[(size_t)b * np + k] = wN[NI * U16[H->h_prim + k]];
+    }
+    if (io.dual) {
+      const int nd = H->n_dual;
+      for (int k = lane; k < nd; k += LANES) io.dual[(size_t)b * nd + k] = wN[NI * (N + U16[H->h_dual + k])];
+    }
+    __syncwarp();
+    if (lane == 0) {
+      double obj = (0.5 * xPx + qx);
+      if (st.scaling) obj *= cinv;
+      if (status == ST_PINF || status == ST_PINF_INACC) obj = OSQP_INFTY;
+      else if (status == ST_DINF || status == ST_DINF_INACC) obj = -OSQP_INFTY;
+      else if (status == ST_NONCVX) obj = qnan;
+      else obj = (H->is_max ? -1.0 : 1.0) * (obj + H->d_const);
+      io.obj_val[b] = obj; io.iter[b] = it[0]; io.status[b] = status;
+      io.pri_res[b] = pri_res; io.dua_res[b] = dua_res;
+    }
+  };
+
+  // fetch instances into slot 0 until one is accepted (or the queue is empty)
+  auto refill0 = [&]() __attribute__((always_inline)) {
+    while (!active[0] && !exhausted) {
+      unsigned b = 0;
+      if (lane == 0) b = atomicAdd(io.work_counter, 1u);
+      b = __shfl_sync(FULL, b, 0);
+      if (b >= (unsigned)io.B) { exhausted = true; break; }
+      inst[0] = (int)b; it[0] = 0;
+      const bool mismatch = load_instance0((int)b);
+      // cold start (auxil.c:155-159) or warm start (osqp.c:929-953)
+      if (st.warm_start && io.x0 != nullptr && io.y0 != nullptr) {
+#pragma unroll
+        for (int k = 0; k < NXL; ++k) {
+          const int i = lane + 32 * k;
+          if (i < N) { x[0][k] = Dinv[i] * io.x0[(size_t)b * N + i]; wN[NI * i] = x[0][k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) y[0][k] = (Einv[j] * io.y0[(size_t)b * M + j]) * c; }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) z[0][k] = ell_dot_col0<NI>(I32 + H->i_ellA + 3 * k, F64, U16, wN, lane); }
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int k = 0; k < NXL; ++k) x[0][k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NZLs; ++k) { z[0][k] = 0.0; y[0][k] = 0.0; }
+      }
+      if (mismatch) { hand_off0(rho_in); continue; }     // a constraint changed type: needs its own factor
+      if (st.max_iter <= 0) {                             // degenerate setting: report the start point
+        double dx0[NXL], dy0[NZLs];
+#pragma unroll
+        for (int k = 0; k < NXL; ++k) dx0[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NZLs; ++k) dy0[k] = 0.0;
+        update_info0();
+        int status = check_termination0(dx0, dy0, false);
+        if (status == ST_UNSOLVED) { status = check_termination0(dx0, dy0, true); if (status == ST_UNSOLVED) status = ST_MAXITER; }
+        finish0(status);
+        continue;
+      }
+      active[0] = true;
+    }
+  };
+
+  // ================================================================ main loop
+  for (;;) {
+    // All warps of the CTA run the same ~50 KB of straight-line code per iteration; without this barrier they drift
+    // apart and every warp misses the instruction cache on its own (ncu: stall_no_instruction 4.4 cycles/issue).
+    // Iteration counts are multiples of check_termination for every instance, so the warps' check iterations coincide.
+    bool any_active = false, any_free = false;
+#pragma unroll
+    for (int s = 0; s < NI; ++s) { any_active |= active[s]; any_free |= !active[s]; }
+    if (!__syncthreads_or((int)(!exhausted || any_active))) break;
+    if (any_free && !exhausted) {                        // refill empty slots, one rotation at a time
+#pragma unroll 1
+      for (int r = 0; r < NI; ++r) { refill0(); rotate_state(); }
+      any_active = false;
+#pragma unroll
+      for (int s = 0; s < NI; ++s) any_active |= active[s];
+    }
+    if (!any_active) continue;    // nothing left for this warp: keep meeting the others at the barrier
+
+    // which slots evaluate their residuals after this iteration
+    bool chk[NI], adp[NI];
+    bool any_chk = false;
+#pragma unroll
+    for (int s = 0; s < NI; ++s) {
+      const int itn = it[s] + 1;
+      const bool can_check = st.check_termination && (itn % st.check_termination == 0);
+      adp[s] = active[s] && st.adaptive_rho && st.adaptive_rho_interval && (itn % st.adaptive_rho_interval == 0);
+      chk[s] = active[s] && (can_check || itn == st.max_iter);
+      any_chk |= chk[s] || adp[s];
+    }
+
+    // ---- one ADMM iteration for all slots (osqp.c:354-372): rhs, KKT solve
+#pragma unroll
+    for (int k = 0; k < NXL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < N) {
+        double qv[NI], r[NI];
+        tabN(AQ, k, qv);
+#pragma unroll
+        for (int s = 0; s < NI; ++s) r[s] = sigma * x[s][k] - qv[s];
+        MO::st(wN + NI * PX[32 * k], r);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NZL; ++k) {
+      const int j = lane + 32 * k;
+      if (j < M) {
+        const double ri = rinv_of(k);
+        double r[NI];
+#pragma unroll
+        for (int s = 0; s < NI; ++s) r[s] = z[s][k] - ri * y[s][k];
+        MO::st(wN + NI * PZ[32 * k], r);
+      }
+    }
+    __syncwarp();
+    cpg_kkt_solve_gen<NI>(F64, I32, U16, wN, lane);
+
+    if (!any_chk) {
+      // ---- update_x, update_z (+project), update_y (auxil.c:185-225)
+#pragma unroll
+      for (int k = 0; k < NXL; ++k) {
+        const int i = lane + 32 * k;
+        if (i < N) {
+          double xt[NI];
+          MO::ld(wN + NI * PX[32 * k], xt);
+#pragma unroll
+          for (int s = 0; s < NI; ++s) x[s][k] = alpha * xt[s] + (1.0 - alpha) * x[s][k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NZL; ++k) {
+        const int j = lane + 32 * k;
+        if (j < M) {
+          const double ri = rinv_of(k), r = rho_of(k);
+          double nu[NI], lv[NI], uv[NI];
+          MO::ld(wN + NI * PZ[32 * k], nu);
+          tabN(AL, k, lv); tabN(AU, k, uv);
+#pragma unroll
+          for (int s = 0; s < NI; ++s) {
+            const double zt = (z[s][k] - ri * y[s][k]) + ri * nu[s];
+            const double v = alpha * zt + (1.0 - alpha) * z[s][k];
+            const double zn = fmin(fmax(v + ri * y[s][k], lv[s]), uv[s]);
+            y[s][k] += r * (v - zn);
+            z[s][k] = zn;
+          }
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < NI; ++s) it[s] += active[s] ? 1 : 0;
+      continue;
+    }
+
+    // ---- same update, keeping the step (dx, dy) for the infeasibility tests of this check iteration
+    double dx[NI][NXL], dy[NI][NZLs];
+#pragma unroll
+    for (int k = 0; k < NXL; ++k) {
+      const int i = lane + 32 * k;
+#pragma unroll
+      for (int s = 0; s < NI; ++s) dx[s][k] = 0.0;
+      if (i < N) {
+        double xt[NI];
+        MO::ld(wN + NI * PX[32 * k], xt);
+#pragma unroll
+        for (int s = 0; s < NI; ++s) {
+          const double xn = alpha * xt[s] + (1.0 - alpha) * x[s][k];
+          dx[s][k] = xn - x[s][k];
+          x[s][k] = xn;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NZLs; ++k) {
+      const int j = lane + 32 * k;
+#pragma unroll
+      for (int s = 0; s < NI; ++s) dy[s][k] = 0.0;
+      if (k < NZL && j < M) {
+        const double ri = rinv_of(k), r = rho_of(k);
+        double nu[NI], lv[NI], uv[NI];
+        MO::ld(wN + NI * PZ[32 * k], nu);
+        tabN(AL, k, lv); tabN(AU, k, uv);
+#pragma unroll
+        for (int s = 0; s < NI; ++s) {
+          const double zt = (z[s][k] - ri * y[s][k]) + ri * nu[s];
+          const double v = alpha * zt + (1.0 - alpha) * z[s][k];
+          const double zn = fmin(fmax(v + ri * y[s][k], lv[s]), uv[s]);
+          const double d = r * (v - zn);
+          dy[s][k] = d;
+          y[s][k] += d;
+          z[s][k] = zn;
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < NI; ++s) it[s] += active[s] ? 1 : 0;
+
+    // ---- residuals, termination, adaptive-rho decision: slot by slot at position 0
+#pragma unroll 1
+    for (int r = 0; r < NI; ++r) {
+      if (chk[0] || adp[0]) {
+        update_info0();
+        int status = ST_UNSOLVED;
+        if (chk[0]) status = check_termination0(dx[0], dy[0], false);
+        if (status == ST_UNSOLVED && it[0] >= st.max_iter) {          // osqp.c:563-568
+          status = check_termination0(dx[0], dy[0], true);
+          if (status == ST_UNSOLVED) status = ST_MAXITER;
+        }
+        if (status != ST_UNSOLVED) { finish0(status); active[0] = false; }
+        else if (adp[0]) {                                            // adapt_rho decision (auxil.c:13-74)
+          const double pn = s_rp / (fmax(s_z, s_Ax) + DIVISION_TOL);
+          const double dn = s_rd / (fmax(fmax(s_q, s_Aty), s_Px) + DIVISION_TOL);
+          double rr = rho_in * sqrt(pn / dn);
+          rr = fmin(fmax(rr, RHO_MIN), RHO_MAX);
+          if (rr > rho_in * st.adaptive_rho_tolerance || rr < rho_in / st.adaptive_rho_tolerance) {
+            hand_off0(rr); active[0] = false;
+          }
+        }
+      }
+      // rotate everything that is indexed by slot
+      rotate_state();
+      { const bool c0 = chk[0], a0 = adp[0];
+#pragma unroll
+        for (int s = 0; s + 1 < NI; ++s) { chk[s] = chk[s + 1]; adp[s] = adp[s + 1]; }
+        chk[NI - 1] = c0; adp[NI - 1] = a0; }
+#pragma unroll
+      for (int k = 0; k < NXL; ++k) { const double t = dx[0][k];
+#pragma unroll
+        for (int s = 0; s + 1 < NI; ++s) dx[s][k] = dx[s + 1][k];
+        dx[NI - 1][k] = t; }
+#pragma unroll
+      for (int k = 0; k < NZLs; ++k) { const double t = dy[0][k];
+#pragma unroll
+        for (int s = 0; s + 1 < NI; ++s) dy[s][k] = dy[s + 1][k];
+        dy[NI - 1][k] = t; }
+    }
+  }
+}
+
+template <class Fam>
+__global__ void __launch_bounds__(Fam::WARPS * 32, 1)
+admm_multi_kernel(const uint8_t* __restrict__ blob_g, const BatchIO io, const Settings st) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t total = reinterpret_cast<const CpgBlobHeader*>(blob_g)->total_bytes;
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {                      // stage the constants blob with TMA bulk copies
+    mbar_expect_tx(&bar, total);
+    constexpr uint32_t CHUNK = 32768;
+    for (uint32_t off = 0; off < total; off += CHUNK)
+      tma_bulk_g2s(smem + off, blob_g + off, (total - off < CHUNK) ? (total - off) : CHUNK, &bar);
+  }
+  mbar_wait(&bar, 0);
+  const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(smem);
+  const int* I32 = reinterpret_cast<const int*>(smem + H->off_i32);
+  const double* F64 = reinterpret_cast<const double*>(smem + H->off_f64);
+  const uint16_t* U16 = reinterpret_cast<const uint16_t*>(smem + H->off_u16);
+  double* wN = reinterpret_cast<double*>(smem + Fam::BLOB_BYTES_PAD) + (size_t)warp * Fam::MULTI_STRIDE;
+  double* bv = wN + Fam::NI * Fam::W_STRIDE;
+  solve_multi<Fam, Fam::NI>(H, I32, F64, U16, wN, bv, lane, io, st);
+}
+
+}  // namespace cpgb200

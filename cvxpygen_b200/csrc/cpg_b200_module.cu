@@ -10,7 +10,7 @@
 #include "cpg_family.h"
 #include "cpg_b200.h"
 #include "cpg_blob_layout.h"
-#include "admm_pair_kernel.cuh"
+#include "admm_multi_kernel.cuh"
 #include "grad_kernel.cuh"
 
 extern "C" const unsigned long long CPG_B200_FN(cpg_blob_words)[];
@@ -38,9 +38,10 @@ struct Fam {
   static constexpr int GBLOB_BYTES_PAD = CPG_FAM_GBLOB_BYTES_PAD;
   static constexpr int GRAD_WARPS = CPG_FAM_GRAD_WARPS;
   static constexpr int GRAD_STRIDE = CPG_FAM_GRAD_STRIDE;
-  static constexpr int PAIR_STRIDE = CPG_FAM_PAIR_STRIDE; // doubles per warp in the pair kernel: interleaved w + batched-row slots
+  static constexpr int NI = CPG_FAM_NI;                     // instances per warp in the main kernel (2 or 4)
+  static constexpr int MULTI_STRIDE = CPG_FAM_MULTI_STRIDE; // doubles per warp: interleaved work vectors + batched-row slots
 };
-constexpr int SMEM_BYTES = Fam::BLOB_BYTES_PAD + Fam::WARPS * Fam::PAIR_STRIDE * 8;
+constexpr int SMEM_BYTES = Fam::BLOB_BYTES_PAD + Fam::WARPS * Fam::MULTI_STRIDE * 8;
 constexpr int TAIL_SMEM_BYTES = Fam::CBLOB_BYTES_PAD + Fam::TAIL_WARPS * (Fam::W_STRIDE + Fam::S_STRIDE) * 8;
 constexpr int TAIL_WORDS = Fam::N + 2 * Fam::M + 2;
 constexpr int GRAD_SMEM_BYTES = Fam::GBLOB_BYTES_PAD + Fam::GRAD_WARPS * Fam::GRAD_STRIDE * 8;
@@ -176,7 +177,7 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
   CK(cudaFuncSetAttribute(cpgb200::admm_tail_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM_BYTES));
   if (!g.d_counter) CK(cudaMalloc(&g.d_counter, sizeof(unsigned int)));
   if (!g.d_tail_count) CK(cudaMalloc(&g.d_tail_count, sizeof(int)));
-  CK(cudaFuncSetAttribute(cpgb200::admm_pair_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CK(cudaFuncSetAttribute(cpgb200::admm_multi_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   g.ready = true;
   return CPG_B200_OK;
 }
@@ -219,9 +220,9 @@ int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const doubl
   CK(cudaMemsetAsync(g.d_counter, 0, sizeof(unsigned int), stream));
   CK(cudaMemsetAsync(g.d_tail_count, 0, sizeof(int), stream));
   int grid = g.n_sm;
-  const int need = (B + 2 * Fam::WARPS - 1) / (2 * Fam::WARPS);
+  const int need = (B + Fam::NI * Fam::WARPS - 1) / (Fam::NI * Fam::WARPS);
   if (grid > need) grid = need;
-  cpgb200::admm_pair_kernel<Fam><<<grid, Fam::WARPS * 32, SMEM_BYTES, stream>>>(g.d_blob, io, st);
+  cpgb200::admm_multi_kernel<Fam><<<grid, Fam::WARPS * 32, SMEM_BYTES, stream>>>(g.d_blob, io, st);
   g.launches += 1;
   CK(cudaGetLastError());
   // instances that changed rho (or a constraint type) continue with their own factor; the kernel exits at once

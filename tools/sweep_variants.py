@@ -6,7 +6,7 @@ import os, sys, time, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, 'tools', '_variants')
-VARIANTS = {'w10': dict(warps=10), 'w12': dict(warps=12), 'w14': dict(warps=14)}
+VARIANTS = {'ni2_w12': dict(ni=2, warps=12), 'ni4_w6': dict(ni=4, warps=6), 'ni4_w7': dict(ni=4, warps=7)}
 
 def build():
     from cvxpygen_b200 import families, cpg
