@@ -153,6 +153,24 @@ int CPG_B200_FN(cpg_b200_load_constants)(const void* blob, int nbytes) {
   return CPG_B200_OK;
 }
 
+int CPG_B200_FN(cpg_b200_load_constants_all)(const void* blob, int nbytes, const void* cblob, int cnbytes,
+                                             const void* tail_blob, int tnbytes, const void* gblob, int gnbytes,
+                                             const void* gS0, int snbytes) {
+  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+  if (!blob || !cblob || !tail_blob || !gblob || !gS0) return CPG_B200_ERR_BAD_ARG;
+  if (nbytes != (int)CPG_B200_FN(cpg_blob_nbytes) || cnbytes != (int)CPG_B200_FN(cpg_cblob_nbytes) ||
+      tnbytes != (int)CPG_B200_FN(cpg_tail_blob_nbytes) || gnbytes != (int)CPG_B200_FN(cpg_gblob_nbytes) ||
+      snbytes != (int)CPG_B200_FN(cpg_gS0_nbytes))
+    return CPG_B200_ERR_BAD_ARG;          // a different layout needs a regenerated library
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(g.d_blob, blob, nbytes, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(g.d_cblob, cblob, cnbytes, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(g.d_tail_blob, tail_blob, tnbytes, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(g.d_gblob, gblob, gnbytes, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(g.d_gS0, gS0, snbytes, cudaMemcpyHostToDevice));
+  return CPG_B200_OK;
+}
+
 int CPG_B200_FN(cpg_b200_init)(int device) {
   g.err[0] = 0;
   CK(cudaSetDevice(device));

@@ -87,6 +87,39 @@ class Module:
         self.init()
         self._check(self._fn('cpg_b200_load_constants')(C.c_char_p(blob), C.c_int(len(blob))))
 
+    def update_shared_params(self, values):
+        """Change user parameters that are shared by the whole batch (e.g. a matrix parameter).  Role of the reference's
+        osqp_update_data_mat branch of cpg_solve (cvxpygen/solvers/osqp.py:20-33 -> re-scale + refactor): the offline
+        setup is re-run on the host and every constants table is re-uploaded.  Needs the cvxpygen_b200 package."""
+        import pickle
+        import numpy as _np
+        from cvxpygen_b200.offline.qp_setup import setup_qp_family
+        with open(os.path.join(self.code_dir, 'cpg_family.pkl'), 'rb') as f:
+            saved = pickle.load(f)
+        fam = saved['family']
+        if not hasattr(self, '_theta'):
+            self._theta = fam.theta_default()
+        for name, val in values.items():
+            p = fam.param(name)                                   # AttributeError for unknown names
+            if name in saved['batch_params']:
+                raise ValueError(f'{name} is a batched parameter: pass it per instance to solve_batch')
+            v = _np.asarray(val, dtype=float)
+            v = v.flatten(order='F') if v.ndim > 1 and v.size == int(_np.prod(p.shape)) and p.size == v.size else v.ravel()
+            if v.size != p.size:
+                raise ValueError(f'parameter {name} stores {p.size} entries, got {v.size}')
+            self._theta[p.col:p.col + p.size] = v
+        st = setup_qp_family(fam, saved['batch_params'], theta=self._theta, rho=saved['rho'], sigma=saved['sigma'],
+                             scaling=saved['scaling'])
+        if st.solve_source != saved['solve_source']:
+            raise RuntimeError('the new parameter values change the sparsity structure of the KKT factor schedule: '
+                               'regenerate the code (cpg.generate_code)')
+        self.init()
+        gS0 = _np.asarray(st.grad_S0, dtype='<f8').tobytes()
+        b = lambda x: (C.c_char_p(x), C.c_int(len(x)))
+        self._check(self._fn('cpg_b200_load_constants_all')(*b(st.blob), *b(st.blob_compact), *b(st.tail_blob),
+                                                           *b(st.grad_blob), *b(gS0)))
+        return st
+
     def launch_count(self):
         return int(self._fn('cpg_b200_launch_count')())
 

@@ -84,6 +84,13 @@ const char* CPG_B200_FN(cpg_b200_last_error)(void);
 int  CPG_B200_FN(cpg_b200_launch_count)(void);               /* kernels launched by the last solve call */
 /* Replace the constants blob (shared parameters changed => host re-ran the offline setup). */
 int  CPG_B200_FN(cpg_b200_load_constants)(const void* blob, int nbytes);
+/* Replace EVERY constants table after a shared-parameter update (role of osqp_update_data_mat -> re-scale + refactor,
+ * osqp_sources/src/osqp.c:1158-1264, done on the host by the offline pipeline): main blob, its compact copy for the
+ * tail kernel, the re-factorisation tables, the backward-pass blob and its KKT slot values.  The sparsity structure
+ * must be the one the library was generated for (same generated solve code); sizes are checked. */
+int  CPG_B200_FN(cpg_b200_load_constants_all)(const void* blob, int nbytes, const void* cblob, int cnbytes,
+                                              const void* tail_blob, int tnbytes, const void* gblob, int gnbytes,
+                                              const void* gS0, int snbytes);
 
 /* Batched solve, DEVICE buffers (row-major, one instance per row), asynchronous on `stream`.
  *   params (B, n_param) in        x0 (B, n_var) / y0 (B, n_con) optional warm start (NULL = cold)

@@ -169,3 +169,30 @@ def test_corner_cases_type_changes_and_infeasibility():
     assert_batch_parity(res.sol_x, res.sol_y, res.cpg_info, ora, TOL, stable=stable)
     assert (res.cpg_info.status == ora['status']).all()          # statuses agree even on the unstable ones
     assert (res.cpg_info.obj_val[kind == 3] == 1e30).all() and (res.cpg_info.obj_val[kind == 4] == -1e30).all()
+
+
+@pytest.mark.gpu
+def test_shared_matrix_parameter_update():
+    """A user parameter that enters a canonical MATRIX is shared by the batch: changing it re-runs the offline setup on
+    the host (scaling, factor, schedule values) and re-uploads every constants table -- the role of
+    osqp_update_data_mat in the reference's update tree (cvxpygen/solvers/osqp.py:20-33)."""
+    import shutil, tempfile, os
+    from cvxpygen_b200 import cpg, families, runtime
+    from helpers import canon_batches
+    d = os.path.join(tempfile.mkdtemp(), 'ls')
+    fam = families.nonneg_ls(3, 2)
+    cpg.generate_code(fam, code_dir=d, batch_params=['b'])
+    mod = runtime.Module(d)
+    B = 64
+    rng = np.random.default_rng(3)
+    bb = rng.standard_normal((B, 3))
+    A_new = np.asarray(fam.param('A').default) * np.array([1.5, -0.7, 2.0]) + 0.1
+    mod.update_shared_params({'A': A_new})
+    res = mod.solve_batch({'b': bb}, return_canonical=True)
+    fam2 = families.nonneg_ls(3, 2, A_data=A_new)
+    q, l, u = canon_batches(fam2, {'b': bb}, B)
+    ora = oracle_solve(fam2, q, l, u)
+    assert_batch_parity(res.sol_x, res.sol_y, res.cpg_info, ora, TOL)
+    with pytest.raises(ValueError):
+        mod.update_shared_params({'b': np.zeros(3)})
+    shutil.rmtree(os.path.dirname(d), ignore_errors=True)

@@ -6,7 +6,7 @@ import os, sys, time, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, 'tools', '_variants')
-VARIANTS = {'ni2_w12': dict(ni=2, warps=12), 'ni4_w6': dict(ni=4, warps=6), 'ni4_w7': dict(ni=4, warps=7)}
+VARIANTS = {'ni2_w11': dict(ni=2, warps=11), 'ni2_w12': dict(ni=2, warps=12), 'ni2_w13': dict(ni=2, warps=13), 'ni2_w14': dict(ni=2, warps=14)}
 
 def build():
     from cvxpygen_b200 import families, cpg
