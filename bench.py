@@ -32,10 +32,10 @@ WORKLOAD = 'MPC QP (n_x=12,n_u=4,N=10) batch=%d per GPU, ADMM-CUDA backend, OSQP
 # algorithmic I/O and work per instance (SURVEY.md section 8d / DESIGN.md): 96 B in + 2.75 KB out + 40 B info
 BYTES_PER_INSTANCE = 12 * 8 + (172 + 172) * 8 + 40
 FLOP_PER_INSTANCE = 0.5e6
-# dram__bytes_read.sum + dram__bytes_write.sum of admm_pair_kernel from the `ncu --set full` capture of this same command
-# at batch 100000 (profiles/r1_final_ncu_summary.md: 13.7 MB + 423.5 MB): 4.37 KB per instance.  The excess over the
+# dram__bytes_read.sum + dram__bytes_write.sum of admm_multi_kernel from the `ncu --set full` capture of this same command
+# at batch 100000 (profiles/r1_v7_ncu_summary.md: 12.8 MB + 418.1 MB): 4.31 KB per instance.  The excess over the
 # algorithmic 2.89 KB is register-spill write-back, not re-reads of inputs.
-TRAFFIC_BYTES_PER_INSTANCE = 4371
+TRAFFIC_BYTES_PER_INSTANCE = 4309
 
 
 def load_peaks():
@@ -248,12 +248,12 @@ def main():
         'gpu_launches': launches_per_step * K,
         'clocks': sampler.summary(),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': B * TRAFFIC_BYTES_PER_INSTANCE / 1e9, 'traffic_unit': 'GB per launch (ncu, profiles/r1_final_ncu_summary.md)',
+                     'traffic': B * TRAFFIC_BYTES_PER_INSTANCE / 1e9, 'traffic_unit': 'GB per launch (ncu, profiles/r1_v7_ncu_summary.md)',
                      'peak_source': peak_src,
                      'algorithmic_bytes_per_instance': BYTES_PER_INSTANCE,
                      'note': 'on-chip design: HBM carries only parameters in / solutions out, so the HBM fraction is tiny by '
-                             'construction; the binding resource is shared-memory bandwidth -- ncu: 70.7 %% of peak '
-                             'shared-memory wavefronts (profiles/r1_final_ncu_summary.md); fp64 fraction = %.4f of 37 TFLOP/s '
+                             'construction; the binding resource is shared-memory bandwidth -- ncu: 78.2 %% of peak '
+                             'shared-memory wavefronts (profiles/r1_v7_ncu_summary.md); fp64 fraction = %.4f of 37 TFLOP/s '
                              'nominal' % (value / world * FLOP_PER_INSTANCE / 37e12)},
     }
     if grad_info:
