@@ -13,7 +13,7 @@ from typing import List, Optional
 
 from .ir import CanonFamily
 
-SOLVERS = ('ADMM-CUDA',)
+SOLVERS = ('ADMM-CUDA', 'IPM-CUDA')
 
 
 def _canonicalize_with_reference(problem, solver_opts, enable_settings):
@@ -38,11 +38,27 @@ def generate_code(problem, code_dir='cpg_code', solver=None, solver_opts=None, e
         raise ValueError(f'Unsupported solver: {solver}.')       # same text as cvxpygen/canonicalizer.py:83
     # gradient=True needs nothing extra: every generated library carries the batched backward pass
     # (cpg_gradient_batch_*); the flag is accepted for signature compatibility with the reference.
-    sys.stdout.write('Generating code with cvxpygen_b200 (ADMM-CUDA, sm_100a) ...\n')
+    sys.stdout.write(f'Generating code with cvxpygen_b200 ({solver.upper()}, sm_100a) ...\n')
     fam = problem if isinstance(problem, CanonFamily) else _canonicalize_with_reference(problem, solver_opts, enable_settings)
     if not fam.params:
         raise ValueError('Solution does not depend on parameters. Aborting code generation.')  # canonicalizer.py:98-99
     opts = dict(solver_opts or {})
+    if solver.upper() == 'IPM-CUDA':
+        # SOCP families: Mehrotra interior-point kernel (role of solver='ECOS' in the reference, cvxpygen/solvers/ecos.py)
+        from . import codegen_ipm
+        from .offline.socp_setup import setup_socp_family
+        if gradient:
+            raise ValueError('gradient=True is generated for the QP path (ADMM-CUDA) only')
+        setup = setup_socp_family(fam, batch_params)
+        codegen_ipm.write_ipm_code(setup, code_dir, prefix=prefix, threads=opts.get('threads'))
+        sys.stdout.write('cvxpygen_b200 finished generating code.\n')
+        if wrapper:
+            sys.stdout.write('Compiling CUDA solver library (nvcc, sm_100a) ...\n')
+            codegen_ipm.compile_ipm_code(code_dir, verbose=verbose)
+            sys.stdout.write('cvxpygen_b200 finished compiling.\n')
+        return setup
+    if fam.solver_type != 'quadratic':
+        raise ValueError('ADMM-CUDA handles the QP canonical form; use solver=\'IPM-CUDA\' for conic families')
     setup = setup_qp_family(fam, batch_params, rho=opts.get('rho', 0.1), sigma=opts.get('sigma', 1e-6),
                             scaling=opts.get('scaling', 10), max_group_rows=opts.get('max_group_rows', 32))
     codegen.write_code(setup, code_dir, prefix=prefix, warps=opts.get('warps'), ni=opts.get('ni'))

@@ -1,0 +1,178 @@
+// cpg_b200_ipm_module.cu -- C-ABI runtime of one generated IPM-CUDA solver library (SOCP families).
+// Compiled once per problem family together with the generated cpg_ipm_family.h (compile-time sizes, table offsets) and
+// cpg_ipm_blob.c (the constant tables).  Implements include/cpg_b200_socp.h; see that header for the reference
+// interfaces it stands beside.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "cpg_ipm_family.h"
+#include "cpg_b200_socp.h"
+#include "ipm_kernel.cuh"
+
+extern "C" const unsigned long long CPG_B200_FN(cpg_ipm_sblob_words)[];
+extern "C" const unsigned int CPG_B200_FN(cpg_ipm_sblob_nbytes);
+extern "C" const unsigned long long CPG_B200_FN(cpg_ipm_gblob_words)[];
+extern "C" const unsigned int CPG_B200_FN(cpg_ipm_gblob_nbytes);
+
+namespace {
+
+using cpgipm::IpmIO;
+using cpgipm::IpmSettings;
+static_assert(sizeof(IpmSettings) == sizeof(CpgB200SocpSettings), "settings struct of the kernel and of the C ABI must match");
+static_assert(cpgipm::SMEM_BYTES <= 232448 - 1024, "per-instance state + tables exceed the shared memory of one SM");
+
+struct Ctx {
+  bool ready = false;
+  int device = -1, n_sm = 0;
+  uint8_t *d_sblob = nullptr, *d_gblob = nullptr;
+  double* d_best = nullptr;
+  int* d_counter = nullptr;
+  int cap_B = 0;
+  double *d_params = nullptr, *d_prim = nullptr, *d_dual = nullptr, *d_x = nullptr, *d_y = nullptr, *d_z = nullptr, *d_s = nullptr;
+  double *d_obj = nullptr, *d_pri = nullptr, *d_dua = nullptr;
+  int *d_iter = nullptr, *d_status = nullptr;
+  int launches = 0;
+  char err[256] = {0};
+} g;
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      snprintf(g.err, sizeof(g.err), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return CPG_B200_ERR_CUDA;                                                                   \
+    }                                                                                             \
+  } while (0)
+
+template <class T_>
+int grow(T_** p, size_t count) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  CK(cudaMalloc(p, sizeof(T_) * (count ? count : 1)));
+  return CPG_B200_OK;
+}
+
+int ensure_staging(int B) {
+  if (B <= g.cap_B) return CPG_B200_OK;
+  int rc;
+  if ((rc = grow(&g.d_params, (size_t)B * cpgipm::NPB))) return rc;
+  if ((rc = grow(&g.d_prim, (size_t)B * cpgipm::NPRIM))) return rc;
+  if ((rc = grow(&g.d_dual, (size_t)B * cpgipm::NDUAL))) return rc;
+  if ((rc = grow(&g.d_x, (size_t)B * cpgipm::N))) return rc;
+  if ((rc = grow(&g.d_y, (size_t)B * cpgipm::P))) return rc;
+  if ((rc = grow(&g.d_z, (size_t)B * cpgipm::M))) return rc;
+  if ((rc = grow(&g.d_s, (size_t)B * cpgipm::M))) return rc;
+  if ((rc = grow(&g.d_obj, (size_t)B))) return rc;
+  if ((rc = grow(&g.d_pri, (size_t)B))) return rc;
+  if ((rc = grow(&g.d_dua, (size_t)B))) return rc;
+  if ((rc = grow(&g.d_iter, (size_t)B))) return rc;
+  if ((rc = grow(&g.d_status, (size_t)B))) return rc;
+  g.cap_B = B;
+  return CPG_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int CPG_B200_FN(cpg_b200_init)(int device) {
+  if (g.ready) return CPG_B200_OK;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  g.device = device; g.n_sm = prop.multiProcessorCount;
+  const size_t sb = CPG_B200_FN(cpg_ipm_sblob_nbytes), gb = CPG_B200_FN(cpg_ipm_gblob_nbytes);
+  CK(cudaMalloc(&g.d_sblob, sb));
+  CK(cudaMalloc(&g.d_gblob, gb));
+  CK(cudaMemcpy(g.d_sblob, CPG_B200_FN(cpg_ipm_sblob_words), sb, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(g.d_gblob, CPG_B200_FN(cpg_ipm_gblob_words), gb, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&g.d_best, sizeof(double) * (size_t)g.n_sm * (cpgipm::NK + cpgipm::MT)));
+  CK(cudaMalloc(&g.d_counter, sizeof(int)));
+  CK(cudaFuncSetAttribute(cpgipm::ipm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cpgipm::SMEM_BYTES));
+  g.ready = true;
+  return CPG_B200_OK;
+}
+
+int CPG_B200_FN(cpg_b200_free)(void) {
+  if (!g.ready) return CPG_B200_OK;
+  void* ptrs[] = {g.d_sblob, g.d_gblob, g.d_best, g.d_counter, g.d_params, g.d_prim, g.d_dual, g.d_x, g.d_y, g.d_z, g.d_s,
+                  g.d_obj, g.d_pri, g.d_dua, g.d_iter, g.d_status};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  g = Ctx();
+  return CPG_B200_OK;
+}
+
+const char* CPG_B200_FN(cpg_b200_last_error)(void) { return g.err; }
+int CPG_B200_FN(cpg_b200_launch_count)(void) { return g.launches; }
+
+int CPG_B200_FN(cpg_socp_dims)(CpgB200SocpDims* out) {
+  if (!out) return CPG_B200_ERR_BAD_ARG;
+  out->n_var = cpgipm::N; out->n_eq = cpgipm::P; out->n_ineq = cpgipm::M; out->n_lp = cpgipm::L; out->n_soc = cpgipm::NSOC;
+  out->n_param = cpgipm::NPB; out->n_prim = cpgipm::NPRIM; out->n_dual = cpgipm::NDUAL;
+  out->threads_per_cta = cpgipm::T; out->smem_bytes = (int)cpgipm::SMEM_BYTES;
+  return CPG_B200_OK;
+}
+
+void CPG_B200_FN(cpg_socp_default_settings)(CpgB200SocpSettings* s) {
+  if (!s) return;
+  s->maxit = 100; s->pad_ = 0;
+  s->feastol = 1e-8; s->abstol = 1e-8; s->reltol = 1e-8;
+  s->feastol_inacc = 1e-4; s->abstol_inacc = 5e-5; s->reltol_inacc = 5e-5;
+}
+
+int CPG_B200_FN(cpg_socp_solve_batch_device)(int B, const double* params, double* prim, double* dual,
+                                             double* sol_x, double* sol_y, double* sol_z, double* sol_s,
+                                             double* obj_val, int* iter, int* status, double* pri_res, double* dua_res,
+                                             const CpgB200SocpSettings* settings, void* stream) {
+  if (!g.ready) { snprintf(g.err, sizeof(g.err), "cpg_b200_init has not been called"); return CPG_B200_ERR_NOT_INIT; }
+  if (B < 0 || (B > 0 && (!prim || !dual || !obj_val || !iter || !status || !pri_res || !dua_res || (cpgipm::NPB > 0 && !params)))) {
+    snprintf(g.err, sizeof(g.err), "null output pointer or negative batch size");
+    return CPG_B200_ERR_BAD_ARG;
+  }
+  g.launches = 0;
+  if (B == 0) return CPG_B200_OK;
+  CpgB200SocpSettings st;
+  if (settings) st = *settings; else CPG_B200_FN(cpg_socp_default_settings)(&st);
+  IpmSettings ks;
+  memcpy(&ks, &st, sizeof(ks));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  CK(cudaMemsetAsync(g.d_counter, 0, sizeof(int), s));
+  IpmIO io{B, params, prim, dual, sol_x, sol_y, sol_z, sol_s, obj_val, iter, status, pri_res, dua_res, g.d_best, g.d_counter};
+  const int grid = B < g.n_sm ? B : g.n_sm;
+  cpgipm::ipm_kernel<<<grid, cpgipm::T, cpgipm::SMEM_BYTES, s>>>(g.d_sblob, g.d_gblob, ks, io);
+  CK(cudaGetLastError());
+  g.launches = 1;
+  return CPG_B200_OK;
+}
+
+int CPG_B200_FN(cpg_socp_solve_batch_host)(int B, const double* params, double* prim, double* dual,
+                                           double* sol_x, double* sol_y, double* sol_z, double* sol_s,
+                                           double* obj_val, int* iter, int* status, double* pri_res, double* dua_res,
+                                           const CpgB200SocpSettings* settings) {
+  if (!g.ready) { snprintf(g.err, sizeof(g.err), "cpg_b200_init has not been called"); return CPG_B200_ERR_NOT_INIT; }
+  if (B == 0) { g.launches = 0; return CPG_B200_OK; }
+  int rc;
+  if ((rc = ensure_staging(B))) return rc;
+  if (cpgipm::NPB > 0) CK(cudaMemcpy(g.d_params, params, sizeof(double) * (size_t)B * cpgipm::NPB, cudaMemcpyHostToDevice));
+  rc = CPG_B200_FN(cpg_socp_solve_batch_device)(B, g.d_params, g.d_prim, g.d_dual, sol_x ? g.d_x : nullptr, sol_y ? g.d_y : nullptr,
+                                                sol_z ? g.d_z : nullptr, sol_s ? g.d_s : nullptr, g.d_obj, g.d_iter, g.d_status,
+                                                g.d_pri, g.d_dua, settings, nullptr);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(prim, g.d_prim, sizeof(double) * (size_t)B * cpgipm::NPRIM, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(dual, g.d_dual, sizeof(double) * (size_t)B * cpgipm::NDUAL, cudaMemcpyDeviceToHost));
+  if (sol_x) CK(cudaMemcpy(sol_x, g.d_x, sizeof(double) * (size_t)B * cpgipm::N, cudaMemcpyDeviceToHost));
+  if (sol_y) CK(cudaMemcpy(sol_y, g.d_y, sizeof(double) * (size_t)B * cpgipm::P, cudaMemcpyDeviceToHost));
+  if (sol_z) CK(cudaMemcpy(sol_z, g.d_z, sizeof(double) * (size_t)B * cpgipm::M, cudaMemcpyDeviceToHost));
+  if (sol_s) CK(cudaMemcpy(sol_s, g.d_s, sizeof(double) * (size_t)B * cpgipm::M, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(obj_val, g.d_obj, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(iter, g.d_iter, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(status, g.d_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(pri_res, g.d_pri, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(dua_res, g.d_dua, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost));
+  return CPG_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,919 @@
+// ipm_kernel.cuh -- batched Mehrotra predictor-corrector interior-point method for one SOCP family (IPM-CUDA backend).
+//
+// One CTA solves one problem instance at a time (persistent CTAs pull instances from a global counter): the iterate,
+// the NT scalings, the numeric LDL' factor of the stretched KKT matrix and all work vectors live in shared memory, the
+// constant index tables of the family are staged once per CTA.  The algorithm is the one the reference runs per
+// instance on the host -- ECOS 2.0.8 as driven by cvxpygen's generated code (cvxpygen/solvers/ecos.py:88-117) --
+// re-organised into barrier-separated phases:
+//
+//   init                      ecos/src/ecos.c:260-452          kkt_init        ecos/src/kkt.c:373-445
+//   computeResiduals          ecos/src/ecos.c:455-499          updateStatistics ecos/src/ecos.c:502-545
+//   checkExitConditions       ecos/src/ecos.c:179-257          compareStatistics / best iterate :61-149
+//   updateScalings / scale    ecos/src/cone.c:138-234,276-305  kkt_update      ecos/src/kkt.c:271-357
+//   kkt_factor (LDL_numeric2 + dynamic regularisation)         ecos/external/ldl/src/ldl.c:266-360
+//   kkt_solve (iterative refinement)  ecos/src/kkt.c:87-265    scale2add       ecos/src/cone.c:313-400
+//   RHS_affine / RHS_combined ecos/src/ecos.c:648-757          lineSearch      ecos/src/ecos.c:947-1046
+//   conicProduct / conicDivision ecos/src/cone.c:452-513       main loop / backscale ecos/src/ecos.c:1075-1607,1051-1070
+//
+// Index space: k = [x (N) | y (P) | z stretched (MT = M + 2 NSOC)]; every second-order cone of size d occupies d + 2
+// consecutive rows, the last two carrying the sparse representation of its scaling (ecos/src/preproc.c:77-330).
+// Tables come from cvxpygen_b200/offline/socp_setup.py; sizes and offsets are compile-time constants (cpg_ipm_family.h).
+//
+// The same source compiles as plain host C++ with -DCPG_IPM_HOST_EMU: every phase then runs its threads one after the
+// other.  That build exists for the CPU tests of the phase logic only (tests/emu); it is not reachable from the product.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef CPG_IPM_HOST_EMU
+#include <algorithm>
+#include <cstring>
+#include <vector>
+#define IPM_FN inline
+#define IPM_CONST static const
+#else
+#define IPM_FN __device__ __forceinline__
+#define IPM_CONST __device__ const
+#endif
+
+namespace cpgipm {
+
+// ---- constants of the reference (ecos/include/ecos.h:45-75)
+constexpr double kGamma = 0.99, kDeltaStat = 7e-8, kDelta = 2e-7, kEps = 1e-13;
+constexpr int kNitref = 9;
+constexpr double kIrErrFact = 6.0, kLinsysAcc = 1e-14;
+constexpr double kSigmaMin = 1e-4, kSigmaMax = 1.0, kStepMin = 1e-6, kStepMax = 0.999, kSafeguard = 500.0;
+enum { kOptimal = 0, kPinf = 1, kDinf = 2, kInaccOffset = 10, kMaxit = -1, kNumerics = -2, kOutcone = -3, kFatal = -7,
+       kNotConverged = -87 };
+
+struct IpmSettings {
+  int maxit;                                  // 100   (cvxpygen/solvers/ecos.py:60-68)
+  int pad_;
+  double feastol, abstol, reltol;             // 1e-8
+  double feastol_inacc, abstol_inacc, reltol_inacc;   // 1e-4, 5e-5, 5e-5
+};
+
+struct IpmIO {
+  int B;
+  const double* params;      // (B, NPB)
+  double* prim;              // (B, NPRIM)
+  double* dual;              // (B, NDUAL)
+  double* sol_x;             // (B, N) or null
+  double* sol_y;             // (B, P) or null
+  double* sol_z;             // (B, M) or null
+  double* sol_s;             // (B, M) or null
+  double* obj_val; int* iter; int* status; double* pri_res; double* dua_res;
+  double* best;              // per-CTA scratch for the best iterate: gridDim.x * (NK + MT) doubles
+  int* counter;              // work counter
+};
+
+constexpr int T = CPG_IPM_THREADS;
+constexpr int NWARP = T / 32;
+constexpr int N = IPM_N, P = IPM_P, M = IPM_M, L = IPM_L, NSOC = IPM_NSOC, MT = IPM_MT, NK = IPM_NK, ZOFF = IPM_ZOFF;
+constexpr int NW = IPM_NW, DG0 = IPM_DG0, TT0 = IPM_TT0, NS = IPM_NS, NT = IPM_NT, NLW = IPM_NLW;
+constexpr int NNZM = IPM_NNZM, NPB = IPM_NPB, NMAP = IPM_NMAP, NPRIM = IPM_NPRIM, NDUAL = IPM_NDUAL, QTOT = IPM_QTOT;
+constexpr int CONE_D = L + NSOC;              // degree of the cone (w->D)
+constexpr int PT = (NK + T - 1) / T;          // elements of a k-space vector owned by one thread
+
+// ---- shared-memory layout (in doubles, then the u16 tables)
+constexpr int O_XYZ = 0, O_CBH = O_XYZ + NK, O_SV = O_CBH + NK, O_LAM = O_SV + MT, O_V = O_LAM + MT, O_W = O_V + L,
+              O_Q = O_W + L, O_SC = O_Q + QTOT, O_S = O_SC + 8 * (NSOC > 0 ? NSOC : 1), O_DINV = O_S + NS,
+              O_RHS = O_DINV + NK, O_PX = O_RHS + NK, O_E = O_PX + NK, O_SOL1 = O_E + NK, O_RZ = O_SOL1 + NK,
+              O_DSW = O_RZ + MT, O_RED = O_DSW + MT, O_CONE = O_RED + 2 * NWARP * 16,
+              O_AG = O_CONE + 4 * (NSOC > 0 ? NSOC : 1), O_F64_END = O_AG + NNZM;
+constexpr int U16_COUNT = (IPM_SB_BYTES - IPM_SB_U16_OFF) / 2;
+constexpr size_t SMEM_BYTES = size_t(O_F64_END) * 8 + size_t(U16_COUNT) * 2 + 16;
+enum { SC_ETA2 = 0, SC_ETA, SC_A, SC_D1, SC_U0, SC_U1, SC_V1, SC_W };
+
+struct Sm {
+  double *xyz, *cbh, *sv, *lam, *v, *w, *q, *sc, *S, *dinv, *rhs, *px, *e, *sol1, *rz, *dsw, *red, *cone, *ag;
+  const uint16_t *mr_t, *mr_s, *fw_t, *fw_s, *fw_slot, *bw_t, *bw_s, *socv, *socu, *tail_k, *perm;
+  int* flag;
+};
+
+struct alignas(8) Op { uint16_t t, a, b, j; };      // S[t] -= S[a] * S[b] * Dinv[j]
+
+struct Gm {                 // global constant tables
+  const double *Sbase, *cbh_base, *unscale, *map_v;
+  const int *map_t, *map_p, *prim_idx, *dual_idx;
+  const Op* ops;            // NOPS update operations of the numeric factorisation
+};
+
+IPM_FN Gm make_gm(const unsigned char* g) {
+  Gm r;
+  const double* f = reinterpret_cast<const double*>(g);
+  r.Sbase = f + IPM_G_SBASE; r.cbh_base = f + IPM_G_CBH_BASE; r.unscale = f + IPM_G_UNSCALE; r.map_v = f + IPM_G_MAP_V;
+  const int* i = reinterpret_cast<const int*>(g + IPM_GB_I32_OFF);
+  r.map_t = i + IPM_GI_MAP_T; r.map_p = i + IPM_GI_MAP_P; r.prim_idx = i + IPM_GI_PRIM_IDX; r.dual_idx = i + IPM_GI_DUAL_IDX;
+  r.ops = reinterpret_cast<const Op*>(g + IPM_GB_OPS_OFF);
+  return r;
+}
+
+IPM_FN Sm make_sm(unsigned char* base) {
+  Sm s;
+  double* f = reinterpret_cast<double*>(base);
+  s.xyz = f + O_XYZ; s.cbh = f + O_CBH; s.sv = f + O_SV; s.lam = f + O_LAM; s.v = f + O_V; s.w = f + O_W; s.q = f + O_Q;
+  s.sc = f + O_SC; s.S = f + O_S; s.dinv = f + O_DINV; s.rhs = f + O_RHS; s.px = f + O_PX; s.e = f + O_E;
+  s.sol1 = f + O_SOL1; s.rz = f + O_RZ; s.dsw = f + O_DSW; s.red = f + O_RED; s.cone = f + O_CONE; s.ag = f + O_AG;
+  const uint16_t* h = reinterpret_cast<const uint16_t*>(f + O_F64_END);
+  s.mr_t = h + IPM_H_MR_T; s.mr_s = h + IPM_H_MR_S; s.fw_t = h + IPM_H_FW_T; s.fw_s = h + IPM_H_FW_S;
+  s.fw_slot = h + IPM_H_FW_SLOT; s.bw_t = h + IPM_H_BW_T; s.bw_s = h + IPM_H_BW_S; s.socv = h + IPM_H_SOCV;
+  s.socu = h + IPM_H_SOCU; s.tail_k = h + IPM_H_TAIL_K; s.perm = h + IPM_H_PERM;
+  s.flag = reinterpret_cast<int*>(const_cast<uint16_t*>(h + U16_COUNT + (U16_COUNT & 1)));
+  return s;
+}
+
+IPM_FN double safediv(double x, double y) { return y < kEps ? x / kEps : x / y; }
+
+// ----------------------------------------------------------------------------------------------------------------------
+// execution model: phases, reductions, per-cone warps
+#ifdef CPG_IPM_HOST_EMU
+IPM_FN void atomic_add(double* p, double v) { *p += v; }
+template <class F> IPM_FN void phase(F&& f) { for (int t = 0; t < T; ++t) f(t); }
+// KS sums and KM maxima over all threads; f(tid, s, m) accumulates with += and fmax
+template <int KS, int KM, class F> IPM_FN void phase_red(Sm&, int&, double* s, double* m, F&& f) {
+  for (int k = 0; k < KS; ++k) s[k] = 0.0;
+  for (int k = 0; k < KM; ++k) m[k] = -INFINITY;
+  for (int t = 0; t < T; ++t) f(t, s, m);
+}
+struct WarpOps {
+  template <class F> double sum(int lo, int hi, F&& f) const { double s = 0; for (int i = lo; i < hi; ++i) s += f(i); return s; }
+  template <class F> void each(int lo, int hi, F&& f) const { for (int i = lo; i < hi; ++i) f(i); }
+  bool leader() const { return true; }
+  void sync() const {}
+};
+// thread part f(tid) and cone part g(cone, WarpOps) of one phase (independent of each other)
+template <class F, class G> IPM_FN void phase_cones(F&& f, G&& g) {
+  for (int t = 0; t < T; ++t) f(t);
+  for (int c = 0; c < NSOC; ++c) g(c, WarpOps());
+}
+template <int KS, int KM, class F, class G>
+IPM_FN void phase_red_cones(Sm& sm, int& rb, double* s, double* m, F&& f, G&& g) {
+  phase_red<KS, KM>(sm, rb, s, m, f);
+  for (int c = 0; c < NSOC; ++c) g(c, WarpOps());
+}
+template <int CNT> struct PerThread {
+  std::vector<double> a; PerThread() : a(size_t(T) * CNT, 0.0) {}
+  double& at(int tid, int j) { return a[size_t(tid) * CNT + j]; }
+};
+#else
+IPM_FN void atomic_add(double* p, double v) { atomicAdd(p, v); }
+template <class F> IPM_FN void phase(F&& f) { f(int(threadIdx.x)); __syncthreads(); }
+IPM_FN double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+IPM_FN double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int KS, int KM, class F> IPM_FN void phase_red(Sm& sm, int& rb, double* s, double* m, F&& f) {
+  static_assert(KS + KM <= 16, "reduction scratch holds 16 values per warp");
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < KS; ++k) s[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < KM; ++k) m[k] = -INFINITY;
+  f(tid, s, m);
+  double* buf = sm.red + rb * (NWARP * 16);
+  rb ^= 1;
+#pragma unroll
+  for (int k = 0; k < KS; ++k) { double v = warp_sum(s[k]); if (lane == 0) buf[wid * 16 + k] = v; }
+#pragma unroll
+  for (int k = 0; k < KM; ++k) { double v = warp_max(m[k]); if (lane == 0) buf[wid * 16 + KS + k] = v; }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < KS; ++k) { double v = 0.0; for (int w = 0; w < NWARP; ++w) v += buf[w * 16 + k]; s[k] = v; }
+#pragma unroll
+  for (int k = 0; k < KM; ++k) { double v = -INFINITY; for (int w = 0; w < NWARP; ++w) v = fmax(v, buf[w * 16 + KS + k]); m[k] = v; }
+}
+struct WarpOps {
+  int lane;
+  template <class F> IPM_FN double sum(int lo, int hi, F&& f) const {
+    double s = 0; for (int i = lo + lane; i < hi; i += 32) s += f(i); return warp_sum(s);
+  }
+  template <class F> IPM_FN void each(int lo, int hi, F&& f) const { for (int i = lo + lane; i < hi; i += 32) f(i); }
+  IPM_FN bool leader() const { return lane == 0; }
+  IPM_FN void sync() const { __syncwarp(); }
+};
+template <class G> IPM_FN void run_cones(G&& g) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // cones go to the LAST warps first so that they overlap with the (front-loaded) elementwise work of the others
+  for (int c = NWARP - 1 - wid; c < NSOC; c += NWARP) g(c, WarpOps{lane});
+}
+template <class F, class G> IPM_FN void phase_cones(F&& f, G&& g) {
+  f(int(threadIdx.x)); run_cones(g); __syncthreads();
+}
+template <int KS, int KM, class F, class G>
+IPM_FN void phase_red_cones(Sm& sm, int& rb, double* s, double* m, F&& f, G&& g) {
+  run_cones(g);
+  phase_red<KS, KM>(sm, rb, s, m, f);
+}
+template <int CNT> struct PerThread {
+  double a[CNT];
+  IPM_FN double& at(int, int j) { return a[j]; }
+};
+#endif
+
+// chunked segmented accumulation: entries [lo, hi) sorted by target; out[target(e)] -= sum value(e)
+// entry(e, t) returns the value of entry e and stores its target in t.  Only the first and the last target of a chunk
+// can be shared with another thread, so only those two are flushed atomically.
+template <class EF> IPM_FN void seg_sub(int tid, int lo, int hi, double* out, EF&& entry) {
+  const int n = hi - lo;
+  if (n <= 0) return;
+  const int chunk = (n + T - 1) / T;
+  int e = lo + tid * chunk;
+  const int end = e + chunk < hi ? e + chunk : hi;
+  if (e >= end) return;
+  int cur = -1;
+  double acc = 0.0;
+  bool first = true;
+  for (; e < end; ++e) {
+    int t;
+    const double v = entry(e, t);
+    if (t != cur) {
+      if (cur >= 0) { if (first) { atomic_add(out + cur, -acc); first = false; } else out[cur] -= acc; }
+      cur = t; acc = 0.0;
+    }
+    acc += v;
+  }
+  atomic_add(out + cur, -acc);
+}
+
+template <class F> IPM_FN void each_k(int tid, int n, F&& f) { for (int i = tid; i < n; i += T) f(i); }
+
+IPM_CONST int kSocSo[NSOC > 0 ? NSOC : 1] = IPM_SOC_SO;      // stretched z offset of each cone
+IPM_CONST int kSocD[NSOC > 0 ? NSOC : 1] = IPM_SOC_D;        // cone sizes
+IPM_CONST int kSocQo[NSOC > 0 ? NSOC : 1] = IPM_SOC_QO;      // offset of q in sm.q
+IPM_CONST int kSocVo[NSOC > 0 ? NSOC : 1] = IPM_SOC_VO;      // offset in socv
+IPM_CONST int kSocUo[NSOC > 0 ? NSOC : 1] = IPM_SOC_UO;      // offset in socu
+IPM_CONST int kOpLo[NLW + 2] = IPM_OP_LO;
+IPM_CONST int kFwLo[NLW + 2] = IPM_FW_LO;
+IPM_CONST int kBwLo[NLW + 1] = IPM_BW_LO;
+IPM_CONST int kLevLo[NLW + 1] = IPM_LEV_LO;
+
+// ----------------------------------------------------------------------------------------------------------------------
+struct Solver {
+  Sm sm; Gm gm; IpmSettings stg;
+  int rb;                                   // reduction scratch toggle
+
+  IPM_FN double sign_of(int k) const {      // Sign vector of createKKT_U (preproc.c:135-170)
+    if (k < N) return 1.0;
+    for (int c = 0; c < NSOC; ++c) if (k == ZOFF + kSocSo[c] + kSocD[c] + 1) return 1.0;
+    return -1.0;
+  }
+
+  // ---- numeric factorisation: S holds the KKT values on entry, the column-scaled factor on exit
+  IPM_FN void pivots(int tid, int lv) {
+    for (int p = kLevLo[lv] + tid; p < kLevLo[lv + 1]; p += T) {
+      const int k = sm.perm[p];
+      double d = sm.S[DG0 + k];
+      const double sg = sign_of(k);
+      if (sg * d <= kEps) d = sg * kDelta;
+      sm.dinv[k] = 1.0 / d;
+    }
+  }
+  IPM_FN void apply_ops(int tid, int lv) {
+    const Op* ops = gm.ops;
+    seg_sub(tid, kOpLo[lv], kOpLo[lv + 1], sm.S, [&](int e, int& t) {
+      const Op o = ops[e];
+      t = o.t;
+      return sm.S[o.a] * sm.S[o.b] * sm.dinv[o.j];
+    });
+  }
+  IPM_FN void tail_factor(int tid);
+  IPM_FN void factor() {
+    if (NLW > 0) phase([&](int tid) { pivots(tid, 0); });
+    for (int lv = 1; lv < NLW; ++lv) {
+      phase([&](int tid) { apply_ops(tid, lv); });
+      phase([&](int tid) { pivots(tid, lv); });
+    }
+    phase([&](int tid) { apply_ops(tid, NLW); });
+    phase([&](int tid) { tail_factor(tid); });
+  }
+
+  // ---- triangular solves, in place on u (k-space)
+  IPM_FN void tail_solve(int tid, double* u);
+  IPM_FN void ldl_solve(double* u) {
+    for (int lv = 1; lv <= NLW; ++lv)
+      phase([&](int tid) {
+        seg_sub(tid, kFwLo[lv], kFwLo[lv + 1], u, [&](int e, int& t) {
+          t = sm.fw_t[e];
+          const int s = sm.fw_s[e];
+          return sm.S[sm.fw_slot[e]] * sm.dinv[s] * u[s];
+        });
+      });
+    phase([&](int tid) {
+      tail_solve(tid, u);
+      // meanwhile: D-solve of the wide columns (the tail warp scales its own entries)
+#ifdef CPG_IPM_HOST_EMU
+      if (tid == 0) for (int p = 0; p < NK - NT; ++p) { const int k = sm.perm[p]; u[k] *= sm.dinv[k]; }
+#else
+      if (tid >= 32 || NT == 0) {
+        const int t2 = NT == 0 ? tid : tid - 32, stride = NT == 0 ? T : T - 32;
+        for (int p = t2; p < NK - NT; p += stride) { const int k = sm.perm[p]; u[k] *= sm.dinv[k]; }
+      }
+#endif
+    });
+    for (int lv = NLW - 1; lv >= 0; --lv)
+      phase([&](int tid) {
+        seg_sub(tid, kBwLo[lv], kBwLo[lv + 1], u, [&](int e, int& t) {
+          t = sm.bw_t[e];
+          return sm.S[e] * sm.dinv[t] * u[sm.bw_s[e]];
+        });
+      });
+  }
+
+  // ---- KKT solve with iterative refinement (kkt_solve, kkt.c:87-265); rhs(k) -> out (k-space); returns #refinements
+  template <class RHS> IPM_FN int kkt_solve(RHS&& rhs, double* out, bool isinit, PerThread<PT>& dpx) {
+    double s_[1], m_[1];
+    phase_red<0, 1>(sm, rb, s_, m_, [&](int tid, double*, double* m) {
+      each_k(tid, NK, [&](int k) { const double b = rhs(k); out[k] = b; m[0] = fmax(m[0], fabs(b)); });
+    });
+    const double thr = (1.0 + m_[0]) * kLinsysAcc;
+    ldl_solve(out);
+    double nerr_prev = NAN;
+    int kref = 0;
+    for (;;) {
+      // error e = b - K out (with the static regularisation written exactly like the reference does)
+      phase_cones(
+          [&](int tid) {
+            each_k(tid, ZOFF + L, [&](int k) {
+              const double o = out[k];
+              double e = rhs(k);
+              if (k < N) e -= kDeltaStat * o;
+              else if (k < ZOFF) e += kDeltaStat * o;
+              else e += kDeltaStat * o + (isinit ? o : sm.v[k - ZOFF] * o);
+              sm.e[k] = e;
+            });
+          },
+          [&](int c, const WarpOps& W) {
+            const int so = ZOFF + kSocSo[c], d = kSocD[c];
+            if (isinit) {
+              W.each(0, d + 2, [&](int r) {
+                const int k = so + r; const double o = out[k];
+                sm.e[k] = r < d ? rhs(k) + (r < d - 1 ? kDeltaStat : -kDeltaStat) * o + o : o;
+              });
+            } else {
+              const double* q = sm.q + kSocQo[c]; const double* sc = sm.sc + 8 * c;
+              const double e2 = sc[SC_ETA2], d1 = sc[SC_D1], u0 = sc[SC_U0], u1 = sc[SC_U1], v1 = sc[SC_V1];
+              const double x1 = out[so], x3 = out[so + d], x4 = out[so + d + 1];
+              const double qtx2 = W.sum(0, d - 1, [&](int i) { return q[i] * out[so + 1 + i]; });
+              const double vu = v1 * x3 + u1 * x4;
+              W.each(0, d - 1, [&](int i) {
+                const int k = so + 1 + i; const double o = out[k];
+                sm.e[k] = rhs(k) + (i + 1 < d - 1 ? kDeltaStat : -kDeltaStat) * o + e2 * (o + vu * q[i]);
+              });
+              if (W.leader()) {
+                sm.e[so] = rhs(so) + (d > 1 ? kDeltaStat : -kDeltaStat) * x1 + e2 * (d1 * x1 + u0 * x4);
+                sm.e[so + d] = e2 * (v1 * qtx2 + x3);
+                sm.e[so + d + 1] = e2 * (u0 * x1 + u1 * qtx2 - x4);
+              }
+            }
+          });
+      phase([&](int tid) {
+        const int n = NNZM, chunk = (n + T - 1) / T;
+        const int lo = tid * chunk, hi = lo + chunk < n ? lo + chunk : n;
+        for (int e = lo; e < hi; ++e) atomic_add(sm.e + sm.mr_s[e], -sm.ag[e] * out[sm.mr_t[e]]);      // - M' [dy; dz]
+        seg_sub(tid, 0, NNZM, sm.e, [&](int e, int& t) { t = sm.mr_t[e]; return sm.ag[e] * out[sm.mr_s[e]]; });   // - M dx
+      });
+      phase_red<0, 1>(sm, rb, s_, m_, [&](int tid, double*, double* m) {
+        each_k(tid, NK, [&](int k) { m[0] = fmax(m[0], fabs(sm.e[k])); });
+      });
+      const double nerr = m_[0];
+      if (kref > 0 && nerr > nerr_prev) {                 // refinement made it worse: undo and stop
+        phase([&](int tid) {
+#pragma unroll
+          for (int j = 0; j < PT; ++j) { const int k = tid + j * T; if (k < NK) out[k] -= dpx.at(tid, j); }
+        });
+        --kref;
+        break;
+      }
+      if (kref == kNitref || nerr < thr || (kref > 0 && nerr_prev < kIrErrFact * nerr)) break;
+      nerr_prev = nerr;
+      ldl_solve(sm.e);
+      phase([&](int tid) {
+#pragma unroll
+        for (int j = 0; j < PT; ++j) { const int k = tid + j * T; if (k < NK) { const double dv = sm.e[k]; dpx.at(tid, j) = dv; out[k] += dv; } }
+      });
+      ++kref;
+    }
+    return kref;
+  }
+
+  // ---- cone helpers (one warp per cone)
+  // lambda = W v for the cone: out may alias v
+  IPM_FN void cone_scale(int c, const WarpOps& W, const double* v, double* out) const {
+    const int so = kSocSo[c], d = kSocD[c];
+    const double* q = sm.q + kSocQo[c]; const double* sc = sm.sc + 8 * c;
+    const double zeta = W.sum(0, d - 1, [&](int i) { return q[i] * v[so + 1 + i]; });
+    const double v0 = v[so];
+    const double factor = v0 + safediv(zeta, 1.0 + sc[SC_A]);
+    const double eta = sc[SC_ETA];
+    W.sync();
+    W.each(0, d - 1, [&](int i) { out[so + 1 + i] = eta * (v[so + 1 + i] + factor * q[i]); });
+    if (W.leader()) out[so] = eta * (sc[SC_A] * v0 + zeta);
+    W.sync();
+  }
+  // line-search contribution of one cone (ecos.c:985-1035): returns the conic step (0 = no restriction)
+  IPM_FN double cone_step(int c, const WarpOps& W, const double* ds, const double* dz) const {
+    const int so = kSocSo[c], d = kSocD[c];
+    const double* lk = sm.lam + so;
+    const double l0 = lk[0];
+    const double n2 = l0 * l0 - W.sum(1, d, [&](int j) { return lk[j] * lk[j]; });
+    if (n2 <= 0.0) return 0.0;
+    const double lkn = sqrt(n2), inv = 1.0 / lkn;
+    const double lb0 = l0 / lkn;
+    double step = 0.0;
+    for (int which = 0; which < 2; ++which) {
+      const double* dv = (which == 0 ? ds : dz) + so;
+      const double lt = lb0 * dv[0] - W.sum(1, d, [&](int j) { return (lk[j] / lkn) * dv[j]; });
+      const double r0 = inv * lt;
+      const double factor = (lt + dv[0]) / (lb0 + 1.0);
+      const double nr = sqrt(W.sum(1, d, [&](int j) { const double r = inv * (dv[j] - factor * (lk[j] / lkn)); return r * r; })) - r0;
+      if (nr > step) step = nr;
+    }
+    return step;
+  }
+
+  IPM_FN int solve_instance(int inst, const IpmIO& io, double* best);
+};
+
+// ----------------------------------------------------------------------------------------------------------------------
+// dense tail block: one warp (lane = row within the block)
+IPM_FN void Solver::tail_factor(int tid) {
+#ifdef CPG_IPM_HOST_EMU
+  if (tid != 0) return;
+  for (int j = 0; j < NT; ++j) {
+    const int kj = sm.tail_k[j];
+    double d = sm.S[DG0 + kj]; const double sg = sign_of(kj);
+    if (sg * d <= kEps) d = sg * kDelta;
+    const double dj = 1.0 / d; sm.dinv[kj] = dj;
+    for (int i = j + 1; i < NT; ++i) {
+      const double sij = sm.S[TT0 + i * NT + j];
+      for (int k = j + 1; k < i; ++k) sm.S[TT0 + i * NT + k] -= sij * sm.S[TT0 + k * NT + j] * dj;
+      sm.S[DG0 + sm.tail_k[i]] -= sij * sij * dj;
+    }
+  }
+#else
+  if (tid >= 32 || NT == 0) return;
+  const int i = tid;
+  const int ki = i < NT ? sm.tail_k[i] : 0;
+  for (int j = 0; j < NT; ++j) {
+    const int kj = sm.tail_k[j];
+    double dj = 0.0;
+    if (i == j) {
+      double d = sm.S[DG0 + kj]; const double sg = sign_of(kj);
+      if (sg * d <= kEps) d = sg * kDelta;
+      dj = 1.0 / d; sm.dinv[kj] = dj;
+    }
+    dj = __shfl_sync(0xffffffffu, dj, j);
+    if (i > j && i < NT) {
+      const double sij = sm.S[TT0 + i * NT + j];
+      for (int k = j + 1; k < i; ++k) sm.S[TT0 + i * NT + k] -= sij * sm.S[TT0 + k * NT + j] * dj;
+      sm.S[DG0 + ki] -= sij * sij * dj;
+    }
+    __syncwarp();
+  }
+#endif
+}
+
+IPM_FN void Solver::tail_solve(int tid, double* u) {
+#ifdef CPG_IPM_HOST_EMU
+  if (tid != 0) return;
+  for (int j = 0; j < NT; ++j)
+    for (int i = j + 1; i < NT; ++i) u[sm.tail_k[i]] -= sm.S[TT0 + i * NT + j] * sm.dinv[sm.tail_k[j]] * u[sm.tail_k[j]];
+  for (int j = 0; j < NT; ++j) u[sm.tail_k[j]] *= sm.dinv[sm.tail_k[j]];
+  for (int j = NT - 1; j >= 0; --j)
+    for (int i = j + 1; i < NT; ++i) u[sm.tail_k[j]] -= sm.S[TT0 + i * NT + j] * sm.dinv[sm.tail_k[j]] * u[sm.tail_k[i]];
+#else
+  if (tid >= 32 || NT == 0) return;
+  const int i = tid;
+  const int ki = i < NT ? sm.tail_k[i] : 0;
+  double ui = i < NT ? u[ki] : 0.0;
+  const double di = i < NT ? sm.dinv[ki] : 0.0;
+  for (int j = 0; j < NT; ++j) {
+    const double uj = __shfl_sync(0xffffffffu, ui, j), dj = __shfl_sync(0xffffffffu, di, j);
+    if (i > j && i < NT) ui -= sm.S[TT0 + i * NT + j] * dj * uj;
+  }
+  ui *= di;
+  for (int r = NT - 1; r > 0; --r) {                       // column sweep: row r is final, push it to rows j < r
+    const double xr = __shfl_sync(0xffffffffu, ui, r);
+    if (i < r) ui -= sm.S[TT0 + r * NT + i] * di * xr;
+  }
+  if (i < NT) u[ki] = ui;
+#endif
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+struct Stats { double gap, mu, kapovert, pcost, dcost, relgap, pres, dres, pinfres, dinfres; };
+
+IPM_FN bool better(const Stats& a, const Stats& b) {        // compareStatistics, ecos.c:61-98
+  const bool g = a.gap > 0 && b.gap > 0 && a.gap < b.gap;
+  const bool mu = a.mu > 0 && a.mu < b.mu;
+  if (a.kapovert > 1) return g && (a.pinfres > 0 && a.pinfres < b.pres) && mu;
+  return g && (a.pres > 0 && a.pres < b.pres) && (a.dres > 0 && a.dres < b.dres) &&
+         (a.kapovert > 0 && a.kapovert < b.kapovert) && mu;
+}
+
+IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
+  PerThread<PT> dpx;
+  double s_[16], m_[4];
+  const double* par = io.params + size_t(inst) * NPB;
+  auto rhs1 = [&](int k) { return k < N ? -sm.cbh[k] : sm.cbh[k]; };
+  auto rhs2 = [&](int k) { return sm.rhs[k]; };
+  double* const zv = sm.xyz + ZOFF;           // z (stretched)
+  double* const wdz = sm.e + ZOFF;            // W dz lives in the error vector between solves
+
+  // ---- cpg_canonicalize: c, b, h from the user parameters (equilibrated), cvxpygen/utils.py:279-294 + equil.c:326-338
+  phase([&](int tid) { each_k(tid, NK, [&](int k) { sm.cbh[k] = gm.cbh_base[k]; }); });
+  phase([&](int tid) { each_k(tid, NMAP, [&](int e) { atomic_add(sm.cbh + gm.map_t[e], gm.map_v[e] * par[gm.map_p[e]]); }); });
+  phase_red<3, 0>(sm, rb, s_, m_, [&](int tid, double* s, double*) {
+    each_k(tid, NK, [&](int k) { const double v = sm.cbh[k]; s[k < N ? 0 : (k < ZOFF ? 1 : 2)] += v * v; });
+  });
+  const double resx0 = fmax(1.0, sqrt(s_[0])), resy0 = fmax(1.0, sqrt(s_[1])), resz0 = fmax(1.0, sqrt(s_[2]));
+
+  // ---- init (ecos.c:260-452): K with the identity scaling, two least-squares solves, bring2cone
+  phase([&](int tid) {
+    each_k(tid, NS, [&](int i) {
+      double v = gm.Sbase[i];
+      if (i >= DG0 + ZOFF && i < DG0 + NK) v += sign_of(i - DG0) > 0 ? 1.0 : -1.0;
+      sm.S[i] = v;
+    });
+    each_k(tid, MT, [&](int i) { sm.sv[i] = 0.0; sm.lam[i] = 0.0; sm.rz[i] = 0.0; sm.dsw[i] = 0.0; });
+    each_k(tid, NK, [&](int k) { sm.xyz[k] = 0.0; });
+  });
+  factor();
+  auto bring2cone = [&](const double* r, double rsign, double* out) {        // out = rsign * r shifted into the cone
+    phase_red_cones<0, 1>(sm, rb, s_, m_,
+        [&](int tid, double*, double* m) { each_k(tid, L, [&](int i) { const double v = rsign * r[i]; if (v <= 0) m[0] = fmax(m[0], -v); }); },
+        [&](int c, const WarpOps& W) {
+          const int so = kSocSo[c], d = kSocD[c];
+          const double nr = sqrt(W.sum(1, d, [&](int j) { return r[so + j] * r[so + j]; }));
+          if (W.leader()) sm.cone[c] = rsign * r[so] - nr;
+        });
+    double alpha = fmax(-kGamma, m_[0]);
+    for (int c = 0; c < NSOC; ++c) { const double cres = sm.cone[c]; if (cres <= 0 && -cres > alpha) alpha = -cres; }
+    alpha += 1.0;
+    phase_cones([&](int tid) { each_k(tid, L, [&](int i) { out[i] = rsign * r[i] + alpha; }); },
+                [&](int c, const WarpOps& W) {
+                  const int so = kSocSo[c], d = kSocD[c];
+                  W.each(0, d, [&](int j) { out[so + j] = rsign * r[so + j] + (j == 0 ? alpha : 0.0); });
+                });
+  };
+  kkt_solve([&](int k) { return k < N ? 0.0 : sm.cbh[k]; }, sm.px, true, dpx);
+  phase([&](int tid) { each_k(tid, N, [&](int k) { sm.xyz[k] = sm.px[k]; }); });
+  bring2cone(sm.px + ZOFF, -1.0, sm.sv);
+  kkt_solve([&](int k) { return k < N ? -sm.cbh[k] : 0.0; }, sm.px, true, dpx);
+  phase([&](int tid) { each_k(tid, P, [&](int i) { sm.xyz[N + i] = sm.px[N + i]; }); });
+  bring2cone(sm.px + ZOFF, 1.0, zv);
+  double kap = 1.0, tau = 1.0;
+
+  // ---- main loop (ecos.c:1123-1583)
+  Stats I{}, Ibest{};
+  double cx = 0, by = 0, hz = 0, rt = 0, best_kap = 1, best_tau = 1, best_cx = 0, best_by = 0, best_hz = 0;
+  double pres_prev = NAN, step = 0.0;
+  int exitcode = kFatal, it = 0;
+  auto save_best = [&]() {
+    Ibest = I; best_kap = kap; best_tau = tau; best_cx = cx; best_by = by; best_hz = hz;
+    phase([&](int tid) { each_k(tid, NK, [&](int k) { best[k] = sm.xyz[k]; }); each_k(tid, MT, [&](int i) { best[NK + i] = sm.sv[i]; }); });
+  };
+  auto restore_best = [&]() {
+    I = Ibest; kap = best_kap; tau = best_tau; cx = best_cx; by = best_by; hz = best_hz;
+    phase([&](int tid) { each_k(tid, NK, [&](int k) { sm.xyz[k] = best[k]; }); each_k(tid, MT, [&](int i) { sm.sv[i] = best[NK + i]; }); });
+  };
+  auto check_exit = [&](int mode) {                          // checkExitConditions, ecos.c:179-257
+    const double feastol = mode ? stg.feastol_inacc : stg.feastol, abstol = mode ? stg.abstol_inacc : stg.abstol,
+                 reltol = mode ? stg.reltol_inacc : stg.reltol;
+    if ((-cx > 0 || -by - hz >= -abstol) && (I.pres < feastol && I.dres < feastol) && (I.gap < abstol || I.relgap < reltol))
+      return int(kOptimal) + mode;
+    if (I.dinfres < feastol && tau < kap) return int(kDinf) + mode;
+    if ((I.pinfres < feastol && tau < kap) || (tau < stg.feastol && kap < stg.feastol && I.pinfres < stg.feastol))
+      return int(kPinf) + mode;
+    return int(kNotConverged);
+  };
+  for (;; ++it) {
+    // computeResiduals: rx -> rhs[0:N], ry -> rhs[N:ZOFF], rz -> rz
+    phase([&](int tid) {
+      each_k(tid, ZOFF, [&](int k) { sm.rhs[k] = 0.0; });
+      each_k(tid, MT, [&](int i) { sm.rz[i] = sm.sv[i]; });
+    });
+    phase([&](int tid) {
+      const int n = NNZM, chunk = (n + T - 1) / T;
+      const int lo = tid * chunk, hi = lo + chunk < n ? lo + chunk : n;
+      for (int e = lo; e < hi; ++e) atomic_add(sm.rhs + sm.mr_s[e], -sm.ag[e] * sm.xyz[sm.mr_t[e]]);   // -A'y - G'z
+      const int split = IPM_NNZA;                                                                      // rows of A first
+      auto mx = [&](int e, int& t) { t = sm.mr_t[e]; return -sm.ag[e] * sm.xyz[sm.mr_s[e]]; };
+      seg_sub(tid, 0, split, sm.rhs, mx);                                                              // A x
+      seg_sub(tid, split, NNZM, sm.rz - ZOFF, mx);                                                     // s + G x
+    });
+    phase_red<16, 0>(sm, rb, s_, m_, [&](int tid, double* s, double*) {
+      each_k(tid, N, [&](int k) {
+        const double hr = sm.rhs[k], c = sm.cbh[k], x = sm.xyz[k];
+        s[0] += hr * hr; s[3] += c * x; s[6] += x * x;
+        const double r = hr - tau * c; sm.rhs[k] = r; s[11] += r * r;
+      });
+      each_k(tid, P, [&](int i) {
+        const int k = N + i; const double hr = sm.rhs[k], b = sm.cbh[k], y = sm.xyz[k];
+        s[1] += hr * hr; s[4] += b * y; s[7] += y * y;
+        const double r = hr - tau * b; sm.rhs[k] = r; s[12] += r * r;
+      });
+      each_k(tid, MT, [&](int i) {
+        const double hr = sm.rz[i], h = sm.cbh[ZOFF + i], z = zv[i], sv = sm.sv[i];
+        s[2] += hr * hr; s[5] += h * z; s[8] += sv * sv; s[9] += z * z; s[10] += sv * z;
+        const double r = hr - tau * h; sm.rz[i] = r; s[13] += r * r;
+      });
+    });
+    {
+      const double hresx = sqrt(s_[0]), hresy = sqrt(s_[1]), hresz = sqrt(s_[2]);
+      cx = s_[3]; by = s_[4]; hz = s_[5];
+      const double nx = sqrt(s_[6]), ny = sqrt(s_[7]), ns = sqrt(s_[8]), nz = sqrt(s_[9]);
+      rt = kap + cx + by + hz;
+      // updateStatistics
+      I.gap = s_[10];
+      I.mu = (I.gap + kap * tau) / (CONE_D + 1);
+      I.kapovert = kap / tau;
+      I.pcost = cx / tau; I.dcost = -(hz + by) / tau;
+      I.relgap = I.pcost < 0 ? I.gap / (-I.pcost) : (I.dcost > 0 ? I.gap / I.dcost : NAN);
+      const double nry = P > 0 ? sqrt(s_[12]) / fmax(resy0 + nx, 1.0) : 0.0;
+      const double nrz = sqrt(s_[13]) / fmax(resz0 + nx + ns, 1.0);
+      I.pres = fmax(nry, nrz) / tau;
+      I.dres = sqrt(s_[11]) / fmax(resx0 + ny + nz, 1.0) / tau;
+      I.pinfres = (hz + by) / fmax(ny + nz, 1.0) < -stg.reltol ? hresx / fmax(ny + nz, 1.0) : NAN;
+      I.dinfres = cx / fmax(nx, 1.0) < -stg.reltol ? fmax(hresy / fmax(nx, 1.0), hresz / fmax(nx + ns, 1.0)) : NAN;
+    }
+    // safeguards and exit tests
+    if (it > 0 && (I.pres > kSafeguard * pres_prev || I.gap < 0)) {
+      restore_best(); exitcode = check_exit(kInaccOffset);
+      if (exitcode == kNotConverged) exitcode = kNumerics;
+      break;
+    }
+    pres_prev = I.pres;
+    exitcode = check_exit(0);
+    if (exitcode != kNotConverged) break;
+    if (it > 0 && step == kStepMin * kGamma) {
+      restore_best(); exitcode = check_exit(kInaccOffset);
+      if (exitcode == kNotConverged) exitcode = kNumerics;
+      break;
+    }
+    if (it == stg.maxit) {
+      if (!better(I, Ibest)) restore_best();
+      exitcode = check_exit(kInaccOffset);
+      if (exitcode == kNotConverged) exitcode = kMaxit;
+      break;
+    }
+    if (isnan(I.pcost)) {
+      if (!better(I, Ibest)) restore_best();
+      exitcode = check_exit(kInaccOffset);
+      if (exitcode == kNotConverged) exitcode = kNumerics;
+      break;
+    }
+    if (it == 0 || better(I, Ibest)) save_best();
+
+    // updateScalings + lambda = W z, and the constant part of the KKT image
+    phase_cones(
+        [&](int tid) {
+          if (tid == 0) *sm.flag = 0;
+          each_k(tid, L, [&](int i) {
+            const double v = safediv(sm.sv[i], zv[i]), w = sqrt(v);
+            sm.v[i] = v; sm.w[i] = w; sm.lam[i] = w * zv[i];
+          });
+          each_k(tid, NS, [&](int i) { sm.S[i] = gm.Sbase[i]; });
+        },
+        [&](int c, const WarpOps& W) {
+          const int so = kSocSo[c], d = kSocD[c];
+          const double* sk = sm.sv + so; const double* zk = zv + so;
+          double* q = sm.q + kSocQo[c]; double* sc = sm.sc + 8 * c;
+          const double sres = sk[0] * sk[0] - W.sum(1, d, [&](int j) { return sk[j] * sk[j]; });
+          const double zres = zk[0] * zk[0] - W.sum(1, d, [&](int j) { return zk[j] * zk[j]; });
+          if (sres <= 0 || zres <= 0) { if (W.leader()) sm.cone[c] = 1.0; return; }
+          const double snorm = sqrt(sres), znorm = sqrt(zres);
+          const double eta2 = safediv(snorm, znorm), eta = sqrt(eta2);
+          const double gamma = sqrt(0.5 * (1.0 + W.sum(0, d, [&](int j) { return safediv(sk[j], snorm) * safediv(zk[j], znorm); })));
+          const double o2g = safediv(0.5, gamma);
+          const double a = o2g * (safediv(sk[0], snorm) + safediv(zk[0], znorm));
+          W.each(1, d, [&](int j) { q[j - 1] = o2g * (safediv(sk[j], snorm) - safediv(zk[j], znorm)); });
+          W.sync();
+          const double w = W.sum(0, d - 1, [&](int i) { return q[i] * q[i]; });
+          const double temp = 1.0 + a;
+          const double cc = 1.0 + a + safediv(w, temp);
+          const double dd = 1.0 + safediv(2.0, temp) + safediv(w, temp * temp);
+          double d1 = 0.5 * (a * a + w * (1.0 - safediv(cc * cc, 1.0 + w * dd)));
+          if (d1 < 0) d1 = 0;
+          const double u0sq = a * a + w - d1, u0 = sqrt(u0sq);
+          const double c2byu02 = safediv(cc * cc, u0sq);
+          if (c2byu02 - dd <= 0) { if (W.leader()) sm.cone[c] = 1.0; return; }
+          if (W.leader()) {
+            sc[SC_ETA2] = eta2; sc[SC_ETA] = eta; sc[SC_A] = a; sc[SC_D1] = d1; sc[SC_U0] = u0;
+            sc[SC_U1] = sqrt(c2byu02); sc[SC_V1] = sqrt(c2byu02 - dd); sc[SC_W] = w;
+            sm.cone[c] = 0.0;
+          }
+          W.sync();
+          cone_scale(c, W, zv, sm.lam);
+        });
+    {
+      bool out = false;
+      for (int c = 0; c < NSOC; ++c) out = out || sm.cone[c] != 0.0;
+      if (out) {
+        restore_best(); exitcode = check_exit(kInaccOffset);
+        if (exitcode == kNotConverged) exitcode = kOutcone;
+        break;
+      }
+    }
+    // kkt_update: the scaling block
+    phase_cones(
+        [&](int tid) { each_k(tid, L, [&](int i) { sm.S[DG0 + ZOFF + i] = -sm.v[i] - kDeltaStat; }); },
+        [&](int c, const WarpOps& W) {
+          const int so = kSocSo[c], d = kSocD[c];
+          const double* q = sm.q + kSocQo[c]; const double* sc = sm.sc + 8 * c;
+          const double e2 = sc[SC_ETA2];
+          const uint16_t* sv_ = sm.socv + kSocVo[c]; const uint16_t* su_ = sm.socu + kSocUo[c];
+          W.each(0, d, [&](int r) { sm.S[DG0 + ZOFF + so + r] = (r == 0 ? -e2 * sc[SC_D1] : -e2) - kDeltaStat; });
+          W.each(0, d - 1, [&](int i) { sm.S[sv_[i]] = -e2 * sc[SC_V1] * q[i]; sm.S[su_[1 + i]] = -e2 * sc[SC_U1] * q[i]; });
+          if (W.leader()) {
+            sm.S[su_[0]] = -e2 * sc[SC_U0];
+            sm.S[DG0 + ZOFF + so + d] = -e2;
+            sm.S[DG0 + ZOFF + so + d + 1] = e2 + kDeltaStat;
+          }
+        });
+    factor();
+    // search directions
+    kkt_solve(rhs1, sm.sol1, false, dpx);
+    phase([&](int tid) {                                      // RHS_affine
+      each_k(tid, P, [&](int i) { sm.rhs[N + i] = -sm.rhs[N + i]; });
+      each_k(tid, MT, [&](int i) { sm.rhs[ZOFF + i] = sm.sv[i] - sm.rz[i]; });
+    });
+    kkt_solve(rhs2, sm.px, false, dpx);
+    phase_red<2, 0>(sm, rb, s_, m_, [&](int tid, double* s, double*) {
+      each_k(tid, NK, [&](int k) { const double c = sm.cbh[k]; s[0] += c * sm.sol1[k]; s[1] += c * sm.px[k]; });
+    });
+    const double dtau_denom = kap / tau - s_[0];
+    const double dtauaff = (rt - kap + s_[1]) / dtau_denom;
+    const double dkapaff = -kap - kap / tau * dtauaff;
+    // dzaff, W dzaff, W\dsaff and the affine line search
+    auto direction_and_linesearch = [&](double dt, bool combined, double dtau_, double dkap_) -> double {
+      // px_z += dt * sol1_z (all of px when combined); wdz = W px_z; dsw = -(combined ? dsw : lam) - wdz
+      phase_red_cones<0, 2>(sm, rb, s_, m_,
+          [&](int tid, double*, double* m) {
+            each_k(tid, combined ? ZOFF : 0, [&](int k) { sm.px[k] += dt * sm.sol1[k]; });
+            each_k(tid, L, [&](int i) {
+              const double dz = sm.px[ZOFF + i] + dt * sm.sol1[ZOFF + i];
+              sm.px[ZOFF + i] = dz;
+              const double wz = sm.w[i] * dz, lam = sm.lam[i];
+              const double dsw = -(combined ? sm.dsw[i] : lam) - wz;
+              wdz[i] = wz; sm.dsw[i] = dsw;
+              m[0] = fmax(m[0], -dsw / lam); m[1] = fmax(m[1], -wz / lam);
+            });
+          },
+          [&](int c, const WarpOps& W) {
+            const int so = kSocSo[c], d = kSocD[c];
+            W.each(0, d + 2, [&](int r) { sm.px[ZOFF + so + r] += dt * sm.sol1[ZOFF + so + r]; });
+            W.sync();
+            cone_scale(c, W, sm.px + ZOFF, wdz);
+            W.each(0, d, [&](int r) { sm.dsw[so + r] = -(combined ? sm.dsw[so + r] : sm.lam[so + r]) - wdz[so + r]; });
+            W.sync();
+            const double st = cone_step(c, W, sm.dsw, wdz);
+            if (W.leader()) sm.cone[c] = st;
+          });
+      // lineSearch, ecos.c:947-1046 (m_[0] = -rhomin, m_[1] = -sigmamin)
+      double alpha;
+      if (L > 0) {
+        const double rhomin = -m_[0], sigmamin = -m_[1];
+        if (-sigmamin > -rhomin) alpha = sigmamin < 0 ? 1.0 / (-sigmamin) : 1.0 / kEps;
+        else alpha = rhomin < 0 ? 1.0 / (-rhomin) : 1.0 / kEps;
+      } else alpha = 10.0;
+      const double mtt = -tau / dtau_, mkk = -kap / dkap_;
+      if (mtt > 0 && mtt < alpha) alpha = mtt;
+      if (mkk > 0 && mkk < alpha) alpha = mkk;
+      for (int c = 0; c < NSOC; ++c) { const double st = sm.cone[c]; if (st != 0.0) { const double t_ = 1.0 / st; if (t_ < alpha) alpha = t_; } }
+      if (alpha > kStepMax) alpha = kStepMax;
+      if (alpha < kStepMin) alpha = kStepMin;
+      return alpha;
+    };
+    const double step_aff = direction_and_linesearch(dtauaff, false, dtauaff, dkapaff);
+    double sigma = 1.0 - step_aff; sigma = sigma * sigma * sigma;
+    if (sigma > kSigmaMax) sigma = kSigmaMax;
+    if (sigma < kSigmaMin) sigma = kSigmaMin;
+    const double sigmamu = sigma * I.mu, oms = 1.0 - sigma;
+    // RHS_combined (ecos.c:688-757): dsw <- lambda \ (lambda o lambda + dsw o wdz - sigma mu e); rhs_z = -(1-sigma) rz + W dsw
+    phase_cones(
+        [&](int tid) {
+          each_k(tid, ZOFF, [&](int k) { sm.rhs[k] *= oms; });
+          each_k(tid, L, [&](int i) {
+            const double lam = sm.lam[i];
+            const double ds1 = lam * lam + sm.dsw[i] * wdz[i] - sigmamu;
+            const double dv = safediv(ds1, lam);
+            sm.dsw[i] = dv;
+            sm.rhs[ZOFF + i] = -oms * sm.rz[i] + sm.w[i] * dv;
+          });
+        },
+        [&](int c, const WarpOps& W) {
+          const int so = kSocSo[c], d = kSocD[c];
+          const double* lk = sm.lam + so; double* ds = sm.dsw + so; const double* wz = wdz + so;
+          double* tmp = sm.px + ZOFF + so;                       // px is free between the two solves
+          const double l0 = lk[0], ds0 = ds[0], wz0 = wz[0];
+          const double ll = W.sum(0, d, [&](int j) { return lk[j] * lk[j]; });
+          const double dw = W.sum(0, d, [&](int j) { return ds[j] * wz[j]; });
+          W.each(1, d, [&](int j) { tmp[j] = 2.0 * l0 * lk[j] + ds0 * wz[j] + wz0 * ds[j]; });
+          const double w0 = ll + dw - sigmamu;
+          W.sync();
+          // conicDivision(lambda, ds1)
+          const double rho = l0 * l0 - W.sum(1, d, [&](int j) { return lk[j] * lk[j]; });
+          const double zeta = W.sum(1, d, [&](int j) { return lk[j] * tmp[j]; });
+          const double factor = safediv(safediv(zeta, l0) - w0, rho);
+          W.each(1, d, [&](int j) { ds[j] = factor * lk[j] + safediv(tmp[j], l0); });
+          if (W.leader()) ds[0] = safediv(l0 * w0 - zeta, rho);
+          W.sync();
+          cone_scale(c, W, sm.dsw, sm.px + ZOFF);
+          W.each(0, d, [&](int r) { sm.rhs[ZOFF + so + r] = -oms * sm.rz[so + r] + tmp[r]; });
+          if (W.leader()) { sm.rhs[ZOFF + so + d] = 0.0; sm.rhs[ZOFF + so + d + 1] = 0.0; }
+          W.sync();
+        });
+    kkt_solve(rhs2, sm.px, false, dpx);
+    phase_red<1, 0>(sm, rb, s_, m_, [&](int tid, double* s, double*) {
+      each_k(tid, NK, [&](int k) { s[0] += sm.cbh[k] * sm.px[k]; });
+    });
+    const double bkap = kap * tau + dkapaff * dtauaff - sigmamu;
+    const double dtau = (oms * rt - bkap / tau + s_[0]) / dtau_denom;
+    const double dkap = -(bkap + kap * dtau) / tau;
+    step = direction_and_linesearch(dtau, true, dtau, dkap) * kGamma;
+    // ds = W (W\ds); update the iterate
+    phase_cones(
+        [&](int tid) {
+          each_k(tid, ZOFF + L, [&](int k) { sm.xyz[k] += step * sm.px[k]; });
+          each_k(tid, L, [&](int i) { sm.sv[i] += step * (sm.w[i] * sm.dsw[i]); });
+        },
+        [&](int c, const WarpOps& W) {
+          const int so = kSocSo[c], d = kSocD[c];
+          cone_scale(c, W, sm.dsw, wdz);
+          W.each(0, d, [&](int r) { sm.sv[so + r] += step * wdz[so + r]; zv[so + r] += step * sm.px[ZOFF + so + r]; });
+        });
+    kap += step * dkap; tau += step * dtau;
+  }
+
+  // ---- backscale (ecos.c:1051-1070) and retrieval (cpg_retrieve_prim / dual / info, cvxpygen/utils.py:950-985)
+  phase([&](int tid) {
+    const double it_ = 1.0 / tau;
+    (void)it_;
+    each_k(tid, NPRIM, [&](int i) { const int k = gm.prim_idx[i]; io.prim[size_t(inst) * NPRIM + i] = sm.xyz[k] * gm.unscale[k] / tau; });
+    each_k(tid, NDUAL, [&](int i) { const int k = gm.dual_idx[i]; io.dual[size_t(inst) * NDUAL + i] = sm.xyz[k] * gm.unscale[k] / tau; });
+    if (io.sol_x) each_k(tid, N, [&](int k) { io.sol_x[size_t(inst) * N + k] = sm.xyz[k] * gm.unscale[k] / tau; });
+    if (io.sol_y) each_k(tid, P, [&](int i) { io.sol_y[size_t(inst) * P + i] = sm.xyz[N + i] * gm.unscale[N + i] / tau; });
+    if (io.sol_z || io.sol_s) {
+      each_k(tid, L, [&](int i) {
+        if (io.sol_z) io.sol_z[size_t(inst) * M + i] = zv[i] * gm.unscale[ZOFF + i] / tau;
+        if (io.sol_s) io.sol_s[size_t(inst) * M + i] = sm.sv[i] / (gm.unscale[ZOFF + i] * tau);
+      });
+      int o = L;
+      for (int c = 0; c < NSOC; ++c) {
+        const int so = kSocSo[c], d = kSocD[c];
+        each_k(tid, d, [&](int r) {
+          if (io.sol_z) io.sol_z[size_t(inst) * M + o + r] = zv[so + r] * gm.unscale[ZOFF + so + r] / tau;
+          if (io.sol_s) io.sol_s[size_t(inst) * M + o + r] = sm.sv[so + r] / (gm.unscale[ZOFF + so + r] * tau);
+        });
+        o += d;
+      }
+    }
+    if (tid == 0) {
+      const double obj = I.pcost + IPM_D_CONST;
+      io.obj_val[inst] = IPM_IS_MAX ? -obj : obj;
+      io.iter[inst] = it; io.status[inst] = exitcode; io.pri_res[inst] = I.pres; io.dua_res[inst] = I.dres;
+    }
+  });
+  return exitcode;
+}
+
+#ifndef CPG_IPM_HOST_EMU
+// ----------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CPG_IPM_THREADS, 1)
+ipm_kernel(const unsigned char* __restrict__ smem_blob, const unsigned char* __restrict__ gmem_blob, IpmSettings stg, IpmIO io) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int next_inst;
+  Solver sv;
+  sv.sm = make_sm(smem_raw);
+  sv.gm = make_gm(gmem_blob);
+  sv.stg = stg; sv.rb = 0;
+  // stage the constant tables: [f64 ag_val | u16 tables] -> [O_AG ... | after the f64 area]
+  {
+    const double* src = reinterpret_cast<const double*>(smem_blob);
+    for (int i = threadIdx.x; i < NNZM; i += T) sv.sm.ag[i] = src[i];
+    const uint16_t* hs = reinterpret_cast<const uint16_t*>(smem_blob + IPM_SB_U16_OFF);
+    uint16_t* hd = reinterpret_cast<uint16_t*>(reinterpret_cast<double*>(smem_raw) + O_F64_END);
+    for (int i = threadIdx.x; i < U16_COUNT; i += T) hd[i] = hs[i];
+  }
+  __syncthreads();
+  double* best = io.best + size_t(blockIdx.x) * (NK + MT);
+  for (;;) {
+    if (threadIdx.x == 0) next_inst = atomicAdd(io.counter, 1);
+    __syncthreads();
+    const int inst = next_inst;
+    __syncthreads();
+    if (inst >= io.B) break;
+    sv.solve_instance(inst, io, best);
+  }
+}
+#endif
+
+}  // namespace cpgipm

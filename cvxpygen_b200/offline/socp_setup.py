@@ -1,0 +1,398 @@
+"""Generation-time setup of one SOCP family for the IPM-CUDA backend (BASELINE config 3).
+
+What the reference does once per problem in ECOS_setup (cvxpygen/solvers/ecos/src/preproc.c:600-1000): equilibrate the
+data (src/equil.c:210-340), build the 'stretched' KKT skeleton with its static regularisation (src/preproc.c:77-330),
+order it with AMD and run the symbolic LDL'.  Here the same steps produce the tables of a CTA-per-instance kernel:
+
+  * everything lives in ONE index space, the natural stretched order  k = [x (n) | y (p) | z stretched (m + 2 nsoc)],
+    so the constraint matrix M = [A ; G stretched] is a single COO table (sorted by row) that serves both the residuals
+    of the iterate and the refinement residuals of the KKT solves;
+  * the elimination order is a minimum-degree order re-sequenced by elimination-tree level (cvxpygen_b200.offline.kkt);
+    the leading WIDE levels are processed by all threads with one barrier per level, the trailing chain of narrow
+    levels is closed into a dense block of at most 32 columns that one warp factors and solves with shuffles;
+  * the numeric factorisation is table driven: a slot array S = [L entries of wide columns | diagonal | dense tail
+    block], a base image of the constant KKT entries, and a list of update operations (target, a, b, column) sorted by
+    the level of the target's column;  L is kept column-scaled by D (S_ij = L_ij D_j), Dinv separately;
+  * triangular solves are pull-form: forward entries sorted by (level of row, row), backward entries in slot order.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import scipy.sparse as sp
+
+from ..ir import CanonFamily
+from . import kkt as _kkt
+
+DELTASTAT = 7e-8          # ecos/include/ecos.h:54
+EQUIL_ITERS = 3           # ecos/include/ecos.h:81
+MAX_TAIL = 32
+
+
+def ecos_equilibrate(A: sp.csc_matrix, G: sp.csc_matrix, l: int, q: List[int], iters: int = EQUIL_ITERS):
+    """Ruiz equilibration as ECOS applies it (use_ruiz_equilibration, ecos/src/equil.c:210-340): per pass the scaling
+    is sqrt(max |entry|) per row and per column, with one shared value -- the SUM of the row maxima -- for all rows of a
+    second-order cone, values below 1e-6 replaced by 1; rows are divided first, then columns."""
+    A = sp.csc_matrix(A, dtype=float, copy=True); G = sp.csc_matrix(G, dtype=float, copy=True)
+    n, p, m = G.shape[1], A.shape[0], G.shape[0]
+    xe, Ae, Ge = np.ones(n), np.ones(p), np.ones(m)
+    cone_of = np.arange(m)
+    o = l
+    for d in q:
+        cone_of[o:o + d] = o; o += d
+    for _ in range(iters):
+        cmax = np.maximum(_kkt_absmax_cols(A, n), _kkt_absmax_cols(G, n))
+        ra = _kkt_absmax_rows(A, p)
+        rg = _kkt_absmax_rows(G, m)
+        tot = np.zeros(m)
+        for i in range(m):                      # sequential accumulation, like the C loop
+            tot[cone_of[i]] += rg[i]
+        rg = tot[cone_of]
+        xt, at, gt = (np.where(np.abs(v) < 1e-6, 1.0, np.sqrt(v)) for v in (cmax, ra, rg))
+        A = _div_rows_cols(A, at, xt); G = _div_rows_cols(G, gt, xt)
+        xe *= xt; Ae *= at; Ge *= gt
+    return A, G, xe, Ae, Ge
+
+
+def _kkt_absmax_cols(M, n):
+    out = np.zeros(n)
+    if M.nnz:
+        np.maximum.at(out, np.repeat(np.arange(n), np.diff(M.indptr)), np.abs(M.data))
+    return out
+
+
+def _kkt_absmax_rows(M, m):
+    out = np.zeros(m)
+    if M.nnz:
+        np.maximum.at(out, M.indices, np.abs(M.data))
+    return out
+
+
+def _div_rows_cols(M, r, c):
+    M = M.copy()
+    cols = np.repeat(np.arange(M.shape[1]), np.diff(M.indptr))
+    M.data = (M.data / r[M.indices]) / c[cols]
+    return M
+
+
+@dataclass
+class SOCPSetup:
+    family: CanonFamily
+    batch_params: List[str]
+    n: int
+    p: int
+    m: int
+    l: int
+    q: List[int]
+    mt: int
+    nk: int
+    npb: int
+    xe: np.ndarray
+    Ae: np.ndarray
+    Ge: np.ndarray
+    A_eq: sp.csc_matrix
+    G_eq: sp.csc_matrix
+    perm: np.ndarray                 # position -> k
+    pos_level: np.ndarray
+    n_wide_levels: int
+    t0: int                          # first tail position
+    tables: Dict[str, np.ndarray] = field(default_factory=dict)
+    defines: Dict[str, int] = field(default_factory=dict)
+    level_ranges: Dict[str, List[int]] = field(default_factory=dict)
+    smem_blob: bytes = b''
+    gmem_blob: bytes = b''
+    prim_idx: Optional[np.ndarray] = None
+    dual_idx: Optional[np.ndarray] = None
+    stats: Dict[str, float] = field(default_factory=dict)
+
+    @property
+    def nt(self):
+        return self.nk - self.t0
+
+
+def stretch_layout(l: int, q: List[int]):
+    """z index -> stretched index; per cone (z offset, stretched offset, size)."""
+    m = l + sum(q)
+    zmap = np.zeros(m, dtype=np.int64); zmap[:l] = np.arange(l)
+    blocks = []
+    o, so = l, l
+    for d in q:
+        zmap[o:o + d] = so + np.arange(d)
+        blocks.append((o, so, d)); o += d; so += d + 2
+    return zmap, blocks, m + 2 * len(q)
+
+
+def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
+                      theta: Optional[np.ndarray] = None) -> SOCPSetup:
+    if fam.solver_type != 'conic':
+        raise ValueError('IPM-CUDA handles the conic canonical form only')
+    if batch_params is None:
+        batch_params = [p.name for p in fam.params if not (fam.changes('A', [p.name]) or fam.changes('G', [p.name]))]
+    for name in batch_params:
+        fam.param(name)
+        if fam.changes('A', [name]) or fam.changes('G', [name]):
+            raise ValueError(f'parameter {name} enters a canonical matrix; per-instance matrix updates are not generated yet')
+    theta = fam.theta_default() if theta is None else np.asarray(theta, dtype=float)
+    n, p, m = fam.n_var, fam.n_eq, fam.n_ineq
+    l, q = int(fam.cone_dims.get('l', 0)), [int(d) for d in fam.cone_dims.get('q', [])]
+    assert l + sum(q) == m
+    nsoc = len(q)
+    A = fam.canon_matrix('A', theta) if p else sp.csc_matrix((0, n))
+    G = fam.canon_matrix('G', theta)
+    A_eq, G_eq, xe, Ae, Ge = ecos_equilibrate(A, G, l, q)
+    zmap, blocks, mt = stretch_layout(l, q)
+    nk = n + p + mt
+    zoff = n + p
+    # ---- M = [A ; G stretched] in k-space rows
+    Ac, Gc = A_eq.tocoo(), G_eq.tocoo()
+    rows = np.r_[n + Ac.row, zoff + zmap[Gc.row]].astype(np.int64)
+    cols = np.r_[Ac.col, Gc.col].astype(np.int64)
+    vals = np.r_[Ac.data, Gc.data]
+    order = np.lexsort((cols, rows))
+    mr_t, mr_s, ag_val = rows[order], cols[order], vals[order]
+    # ---- KKT pattern (k-space), ordering, levels
+    pr = np.r_[np.arange(nk), mr_t, mr_s]; pc = np.r_[np.arange(nk), mr_s, mr_t]
+    for o, so, d in blocks:
+        iv, iu = zoff + so + d, zoff + so + d + 1
+        rr = zoff + so + np.arange(d)
+        pr = np.r_[pr, rr[1:], np.full(d - 1, iv), rr, np.full(d, iu)]
+        pc = np.r_[pc, np.full(d - 1, iv), rr[1:], np.full(d, iu), rr]
+    pat = sp.csr_matrix((np.ones(len(pr)), (pr, pc)), shape=(nk, nk))
+    md = _kkt.minimum_degree_order(pat)
+    struct, parent = _kkt._symbolic(pat, md)
+    reseq, _ = _kkt.level_resequence(struct, parent)
+    perm = md[reseq]
+    struct, parent = _kkt._symbolic(pat, perm)
+    _, level = _kkt.level_resequence(struct, parent)
+    assert np.all(np.diff(level) >= 0)
+    # ---- tail: the longest suffix of whole levels with at most MAX_TAIL columns
+    t0 = nk
+    for lev in range(int(level.max()), -1, -1):
+        first = int(np.searchsorted(level, lev, side='left'))
+        if nk - first > MAX_TAIL:
+            break
+        t0 = first
+    nt = nk - t0
+    nlw = int(level[t0 - 1]) + 1 if t0 > 0 else 0
+    inv = np.empty(nk, dtype=np.int64); inv[perm] = np.arange(nk)
+    # ---- slots
+    slot_of = {}
+    bw_t, bw_s = [], []
+    for j in range(t0):
+        for i in struct[j]:
+            slot_of[(int(i), j)] = len(bw_t)
+            bw_t.append(perm[j]); bw_s.append(perm[int(i)])
+    NW = len(bw_t)
+    DG0 = NW
+    TT0 = NW + nk
+    NS = TT0 + nt * nt
+
+    def sidx(pi, pj):                   # positions, pi > pj
+        if pj < t0:
+            return slot_of[(pi, pj)]
+        return TT0 + (pi - t0) * nt + (pj - t0)
+
+    def kslot(kr, kc):
+        if kr == kc:
+            return DG0 + kr
+        pi, pj = inv[kr], inv[kc]
+        return sidx(max(pi, pj), min(pi, pj))
+    # ---- base image of the constant entries
+    Sbase = np.zeros(NS)
+    Sbase[DG0:DG0 + n] = DELTASTAT
+    Sbase[DG0 + n:DG0 + n + p] = -DELTASTAT
+    for r, c_, v in zip(mr_t, mr_s, ag_val):
+        Sbase[kslot(int(r), int(c_))] += v
+    socv, socu = [], []
+    for o, so, d in blocks:
+        iv, iu = zoff + so + d, zoff + so + d + 1
+        socv += [kslot(zoff + so + r, iv) for r in range(1, d)]
+        socu += [kslot(zoff + so + r, iu) for r in range(d)]
+    # ---- factor operations, pull form, by level of the target's column
+    slot_col_start = np.zeros(t0 + 1, dtype=np.int64)
+    for j in range(t0):
+        slot_col_start[j + 1] = slot_col_start[j] + len(struct[j])
+    ops = []
+    for j in range(t0):
+        R = [int(i) for i in struct[j]]
+        base = int(slot_col_start[j])
+        kj = int(perm[j])
+        for bi, kpos in enumerate(R):
+            lvl = int(level[kpos]) if kpos < t0 else nlw
+            for ai in range(bi, len(R)):
+                ipos = R[ai]
+                tgt = DG0 + int(perm[kpos]) if ai == bi else sidx(ipos, kpos)
+                ops.append((lvl, tgt, base + ai, base + bi, kj))
+    ops.sort()
+    ops = np.array(ops, dtype=np.int64).reshape(-1, 5)
+    op_lo = [int(np.searchsorted(ops[:, 0], lv, side='left')) for lv in range(nlw + 2)]
+    # ---- forward solve entries by (level of row, row)
+    fw = []
+    for (i, j), s in slot_of.items():
+        lvl = int(level[i]) if i < t0 else nlw
+        fw.append((lvl, int(perm[i]), int(perm[j]), s))
+    fw.sort()
+    fw = np.array(fw, dtype=np.int64).reshape(-1, 4)
+    fw_lo = [int(np.searchsorted(fw[:, 0], lv, side='left')) for lv in range(nlw + 2)]
+    bw_lo = [int(slot_col_start[np.searchsorted(level[:t0], lv, side='left')]) for lv in range(nlw + 1)]
+    lev_lo = [int(np.searchsorted(level[:t0], lv, side='left')) for lv in range(nlw + 1)]
+    # ---- affine maps of the per-instance vectors, equilibrated, in k-space: cbh = base + Mb theta_b
+    bcols = fam.param_columns(batch_params) if batch_params else np.zeros(0, dtype=int)
+    npb = len(bcols)
+    theta0 = theta.copy(); theta0[bcols] = 0.0
+    scale_k = np.ones(nk); scale_k[:n] = 1.0 / xe
+    if p:
+        scale_k[n:zoff] = 1.0 / Ae
+    scale_k[zoff + zmap] = 1.0 / Ge
+    krow = {'c': np.arange(n), 'b': n + np.arange(p), 'h': zoff + zmap}
+    base = np.zeros(nk)
+    mt_, mp_, mv_ = [], [], []
+    for pid in ('c', 'b', 'h'):
+        Mp = fam.maps.get(pid)
+        if Mp is None or Mp.shape[0] == 0:
+            continue
+        base[krow[pid]] = np.asarray(Mp @ theta0).ravel() * scale_k[krow[pid]]
+        if npb:
+            Mb = sp.coo_matrix(Mp[:, bcols])
+            mt_ += list(krow[pid][Mb.row]); mp_ += list(Mb.col); mv_ += list(Mb.data * scale_k[krow[pid]][Mb.row])
+    if 'd' in fam.maps and npb and fam.maps['d'][:, bcols].nnz:
+        raise ValueError('objective offset d depending on a batched parameter is not generated yet')
+    d_const = float(np.asarray(fam.maps['d'] @ theta).ravel()[0]) if 'd' in fam.maps else 0.0
+    # ---- output scaling (backscale, ecos/src/ecos.c:1051-1070) and retrieval lists
+    unscale = scale_k.copy()                    # x / xe, y / Ae, z / Ge  (then / tau)
+    prim_idx = np.concatenate([v.indices for v in fam.variables]) if fam.variables else np.zeros(0, int)
+    dual_k = []
+    for dv in fam.duals:
+        dual_k.append(n + dv.indices if dv.vec == 'y' else zoff + zmap[dv.indices])
+    dual_idx = np.concatenate(dual_k) if dual_k else np.zeros(0, int)
+    T = dict(mr_t=mr_t, mr_s=mr_s, ag_val=ag_val, fw_t=fw[:, 1], fw_s=fw[:, 2], fw_slot=fw[:, 3],
+             bw_t=np.array(bw_t, dtype=np.int64), bw_s=np.array(bw_s, dtype=np.int64), socv=np.array(socv, dtype=np.int64),
+             socu=np.array(socu, dtype=np.int64), Sbase=Sbase, ops=ops[:, 1:], tail_k=perm[t0:], cbh_base=base,
+             map_t=np.array(mt_, dtype=np.int64), map_p=np.array(mp_, dtype=np.int64), map_v=np.array(mv_, dtype=float),
+             unscale=unscale, prim_idx=prim_idx, dual_idx=dual_idx, perm=perm)
+    LR = dict(op_lo=op_lo, fw_lo=fw_lo, bw_lo=bw_lo, lev_lo=lev_lo)
+    D = dict(N=n, P=p, M=m, L=l, NSOC=nsoc, MT=mt, NK=nk, ZOFF=zoff, NW=NW, DG0=DG0, TT0=TT0, NS=NS, NT=nt, NLW=nlw,
+             NNZM=len(ag_val), NOPS=len(ops), NFW=len(fw), NPB=npb, NMAP=len(mv_), NPRIM=len(prim_idx),
+             NDUAL=len(dual_idx), QTOT=sum(d - 1 for d in q), IS_MAX=int(fam.is_maximization), NNZA=int(A_eq.nnz))
+    st = SOCPSetup(family=fam, batch_params=list(batch_params), n=n, p=p, m=m, l=l, q=q, mt=mt, nk=nk, npb=npb, xe=xe,
+                   Ae=Ae, Ge=Ge, A_eq=A_eq, G_eq=G_eq, perm=perm, pos_level=level, n_wide_levels=nlw, t0=t0, tables=T,
+                   defines=D, level_ranges=LR, prim_idx=prim_idx, dual_idx=dual_idx)
+    st.stats = dict(nnz_L=NW + nt * (nt - 1) // 2, n_levels=int(level.max()) + 1, n_wide_levels=nlw, tail=nt,
+                    factor_ops=len(ops), d_const=d_const)
+    _pack(st, d_const)
+    return st
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def _pack(st: SOCPSetup, d_const: float):
+    """Two byte strings + the offsets the kernel needs (emitted as #defines into the family header):
+       smem blob  = [f64: ag_val] [u16: mr_t mr_s fw_t fw_s fw_slot bw_t bw_s socv socu tail_k]   (staged per CTA)
+       gmem blob  = [f64: Sbase cbh_base unscale map_v] [i32: map_t map_p prim_idx dual_idx] [u16 x4: ops]"""
+    T, D = st.tables, st.defines
+
+    def cat(parts, dtype, align=8):
+        offs, chunks, pos = {}, [], 0
+        for name, arr in parts:
+            a = np.ascontiguousarray(np.asarray(arr).astype(dtype))
+            offs[name] = pos
+            chunks.append(a); pos += a.size
+        return offs, (np.concatenate(chunks) if chunks else np.zeros(0, dtype))
+    # shared-memory blob
+    fo, f64 = cat([('ag_val', T['ag_val'])], np.float64)
+    names16 = ['mr_t', 'mr_s', 'fw_t', 'fw_s', 'fw_slot', 'bw_t', 'bw_s', 'socv', 'socu', 'tail_k', 'perm']
+    for nm in names16:
+        a = T[nm]
+        assert a.size == 0 or (a.min() >= 0 and a.max() < 65536), nm
+    ho, u16 = cat([(nm, T[nm]) for nm in names16], np.uint16)
+    sm = f64.tobytes()
+    u16_off = len(sm)
+    sm += u16.tobytes()
+    sm += b'\0' * ((-len(sm)) % 16)
+    D['SB_BYTES'] = len(sm); D['SB_U16_OFF'] = u16_off
+    for nm in names16:
+        D['H_' + nm.upper()] = ho[nm]
+    # global blob
+    go, g64 = cat([('Sbase', T['Sbase']), ('cbh_base', T['cbh_base']), ('unscale', T['unscale']), ('map_v', T['map_v'])], np.float64)
+    io, i32 = cat([('map_t', T['map_t']), ('map_p', T['map_p']), ('prim_idx', T['prim_idx']), ('dual_idx', T['dual_idx'])], np.int32)
+    ops = np.ascontiguousarray(T['ops'].astype(np.uint16))
+    assert T['ops'].size == 0 or T['ops'].max() < 65536
+    gm = g64.tobytes()
+    i32_off = len(gm)
+    gm += i32.tobytes()
+    gm += b'\0' * ((-len(gm)) % 8)
+    ops_off = len(gm)
+    gm += ops.tobytes()
+    gm += b'\0' * ((-len(gm)) % 16)
+    D['GB_BYTES'] = len(gm); D['GB_I32_OFF'] = i32_off; D['GB_OPS_OFF'] = ops_off
+    for nm, o in go.items():
+        D['G_' + nm.upper()] = o
+    for nm, o in io.items():
+        D['GI_' + nm.upper()] = o
+    st.smem_blob, st.gmem_blob = sm, gm
+    st.stats['smem_blob_bytes'] = len(sm); st.stats['gmem_blob_bytes'] = len(gm)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# numpy emulation of the table-driven factorisation and solve (used by the CPU tests to pin the tables)
+def fill_slots(st: SOCPSetup, zdiag: np.ndarray, socv_vals=None, socu_vals=None) -> np.ndarray:
+    """S image for a KKT whose (3,3) block has diagonal `zdiag` (length mt, k-space order) and the given v / u columns."""
+    T, D = st.tables, st.defines
+    S = T['Sbase'].copy()
+    S[D['DG0'] + D['ZOFF']:D['DG0'] + D['NK']] += zdiag
+    if socv_vals is not None and len(T['socv']):
+        S[T['socv']] = socv_vals
+    if socu_vals is not None and len(T['socu']):
+        S[T['socu']] = socu_vals
+    return S
+
+
+def emulate_factor(st: SOCPSetup, S: np.ndarray, sign: np.ndarray, eps=1e-13, delta=2e-7):
+    T, D, LR = st.tables, st.defines, st.level_ranges
+    S = S.copy(); Dinv = np.zeros(D['NK'])
+    nlw, nt, t0 = D['NLW'], D['NT'], st.t0
+    ops = T['ops']
+
+    def pivots(ks):
+        d = S[D['DG0'] + ks]
+        d = np.where(sign[ks] * d <= eps, sign[ks] * delta, d)
+        Dinv[ks] = 1.0 / d
+    for lv in range(nlw + 1):
+        lo, hi = LR['op_lo'][lv], LR['op_lo'][lv + 1]
+        o = ops[lo:hi]
+        if len(o):
+            np.subtract.at(S, o[:, 0], S[o[:, 1]] * S[o[:, 2]] * Dinv[o[:, 3]])
+        if lv < nlw:
+            pivots(st.perm[LR['lev_lo'][lv]:LR['lev_lo'][lv + 1]])
+    tk = T['tail_k']
+    for j in range(nt):
+        pivots(tk[j:j + 1])
+        dj = Dinv[tk[j]]
+        for i in range(j + 1, nt):
+            sij = S[D['TT0'] + i * nt + j]
+            for k in range(j + 1, i):
+                S[D['TT0'] + i * nt + k] -= sij * S[D['TT0'] + k * nt + j] * dj
+            S[D['DG0'] + tk[i]] -= sij * sij * dj
+    return S, Dinv
+
+
+def emulate_solve(st: SOCPSetup, S: np.ndarray, Dinv: np.ndarray, rhs: np.ndarray) -> np.ndarray:
+    T, D, LR = st.tables, st.defines, st.level_ranges
+    u = rhs.astype(float).copy()
+    nlw, nt = D['NLW'], D['NT']
+    for lv in range(1, nlw + 1):
+        lo, hi = LR['fw_lo'][lv], LR['fw_lo'][lv + 1]
+        t, s, sl = T['fw_t'][lo:hi], T['fw_s'][lo:hi], T['fw_slot'][lo:hi]
+        np.subtract.at(u, t, S[sl] * Dinv[s] * u[s])
+    tk = T['tail_k']
+    for j in range(nt):
+        for i in range(j + 1, nt):
+            u[tk[i]] -= S[D['TT0'] + i * nt + j] * Dinv[tk[j]] * u[tk[j]]
+    x = u * Dinv
+    for j in range(nt - 1, -1, -1):
+        for i in range(j + 1, nt):
+            x[tk[j]] -= S[D['TT0'] + i * nt + j] * Dinv[tk[j]] * x[tk[i]]
+    for lv in range(nlw - 1, -1, -1):
+        lo, hi = LR['bw_lo'][lv], LR['bw_lo'][lv + 1]
+        t, s = T['bw_t'][lo:hi], T['bw_s'][lo:hi]
+        np.subtract.at(x, t, S[lo:hi] * Dinv[t] * x[s])
+    return x

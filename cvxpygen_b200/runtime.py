@@ -338,6 +338,118 @@ class Module:
         return SimpleNamespace(cpg_prim=prim, cpg_dual=dual, cpg_info=info)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# IPM-CUDA libraries (SOCP families): include/cpg_b200_socp.h
+ECOS_STATUS_STRINGS = {0: 'optimal', 1: 'primal infeasible', 2: 'dual infeasible', 10: 'optimal inaccurate',
+                       11: 'primal infeasible inaccurate', 12: 'dual infeasible inaccurate', -1: 'maximum iterations reached',
+                       -2: 'numerical problems (unreliable search direction)', -3: 'numerical problems (slacks or multipliers outside cone)',
+                       -4: 'interrupted by signal or CTRL-C', -7: 'unknown problem in solver'}
+
+
+class CpgB200SocpSettings(C.Structure):
+    _fields_ = [('maxit', C.c_int), ('pad_', C.c_int), ('feastol', C.c_double), ('abstol', C.c_double),
+                ('reltol', C.c_double), ('feastol_inacc', C.c_double), ('abstol_inacc', C.c_double),
+                ('reltol_inacc', C.c_double)]
+
+
+class CpgB200SocpDims(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ('n_var', 'n_eq', 'n_ineq', 'n_lp', 'n_soc', 'n_param', 'n_prim', 'n_dual',
+                                       'threads_per_cta', 'smem_bytes')]
+
+
+class SocpModule(Module):
+    """One loaded IPM-CUDA solver library bound to one CUDA device."""
+
+    def __init__(self, code_dir, device=0):
+        self.code_dir = os.path.abspath(code_dir)
+        with open(os.path.join(self.code_dir, 'cpg_meta.json')) as f:
+            self.meta = json.load(f)
+        self.prefix = self.meta['prefix']
+        path = os.path.join(self.code_dir, 'libcpg_b200.so')
+        if not os.path.exists(path):
+            raise RuntimeError(f'{path} is missing: run cvxpygen_b200.codegen_ipm.compile_ipm_code (nvcc, sm_100a) first; '
+                               'there is no CPU fallback')
+        self.lib = C.CDLL(path)
+        self._fn('cpg_b200_last_error').restype = C.c_char_p
+        self.dims = CpgB200SocpDims()
+        self._check(self._fn('cpg_socp_dims')(C.byref(self.dims)))
+        self.settings = CpgB200SocpSettings()
+        self.set_solver_default_settings()
+        self.device = device
+        self._initialised = False
+
+    def set_solver_default_settings(self):
+        self._fn('cpg_socp_default_settings')(C.byref(self.settings))
+
+    def set_solver_setting(self, name, value):
+        name = {'max_iters': 'maxit'}.get(name, name)
+        if name == 'pad_' or name not in dict(CpgB200SocpSettings._fields_):
+            raise AttributeError(f'Solver setting "{name}" not available.')
+        setattr(self.settings, name, value)
+
+    def update_shared_params(self, values):
+        raise NotImplementedError('shared-parameter updates are not generated for IPM-CUDA yet: regenerate the code')
+
+    def solve_batch(self, params, return_canonical=False, **settings):
+        self.init()
+        for k, v in settings.items():
+            self.set_solver_setting(k, v)
+        P = params if isinstance(params, np.ndarray) else self.pack_params(params)
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        B = P.shape[0]
+        d = self.dims
+        prim = np.empty((B, d.n_prim)); dual = np.empty((B, d.n_dual))
+        x = np.empty((B, d.n_var)) if return_canonical else None
+        y = np.empty((B, d.n_eq)) if return_canonical else None
+        z = np.empty((B, d.n_ineq)) if return_canonical else None
+        s = np.empty((B, d.n_ineq)) if return_canonical else None
+        obj = np.empty(B); pri = np.empty(B); dua = np.empty(B)
+        it = np.empty(B, dtype=np.int32); st = np.empty(B, dtype=np.int32)
+
+        def p(a, t=C.c_double):
+            return None if a is None else a.ctypes.data_as(C.POINTER(t))
+        t0 = time.perf_counter()
+        self._check(self._fn('cpg_socp_solve_batch_host')(C.c_int(B), p(P), p(prim), p(dual), p(x), p(y), p(z), p(s), p(obj),
+                                                          p(it, C.c_int), p(st, C.c_int), p(pri), p(dua), C.byref(self.settings)))
+        t1 = time.perf_counter()
+        pr, du = self.unpack(prim, dual)
+        info = SimpleNamespace(obj_val=obj, iter=it, status=st, pri_res=pri, dua_res=dua, time=t1 - t0)
+        return SimpleNamespace(cpg_prim=pr, cpg_dual=du, cpg_info=info, prim=prim, dual=dual, sol_x=x, sol_y=y, sol_z=z, sol_s=s)
+
+    def solve_batch_device(self, params, out=None, return_canonical=False, **_):
+        import torch
+        self.init()
+        assert params.is_cuda and params.dtype == torch.float64 and params.is_contiguous()
+        B = params.shape[0]
+        d = self.dims
+        dev = params.device
+        if out is None:
+            mk = lambda *shape, dtype=torch.float64: torch.empty(shape, dtype=dtype, device=dev)
+            out = SimpleNamespace(prim=mk(B, d.n_prim), dual=mk(B, d.n_dual),
+                                  sol_x=mk(B, d.n_var) if return_canonical else None, sol_y=mk(B, d.n_eq) if return_canonical else None,
+                                  sol_z=mk(B, d.n_ineq) if return_canonical else None, sol_s=mk(B, d.n_ineq) if return_canonical else None,
+                                  obj_val=mk(B), pri_res=mk(B), dua_res=mk(B), iter=mk(B, dtype=torch.int32), status=mk(B, dtype=torch.int32))
+        ptr = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._check(self._fn('cpg_socp_solve_batch_device')(C.c_int(B), ptr(params), ptr(out.prim), ptr(out.dual), ptr(out.sol_x),
+                                                            ptr(out.sol_y), ptr(out.sol_z), ptr(out.sol_s), ptr(out.obj_val),
+                                                            ptr(out.iter), ptr(out.status), ptr(out.pri_res), ptr(out.dua_res),
+                                                            C.byref(self.settings), C.c_void_p(stream)))
+        return out
+
+    def solve(self, upd, par):
+        """b3: cpg_module.solve(upd, par) -> result, a batch of one (status is ECOS's integer exit flag, like the
+        reference's ECOS path: status_is_int, cvxpygen/solvers/ecos.py:29)."""
+        vals = {p['name']: np.asarray(getattr(par, p['name']), dtype=float) for p in self.meta['params'] if p['batched']}
+        r = self.solve_batch(vals)
+        prim = SimpleNamespace(**{k: (v[0].flatten(order='F').tolist() if v[0].size > 1 else float(v[0].ravel()[0]))
+                                  for k, v in r.cpg_prim.items()})
+        dual = SimpleNamespace(**{k: (v[0].tolist() if v[0].size > 1 else float(v[0].ravel()[0])) for k, v in r.cpg_dual.items()})
+        info = SimpleNamespace(obj_val=float(r.cpg_info.obj_val[0]), iter=int(r.cpg_info.iter[0]), status=int(r.cpg_info.status[0]),
+                               pri_res=float(r.cpg_info.pri_res[0]), dua_res=float(r.cpg_info.dua_res[0]), time=r.cpg_info.time)
+        return SimpleNamespace(cpg_prim=prim, cpg_dual=dual, cpg_info=info)
+
+
 _modules = {}
 
 
@@ -345,5 +457,7 @@ def load(code_dir=None, device=0) -> Module:
     code_dir = os.path.dirname(os.path.abspath(__file__)) if code_dir is None else os.path.abspath(code_dir)
     key = (code_dir, device)
     if key not in _modules:
-        _modules[key] = Module(code_dir, device)
+        with open(os.path.join(code_dir, 'cpg_meta.json')) as f:
+            solver = json.load(f).get('solver', 'ADMM-CUDA')
+        _modules[key] = (SocpModule if solver == 'IPM-CUDA' else Module)(code_dir, device)
     return _modules[key]

@@ -18,6 +18,7 @@ STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
     'nonneg_LS_3_2': (lambda: families.nonneg_ls(3, 2), ['b']),             # BASELINE config 1 (README example)
     'random_qp_20_5_15': (lambda: families.random_qp(20, 5, 15), ['q', 'b', 'h']),  # unstructured sparsity, q/l/u all batched
     'box_qp_6_8': (lambda: families.box_qp(6, 8), ['q', 'l', 'u']),          # corner cases: type changes, infeasibility
+    'portfolio_socp_100_10': (lambda: families.portfolio_socp(100, 10), ['a', 'w_prev']),   # BASELINE config 3 (IPM-CUDA)
 }
 
 
@@ -31,7 +32,9 @@ def build(name: str, force: bool = False, verbose: bool = False) -> str:
         return d
     fam_fn, batch = STANDARD[name]
     os.makedirs(GENERATED_DIR, exist_ok=True)
-    generate_code(fam_fn(), code_dir=d, solver='ADMM-CUDA', batch_params=batch, prefix='', wrapper=True, verbose=verbose)
+    fam = fam_fn()
+    solver = 'IPM-CUDA' if fam.solver_type == 'conic' else 'ADMM-CUDA'
+    generate_code(fam, code_dir=d, solver=solver, batch_params=batch, prefix='', wrapper=True, verbose=verbose)
     return d
 
 

@@ -1,0 +1,282 @@
+"""IPM-CUDA backend (BASELINE config 3: portfolio SOCP through the Mehrotra interior-point kernel).
+
+CPU tests: the offline tables (equilibration, table-driven LDL' and triangular solves), the phase logic of the kernel
+compiled as host C++ (tests/emu, every barrier-separated phase run thread after thread) against the golden vectors of
+the compiled reference, the generated directory and the exported C ABI.
+GPU tests (-m gpu): the CUDA kernel through the C ABI against the golden vectors and against the compiled reference
+on fresh seeded batches, bit-level properties at full batch size."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from cvxpygen_b200 import families, standard, codegen_ipm, runtime
+from cvxpygen_b200.offline import socp_setup as ss
+from helpers import GOLDEN
+from oracle import ref_ecos
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NAME = 'portfolio_socp_100_10'
+# parity bar of the north star: 1e-5 relative on primal / dual variables.  What is actually reached against the compiled
+# reference is ~1e-9 on x, y, s and ~1e-7 on z (dual degenerate epigraph rows amplify rounding differences).
+RTOL_PRIMAL, RTOL_DUAL = 1e-7, 1e-5
+
+
+@pytest.fixture(scope='module')
+def setup():
+    return ss.setup_socp_family(families.portfolio_socp())
+
+
+def _golden():
+    return np.load(os.path.join(GOLDEN, 'socp_portfolio_100_10.npz'))
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_equilibration_matches_reference_restatement(setup):
+    """cvxpygen_b200.offline.socp_setup.ecos_equilibrate against the oracle's restatement of ecos/src/equil.c."""
+    from oracle.ipm_numpy import ruiz_equilibrate
+    fam = setup.family
+    A, G, xe, Ae, Ge = ruiz_equilibrate(fam.canon_matrix('A'), fam.canon_matrix('G'), setup.l, setup.q)
+    assert np.array_equal(xe, setup.xe) and np.array_equal(Ae, setup.Ae) and np.array_equal(Ge, setup.Ge)
+    assert np.array_equal(A.toarray(), setup.A_eq.toarray()) and np.array_equal(G.toarray(), setup.G_eq.toarray())
+
+
+def test_structure_of_the_schedule(setup):
+    D = setup.defines
+    assert (D['N'], D['P'], D['M'], D['L'], D['NSOC'], D['NK']) == (512, 111, 715, 601, 2, 1342)
+    assert D['NT'] <= ss.MAX_TAIL and D['NLW'] >= 1
+    assert np.all(np.diff(setup.pos_level) >= 0)
+    # every wide level's columns are mutually independent: no L entry inside a level
+    T = setup.tables
+    inv = np.empty(D['NK'], int); inv[T['perm']] = np.arange(D['NK'])
+    lev_of_k = setup.pos_level[inv]
+    assert np.all(lev_of_k[T['bw_s']] > lev_of_k[T['bw_t']])
+
+
+def test_table_driven_factor_and_solve_match_dense_algebra(setup):
+    D, T = setup.defines, setup.tables
+    rs = np.random.RandomState(0)
+    nk, zoff, mt = D['NK'], D['ZOFF'], D['MT']
+    _, blocks, _ = ss.stretch_layout(setup.l, setup.q)
+    zd = -(0.5 + rs.rand(mt))
+    sign = np.r_[np.ones(setup.n), -np.ones(setup.p), -np.ones(mt)]
+    for o, so, d in blocks:
+        zd[so + d + 1] = 0.7; sign[zoff + so + d + 1] = 1
+    sv, su = 0.1 * rs.randn(len(T['socv'])), 0.1 * rs.randn(len(T['socu']))
+    K = np.zeros((nk, nk))
+    K[np.arange(setup.n), np.arange(setup.n)] = ss.DELTASTAT
+    K[setup.n + np.arange(setup.p), setup.n + np.arange(setup.p)] = -ss.DELTASTAT
+    for r, c, v in zip(T['mr_t'], T['mr_s'], T['ag_val']):
+        K[r, c] += v; K[c, r] += v
+    K[zoff + np.arange(mt), zoff + np.arange(mt)] = zd
+    e = f = 0
+    for o, so, d in blocks:
+        iv, iu = zoff + so + d, zoff + so + d + 1
+        for r in range(1, d):
+            K[zoff + so + r, iv] = K[iv, zoff + so + r] = sv[e]; e += 1
+        for r in range(d):
+            K[zoff + so + r, iu] = K[iu, zoff + so + r] = su[f]; f += 1
+    S, Dinv = ss.emulate_factor(setup, ss.fill_slots(setup, zd, sv, su), sign)
+    b = rs.randn(nk)
+    x = ss.emulate_solve(setup, S, Dinv, b)
+    assert np.abs(K @ x - b).max() < 1e-6 * np.abs(b).max()         # static regularisation 7e-8 limits the accuracy
+    assert _rel(x, np.linalg.solve(K, b)) < 1e-7
+
+
+def test_exact_restatement_reproduces_the_compiled_reference():
+    """oracle/ipm_numpy.EcosExact (equilibration, stretched KKT, regularisation, refinement, safeguards) against the
+    golden vectors of the compiled reference: same iteration counts, x/y/s to 1e-9, z to 1e-6."""
+    from oracle.ipm_numpy import EcosExact
+    g = _golden()
+    fam = families.portfolio_socp()
+    c0, b0, h = fam.canon_data('c'), fam.canon_data('b'), fam.canon_data('h')
+    E = EcosExact(fam.canon_matrix('A'), fam.canon_matrix('G'), 601, [12, 102])
+    for k in (0, 3):
+        c = c0.copy(); c[:100] = -g['param_a'][k]
+        b = b0.copy(); b[11:111] = -g['param_w_prev'][k]
+        r = E.solve(c, b, h)
+        assert r['exitflag'] == 0 and r['iter'] == g['iter'][k]
+        assert _rel(r['x'], g['x'][k]) < 1e-8 and _rel(r['y'], g['y'][k]) < 1e-8 and _rel(r['s'], g['s'][k]) < 1e-8
+        assert _rel(r['z'], g['z'][k]) < 1e-6
+
+
+@pytest.fixture(scope='module')
+def emu(setup, tmp_path_factory):
+    d = str(tmp_path_factory.mktemp('ipm_emu'))
+    with open(os.path.join(d, 'cpg_ipm_family.h'), 'w') as f:
+        f.write(codegen_ipm.family_header(setup))
+    out = os.path.join(d, 'libipm_emu.so')
+    r = subprocess.run(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-I', d, '-I', os.path.join(ROOT, 'cvxpygen_b200', 'csrc'),
+                        os.path.join(ROOT, 'tests', 'emu', 'ipm_emu.cpp'), '-o', out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return C.CDLL(out)
+
+
+def _emu_solve(lib, setup, params, maxit=100):
+    D = setup.defines
+    B = params.shape[0]
+    out = dict(prim=np.zeros((B, D['NPRIM'])), dual=np.zeros((B, D['NDUAL'])), x=np.zeros((B, D['N'])), y=np.zeros((B, D['P'])),
+               z=np.zeros((B, D['M'])), s=np.zeros((B, D['M'])), obj=np.zeros(B), iter=np.zeros(B, np.int32),
+               status=np.zeros(B, np.int32), pres=np.zeros(B), dres=np.zeros(B))
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    lib.ipm_emu_solve(setup.smem_blob, setup.gmem_blob, B, P(params), *[P(out[k]) for k in
+                      ('prim', 'dual', 'x', 'y', 'z', 's', 'obj', 'iter', 'status', 'pres', 'dres')], maxit)
+    return out
+
+
+def test_kernel_phase_logic_on_host_matches_golden(emu, setup):
+    """The kernel source compiled as host C++ (phases serialised) against the compiled reference's golden vectors."""
+    g = _golden()
+    B = 8
+    out = _emu_solve(emu, setup, np.c_[g['param_a'][:B], g['param_w_prev'][:B]])
+    assert np.array_equal(out['iter'], g['iter'][:B]) and (out['status'] == 0).all()
+    for k in range(B):
+        assert _rel(out['x'][k], g['x'][k]) < RTOL_PRIMAL and _rel(out['y'][k], g['y'][k]) < RTOL_PRIMAL
+        assert _rel(out['s'][k], g['s'][k]) < RTOL_PRIMAL and _rel(out['z'][k], g['z'][k]) < RTOL_DUAL
+    assert np.allclose(out['obj'], -g['pcost'][:B], rtol=0, atol=1e-9)            # maximisation: obj_val = -pcost
+    fam = setup.family
+    assert np.array_equal(out['prim'][:, :100], out['x'][:, fam.variables[0].indices])
+    zl1 = fam.duals[2].indices[0]
+    assert np.array_equal(out['dual'][:, 11], out['z'][:, zl1])
+
+
+def test_kernel_phase_logic_maxit_and_best_iterate(emu, setup):
+    """maxit = 5: ECOS returns the better of current / best iterate with exit flag -1 (or an inaccurate flag)."""
+    g = _golden()
+    out = _emu_solve(emu, setup, np.c_[g['param_a'][:2], g['param_w_prev'][:2]], maxit=5)
+    assert (out['iter'] == 5).all() and np.isin(out['status'], (-1, 10)).all()
+    if ref_ecos.available():
+        fam = setup.family
+        c0, b0 = fam.canon_data('c'), fam.canon_data('b')
+        r = ref_ecos.RefECOS(c0, fam.canon_matrix('A'), b0, fam.canon_matrix('G'), fam.canon_data('h'), 601, [12, 102], maxit=5)
+        Cb = np.tile(c0, (2, 1)); Cb[:, :100] = -g['param_a'][:2]
+        Bb = np.tile(b0, (2, 1)); Bb[:, 11:111] = -g['param_w_prev'][:2]
+        ref = r.solve_batch(c=Cb, b=Bb)
+        assert np.array_equal(ref['exitflag'], out['status']) and np.array_equal(ref['iter'], out['iter'])
+        assert _rel(out['x'], ref['x']) < 1e-7 and _rel(out['z'], ref['z']) < 1e-6
+
+
+def test_generated_directory_and_c_abi():
+    d = standard.build(NAME)
+    for f in ('cpg_solver.py', 'cpg_module.py', 'cpg_meta.json', 'libcpg_b200.so', 'c/include/cpg_b200_socp.h',
+              'c/include/cpg_ipm_family.h', 'c/solver_code/ipm_kernel.cuh', 'c/solver_code/cpg_b200_ipm_module.cu',
+              'c/src/cpg_ipm_blob.c'):
+        assert os.path.exists(os.path.join(d, f)), f
+    hdr = open(os.path.join(ROOT, 'include', 'cpg_b200_socp.h')).read()
+    declared = set(re.findall(r'CPG_B200_FN\((\w+)\)\s*\(', hdr))
+    assert {'cpg_b200_init', 'cpg_socp_solve_batch_device', 'cpg_socp_solve_batch_host', 'cpg_socp_dims'} <= declared
+    lib = C.CDLL(os.path.join(d, 'libcpg_b200.so'))
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    m = runtime.load(d)
+    assert isinstance(m, runtime.SocpModule)
+    assert (m.dims.n_var, m.dims.n_eq, m.dims.n_ineq, m.dims.n_lp, m.dims.n_soc) == (512, 111, 715, 601, 2)
+    assert (m.dims.n_param, m.dims.n_prim, m.dims.n_dual) == (200, 210, 112)
+    assert m.dims.smem_bytes <= 232448 - 1024
+    assert (m.settings.maxit, m.settings.feastol, m.settings.reltol_inacc) == (100, 1e-8, 5e-5)
+    with pytest.raises(AttributeError):
+        m.set_solver_setting('eps_abs', 1e-3)
+    with pytest.raises(AttributeError):
+        m.pack_params({'nope': np.zeros(3)})
+
+
+def test_wrong_solver_for_family_is_rejected(tmp_path):
+    from cvxpygen_b200 import cpg
+    with pytest.raises(ValueError):
+        cpg.generate_code(families.portfolio_socp(), code_dir=str(tmp_path / 'x'), solver='ADMM-CUDA', wrapper=False)
+    with pytest.raises(ValueError):
+        cpg.generate_code(families.mpc(2, 1, 2), code_dir=str(tmp_path / 'y'), solver='IPM-CUDA', wrapper=False)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _ref_batch(fam, a, wp, **kw):
+    c0, b0 = fam.canon_data('c'), fam.canon_data('b')
+    r = ref_ecos.RefECOS(c0, fam.canon_matrix('A'), b0, fam.canon_matrix('G'), fam.canon_data('h'),
+                         fam.cone_dims['l'], fam.cone_dims['q'], **kw)
+    B = a.shape[0]
+    Cb = np.tile(c0, (B, 1)); Cb[:, :100] = -a
+    Bb = np.tile(b0, (B, 1)); Bb[:, 11:111] = -wp
+    return r.solve_batch(c=Cb, b=Bb)
+
+
+@pytest.mark.gpu
+def test_gpu_portfolio_matches_golden():
+    g = _golden()
+    m = standard.load(NAME)
+    r = m.solve_batch({'a': g['param_a'], 'w_prev': g['param_w_prev']}, return_canonical=True)
+    assert m.launch_count() == 1
+    assert np.array_equal(r.cpg_info.iter, g['iter']) and (r.cpg_info.status == 0).all()
+    for k in range(g['x'].shape[0]):
+        assert _rel(r.sol_x[k], g['x'][k]) < RTOL_PRIMAL and _rel(r.sol_y[k], g['y'][k]) < RTOL_PRIMAL
+        assert _rel(r.sol_s[k], g['s'][k]) < RTOL_PRIMAL and _rel(r.sol_z[k], g['z'][k]) < RTOL_DUAL
+    assert np.allclose(r.cpg_info.obj_val, -g['pcost'], rtol=0, atol=1e-9)
+    fam = families.portfolio_socp()
+    assert np.array_equal(r.cpg_prim['w'], r.sol_x[:, fam.variables[0].indices])
+    assert np.array_equal(r.cpg_dual['d3'], r.sol_y[:, fam.duals[3].indices])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not ref_ecos.available(), reason='oracle/_ref/libecos_ref.so not built')
+def test_gpu_portfolio_matches_compiled_reference_on_fresh_batch():
+    fam = families.portfolio_socp()
+    rng = np.random.default_rng(7)
+    B = 400
+    a = rng.standard_normal((B, 100)) * rng.uniform(0.2, 2.0, (B, 1))
+    wp = np.abs(1 / 100 + 0.02 * rng.standard_normal((B, 100)))
+    ref = _ref_batch(fam, a, wp)
+    m = standard.load(NAME)
+    r = m.solve_batch({'a': a, 'w_prev': wp}, return_canonical=True)
+    assert np.array_equal(r.cpg_info.status, ref['exitflag'])
+    assert (np.abs(r.cpg_info.iter - ref['iter']) <= 1).all() and (r.cpg_info.iter == ref['iter']).mean() > 0.97
+    same = r.cpg_info.iter == ref['iter']
+    for k in np.nonzero(same)[0]:
+        assert _rel(r.sol_x[k], ref['x'][k]) < RTOL_PRIMAL, k
+        assert _rel(r.sol_y[k], ref['y'][k]) < RTOL_PRIMAL and _rel(r.sol_z[k], ref['z'][k]) < RTOL_DUAL, k
+    # an instance that stops one iteration earlier / later still agrees to the solver tolerance on the user variables
+    assert _rel(r.cpg_prim['w'], ref['x'][:, :100]) < 1e-5
+    assert np.allclose(r.cpg_info.obj_val, -ref['pcost'], rtol=0, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_gpu_portfolio_full_batch_properties():
+    """BASELINE config 3 size (batch 50k): optimality conditions of the ORIGINAL (un-equilibrated) problem on every
+    instance, device-buffer entry point."""
+    import torch
+    fam = families.portfolio_socp()
+    B = 50000
+    rng = np.random.default_rng(11)
+    a = rng.standard_normal((B, 100)); wp = np.abs(1 / 100 + 0.01 * rng.standard_normal((B, 100)))
+    m = standard.load(NAME)
+    P = torch.from_numpy(np.ascontiguousarray(np.c_[a, wp])).cuda()
+    out = m.solve_batch_device(P, return_canonical=True)
+    torch.cuda.synchronize()
+    st = out.status.cpu().numpy()
+    assert (st == 0).all()
+    x, y, z, s = (t.cpu().numpy() for t in (out.sol_x, out.sol_y, out.sol_z, out.sol_s))
+    A, G = fam.canon_matrix('A'), fam.canon_matrix('G')
+    c0, b0, h = fam.canon_data('c'), fam.canon_data('b'), fam.canon_data('h')
+    Cb = np.tile(c0, (B, 1)); Cb[:, :100] = -a
+    Bb = np.tile(b0, (B, 1)); Bb[:, 11:111] = -wp
+    assert np.abs(x @ A.T.toarray() - Bb).max() < 1e-6
+    assert np.abs(h[None, :] - x @ G.T.toarray() - s).max() < 1e-6
+    assert np.abs(y @ A.toarray() + z @ G.toarray() + Cb).max() < 1e-6
+    assert (s[:, :601] > -1e-9).all() and (z[:, :601] > -1e-9).all()
+    assert (s[:, 601] >= np.linalg.norm(s[:, 602:613], axis=1) - 1e-8).all()
+    assert (z[:, 613] >= np.linalg.norm(z[:, 614:], axis=1) - 1e-8).all()
+    assert np.abs((s * z).sum(1)).max() < 1e-5
+    w = x[:, :100]
+    assert np.abs(w.sum(1) - 1).max() < 1e-7 and (np.abs(w).sum(1) <= 1.6 + 1e-6).all()
+    # the same batch twice gives the same answer to rounding (accumulation order of shared-memory atomics may differ)
+    out2 = m.solve_batch_device(P, return_canonical=True)
+    torch.cuda.synchronize()
+    assert (out2.iter == out.iter).all() and _rel(out2.sol_x.cpu().numpy(), x) < 1e-9
