@@ -21,6 +21,10 @@ STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
     'portfolio_socp_100_10': (lambda: families.portfolio_socp(100, 10), ['a', 'w_prev']),   # BASELINE config 3 (IPM-CUDA)
 }
 
+# families solved by the ADMM (QP) backend / by the interior-point (SOCP) backend
+QP_NAMES: List[str] = [n for n in STANDARD if not n.startswith('portfolio_socp')]
+SOCP_NAMES: List[str] = [n for n in STANDARD if n.startswith('portfolio_socp')]
+
 
 def code_dir(name: str) -> str:
     return os.path.join(GENERATED_DIR, name)

@@ -22,7 +22,7 @@ from oracle.ref_osqp import RefOSQP           # noqa: E402
 from cvxpygen_b200 import standard            # noqa: E402
 
 B = 48
-for name in standard.STANDARD:
+for name in standard.QP_NAMES:
     fam, params, (q, l, u) = family_and_batch(name, B, seed=2024)
     out = {'B': B, 'seed': 2024}
     for k, v in params.items():

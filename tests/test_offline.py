@@ -12,7 +12,7 @@ from cvxpygen_b200.offline.blob import HEADER_FIELDS, MAGIC
 from cvxpygen_b200.offline.qp_setup import setup_qp_family
 from helpers import GOLDEN
 
-NAMES = list(standard.STANDARD)
+NAMES = list(standard.QP_NAMES)
 
 
 @pytest.fixture(scope='module')

@@ -76,7 +76,7 @@ def test_kat_unconstrained():
     assert abs(r['obj'][0] + 19.209752026813277) < 1e-5
 
 
-@pytest.mark.parametrize('name', list(standard.STANDARD))
+@pytest.mark.parametrize('name', list(standard.QP_NAMES))
 @pytest.mark.parametrize('tag,kw', [('default', {}), ('tight', dict(eps_abs=1e-7, eps_rel=1e-7)), ('norho', dict(adaptive_rho=0))])
 def test_numpy_oracle_matches_golden(name, tag, kw):
     g = np.load(os.path.join(GOLDEN, f'{name}.npz'))
