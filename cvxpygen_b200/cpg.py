@@ -49,7 +49,8 @@ def generate_code(problem, code_dir='cpg_code', solver=None, solver_opts=None, e
         from .offline.socp_setup import setup_socp_family
         if gradient:
             raise ValueError('gradient=True is generated for the QP path (ADMM-CUDA) only')
-        setup = setup_socp_family(fam, batch_params)
+        from .offline.socp_setup import DEFAULT_THREADS
+        setup = setup_socp_family(fam, batch_params, threads=int(opts.get('threads') or DEFAULT_THREADS))
         codegen_ipm.write_ipm_code(setup, code_dir, prefix=prefix, threads=opts.get('threads'))
         sys.stdout.write('cvxpygen_b200 finished generating code.\n')
         if wrapper:

@@ -98,6 +98,14 @@ int grow(T** p, size_t count) {
   return CPG_B200_OK;
 }
 
+// device-side alias of a pinned (cudaHostAlloc / cudaHostRegister) host buffer under unified addressing, else null
+template <class Tp> Tp* mapped_view(Tp* host) {
+  if (!host) return nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return a.type == cudaMemoryTypeHost ? static_cast<Tp*>(a.devicePointer) : nullptr;
+}
+
 int ensure_staging(int B) {
   if (B <= g.cap_B) return CPG_B200_OK;
   int rc;
@@ -130,7 +138,7 @@ int CPG_B200_FN(cpg_b200_launch_count)(void) { return g.launches; }
 void CPG_B200_FN(cpg_b200_default_settings)(CpgB200Settings* s) {
   if (!s) return;
   s->max_iter = 4000; s->check_termination = 25; s->scaled_termination = 0; s->warm_start = 0;
-  s->adaptive_rho = 1; s->adaptive_rho_interval = 0; s->scaling = CPG_FAM_SCALING; s->pad_ = 0;
+  s->adaptive_rho = 1; s->adaptive_rho_interval = 0; s->scaling = CPG_FAM_SCALING; s->host_zero_copy = 1;
   s->eps_abs = 1e-3; s->eps_rel = 1e-3; s->eps_prim_inf = 1e-4; s->eps_dual_inf = 1e-4;
   s->alpha = 1.6; s->adaptive_rho_tolerance = 5.0;
 }
@@ -269,15 +277,24 @@ int CPG_B200_FN(cpg_solve_batch_host)(int B, const double* params, const double*
     CK(cudaMemcpyAsync(g.d_x0, x0, sizeof(double) * (size_t)B * Fam::N, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(g.d_y0, y0, sizeof(double) * (size_t)B * Fam::M, cudaMemcpyHostToDevice, st));
   }
+  // result rows: a pinned host buffer is written by the kernels directly (the stores are posted PCIe writes, so the
+  // transfer of instance i overlaps the solves still running); anything else goes through the staging buffers
+  const bool zc = settings ? settings->host_zero_copy != 0 : true;
+  double* k_prim = zc ? mapped_view(prim) : nullptr;
+  double* k_dual = zc ? mapped_view(dual) : nullptr;
+  double* k_solx = zc ? mapped_view(sol_x) : nullptr;
+  double* k_soly = zc ? mapped_view(sol_y) : nullptr;
   rc = CPG_B200_FN(cpg_solve_batch_device)(B, g.d_params, warm ? g.d_x0 : nullptr, warm ? g.d_y0 : nullptr,
-                                           prim ? g.d_prim : nullptr, dual ? g.d_dual : nullptr,
-                                           sol_x ? g.d_solx : nullptr, sol_y ? g.d_soly : nullptr,
+                                           prim ? (k_prim ? k_prim : g.d_prim) : nullptr,
+                                           dual ? (k_dual ? k_dual : g.d_dual) : nullptr,
+                                           sol_x ? (k_solx ? k_solx : g.d_solx) : nullptr,
+                                           sol_y ? (k_soly ? k_soly : g.d_soly) : nullptr,
                                            g.d_obj, g.d_iter, g.d_status, g.d_pri, g.d_dua, settings, st);
   if (rc) return rc;
-  if (prim) CK(cudaMemcpyAsync(prim, g.d_prim, sizeof(double) * (size_t)B * H->n_prim, cudaMemcpyDeviceToHost, st));
-  if (dual) CK(cudaMemcpyAsync(dual, g.d_dual, sizeof(double) * (size_t)B * H->n_dual, cudaMemcpyDeviceToHost, st));
-  if (sol_x) CK(cudaMemcpyAsync(sol_x, g.d_solx, sizeof(double) * (size_t)B * Fam::N, cudaMemcpyDeviceToHost, st));
-  if (sol_y) CK(cudaMemcpyAsync(sol_y, g.d_soly, sizeof(double) * (size_t)B * Fam::M, cudaMemcpyDeviceToHost, st));
+  if (prim && !k_prim) CK(cudaMemcpyAsync(prim, g.d_prim, sizeof(double) * (size_t)B * H->n_prim, cudaMemcpyDeviceToHost, st));
+  if (dual && !k_dual) CK(cudaMemcpyAsync(dual, g.d_dual, sizeof(double) * (size_t)B * H->n_dual, cudaMemcpyDeviceToHost, st));
+  if (sol_x && !k_solx) CK(cudaMemcpyAsync(sol_x, g.d_solx, sizeof(double) * (size_t)B * Fam::N, cudaMemcpyDeviceToHost, st));
+  if (sol_y && !k_soly) CK(cudaMemcpyAsync(sol_y, g.d_soly, sizeof(double) * (size_t)B * Fam::M, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(obj_val, g.d_obj, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(pri_res, g.d_pri, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(dua_res, g.d_dua, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));

@@ -15,6 +15,10 @@
 //   RHS_affine / RHS_combined ecos/src/ecos.c:648-757          lineSearch      ecos/src/ecos.c:947-1046
 //   conicProduct / conicDivision ecos/src/cone.c:452-513       main loop / backscale ecos/src/ecos.c:1075-1607,1051-1070
 //
+// Every sparse phase (one level of the numeric LDL', one level of a triangular solve, a product with the constant part of
+// K) runs as a GATHER PLAN (cvxpygen_b200/offline/gather.py): each target is owned by one lane group, entries are read
+// lane-interleaved from tables, long rows are summed with butterfly shuffles -- no atomics, fixed summation order.
+//
 // Index space: k = [x (N) | y (P) | z stretched (MT = M + 2 NSOC)]; every second-order cone of size d occupies d + 2
 // consecutive rows, the last two carrying the sparse representation of its scaling (ecos/src/preproc.c:77-330).
 // Tables come from cvxpygen_b200/offline/socp_setup.py; sizes and offsets are compile-time constants (cpg_ipm_family.h).
@@ -31,9 +35,12 @@
 #include <vector>
 #define IPM_FN inline
 #define IPM_CONST static const
+namespace cpgipm { static long g_count[8] = {0, 0, 0, 0, 0, 0, 0, 0}; }     // emulation statistics: solves, factors, barriers
+#define IPM_COUNT(i) (++cpgipm::g_count[i])
 #else
 #define IPM_FN __device__ __forceinline__
 #define IPM_CONST __device__ const
+#define IPM_COUNT(i) ((void)0)
 #endif
 
 namespace cpgipm {
@@ -74,29 +81,35 @@ constexpr int NW = IPM_NW, DG0 = IPM_DG0, TT0 = IPM_TT0, NS = IPM_NS, NT = IPM_N
 constexpr int NNZM = IPM_NNZM, NPB = IPM_NPB, NMAP = IPM_NMAP, NPRIM = IPM_NPRIM, NDUAL = IPM_NDUAL, QTOT = IPM_QTOT;
 constexpr int CONE_D = L + NSOC;              // degree of the cone (w->D)
 constexpr int PT = (NK + T - 1) / T;          // elements of a k-space vector owned by one thread
+constexpr int NCR = MT - L;                   // stretched rows of the second-order cones
+static_assert(IPM_THREADS == CPG_IPM_THREADS, "the gather plans were dealt for another CTA width: regenerate the family");
+static_assert(NT <= 32, "the dense tail block is handled by one warp");
 
-// ---- shared-memory layout (in doubles, then the u16 tables)
+// ---- shared-memory layout (in doubles, then the u32 / u16 tables).  S carries one extra slot that stays zero (the null
+// entry of the plans points at it); the inverse pivots live in the diagonal slots of S (dinv(k) = S[DG0 + k]).
 constexpr int O_XYZ = 0, O_CBH = O_XYZ + NK, O_SV = O_CBH + NK, O_LAM = O_SV + MT, O_V = O_LAM + MT, O_W = O_V + L,
-              O_Q = O_W + L, O_SC = O_Q + QTOT, O_S = O_SC + 8 * (NSOC > 0 ? NSOC : 1), O_DINV = O_S + NS,
-              O_RHS = O_DINV + NK, O_PX = O_RHS + NK, O_E = O_PX + NK, O_SOL1 = O_E + NK, O_RZ = O_SOL1 + NK,
+              O_Q = O_W + L, O_SC = O_Q + QTOT, O_S = O_SC + 8 * (NSOC > 0 ? NSOC : 1),
+              O_RHS = O_S + NS + 1, O_PX = O_RHS + NK, O_E = O_PX + NK, O_SOL1 = O_E + NK, O_RZ = O_SOL1 + NK,
               O_DSW = O_RZ + MT, O_RED = O_DSW + MT, O_CONE = O_RED + 2 * NWARP * 16,
-              O_AG = O_CONE + 4 * (NSOC > 0 ? NSOC : 1), O_F64_END = O_AG + NNZM;
+              O_CE = O_CONE + 4 * (NSOC > 0 ? NSOC : 1), O_TW = O_CE + (NCR > 0 ? NCR : 1),
+              O_AG = O_TW + 2 * 32, O_F64_END = O_AG + NNZM + 1;
+constexpr int U32_COUNT = (IPM_SB_U16_OFF - IPM_SB_U32_OFF) / 4;
 constexpr int U16_COUNT = (IPM_SB_BYTES - IPM_SB_U16_OFF) / 2;
-constexpr size_t SMEM_BYTES = size_t(O_F64_END) * 8 + size_t(U16_COUNT) * 2 + 16;
+constexpr size_t SMEM_BYTES = size_t(O_F64_END) * 8 + size_t(U32_COUNT) * 4 + size_t(U16_COUNT) * 2 + 16;
 enum { SC_ETA2 = 0, SC_ETA, SC_A, SC_D1, SC_U0, SC_U1, SC_V1, SC_W };
 
 struct Sm {
-  double *xyz, *cbh, *sv, *lam, *v, *w, *q, *sc, *S, *dinv, *rhs, *px, *e, *sol1, *rz, *dsw, *red, *cone, *ag;
-  const uint16_t *mr_t, *mr_s, *fw_t, *fw_s, *fw_slot, *bw_t, *bw_s, *socv, *socu, *tail_k, *perm;
+  double *xyz, *cbh, *sv, *lam, *v, *w, *q, *sc, *S, *rhs, *px, *e, *sol1, *rz, *dsw, *red, *cone, *ce, *tw, *ag;
+  const uint32_t *mv_e, *fw_e, *bw_e;
+  const uint16_t *mv_d, *fw_d, *bw_d, *socv, *socu, *tail_k, *perm;
   int* flag;
 };
-
-struct alignas(8) Op { uint16_t t, a, b, j; };      // S[t] -= S[a] * S[b] * Dinv[j]
 
 struct Gm {                 // global constant tables
   const double *Sbase, *cbh_base, *unscale, *map_v;
   const int *map_t, *map_p, *prim_idx, *dual_idx;
-  const Op* ops;            // NOPS update operations of the numeric factorisation
+  const unsigned long long* op_e;      // factorisation plan: entries (slot a | slot b << 16 | diagonal slot << 32)
+  const uint32_t* op_d;                // and descriptors
 };
 
 IPM_FN Gm make_gm(const unsigned char* g) {
@@ -105,7 +118,8 @@ IPM_FN Gm make_gm(const unsigned char* g) {
   r.Sbase = f + IPM_G_SBASE; r.cbh_base = f + IPM_G_CBH_BASE; r.unscale = f + IPM_G_UNSCALE; r.map_v = f + IPM_G_MAP_V;
   const int* i = reinterpret_cast<const int*>(g + IPM_GB_I32_OFF);
   r.map_t = i + IPM_GI_MAP_T; r.map_p = i + IPM_GI_MAP_P; r.prim_idx = i + IPM_GI_PRIM_IDX; r.dual_idx = i + IPM_GI_DUAL_IDX;
-  r.ops = reinterpret_cast<const Op*>(g + IPM_GB_OPS_OFF);
+  r.op_e = reinterpret_cast<const unsigned long long*>(g + IPM_GB_OPS_OFF);
+  r.op_d = reinterpret_cast<const uint32_t*>(g + IPM_GB_OPD_OFF);
   return r;
 }
 
@@ -113,12 +127,14 @@ IPM_FN Sm make_sm(unsigned char* base) {
   Sm s;
   double* f = reinterpret_cast<double*>(base);
   s.xyz = f + O_XYZ; s.cbh = f + O_CBH; s.sv = f + O_SV; s.lam = f + O_LAM; s.v = f + O_V; s.w = f + O_W; s.q = f + O_Q;
-  s.sc = f + O_SC; s.S = f + O_S; s.dinv = f + O_DINV; s.rhs = f + O_RHS; s.px = f + O_PX; s.e = f + O_E;
-  s.sol1 = f + O_SOL1; s.rz = f + O_RZ; s.dsw = f + O_DSW; s.red = f + O_RED; s.cone = f + O_CONE; s.ag = f + O_AG;
-  const uint16_t* h = reinterpret_cast<const uint16_t*>(f + O_F64_END);
-  s.mr_t = h + IPM_H_MR_T; s.mr_s = h + IPM_H_MR_S; s.fw_t = h + IPM_H_FW_T; s.fw_s = h + IPM_H_FW_S;
-  s.fw_slot = h + IPM_H_FW_SLOT; s.bw_t = h + IPM_H_BW_T; s.bw_s = h + IPM_H_BW_S; s.socv = h + IPM_H_SOCV;
-  s.socu = h + IPM_H_SOCU; s.tail_k = h + IPM_H_TAIL_K; s.perm = h + IPM_H_PERM;
+  s.sc = f + O_SC; s.S = f + O_S; s.rhs = f + O_RHS; s.px = f + O_PX; s.e = f + O_E;
+  s.sol1 = f + O_SOL1; s.rz = f + O_RZ; s.dsw = f + O_DSW; s.red = f + O_RED; s.cone = f + O_CONE; s.ce = f + O_CE;
+  s.tw = f + O_TW; s.ag = f + O_AG;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(f + O_F64_END);
+  s.mv_e = w + IPM_E_MV; s.fw_e = w + IPM_E_FW; s.bw_e = w + IPM_E_BW;
+  const uint16_t* h = reinterpret_cast<const uint16_t*>(w + U32_COUNT);
+  s.mv_d = h + IPM_H_MV_D; s.fw_d = h + IPM_H_FW_D; s.bw_d = h + IPM_H_BW_D;
+  s.socv = h + IPM_H_SOCV; s.socu = h + IPM_H_SOCU; s.tail_k = h + IPM_H_TAIL_K; s.perm = h + IPM_H_PERM;
   s.flag = reinterpret_cast<int*>(const_cast<uint16_t*>(h + U16_COUNT + (U16_COUNT & 1)));
   return s;
 }
@@ -129,7 +145,8 @@ IPM_FN double safediv(double x, double y) { return y < kEps ? x / kEps : x / y; 
 // execution model: phases, reductions, per-cone warps
 #ifdef CPG_IPM_HOST_EMU
 IPM_FN void atomic_add(double* p, double v) { *p += v; }
-template <class F> IPM_FN void phase(F&& f) { for (int t = 0; t < T; ++t) f(t); }
+template <class F> IPM_FN void phase(F&& f) { IPM_COUNT(2); for (int t = 0; t < T; ++t) f(t); }
+IPM_FN void sync_phase() { IPM_COUNT(2); }
 // KS sums and KM maxima over all threads; f(tid, s, m) accumulates with += and fmax
 template <int KS, int KM, class F> IPM_FN void phase_red(Sm&, int&, double* s, double* m, F&& f) {
   for (int k = 0; k < KS; ++k) s[k] = 0.0;
@@ -152,6 +169,7 @@ IPM_FN void phase_red_cones(Sm& sm, int& rb, double* s, double* m, F&& f, G&& g)
   phase_red<KS, KM>(sm, rb, s, m, f);
   for (int c = 0; c < NSOC; ++c) g(c, WarpOps());
 }
+template <class G> IPM_FN void cones_then_sync(G&& g) { for (int c = 0; c < NSOC; ++c) g(c, WarpOps()); }
 template <int CNT> struct PerThread {
   std::vector<double> a; PerThread() : a(size_t(T) * CNT, 0.0) {}
   double& at(int tid, int j) { return a[size_t(tid) * CNT + j]; }
@@ -159,6 +177,7 @@ template <int CNT> struct PerThread {
 #else
 IPM_FN void atomic_add(double* p, double v) { atomicAdd(p, v); }
 template <class F> IPM_FN void phase(F&& f) { f(int(threadIdx.x)); __syncthreads(); }
+IPM_FN void sync_phase() { __syncthreads(); }
 IPM_FN double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -206,6 +225,7 @@ template <class G> IPM_FN void run_cones(G&& g) {
 template <class F, class G> IPM_FN void phase_cones(F&& f, G&& g) {
   f(int(threadIdx.x)); run_cones(g); __syncthreads();
 }
+template <class G> IPM_FN void cones_then_sync(G&& g) { run_cones(g); __syncthreads(); }
 template <int KS, int KM, class F, class G>
 IPM_FN void phase_red_cones(Sm& sm, int& rb, double* s, double* m, F&& f, G&& g) {
   run_cones(g);
@@ -217,31 +237,6 @@ template <int CNT> struct PerThread {
 };
 #endif
 
-// chunked segmented accumulation: entries [lo, hi) sorted by target; out[target(e)] -= sum value(e)
-// entry(e, t) returns the value of entry e and stores its target in t.  Only the first and the last target of a chunk
-// can be shared with another thread, so only those two are flushed atomically.
-template <class EF> IPM_FN void seg_sub(int tid, int lo, int hi, double* out, EF&& entry) {
-  const int n = hi - lo;
-  if (n <= 0) return;
-  const int chunk = (n + T - 1) / T;
-  int e = lo + tid * chunk;
-  const int end = e + chunk < hi ? e + chunk : hi;
-  if (e >= end) return;
-  int cur = -1;
-  double acc = 0.0;
-  bool first = true;
-  for (; e < end; ++e) {
-    int t;
-    const double v = entry(e, t);
-    if (t != cur) {
-      if (cur >= 0) { if (first) { atomic_add(out + cur, -acc); first = false; } else out[cur] -= acc; }
-      cur = t; acc = 0.0;
-    }
-    acc += v;
-  }
-  atomic_add(out + cur, -acc);
-}
-
 template <class F> IPM_FN void each_k(int tid, int n, F&& f) { for (int i = tid; i < n; i += T) f(i); }
 
 IPM_CONST int kSocSo[NSOC > 0 ? NSOC : 1] = IPM_SOC_SO;      // stretched z offset of each cone
@@ -249,85 +244,136 @@ IPM_CONST int kSocD[NSOC > 0 ? NSOC : 1] = IPM_SOC_D;        // cone sizes
 IPM_CONST int kSocQo[NSOC > 0 ? NSOC : 1] = IPM_SOC_QO;      // offset of q in sm.q
 IPM_CONST int kSocVo[NSOC > 0 ? NSOC : 1] = IPM_SOC_VO;      // offset in socv
 IPM_CONST int kSocUo[NSOC > 0 ? NSOC : 1] = IPM_SOC_UO;      // offset in socu
-IPM_CONST int kOpLo[NLW + 2] = IPM_OP_LO;
-IPM_CONST int kFwLo[NLW + 2] = IPM_FW_LO;
-IPM_CONST int kBwLo[NLW + 1] = IPM_BW_LO;
 IPM_CONST int kLevLo[NLW + 1] = IPM_LEV_LO;
+
+// ---- gather plans: per (round, warp) entry offset | trip count << 20 | shuffle steps << 28, and the rounds of each phase
+IPM_CONST unsigned kMvWr[] = IPM_MV_WR;   IPM_CONST int kMvPh[] = IPM_MV_PH;
+IPM_CONST unsigned kFwWr[] = IPM_FW_WR;   IPM_CONST int kFwPh[] = IPM_FW_PH;
+IPM_CONST unsigned kBwWr[] = IPM_BW_WR;   IPM_CONST int kBwPh[] = IPM_BW_PH;
+IPM_CONST unsigned kOpWr[] = IPM_OP_WR;   IPM_CONST int kOpPh[] = IPM_OP_PH;
+
+// One plan = entry table E (u32: two u16 fields, or u64: up to four), descriptor table D (u16 with an 11-bit target, or
+// u32 with a 16-bit target) and the per-(round, warp) words above.  run(ph, value, commit): for every cell of phase ph
+//   acc = sum_j value(entry_j);  butterfly over the cell group;  the group leader calls commit(target, flag, acc).
+template <class E, class D, int TB> struct Plan {
+  const E* ent; const D* desc; const unsigned* wr; const int* ph;
+#ifdef CPG_IPM_HOST_EMU
+  template <class V, class C> void run(int phase, V&& value, C&& commit) const {
+    for (int r = ph[phase]; r < ph[phase + 1]; ++r)
+      for (int w = 0; w < NWARP; ++w) {
+        const unsigned m = wr[r * NWARP + w];
+        const int base = int(m & 0xfffffu), len = int((m >> 20) & 0xffu), ns = int(m >> 28);
+        double acc[32]; unsigned d[32]; int g[32];
+        for (int l = 0; l < 32; ++l) {
+          d[l] = desc[r * T + w * 32 + l]; g[l] = 1 << ((d[l] >> TB) & 7u); acc[l] = 0.0;
+          for (int j = 0; j < len; ++j) acc[l] += value(ent[base + j * 32 + l]);
+        }
+        for (int s = 0, o = 1; s < ns; ++s, o <<= 1) {
+          double nx[32];
+          for (int l = 0; l < 32; ++l) nx[l] = o < g[l] ? acc[l] + acc[l ^ o] : acc[l];
+          for (int l = 0; l < 32; ++l) acc[l] = nx[l];
+        }
+        for (int l = 0; l < 32; ++l)
+          if (((d[l] >> (TB + 3)) & 1u) && (l & (g[l] - 1)) == 0) commit(int(d[l] & ((1u << TB) - 1u)), int((d[l] >> (TB + 4)) & 1u), acc[l]);
+      }
+  }
+#else
+  template <class V, class C> IPM_FN void run(int phase, V&& value, C&& commit) const {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int r = ph[phase]; r < ph[phase + 1]; ++r) {
+      const unsigned m = wr[r * NWARP + wid];
+      const unsigned d = desc[r * T + tid];
+      const E* e = ent + (m & 0xfffffu) + lane;
+      const int len = int((m >> 20) & 0xffu), ns = int(m >> 28);
+      double acc = 0.0;
+      int j = 0;
+      for (; j + 4 <= len; j += 4) {              // the four table reads are independent of the arithmetic: issue them first
+        const E e0 = e[j * 32], e1 = e[j * 32 + 32], e2 = e[j * 32 + 64], e3 = e[j * 32 + 96];
+        const double v0 = value(e0), v1 = value(e1), v2 = value(e2), v3 = value(e3);
+        acc += v0; acc += v1; acc += v2; acc += v3;
+      }
+      for (; j < len; ++j) acc += value(e[j * 32]);
+      const int g = 1 << ((d >> TB) & 7u);
+      for (int s = 0, o = 1; s < ns; ++s, o <<= 1) {
+        const double v = __shfl_xor_sync(0xffffffffu, acc, o);
+        if (o < g) acc += v;
+      }
+      if (((d >> (TB + 3)) & 1u) && (lane & (g - 1)) == 0) commit(int(d & ((1u << TB) - 1u)), int((d >> (TB + 4)) & 1u), acc);
+    }
+  }
+#endif
+};
+using PlanS = Plan<uint32_t, uint16_t, 11>;                 // tables in shared memory
+using PlanG = Plan<unsigned long long, uint32_t, 16>;       // tables in global memory (read once per factorisation)
 
 // ----------------------------------------------------------------------------------------------------------------------
 struct Solver {
   Sm sm; Gm gm; IpmSettings stg;
   int rb;                                   // reduction scratch toggle
 
+  IPM_FN PlanS plan_mv() const { return PlanS{sm.mv_e, sm.mv_d, kMvWr, kMvPh}; }
+  IPM_FN PlanS plan_fw() const { return PlanS{sm.fw_e, sm.fw_d, kFwWr, kFwPh}; }
+  IPM_FN PlanS plan_bw() const { return PlanS{sm.bw_e, sm.bw_d, kBwWr, kBwPh}; }
+  IPM_FN PlanG plan_op() const { return PlanG{gm.op_e, gm.op_d, kOpWr, kOpPh}; }
+
   IPM_FN double sign_of(int k) const {      // Sign vector of createKKT_U (preproc.c:135-170)
     if (k < N) return 1.0;
     for (int c = 0; c < NSOC; ++c) if (k == ZOFF + kSocSo[c] + kSocD[c] + 1) return 1.0;
     return -1.0;
   }
+  // pivot of column k with the dynamic regularisation of LDL_numeric2 (ldl.c:336-350); its inverse replaces it in S
+  IPM_FN double inv_pivot(int k, double d) const {
+    const double sg = sign_of(k);
+    if (sg * d <= kEps) d = sg * kDelta;
+    return 1.0 / d;
+  }
 
-  // ---- numeric factorisation: S holds the KKT values on entry, the column-scaled factor on exit
-  IPM_FN void pivots(int tid, int lv) {
-    for (int p = kLevLo[lv] + tid; p < kLevLo[lv + 1]; p += T) {
-      const int k = sm.perm[p];
-      double d = sm.S[DG0 + k];
-      const double sg = sign_of(k);
-      if (sg * d <= kEps) d = sg * kDelta;
-      sm.dinv[k] = 1.0 / d;
-    }
-  }
-  IPM_FN void apply_ops(int tid, int lv) {
-    const Op* ops = gm.ops;
-    seg_sub(tid, kOpLo[lv], kOpLo[lv + 1], sm.S, [&](int e, int& t) {
-      const Op o = ops[e];
-      t = o.t;
-      return sm.S[o.a] * sm.S[o.b] * sm.dinv[o.j];
-    });
-  }
+  // ---- numeric factorisation: S holds the KKT values on entry; on exit the column-scaled factor (S_ij = L_ij D_j), the
+  // inverse pivots in the diagonal slots and the inverse of the tail's unit triangle in the tail block
   IPM_FN void tail_factor(int tid);
   IPM_FN void factor() {
-    if (NLW > 0) phase([&](int tid) { pivots(tid, 0); });
-    for (int lv = 1; lv < NLW; ++lv) {
-      phase([&](int tid) { apply_ops(tid, lv); });
-      phase([&](int tid) { pivots(tid, lv); });
+    IPM_COUNT(1);
+    phase([&](int tid) {
+      for (int p = kLevLo[0] + tid; p < kLevLo[1]; p += T) { const int k = sm.perm[p]; sm.S[DG0 + k] = inv_pivot(k, sm.S[DG0 + k]); }
+    });
+    const PlanG po = plan_op();
+    for (int lv = 1; lv <= NLW; ++lv) {
+      po.run(lv - 1,
+             [&](unsigned long long e) {
+               return sm.S[unsigned(e) & 0xffffu] * sm.S[unsigned(e >> 16) & 0xffffu] * sm.S[unsigned(e >> 32) & 0xffffu];
+             },
+             [&](int t, int flag, double acc) {
+               const double v = sm.S[t] - acc;
+               sm.S[t] = flag ? inv_pivot(t - DG0, v) : v;
+             });
+      sync_phase();
     }
-    phase([&](int tid) { apply_ops(tid, NLW); });
     phase([&](int tid) { tail_factor(tid); });
   }
 
   // ---- triangular solves, in place on u (k-space)
   IPM_FN void tail_solve(int tid, double* u);
   IPM_FN void ldl_solve(double* u) {
-    for (int lv = 1; lv <= NLW; ++lv)
-      phase([&](int tid) {
-        seg_sub(tid, kFwLo[lv], kFwLo[lv + 1], u, [&](int e, int& t) {
-          t = sm.fw_t[e];
-          const int s = sm.fw_s[e];
-          return sm.S[sm.fw_slot[e]] * sm.dinv[s] * u[s];
-        });
-      });
-    phase([&](int tid) {
-      tail_solve(tid, u);
-      // meanwhile: D-solve of the wide columns (the tail warp scales its own entries)
-#ifdef CPG_IPM_HOST_EMU
-      if (tid == 0) for (int p = 0; p < NK - NT; ++p) { const int k = sm.perm[p]; u[k] *= sm.dinv[k]; }
-#else
-      if (tid >= 32 || NT == 0) {
-        const int t2 = NT == 0 ? tid : tid - 32, stride = NT == 0 ? T : T - 32;
-        for (int p = t2; p < NK - NT; p += stride) { const int k = sm.perm[p]; u[k] *= sm.dinv[k]; }
-      }
-#endif
-    });
-    for (int lv = NLW - 1; lv >= 0; --lv)
-      phase([&](int tid) {
-        seg_sub(tid, kBwLo[lv], kBwLo[lv + 1], u, [&](int e, int& t) {
-          t = sm.bw_t[e];
-          return sm.S[e] * sm.dinv[t] * u[sm.bw_s[e]];
-        });
-      });
+    IPM_COUNT(0);
+    const PlanS pf = plan_fw(), pb = plan_bw();
+    // forward: row k of a wide level becomes D^-1 L^-1 b at once (it is final when its level is done); the tail rows
+    // (flag) only collect the contributions of the wide columns
+    for (int lv = 0; lv <= NLW; ++lv) {
+      pf.run(lv, [&](uint32_t e) { return sm.S[e & 0xffffu] * u[e >> 16]; },
+             [&](int k, int tail, double acc) { const double v = u[k] - acc; u[k] = tail ? v : v * sm.S[DG0 + k]; });
+      sync_phase();
+    }
+    phase([&](int tid) { tail_solve(tid, u); });
+    for (int lv = 0; lv < NLW; ++lv) {
+      pb.run(lv, [&](uint32_t e) { return sm.S[e & 0xffffu] * u[e >> 16]; },
+             [&](int k, int, double acc) { u[k] -= sm.S[DG0 + k] * acc; });
+      sync_phase();
+    }
   }
 
   // ---- KKT solve with iterative refinement (kkt_solve, kkt.c:87-265); rhs(k) -> out (k-space); returns #refinements
   template <class RHS> IPM_FN int kkt_solve(RHS&& rhs, double* out, bool isinit, PerThread<PT>& dpx) {
+    IPM_COUNT(3);
     double s_[1], m_[1];
     phase_red<0, 1>(sm, rb, s_, m_, [&](int tid, double*, double* m) {
       each_k(tid, NK, [&](int k) { const double b = rhs(k); out[k] = b; m[0] = fmax(m[0], fabs(b)); });
@@ -337,50 +383,53 @@ struct Solver {
     double nerr_prev = NAN;
     int kref = 0;
     for (;;) {
-      // error e = b - K out (with the static regularisation written exactly like the reference does)
-      phase_cones(
-          [&](int tid) {
-            each_k(tid, ZOFF + L, [&](int k) {
-              const double o = out[k];
-              double e = rhs(k);
-              if (k < N) e -= kDeltaStat * o;
-              else if (k < ZOFF) e += kDeltaStat * o;
-              else e += kDeltaStat * o + (isinit ? o : sm.v[k - ZOFF] * o);
-              sm.e[k] = e;
-            });
-          },
-          [&](int c, const WarpOps& W) {
-            const int so = ZOFF + kSocSo[c], d = kSocD[c];
-            if (isinit) {
-              W.each(0, d + 2, [&](int r) {
-                const int k = so + r; const double o = out[k];
-                sm.e[k] = r < d ? rhs(k) + (r < d - 1 ? kDeltaStat : -kDeltaStat) * o + o : o;
-              });
-            } else {
-              const double* q = sm.q + kSocQo[c]; const double* sc = sm.sc + 8 * c;
-              const double e2 = sc[SC_ETA2], d1 = sc[SC_D1], u0 = sc[SC_U0], u1 = sc[SC_U1], v1 = sc[SC_V1];
-              const double x1 = out[so], x3 = out[so + d], x4 = out[so + d + 1];
-              const double qtx2 = W.sum(0, d - 1, [&](int i) { return q[i] * out[so + 1 + i]; });
-              const double vu = v1 * x3 + u1 * x4;
-              W.each(0, d - 1, [&](int i) {
-                const int k = so + 1 + i; const double o = out[k];
-                sm.e[k] = rhs(k) + (i + 1 < d - 1 ? kDeltaStat : -kDeltaStat) * o + e2 * (o + vu * q[i]);
-              });
-              if (W.leader()) {
-                sm.e[so] = rhs(so) + (d > 1 ? kDeltaStat : -kDeltaStat) * x1 + e2 * (d1 * x1 + u0 * x4);
-                sm.e[so + d] = e2 * (v1 * qtx2 + x3);
-                sm.e[so + d + 1] = e2 * (u0 * x1 + u1 * qtx2 - x4);
-              }
-            }
+      // error e = b - K out (with the static regularisation written exactly like the reference does): rows outside the
+      // second-order cones are completed by the owner of the row in the plan; cone rows get the constant part of K here
+      // and the scaling block from the cone warps (sm.ce), the two are added in the reduction below
+      plan_mv().run(0, [&](uint32_t en) { return sm.ag[en & 0xffffu] * out[en >> 16]; },
+                    [&](int k, int, double acc) {
+                      double e = -acc;
+                      if (k < ZOFF + L) {
+                        const double o = out[k];
+                        double b = rhs(k);
+                        if (k < N) b -= kDeltaStat * o;
+                        else if (k < ZOFF) b += kDeltaStat * o;
+                        else b += kDeltaStat * o + (isinit ? o : sm.v[k - ZOFF] * o);
+                        e += b;
+                      }
+                      sm.e[k] = e;
+                    });
+      cones_then_sync([&](int c, const WarpOps& W) {
+        const int so = ZOFF + kSocSo[c], d = kSocD[c];
+        double* ce = sm.ce + (kSocSo[c] - L);
+        if (isinit) {
+          W.each(0, d + 2, [&](int r) {
+            const int k = so + r; const double o = out[k];
+            ce[r] = r < d ? rhs(k) + (r < d - 1 ? kDeltaStat : -kDeltaStat) * o + o : o;
           });
-      phase([&](int tid) {
-        const int n = NNZM, chunk = (n + T - 1) / T;
-        const int lo = tid * chunk, hi = lo + chunk < n ? lo + chunk : n;
-        for (int e = lo; e < hi; ++e) atomic_add(sm.e + sm.mr_s[e], -sm.ag[e] * out[sm.mr_t[e]]);      // - M' [dy; dz]
-        seg_sub(tid, 0, NNZM, sm.e, [&](int e, int& t) { t = sm.mr_t[e]; return sm.ag[e] * out[sm.mr_s[e]]; });   // - M dx
+        } else {
+          const double* q = sm.q + kSocQo[c]; const double* sc = sm.sc + 8 * c;
+          const double e2 = sc[SC_ETA2], d1 = sc[SC_D1], u0 = sc[SC_U0], u1 = sc[SC_U1], v1 = sc[SC_V1];
+          const double x1 = out[so], x3 = out[so + d], x4 = out[so + d + 1];
+          const double qtx2 = W.sum(0, d - 1, [&](int i) { return q[i] * out[so + 1 + i]; });
+          const double vu = v1 * x3 + u1 * x4;
+          W.each(0, d - 1, [&](int i) {
+            const int k = so + 1 + i; const double o = out[k];
+            ce[1 + i] = rhs(k) + (i + 1 < d - 1 ? kDeltaStat : -kDeltaStat) * o + e2 * (o + vu * q[i]);
+          });
+          if (W.leader()) {
+            ce[0] = rhs(so) + (d > 1 ? kDeltaStat : -kDeltaStat) * x1 + e2 * (d1 * x1 + u0 * x4);
+            ce[d] = e2 * (v1 * qtx2 + x3);
+            ce[d + 1] = e2 * (u0 * x1 + u1 * qtx2 - x4);
+          }
+        }
       });
       phase_red<0, 1>(sm, rb, s_, m_, [&](int tid, double*, double* m) {
-        each_k(tid, NK, [&](int k) { m[0] = fmax(m[0], fabs(sm.e[k])); });
+        each_k(tid, NK, [&](int k) {
+          double v = sm.e[k];
+          if (k >= ZOFF + L) { v += sm.ce[k - (ZOFF + L)]; sm.e[k] = v; }
+          m[0] = fmax(m[0], fabs(v));
+        });
       });
       const double nerr = m_[0];
       if (kref > 0 && nerr > nerr_prev) {                 // refinement made it worse: undo and stop
@@ -442,68 +491,102 @@ struct Solver {
 };
 
 // ----------------------------------------------------------------------------------------------------------------------
-// dense tail block: one warp (lane = row within the block)
+// dense tail block: one warp.  tail_factor leaves the inverse pivots in the diagonal slots and X = inv(L_tail) (strictly
+// lower part) in the block, so that a solve with the block is two small dense products instead of two dependent sweeps.
 IPM_FN void Solver::tail_factor(int tid) {
 #ifdef CPG_IPM_HOST_EMU
-  if (tid != 0) return;
+  if (tid != 0 || NT == 0) return;
+  double* B = sm.S + TT0;
+  double dv[NT > 0 ? NT : 1];
   for (int j = 0; j < NT; ++j) {
     const int kj = sm.tail_k[j];
-    double d = sm.S[DG0 + kj]; const double sg = sign_of(kj);
-    if (sg * d <= kEps) d = sg * kDelta;
-    const double dj = 1.0 / d; sm.dinv[kj] = dj;
+    const double ij = inv_pivot(kj, sm.S[DG0 + kj]);
+    dv[j] = ij;
     for (int i = j + 1; i < NT; ++i) {
-      const double sij = sm.S[TT0 + i * NT + j];
-      for (int k = j + 1; k < i; ++k) sm.S[TT0 + i * NT + k] -= sij * sm.S[TT0 + k * NT + j] * dj;
-      sm.S[DG0 + sm.tail_k[i]] -= sij * sij * dj;
+      const double sij = B[i * NT + j];
+      for (int k = j + 1; k < i; ++k) B[i * NT + k] -= sij * B[k * NT + j] * ij;
+      sm.S[DG0 + sm.tail_k[i]] -= sij * sij * ij;
     }
   }
+  double X[(NT > 0 ? NT : 1) * (NT > 0 ? NT : 1)];
+  for (int c = 0; c < NT; ++c)
+    for (int m = 0; m < NT; ++m) {
+      double a = 0.0;
+      for (int k = 0; k < m; ++k) a -= (B[m * NT + k] * dv[k]) * X[k * NT + c];
+      X[m * NT + c] = m == c ? 1.0 : a;
+    }
+  for (int j = 0; j < NT; ++j) sm.S[DG0 + sm.tail_k[j]] = dv[j];
+  for (int m = 0; m < NT; ++m) for (int c = 0; c < m; ++c) B[m * NT + c] = X[m * NT + c];
 #else
-  if (tid >= 32 || NT == 0) return;
+  if (NT == 0 || tid >= 32) return;
+  constexpr int NTT = NT > 0 ? NT : 1;
   const int i = tid;
-  const int ki = i < NT ? sm.tail_k[i] : 0;
+  const bool on = i < NT;
+  const int ki = on ? sm.tail_k[i] : 0;
+  double* B = sm.S + TT0;
+  double r[NTT], x[NTT], dv[NTT];      // row i of the block (S_ik = L_ik D_k), column i of inv(L), inverse pivots (uniform)
+#pragma unroll
+  for (int k = 0; k < NT; ++k) r[k] = (on && k < i) ? B[i * NT + k] : 0.0;
+  double d = on ? sm.S[DG0 + ki] : 1.0;
+#pragma unroll
   for (int j = 0; j < NT; ++j) {
-    const int kj = sm.tail_k[j];
-    double dj = 0.0;
-    if (i == j) {
-      double d = sm.S[DG0 + kj]; const double sg = sign_of(kj);
-      if (sg * d <= kEps) d = sg * kDelta;
-      dj = 1.0 / d; sm.dinv[kj] = dj;
+    const double ij = inv_pivot(sm.tail_k[j], __shfl_sync(0xffffffffu, d, j));
+    dv[j] = ij;
+    if (i == j) sm.S[DG0 + ki] = ij;
+    const double sij = r[j];
+#pragma unroll
+    for (int k = j + 1; k < NT; ++k) {
+      const double t = sij * __shfl_sync(0xffffffffu, r[j], k) * ij;
+      if (i > k) r[k] -= t;
+      if (i == k) d -= t;
     }
-    dj = __shfl_sync(0xffffffffu, dj, j);
-    if (i > j && i < NT) {
-      const double sij = sm.S[TT0 + i * NT + j];
-      for (int k = j + 1; k < i; ++k) sm.S[TT0 + i * NT + k] -= sij * sm.S[TT0 + k * NT + j] * dj;
-      sm.S[DG0 + ki] -= sij * sij * dj;
-    }
-    __syncwarp();
   }
+#pragma unroll
+  for (int m = 0; m < NT; ++m) {
+    double a = 0.0;
+#pragma unroll
+    for (int k = 0; k < m; ++k) a -= (__shfl_sync(0xffffffffu, r[k], m) * dv[k]) * x[k];
+    x[m] = m == i ? 1.0 : a;
+  }
+#pragma unroll
+  for (int m = 1; m < NT; ++m) if (on && i < m) B[m * NT + i] = x[m];
 #endif
 }
 
 IPM_FN void Solver::tail_solve(int tid, double* u) {
 #ifdef CPG_IPM_HOST_EMU
-  if (tid != 0) return;
-  for (int j = 0; j < NT; ++j)
-    for (int i = j + 1; i < NT; ++i) u[sm.tail_k[i]] -= sm.S[TT0 + i * NT + j] * sm.dinv[sm.tail_k[j]] * u[sm.tail_k[j]];
-  for (int j = 0; j < NT; ++j) u[sm.tail_k[j]] *= sm.dinv[sm.tail_k[j]];
-  for (int j = NT - 1; j >= 0; --j)
-    for (int i = j + 1; i < NT; ++i) u[sm.tail_k[j]] -= sm.S[TT0 + i * NT + j] * sm.dinv[sm.tail_k[j]] * u[sm.tail_k[i]];
+  if (tid != 0 || NT == 0) return;
+  const double* X = sm.S + TT0;
+  double b[NT > 0 ? NT : 1], w[NT > 0 ? NT : 1];
+  for (int i = 0; i < NT; ++i) b[i] = u[sm.tail_k[i]];
+  for (int i = 0; i < NT; ++i) {
+    double y = b[i];
+    for (int j = 0; j < i; ++j) y += X[i * NT + j] * b[j];
+    w[i] = y * sm.S[DG0 + sm.tail_k[i]];
+  }
+  for (int i = 0; i < NT; ++i) {
+    double xv = w[i];
+    for (int m = i + 1; m < NT; ++m) xv += X[m * NT + i] * w[m];
+    u[sm.tail_k[i]] = xv;
+  }
 #else
-  if (tid >= 32 || NT == 0) return;
+  if (NT == 0 || tid >= 32) return;
   const int i = tid;
-  const int ki = i < NT ? sm.tail_k[i] : 0;
-  double ui = i < NT ? u[ki] : 0.0;
-  const double di = i < NT ? sm.dinv[ki] : 0.0;
-  for (int j = 0; j < NT; ++j) {
-    const double uj = __shfl_sync(0xffffffffu, ui, j), dj = __shfl_sync(0xffffffffu, di, j);
-    if (i > j && i < NT) ui -= sm.S[TT0 + i * NT + j] * dj * uj;
-  }
-  ui *= di;
-  for (int r = NT - 1; r > 0; --r) {                       // column sweep: row r is final, push it to rows j < r
-    const double xr = __shfl_sync(0xffffffffu, ui, r);
-    if (i < r) ui -= sm.S[TT0 + r * NT + i] * di * xr;
-  }
-  if (i < NT) u[ki] = ui;
+  const bool on = i < NT;
+  const int ki = on ? sm.tail_k[i] : 0;
+  const double* X = sm.S + TT0;
+  double y = on ? u[ki] : 0.0;
+  sm.tw[i] = y;
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < NT - 1; ++j) if (on && j < i) y += X[i * NT + j] * sm.tw[j];
+  const double w = on ? y * sm.S[DG0 + ki] : 0.0;
+  sm.tw[32 + i] = w;
+  __syncwarp();
+  double xv = w;
+#pragma unroll
+  for (int m = 1; m < NT; ++m) if (on && m > i) xv += X[m * NT + i] * sm.tw[32 + m];
+  if (on) u[ki] = xv;
 #endif
 }
 
@@ -595,20 +678,14 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
     return int(kNotConverged);
   };
   for (;; ++it) {
-    // computeResiduals: rx -> rhs[0:N], ry -> rhs[N:ZOFF], rz -> rz
-    phase([&](int tid) {
-      each_k(tid, ZOFF, [&](int k) { sm.rhs[k] = 0.0; });
-      each_k(tid, MT, [&](int i) { sm.rz[i] = sm.sv[i]; });
-    });
-    phase([&](int tid) {
-      const int n = NNZM, chunk = (n + T - 1) / T;
-      const int lo = tid * chunk, hi = lo + chunk < n ? lo + chunk : n;
-      for (int e = lo; e < hi; ++e) atomic_add(sm.rhs + sm.mr_s[e], -sm.ag[e] * sm.xyz[sm.mr_t[e]]);   // -A'y - G'z
-      const int split = IPM_NNZA;                                                                      // rows of A first
-      auto mx = [&](int e, int& t) { t = sm.mr_t[e]; return -sm.ag[e] * sm.xyz[sm.mr_s[e]]; };
-      seg_sub(tid, 0, split, sm.rhs, mx);                                                              // A x
-      seg_sub(tid, split, NNZM, sm.rz - ZOFF, mx);                                                     // s + G x
-    });
+    // computeResiduals (ecos.c:455-499): -A'y - G'z -> rhs[0:N], A x -> rhs[N:ZOFF], s + G x -> rz
+    plan_mv().run(0, [&](uint32_t en) { return sm.ag[en & 0xffffu] * sm.xyz[en >> 16]; },
+                  [&](int k, int, double acc) {
+                    if (k < N) sm.rhs[k] = -acc;
+                    else if (k < ZOFF) sm.rhs[k] = acc;
+                    else sm.rz[k - ZOFF] = sm.sv[k - ZOFF] + acc;
+                  });
+    sync_phase();
     phase_red<16, 0>(sm, rb, s_, m_, [&](int tid, double* s, double*) {
       each_k(tid, N, [&](int k) {
         const double hr = sm.rhs[k], c = sm.cbh[k], x = sm.xyz[k];
@@ -895,13 +972,17 @@ ipm_kernel(const unsigned char* __restrict__ smem_blob, const unsigned char* __r
   sv.sm = make_sm(smem_raw);
   sv.gm = make_gm(gmem_blob);
   sv.stg = stg; sv.rb = 0;
-  // stage the constant tables: [f64 ag_val | u16 tables] -> [O_AG ... | after the f64 area]
+  // stage the constant tables: [f64 ag_val, 0 | u32 plan entries | u16 descriptors and index lists]
   {
     const double* src = reinterpret_cast<const double*>(smem_blob);
-    for (int i = threadIdx.x; i < NNZM; i += T) sv.sm.ag[i] = src[i];
+    for (int i = threadIdx.x; i < NNZM + 1; i += T) sv.sm.ag[i] = src[i];
+    const uint32_t* ws = reinterpret_cast<const uint32_t*>(smem_blob + IPM_SB_U32_OFF);
+    uint32_t* wd = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(smem_raw) + O_F64_END);
+    for (int i = threadIdx.x; i < U32_COUNT; i += T) wd[i] = ws[i];
     const uint16_t* hs = reinterpret_cast<const uint16_t*>(smem_blob + IPM_SB_U16_OFF);
-    uint16_t* hd = reinterpret_cast<uint16_t*>(reinterpret_cast<double*>(smem_raw) + O_F64_END);
+    uint16_t* hd = reinterpret_cast<uint16_t*>(wd + U32_COUNT);
     for (int i = threadIdx.x; i < U16_COUNT; i += T) hd[i] = hs[i];
+    if (threadIdx.x == 0) sv.sm.S[NS] = 0.0;          // the slot every null entry of the plans points at
   }
   __syncthreads();
   double* best = io.best + size_t(blockIdx.x) * (NK + MT);

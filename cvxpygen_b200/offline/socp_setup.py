@@ -23,10 +23,12 @@ import scipy.sparse as sp
 
 from ..ir import CanonFamily
 from . import kkt as _kkt
+from . import gather as _gather
 
 DELTASTAT = 7e-8          # ecos/include/ecos.h:54
 EQUIL_ITERS = 3           # ecos/include/ecos.h:81
 MAX_TAIL = 32
+DEFAULT_THREADS = 256    # threads of the CTA that solves one instance (the gather plans are dealt for this width)
 
 
 def ecos_equilibrate(A: sp.csc_matrix, G: sp.csc_matrix, l: int, q: List[int], iters: int = EQUIL_ITERS):
@@ -104,6 +106,8 @@ class SOCPSetup:
     prim_idx: Optional[np.ndarray] = None
     dual_idx: Optional[np.ndarray] = None
     stats: Dict[str, float] = field(default_factory=dict)
+    plans: Dict[str, object] = field(default_factory=dict)
+    threads: int = DEFAULT_THREADS
 
     @property
     def nt(self):
@@ -123,7 +127,7 @@ def stretch_layout(l: int, q: List[int]):
 
 
 def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
-                      theta: Optional[np.ndarray] = None) -> SOCPSetup:
+                      theta: Optional[np.ndarray] = None, threads: int = DEFAULT_THREADS) -> SOCPSetup:
     if fam.solver_type != 'conic':
         raise ValueError('IPM-CUDA handles the conic canonical form only')
     if batch_params is None:
@@ -265,6 +269,50 @@ def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None
     for dv in fam.duals:
         dual_k.append(n + dv.indices if dv.vec == 'y' else zoff + zmap[dv.indices])
     dual_idx = np.concatenate(dual_k) if dual_k else np.zeros(0, int)
+    # ---- gather plans (cvxpygen_b200/offline/gather.py): every sparse phase of the kernel in owner-writes form
+    assert nk < 2047 and NS < 65535 and len(ag_val) < 65535
+    # (a) products with the constant off-diagonal part of K, rows in k order: entry = (index into ag, source k)
+    mv_rows = [[] for _ in range(nk)]
+    for e, (r, c_) in enumerate(zip(mr_t, mr_s)):
+        mv_rows[int(r)].append((int(c_), e)); mv_rows[int(c_)].append((int(r), e))
+    plan_mv = _gather.GatherPlan(T=threads, nfields=2, tbits=11, null_entry=(len(ag_val), 0))
+    _gather.add_phase(plan_mv, [(k, 0, [(e, src) for src, e in sorted(mv_rows[k])]) for k in range(nk)])
+    # (b) forward substitution: phase 0 scales the leaves, phase lv pulls row k from the columns below, the last phase
+    #     (flag 1) collects the tail rows;  entry = (slot of S, source k)
+    fw_rows = {}
+    for t_, s_, sl in zip(fw[:, 1], fw[:, 2], fw[:, 3]):
+        fw_rows.setdefault(int(t_), []).append((int(sl), int(s_)))
+    plan_fw = _gather.GatherPlan(T=threads, nfields=2, tbits=11, null_entry=(NS, 0))
+    for lv in range(nlw):
+        ks = [int(perm[pos]) for pos in range(lev_lo[lv], lev_lo[lv + 1])]
+        _gather.add_phase(plan_fw, [(k, 0, sorted(fw_rows.get(k, []), key=lambda x: inv[x[1]])) for k in ks])
+    _gather.add_phase(plan_fw, [(int(k), 1, sorted(fw_rows.get(int(k), []), key=lambda x: inv[x[1]])) for k in perm[t0:]])
+    # (c) backward substitution, wide levels from the top: column k pulls from the rows below it
+    bw_cols = {}
+    for sl, (t_, s_) in enumerate(zip(bw_t, bw_s)):
+        bw_cols.setdefault(int(t_), []).append((sl, int(s_)))
+    plan_bw = _gather.GatherPlan(T=threads, nfields=2, tbits=11, null_entry=(NS, 0))
+    for lv in range(nlw - 1, -1, -1):
+        ks = [int(perm[pos]) for pos in range(lev_lo[lv], lev_lo[lv + 1])]
+        _gather.add_phase(plan_bw, [(k, 0, sorted(bw_cols[k], key=lambda x: inv[x[1]])) for k in ks if k in bw_cols])
+    # (d) numeric factorisation: phase lv-1 completes the columns of level lv (flag 1 = a wide column's diagonal: the
+    #     pivot is taken at commit), the last phase the dense tail block;  entry = (slot a, slot b, diagonal slot of the
+    #     source column -- it holds 1/d once the column is complete --, 0)
+    plan_ops = _gather.GatherPlan(T=threads, nfields=4, tbits=16, null_entry=(NS, NS, NS, 0))
+    for lv in range(1, nlw + 1):
+        o = ops[op_lo[lv]:op_lo[lv + 1]]
+        rows_ = {}
+        for _, tgt, a_, b_, kj in o:
+            rows_.setdefault(int(tgt), []).append((int(a_), int(b_), DG0 + int(kj), 0))
+        rl = []
+        for tgt in sorted(rows_):
+            is_diag = DG0 <= tgt < DG0 + nk
+            wide = is_diag and inv[tgt - DG0] < t0
+            rl.append((tgt, 1 if wide else 0, rows_[tgt]))
+        if lv < nlw:                    # every column of a level >= 1 has a child, hence an update of its diagonal
+            have = {t_ for t_, f_, _ in rl if f_}
+            assert have == {DG0 + int(perm[pos]) for pos in range(lev_lo[lv], lev_lo[lv + 1])}
+        _gather.add_phase(plan_ops, rl)
     T = dict(mr_t=mr_t, mr_s=mr_s, ag_val=ag_val, fw_t=fw[:, 1], fw_s=fw[:, 2], fw_slot=fw[:, 3],
              bw_t=np.array(bw_t, dtype=np.int64), bw_s=np.array(bw_s, dtype=np.int64), socv=np.array(socv, dtype=np.int64),
              socu=np.array(socu, dtype=np.int64), Sbase=Sbase, ops=ops[:, 1:], tail_k=perm[t0:], cbh_base=base,
@@ -273,10 +321,12 @@ def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None
     LR = dict(op_lo=op_lo, fw_lo=fw_lo, bw_lo=bw_lo, lev_lo=lev_lo)
     D = dict(N=n, P=p, M=m, L=l, NSOC=nsoc, MT=mt, NK=nk, ZOFF=zoff, NW=NW, DG0=DG0, TT0=TT0, NS=NS, NT=nt, NLW=nlw,
              NNZM=len(ag_val), NOPS=len(ops), NFW=len(fw), NPB=npb, NMAP=len(mv_), NPRIM=len(prim_idx),
-             NDUAL=len(dual_idx), QTOT=sum(d - 1 for d in q), IS_MAX=int(fam.is_maximization), NNZA=int(A_eq.nnz))
+             NDUAL=len(dual_idx), QTOT=sum(d - 1 for d in q), IS_MAX=int(fam.is_maximization), NNZA=int(A_eq.nnz),
+             THREADS=threads)
     st = SOCPSetup(family=fam, batch_params=list(batch_params), n=n, p=p, m=m, l=l, q=q, mt=mt, nk=nk, npb=npb, xe=xe,
                    Ae=Ae, Ge=Ge, A_eq=A_eq, G_eq=G_eq, perm=perm, pos_level=level, n_wide_levels=nlw, t0=t0, tables=T,
-                   defines=D, level_ranges=LR, prim_idx=prim_idx, dual_idx=dual_idx)
+                   defines=D, level_ranges=LR, prim_idx=prim_idx, dual_idx=dual_idx,
+                   plans=dict(mv=plan_mv, fw=plan_fw, bw=plan_bw, ops=plan_ops), threads=threads)
     st.stats = dict(nnz_L=NW + nt * (nt - 1) // 2, n_levels=int(level.max()) + 1, n_wide_levels=nlw, tail=nt,
                     factor_ops=len(ops), d_const=d_const)
     _pack(st, d_const)
@@ -286,50 +336,67 @@ def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None
 # ----------------------------------------------------------------------------------------------------------------------
 def _pack(st: SOCPSetup, d_const: float):
     """Two byte strings + the offsets the kernel needs (emitted as #defines into the family header):
-       smem blob  = [f64: ag_val] [u16: mr_t mr_s fw_t fw_s fw_slot bw_t bw_s socv socu tail_k]   (staged per CTA)
-       gmem blob  = [f64: Sbase cbh_base unscale map_v] [i32: map_t map_p prim_idx dual_idx] [u16 x4: ops]"""
-    T, D = st.tables, st.defines
+       smem blob  = [f64: ag_val, 0] [u32: entries of the mv, fw, bw plans] [u16: their descriptors, socv socu tail_k perm]
+       gmem blob  = [f64: Sbase cbh_base unscale map_v] [i32: map_t map_p prim_idx dual_idx]
+                    [u64: entries of the factorisation plan] [u32: its descriptors]                (staged per CTA / read in place)"""
+    T, D, PL = st.tables, st.defines, st.plans
 
-    def cat(parts, dtype, align=8):
+    def cat(parts, dtype):
         offs, chunks, pos = {}, [], 0
         for name, arr in parts:
             a = np.ascontiguousarray(np.asarray(arr).astype(dtype))
             offs[name] = pos
             chunks.append(a); pos += a.size
         return offs, (np.concatenate(chunks) if chunks else np.zeros(0, dtype))
+
+    def pack_entries(plan):
+        e = plan.entry_array().astype(np.uint64)
+        w = np.zeros(e.shape[0], dtype=np.uint64)
+        for f in range(plan.nfields):
+            w |= e[:, f] << np.uint64(16 * f)
+        return w
     # shared-memory blob
-    fo, f64 = cat([('ag_val', T['ag_val'])], np.float64)
-    names16 = ['mr_t', 'mr_s', 'fw_t', 'fw_s', 'fw_slot', 'bw_t', 'bw_s', 'socv', 'socu', 'tail_k', 'perm']
+    f64 = np.r_[T['ag_val'], 0.0]
+    eo, e32 = cat([(nm, pack_entries(PL[nm])) for nm in ('mv', 'fw', 'bw')], np.uint32)
+    names16 = ['socv', 'socu', 'tail_k', 'perm']
     for nm in names16:
         a = T[nm]
         assert a.size == 0 or (a.min() >= 0 and a.max() < 65536), nm
-    ho, u16 = cat([(nm, T[nm]) for nm in names16], np.uint16)
+    ho, u16 = cat([('mv_d', PL['mv'].desc_array()), ('fw_d', PL['fw'].desc_array()), ('bw_d', PL['bw'].desc_array())] +
+                  [(nm, T[nm]) for nm in names16], np.uint16)
     sm = f64.tobytes()
+    u32_off = len(sm)
+    sm += e32.tobytes()
     u16_off = len(sm)
     sm += u16.tobytes()
     sm += b'\0' * ((-len(sm)) % 16)
-    D['SB_BYTES'] = len(sm); D['SB_U16_OFF'] = u16_off
-    for nm in names16:
-        D['H_' + nm.upper()] = ho[nm]
+    D['SB_BYTES'] = len(sm); D['SB_U32_OFF'] = u32_off; D['SB_U16_OFF'] = u16_off
+    for nm in ('mv', 'fw', 'bw'):
+        D['E_' + nm.upper()] = eo[nm]
+    for nm, o in ho.items():
+        D['H_' + nm.upper()] = o
     # global blob
     go, g64 = cat([('Sbase', T['Sbase']), ('cbh_base', T['cbh_base']), ('unscale', T['unscale']), ('map_v', T['map_v'])], np.float64)
     io, i32 = cat([('map_t', T['map_t']), ('map_p', T['map_p']), ('prim_idx', T['prim_idx']), ('dual_idx', T['dual_idx'])], np.int32)
-    ops = np.ascontiguousarray(T['ops'].astype(np.uint16))
-    assert T['ops'].size == 0 or T['ops'].max() < 65536
     gm = g64.tobytes()
     i32_off = len(gm)
     gm += i32.tobytes()
-    gm += b'\0' * ((-len(gm)) % 8)
-    ops_off = len(gm)
-    gm += ops.tobytes()
     gm += b'\0' * ((-len(gm)) % 16)
-    D['GB_BYTES'] = len(gm); D['GB_I32_OFF'] = i32_off; D['GB_OPS_OFF'] = ops_off
+    ops_off = len(gm)
+    gm += pack_entries(PL['ops']).astype(np.uint64).tobytes()
+    opd_off = len(gm)
+    gm += PL['ops'].desc_array().astype(np.uint32).tobytes()
+    gm += b'\0' * ((-len(gm)) % 16)
+    D['GB_BYTES'] = len(gm); D['GB_I32_OFF'] = i32_off; D['GB_OPS_OFF'] = ops_off; D['GB_OPD_OFF'] = opd_off
     for nm, o in go.items():
         D['G_' + nm.upper()] = o
     for nm, o in io.items():
         D['GI_' + nm.upper()] = o
     st.smem_blob, st.gmem_blob = sm, gm
     st.stats['smem_blob_bytes'] = len(sm); st.stats['gmem_blob_bytes'] = len(gm)
+    for nm, pl in PL.items():
+        st.stats[f'rounds_{nm}'] = pl.n_rounds
+        st.stats[f'pad_{nm}'] = len(pl.entries)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -346,53 +413,60 @@ def fill_slots(st: SOCPSetup, zdiag: np.ndarray, socv_vals=None, socu_vals=None)
     return S
 
 
-def emulate_factor(st: SOCPSetup, S: np.ndarray, sign: np.ndarray, eps=1e-13, delta=2e-7):
-    T, D, LR = st.tables, st.defines, st.level_ranges
-    S = S.copy(); Dinv = np.zeros(D['NK'])
-    nlw, nt, t0 = D['NLW'], D['NT'], st.t0
-    ops = T['ops']
+def _inv_pivot(d, sg, eps, delta):
+    return 1.0 / (sg * delta if sg * d <= eps else d)
 
-    def pivots(ks):
-        d = S[D['DG0'] + ks]
-        d = np.where(sign[ks] * d <= eps, sign[ks] * delta, d)
-        Dinv[ks] = 1.0 / d
-    for lv in range(nlw + 1):
-        lo, hi = LR['op_lo'][lv], LR['op_lo'][lv + 1]
-        o = ops[lo:hi]
-        if len(o):
-            np.subtract.at(S, o[:, 0], S[o[:, 1]] * S[o[:, 2]] * Dinv[o[:, 3]])
-        if lv < nlw:
-            pivots(st.perm[LR['lev_lo'][lv]:LR['lev_lo'][lv + 1]])
-    tk = T['tail_k']
+
+def emulate_factor(st: SOCPSetup, S: np.ndarray, sign: np.ndarray, eps=1e-13, delta=2e-7):
+    """The kernel's numeric factorisation run from the gather plans: returns the slot array (one extra zero slot; inverse
+    pivots in the diagonal slots, inv(L_tail) in the tail block) and, for convenience, the inverse pivots in k order."""
+    D, LR, plan = st.defines, st.level_ranges, st.plans['ops']
+    DG0, TT0, nlw, nt = D['DG0'], D['TT0'], D['NLW'], D['NT']
+    S = np.r_[S, 0.0]
+    for k in st.perm[LR['lev_lo'][0]:LR['lev_lo'][1]]:
+        S[DG0 + k] = _inv_pivot(S[DG0 + k], sign[k], eps, delta)
+
+    def commit(t, flag, acc):
+        v = S[t] - acc
+        S[t] = _inv_pivot(v, sign[t - DG0], eps, delta) if flag else v
+    for lv in range(1, nlw + 1):
+        _gather.run_phase(plan, lv - 1, lambda e: S[e[0]] * S[e[1]] * S[e[2]], commit)
+    tk = st.tables['tail_k']
+    B = S[TT0:TT0 + nt * nt].reshape(nt, nt)
+    dv = np.zeros(nt)
     for j in range(nt):
-        pivots(tk[j:j + 1])
-        dj = Dinv[tk[j]]
+        dv[j] = _inv_pivot(S[DG0 + tk[j]], sign[tk[j]], eps, delta)
         for i in range(j + 1, nt):
-            sij = S[D['TT0'] + i * nt + j]
+            sij = B[i, j]
             for k in range(j + 1, i):
-                S[D['TT0'] + i * nt + k] -= sij * S[D['TT0'] + k * nt + j] * dj
-            S[D['DG0'] + tk[i]] -= sij * sij * dj
-    return S, Dinv
+                B[i, k] -= sij * B[k, j] * dv[j]
+            S[DG0 + tk[i]] -= sij * sij * dv[j]
+    Lt = np.tril(B, -1) * dv[None, :] + np.eye(nt)
+    X = np.linalg.inv(Lt) if nt else Lt
+    S[DG0 + tk] = dv
+    B[np.tril_indices(nt, -1)] = X[np.tril_indices(nt, -1)]
+    S[TT0:TT0 + nt * nt] = B.ravel()
+    return S, S[DG0:DG0 + D['NK']].copy()
 
 
 def emulate_solve(st: SOCPSetup, S: np.ndarray, Dinv: np.ndarray, rhs: np.ndarray) -> np.ndarray:
-    T, D, LR = st.tables, st.defines, st.level_ranges
+    """The kernel's ldl_solve from the gather plans (forward with the D-solve folded in, tail by inv(L_tail), backward)."""
+    D = st.defines
+    DG0, TT0, nlw, nt = D['DG0'], D['TT0'], D['NLW'], D['NT']
     u = rhs.astype(float).copy()
-    nlw, nt = D['NLW'], D['NT']
-    for lv in range(1, nlw + 1):
-        lo, hi = LR['fw_lo'][lv], LR['fw_lo'][lv + 1]
-        t, s, sl = T['fw_t'][lo:hi], T['fw_s'][lo:hi], T['fw_slot'][lo:hi]
-        np.subtract.at(u, t, S[sl] * Dinv[s] * u[s])
-    tk = T['tail_k']
-    for j in range(nt):
-        for i in range(j + 1, nt):
-            u[tk[i]] -= S[D['TT0'] + i * nt + j] * Dinv[tk[j]] * u[tk[j]]
-    x = u * Dinv
-    for j in range(nt - 1, -1, -1):
-        for i in range(j + 1, nt):
-            x[tk[j]] -= S[D['TT0'] + i * nt + j] * Dinv[tk[j]] * x[tk[i]]
-    for lv in range(nlw - 1, -1, -1):
-        lo, hi = LR['bw_lo'][lv], LR['bw_lo'][lv + 1]
-        t, s = T['bw_t'][lo:hi], T['bw_s'][lo:hi]
-        np.subtract.at(x, t, S[lo:hi] * Dinv[t] * x[s])
-    return x
+
+    def fw_commit(k, tail, acc):
+        v = u[k] - acc
+        u[k] = v if tail else v * S[DG0 + k]
+    for lv in range(nlw + 1):
+        _gather.run_phase(st.plans['fw'], lv, lambda e: S[e[0]] * u[e[1]], fw_commit)
+    tk = st.tables['tail_k']
+    X = np.tril(S[TT0:TT0 + nt * nt].reshape(nt, nt), -1) + np.eye(nt)
+    w = (X @ u[tk]) * S[DG0 + tk]
+    u[tk] = X.T @ w
+
+    def bw_commit(k, _, acc):
+        u[k] -= S[DG0 + k] * acc
+    for lv in range(nlw):
+        _gather.run_phase(st.plans['bw'], lv, lambda e: S[e[0]] * u[e[1]], bw_commit)
+    return u

@@ -32,7 +32,7 @@ STATUS_STRINGS = {1: 'solved', 2: 'solved inaccurate', 3: 'primal infeasible ina
 class CpgB200Settings(C.Structure):
     _fields_ = [('max_iter', C.c_int), ('check_termination', C.c_int), ('scaled_termination', C.c_int),
                 ('warm_start', C.c_int), ('adaptive_rho', C.c_int), ('adaptive_rho_interval', C.c_int),
-                ('scaling', C.c_int), ('pad_', C.c_int),
+                ('scaling', C.c_int), ('host_zero_copy', C.c_int),
                 ('eps_abs', C.c_double), ('eps_rel', C.c_double), ('eps_prim_inf', C.c_double),
                 ('eps_dual_inf', C.c_double), ('alpha', C.c_double), ('adaptive_rho_tolerance', C.c_double)]
 
@@ -44,7 +44,7 @@ class CpgB200Dims(C.Structure):
 
 # settings the reference exposes for OSQP and their cvxpy aliases (cvxpygen/solvers/osqp.py:102-115)
 SETTING_ALIASES = {'warm_starting': 'warm_start'}
-READONLY_SETTINGS = ('scaling', 'pad_')
+READONLY_SETTINGS = ('scaling',)
 
 
 class Module:

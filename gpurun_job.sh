@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python tools/sweep_variants.py run 2>&1 | tail -5
-python tools/sweep_batch.py 2>&1 | tail -5 | tee gpurun_out/sweep_batch.jsonl
+for T in 384 512; do
+timeout 300 python tools/bench_socp.py --code-dir tools/_variants/socp_T$T --batch 20000 --steps 2 --warmup 1 --cpu-sample 0 2>&1 | tail -1 | tee gpurun_out/socp_bench_T$T.log
+done

@@ -60,7 +60,8 @@ typedef struct {
   int adaptive_rho;           /* 1    */
   int adaptive_rho_interval;  /* 0 = 4*check_termination, as OSQP without a timer (osqp.c:267-279) */
   int scaling;                /* read-only: number of Ruiz iterations used at generation time */
-  int pad_;
+  int host_zero_copy;         /* 1: cpg_solve_batch_host lets the kernels store result rows straight into PINNED host
+                                 buffers (posted PCIe writes overlapping the solves); 0 or pageable memory: staging + D2H */
   double eps_abs, eps_rel;            /* 1e-3 */
   double eps_prim_inf, eps_dual_inf;  /* 1e-4 */
   double alpha;                       /* 1.6  */

@@ -6,6 +6,7 @@
 #include "ipm_kernel.cuh"
 
 extern "C" int ipm_emu_smem_bytes() { return int(cpgipm::SMEM_BYTES); }
+extern "C" long ipm_emu_count(int i) { return cpgipm::g_count[i]; }   // 0 ldl solves, 1 factorisations, 2 barriers, 3 KKT solves
 
 extern "C" int ipm_emu_solve(const unsigned char* sblob, const unsigned char* gblob, int B, const double* params,
                              double* prim, double* dual, double* x, double* y, double* z, double* s,
@@ -13,8 +14,8 @@ extern "C" int ipm_emu_solve(const unsigned char* sblob, const unsigned char* gb
   using namespace cpgipm;
   std::vector<double> raw(SMEM_BYTES / 8 + 2, 0.0);
   unsigned char* base = reinterpret_cast<unsigned char*>(raw.data());
-  std::memcpy(reinterpret_cast<double*>(base) + O_AG, sblob, size_t(NNZM) * 8);
-  std::memcpy(reinterpret_cast<double*>(base) + O_F64_END, sblob + IPM_SB_U16_OFF, size_t(U16_COUNT) * 2);
+  std::memcpy(reinterpret_cast<double*>(base) + O_AG, sblob, size_t(NNZM + 1) * 8);
+  std::memcpy(reinterpret_cast<double*>(base) + O_F64_END, sblob + IPM_SB_U32_OFF, size_t(U32_COUNT) * 4 + size_t(U16_COUNT) * 2);
   std::vector<double> best(NK + MT);
   Solver sv;
   sv.sm = make_sm(base); sv.gm = make_gm(gblob); sv.rb = 0;

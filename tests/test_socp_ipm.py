@@ -62,6 +62,34 @@ def test_structure_of_the_schedule(setup):
     assert np.all(lev_of_k[T['bw_s']] > lev_of_k[T['bw_t']])
 
 
+def test_gather_plan_sums_every_row_once():
+    """cvxpygen_b200.offline.gather: ragged rows (empty, single, longer than a warp's quota) dealt over 64 threads; every
+    target is committed exactly once with the sum of its entries, flags and group alignment survive the packing."""
+    from cvxpygen_b200.offline import gather
+    rs = np.random.RandomState(3)
+    vals = rs.randn(500)
+    sizes = [0, 1, 2, 3, 7, 40, 150, 0, 5, 1] * 9
+    plan = gather.GatherPlan(T=64, nfields=2, tbits=11, null_entry=(len(vals), 0))
+    rows = []
+    for t, c in enumerate(sizes):
+        rows.append((t, t % 2, [(int(i), int(rs.randint(0, 100))) for i in rs.randint(0, len(vals), c)]))
+    gather.add_phase(plan, rows[:30]); gather.add_phase(plan, []); gather.add_phase(plan, rows[30:])
+    assert [p.round_hi - p.round_lo for p in plan.phases][1] == 0
+    v = np.r_[vals, 0.0]
+    got = {}
+
+    def commit(t, flag, acc):
+        assert t not in got and flag == t % 2
+        got[t] = acc
+    for ph in range(3):
+        gather.run_phase(plan, ph, lambda e: v[e[0]], commit)
+    assert sorted(got) == list(range(len(sizes)))
+    for t, _, ent in rows:
+        assert abs(got[t] - sum(vals[i] for i, _ in ent)) < 1e-12
+    assert plan.desc_array().dtype == np.uint16 and plan.entry_array().shape[1] == 2
+    assert len(plan.wr_base) == plan.n_rounds * 2 and max(plan.wr_shuf) >= 1      # the long rows are split over lanes
+
+
 def test_table_driven_factor_and_solve_match_dense_algebra(setup):
     D, T = setup.defines, setup.tables
     rs = np.random.RandomState(0)
@@ -234,6 +262,12 @@ def test_gpu_portfolio_matches_compiled_reference_on_fresh_batch():
     a = rng.standard_normal((B, 100)) * rng.uniform(0.2, 2.0, (B, 1))
     wp = np.abs(1 / 100 + 0.02 * rng.standard_normal((B, 100)))
     ref = _ref_batch(fam, a, wp)
+    # rounding stability of the REFERENCE itself: the same batch with the parameters moved in the 13th digit.  Duals of
+    # (nearly) degenerate rows are determined to ~1e-4 only -- the reference's own answer moves by that much -- so the 1e-5
+    # bar on z is asserted where the reference reproduces itself to 1e-6, and 1e-3 everywhere
+    ref2 = _ref_batch(fam, a * (1 + 1e-13 * rng.standard_normal(a.shape)), wp)
+    stable = (ref2['iter'] == ref['iter']) & np.array([_rel(ref2['z'][k], ref['z'][k]) < 1e-6 for k in range(B)])
+    assert stable.mean() > 0.9
     m = standard.load(NAME)
     r = m.solve_batch({'a': a, 'w_prev': wp}, return_canonical=True)
     assert np.array_equal(r.cpg_info.status, ref['exitflag'])
@@ -241,7 +275,8 @@ def test_gpu_portfolio_matches_compiled_reference_on_fresh_batch():
     same = r.cpg_info.iter == ref['iter']
     for k in np.nonzero(same)[0]:
         assert _rel(r.sol_x[k], ref['x'][k]) < RTOL_PRIMAL, k
-        assert _rel(r.sol_y[k], ref['y'][k]) < RTOL_PRIMAL and _rel(r.sol_z[k], ref['z'][k]) < RTOL_DUAL, k
+        assert _rel(r.sol_y[k], ref['y'][k]) < RTOL_PRIMAL, k
+        assert _rel(r.sol_z[k], ref['z'][k]) < (RTOL_DUAL if stable[k] else 1e-3), k
     # an instance that stops one iteration earlier / later still agrees to the solver tolerance on the user variables
     assert _rel(r.cpg_prim['w'], ref['x'][:, :100]) < 1e-5
     assert np.allclose(r.cpg_info.obj_val, -ref['pcost'], rtol=0, atol=1e-7)
@@ -261,8 +296,16 @@ def test_gpu_portfolio_full_batch_properties():
     out = m.solve_batch_device(P, return_canonical=True)
     torch.cuda.synchronize()
     st = out.status.cpu().numpy()
-    assert (st == 0).all()
-    x, y, z, s = (t.cpu().numpy() for t in (out.sol_x, out.sol_y, out.sol_z, out.sol_s))
+    # a handful of instances per 10^5 end "close to optimal" (exit flag 10, reduced tolerances) in the reference as well:
+    # they must be rare and carry the reference's own exit flag; the optimality conditions below are asserted on the rest
+    odd = np.nonzero(st != 0)[0]
+    assert odd.size <= B // 2000 and np.isin(st[odd], (0, 10)).all()
+    if odd.size and ref_ecos.available():
+        ref = _ref_batch(fam, a[odd], wp[odd])
+        assert np.array_equal(ref['exitflag'], st[odd])
+    ok = st == 0
+    x, y, z, s = (t.cpu().numpy()[ok] for t in (out.sol_x, out.sol_y, out.sol_z, out.sol_s))
+    a, wp, B_all, B = a[ok], wp[ok], B, int(ok.sum())
     A, G = fam.canon_matrix('A'), fam.canon_matrix('G')
     c0, b0, h = fam.canon_data('c'), fam.canon_data('b'), fam.canon_data('h')
     Cb = np.tile(c0, (B, 1)); Cb[:, :100] = -a
@@ -279,4 +322,4 @@ def test_gpu_portfolio_full_batch_properties():
     # the same batch twice gives the same answer to rounding (accumulation order of shared-memory atomics may differ)
     out2 = m.solve_batch_device(P, return_canonical=True)
     torch.cuda.synchronize()
-    assert (out2.iter == out.iter).all() and _rel(out2.sol_x.cpu().numpy(), x) < 1e-9
+    assert (out2.iter == out.iter).all() and _rel(out2.sol_x.cpu().numpy()[ok], x) < 1e-9

@@ -18,10 +18,15 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=1)
     ap.add_argument('--cpu-sample', type=int, default=2048)
+    ap.add_argument('--code-dir', default=None, help='a generated IPM-CUDA directory (default: the standard portfolio family)')
     args = ap.parse_args()
     import torch
     from cvxpygen_b200 import standard, families
-    m = standard.load('portfolio_socp_100_10')
+    if args.code_dir:
+        from cvxpygen_b200 import runtime
+        m = runtime.load(args.code_dir)
+    else:
+        m = standard.load('portfolio_socp_100_10')
     B = args.batch
     rng = np.random.default_rng(3)
     a = rng.standard_normal((B, 100)); wp = np.abs(1 / 100 + 0.01 * rng.standard_normal((B, 100)))
