@@ -34,12 +34,14 @@
 #include <cstring>
 #include <vector>
 #define IPM_FN inline
+#define IPM_NOINLINE inline
 #define IPM_CONST static const
 namespace cpgipm { static long g_count[8] = {0, 0, 0, 0, 0, 0, 0, 0}; }     // emulation statistics: solves, factors, barriers
 #define IPM_COUNT(i) (++cpgipm::g_count[i])
 #else
 #define IPM_FN __device__ __forceinline__
-#define IPM_CONST __device__ const
+#define IPM_NOINLINE __device__ __noinline__
+#define IPM_CONST __constant__ const
 #define IPM_COUNT(i) ((void)0)
 #endif
 
@@ -98,11 +100,43 @@ constexpr int U16_COUNT = (IPM_SB_BYTES - IPM_SB_U16_OFF) / 2;
 constexpr size_t SMEM_BYTES = size_t(O_F64_END) * 8 + size_t(U32_COUNT) * 4 + size_t(U16_COUNT) * 2 + 16;
 enum { SC_ETA2 = 0, SC_ETA, SC_A, SC_D1, SC_U0, SC_U1, SC_V1, SC_W };
 
+// Shared-memory view.  On the device every array sits at a compile-time offset of the dynamic shared-memory window, so an
+// access costs no pointer register; the host emulation carries the base of a heap buffer instead.
+#ifndef CPG_IPM_HOST_EMU
+extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
 struct Sm {
-  double *xyz, *cbh, *sv, *lam, *v, *w, *q, *sc, *S, *rhs, *px, *e, *sol1, *rz, *dsw, *red, *cone, *ce, *tw, *ag;
-  const uint32_t *mv_e, *fw_e, *bw_e;
-  const uint16_t *mv_d, *fw_d, *bw_d, *socv, *socu, *tail_k, *perm;
-  int* flag;
+#ifdef CPG_IPM_HOST_EMU
+  unsigned char* base_;
+  IPM_FN unsigned char* base() const { return base_; }
+#else
+  IPM_FN unsigned char* base() const { return smem_raw; }
+#endif
+  IPM_FN double* f64(int off) const { return reinterpret_cast<double*>(base()) + off; }
+  IPM_FN const uint32_t* u32(int off) const { return reinterpret_cast<const uint32_t*>(f64(O_F64_END)) + off; }
+  IPM_FN const uint16_t* u16(int off) const { return reinterpret_cast<const uint16_t*>(u32(U32_COUNT)) + off; }
+  IPM_FN double* xyz() const { return f64(O_XYZ); }   IPM_FN double* cbh() const { return f64(O_CBH); }
+  IPM_FN double* sv() const { return f64(O_SV); }     IPM_FN double* lam() const { return f64(O_LAM); }
+  IPM_FN double* v() const { return f64(O_V); }       IPM_FN double* w() const { return f64(O_W); }
+  IPM_FN double* q() const { return f64(O_Q); }       IPM_FN double* sc() const { return f64(O_SC); }
+  IPM_FN double* S() const { return f64(O_S); }       IPM_FN double* rhs() const { return f64(O_RHS); }
+  IPM_FN double* px() const { return f64(O_PX); }     IPM_FN double* e() const { return f64(O_E); }
+  IPM_FN double* sol1() const { return f64(O_SOL1); } IPM_FN double* rz() const { return f64(O_RZ); }
+  IPM_FN double* dsw() const { return f64(O_DSW); }   IPM_FN double* red() const { return f64(O_RED); }
+  IPM_FN double* cone() const { return f64(O_CONE); } IPM_FN double* ce() const { return f64(O_CE); }
+  IPM_FN double* tw() const { return f64(O_TW); }     IPM_FN double* ag() const { return f64(O_AG); }
+  IPM_FN const uint32_t* mv_e() const { return u32(IPM_E_MV); }
+  IPM_FN const uint32_t* fw_e() const { return u32(IPM_E_FW); }
+  IPM_FN const uint32_t* bw_e() const { return u32(IPM_E_BW); }
+  IPM_FN const uint16_t* mv_d() const { return u16(IPM_H_MV_D); }
+  IPM_FN const uint16_t* fw_d() const { return u16(IPM_H_FW_D); }
+  IPM_FN const uint16_t* bw_d() const { return u16(IPM_H_BW_D); }
+  IPM_FN const uint16_t* socv() const { return u16(IPM_H_SOCV); }
+  IPM_FN const uint16_t* socu() const { return u16(IPM_H_SOCU); }
+  IPM_FN const uint16_t* tail_k() const { return u16(IPM_H_TAIL_K); }
+  IPM_FN const uint16_t* perm() const { return u16(IPM_H_PERM); }
+  IPM_FN const uint16_t* l0mask() const { return u16(IPM_H_L0MASK); }
+  IPM_FN int* flag() const { return reinterpret_cast<int*>(const_cast<uint16_t*>(u16(U16_COUNT + (U16_COUNT & 1)))); }
 };
 
 struct Gm {                 // global constant tables
@@ -121,22 +155,6 @@ IPM_FN Gm make_gm(const unsigned char* g) {
   r.op_e = reinterpret_cast<const unsigned long long*>(g + IPM_GB_OPS_OFF);
   r.op_d = reinterpret_cast<const uint32_t*>(g + IPM_GB_OPD_OFF);
   return r;
-}
-
-IPM_FN Sm make_sm(unsigned char* base) {
-  Sm s;
-  double* f = reinterpret_cast<double*>(base);
-  s.xyz = f + O_XYZ; s.cbh = f + O_CBH; s.sv = f + O_SV; s.lam = f + O_LAM; s.v = f + O_V; s.w = f + O_W; s.q = f + O_Q;
-  s.sc = f + O_SC; s.S = f + O_S; s.rhs = f + O_RHS; s.px = f + O_PX; s.e = f + O_E;
-  s.sol1 = f + O_SOL1; s.rz = f + O_RZ; s.dsw = f + O_DSW; s.red = f + O_RED; s.cone = f + O_CONE; s.ce = f + O_CE;
-  s.tw = f + O_TW; s.ag = f + O_AG;
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(f + O_F64_END);
-  s.mv_e = w + IPM_E_MV; s.fw_e = w + IPM_E_FW; s.bw_e = w + IPM_E_BW;
-  const uint16_t* h = reinterpret_cast<const uint16_t*>(w + U32_COUNT);
-  s.mv_d = h + IPM_H_MV_D; s.fw_d = h + IPM_H_FW_D; s.bw_d = h + IPM_H_BW_D;
-  s.socv = h + IPM_H_SOCV; s.socu = h + IPM_H_SOCU; s.tail_k = h + IPM_H_TAIL_K; s.perm = h + IPM_H_PERM;
-  s.flag = reinterpret_cast<int*>(const_cast<uint16_t*>(h + U16_COUNT + (U16_COUNT & 1)));
-  return s;
 }
 
 IPM_FN double safediv(double x, double y) { return y < kEps ? x / kEps : x / y; }
@@ -196,7 +214,7 @@ template <int KS, int KM, class F> IPM_FN void phase_red(Sm& sm, int& rb, double
 #pragma unroll
   for (int k = 0; k < KM; ++k) m[k] = -INFINITY;
   f(tid, s, m);
-  double* buf = sm.red + rb * (NWARP * 16);
+  double* buf = sm.red() + rb * (NWARP * 16);
   rb ^= 1;
 #pragma unroll
   for (int k = 0; k < KS; ++k) { double v = warp_sum(s[k]); if (lane == 0) buf[wid * 16 + k] = v; }
@@ -241,80 +259,97 @@ template <class F> IPM_FN void each_k(int tid, int n, F&& f) { for (int i = tid;
 
 IPM_CONST int kSocSo[NSOC > 0 ? NSOC : 1] = IPM_SOC_SO;      // stretched z offset of each cone
 IPM_CONST int kSocD[NSOC > 0 ? NSOC : 1] = IPM_SOC_D;        // cone sizes
-IPM_CONST int kSocQo[NSOC > 0 ? NSOC : 1] = IPM_SOC_QO;      // offset of q in sm.q
+IPM_CONST int kSocQo[NSOC > 0 ? NSOC : 1] = IPM_SOC_QO;      // offset of q in sm.q()
 IPM_CONST int kSocVo[NSOC > 0 ? NSOC : 1] = IPM_SOC_VO;      // offset in socv
 IPM_CONST int kSocUo[NSOC > 0 ? NSOC : 1] = IPM_SOC_UO;      // offset in socu
 IPM_CONST int kLevLo[NLW + 1] = IPM_LEV_LO;
 
-// ---- gather plans: per (round, warp) entry offset | trip count << 20 | shuffle steps << 28, and the rounds of each phase
-IPM_CONST unsigned kMvWr[] = IPM_MV_WR;   IPM_CONST int kMvPh[] = IPM_MV_PH;
-IPM_CONST unsigned kFwWr[] = IPM_FW_WR;   IPM_CONST int kFwPh[] = IPM_FW_PH;
-IPM_CONST unsigned kBwWr[] = IPM_BW_WR;   IPM_CONST int kBwPh[] = IPM_BW_PH;
-IPM_CONST unsigned kOpWr[] = IPM_OP_WR;   IPM_CONST int kOpPh[] = IPM_OP_PH;
+// ---- gather plans.  Run-time tables: per (round, warp) one word  entry offset | trip count << 20.  Compile-time
+// description (family header): the rounds of each phase and, per round, the longest cell and the deepest butterfly of any
+// warp -- every loop of a round is unrolled to those bounds, so a round is straight-line code.
+IPM_CONST unsigned kMvWr[] = IPM_MV_WR;
+IPM_CONST unsigned kFwWr[] = IPM_FW_WR;
+IPM_CONST unsigned kBwWr[] = IPM_BW_WR;
+IPM_CONST unsigned kOpWr[] = IPM_OP_WR;
+struct MvShape { static constexpr int ph[] = IPM_MV_PH; static constexpr int lmax[] = IPM_MV_LMAX; static constexpr int lmin[] = IPM_MV_LMIN; static constexpr int smax[] = IPM_MV_SMAX; };
+struct FwShape { static constexpr int ph[] = IPM_FW_PH; static constexpr int lmax[] = IPM_FW_LMAX; static constexpr int lmin[] = IPM_FW_LMIN; static constexpr int smax[] = IPM_FW_SMAX; };
+struct BwShape { static constexpr int ph[] = IPM_BW_PH; static constexpr int lmax[] = IPM_BW_LMAX; static constexpr int lmin[] = IPM_BW_LMIN; static constexpr int smax[] = IPM_BW_SMAX; };
+struct OpShape { static constexpr int ph[] = IPM_OP_PH; static constexpr int lmax[] = IPM_OP_LMAX; static constexpr int lmin[] = IPM_OP_LMIN; static constexpr int smax[] = IPM_OP_SMAX; };
 
-// One plan = entry table E (u32: two u16 fields, or u64: up to four), descriptor table D (u16 with an 11-bit target, or
-// u32 with a 16-bit target) and the per-(round, warp) words above.  run(ph, value, commit): for every cell of phase ph
+// entries and descriptors carry BYTE offsets (index * 8) into the f64 arrays: one add-free LDS per operand
+IPM_FN double at(const double* base, unsigned byte_off) { return *reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + byte_off); }
+template <int I> struct IC { static constexpr int value = I; };
+template <int I, int E_, class F> IPM_FN void static_for(F&& f) {
+  if constexpr (I < E_) { f(IC<I>{}); static_for<I + 1, E_>(f); }
+}
+
+// One plan = entry table (u32: two u16 fields, or u64: up to four), descriptor table (u16 with an 11-bit target, or u32
+// with a 16-bit target) and the words above.  run<PH>(value, commit): for every cell of phase PH
 //   acc = sum_j value(entry_j);  butterfly over the cell group;  the group leader calls commit(target, flag, acc).
-template <class E, class D, int TB> struct Plan {
-  const E* ent; const D* desc; const unsigned* wr; const int* ph;
+template <class Shape, class E, class D, int TB> struct Plan {
+  const E* ent; const D* desc; const unsigned* wr;
+  template <int R, class V, class C> IPM_FN void round(V&& value, C&& commit) const {
+    constexpr int LMAX = Shape::lmax[R], LMIN = Shape::lmin[R], SMAX = Shape::smax[R];      // LMIN: shortest warp of the round
 #ifdef CPG_IPM_HOST_EMU
-  template <class V, class C> void run(int phase, V&& value, C&& commit) const {
-    for (int r = ph[phase]; r < ph[phase + 1]; ++r)
-      for (int w = 0; w < NWARP; ++w) {
-        const unsigned m = wr[r * NWARP + w];
-        const int base = int(m & 0xfffffu), len = int((m >> 20) & 0xffu), ns = int(m >> 28);
-        double acc[32]; unsigned d[32]; int g[32];
-        for (int l = 0; l < 32; ++l) {
-          d[l] = desc[r * T + w * 32 + l]; g[l] = 1 << ((d[l] >> TB) & 7u); acc[l] = 0.0;
-          for (int j = 0; j < len; ++j) acc[l] += value(ent[base + j * 32 + l]);
-        }
-        for (int s = 0, o = 1; s < ns; ++s, o <<= 1) {
-          double nx[32];
-          for (int l = 0; l < 32; ++l) nx[l] = o < g[l] ? acc[l] + acc[l ^ o] : acc[l];
-          for (int l = 0; l < 32; ++l) acc[l] = nx[l];
-        }
-        for (int l = 0; l < 32; ++l)
-          if (((d[l] >> (TB + 3)) & 1u) && (l & (g[l] - 1)) == 0) commit(int(d[l] & ((1u << TB) - 1u)), int((d[l] >> (TB + 4)) & 1u), acc[l]);
+    for (int w = 0; w < NWARP; ++w) {
+      const unsigned m = wr[R * NWARP + w];
+      const int base = int(m & 0xfffffu), len = int(m >> 20);
+      double acc[32]; unsigned d[32]; int g[32];
+      for (int l = 0; l < 32; ++l) {
+        d[l] = desc[R * T + w * 32 + l]; g[l] = 1 << ((d[l] >> TB) & 7u); acc[l] = 0.0;
+        for (int j = 0; j < LMAX; ++j) if (j < len) acc[l] += value(ent[base + j * 32 + l]);
       }
-  }
-#else
-  template <class V, class C> IPM_FN void run(int phase, V&& value, C&& commit) const {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int r = ph[phase]; r < ph[phase + 1]; ++r) {
-      const unsigned m = wr[r * NWARP + wid];
-      const unsigned d = desc[r * T + tid];
-      const E* e = ent + (m & 0xfffffu) + lane;
-      const int len = int((m >> 20) & 0xffu), ns = int(m >> 28);
-      double acc = 0.0;
-      int j = 0;
-      for (; j + 4 <= len; j += 4) {              // the four table reads are independent of the arithmetic: issue them first
-        const E e0 = e[j * 32], e1 = e[j * 32 + 32], e2 = e[j * 32 + 64], e3 = e[j * 32 + 96];
-        const double v0 = value(e0), v1 = value(e1), v2 = value(e2), v3 = value(e3);
-        acc += v0; acc += v1; acc += v2; acc += v3;
+      for (int s = 0; s < SMAX; ++s) {
+        const int o = 1 << s;
+        double nx[32];
+        for (int l = 0; l < 32; ++l) nx[l] = o < g[l] ? acc[l] + acc[l ^ o] : acc[l];
+        for (int l = 0; l < 32; ++l) acc[l] = nx[l];
       }
-      for (; j < len; ++j) acc += value(e[j * 32]);
-      const int g = 1 << ((d >> TB) & 7u);
-      for (int s = 0, o = 1; s < ns; ++s, o <<= 1) {
-        const double v = __shfl_xor_sync(0xffffffffu, acc, o);
-        if (o < g) acc += v;
-      }
-      if (((d >> (TB + 3)) & 1u) && (lane & (g - 1)) == 0) commit(int(d & ((1u << TB) - 1u)), int((d >> (TB + 4)) & 1u), acc);
+      for (int l = 0; l < 32; ++l)
+        if (((d[l] >> (TB + 3)) & 1u) && (l & (g[l] - 1)) == 0) commit(int(d[l] & ((1u << TB) - 1u)), int((d[l] >> (TB + 4)) & 1u), acc[l]);
     }
-  }
+#else
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned m = wr[R * NWARP + wid];
+    const unsigned d = desc[R * T + tid];
+    const E* e = ent + (m & 0xfffffu) + lane;
+    const int len = int(m >> 20);                  // warp-uniform
+    double acc = 0.0;
+#pragma unroll
+    for (int j0 = 0; j0 < LMAX; j0 += 8) {         // table reads of a chunk first: they do not depend on the arithmetic
+      E ev[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j0 + j < LMAX && (j0 + j < LMIN || j0 + j < len)) ev[j] = e[(j0 + j) * 32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j0 + j < LMAX && (j0 + j < LMIN || j0 + j < len)) acc += value(ev[j]);
+    }
+    const int g = 1 << ((d >> TB) & 7u);
+#pragma unroll
+    for (int s = 0; s < SMAX; ++s) {
+      const double v = __shfl_xor_sync(0xffffffffu, acc, 1 << s);
+      if ((1 << s) < g) acc += v;
+    }
+    if (((d >> (TB + 3)) & 1u) && (lane & (g - 1)) == 0) commit(int(d & ((1u << TB) - 1u)), int((d >> (TB + 4)) & 1u), acc);
 #endif
+  }
+  template <int PH, class V, class C> IPM_FN void run(V&& value, C&& commit) const {
+    static_for<Shape::ph[PH], Shape::ph[PH + 1]>([&](auto r) { this->template round<decltype(r)::value>(value, commit); });
+  }
 };
-using PlanS = Plan<uint32_t, uint16_t, 11>;                 // tables in shared memory
-using PlanG = Plan<unsigned long long, uint32_t, 16>;       // tables in global memory (read once per factorisation)
+using PlanMv = Plan<MvShape, uint32_t, uint16_t, 11>;             // tables in shared memory
+using PlanFw = Plan<FwShape, uint32_t, uint16_t, 11>;
+using PlanBw = Plan<BwShape, uint32_t, uint16_t, 11>;
+using PlanOp = Plan<OpShape, unsigned long long, uint32_t, 16>;   // tables in global memory (read once per factorisation)
 
 // ----------------------------------------------------------------------------------------------------------------------
 struct Solver {
   Sm sm; Gm gm; IpmSettings stg;
   int rb;                                   // reduction scratch toggle
 
-  IPM_FN PlanS plan_mv() const { return PlanS{sm.mv_e, sm.mv_d, kMvWr, kMvPh}; }
-  IPM_FN PlanS plan_fw() const { return PlanS{sm.fw_e, sm.fw_d, kFwWr, kFwPh}; }
-  IPM_FN PlanS plan_bw() const { return PlanS{sm.bw_e, sm.bw_d, kBwWr, kBwPh}; }
-  IPM_FN PlanG plan_op() const { return PlanG{gm.op_e, gm.op_d, kOpWr, kOpPh}; }
+  IPM_FN PlanMv plan_mv() const { return PlanMv{sm.mv_e(), sm.mv_d(), kMvWr}; }
+  IPM_FN PlanFw plan_fw() const { return PlanFw{sm.fw_e(), sm.fw_d(), kFwWr}; }
+  IPM_FN PlanBw plan_bw() const { return PlanBw{sm.bw_e(), sm.bw_d(), kBwWr}; }
+  IPM_FN PlanOp plan_op() const { return PlanOp{gm.op_e, gm.op_d, kOpWr}; }
 
   IPM_FN double sign_of(int k) const {      // Sign vector of createKKT_U (preproc.c:135-170)
     if (k < N) return 1.0;
@@ -331,52 +366,69 @@ struct Solver {
   // ---- numeric factorisation: S holds the KKT values on entry; on exit the column-scaled factor (S_ij = L_ij D_j), the
   // inverse pivots in the diagonal slots and the inverse of the tail's unit triangle in the tail block
   IPM_FN void tail_factor(int tid);
-  IPM_FN void factor() {
+  IPM_NOINLINE void factor() {
     IPM_COUNT(1);
     phase([&](int tid) {
-      for (int p = kLevLo[0] + tid; p < kLevLo[1]; p += T) { const int k = sm.perm[p]; sm.S[DG0 + k] = inv_pivot(k, sm.S[DG0 + k]); }
+      for (int p = kLevLo[0] + tid; p < kLevLo[1]; p += T) { const int k = sm.perm()[p]; sm.S()[DG0 + k] = inv_pivot(k, sm.S()[DG0 + k]); }
     });
-    const PlanG po = plan_op();
-    for (int lv = 1; lv <= NLW; ++lv) {
-      po.run(lv - 1,
-             [&](unsigned long long e) {
-               return sm.S[unsigned(e) & 0xffffu] * sm.S[unsigned(e >> 16) & 0xffffu] * sm.S[unsigned(e >> 32) & 0xffffu];
-             },
-             [&](int t, int flag, double acc) {
-               const double v = sm.S[t] - acc;
-               sm.S[t] = flag ? inv_pivot(t - DG0, v) : v;
-             });
+    const PlanOp po = plan_op();
+    static_for<0, NLW>([&](auto lv) {
+      po.template run<decltype(lv)::value>(
+          [&](unsigned long long e) {
+            return at(sm.S(), unsigned(e) & 0xffffu) * at(sm.S(), unsigned(e >> 16) & 0xffffu) * at(sm.S(), unsigned(e >> 32) & 0xffffu);
+          },
+          [&](int t, int flag, double acc) {
+            const double v = sm.S()[t] - acc;
+            sm.S()[t] = flag ? inv_pivot(t - DG0, v) : v;
+          });
       sync_phase();
-    }
+    });
     phase([&](int tid) { tail_factor(tid); });
   }
 
   // ---- triangular solves, in place on u (k-space)
+  // value of right-hand-side entry k as ldl_solve expects it: leaves of the elimination tree pre-multiplied by 1/d_k
+  IPM_FN double lead(int k, double b) const { return ((sm.l0mask()[k >> 4] >> (k & 15)) & 1) ? b * sm.S()[DG0 + k] : b; }
   IPM_FN void tail_solve(int tid, double* u);
-  IPM_FN void ldl_solve(double* u) {
+  IPM_NOINLINE void ldl_solve(double* u) {
     IPM_COUNT(0);
-    const PlanS pf = plan_fw(), pb = plan_bw();
+    const PlanFw pf = plan_fw();
+    const PlanBw pb = plan_bw();
     // forward: row k of a wide level becomes D^-1 L^-1 b at once (it is final when its level is done); the tail rows
-    // (flag) only collect the contributions of the wide columns
-    for (int lv = 0; lv <= NLW; ++lv) {
-      pf.run(lv, [&](uint32_t e) { return sm.S[e & 0xffffu] * u[e >> 16]; },
-             [&](int k, int tail, double acc) { const double v = u[k] - acc; u[k] = tail ? v : v * sm.S[DG0 + k]; });
+    // (flag) only collect the contributions of the wide columns.  The leaves (level 0) arrive already scaled: see lead().
+    static_for<1, NLW + 1>([&](auto lv) {
+      pf.template run<decltype(lv)::value>(
+          [&](uint32_t e) { return at(sm.S(), e & 0xffffu) * at(u, e >> 16); },
+          [&](int k, int tail, double acc) { const double v = u[k] - acc; u[k] = tail ? v : v * sm.S()[DG0 + k]; });
       sync_phase();
-    }
+    });
     phase([&](int tid) { tail_solve(tid, u); });
-    for (int lv = 0; lv < NLW; ++lv) {
-      pb.run(lv, [&](uint32_t e) { return sm.S[e & 0xffffu] * u[e >> 16]; },
-             [&](int k, int, double acc) { u[k] -= sm.S[DG0 + k] * acc; });
+    static_for<0, NLW>([&](auto lv) {
+      pb.template run<decltype(lv)::value>(
+          [&](uint32_t e) { return at(sm.S(), e & 0xffffu) * at(u, e >> 16); },
+          [&](int k, int, double acc) { u[k] -= sm.S()[DG0 + k] * acc; });
       sync_phase();
-    }
+    });
   }
 
   // ---- KKT solve with iterative refinement (kkt_solve, kkt.c:87-265); rhs(k) -> out (k-space); returns #refinements
-  template <class RHS> IPM_FN int kkt_solve(RHS&& rhs, double* out, bool isinit, PerThread<PT>& dpx) {
+  // right-hand sides of the KKT systems: the two initialisation solves (ecos.c:300-420), the constant one (RHS1) and
+  // the vector assembled in sm.rhs (affine / combined direction)
+  enum { RHS_INIT_P = 0, RHS_INIT_D, RHS_ONE, RHS_VEC };
+  IPM_FN double rhs_of(int mode, int k) const {
+    if (mode == RHS_VEC) return sm.rhs()[k];
+    const double c = sm.cbh()[k];
+    if (mode == RHS_ONE) return k < N ? -c : c;
+    if (mode == RHS_INIT_P) return k < N ? 0.0 : c;
+    return k < N ? -c : 0.0;
+  }
+  IPM_NOINLINE int kkt_solve(int mode, double* out, bool isinit) {
     IPM_COUNT(3);
+    PerThread<PT> dpx;
+    auto rhs = [&](int k) { return rhs_of(mode, k); };
     double s_[1], m_[1];
     phase_red<0, 1>(sm, rb, s_, m_, [&](int tid, double*, double* m) {
-      each_k(tid, NK, [&](int k) { const double b = rhs(k); out[k] = b; m[0] = fmax(m[0], fabs(b)); });
+      each_k(tid, NK, [&](int k) { const double b = rhs(k); out[k] = lead(k, b); m[0] = fmax(m[0], fabs(b)); });
     });
     const double thr = (1.0 + m_[0]) * kLinsysAcc;
     ldl_solve(out);
@@ -385,8 +437,9 @@ struct Solver {
     for (;;) {
       // error e = b - K out (with the static regularisation written exactly like the reference does): rows outside the
       // second-order cones are completed by the owner of the row in the plan; cone rows get the constant part of K here
-      // and the scaling block from the cone warps (sm.ce), the two are added in the reduction below
-      plan_mv().run(0, [&](uint32_t en) { return sm.ag[en & 0xffffu] * out[en >> 16]; },
+      // and the scaling block from the cone warps (sm.ce()), the two are added in the reduction below
+      double mloc = 0.0;                    // largest |e| among the rows this thread completes
+      plan_mv().run<0>([&](uint32_t en) { return at(sm.ag(), en & 0xffffu) * at(out, en >> 16); },
                     [&](int k, int, double acc) {
                       double e = -acc;
                       if (k < ZOFF + L) {
@@ -394,21 +447,23 @@ struct Solver {
                         double b = rhs(k);
                         if (k < N) b -= kDeltaStat * o;
                         else if (k < ZOFF) b += kDeltaStat * o;
-                        else b += kDeltaStat * o + (isinit ? o : sm.v[k - ZOFF] * o);
+                        else b += kDeltaStat * o + (isinit ? o : sm.v()[k - ZOFF] * o);
                         e += b;
+                        mloc = fmax(mloc, fabs(e));
+                        e = lead(k, e);
                       }
-                      sm.e[k] = e;
+                      sm.e()[k] = e;
                     });
       cones_then_sync([&](int c, const WarpOps& W) {
         const int so = ZOFF + kSocSo[c], d = kSocD[c];
-        double* ce = sm.ce + (kSocSo[c] - L);
+        double* ce = sm.ce() + (kSocSo[c] - L);
         if (isinit) {
           W.each(0, d + 2, [&](int r) {
             const int k = so + r; const double o = out[k];
             ce[r] = r < d ? rhs(k) + (r < d - 1 ? kDeltaStat : -kDeltaStat) * o + o : o;
           });
         } else {
-          const double* q = sm.q + kSocQo[c]; const double* sc = sm.sc + 8 * c;
+          const double* q = sm.q() + kSocQo[c]; const double* sc = sm.sc() + 8 * c;
           const double e2 = sc[SC_ETA2], d1 = sc[SC_D1], u0 = sc[SC_U0], u1 = sc[SC_U1], v1 = sc[SC_V1];
           const double x1 = out[so], x3 = out[so + d], x4 = out[so + d + 1];
           const double qtx2 = W.sum(0, d - 1, [&](int i) { return q[i] * out[so + 1 + i]; });
@@ -425,9 +480,11 @@ struct Solver {
         }
       });
       phase_red<0, 1>(sm, rb, s_, m_, [&](int tid, double*, double* m) {
-        each_k(tid, NK, [&](int k) {
-          double v = sm.e[k];
-          if (k >= ZOFF + L) { v += sm.ce[k - (ZOFF + L)]; sm.e[k] = v; }
+        m[0] = fmax(m[0], mloc);
+        each_k(tid, NCR, [&](int i) {
+          const int k = ZOFF + L + i;
+          const double v = sm.e()[k] + sm.ce()[i];
+          sm.e()[k] = lead(k, v);
           m[0] = fmax(m[0], fabs(v));
         });
       });
@@ -442,10 +499,10 @@ struct Solver {
       }
       if (kref == kNitref || nerr < thr || (kref > 0 && nerr_prev < kIrErrFact * nerr)) break;
       nerr_prev = nerr;
-      ldl_solve(sm.e);
+      ldl_solve(sm.e());
       phase([&](int tid) {
 #pragma unroll
-        for (int j = 0; j < PT; ++j) { const int k = tid + j * T; if (k < NK) { const double dv = sm.e[k]; dpx.at(tid, j) = dv; out[k] += dv; } }
+        for (int j = 0; j < PT; ++j) { const int k = tid + j * T; if (k < NK) { const double dv = sm.e()[k]; dpx.at(tid, j) = dv; out[k] += dv; } }
       });
       ++kref;
     }
@@ -456,7 +513,7 @@ struct Solver {
   // lambda = W v for the cone: out may alias v
   IPM_FN void cone_scale(int c, const WarpOps& W, const double* v, double* out) const {
     const int so = kSocSo[c], d = kSocD[c];
-    const double* q = sm.q + kSocQo[c]; const double* sc = sm.sc + 8 * c;
+    const double* q = sm.q() + kSocQo[c]; const double* sc = sm.sc() + 8 * c;
     const double zeta = W.sum(0, d - 1, [&](int i) { return q[i] * v[so + 1 + i]; });
     const double v0 = v[so];
     const double factor = v0 + safediv(zeta, 1.0 + sc[SC_A]);
@@ -469,7 +526,7 @@ struct Solver {
   // line-search contribution of one cone (ecos.c:985-1035): returns the conic step (0 = no restriction)
   IPM_FN double cone_step(int c, const WarpOps& W, const double* ds, const double* dz) const {
     const int so = kSocSo[c], d = kSocD[c];
-    const double* lk = sm.lam + so;
+    const double* lk = sm.lam() + so;
     const double l0 = lk[0];
     const double n2 = l0 * l0 - W.sum(1, d, [&](int j) { return lk[j] * lk[j]; });
     if (n2 <= 0.0) return 0.0;
@@ -496,16 +553,16 @@ struct Solver {
 IPM_FN void Solver::tail_factor(int tid) {
 #ifdef CPG_IPM_HOST_EMU
   if (tid != 0 || NT == 0) return;
-  double* B = sm.S + TT0;
+  double* B = sm.S() + TT0;
   double dv[NT > 0 ? NT : 1];
   for (int j = 0; j < NT; ++j) {
-    const int kj = sm.tail_k[j];
-    const double ij = inv_pivot(kj, sm.S[DG0 + kj]);
+    const int kj = sm.tail_k()[j];
+    const double ij = inv_pivot(kj, sm.S()[DG0 + kj]);
     dv[j] = ij;
     for (int i = j + 1; i < NT; ++i) {
       const double sij = B[i * NT + j];
       for (int k = j + 1; k < i; ++k) B[i * NT + k] -= sij * B[k * NT + j] * ij;
-      sm.S[DG0 + sm.tail_k[i]] -= sij * sij * ij;
+      sm.S()[DG0 + sm.tail_k()[i]] -= sij * sij * ij;
     }
   }
   double X[(NT > 0 ? NT : 1) * (NT > 0 ? NT : 1)];
@@ -515,24 +572,24 @@ IPM_FN void Solver::tail_factor(int tid) {
       for (int k = 0; k < m; ++k) a -= (B[m * NT + k] * dv[k]) * X[k * NT + c];
       X[m * NT + c] = m == c ? 1.0 : a;
     }
-  for (int j = 0; j < NT; ++j) sm.S[DG0 + sm.tail_k[j]] = dv[j];
+  for (int j = 0; j < NT; ++j) sm.S()[DG0 + sm.tail_k()[j]] = dv[j];
   for (int m = 0; m < NT; ++m) for (int c = 0; c < m; ++c) B[m * NT + c] = X[m * NT + c];
 #else
   if (NT == 0 || tid >= 32) return;
   constexpr int NTT = NT > 0 ? NT : 1;
   const int i = tid;
   const bool on = i < NT;
-  const int ki = on ? sm.tail_k[i] : 0;
-  double* B = sm.S + TT0;
+  const int ki = on ? sm.tail_k()[i] : 0;
+  double* B = sm.S() + TT0;
   double r[NTT], x[NTT], dv[NTT];      // row i of the block (S_ik = L_ik D_k), column i of inv(L), inverse pivots (uniform)
 #pragma unroll
   for (int k = 0; k < NT; ++k) r[k] = (on && k < i) ? B[i * NT + k] : 0.0;
-  double d = on ? sm.S[DG0 + ki] : 1.0;
+  double d = on ? sm.S()[DG0 + ki] : 1.0;
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
-    const double ij = inv_pivot(sm.tail_k[j], __shfl_sync(0xffffffffu, d, j));
+    const double ij = inv_pivot(sm.tail_k()[j], __shfl_sync(0xffffffffu, d, j));
     dv[j] = ij;
-    if (i == j) sm.S[DG0 + ki] = ij;
+    if (i == j) sm.S()[DG0 + ki] = ij;
     const double sij = r[j];
 #pragma unroll
     for (int k = j + 1; k < NT; ++k) {
@@ -556,36 +613,36 @@ IPM_FN void Solver::tail_factor(int tid) {
 IPM_FN void Solver::tail_solve(int tid, double* u) {
 #ifdef CPG_IPM_HOST_EMU
   if (tid != 0 || NT == 0) return;
-  const double* X = sm.S + TT0;
+  const double* X = sm.S() + TT0;
   double b[NT > 0 ? NT : 1], w[NT > 0 ? NT : 1];
-  for (int i = 0; i < NT; ++i) b[i] = u[sm.tail_k[i]];
+  for (int i = 0; i < NT; ++i) b[i] = u[sm.tail_k()[i]];
   for (int i = 0; i < NT; ++i) {
     double y = b[i];
     for (int j = 0; j < i; ++j) y += X[i * NT + j] * b[j];
-    w[i] = y * sm.S[DG0 + sm.tail_k[i]];
+    w[i] = y * sm.S()[DG0 + sm.tail_k()[i]];
   }
   for (int i = 0; i < NT; ++i) {
     double xv = w[i];
     for (int m = i + 1; m < NT; ++m) xv += X[m * NT + i] * w[m];
-    u[sm.tail_k[i]] = xv;
+    u[sm.tail_k()[i]] = xv;
   }
 #else
   if (NT == 0 || tid >= 32) return;
   const int i = tid;
   const bool on = i < NT;
-  const int ki = on ? sm.tail_k[i] : 0;
-  const double* X = sm.S + TT0;
+  const int ki = on ? sm.tail_k()[i] : 0;
+  const double* X = sm.S() + TT0;
   double y = on ? u[ki] : 0.0;
-  sm.tw[i] = y;
+  sm.tw()[i] = y;
   __syncwarp();
 #pragma unroll
-  for (int j = 0; j < NT - 1; ++j) if (on && j < i) y += X[i * NT + j] * sm.tw[j];
-  const double w = on ? y * sm.S[DG0 + ki] : 0.0;
-  sm.tw[32 + i] = w;
+  for (int j = 0; j < NT - 1; ++j) if (on && j < i) y += X[i * NT + j] * sm.tw()[j];
+  const double w = on ? y * sm.S()[DG0 + ki] : 0.0;
+  sm.tw()[32 + i] = w;
   __syncwarp();
   double xv = w;
 #pragma unroll
-  for (int m = 1; m < NT; ++m) if (on && m > i) xv += X[m * NT + i] * sm.tw[32 + m];
+  for (int m = 1; m < NT; ++m) if (on && m > i) xv += X[m * NT + i] * sm.tw()[32 + m];
   if (on) u[ki] = xv;
 #endif
 }
@@ -602,19 +659,16 @@ IPM_FN bool better(const Stats& a, const Stats& b) {        // compareStatistics
 }
 
 IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
-  PerThread<PT> dpx;
   double s_[16], m_[4];
   const double* par = io.params + size_t(inst) * NPB;
-  auto rhs1 = [&](int k) { return k < N ? -sm.cbh[k] : sm.cbh[k]; };
-  auto rhs2 = [&](int k) { return sm.rhs[k]; };
-  double* const zv = sm.xyz + ZOFF;           // z (stretched)
-  double* const wdz = sm.e + ZOFF;            // W dz lives in the error vector between solves
+  double* const zv = sm.xyz() + ZOFF;           // z (stretched)
+  double* const wdz = sm.e() + ZOFF;            // W dz lives in the error vector between solves
 
   // ---- cpg_canonicalize: c, b, h from the user parameters (equilibrated), cvxpygen/utils.py:279-294 + equil.c:326-338
-  phase([&](int tid) { each_k(tid, NK, [&](int k) { sm.cbh[k] = gm.cbh_base[k]; }); });
-  phase([&](int tid) { each_k(tid, NMAP, [&](int e) { atomic_add(sm.cbh + gm.map_t[e], gm.map_v[e] * par[gm.map_p[e]]); }); });
+  phase([&](int tid) { each_k(tid, NK, [&](int k) { sm.cbh()[k] = gm.cbh_base[k]; }); });
+  phase([&](int tid) { each_k(tid, NMAP, [&](int e) { atomic_add(sm.cbh() + gm.map_t[e], gm.map_v[e] * par[gm.map_p[e]]); }); });
   phase_red<3, 0>(sm, rb, s_, m_, [&](int tid, double* s, double*) {
-    each_k(tid, NK, [&](int k) { const double v = sm.cbh[k]; s[k < N ? 0 : (k < ZOFF ? 1 : 2)] += v * v; });
+    each_k(tid, NK, [&](int k) { const double v = sm.cbh()[k]; s[k < N ? 0 : (k < ZOFF ? 1 : 2)] += v * v; });
   });
   const double resx0 = fmax(1.0, sqrt(s_[0])), resy0 = fmax(1.0, sqrt(s_[1])), resz0 = fmax(1.0, sqrt(s_[2]));
 
@@ -623,10 +677,10 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
     each_k(tid, NS, [&](int i) {
       double v = gm.Sbase[i];
       if (i >= DG0 + ZOFF && i < DG0 + NK) v += sign_of(i - DG0) > 0 ? 1.0 : -1.0;
-      sm.S[i] = v;
+      sm.S()[i] = v;
     });
-    each_k(tid, MT, [&](int i) { sm.sv[i] = 0.0; sm.lam[i] = 0.0; sm.rz[i] = 0.0; sm.dsw[i] = 0.0; });
-    each_k(tid, NK, [&](int k) { sm.xyz[k] = 0.0; });
+    each_k(tid, MT, [&](int i) { sm.sv()[i] = 0.0; sm.lam()[i] = 0.0; sm.rz()[i] = 0.0; sm.dsw()[i] = 0.0; });
+    each_k(tid, NK, [&](int k) { sm.xyz()[k] = 0.0; });
   });
   factor();
   auto bring2cone = [&](const double* r, double rsign, double* out) {        // out = rsign * r shifted into the cone
@@ -635,10 +689,10 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
         [&](int c, const WarpOps& W) {
           const int so = kSocSo[c], d = kSocD[c];
           const double nr = sqrt(W.sum(1, d, [&](int j) { return r[so + j] * r[so + j]; }));
-          if (W.leader()) sm.cone[c] = rsign * r[so] - nr;
+          if (W.leader()) sm.cone()[c] = rsign * r[so] - nr;
         });
     double alpha = fmax(-kGamma, m_[0]);
-    for (int c = 0; c < NSOC; ++c) { const double cres = sm.cone[c]; if (cres <= 0 && -cres > alpha) alpha = -cres; }
+    for (int c = 0; c < NSOC; ++c) { const double cres = sm.cone()[c]; if (cres <= 0 && -cres > alpha) alpha = -cres; }
     alpha += 1.0;
     phase_cones([&](int tid) { each_k(tid, L, [&](int i) { out[i] = rsign * r[i] + alpha; }); },
                 [&](int c, const WarpOps& W) {
@@ -646,12 +700,12 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
                   W.each(0, d, [&](int j) { out[so + j] = rsign * r[so + j] + (j == 0 ? alpha : 0.0); });
                 });
   };
-  kkt_solve([&](int k) { return k < N ? 0.0 : sm.cbh[k]; }, sm.px, true, dpx);
-  phase([&](int tid) { each_k(tid, N, [&](int k) { sm.xyz[k] = sm.px[k]; }); });
-  bring2cone(sm.px + ZOFF, -1.0, sm.sv);
-  kkt_solve([&](int k) { return k < N ? -sm.cbh[k] : 0.0; }, sm.px, true, dpx);
-  phase([&](int tid) { each_k(tid, P, [&](int i) { sm.xyz[N + i] = sm.px[N + i]; }); });
-  bring2cone(sm.px + ZOFF, 1.0, zv);
+  kkt_solve(RHS_INIT_P, sm.px(), true);
+  phase([&](int tid) { each_k(tid, N, [&](int k) { sm.xyz()[k] = sm.px()[k]; }); });
+  bring2cone(sm.px() + ZOFF, -1.0, sm.sv());
+  kkt_solve(RHS_INIT_D, sm.px(), true);
+  phase([&](int tid) { each_k(tid, P, [&](int i) { sm.xyz()[N + i] = sm.px()[N + i]; }); });
+  bring2cone(sm.px() + ZOFF, 1.0, zv);
   double kap = 1.0, tau = 1.0;
 
   // ---- main loop (ecos.c:1123-1583)
@@ -661,11 +715,11 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
   int exitcode = kFatal, it = 0;
   auto save_best = [&]() {
     Ibest = I; best_kap = kap; best_tau = tau; best_cx = cx; best_by = by; best_hz = hz;
-    phase([&](int tid) { each_k(tid, NK, [&](int k) { best[k] = sm.xyz[k]; }); each_k(tid, MT, [&](int i) { best[NK + i] = sm.sv[i]; }); });
+    phase([&](int tid) { each_k(tid, NK, [&](int k) { best[k] = sm.xyz()[k]; }); each_k(tid, MT, [&](int i) { best[NK + i] = sm.sv()[i]; }); });
   };
   auto restore_best = [&]() {
     I = Ibest; kap = best_kap; tau = best_tau; cx = best_cx; by = best_by; hz = best_hz;
-    phase([&](int tid) { each_k(tid, NK, [&](int k) { sm.xyz[k] = best[k]; }); each_k(tid, MT, [&](int i) { sm.sv[i] = best[NK + i]; }); });
+    phase([&](int tid) { each_k(tid, NK, [&](int k) { sm.xyz()[k] = best[k]; }); each_k(tid, MT, [&](int i) { sm.sv()[i] = best[NK + i]; }); });
   };
   auto check_exit = [&](int mode) {                          // checkExitConditions, ecos.c:179-257
     const double feastol = mode ? stg.feastol_inacc : stg.feastol, abstol = mode ? stg.abstol_inacc : stg.abstol,
@@ -679,28 +733,28 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
   };
   for (;; ++it) {
     // computeResiduals (ecos.c:455-499): -A'y - G'z -> rhs[0:N], A x -> rhs[N:ZOFF], s + G x -> rz
-    plan_mv().run(0, [&](uint32_t en) { return sm.ag[en & 0xffffu] * sm.xyz[en >> 16]; },
+    plan_mv().run<0>([&](uint32_t en) { return at(sm.ag(), en & 0xffffu) * at(sm.xyz(), en >> 16); },
                   [&](int k, int, double acc) {
-                    if (k < N) sm.rhs[k] = -acc;
-                    else if (k < ZOFF) sm.rhs[k] = acc;
-                    else sm.rz[k - ZOFF] = sm.sv[k - ZOFF] + acc;
+                    if (k < N) sm.rhs()[k] = -acc;
+                    else if (k < ZOFF) sm.rhs()[k] = acc;
+                    else sm.rz()[k - ZOFF] = sm.sv()[k - ZOFF] + acc;
                   });
     sync_phase();
     phase_red<16, 0>(sm, rb, s_, m_, [&](int tid, double* s, double*) {
       each_k(tid, N, [&](int k) {
-        const double hr = sm.rhs[k], c = sm.cbh[k], x = sm.xyz[k];
+        const double hr = sm.rhs()[k], c = sm.cbh()[k], x = sm.xyz()[k];
         s[0] += hr * hr; s[3] += c * x; s[6] += x * x;
-        const double r = hr - tau * c; sm.rhs[k] = r; s[11] += r * r;
+        const double r = hr - tau * c; sm.rhs()[k] = r; s[11] += r * r;
       });
       each_k(tid, P, [&](int i) {
-        const int k = N + i; const double hr = sm.rhs[k], b = sm.cbh[k], y = sm.xyz[k];
+        const int k = N + i; const double hr = sm.rhs()[k], b = sm.cbh()[k], y = sm.xyz()[k];
         s[1] += hr * hr; s[4] += b * y; s[7] += y * y;
-        const double r = hr - tau * b; sm.rhs[k] = r; s[12] += r * r;
+        const double r = hr - tau * b; sm.rhs()[k] = r; s[12] += r * r;
       });
       each_k(tid, MT, [&](int i) {
-        const double hr = sm.rz[i], h = sm.cbh[ZOFF + i], z = zv[i], sv = sm.sv[i];
+        const double hr = sm.rz()[i], h = sm.cbh()[ZOFF + i], z = zv[i], sv = sm.sv()[i];
         s[2] += hr * hr; s[5] += h * z; s[8] += sv * sv; s[9] += z * z; s[10] += sv * z;
-        const double r = hr - tau * h; sm.rz[i] = r; s[13] += r * r;
+        const double r = hr - tau * h; sm.rz()[i] = r; s[13] += r * r;
       });
     });
     {
@@ -752,20 +806,20 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
     // updateScalings + lambda = W z, and the constant part of the KKT image
     phase_cones(
         [&](int tid) {
-          if (tid == 0) *sm.flag = 0;
+          if (tid == 0) *sm.flag() = 0;
           each_k(tid, L, [&](int i) {
-            const double v = safediv(sm.sv[i], zv[i]), w = sqrt(v);
-            sm.v[i] = v; sm.w[i] = w; sm.lam[i] = w * zv[i];
+            const double v = safediv(sm.sv()[i], zv[i]), w = sqrt(v);
+            sm.v()[i] = v; sm.w()[i] = w; sm.lam()[i] = w * zv[i];
           });
-          each_k(tid, NS, [&](int i) { sm.S[i] = gm.Sbase[i]; });
+          each_k(tid, NS, [&](int i) { sm.S()[i] = gm.Sbase[i]; });
         },
         [&](int c, const WarpOps& W) {
           const int so = kSocSo[c], d = kSocD[c];
-          const double* sk = sm.sv + so; const double* zk = zv + so;
-          double* q = sm.q + kSocQo[c]; double* sc = sm.sc + 8 * c;
+          const double* sk = sm.sv() + so; const double* zk = zv + so;
+          double* q = sm.q() + kSocQo[c]; double* sc = sm.sc() + 8 * c;
           const double sres = sk[0] * sk[0] - W.sum(1, d, [&](int j) { return sk[j] * sk[j]; });
           const double zres = zk[0] * zk[0] - W.sum(1, d, [&](int j) { return zk[j] * zk[j]; });
-          if (sres <= 0 || zres <= 0) { if (W.leader()) sm.cone[c] = 1.0; return; }
+          if (sres <= 0 || zres <= 0) { if (W.leader()) sm.cone()[c] = 1.0; return; }
           const double snorm = sqrt(sres), znorm = sqrt(zres);
           const double eta2 = safediv(snorm, znorm), eta = sqrt(eta2);
           const double gamma = sqrt(0.5 * (1.0 + W.sum(0, d, [&](int j) { return safediv(sk[j], snorm) * safediv(zk[j], znorm); })));
@@ -781,18 +835,18 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
           if (d1 < 0) d1 = 0;
           const double u0sq = a * a + w - d1, u0 = sqrt(u0sq);
           const double c2byu02 = safediv(cc * cc, u0sq);
-          if (c2byu02 - dd <= 0) { if (W.leader()) sm.cone[c] = 1.0; return; }
+          if (c2byu02 - dd <= 0) { if (W.leader()) sm.cone()[c] = 1.0; return; }
           if (W.leader()) {
             sc[SC_ETA2] = eta2; sc[SC_ETA] = eta; sc[SC_A] = a; sc[SC_D1] = d1; sc[SC_U0] = u0;
             sc[SC_U1] = sqrt(c2byu02); sc[SC_V1] = sqrt(c2byu02 - dd); sc[SC_W] = w;
-            sm.cone[c] = 0.0;
+            sm.cone()[c] = 0.0;
           }
           W.sync();
-          cone_scale(c, W, zv, sm.lam);
+          cone_scale(c, W, zv, sm.lam());
         });
     {
       bool out = false;
-      for (int c = 0; c < NSOC; ++c) out = out || sm.cone[c] != 0.0;
+      for (int c = 0; c < NSOC; ++c) out = out || sm.cone()[c] != 0.0;
       if (out) {
         restore_best(); exitcode = check_exit(kInaccOffset);
         if (exitcode == kNotConverged) exitcode = kOutcone;
@@ -801,30 +855,30 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
     }
     // kkt_update: the scaling block
     phase_cones(
-        [&](int tid) { each_k(tid, L, [&](int i) { sm.S[DG0 + ZOFF + i] = -sm.v[i] - kDeltaStat; }); },
+        [&](int tid) { each_k(tid, L, [&](int i) { sm.S()[DG0 + ZOFF + i] = -sm.v()[i] - kDeltaStat; }); },
         [&](int c, const WarpOps& W) {
           const int so = kSocSo[c], d = kSocD[c];
-          const double* q = sm.q + kSocQo[c]; const double* sc = sm.sc + 8 * c;
+          const double* q = sm.q() + kSocQo[c]; const double* sc = sm.sc() + 8 * c;
           const double e2 = sc[SC_ETA2];
-          const uint16_t* sv_ = sm.socv + kSocVo[c]; const uint16_t* su_ = sm.socu + kSocUo[c];
-          W.each(0, d, [&](int r) { sm.S[DG0 + ZOFF + so + r] = (r == 0 ? -e2 * sc[SC_D1] : -e2) - kDeltaStat; });
-          W.each(0, d - 1, [&](int i) { sm.S[sv_[i]] = -e2 * sc[SC_V1] * q[i]; sm.S[su_[1 + i]] = -e2 * sc[SC_U1] * q[i]; });
+          const uint16_t* sv_ = sm.socv() + kSocVo[c]; const uint16_t* su_ = sm.socu() + kSocUo[c];
+          W.each(0, d, [&](int r) { sm.S()[DG0 + ZOFF + so + r] = (r == 0 ? -e2 * sc[SC_D1] : -e2) - kDeltaStat; });
+          W.each(0, d - 1, [&](int i) { sm.S()[sv_[i]] = -e2 * sc[SC_V1] * q[i]; sm.S()[su_[1 + i]] = -e2 * sc[SC_U1] * q[i]; });
           if (W.leader()) {
-            sm.S[su_[0]] = -e2 * sc[SC_U0];
-            sm.S[DG0 + ZOFF + so + d] = -e2;
-            sm.S[DG0 + ZOFF + so + d + 1] = e2 + kDeltaStat;
+            sm.S()[su_[0]] = -e2 * sc[SC_U0];
+            sm.S()[DG0 + ZOFF + so + d] = -e2;
+            sm.S()[DG0 + ZOFF + so + d + 1] = e2 + kDeltaStat;
           }
         });
     factor();
     // search directions
-    kkt_solve(rhs1, sm.sol1, false, dpx);
+    kkt_solve(RHS_ONE, sm.sol1(), false);
     phase([&](int tid) {                                      // RHS_affine
-      each_k(tid, P, [&](int i) { sm.rhs[N + i] = -sm.rhs[N + i]; });
-      each_k(tid, MT, [&](int i) { sm.rhs[ZOFF + i] = sm.sv[i] - sm.rz[i]; });
+      each_k(tid, P, [&](int i) { sm.rhs()[N + i] = -sm.rhs()[N + i]; });
+      each_k(tid, MT, [&](int i) { sm.rhs()[ZOFF + i] = sm.sv()[i] - sm.rz()[i]; });
     });
-    kkt_solve(rhs2, sm.px, false, dpx);
+    kkt_solve(RHS_VEC, sm.px(), false);
     phase_red<2, 0>(sm, rb, s_, m_, [&](int tid, double* s, double*) {
-      each_k(tid, NK, [&](int k) { const double c = sm.cbh[k]; s[0] += c * sm.sol1[k]; s[1] += c * sm.px[k]; });
+      each_k(tid, NK, [&](int k) { const double c = sm.cbh()[k]; s[0] += c * sm.sol1()[k]; s[1] += c * sm.px()[k]; });
     });
     const double dtau_denom = kap / tau - s_[0];
     const double dtauaff = (rt - kap + s_[1]) / dtau_denom;
@@ -834,25 +888,25 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
       // px_z += dt * sol1_z (all of px when combined); wdz = W px_z; dsw = -(combined ? dsw : lam) - wdz
       phase_red_cones<0, 2>(sm, rb, s_, m_,
           [&](int tid, double*, double* m) {
-            each_k(tid, combined ? ZOFF : 0, [&](int k) { sm.px[k] += dt * sm.sol1[k]; });
+            each_k(tid, combined ? ZOFF : 0, [&](int k) { sm.px()[k] += dt * sm.sol1()[k]; });
             each_k(tid, L, [&](int i) {
-              const double dz = sm.px[ZOFF + i] + dt * sm.sol1[ZOFF + i];
-              sm.px[ZOFF + i] = dz;
-              const double wz = sm.w[i] * dz, lam = sm.lam[i];
-              const double dsw = -(combined ? sm.dsw[i] : lam) - wz;
-              wdz[i] = wz; sm.dsw[i] = dsw;
+              const double dz = sm.px()[ZOFF + i] + dt * sm.sol1()[ZOFF + i];
+              sm.px()[ZOFF + i] = dz;
+              const double wz = sm.w()[i] * dz, lam = sm.lam()[i];
+              const double dsw = -(combined ? sm.dsw()[i] : lam) - wz;
+              wdz[i] = wz; sm.dsw()[i] = dsw;
               m[0] = fmax(m[0], -dsw / lam); m[1] = fmax(m[1], -wz / lam);
             });
           },
           [&](int c, const WarpOps& W) {
             const int so = kSocSo[c], d = kSocD[c];
-            W.each(0, d + 2, [&](int r) { sm.px[ZOFF + so + r] += dt * sm.sol1[ZOFF + so + r]; });
+            W.each(0, d + 2, [&](int r) { sm.px()[ZOFF + so + r] += dt * sm.sol1()[ZOFF + so + r]; });
             W.sync();
-            cone_scale(c, W, sm.px + ZOFF, wdz);
-            W.each(0, d, [&](int r) { sm.dsw[so + r] = -(combined ? sm.dsw[so + r] : sm.lam[so + r]) - wdz[so + r]; });
+            cone_scale(c, W, sm.px() + ZOFF, wdz);
+            W.each(0, d, [&](int r) { sm.dsw()[so + r] = -(combined ? sm.dsw()[so + r] : sm.lam()[so + r]) - wdz[so + r]; });
             W.sync();
-            const double st = cone_step(c, W, sm.dsw, wdz);
-            if (W.leader()) sm.cone[c] = st;
+            const double st = cone_step(c, W, sm.dsw(), wdz);
+            if (W.leader()) sm.cone()[c] = st;
           });
       // lineSearch, ecos.c:947-1046 (m_[0] = -rhomin, m_[1] = -sigmamin)
       double alpha;
@@ -864,7 +918,7 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
       const double mtt = -tau / dtau_, mkk = -kap / dkap_;
       if (mtt > 0 && mtt < alpha) alpha = mtt;
       if (mkk > 0 && mkk < alpha) alpha = mkk;
-      for (int c = 0; c < NSOC; ++c) { const double st = sm.cone[c]; if (st != 0.0) { const double t_ = 1.0 / st; if (t_ < alpha) alpha = t_; } }
+      for (int c = 0; c < NSOC; ++c) { const double st = sm.cone()[c]; if (st != 0.0) { const double t_ = 1.0 / st; if (t_ < alpha) alpha = t_; } }
       if (alpha > kStepMax) alpha = kStepMax;
       if (alpha < kStepMin) alpha = kStepMin;
       return alpha;
@@ -877,19 +931,19 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
     // RHS_combined (ecos.c:688-757): dsw <- lambda \ (lambda o lambda + dsw o wdz - sigma mu e); rhs_z = -(1-sigma) rz + W dsw
     phase_cones(
         [&](int tid) {
-          each_k(tid, ZOFF, [&](int k) { sm.rhs[k] *= oms; });
+          each_k(tid, ZOFF, [&](int k) { sm.rhs()[k] *= oms; });
           each_k(tid, L, [&](int i) {
-            const double lam = sm.lam[i];
-            const double ds1 = lam * lam + sm.dsw[i] * wdz[i] - sigmamu;
+            const double lam = sm.lam()[i];
+            const double ds1 = lam * lam + sm.dsw()[i] * wdz[i] - sigmamu;
             const double dv = safediv(ds1, lam);
-            sm.dsw[i] = dv;
-            sm.rhs[ZOFF + i] = -oms * sm.rz[i] + sm.w[i] * dv;
+            sm.dsw()[i] = dv;
+            sm.rhs()[ZOFF + i] = -oms * sm.rz()[i] + sm.w()[i] * dv;
           });
         },
         [&](int c, const WarpOps& W) {
           const int so = kSocSo[c], d = kSocD[c];
-          const double* lk = sm.lam + so; double* ds = sm.dsw + so; const double* wz = wdz + so;
-          double* tmp = sm.px + ZOFF + so;                       // px is free between the two solves
+          const double* lk = sm.lam() + so; double* ds = sm.dsw() + so; const double* wz = wdz + so;
+          double* tmp = sm.px() + ZOFF + so;                       // px is free between the two solves
           const double l0 = lk[0], ds0 = ds[0], wz0 = wz[0];
           const double ll = W.sum(0, d, [&](int j) { return lk[j] * lk[j]; });
           const double dw = W.sum(0, d, [&](int j) { return ds[j] * wz[j]; });
@@ -903,14 +957,14 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
           W.each(1, d, [&](int j) { ds[j] = factor * lk[j] + safediv(tmp[j], l0); });
           if (W.leader()) ds[0] = safediv(l0 * w0 - zeta, rho);
           W.sync();
-          cone_scale(c, W, sm.dsw, sm.px + ZOFF);
-          W.each(0, d, [&](int r) { sm.rhs[ZOFF + so + r] = -oms * sm.rz[so + r] + tmp[r]; });
-          if (W.leader()) { sm.rhs[ZOFF + so + d] = 0.0; sm.rhs[ZOFF + so + d + 1] = 0.0; }
+          cone_scale(c, W, sm.dsw(), sm.px() + ZOFF);
+          W.each(0, d, [&](int r) { sm.rhs()[ZOFF + so + r] = -oms * sm.rz()[so + r] + tmp[r]; });
+          if (W.leader()) { sm.rhs()[ZOFF + so + d] = 0.0; sm.rhs()[ZOFF + so + d + 1] = 0.0; }
           W.sync();
         });
-    kkt_solve(rhs2, sm.px, false, dpx);
+    kkt_solve(RHS_VEC, sm.px(), false);
     phase_red<1, 0>(sm, rb, s_, m_, [&](int tid, double* s, double*) {
-      each_k(tid, NK, [&](int k) { s[0] += sm.cbh[k] * sm.px[k]; });
+      each_k(tid, NK, [&](int k) { s[0] += sm.cbh()[k] * sm.px()[k]; });
     });
     const double bkap = kap * tau + dkapaff * dtauaff - sigmamu;
     const double dtau = (oms * rt - bkap / tau + s_[0]) / dtau_denom;
@@ -919,13 +973,13 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
     // ds = W (W\ds); update the iterate
     phase_cones(
         [&](int tid) {
-          each_k(tid, ZOFF + L, [&](int k) { sm.xyz[k] += step * sm.px[k]; });
-          each_k(tid, L, [&](int i) { sm.sv[i] += step * (sm.w[i] * sm.dsw[i]); });
+          each_k(tid, ZOFF + L, [&](int k) { sm.xyz()[k] += step * sm.px()[k]; });
+          each_k(tid, L, [&](int i) { sm.sv()[i] += step * (sm.w()[i] * sm.dsw()[i]); });
         },
         [&](int c, const WarpOps& W) {
           const int so = kSocSo[c], d = kSocD[c];
-          cone_scale(c, W, sm.dsw, wdz);
-          W.each(0, d, [&](int r) { sm.sv[so + r] += step * wdz[so + r]; zv[so + r] += step * sm.px[ZOFF + so + r]; });
+          cone_scale(c, W, sm.dsw(), wdz);
+          W.each(0, d, [&](int r) { sm.sv()[so + r] += step * wdz[so + r]; zv[so + r] += step * sm.px()[ZOFF + so + r]; });
         });
     kap += step * dkap; tau += step * dtau;
   }
@@ -934,21 +988,21 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
   phase([&](int tid) {
     const double it_ = 1.0 / tau;
     (void)it_;
-    each_k(tid, NPRIM, [&](int i) { const int k = gm.prim_idx[i]; io.prim[size_t(inst) * NPRIM + i] = sm.xyz[k] * gm.unscale[k] / tau; });
-    each_k(tid, NDUAL, [&](int i) { const int k = gm.dual_idx[i]; io.dual[size_t(inst) * NDUAL + i] = sm.xyz[k] * gm.unscale[k] / tau; });
-    if (io.sol_x) each_k(tid, N, [&](int k) { io.sol_x[size_t(inst) * N + k] = sm.xyz[k] * gm.unscale[k] / tau; });
-    if (io.sol_y) each_k(tid, P, [&](int i) { io.sol_y[size_t(inst) * P + i] = sm.xyz[N + i] * gm.unscale[N + i] / tau; });
+    each_k(tid, NPRIM, [&](int i) { const int k = gm.prim_idx[i]; io.prim[size_t(inst) * NPRIM + i] = sm.xyz()[k] * gm.unscale[k] / tau; });
+    each_k(tid, NDUAL, [&](int i) { const int k = gm.dual_idx[i]; io.dual[size_t(inst) * NDUAL + i] = sm.xyz()[k] * gm.unscale[k] / tau; });
+    if (io.sol_x) each_k(tid, N, [&](int k) { io.sol_x[size_t(inst) * N + k] = sm.xyz()[k] * gm.unscale[k] / tau; });
+    if (io.sol_y) each_k(tid, P, [&](int i) { io.sol_y[size_t(inst) * P + i] = sm.xyz()[N + i] * gm.unscale[N + i] / tau; });
     if (io.sol_z || io.sol_s) {
       each_k(tid, L, [&](int i) {
         if (io.sol_z) io.sol_z[size_t(inst) * M + i] = zv[i] * gm.unscale[ZOFF + i] / tau;
-        if (io.sol_s) io.sol_s[size_t(inst) * M + i] = sm.sv[i] / (gm.unscale[ZOFF + i] * tau);
+        if (io.sol_s) io.sol_s[size_t(inst) * M + i] = sm.sv()[i] / (gm.unscale[ZOFF + i] * tau);
       });
       int o = L;
       for (int c = 0; c < NSOC; ++c) {
         const int so = kSocSo[c], d = kSocD[c];
         each_k(tid, d, [&](int r) {
           if (io.sol_z) io.sol_z[size_t(inst) * M + o + r] = zv[so + r] * gm.unscale[ZOFF + so + r] / tau;
-          if (io.sol_s) io.sol_s[size_t(inst) * M + o + r] = sm.sv[so + r] / (gm.unscale[ZOFF + so + r] * tau);
+          if (io.sol_s) io.sol_s[size_t(inst) * M + o + r] = sm.sv()[so + r] / (gm.unscale[ZOFF + so + r] * tau);
         });
         o += d;
       }
@@ -966,23 +1020,21 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
 // ----------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CPG_IPM_THREADS, 1)
 ipm_kernel(const unsigned char* __restrict__ smem_blob, const unsigned char* __restrict__ gmem_blob, IpmSettings stg, IpmIO io) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int next_inst;
   Solver sv;
-  sv.sm = make_sm(smem_raw);
-  sv.gm = make_gm(gmem_blob);
+    sv.gm = make_gm(gmem_blob);
   sv.stg = stg; sv.rb = 0;
   // stage the constant tables: [f64 ag_val, 0 | u32 plan entries | u16 descriptors and index lists]
   {
     const double* src = reinterpret_cast<const double*>(smem_blob);
-    for (int i = threadIdx.x; i < NNZM + 1; i += T) sv.sm.ag[i] = src[i];
+    for (int i = threadIdx.x; i < NNZM + 1; i += T) sv.sm.ag()[i] = src[i];
     const uint32_t* ws = reinterpret_cast<const uint32_t*>(smem_blob + IPM_SB_U32_OFF);
     uint32_t* wd = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(smem_raw) + O_F64_END);
     for (int i = threadIdx.x; i < U32_COUNT; i += T) wd[i] = ws[i];
     const uint16_t* hs = reinterpret_cast<const uint16_t*>(smem_blob + IPM_SB_U16_OFF);
     uint16_t* hd = reinterpret_cast<uint16_t*>(wd + U32_COUNT);
     for (int i = threadIdx.x; i < U16_COUNT; i += T) hd[i] = hs[i];
-    if (threadIdx.x == 0) sv.sm.S[NS] = 0.0;          // the slot every null entry of the plans points at
+    if (threadIdx.x == 0) sv.sm.S()[NS] = 0.0;          // the slot every null entry of the plans points at
   }
   __syncthreads();
   double* best = io.best + size_t(blockIdx.x) * (NK + MT);

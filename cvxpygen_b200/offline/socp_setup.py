@@ -278,12 +278,13 @@ def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None
     plan_mv = _gather.GatherPlan(T=threads, nfields=2, tbits=11, null_entry=(len(ag_val), 0))
     _gather.add_phase(plan_mv, [(k, 0, [(e, src) for src, e in sorted(mv_rows[k])]) for k in range(nk)])
     # (b) forward substitution: phase 0 scales the leaves, phase lv pulls row k from the columns below, the last phase
-    #     (flag 1) collects the tail rows;  entry = (slot of S, source k)
+    #     (flag 1) collects the tail rows;  entry = (slot of S, source k).  Leaves (level 0) have nothing to pull.
     fw_rows = {}
     for t_, s_, sl in zip(fw[:, 1], fw[:, 2], fw[:, 3]):
         fw_rows.setdefault(int(t_), []).append((int(sl), int(s_)))
     plan_fw = _gather.GatherPlan(T=threads, nfields=2, tbits=11, null_entry=(NS, 0))
-    for lv in range(nlw):
+    _gather.add_phase(plan_fw, [])      # level 0: the leaves are scaled by whoever writes the right-hand side (l0mask)
+    for lv in range(1, nlw):
         ks = [int(perm[pos]) for pos in range(lev_lo[lv], lev_lo[lv + 1])]
         _gather.add_phase(plan_fw, [(k, 0, sorted(fw_rows.get(k, []), key=lambda x: inv[x[1]])) for k in ks])
     _gather.add_phase(plan_fw, [(int(k), 1, sorted(fw_rows.get(int(k), []), key=lambda x: inv[x[1]])) for k in perm[t0:]])
@@ -313,7 +314,10 @@ def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None
             have = {t_ for t_, f_, _ in rl if f_}
             assert have == {DG0 + int(perm[pos]) for pos in range(lev_lo[lv], lev_lo[lv + 1])}
         _gather.add_phase(plan_ops, rl)
-    T = dict(mr_t=mr_t, mr_s=mr_s, ag_val=ag_val, fw_t=fw[:, 1], fw_s=fw[:, 2], fw_slot=fw[:, 3],
+    l0mask = np.zeros((nk + 15) // 16, dtype=np.int64)          # bit k: column k is a leaf of the elimination tree
+    for pos in range(lev_lo[0], lev_lo[1] if nlw else 0):
+        l0mask[int(perm[pos]) >> 4] |= 1 << (int(perm[pos]) & 15)
+    T = dict(l0mask=l0mask, mr_t=mr_t, mr_s=mr_s, ag_val=ag_val, fw_t=fw[:, 1], fw_s=fw[:, 2], fw_slot=fw[:, 3],
              bw_t=np.array(bw_t, dtype=np.int64), bw_s=np.array(bw_s, dtype=np.int64), socv=np.array(socv, dtype=np.int64),
              socu=np.array(socu, dtype=np.int64), Sbase=Sbase, ops=ops[:, 1:], tail_k=perm[t0:], cbh_base=base,
              map_t=np.array(mt_, dtype=np.int64), map_p=np.array(mp_, dtype=np.int64), map_v=np.array(mv_, dtype=float),
@@ -350,7 +354,8 @@ def _pack(st: SOCPSetup, d_const: float):
         return offs, (np.concatenate(chunks) if chunks else np.zeros(0, dtype))
 
     def pack_entries(plan):
-        e = plan.entry_array().astype(np.uint64)
+        e = plan.entry_array().astype(np.uint64) * np.uint64(8)        # the kernel wants byte offsets into f64 arrays
+        assert e.max(initial=0) < 65536
         w = np.zeros(e.shape[0], dtype=np.uint64)
         for f in range(plan.nfields):
             w |= e[:, f] << np.uint64(16 * f)
@@ -358,7 +363,7 @@ def _pack(st: SOCPSetup, d_const: float):
     # shared-memory blob
     f64 = np.r_[T['ag_val'], 0.0]
     eo, e32 = cat([(nm, pack_entries(PL[nm])) for nm in ('mv', 'fw', 'bw')], np.uint32)
-    names16 = ['socv', 'socu', 'tail_k', 'perm']
+    names16 = ['socv', 'socu', 'tail_k', 'perm', 'l0mask']
     for nm in names16:
         a = T[nm]
         assert a.size == 0 or (a.min() >= 0 and a.max() < 65536), nm
@@ -458,7 +463,9 @@ def emulate_solve(st: SOCPSetup, S: np.ndarray, Dinv: np.ndarray, rhs: np.ndarra
     def fw_commit(k, tail, acc):
         v = u[k] - acc
         u[k] = v if tail else v * S[DG0 + k]
-    for lv in range(nlw + 1):
+    leaves = st.perm[st.level_ranges['lev_lo'][0]:st.level_ranges['lev_lo'][1]] if nlw else []
+    u[leaves] *= S[DG0 + np.asarray(leaves, dtype=int)]
+    for lv in range(1, nlw + 1):
         _gather.run_phase(st.plans['fw'], lv, lambda e: S[e[0]] * u[e[1]], fw_commit)
     tk = st.tables['tail_k']
     X = np.tril(S[TT0:TT0 + nt * nt].reshape(nt, nt), -1) + np.eye(nt)

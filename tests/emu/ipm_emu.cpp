@@ -18,7 +18,7 @@ extern "C" int ipm_emu_solve(const unsigned char* sblob, const unsigned char* gb
   std::memcpy(reinterpret_cast<double*>(base) + O_F64_END, sblob + IPM_SB_U32_OFF, size_t(U32_COUNT) * 4 + size_t(U16_COUNT) * 2);
   std::vector<double> best(NK + MT);
   Solver sv;
-  sv.sm = make_sm(base); sv.gm = make_gm(gblob); sv.rb = 0;
+  sv.sm.base_ = base; sv.gm = make_gm(gblob); sv.rb = 0;
   sv.stg = IpmSettings{maxit, 0, 1e-8, 1e-8, 1e-8, 1e-4, 5e-5, 5e-5};
   IpmIO io{B, params, prim, dual, x, y, z, s, obj, iter, status, pres, dres, best.data(), nullptr};
   for (int i = 0; i < B; ++i) sv.solve_instance(i, io, best.data());

@@ -262,21 +262,26 @@ def test_gpu_portfolio_matches_compiled_reference_on_fresh_batch():
     a = rng.standard_normal((B, 100)) * rng.uniform(0.2, 2.0, (B, 1))
     wp = np.abs(1 / 100 + 0.02 * rng.standard_normal((B, 100)))
     ref = _ref_batch(fam, a, wp)
-    # rounding stability of the REFERENCE itself: the same batch with the parameters moved in the 13th digit.  Duals of
-    # (nearly) degenerate rows are determined to ~1e-4 only -- the reference's own answer moves by that much -- so the 1e-5
-    # bar on z is asserted where the reference reproduces itself to 1e-6, and 1e-3 everywhere
-    ref2 = _ref_batch(fam, a * (1 + 1e-13 * rng.standard_normal(a.shape)), wp)
-    stable = (ref2['iter'] == ref['iter']) & np.array([_rel(ref2['z'][k], ref['z'][k]) < 1e-6 for k in range(B)])
-    assert stable.mean() > 0.9
     m = standard.load(NAME)
     r = m.solve_batch({'a': a, 'w_prev': wp}, return_canonical=True)
     assert np.array_equal(r.cpg_info.status, ref['exitflag'])
     assert (np.abs(r.cpg_info.iter - ref['iter']) <= 1).all() and (r.cpg_info.iter == ref['iter']).mean() > 0.97
     same = r.cpg_info.iter == ref['iter']
+    ez = np.array([_rel(r.sol_z[k], ref['z'][k]) for k in range(B)])
     for k in np.nonzero(same)[0]:
         assert _rel(r.sol_x[k], ref['x'][k]) < RTOL_PRIMAL, k
         assert _rel(r.sol_y[k], ref['y'][k]) < RTOL_PRIMAL, k
-        assert _rel(r.sol_z[k], ref['z'][k]) < (RTOL_DUAL if stable[k] else 1e-3), k
+        assert _rel(r.sol_s[k], ref['s'][k]) < RTOL_PRIMAL, k
+    # duals: the two rows  +-(w - w_prev)_i <= t_i  are both active when asset i is not traded, their multipliers are then
+    # determined only up to a shift along (+1, -1) and an interior-point method fixes that shift to a few digits.  One
+    # instance in a few hundred lands elsewhere on that face than the reference (measured: the entries move in exact
+    # +d / -d pairs).  Bar: 1e-5 on at least 99 % of the batch, 1e-3 on all, and on EVERY instance the returned duals
+    # satisfy dual feasibility and complementarity as tightly as the reference's own do.
+    assert (ez[same] < RTOL_DUAL).mean() >= 0.99 and ez[same].max() < 1e-3, (ez.max(), (ez < RTOL_DUAL).mean())
+    A, G = fam.canon_matrix('A').toarray(), fam.canon_matrix('G').toarray()
+    Cb = np.tile(fam.canon_data('c'), (B, 1)); Cb[:, :100] = -a
+    assert np.abs(r.sol_y @ A + r.sol_z @ G + Cb).max() < 1e-9
+    assert np.abs((r.sol_s * r.sol_z).sum(1)).max() < 1e-7
     # an instance that stops one iteration earlier / later still agrees to the solver tolerance on the user variables
     assert _rel(r.cpg_prim['w'], ref['x'][:, :100]) < 1e-5
     assert np.allclose(r.cpg_info.obj_val, -ref['pcost'], rtol=0, atol=1e-7)
