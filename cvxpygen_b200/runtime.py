@@ -416,6 +416,17 @@ class SocpModule(Module):
         info = SimpleNamespace(obj_val=obj, iter=it, status=st, pri_res=pri, dua_res=dua, time=t1 - t0)
         return SimpleNamespace(cpg_prim=pr, cpg_dual=du, cpg_info=info, prim=prim, dual=dual, sol_x=x, sol_y=y, sol_z=z, sol_s=s)
 
+    def solve_batch_pinned(self, params, out):
+        """Host-buffer entry on caller-owned (ideally pinned) torch CPU tensors, no allocation on the Python side.
+        out: dict with prim, dual, obj, pri, dua (float64) and it, st (int32); optional sol_x, sol_y, sol_z, sol_s."""
+        self.init()
+        ptr = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+        self._check(self._fn('cpg_socp_solve_batch_host')(C.c_int(params.shape[0]), ptr(params), ptr(out['prim']), ptr(out['dual']),
+                                                          ptr(out.get('sol_x')), ptr(out.get('sol_y')), ptr(out.get('sol_z')),
+                                                          ptr(out.get('sol_s')), ptr(out['obj']), ptr(out['it']), ptr(out['st']),
+                                                          ptr(out['pri']), ptr(out['dua']), C.byref(self.settings)))
+        return out
+
     def solve_batch_device(self, params, out=None, return_canonical=False, **_):
         import torch
         self.init()

@@ -301,13 +301,17 @@ def test_gpu_portfolio_full_batch_properties():
     out = m.solve_batch_device(P, return_canonical=True)
     torch.cuda.synchronize()
     st = out.status.cpu().numpy()
-    # a handful of instances per 10^5 end "close to optimal" (exit flag 10, reduced tolerances) in the reference as well:
-    # they must be rare and carry the reference's own exit flag; the optimality conditions below are asserted on the rest
+    # a handful of instances per 10^5 end "close to optimal" (exit flag 10): ECOS's safeguard |pres| > 500 |pres_prev|
+    # (ecos.c:1180-1200) compares two residuals that are both rounding noise (1e-11 vs 1e-14) in the last iteration, so which
+    # side of 500 the ratio falls on depends on the last bits -- the reference does the same on other instances.  They must
+    # be rare, the reference must call them solved as well, and the returned (best previous) iterate must agree with the
+    # reference's answer to the reduced tolerance; the optimality conditions below are asserted on the rest
     odd = np.nonzero(st != 0)[0]
-    assert odd.size <= B // 2000 and np.isin(st[odd], (0, 10)).all()
+    assert odd.size <= B // 10000 and np.isin(st[odd], (0, 10)).all()
     if odd.size and ref_ecos.available():
         ref = _ref_batch(fam, a[odd], wp[odd])
-        assert np.array_equal(ref['exitflag'], st[odd])
+        assert np.isin(ref['exitflag'], (0, 10)).all()
+        assert _rel(out.sol_x.cpu().numpy()[odd], ref['x']) < 1e-4
     ok = st == 0
     x, y, z, s = (t.cpu().numpy()[ok] for t in (out.sol_x, out.sol_y, out.sol_z, out.sol_s))
     a, wp, B_all, B = a[ok], wp[ok], B, int(ok.sum())
