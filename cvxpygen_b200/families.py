@@ -337,6 +337,81 @@ def portfolio_socp(n=100, m=10, seed=1, k_tc=0.01, k_sh=0.05, Lmax=1.6, name=Non
                        cone_dims={'l': n_lp, 'q': [m + 2, n + 2]})
 
 
+def random_socp(n=30, p=8, l=20, q=(3, 5, 4), density=0.25, seed=5, name=None) -> CanonFamily:
+    """Generic conic family in ECOS form with every vector a user parameter:
+
+        minimise c'x   s.t.  A x = b,   h - G x in  R+^l x SOC(q_1) x ... x SOC(q_k)
+
+    (the canonical form the reference hands to ECOS for any DPP SOCP, cvxpygen/solvers/ecos.py:45-58; the reference's own
+    conic tests are small SOCPs / LPs of this shape, tests/test_E2E_SOCP.py:15-64, tests/test_E2E_LP.py).  A, G are
+    random sparse constants; the defaults of c, b, h are built from a strictly feasible primal-dual pair, so the nominal
+    instance is solvable, while shifted b / h / c give primal-infeasible and unbounded instances for the exit-flag tests.
+    q = () gives a pure LP (no second-order cone), p = 0 a problem without equalities."""
+    rs = np.random.RandomState(seed)
+    q = [int(d) for d in q]
+    m = l + sum(q)
+
+    def sprand(r, c_):
+        M = sp.random(r, c_, density=density, random_state=rs, data_rvs=rs.randn).tolil()
+        for i in range(r):                     # no empty rows: every constraint involves a variable
+            if M.rows[i] == []:
+                M[i, rs.randint(c_)] = rs.randn()
+        return sp.csc_matrix(M)
+    A = sprand(p, n) if p else sp.csc_matrix((0, n))
+    G = sprand(m, n)
+    for j in range(n):                          # no empty columns either: every variable is constrained
+        if G[:, j].nnz == 0:
+            G = G.tolil(); G[rs.randint(m), j] = rs.randn(); G = sp.csc_matrix(G)
+    # structure for the exit-flag tests: LP rows 0 and 1 are  g'x <= h_0  and  -g'x <= h_1  (infeasible when h_0 + h_1 < 0);
+    # the last variable only appears in LP row 2 as  -x_last <= h_2  (unbounded when its cost is negative)
+    assert l >= 3
+    G = G.tolil(); A = A.tolil()
+    G[1, :] = -G[0, :].toarray()
+    G[:, n - 1] = 0.0; G[2, :] = 0.0; G[2, n - 1] = -1.0
+    if p:
+        A[:, n - 1] = 0.0
+        for i in range(p):
+            if A.rows[i] == []:
+                A[i, rs.randint(n - 1)] = rs.randn()
+    for i in range(m):
+        if G.rows[i] == []:
+            G[i, rs.randint(n - 1)] = rs.randn()
+    A = sp.csc_matrix(A); G = sp.csc_matrix(G); A.eliminate_zeros(); G.eliminate_zeros()
+    A.sort_indices(); G.sort_indices()
+    x0 = rs.randn(n)
+    s0 = np.r_[0.5 + rs.rand(l)]
+    z0 = np.r_[0.5 + rs.rand(l)]
+    for d in q:
+        v = rs.randn(d - 1); s0 = np.r_[s0, np.linalg.norm(v) + 0.5 + rs.rand(), v]
+        v = rs.randn(d - 1); z0 = np.r_[z0, np.linalg.norm(v) + 0.5 + rs.rand(), v]
+    h0 = G @ x0 + s0
+    b0 = A @ x0 if p else np.zeros(0)
+    c0 = -(A.T @ rs.randn(p) if p else 0.0) - G.T @ z0
+    specs = [('c', (n,), c0)] + ([('b', (p,), b0)] if p else []) + [('h', (m,), h0)]
+    params = _layout_params(specs)
+    n_theta = sum(pp.size for pp in params) + 1
+    col = {pp.name: pp.col for pp in params}
+    maps = {}
+    for pid, size in (('c', n), ('b', p), ('h', m)):
+        mb = _MapBuilder(size, n_theta)
+        if size and pid in col:
+            for i in range(size):
+                mb.add(i, col[pid] + i, 1.0)
+        maps[pid] = mb.csr()
+    maps['d'] = sp.csr_matrix((1, n_theta))
+    for pid, M in (('A', A), ('G', G)):
+        mb = _MapBuilder(M.nnz, n_theta)
+        for k, v in enumerate(M.data):
+            mb.const(k, v)
+        maps[pid] = mb.csr()
+    variables = [UserVar('x', (n,), np.arange(n))]
+    duals = ([UserDual('d0', 'y', (p,), np.arange(p))] if p else []) + [UserDual('d1' if p else 'd0', 'z', (m,), np.arange(m))]
+    tag = 'x'.join(str(d) for d in q) if q else 'lp'
+    return CanonFamily(name or f'random_socp_{n}_{p}_{l}_{tag}', 'conic', n, p, m, params, maps,
+                       {'A': _csc_pattern(A), 'G': _csc_pattern(G)}, variables, duals, is_maximization=False,
+                       cone_dims={'l': l, 'q': q})
+
+
 def box_qp(n=6, m=8, seed=4, name=None) -> CanonFamily:
     """Small QP with two-sided constraints  l <= A x <= u  whose bounds are user parameters, built to exercise the
     per-instance corner cases of the path: a bound pair collapsing to an equality or opening to (-inf, inf) changes the

@@ -27,7 +27,7 @@ from . import gather as _gather
 
 DELTASTAT = 7e-8          # ecos/include/ecos.h:54
 EQUIL_ITERS = 3           # ecos/include/ecos.h:81
-MAX_TAIL = 32
+MAX_TAIL = 16             # the dense tail block is factored in the registers of one warp (3 x MAX_TAIL doubles per lane)
 DEFAULT_THREADS = 256    # threads of the CTA that solves one instance (the gather plans are dealt for this width)
 
 

@@ -19,11 +19,14 @@ STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
     'random_qp_20_5_15': (lambda: families.random_qp(20, 5, 15), ['q', 'b', 'h']),  # unstructured sparsity, q/l/u all batched
     'box_qp_6_8': (lambda: families.box_qp(6, 8), ['q', 'l', 'u']),          # corner cases: type changes, infeasibility
     'portfolio_socp_100_10': (lambda: families.portfolio_socp(100, 10), ['a', 'w_prev']),   # BASELINE config 3 (IPM-CUDA)
+    # generic conic families (every vector batched): three cones + equalities, and a pure LP; exit flags 0 / 1 / 2
+    'random_socp_30_8_20_3x5x4': (lambda: families.random_socp(30, 8, 20, (3, 5, 4), seed=5), ['c', 'b', 'h']),
+    'random_socp_20_5_30_lp': (lambda: families.random_socp(20, 5, 30, (), seed=6), ['c', 'b', 'h']),
 }
 
 # families solved by the ADMM (QP) backend / by the interior-point (SOCP) backend
-QP_NAMES: List[str] = [n for n in STANDARD if not n.startswith('portfolio_socp')]
-SOCP_NAMES: List[str] = [n for n in STANDARD if n.startswith('portfolio_socp')]
+SOCP_NAMES: List[str] = [n for n in STANDARD if '_socp_' in n]
+QP_NAMES: List[str] = [n for n in STANDARD if n not in SOCP_NAMES]
 
 
 def code_dir(name: str) -> str:

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Golden vectors for BASELINE config 3 (portfolio SOCP, n=100 assets) produced by the UNMODIFIED vendored ECOS 2.0.8
 (oracle/_ref/libecos_ref.so, built by `make -C oracle ref`) with cvxpygen's settings (feastol=abstol=reltol=1e-8).
-The IPM-CUDA kernel is not built yet; these fixtures pin its oracle for the next round."""
+These fixtures pin the IPM-CUDA kernel and its host emulation; the generic conic families add exit flags 1 and 2."""
 import os
 import sys
 
@@ -25,3 +25,16 @@ out = r.solve_batch(c=Cb, b=Bb)
 np.savez_compressed(os.path.join(HERE, 'socp_portfolio_100_10.npz'), param_a=a, param_w_prev=wp,
                     x=out['x'], y=out['y'], z=out['z'], s=out['s'], pcost=out['pcost'], iter=out['iter'], exitflag=out['exitflag'])
 print('iters', out['iter'].mean(), 'exit', np.unique(out['exitflag']), 'us/solve', out['seconds'] / B * 1e6)
+
+# ---- generic conic families (three cones + equalities; pure LP; no equalities): exit flags 0 / 1 / 2
+sys.path.insert(0, os.path.dirname(HERE))
+from helpers import conic_batch             # noqa: E402
+for fam in (families.random_socp(30, 8, 20, (3, 5, 4), seed=5), families.random_socp(20, 5, 30, (), seed=6),
+            families.random_socp(12, 0, 10, (6,), seed=7)):
+    par, kind = conic_batch(fam, 64, seed=99)
+    r = RefECOS(fam.canon_data('c'), fam.canon_matrix('A'), fam.canon_data('b'), fam.canon_matrix('G'), fam.canon_data('h'),
+                fam.cone_dims['l'], fam.cone_dims['q'])
+    out = r.solve_batch(c=par['c'], h=par['h'], b=par.get('b'))
+    np.savez_compressed(os.path.join(HERE, f'socp_{fam.name}.npz'), kind=kind, **{'param_' + k: v for k, v in par.items()},
+                        x=out['x'], y=out['y'], z=out['z'], s=out['s'], pcost=out['pcost'], iter=out['iter'], exitflag=out['exitflag'])
+    print(fam.name, 'kinds', np.bincount(kind), 'flags', np.unique(out['exitflag'], return_counts=True), 'iters', out['iter'].mean())

@@ -99,3 +99,21 @@ def rounding_stable(fam, q, l, u, ora, **settings):
     those "the reference's result" is itself not defined to 1e-5 and they are excluded from the comparison."""
     o2 = oracle_for(fam, **settings).solve_batch(q=q, l=l, u=u)
     return (o2['iter'] == ora['iter']) & (o2['status'] == ora['status'])
+
+
+def conic_batch(fam, B, seed):
+    """Parameter batch for the generic conic families (cvxpygen_b200.families.random_socp): perturbed defaults, with one
+    instance in eight primal infeasible (LP rows 0/1 contradict) and one in eight unbounded (free direction with negative cost).
+    Returns (params dict, kind) with kind 0 = nominal, 1 = primal infeasible, 2 = dual infeasible."""
+    rng = np.random.default_rng(seed)
+    n, p, m = fam.n_var, fam.n_eq, fam.n_ineq
+    kind = rng.integers(0, 8, B)
+    kind = np.where(kind < 6, 0, kind - 5)
+    c = fam.param('c').default + 0.1 * rng.standard_normal((B, n))
+    h = fam.param('h').default + 0.05 * np.abs(rng.standard_normal((B, m)))
+    out = {'c': c, 'h': h}
+    if p:
+        out['b'] = fam.param('b').default + 0.02 * rng.standard_normal((B, p))
+    h[kind == 1, 1] = -h[kind == 1, 0] - 1.0
+    c[kind == 2, n - 1] = -1.0
+    return out, kind

@@ -137,9 +137,7 @@ def test_exact_restatement_reproduces_the_compiled_reference():
         assert _rel(r['z'], g['z'][k]) < 1e-6
 
 
-@pytest.fixture(scope='module')
-def emu(setup, tmp_path_factory):
-    d = str(tmp_path_factory.mktemp('ipm_emu'))
+def _build_emu(setup, d):
     with open(os.path.join(d, 'cpg_ipm_family.h'), 'w') as f:
         f.write(codegen_ipm.family_header(setup))
     out = os.path.join(d, 'libipm_emu.so')
@@ -147,6 +145,11 @@ def emu(setup, tmp_path_factory):
                         os.path.join(ROOT, 'tests', 'emu', 'ipm_emu.cpp'), '-o', out], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return C.CDLL(out)
+
+
+@pytest.fixture(scope='module')
+def emu(setup, tmp_path_factory):
+    return _build_emu(setup, str(tmp_path_factory.mktemp('ipm_emu')))
 
 
 def _emu_solve(lib, setup, params, maxit=100):
@@ -192,6 +195,44 @@ def test_kernel_phase_logic_maxit_and_best_iterate(emu, setup):
         ref = r.solve_batch(c=Cb, b=Bb)
         assert np.array_equal(ref['exitflag'], out['status']) and np.array_equal(ref['iter'], out['iter'])
         assert _rel(out['x'], ref['x']) < 1e-7 and _rel(out['z'], ref['z']) < 1e-6
+
+
+GENERIC = {'random_socp_30_8_20_3x5x4': lambda: families.random_socp(30, 8, 20, (3, 5, 4), seed=5),
+           'random_socp_20_5_30_lp': lambda: families.random_socp(20, 5, 30, (), seed=6),
+           'random_socp_12_0_10_6': lambda: families.random_socp(12, 0, 10, (6,), seed=7)}
+
+
+def _check_against(g, out_x, out_y, out_z, out_s, status, iters, obj, sl=slice(None)):
+    """exit flags and iteration counts identical; optimal instances to the parity bar; certificates by direction"""
+    flag = g['exitflag'][sl]
+    assert np.array_equal(status, flag) and np.array_equal(iters, g['iter'][sl])
+    assert set(np.unique(flag)) == {0, 1, 2}
+    for k in np.nonzero(flag == 0)[0]:
+        assert _rel(out_x[k], g['x'][sl][k]) < RTOL_PRIMAL and _rel(out_s[k], g['s'][sl][k]) < RTOL_PRIMAL, k
+        assert _rel(out_z[k], g['z'][sl][k]) < RTOL_DUAL, k
+        if out_y.shape[1]:
+            assert _rel(out_y[k], g['y'][sl][k]) < RTOL_DUAL, k
+        assert abs(obj[k] - g['pcost'][sl][k]) < 1e-7 * max(1.0, abs(g['pcost'][sl][k]))
+    for k in np.nonzero(flag == 1)[0]:          # certificate of primal infeasibility: (y, z) (ecos.c:1219-1233)
+        assert _rel(out_z[k], g['z'][sl][k]) < 1e-4, k
+    for k in np.nonzero(flag == 2)[0]:          # certificate of unboundedness: x
+        assert _rel(out_x[k], g['x'][sl][k]) < 1e-4, k
+
+
+@pytest.mark.parametrize('name', list(GENERIC))
+def test_generic_conic_families_on_host_match_golden(name, tmp_path):
+    """Three cones + equalities / a pure LP (no second-order cone) / no equalities: the same kernel source and table
+    generator, host build, against the compiled reference's golden vectors incl. primal- and dual-infeasible instances."""
+    fam = GENERIC[name]()
+    st = ss.setup_socp_family(fam)
+    D = st.defines
+    assert D['NT'] <= ss.MAX_TAIL and (D['NSOC'], D['P']) == (len(fam.cone_dims['q']), fam.n_eq)
+    lib = _build_emu(st, str(tmp_path))
+    g = np.load(os.path.join(GOLDEN, f'socp_{name}.npz'))
+    B = 32
+    P = np.concatenate([g['param_' + p.name][:B] for p in fam.params], axis=1)
+    out = _emu_solve(lib, st, P)
+    _check_against(g, out['x'], out['y'][:, :fam.n_eq], out['z'], out['s'], out['status'], out['iter'], out['obj'], slice(0, B))
 
 
 def test_generated_directory_and_c_abi():
@@ -332,3 +373,27 @@ def test_gpu_portfolio_full_batch_properties():
     out2 = m.solve_batch_device(P, return_canonical=True)
     torch.cuda.synchronize()
     assert (out2.iter == out.iter).all() and _rel(out2.sol_x.cpu().numpy()[ok], x) < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', [n for n in standard.SOCP_NAMES if n.startswith('random_socp')])
+def test_gpu_generic_conic_families(name):
+    """The generic conic families through the C ABI: golden vectors (exit flags 0 / 1 / 2, iteration counts, solutions and
+    certificates) and a fresh batch against the compiled reference."""
+    from helpers import conic_batch
+    fam = standard.STANDARD[name][0]()
+    g = np.load(os.path.join(GOLDEN, f'socp_{name}.npz'))
+    m = standard.load(name)
+    par = {p.name: g['param_' + p.name] for p in fam.params}
+    r = m.solve_batch(par, return_canonical=True)
+    _check_against(g, r.sol_x, r.sol_y, r.sol_z, r.sol_s, r.cpg_info.status, r.cpg_info.iter, r.cpg_info.obj_val)
+    assert np.array_equal(r.cpg_prim['x'], r.sol_x)
+    if ref_ecos.available():
+        par2, kind = conic_batch(fam, 512, seed=7)
+        ref = ref_ecos.RefECOS(fam.canon_data('c'), fam.canon_matrix('A'), fam.canon_data('b'), fam.canon_matrix('G'),
+                               fam.canon_data('h'), fam.cone_dims['l'], fam.cone_dims['q']).solve_batch(c=par2['c'], h=par2['h'], b=par2.get('b'))
+        r2 = m.solve_batch(par2, return_canonical=True)
+        assert np.array_equal(r2.cpg_info.status, ref['exitflag'])
+        assert (np.abs(r2.cpg_info.iter - ref['iter']) <= 1).all() and (r2.cpg_info.iter == ref['iter']).mean() > 0.97
+        ok = (ref['exitflag'] == 0) & (r2.cpg_info.iter == ref['iter'])
+        assert _rel(r2.sol_x[ok], ref['x'][ok]) < 1e-6 and np.allclose(r2.cpg_info.obj_val[ok], ref['pcost'][ok], rtol=1e-7, atol=1e-8)
