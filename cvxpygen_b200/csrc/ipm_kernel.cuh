@@ -201,13 +201,23 @@ IPM_FN double warp_sum(double v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// Maximum over the warp with fmax semantics (NaN entries are ignored), on an order-preserving integer image of the
+// doubles: two REDUX.MAX (high word signed, then low word among the lanes that hold the largest high word) instead of
+// five shuffle + DSETP/SEL rounds -- double has no single-instruction max on this architecture.
 IPM_FN double warp_max(double v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+  if (!(v == v)) v = -INFINITY;
+  long long key = __double_as_longlong(v);
+  key ^= (key >> 63) & 0x7fffffffffffffffLL;
+  const int hi = int(key >> 32);
+  const unsigned lo = unsigned(key);
+  const int mhi = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+  key = (static_cast<long long>(mhi) << 32) | static_cast<long long>(mlo);
+  key ^= (key >> 63) & 0x7fffffffffffffffLL;
+  return __longlong_as_double(key);
 }
 template <int KS, int KM, class F> IPM_FN void phase_red(Sm& sm, int& rb, double* s, double* m, F&& f) {
-  static_assert(KS + KM <= 16, "reduction scratch holds 16 values per warp");
+  static_assert(KS + KM <= 16 && NWARP <= 32, "reduction scratch holds 16 values per warp");
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 #pragma unroll
   for (int k = 0; k < KS; ++k) s[k] = 0.0;
@@ -222,9 +232,22 @@ template <int KS, int KM, class F> IPM_FN void phase_red(Sm& sm, int& rb, double
   for (int k = 0; k < KM; ++k) { double v = warp_max(m[k]); if (lane == 0) buf[wid * 16 + KS + k] = v; }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < KS; ++k) { double v = 0.0; for (int w = 0; w < NWARP; ++w) v += buf[w * 16 + k]; s[k] = v; }
+  if constexpr (KS > 8 && NWARP % 2 == 0) {
+    // many sums (the statistics of an iteration): lane (k, half) adds the partials of half of the warps, one shuffle joins
+    // the halves, KS broadcasts hand every thread every total -- instead of KS * NWARP dependent loads and adds per thread
+    const int k = lane & 15, half = lane >> 4;
+    double v = 0.0;
 #pragma unroll
-  for (int k = 0; k < KM; ++k) { double v = -INFINITY; for (int w = 0; w < NWARP; ++w) v = fmax(v, buf[w * 16 + KS + k]); m[k] = v; }
+    for (int w = 0; w < NWARP / 2; ++w) v += buf[(half * (NWARP / 2) + w) * 16 + k];
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+#pragma unroll
+    for (int j = 0; j < KS; ++j) s[j] = __shfl_sync(0xffffffffu, v, j);
+  } else {
+#pragma unroll
+    for (int k = 0; k < KS; ++k) { double v = 0.0; for (int w = 0; w < NWARP; ++w) v += buf[w * 16 + k]; s[k] = v; }
+  }
+#pragma unroll
+  for (int k = 0; k < KM; ++k) m[k] = warp_max(lane < NWARP ? buf[lane * 16 + KS + k] : -INFINITY);
 }
 struct WarpOps {
   int lane;

@@ -196,3 +196,30 @@ def test_shared_matrix_parameter_update():
     with pytest.raises(ValueError):
         mod.update_shared_params({'b': np.zeros(3)})
     shutil.rmtree(os.path.dirname(d), ignore_errors=True)
+
+
+@pytest.mark.gpu
+def test_host_entry_zero_copy_equals_staged():
+    """cpg_solve_batch_host: result rows stored by the kernels straight into PINNED host buffers (zero-copy) are bit-identical
+    to the staged path (host_zero_copy = 0) and to pageable buffers; canonical x / y outputs included."""
+    import torch
+    name, B = 'mpc_12_4_10', 5000
+    mod = standard.load(name)
+    d = mod.dims
+    xi = torch.from_numpy(np.random.default_rng(5).uniform(-1, 1, (B, 12)))
+
+    def buffers(pinned):
+        mk = lambda shape, dt=torch.float64: (torch.zeros(shape, dtype=dt).pin_memory() if pinned else torch.zeros(shape, dtype=dt))
+        return dict(prim=mk((B, d.n_prim)), dual=mk((B, d.n_dual)), sol_x=mk((B, d.n_var)), sol_y=mk((B, d.n_con)),
+                    obj=mk((B,)), pri=mk((B,)), dua=mk((B,)), it=mk((B,), torch.int32), st=mk((B,), torch.int32))
+    hp = xi.clone().pin_memory()
+    zc = mod.solve_batch_pinned(hp, buffers(True))
+    mod.set_solver_setting('host_zero_copy', 0)
+    staged = mod.solve_batch_pinned(hp, buffers(True))
+    mod.set_solver_setting('host_zero_copy', 1)
+    pageable = mod.solve_batch_pinned(xi, buffers(False))
+    assert (zc['st'] == 1).all() and zc['prim'].abs().sum() > 0
+    for k in zc:
+        assert torch.equal(zc[k], staged[k]) and torch.equal(zc[k], pageable[k]), k
+    with pytest.raises(AttributeError):
+        mod.set_solver_setting('scaling', 3)
