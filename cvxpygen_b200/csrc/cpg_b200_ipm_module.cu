@@ -115,6 +115,19 @@ int CPG_B200_FN(cpg_socp_dims)(CpgB200SocpDims* out) {
   return CPG_B200_OK;
 }
 
+int CPG_B200_FN(cpg_socp_load_constants)(const void* smem_blob, int smem_nbytes, const void* gmem_blob, int gmem_nbytes) {
+  if (!g.ready) { snprintf(g.err, sizeof(g.err), "cpg_b200_init has not been called"); return CPG_B200_ERR_NOT_INIT; }
+  if (!smem_blob || !gmem_blob || smem_nbytes != (int)CPG_B200_FN(cpg_ipm_sblob_nbytes) ||
+      gmem_nbytes != (int)CPG_B200_FN(cpg_ipm_gblob_nbytes)) {
+    snprintf(g.err, sizeof(g.err), "constant tables of a different layout: regenerate the code");
+    return CPG_B200_ERR_BAD_ARG;
+  }
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(g.d_sblob, smem_blob, smem_nbytes, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(g.d_gblob, gmem_blob, gmem_nbytes, cudaMemcpyHostToDevice));
+  return CPG_B200_OK;
+}
+
 void CPG_B200_FN(cpg_socp_default_settings)(CpgB200SocpSettings* s) {
   if (!s) return;
   s->maxit = 100; s->pad_ = 0;

@@ -35,12 +35,14 @@
 #include <vector>
 #define IPM_FN inline
 #define IPM_NOINLINE inline
+#define IPM_HD
 #define IPM_CONST static const
 namespace cpgipm { static long g_count[8] = {0, 0, 0, 0, 0, 0, 0, 0}; }     // emulation statistics: solves, factors, barriers
 #define IPM_COUNT(i) (++cpgipm::g_count[i])
 #else
 #define IPM_FN __device__ __forceinline__
 #define IPM_NOINLINE __device__ __noinline__
+#define IPM_HD __host__ __device__
 #define IPM_CONST __constant__ const
 #define IPM_COUNT(i) ((void)0)
 #endif
@@ -355,7 +357,69 @@ template <class Shape, class E, class D, int TB> struct Plan {
     if (((d >> (TB + 3)) & 1u) && (lane & (g - 1)) == 0) commit(int(d & ((1u << TB) - 1u)), int((d >> (TB + 4)) & 1u), acc);
 #endif
   }
+  // total unrolled trip count of a phase (compile time)
+  IPM_HD static constexpr int phase_entries(int ph_) {
+    int n = 0;
+    for (int r = Shape::ph[ph_]; r < Shape::ph[ph_ + 1]; ++r) n += Shape::lmax[r];
+    return n;
+  }
+  IPM_HD static constexpr int phase_lmax(int ph_) {
+    int n = 1;
+    for (int r = Shape::ph[ph_]; r < Shape::ph[ph_ + 1]; ++r) n = Shape::lmax[r] > n ? Shape::lmax[r] : n;
+    return n;
+  }
+#ifndef CPG_IPM_HOST_EMU
+  // The rounds of one phase are independent (no target of a phase is a source in it), so a short multi-round phase runs
+  // stage by stage ACROSS its rounds -- all table reads, then all operand reads and sums, then the butterflies, then the
+  // commits: one warp has several dependent chains in flight instead of one (the kernel is latency bound).
+  template <int PH, class V, class C> IPM_FN void run_staged(V&& value, C&& commit) const {
+    constexpr int R0 = Shape::ph[PH], NR = Shape::ph[PH + 1] - R0, LM = phase_lmax(PH);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned m[NR], d[NR];
+    E ev[NR][LM];
+    double acc[NR];
+    static_for<0, NR>([&](auto r) {
+      constexpr int i = decltype(r)::value;
+      m[i] = wr[(R0 + i) * NWARP + wid];
+      d[i] = desc[(R0 + i) * T + tid];
+    });
+    static_for<0, NR>([&](auto r) {
+      constexpr int i = decltype(r)::value, LMAX = Shape::lmax[R0 + i], LMIN = Shape::lmin[R0 + i];
+      const E* e = ent + (m[i] & 0xfffffu) + lane;
+      const int len = int(m[i] >> 20);
+#pragma unroll
+      for (int j = 0; j < LMAX; ++j) if (j < LMIN || j < len) ev[i][j] = e[j * 32];
+    });
+    static_for<0, NR>([&](auto r) {
+      constexpr int i = decltype(r)::value, LMAX = Shape::lmax[R0 + i], LMIN = Shape::lmin[R0 + i];
+      const int len = int(m[i] >> 20);
+      double a = 0.0;
+#pragma unroll
+      for (int j = 0; j < LMAX; ++j) if (j < LMIN || j < len) a += value(ev[i][j]);
+      acc[i] = a;
+    });
+    static_for<0, NR>([&](auto r) {
+      constexpr int i = decltype(r)::value, SMAX = Shape::smax[R0 + i];
+      const int g = 1 << ((d[i] >> TB) & 7u);
+#pragma unroll
+      for (int s = 0; s < SMAX; ++s) {
+        const double v = __shfl_xor_sync(0xffffffffu, acc[i], 1 << s);
+        if ((1 << s) < g) acc[i] += v;
+      }
+    });
+    static_for<0, NR>([&](auto r) {
+      constexpr int i = decltype(r)::value;
+      const int g = 1 << ((d[i] >> TB) & 7u);
+      if (((d[i] >> (TB + 3)) & 1u) && (lane & (g - 1)) == 0)
+        commit(int(d[i] & ((1u << TB) - 1u)), int((d[i] >> (TB + 4)) & 1u), acc[i]);
+    });
+  }
+#endif
   template <int PH, class V, class C> IPM_FN void run(V&& value, C&& commit) const {
+#ifndef CPG_IPM_HOST_EMU
+    constexpr int NR = Shape::ph[PH + 1] - Shape::ph[PH];
+    if constexpr (NR >= 2 && phase_entries(PH) * int(sizeof(E)) <= 96) { run_staged<PH>(value, commit); return; }
+#endif
     static_for<Shape::ph[PH], Shape::ph[PH + 1]>([&](auto r) { this->template round<decltype(r)::value>(value, commit); });
   }
 };

@@ -388,7 +388,38 @@ class SocpModule(Module):
         setattr(self.settings, name, value)
 
     def update_shared_params(self, values):
-        raise NotImplementedError('shared-parameter updates are not generated for IPM-CUDA yet: regenerate the code')
+        """Change user parameters shared by the whole batch: the offline setup (equilibration, KKT base image, affine maps)
+        is re-run on the host and both constant images are re-uploaded -- what ECOS_updateData does for the reference
+        (cvxpygen/solvers/ecos.py:88-117).  The compiled schedule must stay valid: same sparsity structure, same constant
+        objective offset.  Needs the cvxpygen_b200 package."""
+        import pickle
+        from cvxpygen_b200 import codegen_ipm
+        from cvxpygen_b200.offline.socp_setup import setup_socp_family
+        with open(os.path.join(self.code_dir, 'cpg_family.pkl'), 'rb') as f:
+            saved = pickle.load(f)
+        fam = saved['family']
+        if not hasattr(self, '_theta'):
+            self._theta = fam.theta_default()
+        for name, val in values.items():
+            p = fam.param(name)
+            if name in saved['batch_params']:
+                raise ValueError(f'{name} is a batched parameter: pass it per instance to solve_batch')
+            v = np.asarray(val, dtype=float)
+            v = v.flatten(order='F') if v.ndim > 1 else v.ravel()
+            if v.size != p.size:
+                raise ValueError(f'parameter {name} stores {p.size} entries, got {v.size}')
+            self._theta[p.col:p.col + p.size] = v
+        st = setup_socp_family(fam, saved['batch_params'], theta=self._theta, threads=saved['threads'])
+        strip = lambda txt: '\n'.join(txt.split('\n')[1:])            # first line carries the generation date
+        with open(os.path.join(self.code_dir, 'c', 'include', 'cpg_ipm_family.h')) as f:
+            compiled = f.read()
+        if strip(codegen_ipm.family_header(st, self.prefix)) != strip(compiled):
+            raise RuntimeError('the new parameter values change the compiled schedule (sparsity structure or objective offset): '
+                               'regenerate the code (cpg.generate_code)')
+        self.init()
+        b = lambda x: (C.c_char_p(x), C.c_int(len(x)))
+        self._check(self._fn('cpg_socp_load_constants')(*b(st.smem_blob), *b(st.gmem_blob)))
+        return st
 
     def solve_batch(self, params, return_canonical=False, **settings):
         self.init()

@@ -58,6 +58,11 @@ int  CPG_B200_FN(cpg_b200_free)(void);
 const char* CPG_B200_FN(cpg_b200_last_error)(void);
 int  CPG_B200_FN(cpg_b200_launch_count)(void);               /* kernels launched by the last solve call */
 int  CPG_B200_FN(cpg_socp_dims)(CpgB200SocpDims* out);
+/* Replace the constant tables after a change of SHARED (non-batched) user parameters: the host re-runs the offline setup
+ * (equilibration, KKT base image, affine maps) and uploads both images.  Role of ECOS_updateData for data every instance
+ * shares (cvxpygen/solvers/ecos.py:88-117, ecos/src/ecos.c:1648-1760).  The sizes must equal those compiled in: a change of
+ * the sparsity structure needs regenerated code.  Synchronises the device. */
+int  CPG_B200_FN(cpg_socp_load_constants)(const void* smem_blob, int smem_nbytes, const void* gmem_blob, int gmem_nbytes);
 void CPG_B200_FN(cpg_socp_default_settings)(CpgB200SocpSettings* s);
 
 /* Batched solve, DEVICE buffers (row-major, one instance per row), asynchronous on `stream`.

@@ -397,3 +397,36 @@ def test_gpu_generic_conic_families(name):
         assert (np.abs(r2.cpg_info.iter - ref['iter']) <= 1).all() and (r2.cpg_info.iter == ref['iter']).mean() > 0.97
         ok = (ref['exitflag'] == 0) & (r2.cpg_info.iter == ref['iter'])
         assert _rel(r2.sol_x[ok], ref['x'][ok]) < 1e-6 and np.allclose(r2.cpg_info.obj_val[ok], ref['pcost'][ok], rtol=1e-7, atol=1e-8)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not ref_ecos.available(), reason='oracle/_ref/libecos_ref.so not built')
+def test_gpu_shared_parameter_update(tmp_path):
+    """A user parameter that is NOT batched is shared by every instance: changing it re-runs the offline setup on the host
+    and re-uploads both constant images (cpg_socp_load_constants) -- the role of ECOS_updateData for shared data."""
+    from cvxpygen_b200 import cpg
+    from helpers import conic_batch
+    fam = families.random_socp(20, 5, 30, (4,), seed=8)
+    d = str(tmp_path / 'conic_shared')
+    cpg.generate_code(fam, code_dir=d, solver='IPM-CUDA', batch_params=['c', 'h'], wrapper=True)
+    m = runtime.load(d)
+    par, kind = conic_batch(fam, 96, seed=21)
+    ref = ref_ecos.RefECOS(fam.canon_data('c'), fam.canon_matrix('A'), fam.canon_data('b'), fam.canon_matrix('G'),
+                           fam.canon_data('h'), fam.cone_dims['l'], fam.cone_dims['q'])
+
+    def check(b):
+        r = m.solve_batch({'c': par['c'], 'h': par['h']}, return_canonical=True)
+        o = ref.solve_batch(c=par['c'], h=par['h'], b=np.tile(b, (96, 1)))
+        assert np.array_equal(r.cpg_info.status, o['exitflag']) and (np.abs(r.cpg_info.iter - o['iter']) <= 1).all()
+        ok = (o['exitflag'] == 0) & (r.cpg_info.iter == o['iter'])
+        assert ok.sum() > 40 and _rel(r.sol_x[ok], o['x'][ok]) < 1e-6
+        return r
+    r0 = check(fam.param('b').default)
+    b_new = fam.param('b').default + 0.05 * np.random.default_rng(3).standard_normal(fam.n_eq)
+    m.update_shared_params({'b': b_new})
+    r1 = check(b_new)
+    assert _rel(r1.sol_x, r0.sol_x) > 1e-4                      # the update is visible in the solutions
+    with pytest.raises(ValueError):
+        m.update_shared_params({'c': par['c'][0]})                # batched parameters go through solve_batch
+    with pytest.raises(AttributeError):
+        m.update_shared_params({'nope': 1.0})
