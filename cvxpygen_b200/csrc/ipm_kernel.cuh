@@ -470,7 +470,12 @@ struct Solver {
           });
       sync_phase();
     });
+#ifdef CPG_IPM_HOST_EMU
     phase([&](int tid) { tail_factor(tid); });
+#else
+    tail_factor(int(threadIdx.x));
+    __syncthreads();
+#endif
   }
 
   // ---- triangular solves, in place on u (k-space)
@@ -662,38 +667,40 @@ IPM_FN void Solver::tail_factor(int tid) {
   for (int j = 0; j < NT; ++j) sm.S()[DG0 + sm.tail_k()[j]] = dv[j];
   for (int m = 0; m < NT; ++m) for (int c = 0; c < m; ++c) B[m * NT + c] = X[m * NT + c];
 #else
-  if (NT == 0 || tid >= 32) return;
+  // Right-looking elimination with one thread per entry (i, k), k <= i, of the block: step j takes the pivot (every
+  // participating thread inverts it itself -- the inverse is kept in sm.tw so that the raw pivot stays readable), updates
+  // the trailing entries, one CTA barrier per step.  Then one warp turns the unit triangle into its inverse, lane = column.
   constexpr int NTT = NT > 0 ? NT : 1;
-  const int i = tid;
-  const bool on = i < NT;
-  const int ki = on ? sm.tail_k()[i] : 0;
+  constexpr int NEL = NT * (NT + 1) / 2;
+  static_assert(NEL <= T, "one thread per entry of the tail block");
+  if (NT == 0) return;
   double* B = sm.S() + TT0;
-  double r[NTT], x[NTT], dv[NTT];      // row i of the block (S_ik = L_ik D_k), column i of inv(L), inverse pivots (uniform)
-#pragma unroll
-  for (int k = 0; k < NT; ++k) r[k] = (on && k < i) ? B[i * NT + k] : 0.0;
-  double d = on ? sm.S()[DG0 + ki] : 1.0;
-#pragma unroll
+  int ei = 0, ek = 0;                                   // (i, k) of this thread's entry: tid = i (i + 1) / 2 + k
+  if (tid < NEL) { while ((ei + 1) * (ei + 2) / 2 <= tid) ++ei; ek = tid - ei * (ei + 1) / 2; }
+  const int kslot = tid < NEL ? (ei == ek ? DG0 + int(sm.tail_k()[ei]) : TT0 + ei * NT + ek) : 0;
   for (int j = 0; j < NT; ++j) {
-    const double ij = inv_pivot(sm.tail_k()[j], __shfl_sync(0xffffffffu, d, j));
-    dv[j] = ij;
-    if (i == j) sm.S()[DG0 + ki] = ij;
-    const double sij = r[j];
-#pragma unroll
-    for (int k = j + 1; k < NT; ++k) {
-      const double t = sij * __shfl_sync(0xffffffffu, r[j], k) * ij;
-      if (i > k) r[k] -= t;
-      if (i == k) d -= t;
+    if (tid < NEL && ek >= j) {
+      const int kj = sm.tail_k()[j];
+      const double ij = inv_pivot(kj, sm.S()[DG0 + kj]);
+      if (ek > j) sm.S()[kslot] -= (B[ei * NT + j] * B[ek * NT + j]) * ij;
+      else if (ei == j) sm.tw()[j] = ij;                 // the thread of entry (j, j)
     }
+    __syncthreads();
   }
+  if (tid >= 32) return;
+  const int c = tid;                                    // column of inv(L) held by this lane
+  double x[NTT];
 #pragma unroll
   for (int m = 0; m < NT; ++m) {
     double a = 0.0;
 #pragma unroll
-    for (int k = 0; k < m; ++k) a -= (__shfl_sync(0xffffffffu, r[k], m) * dv[k]) * x[k];
-    x[m] = m == i ? 1.0 : a;
+    for (int k = 0; k < m; ++k) a -= (B[m * NT + k] * sm.tw()[k]) * x[k];
+    x[m] = m == c ? 1.0 : a;
   }
+  __syncwarp();
 #pragma unroll
-  for (int m = 1; m < NT; ++m) if (on && i < m) B[m * NT + i] = x[m];
+  for (int m = 1; m < NT; ++m) if (c < m && c < NT) B[m * NT + c] = x[m];
+  if (c < NT) sm.S()[DG0 + sm.tail_k()[c]] = sm.tw()[c];
 #endif
 }
 
