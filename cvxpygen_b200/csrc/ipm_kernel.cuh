@@ -281,6 +281,17 @@ template <int CNT> struct PerThread {
 #endif
 
 template <class F> IPM_FN void each_k(int tid, int n, F&& f) { for (int i = tid; i < n; i += T) f(i); }
+// elementwise work of a phase whose second-order cones are handled by the last warps (run_cones): those warps are left
+// out here, so that the cone arithmetic overlaps the elementwise part instead of following it
+constexpr int CONE_WARPS = NSOC < NWARP - 1 ? NSOC : NWARP - 1;
+#ifdef CPG_IPM_HOST_EMU
+template <class F> IPM_FN void each_k_nc(int tid, int n, F&& f) { each_k(tid, n, f); }
+#else
+template <class F> IPM_FN void each_k_nc(int tid, int n, F&& f) {
+  constexpr int TN = T - 32 * CONE_WARPS;
+  if (tid < TN) for (int i = tid; i < n; i += TN) f(i);
+}
+#endif
 
 IPM_CONST int kSocSo[NSOC > 0 ? NSOC : 1] = IPM_SOC_SO;      // stretched z offset of each cone
 IPM_CONST int kSocD[NSOC > 0 ? NSOC : 1] = IPM_SOC_D;        // cone sizes
@@ -845,6 +856,7 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
         s[1] += hr * hr; s[4] += b * y; s[7] += y * y;
         const double r = hr - tau * b; sm.rhs()[k] = r; s[12] += r * r;
       });
+      each_k(tid, NS, [&](int i) { sm.S()[i] = gm.Sbase[i]; });      // constant part of K for this iteration's kkt_update
       each_k(tid, MT, [&](int i) {
         const double hr = sm.rz()[i], h = sm.cbh()[ZOFF + i], z = zv[i], sv = sm.sv()[i];
         s[2] += hr * hr; s[5] += h * z; s[8] += sv * sv; s[9] += z * z; s[10] += sv * z;
@@ -901,11 +913,10 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
     phase_cones(
         [&](int tid) {
           if (tid == 0) *sm.flag() = 0;
-          each_k(tid, L, [&](int i) {
+          each_k_nc(tid, L, [&](int i) {
             const double v = safediv(sm.sv()[i], zv[i]), w = sqrt(v);
             sm.v()[i] = v; sm.w()[i] = w; sm.lam()[i] = w * zv[i];
           });
-          each_k(tid, NS, [&](int i) { sm.S()[i] = gm.Sbase[i]; });
         },
         [&](int c, const WarpOps& W) {
           const int so = kSocSo[c], d = kSocD[c];
@@ -949,7 +960,7 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
     }
     // kkt_update: the scaling block
     phase_cones(
-        [&](int tid) { each_k(tid, L, [&](int i) { sm.S()[DG0 + ZOFF + i] = -sm.v()[i] - kDeltaStat; }); },
+        [&](int tid) { each_k_nc(tid, L, [&](int i) { sm.S()[DG0 + ZOFF + i] = -sm.v()[i] - kDeltaStat; }); },
         [&](int c, const WarpOps& W) {
           const int so = kSocSo[c], d = kSocD[c];
           const double* q = sm.q() + kSocQo[c]; const double* sc = sm.sc() + 8 * c;
@@ -982,8 +993,8 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
       // px_z += dt * sol1_z (all of px when combined); wdz = W px_z; dsw = -(combined ? dsw : lam) - wdz
       phase_red_cones<0, 2>(sm, rb, s_, m_,
           [&](int tid, double*, double* m) {
-            each_k(tid, combined ? ZOFF : 0, [&](int k) { sm.px()[k] += dt * sm.sol1()[k]; });
-            each_k(tid, L, [&](int i) {
+            each_k_nc(tid, combined ? ZOFF : 0, [&](int k) { sm.px()[k] += dt * sm.sol1()[k]; });
+            each_k_nc(tid, L, [&](int i) {
               const double dz = sm.px()[ZOFF + i] + dt * sm.sol1()[ZOFF + i];
               sm.px()[ZOFF + i] = dz;
               const double wz = sm.w()[i] * dz, lam = sm.lam()[i];
@@ -1025,8 +1036,8 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
     // RHS_combined (ecos.c:688-757): dsw <- lambda \ (lambda o lambda + dsw o wdz - sigma mu e); rhs_z = -(1-sigma) rz + W dsw
     phase_cones(
         [&](int tid) {
-          each_k(tid, ZOFF, [&](int k) { sm.rhs()[k] *= oms; });
-          each_k(tid, L, [&](int i) {
+          each_k_nc(tid, ZOFF, [&](int k) { sm.rhs()[k] *= oms; });
+          each_k_nc(tid, L, [&](int i) {
             const double lam = sm.lam()[i];
             const double ds1 = lam * lam + sm.dsw()[i] * wdz[i] - sigmamu;
             const double dv = safediv(ds1, lam);
@@ -1067,8 +1078,8 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
     // ds = W (W\ds); update the iterate
     phase_cones(
         [&](int tid) {
-          each_k(tid, ZOFF + L, [&](int k) { sm.xyz()[k] += step * sm.px()[k]; });
-          each_k(tid, L, [&](int i) { sm.sv()[i] += step * (sm.w()[i] * sm.dsw()[i]); });
+          each_k_nc(tid, ZOFF + L, [&](int k) { sm.xyz()[k] += step * sm.px()[k]; });
+          each_k_nc(tid, L, [&](int i) { sm.sv()[i] += step * (sm.w()[i] * sm.dsw()[i]); });
         },
         [&](int c, const WarpOps& W) {
           const int so = kSocSo[c], d = kSocD[c];

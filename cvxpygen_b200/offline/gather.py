@@ -105,9 +105,11 @@ def _cost(cells, nwarp, c_fixed=10.0, c_entry=1.0, c_shuf=3.0):
     return max(per_warp)
 
 
-def add_phase(plan: GatherPlan, rows: Sequence[Tuple[int, int, Sequence[Tuple[int, ...]]]]) -> None:
-    """rows: (target, flag, entries).  Appends one phase (possibly of zero rounds) to the plan."""
+def add_phase(plan: GatherPlan, rows: Sequence[Tuple[int, int, Sequence[Tuple[int, ...]]]], use_warps: int = 0) -> None:
+    """rows: (target, flag, entries).  Appends one phase (possibly of zero rounds) to the plan.  use_warps > 0 deals the
+    cells to the first use_warps warps only (the others are busy with something else during this phase)."""
     T, NW = plan.T, plan.nwarp
+    NU = use_warps if 0 < use_warps < NW else NW
     lo = plan.n_rounds
     rows = [(int(t), int(f), [tuple(int(v) for v in e) for e in ent]) for t, f, ent in rows]
     if not rows:
@@ -118,12 +120,12 @@ def add_phase(plan: GatherPlan, rows: Sequence[Tuple[int, int, Sequence[Tuple[in
     best = None
     for q in range(qmin, max(qmin, min(cmax, 64)) + 1):
         cells = _cells_for(rows, q)
-        cost = _cost(cells, NW)
+        cost = _cost(cells, NU)
         if best is None or cost < best[0]:
             best = (cost, q, cells)
     cells = best[2]
     assert all(t < (1 << plan.tbits) for t, _, _ in rows)
-    dealt = _deal(cells, NW)
+    dealt = _deal(cells, NU)
     n_rounds = dealt[-1][0] + 1
     desc = [0] * (n_rounds * T)
     wr = {(r, w): chunk for r, w, chunk in dealt}

@@ -276,7 +276,11 @@ def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None
     for e, (r, c_) in enumerate(zip(mr_t, mr_s)):
         mv_rows[int(r)].append((int(c_), e)); mv_rows[int(c_)].append((int(r), e))
     plan_mv = _gather.GatherPlan(T=threads, nfields=2, tbits=11, null_entry=(len(ag_val), 0))
-    _gather.add_phase(plan_mv, [(k, 0, [(e, src) for src, e in sorted(mv_rows[k])]) for k in range(nk)])
+    # the kernel runs the second-order cones of a residual on its last warps while the others gather: leave those out
+    nwarp = threads // 32
+    cone_warps = min(nsoc, nwarp - 1)
+    _gather.add_phase(plan_mv, [(k, 0, [(e, src) for src, e in sorted(mv_rows[k])]) for k in range(nk)],
+                      use_warps=nwarp - cone_warps)
     # (b) forward substitution: phase 0 scales the leaves, phase lv pulls row k from the columns below, the last phase
     #     (flag 1) collects the tail rows;  entry = (slot of S, source k).  Leaves (level 0) have nothing to pull.
     fw_rows = {}
