@@ -245,8 +245,10 @@ int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const doubl
   io.tail_state = g.d_tail_state; io.B = B; io.tail_capacity = g.tail_cap;
   CK(cudaMemsetAsync(g.d_counter, 0, sizeof(unsigned int), stream));
   CK(cudaMemsetAsync(g.d_tail_count, 0, sizeof(int), stream));
+  // one persistent CTA per SM; a batch smaller than one wave of slots is still spread over all SMs (every warp pulls its
+  // instances from the global counter), so that few warps share an SM's shared-memory bandwidth: lower latency
   int grid = g.n_sm;
-  const int need = (B + Fam::NI * Fam::WARPS - 1) / (Fam::NI * Fam::WARPS);
+  const int need = (B + Fam::NI - 1) / Fam::NI;
   if (grid > need) grid = need;
   cpgb200::admm_multi_kernel<Fam><<<grid, Fam::WARPS * 32, SMEM_BYTES, stream>>>(g.d_blob, io, st);
   g.launches += 1;
