@@ -226,10 +226,59 @@ __device__ __forceinline__ void tail_solve(const TailView& tv, const double* S, 
   if (nt == nf) { for (int i = lane; i < nk; i += LANES) w[i] *= S[i]; __syncwarp(); }
 }
 
+// ---------------------------------------------------------------- matrix-parameter path
+// Tables of offline/blob.py:pack_matpar_blob in GLOBAL memory + the per-warp shared arrays that hold ONE instance's
+// scaled matrices and scalings (filled by matpar_prepare, matpar_kernel.cuh).
+struct MatView {
+  const CpgMatHeader* H;
+  const int* I32;
+  const double* F64;
+  const uint16_t* U16;
+};
+__device__ __forceinline__ MatView make_mat_view(const uint8_t* blob) {
+  MatView mv;
+  mv.H = reinterpret_cast<const CpgMatHeader*>(blob);
+  mv.I32 = reinterpret_cast<const int*>(blob + mv.H->off_i32);
+  mv.F64 = reinterpret_cast<const double*>(blob + mv.H->off_f64);
+  mv.U16 = reinterpret_cast<const uint16_t*>(blob + mv.H->off_u16);
+  return mv;
+}
+struct MatCtx {
+  MatView mv;
+  double* Av;             // nnzA + 1 scaled entries of A in CSC order (last = 0: padding target of the index tables)
+  double* Pv;             // nnzP + 1 scaled entries of the upper triangle of P
+  double* D; double* Dinv; double* E; double* Einv;   // this instance's equilibration (scaling.c:44-156)
+  double c, cinv;
+};
+// row-blocked ELL of INDICES: entry k of lane's row is value vals[idx[k*32+lane]] times vec[col[k*32+lane]]
+__device__ __forceinline__ double ellx_dot(const int* __restrict__ tab, const uint16_t* __restrict__ U16,
+                                           const double* vals, const double* vec, int lane) {
+  const int K = __ldg(tab);
+  const uint16_t* ix = U16 + __ldg(tab + 1) + lane;
+  const uint16_t* c = U16 + __ldg(tab + 2) + lane;
+  double a0 = 0.0, a1 = 0.0;
+  int k = 0;
+  for (; k + 1 < K; k += 2) {
+    a0 = fma(vals[__ldg(ix + k * LANES)], vec[__ldg(c + k * LANES)], a0);
+    a1 = fma(vals[__ldg(ix + (k + 1) * LANES)], vec[__ldg(c + (k + 1) * LANES)], a1);
+  }
+  if (k < K) a0 = fma(vals[__ldg(ix + k * LANES)], vec[__ldg(c + k * LANES)], a0);
+  return a0 + a1;
+}
+__device__ __forceinline__ double ellx_absmax(const int* __restrict__ tab, const uint16_t* __restrict__ U16,
+                                              const double* vals, int lane) {
+  const int K = __ldg(tab);
+  const uint16_t* ix = U16 + __ldg(tab + 1) + lane;
+  double a = 0.0;
+  for (int k = 0; k < K; ++k) a = fmax(a, fabs(vals[__ldg(ix + k * LANES)]));
+  return a;
+}
+
 struct TailArgs {
   TailView tv;
   double* S;              // per-warp shared memory, n_slots doubles
   const double* state;    // x(n) z(m) y(m) rho iter of the handed-off instance
+  MatCtx* mc;             // MODE 2 only
 };
 
 // ---------------------------------------------------------------- per-instance solver
@@ -253,17 +302,33 @@ struct Instance {
   }
 };
 
-template <class Fam, bool TAIL>
+// MODE 0: family factor from the blob (legacy one-instance-per-warp path); MODE 1: tail kernel, per-instance factor of
+// K(rho_vec) with the family's matrices; MODE 2: matrix-parameter kernel, per-instance matrices, scalings and factor.
+template <class Fam, int MODE>
 __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* __restrict__ I32,
                                const double* __restrict__ F64, const uint16_t* __restrict__ U16,
                                double* __restrict__ w, const int lane, const int b,
                                const BatchIO& io, const Settings& st, const TailArgs* ta) {
   using I = Instance<Fam>;
   constexpr int N = I::N, M = I::M, NXL = I::NXL, NZL = I::NZL;
+  constexpr bool TAIL = MODE >= 1, MATPAR = MODE == 2;
   I s;
-  const double* Dv = F64 + H->f_D;  const double* Dinv = F64 + H->f_Dinv;
-  const double* Ev = F64 + H->f_E;  const double* Einv = F64 + H->f_Einv;
-  const double c = H->c, cinv = H->cinv, sigma = H->sigma, alpha = st.alpha;
+  const double* Dv = MATPAR ? ta->mc->D : F64 + H->f_D;  const double* Dinv = MATPAR ? ta->mc->Dinv : F64 + H->f_Dinv;
+  const double* Ev = MATPAR ? ta->mc->E : F64 + H->f_E;  const double* Einv = MATPAR ? ta->mc->Einv : F64 + H->f_Einv;
+  const double c = MATPAR ? ta->mc->c : H->c, cinv = MATPAR ? ta->mc->cinv : H->cinv, sigma = H->sigma, alpha = st.alpha;
+  // products with A, A' and the full symmetric P: family constants (blob ELL) or this instance's values (index ELL)
+  auto dotA = [&](int k, const double* vec) -> double {
+    if constexpr (MATPAR) return ellx_dot(ta->mc->mv.I32 + ta->mc->mv.H->i_ixA + 3 * k, ta->mc->mv.U16, ta->mc->Av, vec, lane);
+    else return ell_dot(I32 + H->i_ellA + 3 * k, F64, U16, vec, lane);
+  };
+  auto dotAt = [&](int k, const double* vec) -> double {
+    if constexpr (MATPAR) return ellx_dot(ta->mc->mv.I32 + ta->mc->mv.H->i_ixAt + 3 * k, ta->mc->mv.U16, ta->mc->Av, vec, lane);
+    else return ell_dot(I32 + H->i_ellAt + 3 * k, F64, U16, vec, lane);
+  };
+  auto dotP = [&](int k, const double* vec) -> double {
+    if constexpr (MATPAR) return ellx_dot(ta->mc->mv.I32 + ta->mc->mv.H->i_ixP + 3 * k, ta->mc->mv.U16, ta->mc->Pv, vec, lane);
+    else return ell_dot(I32 + H->i_ellP + 3 * k, F64, U16, vec, lane);
+  };
   const bool unscale = st.scaling && !st.scaled_termination;
 
   // ---- a1/a2/a3: canonicalise the instance's vectors and scale them (q <- c D q ; l,u <- E l, E u)
@@ -326,7 +391,16 @@ __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* _
     if (TAIL) {
       const TailView& tv = ta->tv;
       double* S = ta->S;
-      for (int i = lane; i < tv.H->n_slots; i += LANES) S[i] = tv.F64[tv.H->f_S0 + i];
+      if constexpr (MATPAR) {          // form_KKT with this instance's scaled P and A (kkt.c:6-177): sigma on the x diagonal,
+        const MatCtx& mc = *ta->mc;    // P (upper triangle) and A scattered to their slots of the permuted lower triangle
+        const CpgMatHeader* MH = mc.mv.H;
+        for (int i = lane; i < MH->n_slots; i += LANES) S[i] = __ldg(mc.mv.F64 + MH->f_S0 + i);
+        __syncwarp();
+        for (int e = lane; e < MH->nnzP; e += LANES) S[__ldg(mc.mv.U16 + MH->h_Pslot + e)] += mc.Pv[e];
+        for (int e = lane; e < MH->nnzA; e += LANES) S[__ldg(mc.mv.U16 + MH->h_Aslot + e)] = mc.Av[e];
+      } else {
+        for (int i = lane; i < tv.H->n_slots; i += LANES) S[i] = tv.F64[tv.H->f_S0 + i];
+      }
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < NZL; ++k) {
@@ -337,7 +411,7 @@ __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* _
       tail_factor(tv, S, lane);
     }
   };
-  if (TAIL) {
+  if (TAIL && !MATPAR) {
     const double* ts = ta->state;
 #pragma unroll
     for (int k = 0; k < NXL; ++k) { const int i = lane + 32 * k; if (i < N) s.x[k] = ts[i]; }
@@ -361,15 +435,16 @@ __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* _
 #pragma unroll
     for (int k = 0; k < NZL; ++k) {
       const int j = lane + 32 * k;
-      if (j < M) s.z[k] = ell_dot(I32 + H->i_ellA + 3 * k, F64, U16, w, lane);
+      if (j < M) s.z[k] = dotA(k, w);
     }
     __syncwarp();
   }
+  if constexpr (MATPAR) refactor();    // every instance owns its factor (update_matrices + update_rho_vec)
 
   int status = ST_UNSOLVED;
   int it = 0;
   double rho_new = rho_in;
-  bool handoff = !TAIL && type_mismatch;     // a constraint changed type: this instance needs its own KKT factor
+  bool handoff = !TAIL && type_mismatch;     // (MODE 0 only)     // a constraint changed type: this instance needs its own KKT factor
 
   // ---- residuals + norms of the current iterate (update_info, auxil.c:564-629)
   auto update_info = [&]() {
@@ -383,7 +458,7 @@ __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* _
     for (int k = 0; k < NZL; ++k) {
       const int j = lane + 32 * k;
       if (j < M) {
-        const double Ax = ell_dot(I32 + H->i_ellA + 3 * k, F64, U16, w, lane);
+        const double Ax = dotA(k, w);
         const double rp = Ax - s.z[k];
         const double e = unscale ? Einv[j] : 1.0;
         m_rp = fmax(m_rp, fabs(e * rp)); m_z = fmax(m_z, fabs(e * s.z[k])); m_Ax = fmax(m_Ax, fabs(e * Ax));
@@ -395,8 +470,8 @@ __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* _
     for (int k = 0; k < NXL; ++k) {
       const int i = lane + 32 * k;
       if (i < N) {
-        const double Px = ell_dot(I32 + H->i_ellP + 3 * k, F64, U16, w, lane);
-        const double Aty = (M > 0) ? ell_dot(I32 + H->i_ellAt + 3 * k, F64, U16, w, lane) : 0.0;
+        const double Px = dotP(k, w);
+        const double Aty = (M > 0) ? dotAt(k, w) : 0.0;
         const double rd = s.q[k] + Px + Aty;
         const double d = unscale ? Dinv[i] : 1.0;
         m_rd = fmax(m_rd, fabs(d * rd)); m_q = fmax(m_q, fabs(d * s.q[k]));
@@ -455,7 +530,7 @@ __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* _
             for (int k = 0; k < NXL; ++k) {
               const int i = lane + 32 * k;
               if (i < N) {
-                double v = ell_dot(I32 + H->i_ellAt + 3 * k, F64, U16, w, lane);
+                double v = dotAt(k, w);
                 if (unscale) v *= Dinv[i];
                 mx = fmax(mx, fabs(v));
               }
@@ -488,7 +563,7 @@ __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* _
           for (int k = 0; k < NXL; ++k) {
             const int i = lane + 32 * k;
             if (i < N) {
-              double v = ell_dot(I32 + H->i_ellP + 3 * k, F64, U16, w, lane);
+              double v = dotP(k, w);
               if (unscale) v *= Dinv[i];
               mx = fmax(mx, fabs(v));
             }
@@ -499,7 +574,7 @@ __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* _
             for (int k = 0; k < NZL; ++k) {
               const int j = lane + 32 * k;
               if (j < M) {
-                double v = ell_dot(I32 + H->i_ellA + 3 * k, F64, U16, w, lane);
+                double v = dotA(k, w);
                 if (unscale) v *= Einv[j];
                 bad |= ((s.u[k] < OSQP_INFTY * MIN_SCALING) && (v > edi * nd)) ||
                        ((s.l[k] > -OSQP_INFTY * MIN_SCALING) && (v < -edi * nd));
@@ -672,10 +747,11 @@ admm_tail_kernel(const uint8_t* __restrict__ blob_g, const uint8_t* __restrict__
   TailArgs ta;
   ta.tv = make_tail_view(tail_blob_g);
   ta.S = wbase + Fam::W_STRIDE;
+  ta.mc = nullptr;
   for (int slot = blockIdx.x * Fam::TAIL_WARPS + warp; slot < n_tail; slot += gridDim.x * Fam::TAIL_WARPS) {
     ta.state = io.tail_state + (size_t)slot * (Fam::N + 2 * Fam::M + 2);
     const int b = io.tail_ids[slot];
-    solve_instance<Fam, true>(H, I32, F64, U16, wbase, lane, b, io, st, &ta);
+    solve_instance<Fam, 1>(H, I32, F64, U16, wbase, lane, b, io, st, &ta);
     __syncwarp();
   }
 }

@@ -12,6 +12,9 @@
 #include "cpg_blob_layout.h"
 #include "admm_multi_kernel.cuh"
 #include "grad_kernel.cuh"
+#if CPG_FAM_MATPAR
+#include "matpar_kernel.cuh"
+#endif
 
 extern "C" const unsigned long long CPG_B200_FN(cpg_blob_words)[];
 extern "C" const unsigned int CPG_B200_FN(cpg_blob_nbytes);
@@ -23,6 +26,8 @@ extern "C" const unsigned long long CPG_B200_FN(cpg_gblob_words)[];     // backw
 extern "C" const unsigned int CPG_B200_FN(cpg_gblob_nbytes);
 extern "C" const unsigned long long CPG_B200_FN(cpg_gS0_words)[];       // regularised KKT values in slot order (global)
 extern "C" const unsigned int CPG_B200_FN(cpg_gS0_nbytes);
+extern "C" const unsigned long long CPG_B200_FN(cpg_mblob_words)[];     // matrix-parameter tables (global; 16 bytes of zeros when unused)
+extern "C" const unsigned int CPG_B200_FN(cpg_mblob_nbytes);
 
 namespace {
 
@@ -40,7 +45,15 @@ struct Fam {
   static constexpr int GRAD_STRIDE = CPG_FAM_GRAD_STRIDE;
   static constexpr int NI = CPG_FAM_NI;                     // instances per warp in the main kernel (2 or 4)
   static constexpr int MULTI_STRIDE = CPG_FAM_MULTI_STRIDE; // doubles per warp: interleaved work vectors + batched-row slots
+#if CPG_FAM_MATPAR
+  static constexpr int MAT_WARPS = CPG_FAM_MAT_WARPS;       // matrix-parameter kernel: warps per CTA
+  static constexpr int MAT_A_STRIDE = CPG_FAM_MAT_A_STRIDE, MAT_P_STRIDE = CPG_FAM_MAT_P_STRIDE;
+  static constexpr int MAT_STRIDE = CPG_FAM_MAT_STRIDE;     // doubles per warp: w | S | Av | Pv | D Dinv E Einv
+#endif
 };
+#if CPG_FAM_MATPAR
+constexpr int MAT_SMEM_BYTES = Fam::MAT_WARPS * Fam::MAT_STRIDE * 8;
+#endif
 constexpr int SMEM_BYTES = Fam::BLOB_BYTES_PAD + Fam::WARPS * Fam::MULTI_STRIDE * 8;
 constexpr int TAIL_SMEM_BYTES = Fam::CBLOB_BYTES_PAD + Fam::TAIL_WARPS * (Fam::W_STRIDE + Fam::S_STRIDE) * 8;
 constexpr int TAIL_WORDS = Fam::N + 2 * Fam::M + 2;
@@ -54,6 +67,7 @@ struct Ctx {
   uint8_t* d_cblob = nullptr;
   uint8_t* d_gblob = nullptr;
   double* d_gS0 = nullptr;
+  uint8_t* d_mblob = nullptr;
   int cap_G = 0;
   double *g_soly = nullptr, *g_dprim = nullptr, *g_dparams = nullptr, *g_dq = nullptr, *g_dl = nullptr, *g_du = nullptr;
   unsigned int* d_counter = nullptr;
@@ -179,6 +193,20 @@ int CPG_B200_FN(cpg_b200_load_constants_all)(const void* blob, int nbytes, const
   return CPG_B200_OK;
 }
 
+int CPG_B200_FN(cpg_b200_load_mat_constants)(const void* mblob, int nbytes) {
+  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+#if CPG_FAM_MATPAR
+  if (!mblob || nbytes != (int)CPG_B200_FN(cpg_mblob_nbytes)) return CPG_B200_ERR_BAD_ARG;
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(g.d_mblob, mblob, nbytes, cudaMemcpyHostToDevice));
+  return CPG_B200_OK;
+#else
+  (void)mblob; (void)nbytes;
+  snprintf(g.err, sizeof(g.err), "this library was generated without per-instance matrix parameters");
+  return CPG_B200_ERR_BAD_ARG;
+#endif
+}
+
 int CPG_B200_FN(cpg_b200_init)(int device) {
   g.err[0] = 0;
   CK(cudaSetDevice(device));
@@ -201,6 +229,11 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
   if (!g.d_tail_blob) CK(cudaMalloc(&g.d_tail_blob, CPG_B200_FN(cpg_tail_blob_nbytes)));
   CK(cudaMemcpy(g.d_tail_blob, CPG_B200_FN(cpg_tail_blob_words), CPG_B200_FN(cpg_tail_blob_nbytes), cudaMemcpyHostToDevice));
   CK(cudaFuncSetAttribute(cpgb200::admm_tail_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM_BYTES));
+#if CPG_FAM_MATPAR
+  if (!g.d_mblob) CK(cudaMalloc(&g.d_mblob, CPG_B200_FN(cpg_mblob_nbytes)));
+  CK(cudaMemcpy(g.d_mblob, CPG_B200_FN(cpg_mblob_words), CPG_B200_FN(cpg_mblob_nbytes), cudaMemcpyHostToDevice));
+  CK(cudaFuncSetAttribute(cpgb200::admm_matpar_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAT_SMEM_BYTES));
+#endif
   if (!g.d_counter) CK(cudaMalloc(&g.d_counter, sizeof(unsigned int)));
   if (!g.d_tail_count) CK(cudaMalloc(&g.d_tail_count, sizeof(int)));
   CK(cudaFuncSetAttribute(cpgb200::admm_multi_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -209,7 +242,7 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
 }
 
 int CPG_B200_FN(cpg_b200_free)(void) {
-  void* ptrs[] = {g.d_blob, g.d_cblob, g.d_gblob, g.d_gS0, g.g_soly, g.g_dprim, g.g_dparams, g.g_dq, g.g_dl, g.g_du, g.d_tail_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0,
+  void* ptrs[] = {g.d_blob, g.d_cblob, g.d_gblob, g.d_gS0, g.d_mblob, g.g_soly, g.g_dprim, g.g_dparams, g.g_dq, g.g_dl, g.g_du, g.d_tail_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0,
                   g.d_prim, g.d_dual, g.d_solx, g.d_soly, g.d_obj, g.d_pri, g.d_dua, g.d_iter, g.d_status};
   for (void* p : ptrs) if (p) cudaFree(p);
   g = Ctx();
@@ -245,6 +278,18 @@ int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const doubl
   io.tail_state = g.d_tail_state; io.B = B; io.tail_capacity = g.tail_cap;
   CK(cudaMemsetAsync(g.d_counter, 0, sizeof(unsigned int), stream));
   CK(cudaMemsetAsync(g.d_tail_count, 0, sizeof(int), stream));
+#if CPG_FAM_MATPAR
+  // a batched parameter enters P or A: every instance is equilibrated, assembled and factored by its own warp (row f2)
+  {
+    int grid = g.n_sm;
+    const int need = (B + Fam::MAT_WARPS - 1) / Fam::MAT_WARPS;
+    if (grid > need) grid = need;
+    cpgb200::admm_matpar_kernel<Fam><<<grid, Fam::MAT_WARPS * 32, MAT_SMEM_BYTES, stream>>>(g.d_cblob, g.d_tail_blob, g.d_mblob, io, st);
+    g.launches += 1;
+    CK(cudaGetLastError());
+    return CPG_B200_OK;
+  }
+#endif
   // one persistent CTA per SM; a batch smaller than one wave of slots is still spread over all SMs (every warp pulls its
   // instances from the global counter), so that few warps share an SM's shared-memory bandwidth: lower latency
   int grid = g.n_sm;
@@ -310,6 +355,10 @@ int CPG_B200_FN(cpg_gradient_batch_device)(int B, const double* sol_x, const dou
                                            double* dparams, double* dq, double* dl, double* du, void* stream_) {
   (void)sol_x;   // only enters dP / dA (matrix parameters are shared in this build)
   if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+#if CPG_FAM_MATPAR
+  snprintf(g.err, sizeof(g.err), "the backward pass is not generated for families with per-instance matrix parameters");
+  return CPG_B200_ERR_BAD_ARG;
+#endif
   if (B < 0 || !sol_y || !dprim) return CPG_B200_ERR_BAD_ARG;
   g.launches = 0;
   if (B == 0) return CPG_B200_OK;

@@ -13,6 +13,7 @@ inequalities) so that dual signs match the reference's.
 Families:
   nonneg_ls(m, n)      README example (reference: examples/main.py:16-26)
   mpc(nx, nu, N)       MPC QP (reference: tests/test_E2E_QP.py:44-73,127-146; BASELINE config 2)
+  mpc_ltv(nx, nu, N)   the same with the dynamics and stage costs as (batchable) matrix parameters
 """
 from typing import Optional
 
@@ -136,6 +137,76 @@ def mpc(nx=12, nu=4, N=10, Ad=None, Bd=None, Q=None, QN=None, R=None, umax=1.0,
              UserDual('d2', 'y', (nx,), np.arange(nx))]
     return CanonFamily(name or f'mpc_{nx}_{nu}_{N}', 'quadratic', n, n_eq, n_ineq, params, maps,
                        {'P': _csc_pattern(Pu), 'A': _csc_pattern(A)}, variables, duals)
+
+
+def mpc_ltv(nx=12, nu=4, N=10, Ad=None, Bd=None, qdiag=None, rdiag=None, umax=1.0, x_init=None,
+            name=None) -> CanonFamily:
+    """The MPC QP of ``mpc`` with the reference family's MATRIX parameters (tests/test_E2E_QP.py:54-61 declares the
+    dynamics and the cost factors as cvxpy Parameters): ``A`` (nx x nx), ``B`` (nx x nu), the diagonal stage costs
+    ``qdiag`` (nx) and ``rdiag`` (nu), and ``x_init``.  ``A``/``B`` enter the canonical constraint matrix (every one of
+    their entries appears in each of the N stages), ``qdiag``/``rdiag`` the canonical cost matrix P = 2*blkdiag(diag(qdiag)
+    x (N+1), diag(rdiag) x N) -- so batching them exercises the osqp_update_data_mat branch of the generated solve
+    (cvxpygen/solvers/osqp.py:20-33): per-instance re-scaling, KKT assembly and numeric LDL' (SURVEY row f2).
+    The sparsity PATTERN is that of dense A and B: structural entries stay in the pattern even when a value is zero."""
+    dA, dB = default_mpc_dynamics(nx, nu)
+    Ad = dA if Ad is None else np.asarray(Ad, float)
+    Bd = dB if Bd is None else np.asarray(Bd, float)
+    qdiag = np.ones(nx) if qdiag is None else np.asarray(qdiag, float)
+    rdiag = 0.1 * np.ones(nu) if rdiag is None else np.asarray(rdiag, float)
+    x_init = np.zeros(nx) if x_init is None else np.asarray(x_init, float)
+    nX, nU = (N + 1) * nx, N * nu
+    n, n_eq, n_ineq = nX + nU, nX, nU
+    m = n_eq + n_ineq
+    params = _layout_params([('A', (nx, nx), Ad.flatten(order='F')), ('B', (nx, nu), Bd.flatten(order='F')),
+                             ('qdiag', (nx,), qdiag), ('rdiag', (nu,), rdiag), ('x_init', (nx,), x_init)])
+    col = {p.name: p.col for p in params}
+    n_theta = params[-1].col + params[-1].size + 1
+    # structural patterns: P diagonal; A = [[I - shift(A), -shift(B)], [0, I]] with dense A and B blocks
+    Pu = sp.identity(n, format='csc')
+    rows, cols, kind = [], [], []          # kind: ('one',) | ('A', i, j) | ('B', i, j)
+    for i in range(nX):
+        rows.append(i); cols.append(i); kind.append(('one',))
+    for k in range(N):
+        for i in range(nx):
+            for j in range(nx):
+                rows.append((k + 1) * nx + i); cols.append(k * nx + j); kind.append(('A', i, j))
+            for j in range(nu):
+                rows.append((k + 1) * nx + i); cols.append(nX + k * nu + j); kind.append(('B', i, j))
+    for i in range(nU):
+        rows.append(n_eq + i); cols.append(nX + i); kind.append(('one',))
+    tag = sp.csc_matrix((np.arange(1, len(rows) + 1, dtype=float), (rows, cols)), shape=(m, n))
+    tag.sort_indices()
+    order = tag.data.astype(int) - 1                  # CSC position -> triplet number
+    mb = _MapBuilder(len(order), n_theta)
+    for pos, t in enumerate(order):
+        kd = kind[t]
+        if kd[0] == 'one':
+            mb.const(pos, 1.0)
+        elif kd[0] == 'A':
+            mb.add(pos, col['A'] + kd[1] + nx * kd[2], -1.0)
+        else:
+            mb.add(pos, col['B'] + kd[1] + nx * kd[2], -1.0)
+    maps = {'A': mb.csr()}
+    mp = _MapBuilder(n, n_theta)
+    for i in range(nX):
+        mp.add(i, col['qdiag'] + (i % nx), 2.0)
+    for i in range(nU):
+        mp.add(nX + i, col['rdiag'] + (i % nu), 2.0)
+    maps['P'] = mp.csr()
+    maps['q'] = sp.csr_matrix((n, n_theta))
+    md = _MapBuilder(1, n_theta); md.const(0, 0.0); maps['d'] = md.csr()
+    ml, mu = _MapBuilder(m, n_theta), _MapBuilder(m, n_theta)
+    for i in range(nx):
+        ml.add(i, col['x_init'] + i, 1.0); mu.add(i, col['x_init'] + i, 1.0)
+    for i in range(n_ineq):
+        ml.const(n_eq + i, -umax); mu.const(n_eq + i, umax)
+    maps['l'], maps['u'] = ml.csr(), mu.csr()
+    variables = [UserVar('U', (nu, N), nX + np.arange(nU)), UserVar('X', (nx, N + 1), np.arange(nX))]
+    duals = [UserDual('d0', 'y', (nx, N), nx + np.arange(N * nx)), UserDual('d1', 'y', (nu, N), n_eq + np.arange(nU)),
+             UserDual('d2', 'y', (nx,), np.arange(nx))]
+    Apat = (tag.indices.astype(np.int32), tag.indptr.astype(np.int32), (m, n))
+    return CanonFamily(name or f'mpc_ltv_{nx}_{nu}_{N}', 'quadratic', n, n_eq, n_ineq, params, maps,
+                       {'P': _csc_pattern(Pu), 'A': Apat}, variables, duals)
 
 
 def nonneg_ls(m=3, n=2, A_pattern=None, A_data=None, b=None, seed=1, name=None) -> CanonFamily:

@@ -354,3 +354,90 @@ def pack_grad_blob(*, n, m, perm, P_upper, A, slot_of, n_slots, Mq_b, Ml_b, Mu_b
     hv['off_i32'] = len(hdr()); hv['off_f64'] = hv['off_i32'] + len(i32b); hv['off_u16'] = hv['off_f64'] + len(f64b)
     hv['total_bytes'] = hv['off_u16'] + len(u16b)
     return hdr() + i32b + f64b + u16b, S0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Matrix-parameter blob: tables of the per-instance osqp_update_data_mat path -- canonicalisation maps
+# of the P / A entries, entry coordinates for the in-warp Ruiz equilibration (scale_data, scaling.c:44-156), entry ->
+# KKT slot maps for the per-instance assembly (form_KKT / update_KKT_P / update_KKT_A, kkt.c:6-212), and ELL *index*
+# tables (entry number + operand position) for the residual products with per-instance values.  Lives in GLOBAL memory.
+MAT_HEADER_FIELDS: List[Tuple[str, str]] = [
+    ('int', 'magic'), ('int', 'total_bytes'), ('int', 'n'), ('int', 'm'),
+    ('int', 'nk'), ('int', 'npb'), ('int', 'nnzP'), ('int', 'nnzA'),
+    ('int', 'off_i32'), ('int', 'off_f64'), ('int', 'off_u16'), ('int', 'n_slots'),
+    ('int', 'i_ellMP'), ('int', 'i_ellMA'), ('int', 'i_ixA'), ('int', 'i_ixAt'),
+    ('int', 'i_ixP'), ('int', 'f_Pbase'), ('int', 'f_Abase'), ('int', 'f_q_un'),
+    ('int', 'f_S0'), ('int', 'h_Prow'), ('int', 'h_Pcol'), ('int', 'h_Arow'),
+    ('int', 'h_Acol'), ('int', 'h_Pslot'), ('int', 'h_Aslot'), ('int', 'scaling_iters'),
+]
+
+
+def mat_header_struct_c(name='CpgMatHeader') -> str:
+    return 'struct %s {\n%s};\n' % (name, ''.join(f'  {t} {n};\n' for t, n in MAT_HEADER_FIELDS))
+
+
+def _index_ell(M_idx: sp.csr_matrix, n_rows: int, pad_idx: int, col_shift: int = 0):
+    """M_idx: CSR whose data = entry number + 1.  Returns ELL blocks (K, idx(K,32), cols(K,32)); padding -> pad_idx."""
+    out = []
+    for K, vals, cols in ell_row_blocks(M_idx, n_rows):
+        idx = np.where(vals > 0, vals - 1, pad_idx).astype(np.int64)
+        out.append((K, idx, cols + col_shift))
+    return out
+
+
+def pack_matpar_blob(*, n, m, perm, P_pattern, A_pattern, slot_of, n_slots, sigma, MP_b, MA_b, P_base, A_base,
+                     q_un, npb, scaling_iters) -> bytes:
+    """P_pattern / A_pattern: (indices, indptr, shape) CSC (P upper triangle).  MP_b / MA_b: CSR maps of the entries
+    restricted to the batched-parameter columns; P_base / A_base: entry values with the batched parameters at zero (or, for
+    a matrix no batched parameter enters, the unscale_data round trip of the pristine scaled values).  q_un: the linear
+    cost that scale_data sees inside osqp_update_P_A (pristine q after unscale_data)."""
+    nk = n + m
+    ar = _Areas()
+    pinv = np.empty(nk, dtype=np.int64); pinv[np.asarray(perm)] = np.arange(nk)
+    Pi, Pp, _ = P_pattern
+    Ai, Ap, _ = A_pattern
+    nnzP, nnzA = len(Pi), len(Ai)
+    assert max(nnzP, nnzA) + 1 < 65536
+    Prow = np.asarray(Pi, dtype=np.int64); Pcol = np.repeat(np.arange(n), np.diff(Pp))
+    Arow = np.asarray(Ai, dtype=np.int64); Acol = np.repeat(np.arange(n), np.diff(Ap))
+    assert (Prow <= Pcol).all(), 'P must be stored as its upper triangle'
+    Pslot = [int(pinv[r]) if r == c else slot_of(max(pinv[r], pinv[c]), min(pinv[r], pinv[c])) for r, c in zip(Prow, Pcol)]
+    Aslot = [slot_of(max(pinv[n + r], pinv[c]), min(pinv[n + r], pinv[c])) for r, c in zip(Arow, Acol)]
+    S0 = np.zeros(n_slots)
+    S0[pinv[:n]] = sigma
+    hv = dict(magic=MAGIC + 3, n=n, m=m, nk=nk, npb=npb, nnzP=nnzP, nnzA=nnzA, n_slots=n_slots, scaling_iters=int(scaling_iters))
+    hv['i_ellMP'] = _add_ell(ar, ell_row_blocks(MP_b, nnzP))
+    hv['i_ellMA'] = _add_ell(ar, ell_row_blocks(MA_b, nnzA))
+    Aidx = sp.csr_matrix(sp.csc_matrix((np.arange(1, nnzA + 1, dtype=float), Ai, Ap), shape=(m, n)))
+    hv['i_ixA'] = _add_ixell(ar, _index_ell(Aidx, m, nnzA))
+    hv['i_ixAt'] = _add_ixell(ar, _index_ell(sp.csr_matrix(Aidx.T), n, nnzA, col_shift=n))
+    Pidx_u = sp.csc_matrix((np.arange(1, nnzP + 1, dtype=float), Pi, Pp), shape=(n, n))
+    Pidx = sp.csr_matrix(Pidx_u + sp.triu(Pidx_u, 1).T)
+    hv['i_ixP'] = _add_ixell(ar, _index_ell(Pidx, n, nnzP))
+    hv['f_Pbase'] = ar.add_f64(P_base); hv['f_Abase'] = ar.add_f64(A_base)
+    hv['f_q_un'] = ar.add_f64(q_un); hv['f_S0'] = ar.add_f64(S0)
+    hv['h_Prow'] = ar.add_u16(Prow); hv['h_Pcol'] = ar.add_u16(Pcol)
+    hv['h_Arow'] = ar.add_u16(Arow); hv['h_Acol'] = ar.add_u16(Acol)
+    hv['h_Pslot'] = ar.add_u16(Pslot); hv['h_Aslot'] = ar.add_u16(Aslot)
+    fmt = '<' + 'i' * len(MAT_HEADER_FIELDS)
+
+    def hdr():
+        return struct.pack(fmt, *[int(hv.get(nm, 0)) for _, nm in MAT_HEADER_FIELDS])
+    assert len(hdr()) % 16 == 0
+
+    def pad16(b: bytes) -> bytes:
+        return b + b'\0' * ((-len(b)) % 16)
+    i32b = pad16(np.asarray(ar.i32, dtype='<i4').tobytes())
+    f64b = pad16(np.asarray(ar.f64, dtype='<f8').tobytes())
+    u16b = pad16(np.asarray(ar.u16, dtype='<u2').tobytes())
+    hv['off_i32'] = len(hdr()); hv['off_f64'] = hv['off_i32'] + len(i32b); hv['off_u16'] = hv['off_f64'] + len(f64b)
+    hv['total_bytes'] = hv['off_u16'] + len(u16b)
+    return hdr() + i32b + f64b + u16b
+
+
+def _add_ixell(ar: _Areas, blocks) -> int:
+    """int32 table: per 32-row block [K, u16 offset of the entry numbers, u16 offset of the operand positions]."""
+    table = []
+    for K, idx, cols in blocks:
+        table += [K, ar.add_u16(idx), ar.add_u16(cols)]
+    return ar.add_i32(table) if table else ar.add_i32([0, 0, 0])

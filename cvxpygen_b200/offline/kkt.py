@@ -148,9 +148,11 @@ def dense_ldl(Kp: np.ndarray, pattern: np.ndarray):
     return L, D
 
 
-def factorize(K: sp.csc_matrix, n_var: int) -> LDLFactor:
+def factorize(K: sp.csc_matrix, n_var: int, pattern: sp.spmatrix = None) -> LDLFactor:
+    """pattern: optional structural pattern (superset of K's nonzeros) to order and analyse instead of K's own."""
     n = K.shape[0]
-    patt = sp.csr_matrix((np.ones(K.nnz), K.indices, K.indptr), shape=K.shape)
+    Ks = K if pattern is None else sp.csc_matrix(pattern)
+    patt = sp.csr_matrix((np.ones(Ks.nnz), Ks.indices, Ks.indptr), shape=K.shape)
     md = minimum_degree_order(patt)
     struct, parent = _symbolic(patt, md)
     reseq, _ = level_resequence(struct, parent)

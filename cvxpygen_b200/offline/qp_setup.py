@@ -12,7 +12,7 @@ import scipy.sparse as sp
 
 from ..ir import CanonFamily
 from . import kkt as _kkt
-from .blob import pack_blob, pack_tail_blob, pack_grad_blob
+from .blob import pack_blob, pack_tail_blob, pack_grad_blob, pack_matpar_blob
 from .refactor import build_refactor_tables, RefactorTables
 from .equilibrate import ruiz_equilibrate
 from .schedule import SolveSchedule, build_schedule
@@ -45,6 +45,10 @@ class QPSetup:
     blob_compact: bytes = b''
     grad_blob: bytes = b''
     grad_S0: Optional[np.ndarray] = None
+    mat_blob: bytes = b''                  # f2: per-instance matrix parameters (empty = matrices shared by the batch)
+    mat_params: List[str] = field(default_factory=list)
+    nnzP: int = 0
+    nnzA: int = 0
     refactor: Optional[RefactorTables] = None
     solve_source: str = ''
     theta_shared: Optional[np.ndarray] = None
@@ -59,11 +63,11 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
         raise ValueError('ADMM-CUDA handles the QP canonical form only')
     if batch_params is None:
         batch_params = [p.name for p in fam.params if not (fam.changes('P', [p.name]) or fam.changes('A', [p.name]))]
+    mat_params = []
     for name in batch_params:
         fam.param(name)      # AttributeError for unknown names, like the reference's cpg_solve
         if fam.changes('P', [name]) or fam.changes('A', [name]):
-            raise ValueError(f'parameter {name} enters a canonical matrix; per-instance matrix updates '
-                             'are not generated yet (shared parameters may: they are folded at setup)')
+            mat_params.append(name)      # f2: this family is solved by the per-instance matrix kernel (matpar_kernel.cuh)
     theta = fam.theta_default() if theta is None else np.asarray(theta, dtype=float)
     n, m = fam.n_var, fam.n_eq + fam.n_ineq
     bcols = fam.param_columns(batch_params) if batch_params else np.zeros(0, dtype=int)
@@ -82,7 +86,12 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
     rho = min(max(rho, _kkt.RHO_MIN), _kkt.RHO_MAX)
     rho_vec = _kkt.rho_vector(ctype, rho)
     K = _kkt.assemble_kkt(sc['P'], sc['A'], sigma, rho_vec)
-    F = _kkt.factorize(K, n)
+    Kpat = None
+    if mat_params:
+        # batched matrix entries may take any value: order / analyse the STRUCTURAL pattern, not today's nonzeros
+        ones = lambda M: sp.csc_matrix((np.ones(len(M.indices)), M.indices, M.indptr), shape=M.shape)
+        Kpat = _kkt.assemble_kkt(ones(sp.csc_matrix(P)), ones(sp.csc_matrix(A)), 1.0, np.ones(m))
+    F = _kkt.factorize(K, n, pattern=Kpat)
     S = build_schedule(F, max_group_rows=max_group_rows, allow_trailing=allow_trailing)
     # affine maps split into [batched columns | everything else folded into a base vector]
     theta0 = theta.copy(); theta0[bcols] = 0.0
@@ -119,6 +128,9 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
     # backward pass (gradient=True): regularised KKT of the UNSCALED problem on the same symbolic pattern
     grad_blob, grad_S0 = pack_grad_blob(n=n, m=m, perm=F.perm, P_upper=sp.csc_matrix(P), A=sp.csc_matrix(A), slot_of=RT.slot_of,
                                         n_slots=RT.n_slots, Mq_b=Mq_b, Ml_b=Ml_b, Mu_b=Mu_b, npb=npb, prim_idx=prim_idx)
+    mat_blob = b''
+    if mat_params:
+        mat_blob = _matpar_blob(fam, sc, P, A, q, theta0, bcols, npb, F, RT, sigma, scaling, n, m)
     import struct as _struct
     from .blob import HEADER_FIELDS as _HF
     _hdr = dict(zip([n_ for _, n_ in _HF], _struct.unpack('<' + ''.join('i' if t_ == 'int' else 'd' for t_, _ in _HF),
@@ -127,5 +139,40 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
               schedule_entries=S.n_entries, blob_bytes=len(blob))
     return QPSetup(family=fam, batch_params=list(batch_params), n=n, m=m, npb=npb, rho=rho, sigma=sigma,
                    scaling=scaling, D=sc['D'], E=sc['E'], c=sc['c'], ctype=ctype, P_scaled=sc['P'],
-                   A_scaled=sc['A'], factor=F, schedule=S, prim_idx=prim_idx, dual_idx=dual_idx, blob=blob, tail_blob=tail_blob, blob_compact=blob_compact, grad_blob=grad_blob, grad_S0=grad_S0, refactor=RT, solve_source=solve_source,
+                   A_scaled=sc['A'], factor=F, schedule=S, prim_idx=prim_idx, dual_idx=dual_idx, blob=blob, tail_blob=tail_blob, blob_compact=blob_compact, grad_blob=grad_blob, grad_S0=grad_S0, mat_blob=mat_blob, mat_params=mat_params,
+                   nnzP=int(sp.csc_matrix(P).indptr[-1]), nnzA=int(sp.csc_matrix(A).indptr[-1]), refactor=RT, solve_source=solve_source,
                    theta_shared=theta0, batch_cols=bcols, stats=st)
+
+
+def unscale_roundtrip(sc, scaling):
+    """What `unscale_data` (scaling.c:160-175) leaves in the workspace when osqp_update_P_A starts from the pristine
+    post-setup state: P, q, A un-scaled from their SCALED values in the reference's operation order (not bit-identical
+    to the original data).  Returns (P.data, A.data, q)."""
+    P, A = sp.csc_matrix(sc['P']), sp.csc_matrix(sc['A'])
+    if not scaling:
+        return P.data.copy(), A.data.copy(), np.array(sc['q'], dtype=float)
+    D, E, c = sc['D'], sc['E'], sc['c']
+    Dinv, Einv, cinv = 1.0 / D, 1.0 / E, 1.0 / c
+    n = P.shape[0]
+    pc = np.repeat(np.arange(n), np.diff(P.indptr)); ac = np.repeat(np.arange(n), np.diff(A.indptr))
+    Pd = ((P.data * cinv) * Dinv[P.indices]) * Dinv[pc]
+    qd = Dinv * (np.asarray(sc['q'], dtype=float) * cinv)
+    Ad = (A.data * Einv[A.indices]) * Dinv[ac]
+    return Pd, Ad, qd
+
+
+def _matpar_blob(fam, sc, P, A, q, theta0, bcols, npb, F, RT, sigma, scaling, n, m):
+    P, A = sp.csc_matrix(P), sp.csc_matrix(A)
+    Pd_un, Ad_un, q_un = unscale_roundtrip(sc, scaling)
+    MP, MA = fam.maps['P'], fam.maps['A']
+    P_batched = MP[:, bcols].nnz > 0
+    A_batched = MA[:, bcols].nnz > 0
+    # osqp_update_data_mat is called with the WHOLE canonical P->x / A->x of the matrices that are outdated and with NULL
+    # for the other one (cvxpygen/solvers/osqp.py:20-33), which then keeps its unscale/re-scale round-trip values
+    P_base = np.asarray(MP @ theta0).ravel() if P_batched else Pd_un
+    A_base = np.asarray(MA @ theta0).ravel() if A_batched else Ad_un
+    MP_b = sp.csr_matrix(MP[:, bcols]) if P_batched else sp.csr_matrix((MP.shape[0], max(npb, 1)))
+    MA_b = sp.csr_matrix(MA[:, bcols]) if A_batched else sp.csr_matrix((MA.shape[0], max(npb, 1)))
+    return pack_matpar_blob(n=n, m=m, perm=F.perm, P_pattern=fam.patterns['P'], A_pattern=fam.patterns['A'],
+                            slot_of=RT.slot_of, n_slots=RT.n_slots, sigma=sigma, MP_b=MP_b, MA_b=MA_b, P_base=P_base,
+                            A_base=A_base, q_un=q_un, npb=npb, scaling_iters=scaling)

@@ -93,6 +93,13 @@ int  CPG_B200_FN(cpg_b200_load_constants_all)(const void* blob, int nbytes, cons
                                               const void* tail_blob, int tnbytes, const void* gblob, int gnbytes,
                                               const void* gS0, int snbytes);
 
+/* Families generated with per-instance MATRIX parameters (a batched parameter enters P or A): replace the
+ * tables of the per-instance osqp_update_data_mat path (canonicalisation maps of the P / A entries, KKT slot maps, the
+ * round-trip base values) after a SHARED parameter changed.  Error for libraries generated without such parameters.
+ * In these families `params` rows carry the matrix parameters too, and every instance is re-equilibrated
+ * (scale_data, osqp_sources/src/scaling.c:44-156), assembled and factored (kkt.c:184-212, qdldl.c:72-233) on the GPU. */
+int  CPG_B200_FN(cpg_b200_load_mat_constants)(const void* mblob, int nbytes);
+
 /* Batched solve, DEVICE buffers (row-major, one instance per row), asynchronous on `stream`.
  *   params (B, n_param) in        x0 (B, n_var) / y0 (B, n_con) optional warm start (NULL = cold)
  *   prim (B, n_prim), dual (B, n_dual) out; sol_x (B, n_var), sol_y (B, n_con) optional (NULL = skip)

@@ -327,3 +327,20 @@ class AdmmOracle:
         ys = np.where(has_sol[:, None], cinv * E * y, np.nan)
         return dict(x=xs, y=ys, obj=obj, iter=it_out, status=status.astype(np.int32), pri_res=pri_res,
                     dua_res=dua_res, rho_updates=rho_updates)
+
+
+def solve_matrix_batch(P_list, A_list, q_pristine, l_pristine, u_pristine, q=None, l=None, u=None, **settings):
+    """Per-instance matrices (the osqp_update_data_mat branch of the generated solve, cvxpygen/solvers/osqp.py:20-33;
+    0.6.2: osqp_update_P_A, src/osqp.c:1158-1264): scale_data runs on (P_i, A_i) with the linear cost that is in the
+    workspace at that moment -- the pristine one -- then the instance's own q, l, u are loaded (update_lin_cost /
+    update_bounds, osqp.c:752-827) and the problem is solved from a cold start.  One AdmmOracle per instance.
+    P_list / A_list: sequences of (n x n upper-triangular or symmetric) and (m x n) matrices."""
+    outs = []
+    for i, (P_i, A_i) in enumerate(zip(P_list, A_list)):
+        orc = AdmmOracle(P_i, q_pristine, A_i, l_pristine, u_pristine, **settings)
+        kw = {}
+        if q is not None: kw['q'] = np.asarray(q)[i:i + 1]
+        if l is not None: kw['l'] = np.asarray(l)[i:i + 1]
+        if u is not None: kw['u'] = np.asarray(u)[i:i + 1]
+        outs.append(orc.solve_batch(B=1, **kw) if not kw else orc.solve_batch(**kw))
+    return {k: np.concatenate([np.atleast_1d(o[k]) for o in outs]) for k in outs[0]}

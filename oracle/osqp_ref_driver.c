@@ -5,7 +5,9 @@
  * resulting oracle/_ref/libosqp_ref.so travels.  It reproduces, per instance,
  * what cvxpygen's generated cpg_solve() does on the OSQP path
  * (cvxpygen/utils.py:1009-1052, cvxpygen/solvers/osqp.py:20-62):
- *     osqp_update_lin_cost / osqp_update_bounds  ->  osqp_solve
+ *     [osqp_update_P_A]  ->  osqp_update_lin_cost / osqp_update_bounds  ->  osqp_solve
+ * (the matrix update first, like the reference's update table; before it the vectors are put back to their
+ *  generation-time values so that scale_data inside osqp_update_P_A sees the pristine q whatever was solved before)
  * with the batch semantics "every instance is solved from the pristine
  * post-setup state" (rho reset to its initial value, cold start), because a
  * batch has no defined instance order.
@@ -32,6 +34,7 @@ typedef struct {
 typedef struct {
   int n, m, nthreads;
   double rho0;
+  double *q0, *l0, *u0;   /* generation-time vectors (pristine state for matrix updates) */
   OSQPWorkspace **work;   /* one workspace per thread */
   RefSettings s;
 } RefOsqp;
@@ -76,6 +79,9 @@ RefOsqp *ref_osqp_setup(int n, int m,
   if (nthreads < 1) nthreads = 1;
   r->n = n; r->m = m; r->nthreads = nthreads; r->s = *s; r->rho0 = s->rho;
   r->work = (OSQPWorkspace **)calloc(nthreads, sizeof(OSQPWorkspace *));
+  r->q0 = (double *)malloc(sizeof(double) * (n > 0 ? n : 1)); memcpy(r->q0, q, sizeof(double) * n);
+  r->l0 = (double *)malloc(sizeof(double) * (m > 0 ? m : 1)); memcpy(r->l0, l, sizeof(double) * m);
+  r->u0 = (double *)malloc(sizeof(double) * (m > 0 ? m : 1)); memcpy(r->u0, u, sizeof(double) * m);
   for (t = 0; t < nthreads; t++) {
     OSQPData data; OSQPSettings st;
     csc P, A;
@@ -96,6 +102,7 @@ void ref_osqp_free(RefOsqp *r) {
   int t;
   if (!r) return;
   for (t = 0; t < r->nthreads; t++) if (r->work[t]) osqp_cleanup(r->work[t]);
+  free(r->q0); free(r->l0); free(r->u0);
   free(r->work); free(r);
 }
 
@@ -116,6 +123,7 @@ int ref_osqp_adaptive_rho_interval(RefOsqp *r) { return (int)r->work[0]->setting
 typedef struct {
   RefOsqp *r; int B; int tid;
   const double *qb, *lb, *ub, *x0, *y0;
+  const double *Pb, *Ab; int nnzP, nnzA;     /* per-instance matrix values (CSC order) or NULL */
   double *x, *y, *obj; int *iter, *status; double *pri_res, *dua_res; int *rho_updates;
   int *next;
 } Job;
@@ -123,6 +131,12 @@ typedef struct {
 static void solve_one(Job *j, OSQPWorkspace *w, int b) {
   RefOsqp *r = j->r; int n = r->n, m = r->m;
   if (w->settings->rho != r->rho0) osqp_update_rho(w, r->rho0);
+  if (j->Pb || j->Ab) {
+    osqp_update_lin_cost(w, r->q0);
+    if (m > 0) osqp_update_bounds(w, r->l0, r->u0);
+    osqp_update_P_A(w, j->Pb ? j->Pb + (size_t)b * j->nnzP : 0, 0, j->nnzP,
+                    j->Ab ? j->Ab + (size_t)b * j->nnzA : 0, 0, j->nnzA);
+  }
   if (j->qb) osqp_update_lin_cost(w, j->qb + (size_t)b * n);
   if (j->lb && j->ub) osqp_update_bounds(w, j->lb + (size_t)b * m, j->ub + (size_t)b * m);
   if (j->x0 && j->y0) {
@@ -152,12 +166,36 @@ static void *worker(void *arg) {
   return 0;
 }
 
+static double run_jobs(RefOsqp *r, int B, Job *proto, int nthreads);
+
+/* Same with per-instance matrices: Pb (B, nnzP) / Ab (B, nnzA) in CSC order, either may be NULL
+ * (osqp_update_P_A with Px_new_idx = Ax_new_idx = NULL, osqp.c:1158). */
+double ref_osqp_solve_batch_mat(RefOsqp *r, int B, const double *Pb, int nnzP, const double *Ab, int nnzA,
+                                const double *qb, const double *lb, const double *ub,
+                                double *x, double *y, double *obj,
+                                int *iter, int *status, double *pri_res, double *dua_res,
+                                int *rho_updates, int nthreads) {
+  Job j; memset(&j, 0, sizeof(j));
+  j.r = r; j.B = B; j.qb = qb; j.lb = lb; j.ub = ub; j.Pb = Pb; j.Ab = Ab; j.nnzP = nnzP; j.nnzA = nnzA;
+  j.x = x; j.y = y; j.obj = obj; j.iter = iter; j.status = status;
+  j.pri_res = pri_res; j.dua_res = dua_res; j.rho_updates = rho_updates;
+  return run_jobs(r, B, &j, nthreads);
+}
+
 double ref_osqp_solve_batch(RefOsqp *r, int B,
                             const double *qb, const double *lb, const double *ub,
                             const double *x0, const double *y0,
                             double *x, double *y, double *obj,
                             int *iter, int *status, double *pri_res, double *dua_res,
                             int *rho_updates, int nthreads) {
+  Job j; memset(&j, 0, sizeof(j));
+  j.r = r; j.B = B; j.qb = qb; j.lb = lb; j.ub = ub; j.x0 = x0; j.y0 = y0;
+  j.x = x; j.y = y; j.obj = obj; j.iter = iter; j.status = status;
+  j.pri_res = pri_res; j.dua_res = dua_res; j.rho_updates = rho_updates;
+  return run_jobs(r, B, &j, nthreads);
+}
+
+static double run_jobs(RefOsqp *r, int B, Job *proto, int nthreads) {
   struct timespec t0, t1;
   int next = 0, t;
   Job jobs[256]; pthread_t th[256];
@@ -165,12 +203,7 @@ double ref_osqp_solve_batch(RefOsqp *r, int B,
   if (nthreads > r->nthreads) nthreads = r->nthreads;
   if (nthreads > 256) nthreads = 256;
   clock_gettime(CLOCK_MONOTONIC, &t0);
-  for (t = 0; t < nthreads; t++) {
-    Job *j = &jobs[t];
-    j->r = r; j->B = B; j->tid = t; j->qb = qb; j->lb = lb; j->ub = ub; j->x0 = x0; j->y0 = y0;
-    j->x = x; j->y = y; j->obj = obj; j->iter = iter; j->status = status;
-    j->pri_res = pri_res; j->dua_res = dua_res; j->rho_updates = rho_updates; j->next = &next;
-  }
+  for (t = 0; t < nthreads; t++) { jobs[t] = *proto; jobs[t].tid = t; jobs[t].next = &next; }
   if (nthreads == 1) worker(&jobs[0]);
   else {
     for (t = 0; t < nthreads; t++) pthread_create(&th[t], 0, worker, &jobs[t]);

@@ -43,6 +43,7 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         L.ref_osqp_setup.restype = C.c_void_p
         L.ref_osqp_solve_batch.restype = C.c_double
+        L.ref_osqp_solve_batch_mat.restype = C.c_double
         L.ref_osqp_adaptive_rho_interval.restype = C.c_int
         _lib = L
     return _lib
@@ -113,6 +114,25 @@ class RefOSQP:
                                          _p(x, C.c_double), _p(y, C.c_double), _p(obj, C.c_double),
                                          _p(it, C.c_int), _p(st, C.c_int), _p(pr, C.c_double), _p(dr, C.c_double),
                                          _p(ru, C.c_int), C.c_int(nt))
+        return dict(x=x, y=y, obj=obj, iter=it, status=st, pri_res=pr, dua_res=dr, rho_updates=ru, seconds=sec)
+
+    def solve_batch_mat(self, Px=None, Ax=None, q=None, l=None, u=None, nthreads=None):
+        """Per-instance matrices: Px (B, nnz(P upper)) / Ax (B, nnzA) in CSC order (either may be None), then q/l/u as in
+        solve_batch.  Per instance: vectors back to their setup values, osqp_update_P_A (osqp.c:1158-1264: unscale,
+        overwrite, scale_data, refactor), osqp_update_lin_cost / _bounds, osqp_solve."""
+        B = next(a.shape[0] for a in (Px, Ax, q, l, u) if a is not None)
+        c64 = lambda a, clip=False: None if a is None else np.ascontiguousarray(np.clip(a, -1e30, 1e30) if clip else a, dtype=np.float64)
+        Px, Ax, q, l, u = c64(Px), c64(Ax), c64(q), c64(l, True), c64(u, True)
+        x = np.zeros((B, self.n)); y = np.zeros((B, self.m))
+        obj = np.zeros(B); it = np.zeros(B, np.int32); st = np.zeros(B, np.int32)
+        pr = np.zeros(B); dr = np.zeros(B); ru = np.zeros(B, np.int32)
+        nt = self.nthreads if nthreads is None else nthreads
+        sec = lib().ref_osqp_solve_batch_mat(self.h, C.c_int(B), _p(Px, C.c_double), C.c_int(0 if Px is None else Px.shape[1]),
+                                             _p(Ax, C.c_double), C.c_int(0 if Ax is None else Ax.shape[1]),
+                                             _p(q, C.c_double), _p(l, C.c_double), _p(u, C.c_double),
+                                             _p(x, C.c_double), _p(y, C.c_double), _p(obj, C.c_double),
+                                             _p(it, C.c_int), _p(st, C.c_int), _p(pr, C.c_double), _p(dr, C.c_double),
+                                             _p(ru, C.c_int), C.c_int(nt))
         return dict(x=x, y=y, obj=obj, iter=it, status=st, pri_res=pr, dua_res=dr, rho_updates=ru, seconds=sec)
 
     def __del__(self):

@@ -117,3 +117,48 @@ def conic_batch(fam, B, seed):
     h[kind == 1, 1] = -h[kind == 1, 0] - 1.0
     c[kind == 2, n - 1] = -1.0
     return out, kind
+
+
+# ---------------------------------------------------------------------------------------------------------
+# families with per-instance MATRIX parameters
+def ltv_batch(fam, B, seed=3, spread=0.05):
+    """Parameter batch for families.mpc_ltv: perturbed dynamics, random diagonal stage costs, random initial state."""
+    rng = np.random.default_rng(seed)
+    A0, B0 = fam.param('A').default, fam.param('B').default
+    return {'A': A0[None, :] + spread * rng.standard_normal((B, A0.size)),
+            'B': B0[None, :] + spread * rng.standard_normal((B, B0.size)),
+            'qdiag': rng.uniform(0.5, 2.0, (B, fam.param('qdiag').size)),
+            'rdiag': rng.uniform(0.05, 0.5, (B, fam.param('rdiag').size)),
+            'x_init': rng.uniform(-1, 1, (B, fam.param('x_init').size))}
+
+
+def canon_matrix_batches(fam, params, B):
+    """(Px (B, nnzP), Ax (B, nnzA)) canonical matrix entries in CSC order + (q, l, u) batches."""
+    th = np.tile(fam.theta_default(), (B, 1))
+    for pn, v in params.items():
+        p = fam.param(pn)
+        th[:, p.col:p.col + p.size] = v
+    Px = np.asarray((fam.maps['P'] @ th.T).T)
+    Ax = np.asarray((fam.maps['A'] @ th.T).T)
+    return Px, Ax, canon_batches(fam, params, B)
+
+
+def matrix_oracle_solve(fam, Px, Ax, q, l, u, prefer_ref=True, **settings):
+    """Reference result for per-instance matrices: osqp_update_P_A + vector updates + solve from the pristine workspace
+    (compiled OSQP 0.6.2 when present, else the numpy restatement)."""
+    import scipy.sparse as sp
+    if prefer_ref and ref_available():
+        from oracle.ref_osqp import RefOSQP
+        r = RefOSQP(fam.canon_matrix('P'), fam.canon_data('q'), fam.canon_matrix('A'),
+                    fam.canon_data('l'), fam.canon_data('u'), nthreads=min(8, os.cpu_count() or 1), **settings)
+        assert r._keep[0].nnz == Px.shape[1] and r._keep[1].nnz == Ax.shape[1], 'structural zeros were dropped'
+        return r.solve_batch_mat(Px=Px, Ax=Ax, q=q, l=l, u=u)
+    from oracle.admm_numpy import solve_matrix_batch
+    from cvxpygen_b200.offline.qp_setup import unscale_roundtrip
+    from cvxpygen_b200.offline.equilibrate import ruiz_equilibrate
+    Pi, Pp, Ps = fam.patterns['P']; Ai, Ap, As = fam.patterns['A']
+    sc = ruiz_equilibrate(fam.canon_matrix('P'), fam.canon_matrix('A'), fam.canon_data('q'), int(settings.get('scaling', 10)))
+    q_un = unscale_roundtrip(sc, int(settings.get('scaling', 10)))[2]
+    Pl = [sp.csc_matrix((Px[i], Pi, Pp), shape=Ps) for i in range(Px.shape[0])]
+    Al = [sp.csc_matrix((Ax[i], Ai, Ap), shape=As) for i in range(Ax.shape[0])]
+    return solve_matrix_batch(Pl, Al, q_un, fam.canon_data('l'), fam.canon_data('u'), q=q, l=l, u=u, **settings)

@@ -1,0 +1,181 @@
+"""Per-instance matrix parameters: the osqp_update_data_mat branch of the generated solve
+(cvxpygen/solvers/osqp.py:20-33 -> osqp_update_P_A, osqp_sources/src/osqp.c:1158-1264) for a whole batch.
+
+CPU part: the numpy restatement against the compiled reference; the kernel's tables (offline/blob.py:pack_matpar_blob)
+emulated in numpy against a direct equilibration / KKT assembly.  GPU part: the CUDA path against the reference."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from cvxpygen_b200 import families, standard
+from cvxpygen_b200.offline import kkt as _kkt
+from cvxpygen_b200.offline.equilibrate import ruiz_equilibrate
+from cvxpygen_b200.offline.matpar import emulate_prepare, emulate_assemble
+from cvxpygen_b200.offline.qp_setup import setup_qp_family, unscale_roundtrip
+from cvxpygen_b200.offline.refactor import emulate_factor, emulate_solve
+
+from helpers import ltv_batch, canon_matrix_batches, matrix_oracle_solve, ref_available, rel_err
+
+BATCHED = ['A', 'B', 'qdiag', 'rdiag', 'x_init']
+
+
+@pytest.fixture(scope='module')
+def ltv_small():
+    fam = families.mpc_ltv(4, 2, 5)
+    return fam, setup_qp_family(fam, BATCHED)
+
+
+def _theta_rows(fam, setup, params, B):
+    th = np.tile(fam.theta_default(), (B, 1))
+    for pn, v in params.items():
+        p = fam.param(pn)
+        th[:, p.col:p.col + p.size] = v
+    return th[:, setup.batch_cols]
+
+
+def test_pattern_is_structural():
+    fam = families.mpc_ltv(4, 2, 5)
+    assert fam.canon_matrix('A').nnz == (5 + 1) * 4 + 5 * 4 * (4 + 2) + 5 * 2          # dense A, B blocks stay in the pattern
+    g = families.mpc(4, 2, 5)
+    assert abs(fam.canon_matrix('A').toarray() - g.canon_matrix('A').toarray()).max() == 0.0
+    assert abs(fam.canon_matrix('P').toarray() - g.canon_matrix('P').toarray()).max() == 0.0
+
+
+def test_tables_equilibrate_bit_exact(ltv_small):
+    """matpar_prepare's operation sequence on the packed tables == scale_data on the instance's matrices, bit for bit."""
+    fam, setup = ltv_small
+    B = 4
+    params = ltv_batch(fam, B)
+    Px, Ax, _ = canon_matrix_batches(fam, params, B)
+    thb = _theta_rows(fam, setup, params, B)
+    sc0 = ruiz_equilibrate(fam.canon_matrix('P'), fam.canon_matrix('A'), fam.canon_data('q'), 10)
+    q_un = unscale_roundtrip(sc0, 10)[2]
+    Pi, Pp, Ps = fam.patterns['P']; Ai, Ap, As = fam.patterns['A']
+    for i in range(B):
+        emu = emulate_prepare(setup.mat_blob, thb[i])
+        ref = ruiz_equilibrate(sp.csc_matrix((Px[i], Pi, Pp), shape=Ps), sp.csc_matrix((Ax[i], Ai, Ap), shape=As), q_un, 10)
+        assert np.array_equal(emu['D'], ref['D']) and np.array_equal(emu['E'], ref['E']) and emu['c'] == ref['c']
+        assert np.array_equal(emu['Pv'], ref['P'].data) and np.array_equal(emu['Av'], ref['A'].data)
+
+
+def test_tables_assemble_and_factor(ltv_small):
+    """slot maps: the assembled S is the permuted KKT matrix; factor + solve on it == dense solve."""
+    fam, setup = ltv_small
+    params = ltv_batch(fam, 2, seed=5)
+    thb = _theta_rows(fam, setup, params, 2)
+    n, m = setup.n, setup.m
+    rho_vec = _kkt.rho_vector(setup.ctype, setup.rho)
+    Pi, Pp, Ps = fam.patterns['P']; Ai, Ap, As = fam.patterns['A']
+    for i in range(2):
+        emu = emulate_prepare(setup.mat_blob, thb[i])
+        S = emulate_assemble(emu['blob'], emu['Pv'], emu['Av'], setup.refactor.rho_slot, rho_vec)
+        K = _kkt.assemble_kkt(sp.csc_matrix((emu['Pv'], Pi, Pp), shape=Ps), sp.csc_matrix((emu['Av'], Ai, Ap), shape=As),
+                              setup.sigma, rho_vec).toarray()
+        perm = setup.factor.perm
+        Kp = K[np.ix_(perm, perm)]
+        T = setup.refactor
+        assert np.array_equal(S[:n + m], np.diag(Kp))
+        ii, jj = np.nonzero(T.slot >= 0)
+        assert np.array_equal(S[T.slot[ii, jj]], Kp[ii, jj])
+        # numeric factorisation + solve with the kernel's op lists on these values
+        T2 = type(T)(**{**T.__dict__, 'S0': np.where(np.isin(np.arange(T.n_slots), T.rho_slot), 0.0, S)})
+        Sf = emulate_factor(T2, rho_vec)
+        rhs = np.random.default_rng(i).standard_normal(n + m)
+        got = emulate_solve(T2, Sf, rhs[perm])
+        want = np.linalg.solve(K, rhs)[perm]
+        assert np.abs(got - want).max() < 1e-9 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.skipif(not ref_available(), reason='oracle/_ref not built')
+def test_numpy_restatement_vs_reference_matrix_updates():
+    """oracle pinning for this path: osqp_update_P_A + update_lin_cost/bounds + osqp_solve (compiled 0.6.2) vs the numpy
+    restatement -- identical iteration counts and statuses, x / y to 1e-9."""
+    fam = families.mpc_ltv(6, 3, 10)
+    B = 6
+    params = ltv_batch(fam, B)
+    Px, Ax, (q, l, u) = canon_matrix_batches(fam, params, B)
+    ref = matrix_oracle_solve(fam, Px, Ax, q, l, u, prefer_ref=True)
+    npy = matrix_oracle_solve(fam, Px, Ax, q, l, u, prefer_ref=False)
+    assert np.array_equal(ref['iter'], npy['iter']) and np.array_equal(ref['status'], npy['status'])
+    assert (ref['status'] == 1).all()
+    assert rel_err(npy['x'], ref['x']).max() < 1e-9 and rel_err(npy['y'], ref['y']).max() < 1e-9
+    # and the matrices matter: the shared-matrix solve of the same x_init gives another answer
+    from helpers import oracle_solve
+    shared = oracle_solve(fam, q, l, u)
+    assert rel_err(shared['x'], ref['x']).min() > 1e-3
+
+
+def test_generated_library_exports_matrix_entry():
+    import ctypes, os
+    d = standard.build('mpc_ltv_6_3_10')
+    lib = ctypes.CDLL(os.path.join(d, 'libcpg_b200.so'))
+    for sym in ('cpg_b200_load_mat_constants', 'cpg_solve_batch_device', 'cpg_solve_batch_host'):
+        assert hasattr(lib, sym)
+    hdr = open(os.path.join(d, 'c', 'include', 'cpg_family.h')).read()
+    assert '#define CPG_FAM_MATPAR 1' in hdr
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,B', [('mpc_ltv_6_3_10', 300), ('mpc_ltv_12_4_10', 200)])
+def test_gpu_matrix_parameters_vs_reference(name, B):
+    from cvxpygen_b200 import runtime
+    fam = standard.STANDARD[name][0]()
+    mod = standard.load(name, device=0)
+    params = ltv_batch(fam, B, seed=11)
+    res = mod.solve_batch(params, return_canonical=True)
+    assert mod.launch_count() == 1
+    Px, Ax, (q, l, u) = canon_matrix_batches(fam, params, B)
+    ora = matrix_oracle_solve(fam, Px, Ax, q, l, u)
+    info = res.cpg_info
+    assert np.array_equal(info.status, ora['status']), np.nonzero(info.status != ora['status'])[0][:5]
+    assert np.array_equal(info.iter, ora['iter']), np.nonzero(info.iter != ora['iter'])[0][:5]
+    assert (info.status == 1).mean() > 0.95
+    ok = np.isin(info.status, [1, 2, -2])
+    assert rel_err(res.sol_x[ok], ora['x'][ok]).max() < 1e-7       # north_star tolerance is 1e-5
+    assert rel_err(res.sol_y[ok], ora['y'][ok]).max() < 1e-7
+    assert np.allclose(info.obj_val[ok], ora['obj'][ok], rtol=1e-7, atol=1e-10)
+    # user-level gathers
+    X = res.cpg_prim['X']
+    assert np.abs(X[:, :, 0] - params['x_init']).max() < 1e-2      # x_0 = x_init to solver accuracy
+
+
+@pytest.mark.gpu
+def test_gpu_matrix_parameters_reduce_to_shared_family():
+    """With every instance carrying the DEFAULT matrices the matrix-parameter kernel must reproduce the shared-matrix
+    kernels' results on the same x_init (same algorithm, per-instance factor instead of the family's)."""
+    B = 500
+    fam = families.mpc_ltv(12, 4, 10)
+    xi = np.random.default_rng(2).uniform(-1, 1, (B, 12))
+    a = standard.load('mpc_ltv_12_4_10', device=0).solve_batch({'x_init': xi}, return_canonical=True)
+    b = standard.load('mpc_12_4_10', device=0).solve_batch({'x_init': xi}, return_canonical=True)
+    assert np.array_equal(a.cpg_info.iter, b.cpg_info.iter) and np.array_equal(a.cpg_info.status, b.cpg_info.status)
+    assert rel_err(a.sol_x, b.sol_x).max() < 1e-7 and rel_err(a.sol_y, b.sol_y).max() < 1e-7
+
+
+@pytest.mark.gpu
+def test_gpu_matrix_parameters_large_batch_properties():
+    """20 000 instances: optimality conditions of every instance's OWN problem (unscaled), run-to-run reproducibility."""
+    name, B = 'mpc_ltv_12_4_10', 20000
+    fam = standard.STANDARD[name][0]()
+    mod = standard.load(name, device=0)
+    params = ltv_batch(fam, B, seed=21)
+    r1 = mod.solve_batch(params, return_canonical=True)
+    r2 = mod.solve_batch(params, return_canonical=True)
+    assert np.array_equal(r1.sol_x, r2.sol_x, equal_nan=True) and np.array_equal(r1.cpg_info.iter, r2.cpg_info.iter)
+    ok = r1.cpg_info.status == 1
+    assert ok.mean() > 0.99
+    Px, Ax, (q, l, u) = canon_matrix_batches(fam, params, B)
+    Ai, Ap, As = fam.patterns['A']
+    rows = np.asarray(Ai); cols = np.repeat(np.arange(As[1]), np.diff(Ap))
+    Axx = np.zeros((B, As[0]))
+    np.add.at(Axx, (slice(None), rows), Ax * r1.sol_x[:, cols])
+    viol = np.maximum(np.maximum(l - Axx, Axx - u), 0.0).max(axis=1)
+    scale = np.maximum(np.abs(Axx).max(axis=1), 1.0)
+    assert (viol[ok] < 2e-3 * (1 + scale[ok])).all()               # eps_abs + eps_rel * |Ax| with eps = 1e-3
+    ATy = np.zeros((B, As[1]))
+    np.add.at(ATy, (slice(None), cols), Ax * r1.sol_y[:, rows])
+    Pdiag = Px                                                      # P is diagonal in this family
+    rd = np.abs(Pdiag * r1.sol_x + q + ATy).max(axis=1)
+    sc2 = np.maximum(np.maximum(np.abs(Pdiag * r1.sol_x).max(axis=1), np.abs(ATy).max(axis=1)), 1.0)
+    assert (rd[ok] < 2e-3 * (1 + sc2[ok])).all()
