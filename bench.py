@@ -115,8 +115,9 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=40000, help='instances in the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--with-grad', action='store_true', help='also time config 4: forward + backward (gradient=True)')
-    ap.add_argument('--workload', default='mpc', choices=['mpc', 'portfolio_socp'],
-                    help='mpc = the headline (BASELINE configs[1]); portfolio_socp = configs[2] through the IPM-CUDA backend')
+    ap.add_argument('--workload', default='mpc', choices=['mpc', 'portfolio_socp', 'mpc_ltv'],
+                    help='mpc = the headline (BASELINE configs[1]); portfolio_socp = configs[2] through the IPM-CUDA backend; '
+                         'mpc_ltv = the MPC family with per-instance matrix parameters (SURVEY row f2)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -127,6 +128,9 @@ def main():
     if args.workload == 'portfolio_socp':
         args.batch = args.batch or 50000
         return main_socp(args, rank, world, local_rank, W, K, cores)
+    if args.workload == 'mpc_ltv':
+        args.batch = args.batch or 20000
+        return main_ltv(args, rank, world, local_rank, W, K, cores)
     args.batch = args.batch or 100000
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
@@ -421,6 +425,145 @@ def main_socp(args, rank, world, local_rank, W, K, cores):
             ips, nw = run_reference_cpu_socp(n, cores)
             line['cpu_baseline'] = {'value': ips, 'unit': 'instances/s', 'cores': nw, 'kind': 'reference',
                                     'sample': f'{n} instances of the same workload, vendored ECOS 2.0.8 (oracle/_ref), {nw} host threads'}
+        except Exception as e:
+            line['cpu_baseline'] = {'value': None, 'unit': 'instances/s', 'cores': cores, 'kind': 'reference', 'sample': f'unavailable: {e}'}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# MPC QP with per-instance matrix parameters (python bench.py --workload mpc_ltv); the reference arm is
+# osqp_update_P_A + update_lin_cost/bounds + osqp_solve per instance on the host cores (oracle/_ref).
+LTV_FAMILY = 'mpc_ltv_12_4_10'
+LTV_WORKLOAD = ('MPC QP (n_x=12,n_u=4,N=10) with per-instance dynamics A, B and stage costs (220-entry parameter row; dense-pattern '
+                'A: nnz 2092) batch=%d per GPU, ADMM-CUDA matrix-parameter kernel, OSQP default settings')
+LTV_BYTES_PER_INSTANCE = 220 * 8 + (172 + 172) * 8 + 40
+
+
+def ltv_canonical(B, seed):
+    from cvxpygen_b200 import families
+    fam = families.mpc_ltv(12, 4, 10)
+    params = families.mpc_ltv_batch(fam, B, seed=seed)
+    th = np.tile(fam.theta_default(), (B, 1))
+    for pn, v in params.items():
+        p = fam.param(pn)
+        th[:, p.col:p.col + p.size] = v
+    Px = np.asarray((fam.maps['P'] @ th.T).T); Ax = np.asarray((fam.maps['A'] @ th.T).T)
+    l = np.clip(np.asarray(th @ fam.maps['l'].T.toarray()), -1e30, 1e30)
+    u = np.clip(np.asarray(th @ fam.maps['u'].T.toarray()), -1e30, 1e30)
+    return fam, params, Px, Ax, l, u
+
+
+def run_reference_cpu_ltv(n_inst, threads, seed=31):
+    from oracle import ref_osqp
+    if not ref_osqp.available():
+        raise RuntimeError('oracle/_ref/libosqp_ref.so missing (run `make -C oracle ref` where /root/reference exists)')
+    fam, _, Px, Ax, l, u = ltv_canonical(n_inst, seed)
+    r = ref_osqp.RefOSQP(fam.canon_matrix('P'), fam.canon_data('q'), fam.canon_matrix('A'),
+                         fam.canon_data('l'), fam.canon_data('u'), nthreads=threads)
+    out = r.solve_batch_mat(Px=Px, Ax=Ax, l=l, u=u, nthreads=threads)
+    return n_inst / out['seconds'], out
+
+
+def main_ltv(args, rank, world, local_rank, W, K, cores):
+    metric = 'QP instances/sec (MPC n_x=12,n_u=4,N=10, per-instance matrices)'
+    B = args.batch
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        sample = min(B, 4000)
+        run_reference_cpu_ltv(256, cores)
+        t = []
+        for _ in range(K):
+            ips, _ = run_reference_cpu_ltv(sample, cores)
+            t.append(sample / ips)
+        ms = 1e3 * float(np.mean(t)); value = sample / (ms / 1e3)
+        print(json.dumps({'impl': 'reference', 'metric': metric, 'value': value, 'unit': 'instances/s', 'n_gpus': args.gpus, 'steps': K,
+                          'warmup': W, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+                          'data': 'synthetic', 'config': {'workload': LTV_WORKLOAD % B, 'sample': f'{sample} instances per step'},
+                          'cpu_baseline': {'value': value, 'unit': 'instances/s', 'cores': cores, 'kind': 'reference',
+                                           'sample': f'{sample} instances/step x {K} steps, vendored OSQP 0.6.2 (oracle/_ref): '
+                                                     f'osqp_update_P_A + update_bounds + osqp_solve per instance, {cores} host threads'},
+                          'e2e': {'value': value, 'unit': 'instances/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
+        return
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    from cvxpygen_b200 import standard, families
+    mod = standard.load(LTV_FAMILY, device=local_rank).init()
+    fam = families.mpc_ltv(12, 4, 10)
+    P_host = mod.pack_params(families.mpc_ltv_batch(fam, B, seed=31 + rank))
+    params = torch.from_numpy(P_host).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out = None
+    for _ in range(W):
+        out = mod.solve_batch_device(params, out=out)
+    torch.cuda.synchronize()
+    launches_per_step = mod.launch_count()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for k in range(K):
+        flush.fill_(k & 0xff)
+        ev[k][0].record()
+        out = mod.solve_batch_device(params, out=out)
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag.set(); sampler.join()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / K
+    value = world * B / (ms_step / 1e3)
+    d = mod.dims
+    pin = lambda shape, dt=torch.float64: torch.empty(shape, dtype=dt).pin_memory()
+    hp = pin((B, d.n_param)); hp.copy_(torch.from_numpy(P_host))
+    hout = dict(prim=pin((B, d.n_prim)), dual=pin((B, d.n_dual)), obj=pin((B,)), pri=pin((B,)), dua=pin((B,)),
+                it=pin((B,), torch.int32), st=pin((B,), torch.int32))
+    mod.solve_batch_pinned(hp, hout)
+    e2e_steps = 3
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        mod.solve_batch_pinned(hp, hout)
+    te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    st = out.status.cpu().numpy(); it = out.iter.cpu().numpy()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = load_peaks()
+    achieved = B * LTV_BYTES_PER_INSTANCE / (ms_step / 1e3) / 1e9
+    line = {'metric': metric, 'value': value, 'unit': 'instances/s', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_step,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': LTV_WORKLOAD % B, 'family': LTV_FAMILY, 'batch_per_gpu': B, 'parallelism': f'batch-shard x{world}',
+                       'l2': 'flushed between steps (256 MiB write), per-step CUDA events summed',
+                       'mean_iter': float(it.mean()), 'frac_solved': float((st == 1).mean())},
+            'e2e': {'value': world * B / float(te.item()), 'unit': 'instances/s', 'h2d_bytes_per_step': B * d.n_param * 8,
+                    'd2h_bytes_per_step': B * ((d.n_prim + d.n_dual) * 8 + 32), 'steps': e2e_steps,
+                    'note': 'pinned host buffers through cpg_solve_batch_host: H2D of the parameter rows, kernel (zero-copy result rows), D2H of the info arrays; host clock'},
+            'gpu_launches': launches_per_step * K, 'clocks': sampler.summary(),
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                         'peak_source': peak_src, 'algorithmic_bytes_per_instance': LTV_BYTES_PER_INSTANCE,
+                         'note': 'one warp per instance: equilibration, KKT assembly, numeric LDL\' and the ADMM loop all on chip '
+                                 '(factor in shared memory, tables in L2); HBM carries the parameter row in and the solution rows out; '
+                                 'the binding resource is the dependent chain of the per-instance triangular solves (profiles/r1_matpar_ncu_summary.md)'}}
+    if not args.no_cpu_baseline:
+        try:
+            n = min(args.cpu_sample, 4000)
+            ips, _ = run_reference_cpu_ltv(n, cores)
+            line['cpu_baseline'] = {'value': ips, 'unit': 'instances/s', 'cores': cores, 'kind': 'reference',
+                                    'sample': f'{n} instances of the same workload, vendored OSQP 0.6.2 (oracle/_ref): osqp_update_P_A + '
+                                              f'update_bounds + osqp_solve per instance, {cores} host threads'}
         except Exception as e:
             line['cpu_baseline'] = {'value': None, 'unit': 'instances/s', 'cores': cores, 'kind': 'reference', 'sample': f'unavailable: {e}'}
     print(json.dumps(line))

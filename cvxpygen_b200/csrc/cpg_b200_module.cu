@@ -48,7 +48,7 @@ struct Fam {
 #if CPG_FAM_MATPAR
   static constexpr int MAT_WARPS = CPG_FAM_MAT_WARPS;       // matrix-parameter kernel: warps per CTA
   static constexpr int MAT_A_STRIDE = CPG_FAM_MAT_A_STRIDE, MAT_P_STRIDE = CPG_FAM_MAT_P_STRIDE;
-  static constexpr int MAT_STRIDE = CPG_FAM_MAT_STRIDE;     // doubles per warp: w | S | Av | Pv | D Dinv E Einv
+  static constexpr int MAT_STRIDE = CPG_FAM_MAT_STRIDE;     // doubles of shared memory per warp: w | S | Pv | D Dinv E Einv
 #endif
 };
 #if CPG_FAM_MATPAR
@@ -68,6 +68,7 @@ struct Ctx {
   uint8_t* d_gblob = nullptr;
   double* d_gS0 = nullptr;
   uint8_t* d_mblob = nullptr;
+  double* d_mat_scratch = nullptr;       // per-warp slices for the scaled entries of A (matrix-parameter kernel)
   int cap_G = 0;
   double *g_soly = nullptr, *g_dprim = nullptr, *g_dparams = nullptr, *g_dq = nullptr, *g_dl = nullptr, *g_du = nullptr;
   unsigned int* d_counter = nullptr;
@@ -225,7 +226,11 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
   CK(cudaMemcpy(g.d_gblob, CPG_B200_FN(cpg_gblob_words), CPG_B200_FN(cpg_gblob_nbytes), cudaMemcpyHostToDevice));
   if (!g.d_gS0) CK(cudaMalloc(&g.d_gS0, CPG_B200_FN(cpg_gS0_nbytes)));
   CK(cudaMemcpy(g.d_gS0, CPG_B200_FN(cpg_gS0_words), CPG_B200_FN(cpg_gS0_nbytes), cudaMemcpyHostToDevice));
+#if CPG_FAM_MATPAR
+  CK(cudaFuncSetAttribute(cpgb200::qp_grad_kernel<Fam, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAD_SMEM_BYTES));
+#else
   CK(cudaFuncSetAttribute(cpgb200::qp_grad_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAD_SMEM_BYTES));
+#endif
   if (!g.d_tail_blob) CK(cudaMalloc(&g.d_tail_blob, CPG_B200_FN(cpg_tail_blob_nbytes)));
   CK(cudaMemcpy(g.d_tail_blob, CPG_B200_FN(cpg_tail_blob_words), CPG_B200_FN(cpg_tail_blob_nbytes), cudaMemcpyHostToDevice));
   CK(cudaFuncSetAttribute(cpgb200::admm_tail_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM_BYTES));
@@ -233,6 +238,7 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
   if (!g.d_mblob) CK(cudaMalloc(&g.d_mblob, CPG_B200_FN(cpg_mblob_nbytes)));
   CK(cudaMemcpy(g.d_mblob, CPG_B200_FN(cpg_mblob_words), CPG_B200_FN(cpg_mblob_nbytes), cudaMemcpyHostToDevice));
   CK(cudaFuncSetAttribute(cpgb200::admm_matpar_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAT_SMEM_BYTES));
+  if (!g.d_mat_scratch) CK(cudaMalloc(&g.d_mat_scratch, sizeof(double) * (size_t)g.n_sm * (Fam::MAT_WARPS > Fam::GRAD_WARPS ? Fam::MAT_WARPS : Fam::GRAD_WARPS) * Fam::MAT_A_STRIDE));
 #endif
   if (!g.d_counter) CK(cudaMalloc(&g.d_counter, sizeof(unsigned int)));
   if (!g.d_tail_count) CK(cudaMalloc(&g.d_tail_count, sizeof(int)));
@@ -242,7 +248,7 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
 }
 
 int CPG_B200_FN(cpg_b200_free)(void) {
-  void* ptrs[] = {g.d_blob, g.d_cblob, g.d_gblob, g.d_gS0, g.d_mblob, g.g_soly, g.g_dprim, g.g_dparams, g.g_dq, g.g_dl, g.g_du, g.d_tail_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0,
+  void* ptrs[] = {g.d_blob, g.d_cblob, g.d_gblob, g.d_gS0, g.d_mblob, g.d_mat_scratch, g.g_soly, g.g_dprim, g.g_dparams, g.g_dq, g.g_dl, g.g_du, g.d_tail_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0,
                   g.d_prim, g.d_dual, g.d_solx, g.d_soly, g.d_obj, g.d_pri, g.d_dua, g.d_iter, g.d_status};
   for (void* p : ptrs) if (p) cudaFree(p);
   g = Ctx();
@@ -284,7 +290,7 @@ int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const doubl
     int grid = g.n_sm;
     const int need = (B + Fam::MAT_WARPS - 1) / Fam::MAT_WARPS;
     if (grid > need) grid = need;
-    cpgb200::admm_matpar_kernel<Fam><<<grid, Fam::MAT_WARPS * 32, MAT_SMEM_BYTES, stream>>>(g.d_cblob, g.d_tail_blob, g.d_mblob, io, st);
+    cpgb200::admm_matpar_kernel<Fam><<<grid, Fam::MAT_WARPS * 32, MAT_SMEM_BYTES, stream>>>(g.d_cblob, g.d_tail_blob, g.d_mblob, g.d_mat_scratch, io, st);
     g.launches += 1;
     CK(cudaGetLastError());
     return CPG_B200_OK;
@@ -356,7 +362,7 @@ int CPG_B200_FN(cpg_gradient_batch_device)(int B, const double* sol_x, const dou
   (void)sol_x;   // only enters dP / dA (matrix parameters are shared in this build)
   if (!g.ready) return CPG_B200_ERR_NOT_INIT;
 #if CPG_FAM_MATPAR
-  snprintf(g.err, sizeof(g.err), "the backward pass is not generated for families with per-instance matrix parameters");
+  snprintf(g.err, sizeof(g.err), "this family has per-instance matrix parameters: call cpg_gradient_batch_*_mat (it needs the parameter rows)");
   return CPG_B200_ERR_BAD_ARG;
 #endif
   if (B < 0 || !sol_y || !dprim) return CPG_B200_ERR_BAD_ARG;
@@ -372,6 +378,70 @@ int CPG_B200_FN(cpg_gradient_batch_device)(int B, const double* sol_x, const dou
   g.launches += 1;
   CK(cudaGetLastError());
   return CPG_B200_OK;
+}
+
+int CPG_B200_FN(cpg_gradient_batch_device_mat)(int B, const double* params, const double* sol_x, const double* sol_y,
+                                               const double* dprim, double* dparams, double* dq, double* dl, double* du,
+                                               double* dP, double* dA, void* stream_) {
+  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+#if CPG_FAM_MATPAR
+  if (B < 0 || !params || !sol_x || !sol_y || !dprim) return CPG_B200_ERR_BAD_ARG;
+  g.launches = 0;
+  if (B == 0) return CPG_B200_OK;
+  cpgb200::GradIO io;
+  io.sol_y = sol_y; io.dprim = dprim; io.dparams = dparams; io.dq = dq; io.dl = dl; io.du = du; io.S0 = g.d_gS0; io.B = B;
+  io.params = params; io.sol_x = sol_x; io.dP = dP; io.dA = dA; io.mblob = g.d_mblob; io.a_scratch = g.d_mat_scratch;
+  int grid = g.n_sm;
+  const int need = (B + Fam::GRAD_WARPS - 1) / Fam::GRAD_WARPS;
+  if (grid > need) grid = need;
+  cpgb200::qp_grad_kernel<Fam, true><<<grid, Fam::GRAD_WARPS * 32, GRAD_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      g.d_gblob, g.d_tail_blob, io);
+  g.launches += 1;
+  CK(cudaGetLastError());
+  return CPG_B200_OK;
+#else
+  (void)B; (void)params; (void)sol_x; (void)sol_y; (void)dprim; (void)dparams; (void)dq; (void)dl; (void)du; (void)dP; (void)dA; (void)stream_;
+  snprintf(g.err, sizeof(g.err), "this library was generated without per-instance matrix parameters: call cpg_gradient_batch_*");
+  return CPG_B200_ERR_BAD_ARG;
+#endif
+}
+
+int CPG_B200_FN(cpg_gradient_batch_host_mat)(int B, const double* params, const double* sol_x, const double* sol_y,
+                                             const double* dprim, double* dparams, double* dq, double* dl, double* du,
+                                             double* dP, double* dA) {
+  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+#if CPG_FAM_MATPAR
+  if (B < 0 || !params || !sol_x || !sol_y || !dprim) return CPG_B200_ERR_BAD_ARG;
+  if (B == 0) { g.launches = 0; return CPG_B200_OK; }
+  const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words));
+  const CpgMatHeader* MH = reinterpret_cast<const CpgMatHeader*>(CPG_B200_FN(cpg_mblob_words));
+  const size_t szs[] = {(size_t)H->npb, (size_t)Fam::N, (size_t)Fam::M, (size_t)H->n_prim,          // in: params x y dprim
+                        (size_t)H->npb, (size_t)Fam::N, (size_t)Fam::M, (size_t)Fam::M, (size_t)MH->nnzP, (size_t)MH->nnzA};
+  const double* ins[] = {params, sol_x, sol_y, dprim};
+  double* outs[] = {dparams, dq, dl, du, dP, dA};
+  double* dev[10] = {nullptr};
+  cudaStream_t st = 0;
+  int rc = CPG_B200_OK;
+  for (int k = 0; k < 10 && rc == CPG_B200_OK; ++k) {
+    if (k >= 4 && !outs[k - 4]) continue;
+    if (cudaMalloc(&dev[k], sizeof(double) * (size_t)B * (szs[k] ? szs[k] : 1)) != cudaSuccess) rc = CPG_B200_ERR_CUDA;
+  }
+  for (int k = 0; k < 4 && rc == CPG_B200_OK; ++k)
+    if (cudaMemcpyAsync(dev[k], ins[k], sizeof(double) * (size_t)B * szs[k], cudaMemcpyHostToDevice, st) != cudaSuccess) rc = CPG_B200_ERR_CUDA;
+  if (rc == CPG_B200_OK)
+    rc = CPG_B200_FN(cpg_gradient_batch_device_mat)(B, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7], dev[8], dev[9], st);
+  for (int k = 4; k < 10 && rc == CPG_B200_OK; ++k)
+    if (outs[k - 4] && cudaMemcpyAsync(outs[k - 4], dev[k], sizeof(double) * (size_t)B * szs[k], cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      rc = CPG_B200_ERR_CUDA;
+  if (cudaStreamSynchronize(st) != cudaSuccess && rc == CPG_B200_OK) rc = CPG_B200_ERR_CUDA;
+  if (rc == CPG_B200_ERR_CUDA && !g.err[0]) snprintf(g.err, sizeof(g.err), "CUDA error in cpg_gradient_batch_host_mat: %s", cudaGetErrorString(cudaGetLastError()));
+  for (int k = 0; k < 10; ++k) if (dev[k]) cudaFree(dev[k]);
+  return rc;
+#else
+  (void)B; (void)params; (void)sol_x; (void)sol_y; (void)dprim; (void)dparams; (void)dq; (void)dl; (void)du; (void)dP; (void)dA;
+  snprintf(g.err, sizeof(g.err), "this library was generated without per-instance matrix parameters: call cpg_gradient_batch_*");
+  return CPG_B200_ERR_BAD_ARG;
+#endif
 }
 
 int CPG_B200_FN(cpg_gradient_batch_host)(int B, const double* sol_x, const double* sol_y, const double* dprim,

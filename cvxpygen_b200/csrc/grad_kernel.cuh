@@ -18,8 +18,16 @@
 // One stateless difference: the reference's dl/du split follows a[] carried over from EARLIER calls (a row that
 // flips from upper- to lower-active without passing through inactive keeps its old label, :437-449); here the
 // split follows sign(y) of the instance itself.  dl + du and dtheta are unaffected for l = u rows.
+// Families with per-instance MATRIX parameters (rows a16 + f2; template flag MATPAR): the instance's unscaled P and A are
+// canonicalised from its parameter row first (what cpg_P_to_K / cpg_A_to_K + cpg_ldl_numeric do when P / A are outdated,
+// cvxpygen/writer.py:240-263), K is assembled through the slot maps of the matrix blob, the refinement products run over
+// the index tables, and the matrix gradients  dP_k = -1/2 (r_i x_j + x_i r_j),  dA_k = -(r_{n+i} x_j + y_i r_j) [row active]
+// (:513-529) are folded into dtheta through the transposed maps of the P / A entries (writer.py:292-303).
 #pragma once
 #include "admm_kernel.cuh"
+#if CPG_FAM_MATPAR
+#include "matpar_kernel.cuh"
+#endif
 
 namespace cpgb200 {
 
@@ -34,9 +42,16 @@ struct GradIO {
   double* du;
   const double* S0;        // (n_slots) regularised KKT in slot order (global memory)
   int B;
+  // matrix-parameter families only
+  const double* params;    // (B, npb) the instances' parameter rows (their P and A are canonicalised from them)
+  const double* sol_x;     // (B, n) canonical primal solution (enters dP and dA)
+  double* dP;              // optional (B, nnzP) / (B, nnzA) canonical matrix gradients
+  double* dA;
+  const uint8_t* mblob;    // matrix tables (global)
+  double* a_scratch;       // per-warp slices for the entries of A
 };
 
-template <class Fam>
+template <class Fam, bool MATPAR = false>
 __global__ void __launch_bounds__(Fam::GRAD_WARPS * 32, 1)
 qp_grad_kernel(const uint8_t* __restrict__ gblob_g, const uint8_t* __restrict__ tail_blob_g, const GradIO io) {
   constexpr int N = Fam::N, M = Fam::M, NK = N + M, NXL = (N + 31) / 32, NZL = (M + 31) / 32, NZLs = NZL > 0 ? NZL : 1;
@@ -65,6 +80,33 @@ qp_grad_kernel(const uint8_t* __restrict__ gblob_g, const uint8_t* __restrict__ 
   double* rhsx = r + Fam::W_STRIDE;
   double* ys = rhsx + ((N + 1) & ~1);
   const int n_slots = H->n_slots;
+#if CPG_FAM_MATPAR
+  double* xs = ys + ((M + 1) & ~1);          // canonical x of the instance
+  MatCtx mc;
+  if constexpr (MATPAR) {
+    mc.mv = make_mat_view(io.mblob);
+    mc.Pv = xs + ((N + 1) & ~1);
+    mc.Av = io.a_scratch + ((size_t)blockIdx.x * Fam::GRAD_WARPS + warp) * Fam::MAT_A_STRIDE;
+  }
+#endif
+  auto dotA = [&](int k) -> double {
+#if CPG_FAM_MATPAR
+    if constexpr (MATPAR) return ellx_dot(mc.mv.I32 + mc.mv.H->i_ixA + 3 * k, mc.mv.U16, mc.Av, r, lane);
+#endif
+    return ell_dot(I32 + H->i_ellA + 3 * k, F64, U16, r, lane);
+  };
+  auto dotAt = [&](int k) -> double {
+#if CPG_FAM_MATPAR
+    if constexpr (MATPAR) return ellx_dot(mc.mv.I32 + mc.mv.H->i_ixAt + 3 * k, mc.mv.U16, mc.Av, r, lane);
+#endif
+    return ell_dot(I32 + H->i_ellAt + 3 * k, F64, U16, r, lane);
+  };
+  auto dotP = [&](int k) -> double {
+#if CPG_FAM_MATPAR
+    if constexpr (MATPAR) return ellx_dot(mc.mv.I32 + mc.mv.H->i_ixP + 3 * k, mc.mv.U16, mc.Pv, r, lane);
+#endif
+    return ell_dot(I32 + H->i_ellP + 3 * k, F64, U16, r, lane);
+  };
 
   for (int b = blockIdx.x * Fam::GRAD_WARPS + warp; b < io.B; b += gridDim.x * Fam::GRAD_WARPS) {
     // ---- inputs: dual solution -> active set; upstream gradient scattered into canonical dx (cpg_update_d<var>)
@@ -79,7 +121,24 @@ qp_grad_kernel(const uint8_t* __restrict__ gblob_g, const uint8_t* __restrict__ 
       }
     }
     for (int i = lane; i < N; i += LANES) rhsx[i] = 0.0;
-    for (int i = lane; i < n_slots; i += LANES) S[i] = __ldg(io.S0 + i);
+#if CPG_FAM_MATPAR
+    if constexpr (MATPAR) {
+      // this instance's K_reg = [[P + reg I, A'], [A, -reg I]] on the symbolic pattern (cvxpygen/writer.py:361-364)
+      matpar_canon(mc, io.params + (size_t)b * H->npb, lane);
+      for (int i = lane; i < N; i += LANES) xs[i] = io.sol_x[(size_t)b * N + i];
+      for (int i = lane; i < n_slots; i += LANES) S[i] = 0.0;
+      __syncwarp();
+      for (int i = lane; i < N; i += LANES) S[U16[H->h_pinvx + i]] = 1e-6;
+      for (int j = lane; j < M; j += LANES) S[U16[H->h_pinvz + j]] = -1e-6;
+      __syncwarp();
+      const CpgMatHeader* MH = mc.mv.H;
+      for (int e = lane; e < MH->nnzP; e += LANES) S[__ldg(mc.mv.U16 + MH->h_Pslot + e)] += mc.Pv[e];
+      for (int e = lane; e < MH->nnzA; e += LANES) S[__ldg(mc.mv.U16 + MH->h_Aslot + e)] = mc.Av[e];
+    } else
+#endif
+    {
+      for (int i = lane; i < n_slots; i += LANES) S[i] = __ldg(io.S0 + i);
+    }
     __syncwarp();
     {
       const int np = H->n_prim;
@@ -116,14 +175,13 @@ qp_grad_kernel(const uint8_t* __restrict__ gblob_g, const uint8_t* __restrict__ 
       for (int k = 0; k < NXL; ++k) {
         const int i = lane + 32 * k;
         dxk[k] = 0.0;
-        if (i < N) dxk[k] = rhsx[i] - ell_dot(I32 + H->i_ellP + 3 * k, F64, U16, r, lane)
-                                    - ((M > 0) ? ell_dot(I32 + H->i_ellAt + 3 * k, F64, U16, r, lane) : 0.0);
+        if (i < N) dxk[k] = rhsx[i] - dotP(k) - ((M > 0) ? dotAt(k) : 0.0);
       }
 #pragma unroll
       for (int k = 0; k < NZL; ++k) {
         const int j = lane + 32 * k;
         dzk[k] = 0.0;
-        if (j < M && ((act >> k) & 1u)) dzk[k] = -ell_dot(I32 + H->i_ellA + 3 * k, F64, U16, r, lane);
+        if (j < M && ((act >> k) & 1u)) dzk[k] = -dotA(k);
       }
 #pragma unroll
       for (int k = 0; k < NXL; ++k) { const int i = lane + 32 * k; if (i < N) w[U16[H->h_pinvx + i]] = dxk[k]; }
@@ -146,6 +204,20 @@ qp_grad_kernel(const uint8_t* __restrict__ gblob_g, const uint8_t* __restrict__ 
         if (io.du) io.du[(size_t)b * M + j] = (yv > GRAD_ACTIVE_TOL) ? rv : 0.0;
       }
     }
+#if CPG_FAM_MATPAR
+    if constexpr (MATPAR) {
+      const CpgMatHeader* MH = mc.mv.H;
+      if (io.dP) for (int e = lane; e < MH->nnzP; e += LANES) {
+        const int i = __ldg(mc.mv.U16 + MH->h_Prow + e), j = __ldg(mc.mv.U16 + MH->h_Pcol + e);
+        io.dP[(size_t)b * MH->nnzP + e] = -0.5 * (r[i] * xs[j] + xs[i] * r[j]);
+      }
+      if (io.dA) for (int e = lane; e < MH->nnzA; e += LANES) {
+        const int i = __ldg(mc.mv.U16 + MH->h_Arow + e), j = __ldg(mc.mv.U16 + MH->h_Acol + e);
+        const double yv = ys[i];
+        io.dA[(size_t)b * MH->nnzA + e] = (yv < -GRAD_ACTIVE_TOL || yv > GRAD_ACTIVE_TOL) ? -(r[N + i] * xs[j] + yv * r[j]) : 0.0;
+      }
+    }
+#endif
     if (io.dparams) {
       const int npb = H->npb;
       for (int cidx = lane; cidx < npb; cidx += LANES) {
@@ -155,7 +227,17 @@ qp_grad_kernel(const uint8_t* __restrict__ gblob_g, const uint8_t* __restrict__ 
           const double v = F64[H->f_tval + e];
           if (kind == 0) acc -= v * r[idx];                                           // dq = -r_x
           else if (kind == 1) { if (ys[idx] < -GRAD_ACTIVE_TOL) acc += v * r[N + idx]; }   // dl
-          else { if (ys[idx] > GRAD_ACTIVE_TOL) acc += v * r[N + idx]; }                   // du
+          else if (kind == 2) { if (ys[idx] > GRAD_ACTIVE_TOL) acc += v * r[N + idx]; }    // du
+#if CPG_FAM_MATPAR
+          else if (MATPAR && kind == 3) {                                                  // dP entry idx
+            const int i = __ldg(mc.mv.U16 + mc.mv.H->h_Prow + idx), j = __ldg(mc.mv.U16 + mc.mv.H->h_Pcol + idx);
+            acc += v * (-0.5 * (r[i] * xs[j] + xs[i] * r[j]));
+          } else if (MATPAR && kind == 4) {                                                // dA entry idx (active rows only)
+            const int i = __ldg(mc.mv.U16 + mc.mv.H->h_Arow + idx), j = __ldg(mc.mv.U16 + mc.mv.H->h_Acol + idx);
+            const double yv = ys[i];
+            if (yv < -GRAD_ACTIVE_TOL || yv > GRAD_ACTIVE_TOL) acc -= v * (r[N + i] * xs[j] + yv * r[j]);
+          }
+#endif
         }
         io.dparams[(size_t)b * npb + cidx] = acc;
       }

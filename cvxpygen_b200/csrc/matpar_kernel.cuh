@@ -30,15 +30,10 @@ __device__ __forceinline__ double limit_scaling1(double v) {      // scaling.c:7
   return v > 1e4 ? 1e4 : v;
 }
 
-// steps 1-2; on exit mc.Av / mc.Pv hold the scaled matrices, mc.D/Dinv/E/Einv/c/cinv the scalings.  w: >= n+m doubles scratch.
-template <class Fam>
-__device__ void matpar_prepare(MatCtx& mc, const double* __restrict__ th, double* __restrict__ w, const int lane,
-                               const int scaling) {
-  constexpr int N = Fam::N, M = Fam::M, NXL = (N + 31) / 32, NZL = (M + 31) / 32, NZLs = NZL > 0 ? NZL : 1;
+// step 1: cpg_canonicalize_P / _A for this instance (UNSCALED entries into mc.Pv / mc.Av; slot nnz = 0 for padding)
+__device__ __forceinline__ void matpar_canon(MatCtx& mc, const double* __restrict__ th, const int lane) {
   const CpgMatHeader* H = mc.mv.H;
   const int* I32 = mc.mv.I32; const double* F64 = mc.mv.F64; const uint16_t* U16 = mc.mv.U16;
-  const int nnzP = H->nnzP, nnzA = H->nnzA;
-  // ---- 1. cpg_canonicalize_P / _A for this instance
   auto canon = [&](double* out, int nnz, int i_ell, int f_base) {
     for (int e0 = 0, blk = 0; e0 < nnz; e0 += LANES, ++blk) {
       const int e = e0 + lane;
@@ -53,9 +48,20 @@ __device__ void matpar_prepare(MatCtx& mc, const double* __restrict__ th, double
     }
     if (lane == 0) out[nnz] = 0.0;
   };
-  canon(mc.Pv, nnzP, H->i_ellMP, H->f_Pbase);
-  canon(mc.Av, nnzA, H->i_ellMA, H->f_Abase);
+  canon(mc.Pv, H->nnzP, H->i_ellMP, H->f_Pbase);
+  canon(mc.Av, H->nnzA, H->i_ellMA, H->f_Abase);
   __syncwarp();
+}
+
+// steps 1-2; on exit mc.Av / mc.Pv hold the scaled matrices, mc.D/Dinv/E/Einv/c/cinv the scalings.  w: >= n+m doubles scratch.
+template <class Fam>
+__device__ void matpar_prepare(MatCtx& mc, const double* __restrict__ th, double* __restrict__ w, const int lane,
+                               const int scaling) {
+  constexpr int N = Fam::N, M = Fam::M, NXL = (N + 31) / 32, NZL = (M + 31) / 32, NZLs = NZL > 0 ? NZL : 1;
+  const CpgMatHeader* H = mc.mv.H;
+  const int* I32 = mc.mv.I32; const double* F64 = mc.mv.F64; const uint16_t* U16 = mc.mv.U16;
+  const int nnzP = H->nnzP, nnzA = H->nnzA;
+  matpar_canon(mc, th, lane);
   // ---- 2. scale_data
   double d[NXL], e_[NZLs], q[NXL];
 #pragma unroll
@@ -120,11 +126,14 @@ __device__ void matpar_prepare(MatCtx& mc, const double* __restrict__ th, double
 
 // One persistent CTA per SM; every warp pulls instance numbers from the global counter.  Nothing is staged: the family's
 // compact blob, the refactorisation tables and the matrix tables are read from global memory (L2-resident, shared by all
-// warps) so that shared memory is left to the per-instance state: w | S | Av | Pv | D Dinv E Einv.
+// warps) so that shared memory is left to the per-instance state that every ADMM iteration touches: w | S | Pv | D Dinv E
+// Einv.  The scaled entries of A -- read by the equilibration, the assembly and the residual products every 25 iterations
+// only -- live in a per-warp slice of a global scratch buffer (a few MB in total: L2-resident), which is what lets five
+// instead of three warps share an SM at MPC-12/4/10 with dense dynamics.
 template <class Fam>
 __global__ void __launch_bounds__(Fam::MAT_WARPS * 32, 1)
 admm_matpar_kernel(const uint8_t* __restrict__ cblob_g, const uint8_t* __restrict__ tail_blob_g,
-                   const uint8_t* __restrict__ mblob_g, const BatchIO io, const Settings st) {
+                   const uint8_t* __restrict__ mblob_g, double* __restrict__ a_scratch, const BatchIO io, const Settings st) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(cblob_g);
@@ -139,8 +148,8 @@ admm_matpar_kernel(const uint8_t* __restrict__ cblob_g, const uint8_t* __restric
   ta.S = wbase + Fam::W_STRIDE;
   ta.state = nullptr;
   ta.mc = &mc;
-  mc.Av = ta.S + Fam::S_STRIDE;
-  mc.Pv = mc.Av + Fam::MAT_A_STRIDE;
+  mc.Av = a_scratch + ((size_t)blockIdx.x * Fam::MAT_WARPS + warp) * Fam::MAT_A_STRIDE;
+  mc.Pv = ta.S + Fam::S_STRIDE;
   mc.D = mc.Pv + Fam::MAT_P_STRIDE;
   constexpr int NP = (Fam::N + 1) & ~1, MP = (Fam::M + 1) & ~1;
   mc.Dinv = mc.D + NP; mc.E = mc.Dinv + NP; mc.Einv = mc.E + MP;

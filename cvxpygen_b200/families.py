@@ -209,6 +209,18 @@ def mpc_ltv(nx=12, nu=4, N=10, Ad=None, Bd=None, qdiag=None, rdiag=None, umax=1.
                        {'P': _csc_pattern(Pu), 'A': Apat}, variables, duals)
 
 
+def mpc_ltv_batch(fam: CanonFamily, B: int, seed: int = 3, spread: float = 0.05):
+    """Synthetic per-instance parameters for ``mpc_ltv`` (bench.py --workload mpc_ltv and the tests): dynamics perturbed
+    entry-wise around the family's defaults (N(0, spread^2)), diagonal stage costs U[0.5, 2] / U[0.05, 0.5], x_init U[-1, 1]."""
+    rng = np.random.default_rng(seed)
+    A0, B0 = fam.param('A').default, fam.param('B').default
+    return {'A': A0[None, :] + spread * rng.standard_normal((B, A0.size)),
+            'B': B0[None, :] + spread * rng.standard_normal((B, B0.size)),
+            'qdiag': rng.uniform(0.5, 2.0, (B, fam.param('qdiag').size)),
+            'rdiag': rng.uniform(0.05, 0.5, (B, fam.param('rdiag').size)),
+            'x_init': rng.uniform(-1, 1, (B, fam.param('x_init').size))}
+
+
 def nonneg_ls(m=3, n=2, A_pattern=None, A_data=None, b=None, seed=1, name=None) -> CanonFamily:
     """README example  min ||A x - b||^2  s.t. x >= 0  (reference: examples/main.py:16-26).
 

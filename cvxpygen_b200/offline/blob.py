@@ -295,7 +295,8 @@ def grad_header_struct_c(name='CpgGradHeader') -> str:
     return 'struct %s {\n%s};\n' % (name, ''.join(f'  {t} {n};\n' for t, n in GRAD_HEADER_FIELDS))
 
 
-def pack_grad_blob(*, n, m, perm, P_upper, A, slot_of, n_slots, Mq_b, Ml_b, Mu_b, npb, prim_idx, reg=1e-6):
+def pack_grad_blob(*, n, m, perm, P_upper, A, slot_of, n_slots, Mq_b, Ml_b, Mu_b, npb, prim_idx, reg=1e-6,
+                   MP_b=None, MA_b=None):
     """P_upper, A: UNSCALED canonical matrices; slot_of(i, j) -> slot of the lower-triangle entry (pivot positions).
     Returns (blob for shared memory, S0 array for global memory)."""
     nk = n + m
@@ -321,10 +322,13 @@ def pack_grad_blob(*, n, m, perm, P_upper, A, slot_of, n_slots, Mq_b, Ml_b, Mu_b
             arow_slot.append(s_)
         arow_ptr.append(len(arow_slot))
     hv = dict(magic=MAGIC + 2, n=n, m=m, nk=nk, npb=npb, n_prim=len(prim_idx), n_slots=n_slots)
-    hv['i_ellA'] = _add_ell(ar, ell_row_blocks(A, m))
-    At_blocks = [(K, v, cidx + n) for K, v, cidx in ell_row_blocks(sp.csr_matrix(A.T), n)]
-    hv['i_ellAt'] = _add_ell(ar, At_blocks)
-    hv['i_ellP'] = _add_ell(ar, ell_row_blocks(Pfull, n))
+    if MP_b is None and MA_b is None:
+        hv['i_ellA'] = _add_ell(ar, ell_row_blocks(A, m))
+        At_blocks = [(K, v, cidx + n) for K, v, cidx in ell_row_blocks(sp.csr_matrix(A.T), n)]
+        hv['i_ellAt'] = _add_ell(ar, At_blocks)
+        hv['i_ellP'] = _add_ell(ar, ell_row_blocks(Pfull, n))
+    else:       # matrix-parameter family: the products run over the index tables of the matrix blob with per-instance values
+        hv['i_ellA'] = hv['i_ellAt'] = hv['i_ellP'] = ar.add_i32([0, 0, 0])
     hv['i_arow_ptr'] = ar.add_i32(arow_ptr)
     hv['h_arow_slot'] = ar.add_u16(arow_slot)
     hv['h_pinvx'] = ar.add_u16(pinv[:n]); hv['h_pinvz'] = ar.add_u16(pinv[n:])
@@ -332,6 +336,9 @@ def pack_grad_blob(*, n, m, perm, P_upper, A, slot_of, n_slots, Mq_b, Ml_b, Mu_b
     # transposed maps: for every batched parameter entry c the list of (kind, row, coefficient)
     tptr, tidx, tkind, tval = [0], [], [], []
     Ms = [sp.csc_matrix(M) for M in (Mq_b, Ml_b, Mu_b)]
+    if MP_b is not None or MA_b is not None:      # kinds 3 / 4: entries of P / A (idx = entry number in CSC order)
+        Ms += [sp.csc_matrix(MP_b if MP_b is not None else sp.csr_matrix((0, max(npb, 1)))),
+               sp.csc_matrix(MA_b if MA_b is not None else sp.csr_matrix((0, max(npb, 1))))]
     for cidx in range(npb):
         for kind, M in enumerate(Ms):
             s_, e_ = M.indptr[cidx], M.indptr[cidx + 1]

@@ -126,8 +126,11 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
     RT = build_refactor_tables(F, K, n)
     tail_blob = pack_tail_blob(RT)
     # backward pass (gradient=True): regularised KKT of the UNSCALED problem on the same symbolic pattern
+    gkw = {}
+    if mat_params:      # rows a16 + f2: transposed maps of the P / A entries -> dtheta of the matrix parameters
+        gkw = dict(MP_b=sp.csr_matrix(fam.maps['P'][:, bcols]), MA_b=sp.csr_matrix(fam.maps['A'][:, bcols]))
     grad_blob, grad_S0 = pack_grad_blob(n=n, m=m, perm=F.perm, P_upper=sp.csc_matrix(P), A=sp.csc_matrix(A), slot_of=RT.slot_of,
-                                        n_slots=RT.n_slots, Mq_b=Mq_b, Ml_b=Ml_b, Mu_b=Mu_b, npb=npb, prim_idx=prim_idx)
+                                        n_slots=RT.n_slots, Mq_b=Mq_b, Ml_b=Ml_b, Mu_b=Mu_b, npb=npb, prim_idx=prim_idx, **gkw)
     mat_blob = b''
     if mat_params:
         mat_blob = _matpar_blob(fam, sc, P, A, q, theta0, bcols, npb, F, RT, sigma, scaling, n, m)

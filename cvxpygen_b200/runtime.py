@@ -291,6 +291,47 @@ class Module:
                 col += p['size']
         return out
 
+    @property
+    def has_matrix_params(self):
+        return bool(self.meta.get('matrix_params'))
+
+    def gradient_batch_mat(self, params, sol_x, sol_y, dprim, return_canonical=False):
+        """Backward pass of a family with per-instance matrix parameters (host arrays): `params` as given to solve_batch
+        (dict or packed rows), sol_x / sol_y the canonical solution of the forward pass.  Returns the dict of parameter
+        gradients[, dq, dl, du, dP, dA] (dP / dA: canonical matrix entries in CSC order)."""
+        self.init()
+        P = params if isinstance(params, np.ndarray) else self.pack_params(params)
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        sol_x = np.ascontiguousarray(sol_x, dtype=np.float64); sol_y = np.ascontiguousarray(sol_y, dtype=np.float64)
+        B = sol_y.shape[0]
+        if P.shape[0] == 1 and B > 1:
+            P = np.ascontiguousarray(np.broadcast_to(P, (B, P.shape[1])))
+        D = np.ascontiguousarray(dprim if isinstance(dprim, np.ndarray) else self.pack_dprim(dprim, B), dtype=np.float64)
+        d = self.dims
+        dpar = np.empty((B, d.n_param))
+        dq = np.empty((B, d.n_var)) if return_canonical else None
+        dl = np.empty((B, d.n_con)) if return_canonical else None
+        du = np.empty((B, d.n_con)) if return_canonical else None
+        dP = np.empty((B, self.meta['nnzP'])) if return_canonical else None
+        dA = np.empty((B, self.meta['nnzA'])) if return_canonical else None
+        p = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+        self._check(self._fn('cpg_gradient_batch_host_mat')(C.c_int(B), p(P), p(sol_x), p(sol_y), p(D), p(dpar), p(dq), p(dl),
+                                                            p(du), p(dP), p(dA)))
+        res = self.unpack_dparams(dpar)
+        return (res, dq, dl, du, dP, dA) if return_canonical else res
+
+    def gradient_batch_device_mat(self, params, sol_x, sol_y, dprim, dparams=None):
+        import torch
+        self.init()
+        B = sol_y.shape[0]
+        if dparams is None:
+            dparams = torch.empty((B, self.dims.n_param), dtype=torch.float64, device=sol_y.device)
+        ptr = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(sol_y.device).cuda_stream)
+        self._check(self._fn('cpg_gradient_batch_device_mat')(C.c_int(B), ptr(params), ptr(sol_x), ptr(sol_y), ptr(dprim),
+                                                              ptr(dparams), None, None, None, None, None, stream))
+        return dparams
+
     def gradient_batch(self, sol_y, dprim, sol_x=None, return_canonical=False):
         """Host arrays.  Returns (dict name -> (B, size) gradients of the batched parameters[, dq, dl, du])."""
         self.init()

@@ -132,6 +132,19 @@ int CPG_B200_FN(cpg_gradient_batch_device)(int B, const double* sol_x, const dou
 int CPG_B200_FN(cpg_gradient_batch_host)(int B, const double* sol_x, const double* sol_y, const double* dprim,
                                          double* dparams, double* dq, double* dl, double* du);
 
+/* The same for families generated with per-instance MATRIX parameters (SURVEY rows a16 + f2).  Reference counterpart:
+ * the P / A branch of <p>cpg_gradient() (cvxpygen/writer.py:240-263: cpg_P_to_K, cpg_A_to_K, cpg_ldl_numeric) followed by
+ * cpg_osqp_gradient() and the un-canonicalisation of dP / dA through canon_P_map / canon_A_map (writer.py:292-303).
+ *   params (B, n_param): the parameter rows of the forward solve (each instance's P and A are canonicalised from them)
+ *   sol_x required;  dP (B, nnz(P upper)), dA (B, nnz(A)): optional canonical matrix gradients in CSC order (NULL = skip)
+ * Error for libraries generated without such parameters (and cpg_gradient_batch_* is an error for those with). */
+int CPG_B200_FN(cpg_gradient_batch_device_mat)(int B, const double* params, const double* sol_x, const double* sol_y,
+                                               const double* dprim, double* dparams, double* dq, double* dl, double* du,
+                                               double* dP, double* dA, void* stream);
+int CPG_B200_FN(cpg_gradient_batch_host_mat)(int B, const double* params, const double* sol_x, const double* sol_y,
+                                             const double* dprim, double* dparams, double* dq, double* dl, double* du,
+                                             double* dP, double* dA);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,43 @@ void grad_ref_batch(int B, const double* x, const double* y, const double* dx, d
     memcpy(du + (size_t)b * %(m)d, CPG_OSQP_Grad.du, sizeof(double) * %(m)d);
   }
 }
+/* Per-instance matrices (Px (B, nnzP) upper triangle, Ax (B, nnzA), CSC order): what the generated cpg_gradient() does
+   when P / A are outdated (cvxpygen/writer.py:240-263): cpg_P_to_K / cpg_A_to_K, cpg_ldl_numeric, a[] = 1, then
+   cpg_osqp_gradient().  Also returns dP (B, nnzP) and dA (B, nnzA). */
+void grad_ref_batch_mat(int B, const double* Px, const double* Ax, const double* x, const double* y, const double* dx,
+                        double* dq, double* dl, double* du, double* dP, double* dA) {
+  int b, i, j, k;
+  const int nnzP = CPG_OSQP_Grad.dP->p[%(n)d], nnzA = CPG_OSQP_Grad.dA->p[%(n)d];
+  for (b = 0; b < B; b++) {
+    cpg_grad_csc Pm = *CPG_OSQP_Grad.dP, Am = *CPG_OSQP_Grad.dA;
+    Pm.x = (cpg_grad_float*)(Px + (size_t)b * nnzP);
+    Am.x = (cpg_grad_float*)(Ax + (size_t)b * nnzA);
+    memcpy(sol_x, x + (size_t)b * %(n)d, sizeof(double) * %(n)d);
+    memcpy(sol_y, y + (size_t)b * %(m)d, sizeof(double) * %(m)d);
+    for (i = 0; i < %(n)d; i++) CPG_OSQP_Grad.dx[i] = dx[(size_t)b * %(n)d + i];
+    cpg_P_to_K(&Pm, CPG_OSQP_Grad.K, CPG_OSQP_Grad.K_true);
+    cpg_A_to_K(&Am, CPG_OSQP_Grad.K, CPG_OSQP_Grad.K_true);
+    if (CPG_OSQP_Grad.init) {
+      cpg_ldl_symbolic();
+      cpg_ldl_numeric();
+      for (j = 0; j < %(N)d - 1; j++)
+        for (k = CPG_OSQP_Grad.L->p[j]; k < CPG_OSQP_Grad.L->p[j + 1]; k++) {
+          i = CPG_OSQP_Grad.L->i[k];
+          CPG_OSQP_Grad.Lmask[(2 * %(N)d - 3 - j) * j / 2 + i - 1] = 1;
+        }
+      CPG_OSQP_Grad.init = 0;
+    } else {
+      cpg_ldl_numeric();
+      for (i = 0; i < %(m)d; i++) CPG_OSQP_Grad.a[i] = 1;
+    }
+    cpg_osqp_gradient();
+    memcpy(dq + (size_t)b * %(n)d, CPG_OSQP_Grad.dq, sizeof(double) * %(n)d);
+    memcpy(dl + (size_t)b * %(m)d, CPG_OSQP_Grad.dl, sizeof(double) * %(m)d);
+    memcpy(du + (size_t)b * %(m)d, CPG_OSQP_Grad.du, sizeof(double) * %(m)d);
+    memcpy(dP + (size_t)b * nnzP, CPG_OSQP_Grad.dP->x, sizeof(double) * nnzP);
+    memcpy(dA + (size_t)b * nnzA, CPG_OSQP_Grad.dA->x, sizeof(double) * nnzA);
+  }
+}
 '''
 
 
@@ -143,9 +180,31 @@ def grad_ref_batch(so, n, m, x, y, dx):
     return dq, dl, du
 
 
+def grad_ref_batch_mat(so, n, m, Px, Ax, x, y, dx):
+    import ctypes as C
+    lib = C.CDLL(so)
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    Px, Ax, x, y, dx = c(Px), c(Ax), c(x), c(y), c(dx)
+    B = x.shape[0]
+    dq = np.zeros((B, n)); dl = np.zeros((B, m)); du = np.zeros((B, m))
+    dP = np.zeros((B, Px.shape[1])); dA = np.zeros((B, Ax.shape[1]))
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    lib.grad_ref_batch_mat(C.c_int(B), p(Px), p(Ax), p(x), p(y), p(dx), p(dq), p(dl), p(du), p(dP), p(dA))
+    return dq, dl, du, dP, dA
+
+
+def structural(M):
+    """same pattern, every stored entry = 1: keeps structural zeros through scipy's sparse arithmetic."""
+    M = sp.csc_matrix(M)
+    return sp.csc_matrix((np.ones(len(M.indices)), M.indices.copy(), M.indptr.copy()), shape=M.shape)
+
+
 if __name__ == '__main__':
     sys.path.insert(0, ROOT)
     from cvxpygen_b200 import standard
     for name in (sys.argv[1:] or ['mpc_6_3_10', 'nonneg_LS_3_2', 'random_qp_20_5_15', 'mpc_12_4_10']):
         fam = standard.STANDARD[name][0]()
-        print('built', build(name, fam.canon_matrix('P'), fam.canon_matrix('A')))
+        if name in standard.MATPAR_NAMES:     # every structural entry must exist in K / K_true: values are set per instance
+            print('built', build(name, structural(fam.canon_matrix('P')), structural(fam.canon_matrix('A'))))
+        else:
+            print('built', build(name, fam.canon_matrix('P'), fam.canon_matrix('A')))

@@ -66,3 +66,38 @@ def param_gradient(fam, dq, dl, du, names=None):
         if M is not None and M.nnz:
             out += d @ M[:, cols].toarray()
     return out
+
+
+def qp_backward_mat(P_pattern, A_pattern, Px, Ax, x, y, dx, n_refine=3):
+    """Per-instance matrices (SURVEY rows a16 + f2).  P_pattern / A_pattern: (indices, indptr, shape) CSC (P upper triangle);
+    Px (B, nnzP), Ax (B, nnzA) the instances' entries.  Returns dq, dl, du, dP (B, nnzP), dA (B, nnzA):
+      dP_k = -1/2 (r_i x_j + x_i r_j),  dA_k = -(r_{n+i} x_j + y_i r_j) on active rows, 0 otherwise
+    for the stored entry k = (i, j)   (cpg_osqp_grad_compute.c.jinja2:513-529)."""
+    Pi, Pp, Ps = P_pattern; Ai, Ap, As = A_pattern
+    n, m = Ps[0], As[0]
+    Prow = np.asarray(Pi); Pcol = np.repeat(np.arange(n), np.diff(Pp))
+    Arow = np.asarray(Ai); Acol = np.repeat(np.arange(n), np.diff(Ap))
+    x = np.atleast_2d(x); y = np.atleast_2d(y); dx = np.atleast_2d(dx)
+    B = x.shape[0]
+    dq = np.zeros((B, n)); dl = np.zeros((B, m)); du = np.zeros((B, m))
+    dP = np.zeros((B, len(Prow))); dA = np.zeros((B, len(Arow)))
+    for b in range(B):
+        P = sp.csc_matrix((Px[b], Pi, Pp), shape=Ps); A = sp.csc_matrix((Ax[b], Ai, Ap), shape=As)
+        q_, l_, u_, R = qp_backward(P, A, x[b], y[b], dx[b], n_refine)
+        r = R[0]
+        dq[b], dl[b], du[b] = q_[0], l_[0], u_[0]
+        dP[b] = -0.5 * (r[Prow] * x[b, Pcol] + x[b, Prow] * r[Pcol])
+        act = np.abs(y[b]) > ACTIVE_TOL
+        dA[b] = np.where(act[Arow], -(r[n + Arow] * x[b, Acol] + y[b, Arow] * r[Acol]), 0.0)
+    return dq, dl, du, dP, dA
+
+
+def param_gradient_mat(fam, dq, dl, du, dP, dA, names=None):
+    """dtheta including the matrix ids: sum over id in {q, l, u, P, A} of map_id' d(id)   (cvxpygen/writer.py:268-303)."""
+    cols = fam.param_columns(names)
+    out = param_gradient(fam, dq, dl, du, names)
+    for pid, d in (('P', dP), ('A', dA)):
+        M = fam.maps.get(pid)
+        if M is not None and M.nnz:
+            out += d @ M[:, cols].toarray()
+    return out

@@ -38,3 +38,28 @@ for name in ('mpc_12_4_10', 'mpc_6_3_10', 'nonneg_LS_3_2'):
         out['param_' + k] = v
     np.savez_compressed(os.path.join(HERE, f'grad_{name}.npz'), **out)
     print(name, 'active fraction', float((np.abs(sol['y']) > 1e-12).mean()), '|dq|max', float(np.abs(dq).max()))
+
+# ---- families with per-instance MATRIX parameters (rows a16 + f2): the reference's P / A branch of cpg_gradient
+# (cpg_P_to_K, cpg_A_to_K, cpg_ldl_numeric, cpg_osqp_gradient; cvxpygen/writer.py:240-263) incl. dP and dA
+from helpers import ltv_batch, canon_matrix_batches, matrix_oracle_solve     # noqa: E402
+from oracle.build_grad_ref import grad_ref_batch_mat, structural              # noqa: E402
+
+for name in ('mpc_ltv_6_3_10',):
+    fam = standard.STANDARD[name][0]()
+    Bm = 24
+    params = ltv_batch(fam, Bm, seed=78)
+    Px, Ax, (q, l, u) = canon_matrix_batches(fam, params, Bm)
+    so = os.path.join(os.path.dirname(os.path.dirname(HERE)), 'oracle', '_ref', f'libgrad_ref_{name}.so')
+    if not os.path.exists(so):
+        build(name, structural(fam.canon_matrix('P')), structural(fam.canon_matrix('A')))
+    sol = matrix_oracle_solve(fam, Px, Ax, q, l, u)
+    n, m = fam.n_var, fam.n_eq + fam.n_ineq
+    prim_idx = np.concatenate([v.indices for v in fam.variables])
+    dprim = np.random.default_rng(6).standard_normal((Bm, len(prim_idx)))
+    dx = np.zeros((Bm, n)); dx[:, prim_idx] = dprim
+    dq, dl, du, dP, dA = grad_ref_batch_mat(so, n, m, Px, Ax, sol['x'], sol['y'], dx)
+    out = dict(sol_x=sol['x'], sol_y=sol['y'], dprim=dprim, dq=dq, dl=dl, du=du, dP=dP, dA=dA, Px=Px, Ax=Ax)
+    for k, v in params.items():
+        out['param_' + k] = v
+    np.savez_compressed(os.path.join(HERE, f'grad_mat_{name}.npz'), **out)
+    print(name, 'active fraction', float((np.abs(sol['y']) > 1e-12).mean()), '|dA|max', float(np.abs(dA).max()))

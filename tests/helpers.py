@@ -122,14 +122,7 @@ def conic_batch(fam, B, seed):
 # ---------------------------------------------------------------------------------------------------------
 # families with per-instance MATRIX parameters
 def ltv_batch(fam, B, seed=3, spread=0.05):
-    """Parameter batch for families.mpc_ltv: perturbed dynamics, random diagonal stage costs, random initial state."""
-    rng = np.random.default_rng(seed)
-    A0, B0 = fam.param('A').default, fam.param('B').default
-    return {'A': A0[None, :] + spread * rng.standard_normal((B, A0.size)),
-            'B': B0[None, :] + spread * rng.standard_normal((B, B0.size)),
-            'qdiag': rng.uniform(0.5, 2.0, (B, fam.param('qdiag').size)),
-            'rdiag': rng.uniform(0.05, 0.5, (B, fam.param('rdiag').size)),
-            'x_init': rng.uniform(-1, 1, (B, fam.param('x_init').size))}
+    return families.mpc_ltv_batch(fam, B, seed=seed, spread=spread)
 
 
 def canon_matrix_batches(fam, params, B):

@@ -179,3 +179,100 @@ def test_gpu_matrix_parameters_large_batch_properties():
     rd = np.abs(Pdiag * r1.sol_x + q + ATy).max(axis=1)
     sc2 = np.maximum(np.maximum(np.abs(Pdiag * r1.sol_x).max(axis=1), np.abs(ATy).max(axis=1)), 1.0)
     assert (rd[ok] < 2e-3 * (1 + sc2[ok])).all()
+
+
+# ------------------------------------------------------------------------------------------------ backward pass (a16 + f2)
+import os
+from helpers import GOLDEN
+from oracle.grad_numpy import qp_backward_mat, param_gradient_mat
+
+
+def _relmax(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def test_numpy_matrix_backward_matches_reference_generated_c():
+    """numpy restatement vs the reference's generated C on per-instance matrices (cpg_P_to_K / cpg_A_to_K +
+    cpg_ldl_numeric + cpg_osqp_gradient), golden vectors from tests/golden/make_golden_grad.py."""
+    name = 'mpc_ltv_6_3_10'
+    g = np.load(os.path.join(GOLDEN, f'grad_mat_{name}.npz'))
+    fam = standard.STANDARD[name][0]()
+    prim_idx = np.concatenate([v.indices for v in fam.variables])
+    dx = np.zeros((g['dprim'].shape[0], fam.n_var)); dx[:, prim_idx] = g['dprim']
+    dq, dl, du, dP, dA = qp_backward_mat(fam.patterns['P'], fam.patterns['A'], g['Px'], g['Ax'], g['sol_x'], g['sol_y'], dx)
+    assert _relmax(dq, g['dq']) < 1e-9 and _relmax(dl + du, g['dl'] + g['du']) < 1e-9
+    assert _relmax(dP, g['dP']) < 1e-9 and _relmax(dA, g['dA']) < 1e-9
+
+
+@pytest.mark.skipif(not ref_available(), reason='oracle/_ref not built')
+def test_matrix_backward_matches_finite_differences():
+    """d/dtheta of c'x*(theta) w.r.t. entries of A, B, qdiag, rdiag, x_init of one instance (tight forward solves)."""
+    fam = families.mpc_ltv(4, 2, 5)
+    B = 2
+    params = ltv_batch(fam, B, seed=13)
+    kw = dict(eps_abs=1e-11, eps_rel=1e-11, max_iter=400000)
+
+    def solve(pr):
+        Px, Ax, (q, l, u) = canon_matrix_batches(fam, pr, B)
+        return matrix_oracle_solve(fam, Px, Ax, q, l, u, **kw), Px, Ax
+    sol, Px, Ax = solve(params)
+    cvec = np.random.default_rng(1).standard_normal(fam.n_var)
+    dx = np.tile(cvec, (B, 1))
+    dq, dl, du, dP, dA = qp_backward_mat(fam.patterns['P'], fam.patterns['A'], Px, Ax, sol['x'], sol['y'], dx)
+    names = ['A', 'B', 'qdiag', 'rdiag', 'x_init']
+    g = param_gradient_mat(fam, dq, dl, du, dP, dA, names)
+    cols = fam.param_columns(names)
+    h = 1e-6
+    rng = np.random.default_rng(4)
+    for k in rng.choice(len(cols), 12, replace=False):
+        nm = next(p.name for p in fam.params if p.col <= cols[k] < p.col + p.size)
+        off = cols[k] - fam.param(nm).col
+        fd = np.zeros(B)
+        for sgn in (+1, -1):
+            p2 = {a: v.copy() for a, v in params.items()}
+            p2[nm][:, off] += sgn * h
+            fd += sgn * (solve(p2)[0]['x'] @ cvec) / (2 * h)
+        assert np.allclose(g[:, k], fd, rtol=2e-3, atol=2e-5), (nm, off, g[:, k], fd)
+
+
+@pytest.mark.gpu
+def test_gpu_matrix_backward_matches_reference_golden():
+    name = 'mpc_ltv_6_3_10'
+    g = np.load(os.path.join(GOLDEN, f'grad_mat_{name}.npz'))
+    fam = standard.STANDARD[name][0]()
+    mod = standard.load(name)
+    names = standard.STANDARD[name][1]
+    params = {nm: g['param_' + nm] for nm in names}
+    res, dq, dl, du, dP, dA = mod.gradient_batch_mat(params, g['sol_x'], g['sol_y'], g['dprim'], return_canonical=True)
+    assert mod.launch_count() == 1
+    assert _relmax(dq, g['dq']) < 1e-5 and _relmax(dl + du, g['dl'] + g['du']) < 1e-5
+    assert _relmax(dP, g['dP']) < 1e-5 and _relmax(dA, g['dA']) < 1e-5
+    ref = param_gradient_mat(fam, g['dq'], g['dl'], g['du'], g['dP'], g['dA'], names)
+    got = np.concatenate([res[nm] for nm in names], axis=1)
+    assert _relmax(got, ref) < 1e-5
+    with pytest.raises(RuntimeError):          # the shared-matrix entry has no parameter rows to canonicalise P / A from
+        mod.gradient_batch(g['sol_y'], g['dprim'])
+
+
+@pytest.mark.gpu
+def test_gpu_matrix_forward_backward_torch_layer():
+    import torch
+    from cvxpygen_b200.torch_layer import BatchedQPLayer
+    name, B = 'mpc_ltv_12_4_10', 256
+    fam = standard.STANDARD[name][0]()
+    mod = standard.load(name)
+    params = ltv_batch(fam, B, seed=41)
+    th = torch.tensor(mod.pack_params(params), dtype=torch.float64, device='cuda', requires_grad=True)
+    prim = BatchedQPLayer(mod)(th)
+    wgt = torch.randn(prim.shape, dtype=torch.float64, device='cuda', generator=torch.Generator('cuda').manual_seed(0))
+    (prim * wgt).sum().backward()
+    nchk = 32
+    sub = {k: v[:nchk] for k, v in params.items()}
+    Px, Ax, (q, l, u) = canon_matrix_batches(fam, sub, nchk)
+    sol = matrix_oracle_solve(fam, Px, Ax, q, l, u)
+    prim_idx = np.concatenate([v.indices for v in fam.variables])
+    assert np.allclose(prim[:nchk].detach().cpu().numpy(), sol['x'][:, prim_idx], rtol=1e-6, atol=1e-9)
+    dx = np.zeros((nchk, fam.n_var)); dx[:, prim_idx] = wgt[:nchk].cpu().numpy()
+    dq, dl, du, dP, dA = qp_backward_mat(fam.patterns['P'], fam.patterns['A'], Px, Ax, sol['x'], sol['y'], dx)
+    ref = param_gradient_mat(fam, dq, dl, du, dP, dA, standard.STANDARD[name][1])
+    assert _relmax(th.grad[:nchk].cpu().numpy(), ref) < 1e-5
