@@ -134,8 +134,11 @@ static void solve_one(Job *j, OSQPWorkspace *w, int b) {
   if (j->Pb || j->Ab) {
     osqp_update_lin_cost(w, r->q0);
     if (m > 0) osqp_update_bounds(w, r->l0, r->u0);
-    osqp_update_P_A(w, j->Pb ? j->Pb + (size_t)b * j->nnzP : 0, 0, j->nnzP,
-                    j->Ab ? j->Ab + (size_t)b * j->nnzA : 0, 0, j->nnzA);
+    /* 0.6.2 spells "the other matrix is NULL" (osqp_update_data_mat of OSQP v1) as osqp_update_P / osqp_update_A:
+       each un-scales the data, overwrites its matrix, re-runs scale_data and re-factors (osqp.c:974-1156) */
+    if (j->Pb && j->Ab) osqp_update_P_A(w, j->Pb + (size_t)b * j->nnzP, 0, j->nnzP, j->Ab + (size_t)b * j->nnzA, 0, j->nnzA);
+    else if (j->Ab) osqp_update_A(w, j->Ab + (size_t)b * j->nnzA, 0, j->nnzA);
+    else osqp_update_P(w, j->Pb + (size_t)b * j->nnzP, 0, j->nnzP);
   }
   if (j->qb) osqp_update_lin_cost(w, j->qb + (size_t)b * n);
   if (j->lb && j->ub) osqp_update_bounds(w, j->lb + (size_t)b * m, j->ub + (size_t)b * m);

@@ -144,7 +144,8 @@ def matrix_oracle_solve(fam, Px, Ax, q, l, u, prefer_ref=True, **settings):
         from oracle.ref_osqp import RefOSQP
         r = RefOSQP(fam.canon_matrix('P'), fam.canon_data('q'), fam.canon_matrix('A'),
                     fam.canon_data('l'), fam.canon_data('u'), nthreads=min(8, os.cpu_count() or 1), **settings)
-        assert r._keep[0].nnz == Px.shape[1] and r._keep[1].nnz == Ax.shape[1], 'structural zeros were dropped'
+        assert (Px is None or r._keep[0].nnz == Px.shape[1]) and (Ax is None or r._keep[1].nnz == Ax.shape[1]), \
+            'structural zeros were dropped'
         return r.solve_batch_mat(Px=Px, Ax=Ax, q=q, l=l, u=u)
     from oracle.admm_numpy import solve_matrix_batch
     from cvxpygen_b200.offline.qp_setup import unscale_roundtrip
@@ -152,6 +153,7 @@ def matrix_oracle_solve(fam, Px, Ax, q, l, u, prefer_ref=True, **settings):
     Pi, Pp, Ps = fam.patterns['P']; Ai, Ap, As = fam.patterns['A']
     sc = ruiz_equilibrate(fam.canon_matrix('P'), fam.canon_matrix('A'), fam.canon_data('q'), int(settings.get('scaling', 10)))
     q_un = unscale_roundtrip(sc, int(settings.get('scaling', 10)))[2]
-    Pl = [sp.csc_matrix((Px[i], Pi, Pp), shape=Ps) for i in range(Px.shape[0])]
-    Al = [sp.csc_matrix((Ax[i], Ai, Ap), shape=As) for i in range(Ax.shape[0])]
+    B = (Px if Px is not None else Ax).shape[0]
+    Pl = [sp.csc_matrix((Px[i], Pi, Pp), shape=Ps) if Px is not None else fam.canon_matrix('P') for i in range(B)]
+    Al = [sp.csc_matrix((Ax[i], Ai, Ap), shape=As) if Ax is not None else fam.canon_matrix('A') for i in range(B)]
     return solve_matrix_batch(Pl, Al, q_un, fam.canon_data('l'), fam.canon_data('u'), q=q, l=l, u=u, **settings)

@@ -141,6 +141,26 @@ def test_gpu_matrix_parameters_vs_reference(name, B):
 
 
 @pytest.mark.gpu
+def test_gpu_sparse_matrix_parameter_only_A_batched():
+    """README example (examples/main.py:16-26) with its sparse parameter A per instance: only A is outdated, so the
+    reference calls osqp_update_data_mat with P = NULL (cvxpygen/solvers/osqp.py:28-31) and P keeps its unscale/re-scale
+    round-trip values -- the kernel's base table carries exactly those."""
+    name, B = 'nonneg_LS_3_2_A', 400
+    fam = standard.STANDARD[name][0]()
+    rng = np.random.default_rng(8)
+    params = {'A': fam.param('A').default[None, :] + 0.5 * rng.standard_normal((B, 3)),
+              'b': fam.param('b').default[None, :] + 0.5 * rng.standard_normal((B, 3))}
+    res = standard.load(name, device=0).solve_batch(params, return_canonical=True)
+    _, Ax, (q, l, u) = canon_matrix_batches(fam, params, B)
+    ora = matrix_oracle_solve(fam, None, Ax, q, l, u)
+    assert np.array_equal(res.cpg_info.status, ora['status']) and np.array_equal(res.cpg_info.iter, ora['iter'])
+    ok = np.isin(ora['status'], [1, 2, -2])
+    assert ok.mean() > 0.9
+    assert np.abs(res.sol_x[ok] - ora['x'][ok]).max() < 1e-7 * max(1.0, np.abs(ora['x'][ok]).max())
+    assert np.abs(res.sol_y[ok] - ora['y'][ok]).max() < 1e-7 * max(1.0, np.abs(ora['y'][ok]).max())
+
+
+@pytest.mark.gpu
 def test_gpu_matrix_parameters_reduce_to_shared_family():
     """With every instance carrying the DEFAULT matrices the matrix-parameter kernel must reproduce the shared-matrix
     kernels' results on the same x_init (same algorithm, per-instance factor instead of the family's)."""

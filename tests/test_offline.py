@@ -95,10 +95,11 @@ def test_minimum_degree_and_levels_on_arrow_matrix():
     assert sum(len(s) for s in struct_) == n - 1
 
 
-def test_rejects_matrix_parameter_as_batched():
+def test_matrix_parameter_as_batched_selects_the_matrix_path():
     fam = families.nonneg_ls(3, 2)
-    with pytest.raises(ValueError):
-        setup_qp_family(fam, ['A'])
+    st = setup_qp_family(fam, ['A'])                 # row f2: per-instance matrix parameters are generated
+    assert st.mat_params == ['A'] and len(st.mat_blob) > 0
+    assert len(setup_qp_family(fam, ['b']).mat_blob) == 0
     with pytest.raises(AttributeError):
         setup_qp_family(fam, ['nope'])
 
