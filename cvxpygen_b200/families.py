@@ -13,6 +13,7 @@ inequalities) so that dual signs match the reference's.
 Families:
   nonneg_ls(m, n)      README example (reference: examples/main.py:16-26)
   mpc(nx, nu, N)       MPC QP (reference: tests/test_E2E_QP.py:44-73,127-146; BASELINE config 2)
+  mpc_reference(H)     the reference's test MPC with all six parameters (diag / sparse matrix parameters)
   mpc_ltv(nx, nu, N)   the same with the dynamics and stage costs as (batchable) matrix parameters
 """
 from typing import Optional
@@ -207,6 +208,97 @@ def mpc_ltv(nx=12, nu=4, N=10, Ad=None, Bd=None, qdiag=None, rdiag=None, umax=1.
     Apat = (tag.indices.astype(np.int32), tag.indptr.astype(np.int32), (m, n))
     return CanonFamily(name or f'mpc_ltv_{nx}_{nu}_{N}', 'quadratic', n, n_eq, n_ineq, params, maps,
                        {'P': _csc_pattern(Pu), 'A': Apat}, variables, duals)
+
+
+def mpc_reference(H=10, name=None) -> CanonFamily:
+    """The reference's own test MPC (tests/test_E2E_QP.py:44-73, data :127-146) with ALL its parameters: n = 6 states,
+    m = 3 inputs, horizon H;  ``Psqrt``, ``Qsqrt``, ``Rsqrt`` diagonal parameters (stored: the diagonal), ``A`` and ``B``
+    SPARSE parameters (stored: the nonzeros in column-major order, reference README.md:140-143), ``x_init``.
+
+        min  |Psqrt X[:,H-1]|^2 + |Qsqrt X[:,:H]|^2 + |Rsqrt U|^2 + 1
+        s.t. X[:,1:] = A X[:,:H] + B U,  |U| <= 1,  X[:,0] = x_init
+
+    The cost factors multiply variables inside sum_squares, so -- as in cvxpy's DPP canonicalisation -- they enter through
+    auxiliary variables: canonical x = [X(:) ; U(:) ; TQ = Qsqrt X[:,:H] ; TP = Psqrt X[:,H-1] ; TR = Rsqrt U], P = 2 I on
+    the auxiliaries (constant), every matrix parameter in the constraint matrix A; objective offset d = 1.
+    rows: [x_0 = x_init (d2) ; dynamics (d0) ; TQ, TP, TR definitions ; -1 <= U <= 1 (d1)]."""
+    n, m = 6, 3
+    nzA = sorted([(i, i) for i in range(n)] + [(i, 3 + i) for i in range(n // 2)], key=lambda rc: (rc[1], rc[0]))
+    nzB = sorted([(3 + i, i) for i in range(n // 2)], key=lambda rc: (rc[1], rc[0]))
+    td = 0.1
+    A0 = np.eye(6); A0[:3, 3:] += td * np.eye(3)
+    B0 = np.zeros((6, 3)); B0[3:, :] = td * np.eye(3)
+    params = _layout_params([('Psqrt', (n, n), np.ones(n)), ('Qsqrt', (n, n), np.ones(n)),
+                             ('Rsqrt', (m, m), np.sqrt(0.1) * np.ones(m)),
+                             ('A', (n, n), [A0[r, c] for r, c in nzA]), ('B', (n, m), [B0[r, c] for r, c in nzB]),
+                             ('x_init', (n,), np.zeros(n))])
+    col = {p.name: p.col for p in params}
+    n_theta = params[-1].col + params[-1].size + 1
+    nX, nU = n * (H + 1), m * H
+    oX, oU, oTQ, oTP, oTR = 0, nX, nX + nU, nX + nU + n * H, nX + nU + n * H + n
+    nv = oTR + m * H
+    r0, rD, rTQ, rTP, rTR, rB = 0, n, n + n * H, n + 2 * n * H, 2 * n + 2 * n * H, 2 * n + 2 * n * H + m * H
+    n_eq, n_ineq = rB, m * H
+    mt = n_eq + n_ineq
+    ent = []                                         # (row, col, ('c', value) | ('p', theta column, coefficient))
+    for i in range(n):
+        ent.append((r0 + i, oX + i, ('c', 1.0)))
+    for k in range(H):
+        for i in range(n):
+            ent.append((rD + k * n + i, oX + (k + 1) * n + i, ('c', 1.0)))
+            ent.append((rTQ + k * n + i, oTQ + k * n + i, ('c', 1.0)))
+            ent.append((rTQ + k * n + i, oX + k * n + i, ('p', col['Qsqrt'] + i, -1.0)))
+        for e, (r, c) in enumerate(nzA):
+            ent.append((rD + k * n + r, oX + k * n + c, ('p', col['A'] + e, -1.0)))
+        for e, (r, c) in enumerate(nzB):
+            ent.append((rD + k * n + r, oU + k * m + c, ('p', col['B'] + e, -1.0)))
+        for j in range(m):
+            ent.append((rTR + k * m + j, oTR + k * m + j, ('c', 1.0)))
+            ent.append((rTR + k * m + j, oU + k * m + j, ('p', col['Rsqrt'] + j, -1.0)))
+            ent.append((rB + k * m + j, oU + k * m + j, ('c', 1.0)))
+    for i in range(n):
+        ent.append((rTP + i, oTP + i, ('c', 1.0)))
+        ent.append((rTP + i, oX + (H - 1) * n + i, ('p', col['Psqrt'] + i, -1.0)))
+    ent.sort(key=lambda e: (e[1], e[0]))
+    Ar = np.array([e[0] for e in ent]); Ac = np.array([e[1] for e in ent])
+    indptr = np.zeros(nv + 1, dtype=np.int64)
+    np.add.at(indptr, Ac + 1, 1); indptr = np.cumsum(indptr).astype(np.int32)
+    mbA = _MapBuilder(len(ent), n_theta)
+    for k, e in enumerate(ent):
+        if e[2][0] == 'c':
+            mbA.const(k, e[2][1])
+        else:
+            mbA.add(k, e[2][1], e[2][2])
+    naux = nv - oTQ
+    Pu = sp.csc_matrix((2.0 * np.ones(naux), (oTQ + np.arange(naux), oTQ + np.arange(naux))), shape=(nv, nv))
+    mbP = _MapBuilder(naux, n_theta)
+    for k in range(naux):
+        mbP.const(k, 2.0)
+    maps = {'A': mbA.csr(), 'P': mbP.csr(), 'q': sp.csr_matrix((nv, n_theta))}
+    md = _MapBuilder(1, n_theta); md.const(0, 1.0); maps['d'] = md.csr()
+    ml, mu = _MapBuilder(mt, n_theta), _MapBuilder(mt, n_theta)
+    for i in range(n):
+        ml.add(r0 + i, col['x_init'] + i, 1.0); mu.add(r0 + i, col['x_init'] + i, 1.0)
+    for i in range(n_ineq):
+        ml.const(rB + i, -1.0); mu.const(rB + i, 1.0)
+    maps['l'], maps['u'] = ml.csr(), mu.csr()
+    variables = [UserVar('U', (m, H), oU + np.arange(nU)), UserVar('X', (n, H + 1), oX + np.arange(nX))]
+    duals = [UserDual('d0', 'y', (n, H), rD + np.arange(n * H)), UserDual('d1', 'y', (m, H), rB + np.arange(m * H)),
+             UserDual('d2', 'y', (n,), r0 + np.arange(n))]
+    return CanonFamily(name or f'mpc_ref_6_3_{H}', 'quadratic', nv, n_eq, n_ineq, params, maps,
+                       {'P': _csc_pattern(Pu), 'A': (Ar.astype(np.int32), indptr, (mt, nv))}, variables, duals)
+
+
+def mpc_reference_batch(fam: CanonFamily, B: int, seed: int = 0, spread: float = 0.05):
+    """Per-instance values of all six parameters: the reference's data (tests/test_E2E_QP.py:127-146: x_init = -2 + 4 rand)
+    with the stored entries of A, B and the cost factors perturbed entry-wise (relative N(0, spread^2))."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for nm in ('Psqrt', 'Qsqrt', 'Rsqrt', 'A', 'B'):
+        d = fam.param(nm).default
+        out[nm] = d[None, :] * (1.0 + spread * rng.standard_normal((B, d.size)))
+    out['x_init'] = -2.0 + 4.0 * rng.random((B, 6))
+    return out
 
 
 def mpc_ltv_batch(fam: CanonFamily, B: int, seed: int = 3, spread: float = 0.05):

@@ -21,6 +21,7 @@ STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
     # f2: the MPC family with its matrices as per-instance parameters (dynamics A, B and diagonal stage costs)
     'mpc_ltv_6_3_10': (lambda: families.mpc_ltv(6, 3, 10), ['A', 'B', 'qdiag', 'rdiag', 'x_init']),
     'mpc_ltv_12_4_10': (lambda: families.mpc_ltv(12, 4, 10), ['A', 'B', 'qdiag', 'rdiag', 'x_init']),
+    'mpc_ref_6_3_10': (lambda: families.mpc_reference(10), ['Psqrt', 'Qsqrt', 'Rsqrt', 'A', 'B', 'x_init']),   # the reference's test MPC, all parameters
     'nonneg_LS_3_2_A': (lambda: families.nonneg_ls(3, 2, name='nonneg_LS_3_2_A'), ['A', 'b']),   # README example, A per instance
     'portfolio_socp_100_10': (lambda: families.portfolio_socp(100, 10), ['a', 'w_prev']),   # BASELINE config 3 (IPM-CUDA)
     # generic conic families (every vector batched): three cones + equalities, and a pure LP; exit flags 0 / 1 / 2
@@ -30,7 +31,7 @@ STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
 
 # families solved by the ADMM (QP) backend / by the interior-point (SOCP) backend
 SOCP_NAMES: List[str] = [n for n in STANDARD if '_socp_' in n]
-MATPAR_NAMES: List[str] = ['mpc_ltv_6_3_10', 'mpc_ltv_12_4_10', 'nonneg_LS_3_2_A']
+MATPAR_NAMES: List[str] = ['mpc_ltv_6_3_10', 'mpc_ltv_12_4_10', 'mpc_ref_6_3_10', 'nonneg_LS_3_2_A']
 QP_NAMES: List[str] = [n for n in STANDARD if n not in SOCP_NAMES and n not in MATPAR_NAMES]
 
 

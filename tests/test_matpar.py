@@ -160,6 +160,84 @@ def test_gpu_sparse_matrix_parameter_only_A_batched():
     assert np.abs(res.sol_y[ok] - ora['y'][ok]).max() < 1e-7 * max(1.0, np.abs(ora['y'][ok]).max())
 
 
+def _reference_mpc_case(B, seed):
+    fam = standard.STANDARD['mpc_ref_6_3_10'][0]()
+    params = families.mpc_reference_batch(fam, B, seed=seed)
+    _, Ax, (q, l, u) = canon_matrix_batches(fam, params, B)
+    return fam, params, Ax, q, l, u
+
+
+@pytest.mark.skipif(not ref_available(), reason='oracle/_ref not built')
+def test_reference_test_mpc_all_parameters_oracles_agree():
+    """The reference's own test MPC (tests/test_E2E_QP.py:44-73) with its six parameters per instance: diagonal cost
+    factors, sparse A and B (stored entries in column-major order), x_init.  P is constant -> only-A branch."""
+    fam, params, Ax, q, l, u = _reference_mpc_case(5, seed=0)
+    assert fam.n_var == 192 and fam.param('A').size == 9 and fam.param('B').size == 3 and fam.param('Qsqrt').size == 6
+    ref = matrix_oracle_solve(fam, None, Ax, q, l, u)
+    npy = matrix_oracle_solve(fam, None, Ax, q, l, u, prefer_ref=False)
+    assert np.array_equal(ref['iter'], npy['iter']) and (ref['status'] == 1).all()
+    assert rel_err(npy['x'], ref['x']).max() < 1e-8
+    # the canonical form really is the reference's problem: dynamics hold and the objective is the user-level one (minus d = 1)
+    tight = matrix_oracle_solve(fam, None, Ax, q, l, u, eps_abs=1e-9, eps_rel=1e-9)
+    X = tight['x'][:, :66].reshape(5, 11, 6); U = tight['x'][:, 66:96].reshape(5, 10, 3)
+    obj = ((params['Psqrt'] * X[:, 9]) ** 2).sum(1) + ((params['Qsqrt'][:, None, :] * X[:, :10]) ** 2).sum((1, 2)) \
+        + ((params['Rsqrt'][:, None, :] * U) ** 2).sum((1, 2))
+    assert np.allclose(obj, tight['obj'], rtol=1e-6)
+    assert np.abs(X[:, 0] - params['x_init']).max() < 1e-7 and np.abs(U).max() <= 1 + 1e-7
+
+
+@pytest.mark.gpu
+def test_gpu_reference_test_mpc_all_parameters():
+    B = 1000
+    fam, params, Ax, q, l, u = _reference_mpc_case(B, seed=1)
+    res = standard.load('mpc_ref_6_3_10', device=0).solve_batch(params, return_canonical=True)
+    ora = matrix_oracle_solve(fam, None, Ax, q, l, u)
+    assert np.array_equal(res.cpg_info.status, ora['status']) and np.array_equal(res.cpg_info.iter, ora['iter'])
+    assert (ora['status'] == 1).mean() > 0.99
+    ok = ora['status'] == 1
+    assert rel_err(res.sol_x[ok], ora['x'][ok]).max() < 1e-7 and rel_err(res.sol_y[ok], ora['y'][ok]).max() < 1e-7
+    assert np.allclose(res.cpg_info.obj_val[ok], ora['obj'][ok] + 1.0, rtol=1e-7)      # cpg_retrieve_info adds d = 1 (utils.py:980)
+    assert np.abs(res.cpg_prim['X'][:, :, 0] - params['x_init']).max() < 2e-2
+
+
+@pytest.mark.gpu
+def test_gpu_matrix_parameters_warm_start():
+    """x0 / y0 (osqp_warm_start, osqp.c:929-953) on the matrix-parameter path: starting from the solution stops at the first check."""
+    B = 300
+    fam, params, Ax, q, l, u = _reference_mpc_case(B, seed=2)
+    mod = standard.load('mpc_ref_6_3_10', device=0)
+    cold = mod.solve_batch(params, return_canonical=True)
+    warm = mod.solve_batch(params, x0=cold.sol_x, y0=cold.sol_y, return_canonical=True)
+    assert (warm.cpg_info.iter == 25).all() and (warm.cpg_info.status == 1).all()
+    assert rel_err(warm.sol_x, cold.sol_x).max() < 1e-2
+
+
+@pytest.mark.gpu
+def test_gpu_shared_parameter_update_on_matrix_family():
+    """A family generated with only A, x_init batched: B and the cost factors are SHARED; changing them = host re-setup +
+    cpg_b200_load_constants_all + cpg_b200_load_mat_constants, then the batch is solved with the new shared values."""
+    import tempfile
+    from cvxpygen_b200 import cpg, runtime
+    fam = families.mpc_reference(10)
+    with tempfile.TemporaryDirectory() as td:
+        cpg.generate_code(fam, code_dir=td, solver='ADMM-CUDA', batch_params=['A', 'x_init'])
+        mod = runtime.load(td, 0)
+        B = 64
+        full = families.mpc_reference_batch(fam, B, seed=5)
+        newB = fam.param('B').default * 1.3
+        newR = fam.param('Rsqrt').default * 0.7
+        mod.update_shared_params({'B': newB, 'Rsqrt': newR})
+        res = mod.solve_batch({'A': full['A'], 'x_init': full['x_init']}, return_canonical=True)
+        # reference: the same family object with the new defaults, all instances sharing B / Rsqrt
+        fam2 = families.mpc_reference(10)
+        fam2.param('B').default[:] = newB; fam2.param('Rsqrt').default[:] = newR
+        p2 = {'A': full['A'], 'x_init': full['x_init']}
+        _, Ax, (q, l, u) = canon_matrix_batches(fam2, p2, B)
+        ora = matrix_oracle_solve(fam2, None, Ax, q, l, u)
+        assert np.array_equal(res.cpg_info.iter, ora['iter']) and np.array_equal(res.cpg_info.status, ora['status'])
+        assert rel_err(res.sol_x, ora['x']).max() < 1e-7
+
+
 @pytest.mark.gpu
 def test_gpu_matrix_parameters_reduce_to_shared_family():
     """With every instance carrying the DEFAULT matrices the matrix-parameter kernel must reproduce the shared-matrix
