@@ -34,6 +34,7 @@ WORKLOAD = 'MPC QP (n_x=12,n_u=4,N=10) batch=%d per GPU, ADMM-CUDA backend, OSQP
 SOCP_FAMILY = 'portfolio_socp_100_10'
 SOCP_WORKLOAD = 'portfolio SOCP (n=100 assets, 10 factors; 512 vars, 111 eq, 715 cone rows) batch=%d per GPU, IPM-CUDA backend, ECOS default settings (tol 1e-8)'
 SOCP_BYTES_PER_INSTANCE = 200 * 8 + (210 + 112) * 8 + 40        # a, w_prev in; w, delta_w, f + duals out; info (~4.2 KB)
+SOCP_TRAFFIC_BYTES_PER_INSTANCE = 2164                           # ncu at batch 1184: (2.365 MB + 0.197 MB) / 1184
 # algorithmic I/O and work per instance (SURVEY.md section 8d / DESIGN.md): 96 B in + 2.75 KB out + 40 B info
 BYTES_PER_INSTANCE = 12 * 8 + (172 + 172) * 8 + 40
 FLOP_PER_INSTANCE = 0.5e6
@@ -414,7 +415,10 @@ def main_socp(args, rank, world, local_rank, W, K, cores):
                     'd2h_bytes_per_step': B * ((d.n_prim + d.n_dual) * 8 + 32), 'steps': e2e_steps,
                     'note': 'pinned host buffers through cpg_socp_solve_batch_host: H2D, kernel, D2H; host clock'},
             'gpu_launches': launches_per_step * K, 'clocks': sampler.summary(),
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': B * SOCP_TRAFFIC_BYTES_PER_INSTANCE / 1e9,
+                         'traffic_unit': 'GB per launch, scaled from the ncu capture at batch 1184 (profiles/r1_ipm_v7_ncu_summary.md: 2.37 MB read + '
+                                         '0.20 MB written -- the result rows of so small a batch stay in L2; at batch 50000 they are written back: + 2.6 KB/instance)',
                          'peak_source': peak_src, 'algorithmic_bytes_per_instance': SOCP_BYTES_PER_INSTANCE,
                          'note': 'one CTA per instance with the whole interior-point state (iterate, scalings, numeric LDL\' factor, work '
                                  'vectors: ~215 KB) in shared memory; HBM carries parameters in / solutions out only; the binding resource '
@@ -439,6 +443,7 @@ LTV_FAMILY = 'mpc_ltv_12_4_10'
 LTV_WORKLOAD = ('MPC QP (n_x=12,n_u=4,N=10) with per-instance dynamics A, B and stage costs (220-entry parameter row; dense-pattern '
                 'A: nnz 2092) batch=%d per GPU, ADMM-CUDA matrix-parameter kernel, OSQP default settings')
 LTV_BYTES_PER_INSTANCE = 220 * 8 + (172 + 172) * 8 + 40
+LTV_TRAFFIC_BYTES_PER_INSTANCE = 3001      # ncu: (38.08 MB + 21.94 MB) / 20000 instances
 
 
 def ltv_canonical(B, seed):
@@ -552,7 +557,10 @@ def main_ltv(args, rank, world, local_rank, W, K, cores):
                     'd2h_bytes_per_step': B * ((d.n_prim + d.n_dual) * 8 + 32), 'steps': e2e_steps,
                     'note': 'pinned host buffers through cpg_solve_batch_host: H2D of the parameter rows, kernel (zero-copy result rows), D2H of the info arrays; host clock'},
             'gpu_launches': launches_per_step * K, 'clocks': sampler.summary(),
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': B * LTV_TRAFFIC_BYTES_PER_INSTANCE / 1e9,
+                         'traffic_unit': 'GB per launch (ncu dram__bytes_read+write at batch 20000, profiles/r1_matpar_v1_ncu_summary.md: '
+                                         '38.1 MB read + 21.9 MB written; part of the result rows is still in the 126 MB L2 when the kernel ends)',
                          'peak_source': peak_src, 'algorithmic_bytes_per_instance': LTV_BYTES_PER_INSTANCE,
                          'note': 'one warp per instance: equilibration, KKT assembly, numeric LDL\' and the ADMM loop all on chip '
                                  '(factor in shared memory, tables in L2); HBM carries the parameter row in and the solution rows out; '

@@ -1,3 +1,6 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_matpar.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/gpu_tests_matpar.log
-timeout 300 python tools/time_matpar.py mpc_ltv_6_3_10 20000 2>&1 | tail -1
+for N in 8 4; do
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_n$N.err | tail -1 | tee gpurun_out/bench_mpc_n$N.json
+done
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 8 --steps 3 --warmup 3 --no-cpu-baseline --workload portfolio_socp 2>>gpurun_out/bench_n8.err | tail -1 | tee gpurun_out/bench_socp_n8.json
+tail -3 gpurun_out/bench_n8.err
