@@ -156,19 +156,23 @@ __device__ __forceinline__ void tail_factor(const TailView& tv, double* S, int l
   }
 }
 
-__device__ __forceinline__ double slot_tile_acc(const int* h, const uint16_t* U16, const double* S,
+// entries of a tile: one 32-bit word per (k, lane) = slot | position << 16, lane-interleaved (offline/blob.py:pack_tail_blob)
+__device__ __forceinline__ double slot_tile_acc(const int* h, const int* __restrict__ I32, const double* S,
                                                 const double* w, int lane) {
-  const uint16_t* sl = U16 + h[0] + lane;
-  const uint16_t* c = U16 + h[1] + lane;
+  const unsigned* wd = reinterpret_cast<const unsigned*>(I32) + h[0] + lane;
   const int K = h[2];
-  double a0 = 0.0, a1 = 0.0;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   int k = 0;
-  for (; k + 1 < K; k += 2) {
-    a0 = fma(S[sl[k * LANES]], w[c[k * LANES]], a0);
-    a1 = fma(S[sl[(k + 1) * LANES]], w[c[(k + 1) * LANES]], a1);
+  for (; k + 3 < K; k += 4) {
+    const unsigned e0 = __ldg(wd + k * LANES), e1 = __ldg(wd + (k + 1) * LANES);
+    const unsigned e2 = __ldg(wd + (k + 2) * LANES), e3 = __ldg(wd + (k + 3) * LANES);
+    a0 = fma(S[e0 & 0xffffu], w[e0 >> 16], a0);
+    a1 = fma(S[e1 & 0xffffu], w[e1 >> 16], a1);
+    a2 = fma(S[e2 & 0xffffu], w[e2 >> 16], a2);
+    a3 = fma(S[e3 & 0xffffu], w[e3 >> 16], a3);
   }
-  if (k < K) a0 = fma(S[sl[k * LANES]], w[c[k * LANES]], a0);
-  double acc = a0 + a1;
+  for (; k < K; ++k) { const unsigned e0 = __ldg(wd + k * LANES); a0 = fma(S[e0 & 0xffffu], w[e0 >> 16], a0); }
+  double acc = (a0 + a1) + (a2 + a3);
   for (int o = 16; o >= h[3]; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
   return acc;
 }
@@ -203,6 +207,46 @@ __device__ __forceinline__ double group_sweep(double val, const uint16_t* __rest
   return val;
 }
 
+// The same sweep when the group's couplings sit in a packed strict-lower triangle Sg[tri(j) + t] (j = row being swept,
+// t > j its dependents; offline/refactor.py:tri_offset): no index table -- an ascending sweep reads consecutive addresses
+// across the lanes, a descending one reads column t of the triangle at a per-lane base.
+template <bool ASCENDING>
+__device__ __forceinline__ double group_sweep_dense(double val, const double* __restrict__ Sg, const int g, const int lane) {
+  // tri(j) = j (g - 1) - j (j - 1) / 2 - (j + 1);   coupling (t, j), t > j, at tri(j) + t;   tri(j + 1) - tri(j) = g - 2 - j
+  const int nblk = (g + 7) >> 3;
+  if (ASCENDING) {
+    const bool in = lane < g;
+    const double* p = Sg - 1 + lane;            // tri(0) + lane
+    int step = g - 2;                           // tri(j + 1) - tri(j) at j = 0
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int lb = lane - blk * 8;            // dep_u  <=>  lane > blk * 8 + u
+      double cf[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        cf[u] = (in && lb > u) ? *p : 0.0;
+        p += step; --step;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (blk * 8 + u < g) val = fma(-cf[u], __shfl_sync(FULL, val, blk * 8 + u), val);
+    }
+  } else {
+    const int tl = lane < g ? lane : g - 1;
+    const double* p = Sg + (tl * (g - 1) - (tl * (tl - 1)) / 2 - (tl + 1)) + (g - 1);     // tri(lane) + j at j = g - 1
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int lb = g - 1 - blk * 8 - lane;    // dep_u  <=>  lane < g - 1 - blk * 8 - u
+      double cf[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cf[u] = (lb > u) ? p[-u] : 0.0;
+      p -= 8;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (blk * 8 + u < g) val = fma(-cf[u], __shfl_sync(FULL, val, g - 1 - blk * 8 - u), val);
+    }
+  }
+  return val;
+}
+
 // K x = b with the per-instance factor: grouped level-scheduled L solve, D^{-1}, L' solve (QDLDL_solve, qdldl.c:269-281)
 __device__ __forceinline__ void tail_solve(const TailView& tv, const double* S, double* w, int lane) {
   const int* T = tv.I32 + tv.H->i_tiles;
@@ -213,12 +257,14 @@ __device__ __forceinline__ void tail_solve(const TailView& tv, const double* S, 
       __syncwarp();
     }
     const int* h = T + 8 * t;
-    const double acc = slot_tile_acc(h, tv.U16, S, w, lane);
+    const double acc = slot_tile_acc(h, tv.I32, S, w, lane);
     const int nrows = h[4];
     const int row = tv.U16[h[5] + lane];
     double val = w[row] - acc;
-    if (h[7]) val = (t < nf) ? group_sweep<true>(val, tv.U16 + h[6], S, nrows, lane)
-                             : group_sweep<false>(val, tv.U16 + h[6], S, nrows, lane);
+    if (h[7] == 2) val = (t < nf) ? group_sweep_dense<true>(val, S + h[6], nrows, lane)
+                                  : group_sweep_dense<false>(val, S + h[6], nrows, lane);
+    else if (h[7]) val = (t < nf) ? group_sweep<true>(val, tv.U16 + h[6], S, nrows, lane)
+                                  : group_sweep<false>(val, tv.U16 + h[6], S, nrows, lane);
     __syncwarp();
     if (lane < nrows) w[row] = val;
     __syncwarp();

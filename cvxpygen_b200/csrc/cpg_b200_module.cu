@@ -48,7 +48,8 @@ struct Fam {
 #if CPG_FAM_MATPAR
   static constexpr int MAT_WARPS = CPG_FAM_MAT_WARPS;       // matrix-parameter kernel: warps per CTA
   static constexpr int MAT_A_STRIDE = CPG_FAM_MAT_A_STRIDE, MAT_P_STRIDE = CPG_FAM_MAT_P_STRIDE;
-  static constexpr int MAT_STRIDE = CPG_FAM_MAT_STRIDE;     // doubles of shared memory per warp: w | S | Pv | D Dinv E Einv
+  static constexpr int MAT_STRIDE = CPG_FAM_MAT_STRIDE;     // doubles of shared memory per warp: w | S | Pv
+  static constexpr int MAT_G_STRIDE = CPG_FAM_MAT_G_STRIDE; // doubles of global scratch per warp: Av | D Dinv E Einv
 #endif
 };
 #if CPG_FAM_MATPAR
@@ -238,7 +239,7 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
   if (!g.d_mblob) CK(cudaMalloc(&g.d_mblob, CPG_B200_FN(cpg_mblob_nbytes)));
   CK(cudaMemcpy(g.d_mblob, CPG_B200_FN(cpg_mblob_words), CPG_B200_FN(cpg_mblob_nbytes), cudaMemcpyHostToDevice));
   CK(cudaFuncSetAttribute(cpgb200::admm_matpar_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAT_SMEM_BYTES));
-  if (!g.d_mat_scratch) CK(cudaMalloc(&g.d_mat_scratch, sizeof(double) * (size_t)g.n_sm * (Fam::MAT_WARPS > Fam::GRAD_WARPS ? Fam::MAT_WARPS : Fam::GRAD_WARPS) * Fam::MAT_A_STRIDE));
+  if (!g.d_mat_scratch) CK(cudaMalloc(&g.d_mat_scratch, sizeof(double) * (size_t)g.n_sm * (Fam::MAT_WARPS > Fam::GRAD_WARPS ? Fam::MAT_WARPS : Fam::GRAD_WARPS) * Fam::MAT_G_STRIDE));
 #endif
   if (!g.d_counter) CK(cudaMalloc(&g.d_counter, sizeof(unsigned int)));
   if (!g.d_tail_count) CK(cudaMalloc(&g.d_tail_count, sizeof(int)));

@@ -86,7 +86,7 @@ qp_grad_kernel(const uint8_t* __restrict__ gblob_g, const uint8_t* __restrict__ 
   if constexpr (MATPAR) {
     mc.mv = make_mat_view(io.mblob);
     mc.Pv = xs + ((N + 1) & ~1);
-    mc.Av = io.a_scratch + ((size_t)blockIdx.x * Fam::GRAD_WARPS + warp) * Fam::MAT_A_STRIDE;
+    mc.Av = io.a_scratch + ((size_t)blockIdx.x * Fam::GRAD_WARPS + warp) * Fam::MAT_G_STRIDE;
   }
 #endif
   auto dotA = [&](int k) -> double {

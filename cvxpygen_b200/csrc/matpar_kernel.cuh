@@ -126,10 +126,10 @@ __device__ void matpar_prepare(MatCtx& mc, const double* __restrict__ th, double
 
 // One persistent CTA per SM; every warp pulls instance numbers from the global counter.  Nothing is staged: the family's
 // compact blob, the refactorisation tables and the matrix tables are read from global memory (L2-resident, shared by all
-// warps) so that shared memory is left to the per-instance state that every ADMM iteration touches: w | S | Pv | D Dinv E
-// Einv.  The scaled entries of A -- read by the equilibration, the assembly and the residual products every 25 iterations
-// only -- live in a per-warp slice of a global scratch buffer (a few MB in total: L2-resident), which is what lets five
-// instead of three warps share an SM at MPC-12/4/10 with dense dynamics.
+// warps) so that shared memory is left to the per-instance state that every ADMM iteration touches: w | S | Pv.  The scaled
+// entries of A and the scalings D, 1/D, E, 1/E -- read by the equilibration, the assembly, the residual checks every 25
+// iterations and the epilogue only -- live in a per-warp slice of a global scratch buffer (a few MB in total:
+// L2-resident), which is what lets five instead of three warps share an SM at MPC-12/4/10 with dense dynamics.
 template <class Fam>
 __global__ void __launch_bounds__(Fam::MAT_WARPS * 32, 1)
 admm_matpar_kernel(const uint8_t* __restrict__ cblob_g, const uint8_t* __restrict__ tail_blob_g,
@@ -148,10 +148,10 @@ admm_matpar_kernel(const uint8_t* __restrict__ cblob_g, const uint8_t* __restric
   ta.S = wbase + Fam::W_STRIDE;
   ta.state = nullptr;
   ta.mc = &mc;
-  mc.Av = a_scratch + ((size_t)blockIdx.x * Fam::MAT_WARPS + warp) * Fam::MAT_A_STRIDE;
+  mc.Av = a_scratch + ((size_t)blockIdx.x * Fam::MAT_WARPS + warp) * Fam::MAT_G_STRIDE;
   mc.Pv = ta.S + Fam::S_STRIDE;
-  mc.D = mc.Pv + Fam::MAT_P_STRIDE;
   constexpr int NP = (Fam::N + 1) & ~1, MP = (Fam::M + 1) & ~1;
+  mc.D = mc.Av + Fam::MAT_A_STRIDE;        // the scalings are read by the prologue, the checks and the epilogue only
   mc.Dinv = mc.D + NP; mc.E = mc.Dinv + NP; mc.Einv = mc.E + MP;
   for (;;) {
     int b = 0;

@@ -252,13 +252,23 @@ def pack_tail_blob(T) -> bytes:
     hv['h_ops'] = ar.add_u16(T.ops)
     align_u16(2)
     hv['h_scale'] = ar.add_u16(T.scale)
+    # tile header (8 ints): [i32 offset of the packed entries (slot | position << 16, lane-interleaved), 0, K, r_pad, rows,
+    #                        u16 offset of the row list, inside: u16 offset of the slot table | first slot of the packed triangle,
+    #                        0 no couplings inside / 1 slot table / 2 packed triangle]
     tab = []
     for t in list(T.fwd_tiles) + list(T.bwd_tiles):
-        hs = ar.add_u16(t.slots)
-        hc = ar.add_u16(t.cols)
+        words = (t.slots.astype(np.uint32) | (t.cols.astype(np.uint32) << 16)).astype(np.uint32).view(np.int32)
+        hw = ar.add_i32(words)
         hr = ar.add_u16(np.concatenate([t.rows, np.zeros(LANES - len(t.rows), dtype=np.uint16)]))
-        hin = ar.add_u16(t.inside) if t.inside is not None else 0
-        tab += [hs, hc, t.slots.shape[0], t.r_pad, len(t.rows), hr, hin, 1 if t.inside is not None else 0]
+        if t.inside is None:
+            hin, kind = 0, 0
+        elif t.dense_base >= 0:
+            hin, kind = int(t.dense_base), 2
+        else:
+            hin, kind = ar.add_u16(t.inside), 1
+        tab += [hw, 0, t.slots.shape[0], t.r_pad, len(t.rows), hr, hin, kind]
+    while len(ar.i32) % 4:            # tile headers are fetched as two int4
+        ar.i32.append(0)
     hv['i_tiles'] = ar.add_i32(tab if tab else [0] * 8)
     fmt = '<' + 'i' * len(TAIL_HEADER_FIELDS)
 

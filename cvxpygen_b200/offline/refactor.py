@@ -9,7 +9,9 @@ elimination tree, pattern of L) is the family's; only values change.  QDLDL does
 up-looking, row-by-row numeric factorisation -- sequential.  For a warp we pre-compute:
 
   * S layout: value slot of every entry of the lower triangle of P K P' inside the pattern of L
-    (slots [0,nk) = diagonal, then the strictly-lower entries column by column);
+    (slots [0,nk) = diagonal; then, for every solve group whose diagonal block is at least half full, a packed
+    strict-lower triangle -- padding included -- that the kernel addresses arithmetically; then the remaining
+    strictly-lower entries column by column);
   * S0: slot values of K without the -1/rho diagonal;  rho_slot[j] = diagonal slot of constraint j;
   * per elimination-tree level (columns of a level are independent):
       - the columns of the level                          -> D_j = S[j], S[j] <- 1/D_j
@@ -38,6 +40,8 @@ class SlotTile:
     r_pad: int
     slots: np.ndarray    # (K, 32) uint16 slot into S   (padding: slot of a zero entry, see zero_slot)
     cols: np.ndarray     # (K, 32) uint16 position in w
+    dense_base: int = -1        # >= 0: the couplings INSIDE this group tile sit in a packed strict-lower triangle starting at
+    #                             this slot (see tri_offset): the kernel addresses them arithmetically, no index table
     inside: np.ndarray = None   # group tiles only: (nrows, 32) uint16, inside[j, t] = slot of the coefficient that
     #                             couples row t to row j of the SAME tile (zero_slot if none).  The kernel resolves these
     #                             dependencies with an in-register sweep (one shuffle + FMA per row) instead of one
@@ -71,6 +75,15 @@ class RefactorTables:
     @property
     def zero_slot(self):
         return self.n_slots - 1
+
+
+DENSE_GROUP_MIN_FILL = 0.5     # a group whose diagonal block is at least this full gets the packed-triangle layout
+
+
+def tri_offset(j: int, g: int) -> int:
+    """Packed strict-lower triangle of a g-row group, stored by COLUMN j (the row being swept) with the dependent rows
+    t = j+1 .. g-1 contiguous: coupling (t, j) lives at dense_base + tri_offset(j, g) + t."""
+    return j * (g - 1) - (j * (j - 1)) // 2 - (j + 1)
 
 
 def _slot_tiles(rows, entries, zero_slot) -> List[SlotTile]:
@@ -118,7 +131,7 @@ def _level_groups(level: np.ndarray, lo_level: int):
     return groups
 
 
-def _group_tiles(rows, outside, inside_pairs, zero_slot):
+def _group_tiles(rows, outside, inside_pairs, zero_slot, dense_base=-1):
     """rows sorted ascending; outside[i] = [(slot, col)] entries outside the group; inside_pairs[(t, j)] = slot coupling
     row index t to row index j (both indices into `rows`).  One tile per <= 32 rows; only single-tile groups carry
     inside couplings (wide levels have none)."""
@@ -129,7 +142,10 @@ def _group_tiles(rows, outside, inside_pairs, zero_slot):
         ins = np.full((g, LANES), zero_slot, dtype=np.uint16)
         for (t, j), sl in inside_pairs.items():
             ins[j, t] = sl
+            if dense_base >= 0:
+                assert sl == dense_base + tri_offset(min(t, j), g) + max(t, j)
         tiles[0].inside = ins
+        tiles[0].dense_base = dense_base
     return tiles
 
 
@@ -139,11 +155,33 @@ def build_refactor_tables(F: LDLFactor, K: sp.csc_matrix, n_var: int) -> Refacto
     perm = F.perm
     pinv = np.empty(nk, dtype=np.int64); pinv[perm] = np.arange(nk)
     patt = F.Lpattern
-    # slots of strictly-lower entries, column by column
+    level = F.level
+    # the triangular solves work on GROUPS of consecutive elimination-tree levels (<= 32 rows); the forward and the backward
+    # solve share one partition (level 0 -- the leaves -- only matters to the backward solve and gets its own groups)
+    fwd_groups = _level_groups(level, 1)
+    lvl0 = np.nonzero(level == 0)[0].tolist()
+    bwd_groups = ([lvl0] if lvl0 else []) + fwd_groups
+    # slots of strictly-lower entries: first, for every group whose diagonal block is dense enough, a packed triangle
+    # (entries outside the symbolic pattern inside it are padding: they stay zero and cost storage only); then the
+    # remaining entries column by column
     slot = -np.ones((nk, nk), dtype=np.int64)
     s = nk
+    dense_base = {}
+    for gi, rows in enumerate(fwd_groups):
+        g = len(rows)
+        if g < 2 or g > LANES:
+            continue
+        nin = int(np.tril(patt[np.ix_(rows, rows)], -1).sum())
+        if nin < DENSE_GROUP_MIN_FILL * g * (g - 1) / 2:
+            continue
+        dense_base[gi] = s
+        for j in range(g):
+            for t in range(j + 1, g):
+                if patt[rows[t], rows[j]]:
+                    slot[rows[t], rows[j]] = s + tri_offset(j, g) + t
+        s += g * (g - 1) // 2
     for j in range(nk):
-        rows = np.nonzero(patt[:, j])[0]
+        rows = np.nonzero(patt[:, j] & (slot[:, j] < 0))[0]
         slot[rows, j] = np.arange(s, s + len(rows))
         s += len(rows)
     n_slots = s + 1
@@ -156,7 +194,6 @@ def build_refactor_tables(F: LDLFactor, K: sp.csc_matrix, n_var: int) -> Refacto
     S0[slot[ii, jj]] = Kp[ii, jj]
     rho_slot = pinv[n_var:]
     S0[rho_slot] = 0.0
-    level = F.level
     n_levels = int(level.max()) + 1
     level_ptr, level_cols = [0], []
     op_ptr, ops = [0], []
@@ -178,7 +215,7 @@ def build_refactor_tables(F: LDLFactor, K: sp.csc_matrix, n_var: int) -> Refacto
     # triangular solves: groups of consecutive levels (<= 32 rows) resolve their internal dependencies in registers
     fwd, bwd = [], []
     pos_in = {}
-    for rows in _level_groups(level, 1):
+    for gi, rows in enumerate(fwd_groups):
         rset = {r: t for t, r in enumerate(rows)}
         outside, inside = [], {}
         for t, i in enumerate(rows):
@@ -189,8 +226,10 @@ def build_refactor_tables(F: LDLFactor, K: sp.csc_matrix, n_var: int) -> Refacto
                 else:
                     ent.append((slot[i, j], j))
             outside.append(ent)
-        fwd += _group_tiles(rows, outside, inside if len(rows) <= LANES else {}, n_slots - 1)
-    for rows in reversed(_level_groups(level, 0)):
+        fwd += _group_tiles(rows, outside, inside if len(rows) <= LANES else {}, n_slots - 1, dense_base.get(gi, -1))
+    for bi in range(len(bwd_groups) - 1, -1, -1):
+        rows = bwd_groups[bi]
+        gi = bi - (1 if lvl0 else 0)                 # index of the same group in fwd_groups (-1: the level-0 group)
         rset = {r: t for t, r in enumerate(rows)}
         outside, inside = [], {}
         for t, i in enumerate(rows):
@@ -203,7 +242,7 @@ def build_refactor_tables(F: LDLFactor, K: sp.csc_matrix, n_var: int) -> Refacto
             outside.append(ent)
         if len(rows) > LANES:
             assert not inside
-        bwd += _group_tiles(rows, outside, inside, n_slots - 1)
+        bwd += _group_tiles(rows, outside, inside, n_slots - 1, dense_base.get(gi, -1) if gi >= 0 else -1)
     return RefactorTables(nk=nk, n_slots=n_slots, S0=S0, rho_slot=rho_slot.astype(np.int64),
                           level_ptr=np.asarray(level_ptr), level_cols=np.asarray(level_cols),
                           op_ptr=np.asarray(op_ptr), ops=np.asarray(ops, dtype=np.int64).reshape(-1, 4),
@@ -247,10 +286,16 @@ def emulate_solve(T: RefactorTables, S: np.ndarray, w: np.ndarray) -> np.ndarray
         val = w[r] - outside_acc(tile)[:g]
         if tile.inside is not None:
             order = range(g) if ascending else range(g - 1, -1, -1)
+            tt = np.arange(g)
             for j in order:
                 vj = val[j]
-                coef = S[tile.inside[j, :g].astype(int)]
-                mask = (np.arange(g) > j) if ascending else (np.arange(g) < j)
+                mask = (tt > j) if ascending else (tt < j)
+                if tile.dense_base >= 0:      # packed triangle, addressed arithmetically like group_sweep_dense in the kernel
+                    addr = np.array([tile.dense_base + tri_offset(min(t, j), g) + max(t, j) if t != j else T.zero_slot
+                                     for t in range(g)])
+                    coef = np.where(mask, S[addr], 0.0)
+                else:
+                    coef = S[tile.inside[j, :g].astype(int)]
                 val = np.where(mask, val - coef * vj, val)
         w[r] = val
     for t in T.fwd_tiles:

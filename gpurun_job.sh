@@ -1,6 +1,9 @@
 mkdir -p gpurun_out
-for N in 8 4; do
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_n$N.err | tail -1 | tee gpurun_out/bench_mpc_n$N.json
-done
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 8 --steps 3 --warmup 3 --no-cpu-baseline --workload portfolio_socp 2>>gpurun_out/bench_n8.err | tail -1 | tee gpurun_out/bench_socp_n8.json
-tail -3 gpurun_out/bench_n8.err
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/gpu_tests.log
+timeout 600 python bench.py --workload mpc_ltv --steps 5 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_ltv.json
+timeout 600 python bench.py --steps 10 --warmup 3 --with-grad 2>&1 | tail -1 > gpurun_out/bench_mpc.json
+python -c "
+import json
+for f in ('bench_ltv','bench_mpc'):
+    d=json.load(open('gpurun_out/%s.json'%f)); print(f, d['value'], d['e2e']['value'], d['config'].get('gradient'), d['cpu_baseline']['value'])
+"
