@@ -587,6 +587,61 @@ def random_socp(n=30, p=8, l=20, q=(3, 5, 4), density=0.25, seed=5, name=None) -
                        cone_dims={'l': l, 'q': q})
 
 
+def network_lp(n=50, m=10, seed=0, name=None) -> CanonFamily:
+    """The reference's network-flow LP (tests/test_E2E_LP.py:15-36, data :66-74; run there with solver='ECOS'):
+
+        maximise w'f   s.t.  R f <= c,  f_min <= f <= f_max
+
+    n flows over m links; ECOS form  min -w'f  s.t.  h - G f in R+^(m+2n),  G = [R ; -I ; I],  h = [c ; -f_min ; f_max],
+    no equalities.  ``R`` (0/1 routing matrix, shared), ``c``, ``w``, ``f_min``, ``f_max`` are the user parameters; the
+    vectors are the ones a batch varies.  Duals: d0 (link capacities), d1 (lower bounds), d2 (upper bounds)."""
+    rs = np.random.RandomState(seed)
+    R = np.round(rs.rand(m, n))
+    cdef = n * (0.1 + 0.1 * rs.rand(m))
+    wdef = rs.rand(n)
+    Rs = sp.csc_matrix(R); Rs.eliminate_zeros()
+    G = sp.vstack([Rs, -sp.identity(n), sp.identity(n)], format='csc'); G.sort_indices()
+    A = sp.csc_matrix((0, n))
+    params = _layout_params([('R', (m, n), R.flatten(order='F')), ('c', (m,), cdef), ('w', (n,), wdef),
+                             ('f_min', (n,), np.zeros(n)), ('f_max', (n,), np.ones(n))])
+    col = {p.name: p.col for p in params}
+    n_theta = params[-1].col + params[-1].size + 1
+    mt = m + 2 * n
+    mc = _MapBuilder(n, n_theta)
+    for i in range(n):
+        mc.add(i, col['w'] + i, -1.0)
+    mh = _MapBuilder(mt, n_theta)
+    for i in range(m):
+        mh.add(i, col['c'] + i, 1.0)
+    for i in range(n):
+        mh.add(m + i, col['f_min'] + i, -1.0)
+        mh.add(m + n + i, col['f_max'] + i, 1.0)
+    mg = _MapBuilder(G.nnz, n_theta)
+    Gc = sp.coo_matrix(G)
+    order = np.lexsort((Gc.row, Gc.col))
+    for k, (r, c_, v) in enumerate(zip(Gc.row[order], Gc.col[order], Gc.data[order])):
+        if r < m:
+            mg.add(k, col['R'] + r + m * c_, 1.0)          # R is a dense parameter, Fortran order
+        else:
+            mg.const(k, v)
+    maps = {'c': mc.csr(), 'd': sp.csr_matrix((1, n_theta)), 'A': sp.csr_matrix((0, n_theta)), 'b': sp.csr_matrix((0, n_theta)),
+            'G': mg.csr(), 'h': mh.csr()}
+    variables = [UserVar('f', (n,), np.arange(n))]
+    duals = [UserDual('d0', 'z', (m,), np.arange(m)), UserDual('d1', 'z', (n,), m + np.arange(n)),
+             UserDual('d2', 'z', (n,), m + n + np.arange(n))]
+    return CanonFamily(name or f'network_lp_{n}_{m}', 'conic', n, 0, mt, params, maps,
+                       {'A': _csc_pattern(A), 'G': _csc_pattern(G)}, variables, duals, is_maximization=True,
+                       cone_dims={'l': mt, 'q': []})
+
+
+def network_lp_batch(fam: CanonFamily, B: int, seed: int = 1):
+    """Per-instance vectors drawn like the reference's assign_data (tests/test_E2E_LP.py:66-74)."""
+    rng = np.random.default_rng(seed)
+    n, m = fam.param('w').size, fam.param('c').size
+    return {'c': n * (0.1 + 0.1 * rng.random((B, m))), 'w': rng.random((B, n)),
+            'f_min': 0.05 * rng.random((B, n)), 'f_max': 1.0 + 0.1 * rng.random((B, n))}
+
+
 def box_qp(n=6, m=8, seed=4, name=None) -> CanonFamily:
     """Small QP with two-sided constraints  l <= A x <= u  whose bounds are user parameters, built to exercise the
     per-instance corner cases of the path: a bound pair collapsing to an equality or opening to (-inf, inf) changes the

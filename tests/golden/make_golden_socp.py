@@ -38,3 +38,17 @@ for fam in (families.random_socp(30, 8, 20, (3, 5, 4), seed=5), families.random_
     np.savez_compressed(os.path.join(HERE, f'socp_{fam.name}.npz'), kind=kind, **{'param_' + k: v for k, v in par.items()},
                         x=out['x'], y=out['y'], z=out['z'], s=out['s'], pcost=out['pcost'], iter=out['iter'], exitflag=out['exitflag'])
     print(fam.name, 'kinds', np.bincount(kind), 'flags', np.unique(out['exitflag'], return_counts=True), 'iters', out['iter'].mean())
+
+# ---- the reference's own LP test problem run with ECOS (tests/test_E2E_LP.py:15-36, 66-74): network flow, n = 50, m = 10
+fam = families.network_lp(50, 10)
+par = families.network_lp_batch(fam, 48, seed=2025)
+th = np.tile(fam.theta_default(), (48, 1))
+for k, v in par.items():
+    p = fam.param(k); th[:, p.col:p.col + p.size] = v
+Cb = np.asarray(th @ fam.maps['c'].T.toarray()); Hb = np.asarray(th @ fam.maps['h'].T.toarray())
+r = RefECOS(fam.canon_data('c'), fam.canon_matrix('A'), fam.canon_data('b'), fam.canon_matrix('G'), fam.canon_data('h'),
+            fam.cone_dims['l'], fam.cone_dims['q'])
+out = r.solve_batch(c=Cb, h=Hb)
+np.savez_compressed(os.path.join(HERE, f'socp_{fam.name}.npz'), **{'param_' + k: v for k, v in par.items()},
+                    x=out['x'], y=out['y'], z=out['z'], s=out['s'], pcost=out['pcost'], iter=out['iter'], exitflag=out['exitflag'])
+print(fam.name, 'flags', np.unique(out['exitflag'], return_counts=True), 'iters', out['iter'].mean())

@@ -235,6 +235,56 @@ def test_generic_conic_families_on_host_match_golden(name, tmp_path):
     _check_against(g, out['x'], out['y'][:, :fam.n_eq], out['z'], out['s'], out['status'], out['iter'], out['obj'], slice(0, B))
 
 
+def _network_inputs(g, fam):
+    names = standard.STANDARD['network_lp_50_10'][1]
+    return np.concatenate([g['param_' + nm] for nm in names], axis=1), names
+
+
+def test_reference_network_lp_on_host_matches_golden(tmp_path):
+    """The reference's own LP test problem (tests/test_E2E_LP.py:15-36, network flow n = 50, m = 10, solved there with
+    ECOS): a maximisation with no equalities and no second-order cone, four batched vector parameters, the routing matrix
+    shared.  Kernel phase logic on the host against the compiled ECOS golden vectors."""
+    fam = families.network_lp(50, 10)
+    g = np.load(os.path.join(GOLDEN, 'socp_network_lp_50_10.npz'))
+    P, names = _network_inputs(g, fam)
+    st = ss.setup_socp_family(fam, names)
+    assert (st.defines['NSOC'], st.defines['P'], st.defines['IS_MAX']) == (0, 0, 1)
+    lib = _build_emu(st, str(tmp_path))
+    B = 24
+    out = _emu_solve(lib, st, P[:B])
+    assert np.array_equal(out['status'], g['exitflag'][:B]) and np.array_equal(out['iter'], g['iter'][:B])
+    for k in range(B):
+        assert _rel(out['x'][k], g['x'][k]) < RTOL_PRIMAL and _rel(out['z'][k], g['z'][k]) < RTOL_DUAL
+    assert np.allclose(out['obj'], -g['pcost'][:B], rtol=1e-9)                 # maximise w'f: obj_val = -pcost
+    assert np.allclose(out['obj'], (g['param_w'][:B] * out['x']).sum(1), rtol=1e-7)
+    # user-level gathers: f = x, d0 / d1 / d2 = capacity / lower / upper multipliers
+    assert np.array_equal(out['prim'][:, :50], out['x']) and np.array_equal(out['dual'][:, :110], out['z'])
+
+
+@pytest.mark.gpu
+def test_gpu_reference_network_lp():
+    fam = families.network_lp(50, 10)
+    g = np.load(os.path.join(GOLDEN, 'socp_network_lp_50_10.npz'))
+    m = standard.load('network_lp_50_10')
+    names = standard.STANDARD['network_lp_50_10'][1]
+    r = m.solve_batch({nm: g['param_' + nm] for nm in names}, return_canonical=True)
+    assert np.array_equal(r.cpg_info.status, g['exitflag']) and np.array_equal(r.cpg_info.iter, g['iter'])
+    assert _rel(r.sol_x, g['x']) < RTOL_PRIMAL and _rel(r.sol_z, g['z']) < RTOL_DUAL
+    assert np.allclose(r.cpg_info.obj_val, -g['pcost'], rtol=1e-9)
+    assert np.array_equal(r.cpg_prim['f'], r.sol_x) and np.array_equal(r.cpg_dual['d0'], r.sol_z[:, :10])
+    # a fresh, larger batch: feasibility and optimality of every instance's own LP
+    B = 5000
+    par = families.network_lp_batch(fam, B, seed=77)
+    r2 = m.solve_batch(par, return_canonical=True)
+    assert (r2.cpg_info.status == 0).all()
+    R = fam.param('R').default.reshape(10, 50, order='F')
+    f = r2.cpg_prim['f']
+    assert (f @ R.T - par['c']).max() < 1e-7 and (par['f_min'] - f).max() < 1e-7 and (f - par['f_max']).max() < 1e-7
+    gap = np.abs((par['w'] * f).sum(1) - (-(r2.sol_z[:, :10] * par['c']).sum(1) + (r2.sol_z[:, 10:60] * par['f_min']).sum(1)
+                                          - (r2.sol_z[:, 60:] * par['f_max']).sum(1)) * -1)
+    assert (gap < 1e-6 * np.maximum(1.0, np.abs(r2.cpg_info.obj_val))).all()     # strong duality: w'f = c'z0 - fmin'z1 + fmax'z2
+
+
 def test_generated_directory_and_c_abi():
     d = standard.build(NAME)
     for f in ('cpg_solver.py', 'cpg_module.py', 'cpg_meta.json', 'libcpg_b200.so', 'c/include/cpg_b200_socp.h',
