@@ -587,6 +587,85 @@ def random_socp(n=30, p=8, l=20, q=(3, 5, 4), density=0.25, seed=5, name=None) -
                        cone_dims={'l': l, 'q': q})
 
 
+def portfolio_qp(n=50, m=10, seed=0, name=None) -> CanonFamily:
+    """The reference's portfolio test problem in its QP form (tests/test_E2E_QP.py:76-110, data :148-162; run there with OSQP):
+
+        maximise a'w - |Sig_f_sqrt f|^2 - |d_sqrt . w|^2 - k_tc'|delta_w| + k_sh' min(0, w)
+        s.t.     f = F'w,  1'w = 1,  |w|_1 <= L,  delta_w = w - w_prev
+
+    canonical x = [w ; delta_w ; f ; t >= |delta_w| ; s <= min(0, w) ; v >= |w| ; g = Sig_f_sqrt f ; e = d_sqrt . w],
+    P = 2 I on (g, e) -- the factors multiply variables inside sum_squares, so they enter the constraint matrix through
+    auxiliaries like in cvxpy's DPP canonicalisation -- q = [-a ; 0 ; 0 ; k_tc ; -k_sh ; 0 ; 0 ; 0].
+    rows: equalities  f - F'w = 0 (d0) | 1'w = 1 (d1) | delta_w - w = -w_prev (d3) | g - Sig f = 0 | e - d . w = 0
+          inequalities  +-delta_w - t <= 0 | s <= 0 | s - w <= 0 | +-w - v <= 0 | 1'v <= L (d2)
+    ``a``, ``w_prev``, ``k_tc``, ``k_sh``, ``L`` only touch q, l, u; ``F``, ``Sig_f_sqrt``, ``d_sqrt`` are matrix parameters."""
+    rs = np.random.RandomState(seed)
+    alpha = rs.randn(n)
+    F = np.round(rs.randn(n, m))
+    Sig = np.diag(rs.rand(m))
+    dsq = rs.rand(n)
+    params = _layout_params([('a', (n,), alpha), ('F', (n, m), F.flatten(order='F')), ('Sig_f_sqrt', (m, m), Sig.flatten(order='F')),
+                             ('d_sqrt', (n,), dsq), ('k_tc', (n,), 0.01 * np.ones(n)), ('k_sh', (n,), 0.05 * np.ones(n)),
+                             ('w_prev', (n,), np.zeros(n)), ('L', (), 1.6)])
+    col = {p.name: p.col for p in params}
+    n_theta = params[-1].col + params[-1].size + 1
+    ow, od, of, ot, os_, ov, og, oe = 0, n, 2 * n, 2 * n + m, 3 * n + m, 4 * n + m, 5 * n + m, 5 * n + 2 * m
+    nv = oe + n
+    r_f, r_one, r_dw, r_g, r_e = 0, m, m + 1, m + 1 + n, 2 * m + 1 + n
+    n_eq = r_e + n
+    i_t1, i_t2, i_s1, i_s2, i_v1, i_v2, i_L = n_eq, n_eq + n, n_eq + 2 * n, n_eq + 3 * n, n_eq + 4 * n, n_eq + 5 * n, n_eq + 6 * n
+    mt = i_L + 1
+    n_ineq = mt - n_eq
+    ent = []
+    for j in range(m):
+        ent.append((r_f + j, of + j, ('c', 1.0)))
+        for i in range(n):
+            ent.append((r_f + j, ow + i, ('p', col['F'] + i + n * j, -1.0)))          # -(F'w)_j = -sum_i F_ij w_i
+        ent.append((r_g + j, og + j, ('c', 1.0)))
+        for k in range(m):
+            ent.append((r_g + j, of + k, ('p', col['Sig_f_sqrt'] + j + m * k, -1.0)))
+    for i in range(n):
+        ent += [(r_one, ow + i, ('c', 1.0)), (r_dw + i, od + i, ('c', 1.0)), (r_dw + i, ow + i, ('c', -1.0)),
+                (r_e + i, oe + i, ('c', 1.0)), (r_e + i, ow + i, ('p', col['d_sqrt'] + i, -1.0)),
+                (i_t1 + i, od + i, ('c', 1.0)), (i_t1 + i, ot + i, ('c', -1.0)),
+                (i_t2 + i, od + i, ('c', -1.0)), (i_t2 + i, ot + i, ('c', -1.0)),
+                (i_s1 + i, os_ + i, ('c', 1.0)), (i_s2 + i, os_ + i, ('c', 1.0)), (i_s2 + i, ow + i, ('c', -1.0)),
+                (i_v1 + i, ow + i, ('c', 1.0)), (i_v1 + i, ov + i, ('c', -1.0)),
+                (i_v2 + i, ow + i, ('c', -1.0)), (i_v2 + i, ov + i, ('c', -1.0)), (i_L, ov + i, ('c', 1.0))]
+    ent.sort(key=lambda e: (e[1], e[0]))
+    Ar = np.array([e[0] for e in ent]); Ac = np.array([e[1] for e in ent])
+    indptr = np.zeros(nv + 1, dtype=np.int64)
+    np.add.at(indptr, Ac + 1, 1); indptr = np.cumsum(indptr).astype(np.int32)
+    mbA = _MapBuilder(len(ent), n_theta)
+    for k, e in enumerate(ent):
+        if e[2][0] == 'c':
+            mbA.const(k, e[2][1])
+        else:
+            mbA.add(k, e[2][1], e[2][2])
+    naux = m + n
+    Pu = sp.csc_matrix((2.0 * np.ones(naux), (og + np.arange(naux), og + np.arange(naux))), shape=(nv, nv))
+    mbP = _MapBuilder(naux, n_theta)
+    for k in range(naux):
+        mbP.const(k, 2.0)
+    mq = _MapBuilder(nv, n_theta)
+    for i in range(n):
+        mq.add(ow + i, col['a'] + i, -1.0); mq.add(ot + i, col['k_tc'] + i, 1.0); mq.add(os_ + i, col['k_sh'] + i, -1.0)
+    ml, mu = _MapBuilder(mt, n_theta), _MapBuilder(mt, n_theta)
+    ml.const(r_one, 1.0); mu.const(r_one, 1.0)
+    for i in range(n):
+        ml.add(r_dw + i, col['w_prev'] + i, -1.0); mu.add(r_dw + i, col['w_prev'] + i, -1.0)
+    for r in range(n_eq, mt):
+        ml.const(r, -INF)
+    mu.add(i_L, col['L'], 1.0)
+    maps = {'A': mbA.csr(), 'P': mbP.csr(), 'q': mq.csr(), 'd': sp.csr_matrix((1, n_theta)), 'l': ml.csr(), 'u': mu.csr()}
+    variables = [UserVar('w', (n,), ow + np.arange(n)), UserVar('delta_w', (n,), od + np.arange(n)), UserVar('f', (m,), of + np.arange(m))]
+    duals = [UserDual('d0', 'y', (m,), r_f + np.arange(m)), UserDual('d1', 'y', (), np.array([r_one])),
+             UserDual('d2', 'y', (), np.array([i_L])), UserDual('d3', 'y', (n,), r_dw + np.arange(n))]
+    return CanonFamily(name or f'portfolio_qp_{n}_{m}', 'quadratic', nv, n_eq, n_ineq, params, maps,
+                       {'P': _csc_pattern(Pu), 'A': (Ar.astype(np.int32), indptr, (mt, nv))}, variables, duals,
+                       is_maximization=True)
+
+
 def network_lp(n=50, m=10, seed=0, name=None) -> CanonFamily:
     """The reference's network-flow LP (tests/test_E2E_LP.py:15-36, data :66-74; run there with solver='ECOS'):
 

@@ -17,6 +17,10 @@ from typing import Dict, List, Tuple
 import numpy as np
 import scipy.sparse as sp
 
+import threading
+
+_TLS = threading.local()
+
 MAGIC = 0x42323030   # 'B200'
 LANES = 32
 
@@ -104,6 +108,11 @@ def _add_ell(ar: _Areas, blocks) -> int:
     for K, vals, cols in blocks:
         table += [K, ar.add_f64(vals), ar.add_u16(cols)]
     return ar.add_i32(table) if table else ar.add_i32([0, 0, 0])
+
+
+def last_solve_source() -> str:
+    """generated straight-line KKT solve of the last pack_blob(with_tiles=True) call of THIS thread"""
+    return _TLS.last_solve_source
 
 
 def pack_blob(*, n, m, perm, schedule, Ps_upper, As, D, E, c, sigma, rho, ctype,
@@ -212,8 +221,8 @@ def pack_blob(*, n, m, perm, schedule, Ps_upper, As, D, E, c, sigma, rho, ctype,
     assert len(blob) == hv['total_bytes'] and len(blob) % 16 == 0
     if with_tiles:
         from .emit_solve import emit_kkt_solve
-        pack_blob.last_solve_source = emit_kkt_solve(schedule, encodings, tile_info)
-        pack_blob.last_header = dict(hv)
+        _TLS.last_solve_source = emit_kkt_solve(schedule, encodings, tile_info)   # per thread: families are built concurrently
+        _TLS.last_header = dict(hv)
     return blob
 
 

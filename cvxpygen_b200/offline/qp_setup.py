@@ -12,7 +12,7 @@ import scipy.sparse as sp
 
 from ..ir import CanonFamily
 from . import kkt as _kkt
-from .blob import pack_blob, pack_tail_blob, pack_grad_blob, pack_matpar_blob
+from .blob import pack_blob, pack_tail_blob, pack_grad_blob, pack_matpar_blob, last_solve_source as _last_solve_source
 from .refactor import build_refactor_tables, RefactorTables
 from .equilibrate import ruiz_equilibrate
 from .schedule import SolveSchedule, build_schedule
@@ -117,7 +117,7 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
                      c=sc['c'], sigma=sigma, rho=rho, ctype=ctype, q_base=q_base, l_base=l_base, u_base=u_base,
                      Mq_b=Mq_b, Ml_b=Ml_b, Mu_b=Mu_b, npb=npb, prim_idx=prim_idx, dual_idx=dual_idx,
                      d_const=d_const, is_max=fam.is_maximization)
-    solve_source = pack_blob.last_solve_source
+    solve_source = _last_solve_source()
     # the tail kernel needs everything but the (large) tile schedule: a compact copy leaves room for more warps
     blob_compact = pack_blob(n=n, m=m, perm=F.perm, schedule=S, Ps_upper=sc['P'], As=sc['A'], D=sc['D'], E=sc['E'],
                              c=sc['c'], sigma=sigma, rho=rho, ctype=ctype, q_base=q_base, l_base=l_base, u_base=u_base,

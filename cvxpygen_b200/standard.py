@@ -17,6 +17,7 @@ STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
     'mpc_6_3_10': (lambda: families.mpc(6, 3, 10), ['x_init']),             # the reference test's MPC size
     'nonneg_LS_3_2': (lambda: families.nonneg_ls(3, 2), ['b']),             # BASELINE config 1 (README example)
     'random_qp_20_5_15': (lambda: families.random_qp(20, 5, 15), ['q', 'b', 'h']),  # unstructured sparsity, q/l/u all batched
+    'portfolio_qp_50_10': (lambda: families.portfolio_qp(50, 10), ['a', 'w_prev']),   # the reference's portfolio test problem (QP form, OSQP)
     'box_qp_6_8': (lambda: families.box_qp(6, 8), ['q', 'l', 'u']),          # corner cases: type changes, infeasibility
     # f2: the MPC family with its matrices as per-instance parameters (dynamics A, B and diagonal stage costs)
     'mpc_ltv_6_3_10': (lambda: families.mpc_ltv(6, 3, 10), ['A', 'B', 'qdiag', 'rdiag', 'x_init']),
@@ -53,8 +54,14 @@ def build(name: str, force: bool = False, verbose: bool = False) -> str:
     return d
 
 
-def build_all(force: bool = False, verbose: bool = False):
-    return {name: build(name, force, verbose) for name in STANDARD}
+def build_all(force: bool = False, verbose: bool = False, jobs: int = None):
+    """Generate + compile every standard family.  The nvcc invocations (minutes of front-end time for the families with
+    long generated straight-line solves) run concurrently, one subprocess per family, on the host cores."""
+    import concurrent.futures as cf
+    jobs = jobs or max(1, min(len(STANDARD), (os.cpu_count() or 2)))
+    with cf.ThreadPoolExecutor(jobs) as ex:
+        futs = {name: ex.submit(build, name, force, verbose) for name in STANDARD}
+        return {name: f.result() for name, f in futs.items()}
 
 
 def load(name: str, device: int = 0):

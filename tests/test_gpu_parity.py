@@ -9,7 +9,7 @@ from helpers import family_and_batch, oracle_solve, rel_err, assert_batch_parity
 
 TOL = 1e-5   # north_star: "within 1e-5 relative on primal/dual variables"
 
-FAMS = [('mpc_12_4_10', 512), ('mpc_6_3_10', 512), ('nonneg_LS_3_2', 256), ('random_qp_20_5_15', 256)]
+FAMS = [('mpc_12_4_10', 512), ('mpc_6_3_10', 512), ('nonneg_LS_3_2', 256), ('random_qp_20_5_15', 256), ('portfolio_qp_50_10', 256)]
 
 
 @pytest.mark.gpu
