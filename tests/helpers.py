@@ -67,7 +67,7 @@ def rel_err(a, b):
     return np.linalg.norm(a - b, axis=1) / np.maximum(nb, 1e-12)
 
 
-def assert_batch_parity(got_x, got_y, got_info, ora, tol, eps_abs=1e-3, stable=None):
+def assert_batch_parity(got_x, got_y, got_info, ora, tol, eps_abs=1e-3, stable=None, obj_sign=1.0):
     """got_info: object with status, iter, obj_val, pri_res, dua_res arrays.
     stable: optional boolean mask of the instances on which the comparison is meaningful (see rounding_stable)."""
     st = np.asarray(got_info.status)
@@ -82,7 +82,8 @@ def assert_batch_parity(got_x, got_y, got_info, ora, tol, eps_abs=1e-3, stable=N
     if sol.any():
         assert rel_err(got_x[sol], ora['x'][sol]).max() < tol
         assert rel_err(got_y[sol], ora['y'][sol]).max() < tol
-        assert np.allclose(got_info.obj_val[sol], ora['obj'][sol], rtol=1e-6, atol=1e-9)
+        # cpg_retrieve_info reports -(solver objective) for maximisation problems (cvxpygen/utils.py:980)
+        assert np.allclose(got_info.obj_val[sol], obj_sign * ora['obj'][sol], rtol=1e-6, atol=1e-9)
         # residuals are differences of O(1) numbers: compare on the scale of the stopping tolerance
         assert np.allclose(got_info.pri_res[sol], ora['pri_res'][sol], rtol=1e-5, atol=1e-3 * eps_abs)
         assert np.allclose(got_info.dua_res[sol], ora['dua_res'][sol], rtol=1e-5, atol=1e-3 * eps_abs)

@@ -21,7 +21,7 @@ def test_parity_vs_oracle(name, B, adaptive_rho):
     res = mod.solve_batch(params, return_canonical=True, adaptive_rho=adaptive_rho)
     mod.set_solver_default_settings()
     ora = oracle_solve(fam, q, l, u, adaptive_rho=adaptive_rho)
-    sol = assert_batch_parity(res.sol_x, res.sol_y, res.cpg_info, ora, TOL)
+    sol = assert_batch_parity(res.sol_x, res.sol_y, res.cpg_info, ora, TOL, obj_sign=-1.0 if fam.is_maximization else 1.0)
     # user-level retrieval = gather of the canonical solution (a12)
     for v in fam.variables:
         got = res.cpg_prim[v.name].reshape(B, -1, order='F') if len(v.shape) > 1 else res.cpg_prim[v.name]
