@@ -587,6 +587,63 @@ def random_socp(n=30, p=8, l=20, q=(3, 5, 4), density=0.25, seed=5, name=None) -
                        cone_dims={'l': l, 'q': q})
 
 
+def actuator(name=None) -> CanonFamily:
+    """The reference's actuator-allocation test problem (tests/test_E2E_QP.py:16-41, data :116-125), chosen there "for
+    degenerate vectors and matrices": one actuator (n = 1), three objectives (m = 3),
+
+        minimise |A u - w|^2 + lamb_sm |delta_u|^2 + kappa'|u|   s.t.  u_min <= u <= u_max,  delta_u = u - u_prev
+
+    canonical x = [u ; delta_u ; r = A u - w (3) ; t >= |u|];  P = diag(0, 2 lamb_sm, 2, 2, 2, 0) -- the scalar parameter
+    lamb_sm enters P --, q = kappa on t;  rows: r - A u = -w | delta_u - u = -u_prev (d2) | u_min <= u <= u_max (d0 / d1 share
+    the two-sided row) | +-u - t <= 0.  Scalar parameters have shape ()."""
+    params = _layout_params([('A', (3, 1), np.ones(3)), ('w', (3,), np.array([2.0, 3.0, 5.0])), ('lamb_sm', (), 0.5488135039273248),
+                             ('kappa', (1,), 0.1), ('u_prev', (1,), 0.0), ('u_min', (1,), -1.0), ('u_max', (1,), 1.0)])
+    col = {p.name: p.col for p in params}
+    n_theta = params[-1].col + params[-1].size + 1
+    iu, idu, ir, it = 0, 1, 2, 5
+    nv = 6
+    ent = [(0 + i, ir + i, ('c', 1.0)) for i in range(3)] + [(0 + i, iu, ('p', col['A'] + i, -1.0)) for i in range(3)]
+    ent += [(3, idu, ('c', 1.0)), (3, iu, ('c', -1.0)), (4, iu, ('c', 1.0)),
+            (5, iu, ('c', 1.0)), (5, it, ('c', -1.0)), (6, iu, ('c', -1.0)), (6, it, ('c', -1.0))]
+    n_eq, mt = 4, 7
+    ent.sort(key=lambda e: (e[1], e[0]))
+    Ar = np.array([e[0] for e in ent]); Ac = np.array([e[1] for e in ent])
+    indptr = np.zeros(nv + 1, dtype=np.int64)
+    np.add.at(indptr, Ac + 1, 1); indptr = np.cumsum(indptr).astype(np.int32)
+    mbA = _MapBuilder(len(ent), n_theta)
+    for k, e in enumerate(ent):
+        if e[2][0] == 'c':
+            mbA.const(k, e[2][1])
+        else:
+            mbA.add(k, e[2][1], e[2][2])
+    Pu = sp.csc_matrix((np.ones(4), ([idu, ir, ir + 1, ir + 2], [idu, ir, ir + 1, ir + 2])), shape=(nv, nv))
+    mbP = _MapBuilder(4, n_theta)
+    mbP.add(0, col['lamb_sm'], 2.0)
+    for k in range(1, 4):
+        mbP.const(k, 2.0)
+    mq = _MapBuilder(nv, n_theta); mq.add(it, col['kappa'], 1.0)
+    ml, mu = _MapBuilder(mt, n_theta), _MapBuilder(mt, n_theta)
+    for i in range(3):
+        ml.add(i, col['w'] + i, -1.0); mu.add(i, col['w'] + i, -1.0)
+    ml.add(3, col['u_prev'], -1.0); mu.add(3, col['u_prev'], -1.0)
+    ml.add(4, col['u_min'], 1.0); mu.add(4, col['u_max'], 1.0)
+    ml.const(5, -INF); ml.const(6, -INF)
+    maps = {'A': mbA.csr(), 'P': mbP.csr(), 'q': mq.csr(), 'd': sp.csr_matrix((1, n_theta)), 'l': ml.csr(), 'u': mu.csr()}
+    variables = [UserVar('u', (1,), np.array([iu])), UserVar('delta_u', (1, 1), np.array([idu]))]
+    duals = [UserDual('d0', 'y', (1,), np.array([4])), UserDual('d1', 'y', (1, 1), np.array([3]))]
+    return CanonFamily(name or 'actuator_1_3', 'quadratic', nv, n_eq, mt - n_eq, params, maps,
+                       {'P': _csc_pattern(Pu), 'A': (Ar.astype(np.int32), indptr, (mt, nv))}, variables, duals)
+
+
+def actuator_batch(fam: CanonFamily, B: int, seed: int = 0):
+    """Per-instance values of ALL seven parameters (lamb_sm enters P, A enters the constraint matrix)."""
+    rng = np.random.default_rng(seed)
+    lo = -1.0 - 0.5 * rng.random((B, 1))
+    return {'A': 1.0 + 0.3 * rng.standard_normal((B, 3)), 'w': np.array([2.0, 3.0, 5.0]) + rng.standard_normal((B, 3)),
+            'lamb_sm': rng.random((B, 1)), 'kappa': 0.1 + 0.1 * rng.random((B, 1)), 'u_prev': 0.5 * rng.standard_normal((B, 1)),
+            'u_min': lo, 'u_max': lo + 0.5 + 2.0 * rng.random((B, 1))}
+
+
 def portfolio_qp(n=50, m=10, seed=0, name=None) -> CanonFamily:
     """The reference's portfolio test problem in its QP form (tests/test_E2E_QP.py:76-110, data :148-162; run there with OSQP):
 
@@ -664,6 +721,67 @@ def portfolio_qp(n=50, m=10, seed=0, name=None) -> CanonFamily:
     return CanonFamily(name or f'portfolio_qp_{n}_{m}', 'quadratic', nv, n_eq, n_ineq, params, maps,
                        {'P': _csc_pattern(Pu), 'A': (Ar.astype(np.int32), indptr, (mt, nv))}, variables, duals,
                        is_maximization=True)
+
+
+def adp_socp(name=None) -> CanonFamily:
+    """The reference's SOCP test problem (tests/test_E2E_SOCP.py:15-35, data :38-63; run there with ECOS among others):
+    one step of approximate dynamic programming with two norm-bounded inputs,
+
+        minimise |f + G u_0|^2 + |Rsqrt u_0|^2   s.t.  |u_i|_2 <= 0.1,  i = 0, 1        (u is 2 x 3, u_i its rows)
+
+    ECOS form: x = [u(:) (Fortran order) ; t1 ; t2], minimise t1 + t2 with the two squared norms as rotated cones
+    (1 + t, 1 - t, 2 v) in SOC and the two input bounds (0.1, u_i) in SOC(4); no LP cone, no equalities.
+    ``f`` (what the current state enters through) is the per-instance vector; ``G`` and ``Rsqrt`` are matrix parameters."""
+    n, m = 6, 3
+    rs = np.random.RandomState(0)
+    state = -2 * np.ones(6) + 4 * rs.rand(6)
+    td = 0.1
+    A = np.eye(6) + td * np.block([[np.zeros((3, 3)), np.eye(3)], [np.zeros((3, 3)), -np.diag(state[3:])]])
+    Bm = td * np.vstack([np.zeros((3, 3)), np.diag(state[3:])])
+    params = _layout_params([('Rsqrt', (m, m), np.sqrt(0.1) * np.ones(m)), ('f', (n,), A @ state), ('G', (n, m), Bm.flatten(order='F'))])
+    col = {p.name: p.col for p in params}
+    n_theta = params[-1].col + params[-1].size + 1
+    nv = 2 * m + 2
+    it1, it2 = 2 * m, 2 * m + 1
+    u0 = lambda j: 2 * j                      # u[0, j] in Fortran order of the 2 x m variable
+    u1 = lambda j: 2 * j + 1
+    q = [n + 2, m + 2, m + 1, m + 1]
+    rows = sum(q)
+    ent, hmap = [], _MapBuilder(rows, n_theta)
+    r = 0
+    ent += [(r, it1, ('c', -1.0)), (r + 1, it1, ('c', 1.0))]; hmap.const(r, 1.0); hmap.const(r + 1, 1.0)
+    for i in range(n):
+        hmap.add(r + 2 + i, col['f'] + i, 2.0)
+        for j in range(m):
+            ent.append((r + 2 + i, u0(j), ('p', col['G'] + i + n * j, -2.0)))
+    r += n + 2
+    ent += [(r, it2, ('c', -1.0)), (r + 1, it2, ('c', 1.0))]; hmap.const(r, 1.0); hmap.const(r + 1, 1.0)
+    for j in range(m):
+        ent.append((r + 2 + j, u0(j), ('p', col['Rsqrt'] + j, -2.0)))
+    r += m + 2
+    for idx in (u0, u1):
+        hmap.const(r, 0.1)
+        for j in range(m):
+            ent.append((r + 1 + j, idx(j), ('c', -1.0)))
+        r += m + 1
+    ent.sort(key=lambda e: (e[1], e[0]))
+    Gr = np.array([e[0] for e in ent]); Gc = np.array([e[1] for e in ent])
+    indptr = np.zeros(nv + 1, dtype=np.int64)
+    np.add.at(indptr, Gc + 1, 1); indptr = np.cumsum(indptr).astype(np.int32)
+    mg = _MapBuilder(len(ent), n_theta)
+    for k, e in enumerate(ent):
+        if e[2][0] == 'c':
+            mg.const(k, e[2][1])
+        else:
+            mg.add(k, e[2][1], e[2][2])
+    mc = _MapBuilder(nv, n_theta); mc.const(it1, 1.0); mc.const(it2, 1.0)
+    maps = {'c': mc.csr(), 'd': sp.csr_matrix((1, n_theta)), 'A': sp.csr_matrix((0, n_theta)), 'b': sp.csr_matrix((0, n_theta)),
+            'G': mg.csr(), 'h': hmap.csr()}
+    variables = [UserVar('u', (2, m), np.arange(2 * m))]
+    duals = [UserDual('d0', 'z', None, (n + 2) + (m + 2) + np.arange(2 * (m + 1)))]
+    return CanonFamily(name or 'adp_socp_6_3', 'conic', nv, 0, rows, params, maps,
+                       {'A': _csc_pattern(sp.csc_matrix((0, nv))), 'G': (Gr.astype(np.int32), indptr, (rows, nv))}, variables, duals,
+                       is_maximization=False, cone_dims={'l': 0, 'q': q})
 
 
 def network_lp(n=50, m=10, seed=0, name=None) -> CanonFamily:

@@ -23,18 +23,20 @@ STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
     'mpc_ltv_6_3_10': (lambda: families.mpc_ltv(6, 3, 10), ['A', 'B', 'qdiag', 'rdiag', 'x_init']),
     'mpc_ltv_12_4_10': (lambda: families.mpc_ltv(12, 4, 10), ['A', 'B', 'qdiag', 'rdiag', 'x_init']),
     'mpc_ref_6_3_10': (lambda: families.mpc_reference(10), ['Psqrt', 'Qsqrt', 'Rsqrt', 'A', 'B', 'x_init']),   # the reference's test MPC, all parameters
+    'actuator_1_3': (lambda: families.actuator(), ['A', 'w', 'lamb_sm', 'kappa', 'u_prev', 'u_min', 'u_max']),   # degenerate shapes, scalar parameter in P
     'nonneg_LS_3_2_A': (lambda: families.nonneg_ls(3, 2, name='nonneg_LS_3_2_A'), ['A', 'b']),   # README example, A per instance
     'portfolio_socp_100_10': (lambda: families.portfolio_socp(100, 10), ['a', 'w_prev']),   # BASELINE config 3 (IPM-CUDA)
     # generic conic families (every vector batched): three cones + equalities, and a pure LP; exit flags 0 / 1 / 2
     'random_socp_30_8_20_3x5x4': (lambda: families.random_socp(30, 8, 20, (3, 5, 4), seed=5), ['c', 'b', 'h']),
     'random_socp_20_5_30_lp': (lambda: families.random_socp(20, 5, 30, (), seed=6), ['c', 'b', 'h']),
     # the reference's network-flow LP (tests/test_E2E_LP.py, solved there with ECOS): vectors per instance, routing matrix shared
+    'adp_socp_6_3': (lambda: families.adp_socp(), ['f']),      # the reference's SOCP test problem (tests/test_E2E_SOCP.py), four second-order cones, no LP cone
     'network_lp_50_10': (lambda: families.network_lp(50, 10), ['c', 'w', 'f_min', 'f_max']),
 }
 
 # families solved by the ADMM (QP) backend / by the interior-point (SOCP) backend
-SOCP_NAMES: List[str] = [n for n in STANDARD if '_socp_' in n or n.startswith('network_lp')]
-MATPAR_NAMES: List[str] = ['mpc_ltv_6_3_10', 'mpc_ltv_12_4_10', 'mpc_ref_6_3_10', 'nonneg_LS_3_2_A']
+SOCP_NAMES: List[str] = [n for n in STANDARD if '_socp_' in n or n.startswith('network_lp')]     # conic families (IPM-CUDA)
+MATPAR_NAMES: List[str] = ['mpc_ltv_6_3_10', 'mpc_ltv_12_4_10', 'mpc_ref_6_3_10', 'actuator_1_3', 'nonneg_LS_3_2_A']
 QP_NAMES: List[str] = [n for n in STANDARD if n not in SOCP_NAMES and n not in MATPAR_NAMES]
 
 

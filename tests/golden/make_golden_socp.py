@@ -52,3 +52,16 @@ out = r.solve_batch(c=Cb, h=Hb)
 np.savez_compressed(os.path.join(HERE, f'socp_{fam.name}.npz'), **{'param_' + k: v for k, v in par.items()},
                     x=out['x'], y=out['y'], z=out['z'], s=out['s'], pcost=out['pcost'], iter=out['iter'], exitflag=out['exitflag'])
 print(fam.name, 'flags', np.unique(out['exitflag'], return_counts=True), 'iters', out['iter'].mean())
+
+# ---- the reference's SOCP test problem (tests/test_E2E_SOCP.py:15-63, ADP step): four second-order cones, no LP cone, no equalities
+fam = families.adp_socp()
+rng = np.random.default_rng(2026)
+fb = fam.param('f').default[None, :] + 0.5 * rng.standard_normal((48, 6))
+th = np.tile(fam.theta_default(), (48, 1)); p = fam.param('f'); th[:, p.col:p.col + p.size] = fb
+Hb = np.asarray(th @ fam.maps['h'].T.toarray())
+r = RefECOS(fam.canon_data('c'), fam.canon_matrix('A'), fam.canon_data('b'), fam.canon_matrix('G'), fam.canon_data('h'),
+            fam.cone_dims['l'], fam.cone_dims['q'])
+out = r.solve_batch(h=Hb)
+np.savez_compressed(os.path.join(HERE, f'socp_{fam.name}.npz'), param_f=fb,
+                    x=out['x'], y=out['y'], z=out['z'], s=out['s'], pcost=out['pcost'], iter=out['iter'], exitflag=out['exitflag'])
+print(fam.name, 'flags', np.unique(out['exitflag'], return_counts=True), 'iters', out['iter'].mean())

@@ -238,6 +238,61 @@ def test_gpu_shared_parameter_update_on_matrix_family():
         assert rel_err(res.sol_x, ora['x']).max() < 1e-7
 
 
+@pytest.mark.skipif(not ref_available(), reason='oracle/_ref not built')
+def test_reference_actuator_problem_oracles_agree():
+    """The reference's "degenerate vectors and matrices" test problem (tests/test_E2E_QP.py:16-41): one actuator, a 1 x 1
+    matrix variable, scalar parameters; lamb_sm enters P and A enters the constraint matrix (osqp_update_P_A branch)."""
+    fam = families.actuator()
+    B = 32
+    params = families.actuator_batch(fam, B, seed=1)
+    Px, Ax, (q, l, u) = canon_matrix_batches(fam, params, B)
+    ref = matrix_oracle_solve(fam, Px, Ax, q, l, u)
+    npy = matrix_oracle_solve(fam, Px, Ax, q, l, u, prefer_ref=False)
+    assert np.array_equal(ref['iter'], npy['iter']) and (ref['status'] == 1).all()
+    assert np.abs(ref['x'] - npy['x']).max() < 1e-7
+    tight = matrix_oracle_solve(fam, Px, Ax, q, l, u, eps_abs=1e-10, eps_rel=1e-10, max_iter=100000)
+    uu = tight['x'][:, 0]
+    obj = ((params['A'] * uu[:, None] - params['w']) ** 2).sum(1) + params['lamb_sm'][:, 0] * (uu - params['u_prev'][:, 0]) ** 2 \
+        + params['kappa'][:, 0] * np.abs(uu)
+    assert np.allclose(obj, tight['obj'], rtol=1e-8, atol=1e-9)
+    st = setup_qp_family(fam, standard.STANDARD['actuator_1_3'][1])
+    assert st.mat_params == ['A', 'lamb_sm']
+
+
+@pytest.mark.gpu
+def test_gpu_reference_actuator_problem():
+    name, B = 'actuator_1_3', 2000
+    fam = standard.STANDARD[name][0]()
+    params = families.actuator_batch(fam, B, seed=2)
+    mod = standard.load(name, device=0)
+    res = mod.solve_batch(params, return_canonical=True)
+    Px, Ax, (q, l, u) = canon_matrix_batches(fam, params, B)
+    ora = matrix_oracle_solve(fam, Px, Ax, q, l, u)
+    assert np.array_equal(res.cpg_info.status, ora['status']) and np.array_equal(res.cpg_info.iter, ora['iter'])
+    ok = ora['status'] == 1
+    assert ok.mean() > 0.99 and np.abs(res.sol_x[ok] - ora['x'][ok]).max() < 1e-7 and np.abs(res.sol_y[ok] - ora['y'][ok]).max() < 1e-6
+    assert res.cpg_prim['u'].shape == (B, 1) and res.cpg_prim['delta_u'].shape == (B, 1, 1)
+    assert np.abs(res.cpg_prim['delta_u'][:, 0, 0] - (res.cpg_prim['u'][:, 0] - params['u_prev'][:, 0]))[ok].max() < 1e-2
+    # backward pass with P AND A per instance: d/dtheta of u against the numpy restatement
+    dprim = np.zeros((B, 2)); dprim[:, 0] = 1.0
+    g = mod.gradient_batch_mat(params, res.sol_x, res.sol_y, dprim)
+    nchk = 64
+    dx = np.zeros((nchk, fam.n_var)); dx[:, 0] = 1.0
+    dq, dl, du, dP, dA = qp_backward_mat(fam.patterns['P'], fam.patterns['A'], Px[:nchk], Ax[:nchk], res.sol_x[:nchk], res.sol_y[:nchk], dx)
+    names = standard.STANDARD[name][1]
+    want = param_gradient_mat(fam, dq, dl, du, dP, dA, names)
+    got = np.concatenate([g[nm][:nchk] for nm in names], axis=1)
+    # u = 0 makes BOTH rows of |u| <= t active: K is then singular up to the 1e-6 regularisation and the answer depends on the
+    # factorisation at the 1e-4 level (LDL' on the symbolic pattern here, pivoted LU in the restatement, up/down-dated LDL' in
+    # the reference) -- those instances get the looser bar
+    y = res.sol_y[:nchk]
+    degenerate = (np.abs(y[:, 5]) > 1e-12) & (np.abs(y[:, 6]) > 1e-12)
+    assert (~degenerate).mean() > 0.7
+    scale = max(1.0, np.abs(want).max())
+    assert np.abs(got - want)[~degenerate].max() < 1e-6 * scale
+    assert np.abs(got - want).max() < 1e-3 * scale
+
+
 @pytest.mark.gpu
 def test_gpu_matrix_parameters_reduce_to_shared_family():
     """With every instance carrying the DEFAULT matrices the matrix-parameter kernel must reproduce the shared-matrix

@@ -261,6 +261,39 @@ def test_reference_network_lp_on_host_matches_golden(tmp_path):
     assert np.array_equal(out['prim'][:, :50], out['x']) and np.array_equal(out['dual'][:, :110], out['z'])
 
 
+def test_reference_adp_socp_on_host_matches_golden(tmp_path):
+    """The reference's SOCP test problem (tests/test_E2E_SOCP.py:15-63, one ADP step): two squared norms as rotated cones and
+    two input-norm bounds -- four second-order cones, NO LP cone, no equalities -- with `f` per instance."""
+    fam = families.adp_socp()
+    g = np.load(os.path.join(GOLDEN, 'socp_adp_socp_6_3.npz'))
+    st = ss.setup_socp_family(fam, ['f'])
+    assert (st.defines['NSOC'], st.defines['P'], st.defines['L']) == (4, 0, 0)
+    lib = _build_emu(st, str(tmp_path))
+    B = 24
+    out = _emu_solve(lib, st, g['param_f'][:B])
+    assert np.array_equal(out['status'], g['exitflag'][:B]) and np.array_equal(out['iter'], g['iter'][:B])
+    for k in range(B):
+        assert _rel(out['x'][k], g['x'][k]) < 1e-6 and _rel(out['s'][k], g['s'][k]) < 1e-6
+    assert np.allclose(out['obj'], g['pcost'][:B], rtol=1e-7)
+    # the user-level problem: u = first six canonical variables (2 x 3, Fortran order); objective = the two squared norms
+    u0 = out['x'][:, 0:6:2]
+    G = fam.param('G').default.reshape(6, 3, order='F'); Rs = fam.param('Rsqrt').default
+    obj = ((g['param_f'][:B] + u0 @ G.T) ** 2).sum(1) + ((Rs * u0) ** 2).sum(1)
+    assert np.allclose(obj, out['obj'], rtol=1e-5, atol=1e-7)
+    assert np.linalg.norm(u0, axis=1).max() <= 0.1 + 1e-7 and np.linalg.norm(out['x'][:, 1:6:2], axis=1).max() <= 0.1 + 1e-7
+
+
+@pytest.mark.gpu
+def test_gpu_reference_adp_socp():
+    g = np.load(os.path.join(GOLDEN, 'socp_adp_socp_6_3.npz'))
+    m = standard.load('adp_socp_6_3')
+    r = m.solve_batch({'f': g['param_f']}, return_canonical=True)
+    assert np.array_equal(r.cpg_info.status, g['exitflag']) and np.array_equal(r.cpg_info.iter, g['iter'])
+    assert _rel(r.sol_x, g['x']) < 1e-6 and _rel(r.sol_s, g['s']) < 1e-6
+    assert np.allclose(r.cpg_info.obj_val, g['pcost'], rtol=1e-7)
+    assert r.cpg_prim['u'].shape == (len(g['iter']), 2, 3) and np.array_equal(r.cpg_prim['u'][:, 0, :], r.sol_x[:, 0:6:2])
+
+
 @pytest.mark.gpu
 def test_gpu_reference_network_lp():
     fam = families.network_lp(50, 10)
