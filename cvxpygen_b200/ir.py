@@ -119,7 +119,40 @@ class CanonFamily:
         """canonical ids touched by one user parameter (adjacency, cvxpygen/canonicalizer.py:117-120)."""
         return [k for k in self.maps if self.changes(k, [name])]
 
-    # ---- bridge from the reference's own canonicaliser (needs cvxpy; untested here) ----
+    # ---- a family straight from canonical QP data (no modelling layer at all) -----------------------------------
+    @classmethod
+    def from_canonical_qp(cls, name, P, q, A, l, u, n_eq=None, matrix_params=False) -> 'CanonFamily':
+        """min 1/2 x'Px + q'x  s.t.  l <= Ax <= u  with the canonical vectors themselves as user parameters ``q``, ``l``,
+        ``u`` (and, with ``matrix_params``, the stored entries of ``P`` (upper triangle) and ``A`` in CSC order as ``P``,
+        ``A``): the identity maps the reference would emit for a problem whose parameters ARE its canonical data.
+        Structural zeros of P / A stay in the pattern.  Variables: ``x``; duals: ``y``."""
+        P = sp.triu(sp.csc_matrix(P), format='csc'); P.sort_indices()
+        A = sp.csc_matrix(A); A.sort_indices()
+        n, m = P.shape[0], A.shape[0]
+        q = np.asarray(q, dtype=float).ravel(); l = np.asarray(l, dtype=float).ravel(); u = np.asarray(u, dtype=float).ravel()
+        specs = [('q', (n,), q), ('l', (m,), l), ('u', (m,), u)]
+        if matrix_params:
+            specs += [('P', (P.nnz,), P.data), ('A', (A.nnz,), A.data)]
+        params, col = [], 0
+        for nm, shape, default in specs:
+            params.append(UserParam(nm, tuple(shape), int(np.asarray(default).size), col, np.array(default, dtype=float)))
+            col += params[-1].size
+        n_theta = col + 1
+        ident = lambda size, c0: sp.csr_matrix((np.ones(size), (np.arange(size), c0 + np.arange(size))), shape=(size, n_theta))
+        const = lambda v: sp.csr_matrix((np.asarray(v, dtype=float), (np.arange(len(v)), np.full(len(v), n_theta - 1))),
+                                        shape=(len(v), n_theta))
+        pc = {p.name: p.col for p in params}
+        maps = {'q': ident(n, pc['q']), 'l': ident(m, pc['l']), 'u': ident(m, pc['u']), 'd': sp.csr_matrix((1, n_theta)),
+                'P': ident(P.nnz, pc['P']) if matrix_params else const(P.data),
+                'A': ident(A.nnz, pc['A']) if matrix_params else const(A.data)}
+        if n_eq is None:
+            n_eq = int(np.sum(l == u))
+        pat = lambda M: (M.indices.astype(np.int32), M.indptr.astype(np.int32), M.shape)
+        return cls(name, 'quadratic', n, n_eq, m - n_eq, params, maps, {'P': pat(P), 'A': pat(A)},
+                   [UserVar('x', (n,), np.arange(n))], [UserDual('y', 'y', (m,), np.arange(m))])
+
+    # ---- bridge from the reference's own canonicaliser (exercised on the reference's dataclasses in tests/test_reference_bridge.py;
+    #      the cvxpy-driven end of it cannot run in this image) ----
     @classmethod
     def from_reference_canon(cls, name, canon, solver_interface) -> 'CanonFamily':
         """Build the IR from (Canon, SolverInterface) as returned by the reference's

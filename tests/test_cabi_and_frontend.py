@@ -113,3 +113,26 @@ def test_generate_code_argument_errors():
 def test_standard_families_are_built_or_buildable():
     d = standard.build('nonneg_LS_3_2')
     assert os.path.exists(os.path.join(d, 'libcpg_b200.so'))
+
+
+def test_family_from_canonical_qp_data():
+    """CanonFamily.from_canonical_qp: OSQP's own basic_qp (osqp_sources/tests/basic_qp/generate_problem.py) as a family whose
+    parameters are its canonical vectors -- and, with matrix_params, its matrix entries; the offline setup accepts both."""
+    import scipy.sparse as sp
+    from cvxpygen_b200.ir import CanonFamily
+    from cvxpygen_b200.offline.qp_setup import setup_qp_family
+    from oracle.admm_numpy import AdmmOracle
+    P = sp.csc_matrix([[4.0, 1.0], [1.0, 2.0]]); q = np.array([1.0, 1.0])
+    A = sp.csc_matrix([[1.0, 1.0], [1.0, 0.0], [0.0, 1.0], [0.0, 1.0]])
+    l = np.array([1.0, 0.0, 0.0, -np.inf]); u = np.array([1.0, 0.7, 0.7, np.inf])
+    fam = CanonFamily.from_canonical_qp('basic_qp', P, q, A, np.clip(l, -1e30, 1e30), np.clip(u, -1e30, 1e30))
+    assert [p.name for p in fam.params] == ['q', 'l', 'u'] and fam.n_eq == 1
+    assert np.array_equal(fam.canon_data('q'), q) and fam.canon_matrix('P').nnz == 3
+    st = setup_qp_family(fam, ['q', 'l', 'u'])
+    assert st.npb == 2 + 4 + 4 and not st.mat_params
+    fam2 = CanonFamily.from_canonical_qp('basic_qp_m', P, q, A, np.clip(l, -1e30, 1e30), np.clip(u, -1e30, 1e30), matrix_params=True)
+    st2 = setup_qp_family(fam2, ['q', 'l', 'u', 'P', 'A'])
+    assert st2.mat_params == ['P', 'A'] and len(st2.mat_blob) > 0
+    sol = AdmmOracle(fam.canon_matrix('P'), q, fam.canon_matrix('A'), fam.canon_data('l'), fam.canon_data('u'),
+                     eps_abs=1e-9, eps_rel=1e-9).solve_batch(B=1)
+    assert np.allclose(sol['x'][0], [0.3, 0.7], atol=1e-6) and abs(sol['obj'][0] - 1.88) < 1e-6      # OSQP's known answer
