@@ -115,6 +115,35 @@ def test_generated_library_exports_matrix_entry():
     assert '#define CPG_FAM_MATPAR 1' in hdr
 
 
+def test_pack_params_matrix_layouts():
+    """Host side of the batched call for matrix parameters: per-instance matrices are flattened in Fortran order (reference
+    TPL/cpg_solver.py.jinja2:26-34), one value broadcasts over the batch, sparse / diagonal parameters are passed as their
+    stored entries, missing parameters take their defaults."""
+    from cvxpygen_b200 import runtime
+    mod = runtime.load(standard.build('mpc_ltv_6_3_10'), 0)            # no device needed for packing
+    fam = standard.STANDARD['mpc_ltv_6_3_10'][0]()
+    B = 5
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((B, 6, 6)); Bm = rng.standard_normal((6, 3)); xi = rng.standard_normal((B, 6))
+    rows = mod.pack_params({'A': A, 'B': Bm, 'x_init': xi})
+    assert rows.shape == (B, mod.dims.n_param) == (B, 36 + 18 + 6 + 3 + 6)
+    cols = {p.name: (p.col, p.size) for p in fam.params}
+    off = lambda nm: sum(fam.param(x).size for x in standard.STANDARD['mpc_ltv_6_3_10'][1][:standard.STANDARD['mpc_ltv_6_3_10'][1].index(nm)])
+    for b in range(B):
+        assert np.array_equal(rows[b, off('A'):off('A') + 36], A[b].flatten(order='F'))
+        assert np.array_equal(rows[b, off('B'):off('B') + 18], Bm.flatten(order='F'))            # broadcast
+        assert np.array_equal(rows[b, off('qdiag'):off('qdiag') + 6], fam.param('qdiag').default)   # default
+        assert np.array_equal(rows[b, off('x_init'):off('x_init') + 6], xi[b])
+    with pytest.raises(AttributeError):
+        mod.pack_params({'nope': xi})
+    with pytest.raises(ValueError):
+        mod.pack_params({'A': A, 'x_init': xi[:3]})
+    ref = runtime.load(standard.build('mpc_ref_6_3_10'), 0)
+    r2 = ref.pack_params({'Qsqrt': np.full((B, 6), 2.0), 'A': np.arange(9.0)})      # stored entries of the diagonal / sparse parameters
+    assert r2.shape == (B, 6 + 6 + 3 + 9 + 3 + 6) and np.array_equal(r2[:, 6:12], np.full((B, 6), 2.0))
+    assert np.array_equal(r2[0, 15:24], np.arange(9.0))
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize('name,B', [('mpc_ltv_6_3_10', 300), ('mpc_ltv_12_4_10', 200)])
