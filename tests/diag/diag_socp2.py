@@ -2,8 +2,8 @@
 """Diagnostic: instances of the config-3 batch whose exit flag is not 0 on the GPU; saves them with the reference's answer."""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'tests'))
 import torch
 from cvxpygen_b200 import standard, families
 from oracle import ref_ecos
