@@ -59,11 +59,16 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.rows = index, threading.Event(), []
+        self.active = threading.Event()           # samples are taken only while a timed region is running
+        self.active.set()
 
     def run(self):
         q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
         while not self.stop_flag.is_set():
+            if not self.active.is_set():
+                self.stop_flag.wait(0.02)
+                continue
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={q}', '--format=csv,noheader,nounits'],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -196,7 +201,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler.stop_flag.set(); sampler.join()
+    sampler.active.clear()
     ms_total = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -217,10 +222,12 @@ def main():
             mod.solve_batch_pinned(hp, hout)
         if world > 1:
             dist.barrier()
+        sampler.active.set()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             mod.solve_batch_pinned(hp, hout)
         t1 = time.perf_counter()
+        sampler.active.clear()
         te = torch.tensor([(t1 - t0) / e2e_steps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -231,6 +238,7 @@ def main():
     mod.set_solver_setting('host_zero_copy', 0)
     e2e_staged = time_e2e()
     mod.set_solver_setting('host_zero_copy', 1)
+    sampler.stop_flag.set(); sampler.join()         # clocks sampled over both timed regions (device-resident and end-to-end)
     h2d = B * 12 * 8
     d2h = B * ((d.n_prim + d.n_dual) * 8 + 3 * 8 + 2 * 4)
 
@@ -379,7 +387,7 @@ def main_socp(args, rank, world, local_rank, W, K, cores):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler.stop_flag.set(); sampler.join()
+    sampler.active.clear()
     t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -392,10 +400,12 @@ def main_socp(args, rank, world, local_rank, W, K, cores):
                 it=pin((B,), torch.int32), st=pin((B,), torch.int32))
     mod.solve_batch_pinned(hp, hout)
     e2e_steps = 2
+    sampler.active.set()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         mod.solve_batch_pinned(hp, hout)
     te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    sampler.stop_flag.set(); sampler.join()         # clocks sampled over both timed regions
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     st = out.status.cpu().numpy(); it = out.iter.cpu().numpy()
@@ -522,7 +532,7 @@ def main_ltv(args, rank, world, local_rank, W, K, cores):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler.stop_flag.set(); sampler.join()
+    sampler.active.clear()
     t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -535,10 +545,12 @@ def main_ltv(args, rank, world, local_rank, W, K, cores):
                 it=pin((B,), torch.int32), st=pin((B,), torch.int32))
     mod.solve_batch_pinned(hp, hout)
     e2e_steps = 3
+    sampler.active.set()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         mod.solve_batch_pinned(hp, hout)
     te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    sampler.stop_flag.set(); sampler.join()         # clocks sampled over both timed regions
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     st = out.status.cpu().numpy(); it = out.iter.cpu().numpy()
