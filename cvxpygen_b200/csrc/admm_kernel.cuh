@@ -66,6 +66,13 @@ struct BatchIO {
 };
 
 // ---------------------------------------------------------------- TMA bulk copy + mbarrier helpers
+#ifdef CPG_SIMT_HOST_EMU
+// host build of the test suite (tests/emu/simt): the staging copy is a memcpy by the issuing thread, the wait a block barrier
+__device__ __forceinline__ void mbar_init(uint64_t*, int) {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t*) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) { __syncthreads(); }
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -85,6 +92,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+#endif
 
 // ---------------------------------------------------------------- warp reductions
 __device__ __forceinline__ double warp_max(double v) {

@@ -1,0 +1,152 @@
+"""The warp-per-instance CUDA kernels, run on the CPU.
+
+tests/emu/simt/cuda_runtime.h is a small SIMT emulator (every CUDA thread a fiber, switches at the warp / block
+synchronisation points); tests/emu/admm_emu.cpp builds the PRODUCT kernel sources of one generated family against it
+-- admm_matpar_kernel (per-instance matrices), admm_tail_kernel (per-instance factor), qp_grad_kernel (backward pass).
+The lane-level logic of these kernels (shuffle sweeps, table-driven factorisation, gather tables, in-warp equilibration)
+is thereby checked against the oracle in the CPU-only suite, before any GPU time is spent; the GPU tests
+(tests/test_matpar.py, tests/test_gpu_parity.py, tests/test_grad.py) remain the parity tests proper."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from cvxpygen_b200 import codegen, families
+from cvxpygen_b200.offline.qp_setup import setup_qp_family
+from helpers import canon_batches, canon_matrix_batches, matrix_oracle_solve, oracle_solve, rel_err
+from oracle.grad_numpy import qp_backward, qp_backward_mat, param_gradient, param_gradient_mat
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build_emu(fam, batch, out_dir):
+    st = setup_qp_family(fam, batch)
+    codegen.write_code(st, out_dir)
+    inc, sol, src = (os.path.join(out_dir, 'c', d) for d in ('include', 'solver_code', 'src'))
+    so = os.path.join(out_dir, 'libadmm_emu.so')
+    cmd = ['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-DCPG_SIMT_HOST_EMU', '-w', '-ffp-contract=off',
+           '-I', os.path.join(HERE, 'emu', 'simt'), '-I', inc, '-I', sol, os.path.join(HERE, 'emu', 'admm_emu.cpp'),
+           '-x', 'c', os.path.join(src, 'cpg_blob.c'), '-o', so]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    lib = C.CDLL(so)
+    dims = (C.c_int * 6)()
+    lib.emu_dims(dims)
+    return st, lib, list(dims)
+
+
+def _ptr(a, t=C.c_double):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def run_solve(lib, fn, dims, rows, grid=2, adaptive_rho_interval=0, eps=1e-3):
+    n, m, npb, n_prim, n_dual, _ = dims
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    B = rows.shape[0]
+    out = dict(prim=np.zeros((B, n_prim)), dual=np.zeros((B, n_dual)), x=np.zeros((B, n)), y=np.zeros((B, m)), obj=np.zeros(B),
+               iter=np.zeros(B, np.int32), status=np.zeros(B, np.int32), pri=np.zeros(B), dua=np.zeros(B))
+    rc = getattr(lib, fn)(C.c_int(B), _ptr(rows), _ptr(out['prim']), _ptr(out['dual']), _ptr(out['x']), _ptr(out['y']),
+                          _ptr(out['obj']), _ptr(out['iter'], C.c_int), _ptr(out['status'], C.c_int), _ptr(out['pri']),
+                          _ptr(out['dua']), C.c_int(grid), C.c_int(adaptive_rho_interval), C.c_double(eps))
+    assert rc == 0
+    return out
+
+
+def _rows(fam, st, params, B):
+    th = np.tile(fam.theta_default(), (B, 1))
+    for pn, v in params.items():
+        p = fam.param(pn)
+        th[:, p.col:p.col + p.size] = v
+    return th[:, st.batch_cols]
+
+
+def test_matrix_parameter_kernel_on_the_emulator(tmp_path):
+    """admm_matpar_kernel end to end (canonicalise, equilibrate, assemble, factor, ADMM with a rho update) for a small LTV MPC
+    family, 7 instances over 2 blocks x 8 warps, against the reference / the numpy restatement of osqp_update_P_A + solve."""
+    fam = families.mpc_ltv(4, 2, 5)
+    batch = ['A', 'B', 'qdiag', 'rdiag', 'x_init']
+    st, lib, dims = build_emu(fam, batch, str(tmp_path))
+    assert dims[5] == 1
+    B = 7
+    params = families.mpc_ltv_batch(fam, B, seed=3)
+    out = run_solve(lib, 'emu_matpar_solve', dims, _rows(fam, st, params, B))
+    Px, Ax, (q, l, u) = canon_matrix_batches(fam, params, B)
+    ora = matrix_oracle_solve(fam, Px, Ax, q, l, u)
+    assert np.array_equal(out['iter'], ora['iter']) and np.array_equal(out['status'], ora['status'])
+    assert rel_err(out['x'], ora['x']).max() < 1e-9 and rel_err(out['y'], ora['y']).max() < 1e-9
+    assert np.allclose(out['obj'], ora['obj'], rtol=1e-9) and np.allclose(out['pri'], ora['pri_res'], rtol=1e-6, atol=1e-12)
+    prim_idx = np.concatenate([v.indices for v in fam.variables])
+    assert np.array_equal(out['prim'], out['x'][:, prim_idx])
+    # tighter tolerance + rho adaptation every 25 iterations: in-place re-factorisations of the per-instance K
+    kw = dict(adaptive_rho_interval=25, eps_abs=1e-6, eps_rel=1e-6)
+    out2 = run_solve(lib, 'emu_matpar_solve', dims, _rows(fam, st, params, B), adaptive_rho_interval=25, eps=1e-6)
+    ora2 = matrix_oracle_solve(fam, Px, Ax, q, l, u, **kw)
+    assert ora2['rho_updates'].sum() > 0
+    assert np.array_equal(out2['iter'], ora2['iter']) and rel_err(out2['x'], ora2['x']).max() < 1e-8
+
+
+def test_tail_kernel_on_the_emulator(tmp_path):
+    """admm_tail_kernel: every instance queued at iteration 0 (the route of a constraint-type change), so the kernel factors
+    K numerically on the symbolic pattern (dense-group packed triangles included) and runs the whole ADMM loop on it."""
+    fam = families.mpc(4, 2, 6)
+    st, lib, dims = build_emu(fam, ['x_init'], str(tmp_path))
+    B = 6
+    xi = np.random.default_rng(4).uniform(-1, 1, (B, 4))
+    q, l, u = canon_batches(fam, {'x_init': xi}, B)
+    for kw, ari, eps in ((dict(), 0, 1e-3), (dict(adaptive_rho_interval=25, eps_abs=1e-6, eps_rel=1e-6), 25, 1e-6)):
+        out = run_solve(lib, 'emu_tail_solve', dims, xi, adaptive_rho_interval=ari, eps=eps)
+        ora = oracle_solve(fam, q, l, u, **kw)
+        assert np.array_equal(out['iter'], ora['iter']) and np.array_equal(out['status'], ora['status'])
+        assert rel_err(out['x'], ora['x']).max() < 1e-9 and rel_err(out['y'], ora['y']).max() < 1e-9
+
+
+def _run_grad(lib, dims, rows, sol_x, sol_y, dprim, nnzP=0, nnzA=0, grid=2):
+    n, m, npb, n_prim, n_dual, matpar = dims
+    B = sol_y.shape[0]
+    c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+    rows, sol_x, sol_y, dprim = c(rows), c(sol_x), c(sol_y), c(dprim)
+    out = dict(dparams=np.zeros((B, max(npb, 1))), dq=np.zeros((B, n)), dl=np.zeros((B, m)), du=np.zeros((B, m)),
+               dP=np.zeros((B, max(nnzP, 1))), dA=np.zeros((B, max(nnzA, 1))))
+    rc = lib.emu_gradient(C.c_int(B), _ptr(rows), _ptr(sol_x), _ptr(sol_y), _ptr(dprim), _ptr(out['dparams']), _ptr(out['dq']),
+                          _ptr(out['dl']), _ptr(out['du']), _ptr(out['dP']) if matpar else None, _ptr(out['dA']) if matpar else None,
+                          C.c_int(grid))
+    assert rc == 0
+    return out
+
+
+def test_backward_kernels_on_the_emulator(tmp_path):
+    """qp_grad_kernel (shared matrices) and qp_grad_kernel<Fam, true> (per-instance matrices, dP / dA folded into dtheta)
+    against the numpy restatement of the reference's cpg_osqp_gradient."""
+    # shared matrices
+    fam = families.mpc(4, 2, 6)
+    st, lib, dims = build_emu(fam, ['x_init'], str(tmp_path / 'a'))
+    B = 5
+    xi = np.random.default_rng(6).uniform(-1, 1, (B, 4))
+    q, l, u = canon_batches(fam, {'x_init': xi}, B)
+    sol = oracle_solve(fam, q, l, u, eps_abs=1e-8, eps_rel=1e-8)
+    prim_idx = np.concatenate([v.indices for v in fam.variables])
+    dprim = np.random.default_rng(7).standard_normal((B, len(prim_idx)))
+    dx = np.zeros((B, fam.n_var)); dx[:, prim_idx] = dprim
+    got = _run_grad(lib, dims, None, None, sol['y'], dprim)
+    dq, dl, du, _ = qp_backward(fam.canon_matrix('P'), fam.canon_matrix('A'), sol['x'], sol['y'], dx)
+    assert np.abs(got['dq'] - dq).max() < 1e-7 * np.abs(dq).max() and np.abs(got['dl'] + got['du'] - dl - du).max() < 1e-7 * np.abs(dl + du).max()
+    want = param_gradient(fam, dq, dl, du, ['x_init'])
+    assert np.abs(got['dparams'][:, :4] - want).max() < 1e-7 * np.abs(want).max()
+    # per-instance matrices
+    fam = families.mpc_ltv(4, 2, 5)
+    batch = ['A', 'B', 'qdiag', 'rdiag', 'x_init']
+    st, lib, dims = build_emu(fam, batch, str(tmp_path / 'b'))
+    params = families.mpc_ltv_batch(fam, B, seed=8)
+    Px, Ax, (q, l, u) = canon_matrix_batches(fam, params, B)
+    sol = matrix_oracle_solve(fam, Px, Ax, q, l, u, eps_abs=1e-8, eps_rel=1e-8)
+    prim_idx = np.concatenate([v.indices for v in fam.variables])
+    dprim = np.random.default_rng(9).standard_normal((B, len(prim_idx)))
+    dx = np.zeros((B, fam.n_var)); dx[:, prim_idx] = dprim
+    got = _run_grad(lib, dims, _rows(fam, st, params, B), sol['x'], sol['y'], dprim, nnzP=Px.shape[1], nnzA=Ax.shape[1])
+    dq, dl, du, dP, dA = qp_backward_mat(fam.patterns['P'], fam.patterns['A'], Px, Ax, sol['x'], sol['y'], dx)
+    for k, ref in (('dq', dq), ('dP', dP), ('dA', dA)):
+        assert np.abs(got[k] - ref).max() < 1e-7 * max(np.abs(ref).max(), 1e-30), k
+    want = param_gradient_mat(fam, dq, dl, du, dP, dA, batch)
+    assert np.abs(got['dparams'] - want).max() < 1e-7 * np.abs(want).max()
