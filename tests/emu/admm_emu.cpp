@@ -8,7 +8,7 @@
 #include "cpg_family.h"
 #include "cpg_b200.h"
 #include "cpg_blob_layout.h"
-#include "admm_kernel.cuh"
+#include "admm_multi_kernel.cuh"
 #include "grad_kernel.cuh"
 #if CPG_FAM_MATPAR
 #include "matpar_kernel.cuh"
@@ -26,6 +26,8 @@ namespace cpgb200 { alignas(128) uint8_t smem[256 * 1024]; }
 namespace {
 struct Fam {
   static constexpr int N = CPG_FAM_N, M = CPG_FAM_M;
+  static constexpr int TRAIL = CPG_FAM_TRAIL_TILES, WARPS = CPG_FAM_WARPS, NI = CPG_FAM_NI, MULTI_STRIDE = CPG_FAM_MULTI_STRIDE;
+  static constexpr int BLOB_BYTES_PAD = CPG_FAM_BLOB_BYTES_PAD;
   static constexpr int CBLOB_BYTES_PAD = CPG_FAM_CBLOB_BYTES_PAD;
   static constexpr int W_STRIDE = CPG_FAM_W_STRIDE, S_STRIDE = CPG_FAM_S_STRIDE;
   static constexpr int TAIL_WARPS = CPG_FAM_TAIL_WARPS;
@@ -76,6 +78,32 @@ int emu_matpar_solve(int B, const double* params, double* prim, double* dual, do
 #else
   return 1;
 #endif
+}
+
+// The two launches of cpg_solve_batch_device for shared-matrix families: admm_multi_kernel (NI instances per warp, generated
+// straight-line KKT solve, lockstep CTA) and then admm_tail_kernel on whatever it handed off (rho updates, type changes)
+int emu_main_solve(int B, const double* params, double* prim, double* dual, double* sol_x, double* sol_y, double* obj,
+                   int* iter, int* status, double* pri, double* dua, int grid, int adaptive_rho_interval, double eps) {
+  constexpr int WORDS = Fam::N + 2 * Fam::M + 2;
+  std::vector<double> state((size_t)B * WORDS, 0.0);
+  std::vector<int> ids(B);
+  int count = 0;
+  unsigned counter = 0;
+  cpgb200::BatchIO io;
+  memset(&io, 0, sizeof(io));
+  io.params = params; io.prim = prim; io.dual = dual; io.sol_x = sol_x; io.sol_y = sol_y; io.obj_val = obj; io.iter = iter;
+  io.status = status; io.pri_res = pri; io.dua_res = dua; io.B = B; io.work_counter = &counter;
+  io.tail_count = &count; io.tail_ids = ids.data(); io.tail_state = state.data(); io.tail_capacity = B;
+  const cpgb200::Settings st = default_settings(adaptive_rho_interval, eps);
+  simt::launch(grid, Fam::WARPS * 32, [&] {
+    cpgb200::admm_multi_kernel<Fam>(reinterpret_cast<const uint8_t*>(CPG_B200_FN(cpg_blob_words)), io, st);
+  });
+  const int handed_off = count;
+  simt::launch(grid, Fam::TAIL_WARPS * 32, [&] {
+    cpgb200::admm_tail_kernel<Fam>(reinterpret_cast<const uint8_t*>(CPG_B200_FN(cpg_cblob_words)),
+                                   reinterpret_cast<const uint8_t*>(CPG_B200_FN(cpg_tail_blob_words)), io, st);
+  });
+  return handed_off;
 }
 
 // admm_tail_kernel: every instance is queued at iteration 0 with the family's rho (the route an instance whose bounds

@@ -35,6 +35,8 @@ struct ushort2 { unsigned short x, y; };
 struct ushort4 { unsigned short x, y, z, w; };
 struct int4 { int x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
+struct alignas(16) double2 { double x, y; };
+inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 typedef void* cudaStream_t;
 
 namespace simt {
