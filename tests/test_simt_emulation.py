@@ -112,6 +112,32 @@ def test_main_kernel_on_the_emulator(tmp_path):
     assert np.array_equal(out2['iter'], ora2['iter']) and rel_err(out2['x'], ora2['x']).max() < 1e-8
 
 
+@pytest.mark.parametrize('name,B', [('nonneg_LS_3_2', 40), ('box_qp_6_8', 96), ('random_qp_20_5_15', 24)])
+def test_standard_families_on_the_emulator(name, B, tmp_path):
+    """Main + tail kernels of the small standard families: unstructured sparsity with q, l, u all batched; box_qp's corner
+    cases -- bounds that change a constraint's type (hand-off at iteration 0), primal and dual infeasibility certificates,
+    no-solution statuses with NaN solutions and +-1e30 objectives."""
+    from cvxpygen_b200 import standard
+    from helpers import family_and_batch, assert_batch_parity, rounding_stable
+    from types import SimpleNamespace
+    fam, params, (q, l, u) = family_and_batch(name, B, seed=12)
+    if name == 'box_qp_6_8':            # regular / equality-collapsed / loose rows, primal infeasible, dual infeasible
+        from test_gpu_parity import corner_case_batch
+        params, kind = corner_case_batch(fam, B)
+        q, l, u = canon_batches(fam, params, B)
+    batch = standard.STANDARD[name][1]
+    st, lib, dims = build_emu(fam, batch, str(tmp_path))
+    out = run_solve(lib, 'emu_main_solve', dims, _rows(fam, st, params, B), grid=2)
+    ora = oracle_solve(fam, q, l, u)
+    info = SimpleNamespace(status=out['status'], iter=out['iter'], obj_val=out['obj'], pri_res=out['pri'], dua_res=out['dua'])
+    stable = rounding_stable(fam, q, l, u, ora) if name == 'box_qp_6_8' else None
+    assert_batch_parity(out['x'], out['y'], info, ora, 1e-8, stable=stable)
+    if name == 'box_qp_6_8':
+        assert out['rc'] > 0                                             # some instances went through the tail kernel
+        assert set(np.unique(ora['status'])) >= {1, -3, -4} and np.array_equal(out['status'], ora['status'])
+        assert (out['obj'][kind == 3] == 1e30).all() and (out['obj'][kind == 4] == -1e30).all()
+
+
 def test_tail_kernel_on_the_emulator(tmp_path):
     """admm_tail_kernel: every instance queued at iteration 0 (the route of a constraint-type change), so the kernel factors
     K numerically on the symbolic pattern (dense-group packed triangles included) and runs the whole ADMM loop on it."""
