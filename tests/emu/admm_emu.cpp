@@ -52,6 +52,8 @@ cpgb200::Settings default_settings(int adaptive_rho_interval, double eps) {
 
 extern "C" {
 
+void emu_set_schedule(int mode) { simt::rt().schedule = mode; }
+
 int emu_dims(int* out) {   // n, m, npb, n_prim, n_dual, matpar
   const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words));
   out[0] = H->n; out[1] = H->m; out[2] = H->npb; out[3] = H->n_prim; out[4] = H->n_dual; out[5] = CPG_FAM_MATPAR;

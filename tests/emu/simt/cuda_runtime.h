@@ -8,7 +8,7 @@
 // between two barriers -- is executed exactly as written.  Arithmetic is IEEE double with std::fma, i.e. the results are
 // those of the GPU up to the order of floating-point atomics.  Blocks run one after the other.
 //
-// Not emulated: real concurrency (no data race is ever observed), memory spaces (shared memory is one host buffer per
+// Not emulated: real concurrency (races show up only as schedule dependence, see simt::Runtime::schedule), memory spaces (shared memory is one host buffer per
 // block), TMA / mbarrier (admm_kernel.cuh replaces its four helpers by a memcpy under CPG_SIMT_HOST_EMU).
 #pragma once
 #include <math.h>
@@ -65,6 +65,7 @@ struct Runtime {
   BlockState block;
   Fiber* cur = nullptr;
   std::function<void()> body;
+  int schedule = 0;          // 0: threads resumed in ascending order, 1: descending, >= 2: a fixed pseudo-random permutation per pass
 };
 inline Runtime& rt() { static Runtime r; return r; }
 inline Fiber* cur() { return rt().cur; }
@@ -122,9 +123,22 @@ inline void launch(int grid, int threads, std::function<void()> body) {
       f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = STACK_BYTES; f.ctx.uc_link = &r.main_ctx;
       makecontext(&f.ctx, fiber_entry, 0);
     }
+    // The order in which runnable threads are resumed is the emulator's only freedom.  A kernel whose result depends on it
+    // has an unsynchronised dependency between lanes (a missing __syncwarp / __syncthreads): running the same launch under
+    // several schedules and comparing bit for bit is the race check of tests/test_simt_emulation.py.
+    std::vector<int> order(threads);
+    uint64_t lcg = 0x9e3779b97f4a7c15ull * (uint64_t)(r.schedule + 1);
     for (int alive = threads; alive > 0;) {
       alive = 0;
-      for (int t = 0; t < threads; ++t) {
+      for (int t = 0; t < threads; ++t) order[t] = r.schedule == 1 ? threads - 1 - t : t;
+      if (r.schedule >= 2)
+        for (int t = threads - 1; t > 0; --t) {
+          lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+          const int k = (int)((lcg >> 33) % (uint64_t)(t + 1));
+          const int tmp = order[t]; order[t] = order[k]; order[k] = tmp;
+        }
+      for (int ti = 0; ti < threads; ++ti) {
+        const int t = order[ti];
         Fiber& f = r.fibers[t];
         if (f.done) continue;
         r.cur = &f;

@@ -201,3 +201,43 @@ def test_backward_kernels_on_the_emulator(tmp_path):
         assert np.abs(got[k] - ref).max() < 1e-7 * max(np.abs(ref).max(), 1e-30), k
     want = param_gradient_mat(fam, dq, dl, du, dP, dA, batch)
     assert np.abs(got['dparams'] - want).max() < 1e-7 * np.abs(want).max()
+
+
+def test_results_do_not_depend_on_the_thread_schedule(tmp_path):
+    """Race check: the emulator resumes runnable threads in ascending, descending or shuffled order; a lane that consumed
+    another lane's shared-memory value without a barrier in between would see a different value under a different order.
+    The main kernel (no atomics on its path) must return bit-identical results under every schedule; the kernels that
+    factor K numerically add their update terms with shared-memory atomics, whose ORDER is the schedule's -- there the
+    results may differ in the last bits only (same iteration counts, 1e-12)."""
+    fam = families.mpc(4, 2, 6)
+    st, lib, dims = build_emu(fam, ['x_init'], str(tmp_path / 'mpc'))
+    xi = np.random.default_rng(2).uniform(-1.5, 1.5, (21, 4))
+    base = None
+    for mode in (0, 1, 2, 3):
+        lib.emu_set_schedule(mode)
+        out = run_solve(lib, 'emu_main_solve', dims, xi)
+        assert out['rc'] == 0                                  # nothing handed off: the whole solve ran in admm_multi_kernel
+        cur = (out['x'].tobytes(), out['y'].tobytes(), out['iter'].tobytes(), out['status'].tobytes(), out['obj'].tobytes())
+        base = base or cur
+        assert cur == base, f'schedule {mode} changes the result'
+    lib.emu_set_schedule(0)
+    fam = families.mpc_ltv(4, 2, 5)
+    batch = ['A', 'B', 'qdiag', 'rdiag', 'x_init']
+    st, lib, dims = build_emu(fam, batch, str(tmp_path / 'ltv'))
+    B = 5
+    params = families.mpc_ltv_batch(fam, B, seed=21)
+    rows = _rows(fam, st, params, B)
+    prim_idx = np.concatenate([v.indices for v in fam.variables])
+    dprim = np.random.default_rng(1).standard_normal((B, len(prim_idx)))
+    base = None
+    for mode in (0, 1, 2, 3):
+        lib.emu_set_schedule(mode)
+        out = run_solve(lib, 'emu_matpar_solve', dims, rows, adaptive_rho_interval=25, eps=1e-5)
+        g = _run_grad(lib, dims, rows, out['x'], out['y'], dprim, nnzP=st.nnzP, nnzA=st.nnzA)
+        if base is None:
+            base = (out, g)
+            continue
+        assert np.array_equal(out['iter'], base[0]['iter']) and np.array_equal(out['status'], base[0]['status'])
+        assert rel_err(out['x'], base[0]['x']).max() < 1e-12 and rel_err(out['y'], base[0]['y']).max() < 1e-12
+        assert np.abs(g['dparams'] - base[1]['dparams']).max() < 1e-10 * np.abs(base[1]['dparams']).max()
+    lib.emu_set_schedule(0)
