@@ -140,6 +140,12 @@ __device__ __forceinline__ TailView make_tail_view(const uint8_t* blob) {
   return tv;
 }
 
+// CPG_TAIL_GATHER_FACTOR = 1 selects the owner-writes (atomics-free, deterministic) form of the update phase; the default is
+// the push form with shared-memory atomicAdd(double).  Both are checked on the SIMT emulator (tests/test_simt_emulation.py);
+// the gather form has not been timed on the GPU yet, which is why it is not the default.
+#ifndef CPG_TAIL_GATHER_FACTOR
+#define CPG_TAIL_GATHER_FACTOR 0
+#endif
 // Numeric factorisation of K(rho_vec) on the family's symbolic pattern (role of QDLDL_factor, qdldl.c:72-233,
 // after update_KKT_param2, kkt.c:214-222).  S holds K's lower triangle in slot order with -1/rho_vec already
 // written; on exit S[j] = 1/D_j and the other slots hold L.  Right-looking, one elimination-tree level at a time.
@@ -151,13 +157,29 @@ __device__ __forceinline__ void tail_factor(const TailView& tv, double* S, int l
   const uint16_t* lc = tv.U16 + tv.H->h_level_cols;
   const ushort4* ops = reinterpret_cast<const ushort4*>(tv.U16 + tv.H->h_ops);
   const ushort2* scl = reinterpret_cast<const ushort2*>(tv.U16 + tv.H->h_scale);
+#if CPG_TAIL_GATHER_FACTOR
+  const int* gtp = tv.I32 + tv.H->i_gtgt_ptr;
+  const int* gsg = tv.I32 + tv.H->i_gseg;
+  const ushort4* gops = reinterpret_cast<const ushort4*>(tv.U16 + tv.H->h_gops);
+#endif
   for (int lv = 0; lv < nl; ++lv) {
     for (int c = lp[lv] + lane; c < lp[lv + 1]; c += LANES) { const int j = lc[c]; S[j] = 1.0 / S[j]; }
     __syncwarp();
+#if CPG_TAIL_GATHER_FACTOR
+    // owner-writes form: a target's ops are contiguous and summed by ONE lane in table order (no atomics, deterministic)
+    for (int ti = gtp[lv] + lane; ti < gtp[lv + 1]; ti += LANES) {
+      const int o0 = __ldg(gsg + ti), o1 = __ldg(gsg + ti + 1);
+      ushort4 q = __ldg(gops + o0);
+      double acc = S[q.y] * S[q.z] * S[q.w];
+      for (int o = o0 + 1; o < o1; ++o) { q = __ldg(gops + o); acc += S[q.y] * S[q.z] * S[q.w]; }
+      S[q.x] -= acc;
+    }
+#else
     for (int o = op[lv] + lane; o < op[lv + 1]; o += LANES) {
       const ushort4 q = __ldg(ops + o);
       atomicAdd(&S[q.x], -(S[q.y] * S[q.z] * S[q.w]));
     }
+#endif
     __syncwarp();
     for (int o = sp[lv] + lane; o < sp[lv + 1]; o += LANES) { const ushort2 q = __ldg(scl + o); S[q.x] *= S[q.y]; }
     __syncwarp();

@@ -234,7 +234,7 @@ TAIL_HEADER_FIELDS: List[Tuple[str, str]] = [
     ('int', 'off_i32'), ('int', 'off_f64'), ('int', 'off_u16'), ('int', 'pad0'),
     ('int', 'i_level_ptr'), ('int', 'i_op_ptr'), ('int', 'i_scale_ptr'), ('int', 'i_tiles'),
     ('int', 'f_S0'), ('int', 'h_rho_slot'), ('int', 'h_level_cols'), ('int', 'h_ops'),
-    ('int', 'h_scale'), ('int', 'pad1'), ('int', 'pad2'), ('int', 'pad3'),
+    ('int', 'h_scale'), ('int', 'i_gtgt_ptr'), ('int', 'i_gseg'), ('int', 'h_gops'),     # owner-writes form of the update ops
 ]
 
 
@@ -261,6 +261,10 @@ def pack_tail_blob(T) -> bytes:
     hv['h_ops'] = ar.add_u16(T.ops)
     align_u16(2)
     hv['h_scale'] = ar.add_u16(T.scale)
+    hv['i_gtgt_ptr'] = ar.add_i32(T.g_tgt_ptr)
+    hv['i_gseg'] = ar.add_i32(T.g_seg)
+    align_u16(4)
+    hv['h_gops'] = ar.add_u16(T.g_ops)
     # tile header (8 ints): [i32 offset of the packed entries (slot | position << 16, lane-interleaved), 0, K, r_pad, rows,
     #                        u16 offset of the row list, inside: u16 offset of the slot table | first slot of the packed triangle,
     #                        0 no couplings inside / 1 slot table / 2 packed triangle]

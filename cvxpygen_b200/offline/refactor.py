@@ -63,6 +63,12 @@ class RefactorTables:
     fwd_tiles: List[SlotTile]
     bwd_tiles: List[SlotTile]
     slot: np.ndarray = None       # (nk, nk) slot of the strictly-lower entry (i, j) in pivot positions, -1 outside the pattern
+    # owner-writes ("gather") form of the update ops: per level the distinct targets, most loaded first; target ti owns the
+    # ops g_ops[g_seg[ti]:g_seg[ti+1]] (all with the same t) and is the only writer of S[t] in that level -> no atomics, one
+    # fixed summation order.  Kernel path: tail_factor under CPG_TAIL_GATHER_FACTOR.
+    g_tgt_ptr: np.ndarray = None  # (n_levels+1,) into the target list
+    g_seg: np.ndarray = None      # (n_targets+1,) first op of every target
+    g_ops: np.ndarray = None      # (n_ops, 4): t, a, b, j -- the ops of `ops`, level by level, grouped by target
 
     def slot_of(self, i: int, j: int) -> int:
         if i == j:
@@ -243,7 +249,21 @@ def build_refactor_tables(F: LDLFactor, K: sp.csc_matrix, n_var: int) -> Refacto
         if len(rows) > LANES:
             assert not inside
         bwd += _group_tiles(rows, outside, inside, n_slots - 1, dense_base.get(gi, -1) if gi >= 0 else -1)
-    return RefactorTables(nk=nk, n_slots=n_slots, S0=S0, rho_slot=rho_slot.astype(np.int64),
+    ops_arr = np.asarray(ops, dtype=np.int64).reshape(-1, 4)
+    g_tgt_ptr, g_seg, g_ops = [0], [0], []
+    for lv in range(n_levels):
+        o = ops_arr[op_ptr[lv]:op_ptr[lv + 1]]
+        if len(o):
+            tg, inv, cnt = np.unique(o[:, 0], return_inverse=True, return_counts=True)
+            for ti in np.lexsort((tg, -cnt)):                    # most loaded targets first: strided lanes stay balanced
+                sel = o[inv == ti]
+                g_ops.append(sel)
+                g_seg.append(g_seg[-1] + len(sel))
+        g_tgt_ptr.append(len(g_seg) - 1)
+    g_ops = np.concatenate(g_ops).reshape(-1, 4) if g_ops else np.zeros((0, 4), dtype=np.int64)
+    assert len(g_ops) == len(ops_arr)
+    return RefactorTables(g_tgt_ptr=np.asarray(g_tgt_ptr), g_seg=np.asarray(g_seg), g_ops=g_ops,
+                          nk=nk, n_slots=n_slots, S0=S0, rho_slot=rho_slot.astype(np.int64),
                           level_ptr=np.asarray(level_ptr), level_cols=np.asarray(level_cols),
                           op_ptr=np.asarray(op_ptr), ops=np.asarray(ops, dtype=np.int64).reshape(-1, 4),
                           scale_ptr=np.asarray(scale_ptr), scale=np.asarray(scale, dtype=np.int64).reshape(-1, 2),
@@ -260,6 +280,26 @@ def emulate_factor(T: RefactorTables, rho_vec: np.ndarray) -> np.ndarray:
         o = T.ops[T.op_ptr[lv]:T.op_ptr[lv + 1]]
         if len(o):
             np.subtract.at(S, o[:, 0], S[o[:, 1]] * S[o[:, 2]] * S[o[:, 3]])
+        sc = T.scale[T.scale_ptr[lv]:T.scale_ptr[lv + 1]]
+        if len(sc):
+            S[sc[:, 0]] *= S[sc[:, 1]]
+    return S
+
+
+def emulate_factor_gather(T: RefactorTables, rho_vec: np.ndarray) -> np.ndarray:
+    """The owner-writes form (tail_factor under CPG_TAIL_GATHER_FACTOR): every target sums its own ops in table order."""
+    S = T.S0.copy()
+    S[T.rho_slot] = -1.0 / rho_vec
+    for lv in range(len(T.level_ptr) - 1):
+        cols = T.level_cols[T.level_ptr[lv]:T.level_ptr[lv + 1]]
+        S[cols] = 1.0 / S[cols]
+        for ti in range(T.g_tgt_ptr[lv], T.g_tgt_ptr[lv + 1]):
+            o = T.g_ops[T.g_seg[ti]:T.g_seg[ti + 1]]
+            assert (o[:, 0] == o[0, 0]).all()
+            acc = 0.0
+            for t_, a, b, j in o:
+                acc += S[a] * S[b] * S[j]
+            S[o[0, 0]] -= acc
         sc = T.scale[T.scale_ptr[lv]:T.scale_ptr[lv + 1]]
         if len(sc):
             S[sc[:, 0]] *= S[sc[:, 1]]

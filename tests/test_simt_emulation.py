@@ -21,12 +21,12 @@ from oracle.grad_numpy import qp_backward, qp_backward_mat, param_gradient, para
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def build_emu(fam, batch, out_dir):
+def build_emu(fam, batch, out_dir, flags=()):
     st = setup_qp_family(fam, batch)
     codegen.write_code(st, out_dir)
     inc, sol, src = (os.path.join(out_dir, 'c', d) for d in ('include', 'solver_code', 'src'))
     so = os.path.join(out_dir, 'libadmm_emu.so')
-    cmd = ['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-DCPG_SIMT_HOST_EMU', '-w', '-ffp-contract=off',
+    cmd = ['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-DCPG_SIMT_HOST_EMU', '-w', '-ffp-contract=off', *flags,
            '-I', os.path.join(HERE, 'emu', 'simt'), '-I', inc, '-I', sol, os.path.join(HERE, 'emu', 'admm_emu.cpp'),
            '-x', 'c', os.path.join(src, 'cpg_blob.c'), '-o', so]
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -241,3 +241,36 @@ def test_results_do_not_depend_on_the_thread_schedule(tmp_path):
         assert rel_err(out['x'], base[0]['x']).max() < 1e-12 and rel_err(out['y'], base[0]['y']).max() < 1e-12
         assert np.abs(g['dparams'] - base[1]['dparams']).max() < 1e-10 * np.abs(base[1]['dparams']).max()
     lib.emu_set_schedule(0)
+
+
+def test_gather_form_factorisation_is_deterministic(tmp_path):
+    """tail_factor under CPG_TAIL_GATHER_FACTOR (owner-writes update phase, no atomics; not the default build until it has
+    been timed on the GPU): same answers as the reference, and -- with no atomic left on the path -- bit-identical results
+    under every thread schedule, for the solve and for the backward pass."""
+    fam = families.mpc_ltv(4, 2, 5)
+    batch = ['A', 'B', 'qdiag', 'rdiag', 'x_init']
+    st, lib, dims = build_emu(fam, batch, str(tmp_path), flags=('-DCPG_TAIL_GATHER_FACTOR=1',))
+    B = 6
+    params = families.mpc_ltv_batch(fam, B, seed=33)
+    rows = _rows(fam, st, params, B)
+    Px, Ax, (q, l, u) = canon_matrix_batches(fam, params, B)
+    kw = dict(adaptive_rho_interval=25, eps_abs=1e-6, eps_rel=1e-6)
+    ora = matrix_oracle_solve(fam, Px, Ax, q, l, u, **kw)
+    prim_idx = np.concatenate([v.indices for v in fam.variables])
+    dprim = np.random.default_rng(3).standard_normal((B, len(prim_idx)))
+    base = None
+    for mode in (0, 1, 2):
+        lib.emu_set_schedule(mode)
+        out = run_solve(lib, 'emu_matpar_solve', dims, rows, adaptive_rho_interval=25, eps=1e-6)
+        g = _run_grad(lib, dims, rows, out['x'], out['y'], dprim, nnzP=st.nnzP, nnzA=st.nnzA)
+        cur = (out['x'].tobytes(), out['y'].tobytes(), out['iter'].tobytes(), g['dparams'].tobytes(), g['dA'].tobytes())
+        if base is None:
+            base = cur
+            assert np.array_equal(out['iter'], ora['iter']) and rel_err(out['x'], ora['x']).max() < 1e-8
+        assert cur == base, f'schedule {mode} changes the result'
+    lib.emu_set_schedule(0)
+    # the tables themselves: owner-writes == push form up to rounding
+    from cvxpygen_b200.offline import kkt, refactor
+    rv = kkt.rho_vector(st.ctype, 0.37)
+    a, b = refactor.emulate_factor(st.refactor, rv), refactor.emulate_factor_gather(st.refactor, rv)
+    assert np.abs(a - b).max() < 1e-13 * np.abs(a).max()
