@@ -53,6 +53,13 @@ cpgb200::Settings default_settings(int adaptive_rho_interval, double eps) {
 extern "C" {
 
 void emu_set_schedule(int mode) { simt::rt().schedule = mode; }
+// synchronisation points executed since the last call, summed over all lanes: shuffles (incl. the ones inside __any_sync),
+// __syncwarp, __syncthreads -- each is one step of a warp's dependent chain
+void emu_counters(long long* out) {
+  simt::Runtime& r = simt::rt();
+  out[0] = r.n_exchange; out[1] = r.n_syncwarp; out[2] = r.n_syncthreads;
+  r.n_exchange = r.n_syncwarp = r.n_syncthreads = 0;
+}
 
 int emu_dims(int* out) {   // n, m, npb, n_prim, n_dual, matpar
   const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words));

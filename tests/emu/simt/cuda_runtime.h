@@ -65,6 +65,7 @@ struct Runtime {
   BlockState block;
   Fiber* cur = nullptr;
   std::function<void()> body;
+  long long n_exchange = 0, n_syncwarp = 0, n_syncthreads = 0;   // per-lane counts of synchronisation points (profiling aid)
   int schedule = 0;          // 0: threads resumed in ascending order, 1: descending, >= 2: a fixed pseudo-random permutation per pass
 };
 inline Runtime& rt() { static Runtime r; return r; }
@@ -88,6 +89,7 @@ template <class T> inline T from_bits(uint64_t u) { T v; memcpy(&v, &u, sizeof(T
 template <class T> inline T exchange(T v, int src_lane) {
   static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
   WarpState& w = rt().warps[cur()->warp];
+  ++rt().n_exchange;
   w.buf[cur()->lane] = to_bits(v);
   warp_barrier();
   const T r = from_bits<T>(w.buf[src_lane & (WARP - 1)]);
@@ -173,8 +175,8 @@ inline unsigned __ballot_sync(unsigned, int pred) {
   for (int o = 16; o; o >>= 1) v |= simt::exchange(v, simt::cur()->lane ^ o);
   return v;
 }
-inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_barrier(); }
-inline void __syncthreads() { simt::block_barrier(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { ++simt::rt().n_syncwarp; simt::warp_barrier(); }
+inline void __syncthreads() { ++simt::rt().n_syncthreads; simt::block_barrier(); }
 inline int __syncthreads_or(int pred) { simt::rt().block.or_acc |= (pred != 0); simt::block_barrier(); const int r = simt::rt().block.or_result; simt::block_barrier(); return r; }
 
 template <class T> inline T atomicAdd(T* p, T v) { const T old = *p; *p = old + v; return old; }
