@@ -112,9 +112,11 @@ def test_main_kernel_on_the_emulator(tmp_path):
     assert np.array_equal(out2['iter'], ora2['iter']) and rel_err(out2['x'], ora2['x']).max() < 1e-8
 
 
-@pytest.mark.parametrize('name,B', [('nonneg_LS_3_2', 40), ('box_qp_6_8', 96), ('random_qp_20_5_15', 24)])
+@pytest.mark.parametrize('name,B', [('nonneg_LS_3_2', 40), ('box_qp_6_8', 96), ('random_qp_20_5_15', 24),
+                                    ('mpc_12_4_10', 12), ('portfolio_qp_50_10', 6)])
 def test_standard_families_on_the_emulator(name, B, tmp_path):
-    """Main + tail kernels of the small standard families: unstructured sparsity with q, l, u all batched; box_qp's corner
+    """Main + tail kernels of the standard families -- incl. the headline MPC-12/4/10 family with its 374-step generated solve and
+    the 742-row portfolio QP --: unstructured sparsity with q, l, u all batched; box_qp's corner
     cases -- bounds that change a constraint's type (hand-off at iteration 0), primal and dual infeasibility certificates,
     no-solution statuses with NaN solutions and +-1e30 objectives."""
     from cvxpygen_b200 import standard
@@ -131,7 +133,7 @@ def test_standard_families_on_the_emulator(name, B, tmp_path):
     ora = oracle_solve(fam, q, l, u)
     info = SimpleNamespace(status=out['status'], iter=out['iter'], obj_val=out['obj'], pri_res=out['pri'], dua_res=out['dua'])
     stable = rounding_stable(fam, q, l, u, ora) if name == 'box_qp_6_8' else None
-    assert_batch_parity(out['x'], out['y'], info, ora, 1e-8, stable=stable)
+    assert_batch_parity(out['x'], out['y'], info, ora, 1e-8, stable=stable, obj_sign=-1.0 if fam.is_maximization else 1.0)
     if name == 'box_qp_6_8':
         assert out['rc'] > 0                                             # some instances went through the tail kernel
         assert set(np.unique(ora['status'])) >= {1, -3, -4} and np.array_equal(out['status'], ora['status'])
