@@ -90,8 +90,7 @@ class ADMMCUDAInterface(*_BASES):
         from .. import codegen
         from ..ir import CanonFamily
         from ..offline.qp_setup import setup_qp_family
-        if gradient:
-            raise NotImplementedError('gradient=True is not generated by the ADMM-CUDA backend yet')
+        # gradient=True needs nothing extra: every generated library carries the batched backward pass (cpg_gradient_batch_*)
         fam = self.family if self.family is not None else CanonFamily.from_reference_canon(
             getattr(configuration, 'code_dir', 'problem'), canon, self)
         setup = setup_qp_family(fam, batch_params)

@@ -74,3 +74,41 @@ def test_bridge_roundtrip_generates_identical_constants(builder, batch):
     assert all(np.array_equal(a.indices, b.indices) and a.vec == b.vec for a, b in zip(fam.duals, fam2.duals))
     s1, s2 = setup_qp_family(fam, batch), setup_qp_family(fam2, batch)
     assert s1.blob == s2.blob and s1.tail_blob == s2.tail_blob and s1.mat_blob == s2.mat_blob and s1.grad_blob == s2.grad_blob
+
+
+def _class_level_names(path, cls):
+    """names assigned / defined at class level of `cls` in a reference source file (parsed, not imported: cvxpy is absent)"""
+    import ast
+    tree = ast.parse(open(path).read())
+    node = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == cls)
+    names = set()
+    for st in node.body:
+        if isinstance(st, ast.Assign):
+            names |= {t.id for t in st.targets if isinstance(t, ast.Name)}
+        elif isinstance(st, ast.AnnAssign) and isinstance(st.target, ast.Name):
+            names.add(st.target.id)
+        elif isinstance(st, ast.FunctionDef):
+            names.add(st.name)
+    return names
+
+
+def test_plugin_classes_carry_the_reference_interface():
+    """b1: ADMMCUDAInterface / IPMCUDAInterface expose every class-level attribute and method that the reference plugins they
+    stand beside (OSQPInterface + QPCanonMixin, ECOSInterface) define -- except what only makes sense for a CPU solver whose
+    workspace the writer addresses field by field (ws_ptrs) and the cvxpy-side affine-map plumbing the mixin provides."""
+    from cvxpygen_b200.solvers import ADMMCUDAInterface, IPMCUDAInterface
+    sol = os.path.join(REF, 'cvxpygen', 'solvers')
+    osqp = _class_level_names(os.path.join(sol, 'osqp.py'), 'OSQPInterface') | \
+        _class_level_names(os.path.join(sol, '_interface.py'), 'QPCanonMixin')
+    ecos = _class_level_names(os.path.join(sol, 'ecos.py'), 'ECOSInterface')
+    cpu_only = {'ws_ptrs', 'get_affine_map', 'augment_vector_parameter', 'cmake_context_extra', 'setup_py_context',
+                'declare_workspace', 'define_workspace', '__init__'}
+    for ours, ref in ((ADMMCUDAInterface, osqp), (IPMCUDAInterface, ecos)):
+        missing = {n for n in ref - cpu_only if not hasattr(ours, n)}
+        assert not missing, (ours.__name__, sorted(missing))
+    assert ADMMCUDAInterface.canon_p_ids == ['P', 'q', 'd', 'A', 'l', 'u'] and IPMCUDAInterface.canon_p_ids == ['c', 'd', 'A', 'b', 'G', 'h']
+    assert IPMCUDAInterface.status_is_int and IPMCUDAInterface.dual_var_names == ['y', 'z'] and IPMCUDAInterface.dual_var_split
+    i = IPMCUDAInterface(family=families.adp_socp())
+    assert i.canon_constants['q'] == [8, 5, 4, 4] and i.stgs_translation == {'max_iters': 'maxit'}
+    with pytest.raises(ValueError):
+        IPMCUDAInterface.check_unsupported_cones(SimpleNamespace(exp=1))
