@@ -104,6 +104,8 @@ def test_main_kernel_on_the_emulator(tmp_path):
     assert np.allclose(out['obj'], ora['obj'], rtol=1e-9)
     prim_idx = np.concatenate([v.indices for v in fam.variables]); dual_idx = np.concatenate([d.indices for d in fam.duals])
     assert np.array_equal(out['prim'], out['x'][:, prim_idx]) and np.array_equal(out['dual'], out['y'][:, dual_idx])
+    one = run_solve(lib, 'emu_main_solve', dims, xi[:1], grid=1)           # a single instance: one half-filled warp slot
+    assert one['iter'][0] == ora['iter'][0] and np.array_equal(one['x'][0], out['x'][0])
     # rho adaptation every 25 iterations at 1e-6: hand-offs to the tail kernel
     kw = dict(adaptive_rho_interval=25, eps_abs=1e-6, eps_rel=1e-6)
     out2 = run_solve(lib, 'emu_main_solve', dims, xi, grid=2, adaptive_rho_interval=25, eps=1e-6)
