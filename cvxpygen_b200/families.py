@@ -644,6 +644,32 @@ def actuator_batch(fam: CanonFamily, B: int, seed: int = 0):
             'u_min': lo, 'u_max': lo + 0.5 + 2.0 * rng.random((B, 1))}
 
 
+def osqp_update_matrices_kat(name=None):
+    """OSQP's own known-answer test for matrix updates (osqp_sources/tests/update_matrices/generate_problem.py: n = 5, m = 8,
+    numpy Generator(PCG64(2)) -- the construction is repeated here stream for stream) as a family whose parameters are its
+    canonical data (``q``, ``l``, ``u`` and the stored entries of ``P`` / ``A``).  Returns (family, cases): the original and the
+    updated matrix entries and the expected x / objective of the four variants the reference test asserts
+    (test_update_matrices.h: original, P updated, A updated, both; TESTS_TOL = 1e-4, duals zero)."""
+    from numpy.random import Generator, PCG64
+    from .ir import CanonFamily as _CF
+    rg = Generator(PCG64(2))
+    n, m, dens = 5, 8, 0.7
+    A = sp.random(m, n, density=dens, format='csc', random_state=rg)
+    P = sp.random(n, n, density=dens, random_state=rg)
+    P = (P @ P.T).tocsc() + sp.eye(n, format='csc')
+    Pu = sp.triu(P, format='csc'); Pu.sort_indices(); A.sort_indices()
+    A_new = A.copy(); A_new.data = A_new.data + rg.standard_normal(A_new.nnz)
+    Pu_new = Pu.copy(); Pu_new.data = Pu_new.data + 0.1 * rg.standard_normal(Pu_new.nnz)
+    q = rg.standard_normal(n); l = -30 + rg.standard_normal(m); u = 30 + rg.standard_normal(m)
+    fam = _CF.from_canonical_qp(name or 'osqp_update_matrices_5_8', Pu, q, A, l, u, n_eq=0, matrix_params=True)
+    x_orig = np.array([-4.61725223e-01, 7.97298788e-01, 5.55470173e-04, 3.37603740e-01, -1.14060693e+00])
+    x_pnew = np.array([-0.48845963, 0.70997599, -0.09017696, 0.33176037, -1.01867464])
+    cases = dict(P=np.stack([Pu.data, Pu_new.data, Pu.data, Pu_new.data]), A=np.stack([A.data, A.data, A_new.data, A_new.data]),
+                 x=np.stack([x_orig, x_pnew, x_orig, x_pnew]),
+                 obj=np.array([-1.885431747787806, -1.7649689689774013, -1.8854317477878062, -1.764968968977401]))
+    return fam, cases
+
+
 def portfolio_qp(n=50, m=10, seed=0, name=None) -> CanonFamily:
     """The reference's portfolio test problem in its QP form (tests/test_E2E_QP.py:76-110, data :148-162; run there with OSQP):
 

@@ -24,6 +24,7 @@ STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
     'mpc_ltv_12_4_10': (lambda: families.mpc_ltv(12, 4, 10), ['A', 'B', 'qdiag', 'rdiag', 'x_init']),
     'mpc_ref_6_3_10': (lambda: families.mpc_reference(10), ['Psqrt', 'Qsqrt', 'Rsqrt', 'A', 'B', 'x_init']),   # the reference's test MPC, all parameters
     'actuator_1_3': (lambda: families.actuator(), ['A', 'w', 'lamb_sm', 'kappa', 'u_prev', 'u_min', 'u_max']),   # degenerate shapes, scalar parameter in P
+    'osqp_update_matrices_5_8': (lambda: families.osqp_update_matrices_kat()[0], ['q', 'l', 'u', 'P', 'A']),   # OSQP's own KAT for matrix updates
     'nonneg_LS_3_2_A': (lambda: families.nonneg_ls(3, 2, name='nonneg_LS_3_2_A'), ['A', 'b']),   # README example, A per instance
     'portfolio_socp_100_10': (lambda: families.portfolio_socp(100, 10), ['a', 'w_prev']),   # BASELINE config 3 (IPM-CUDA)
     # generic conic families (every vector batched): three cones + equalities, and a pure LP; exit flags 0 / 1 / 2
@@ -36,7 +37,8 @@ STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
 
 # families solved by the ADMM (QP) backend / by the interior-point (SOCP) backend
 SOCP_NAMES: List[str] = [n for n in STANDARD if '_socp_' in n or n.startswith('network_lp')]     # conic families (IPM-CUDA)
-MATPAR_NAMES: List[str] = ['mpc_ltv_6_3_10', 'mpc_ltv_12_4_10', 'mpc_ref_6_3_10', 'actuator_1_3', 'nonneg_LS_3_2_A']
+MATPAR_NAMES: List[str] = ['mpc_ltv_6_3_10', 'mpc_ltv_12_4_10', 'mpc_ref_6_3_10', 'actuator_1_3', 'osqp_update_matrices_5_8',
+                           'nonneg_LS_3_2_A']
 QP_NAMES: List[str] = [n for n in STANDARD if n not in SOCP_NAMES and n not in MATPAR_NAMES]
 
 

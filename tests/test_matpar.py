@@ -144,6 +144,46 @@ def test_pack_params_matrix_layouts():
     assert np.array_equal(r2[0, 15:24], np.arange(9.0))
 
 
+def _kat_batches():
+    fam, cases = families.osqp_update_matrices_kat()
+    B = 4
+    vec = {k: np.tile(fam.param(k).default, (B, 1)) for k in ('q', 'l', 'u')}
+    return fam, cases, dict(vec, P=cases['P'], A=cases['A'])
+
+
+def test_osqp_update_matrices_known_answers():
+    """Oracle pinning for the matrix-update path on OSQP's OWN known-answer test (osqp_sources/tests/update_matrices: the
+    data generator is repeated stream for stream, the expected values are the ones test_update_matrices.h asserts with
+    TESTS_TOL = 1e-4): original problem, P updated, A updated, both -- compiled reference (when built) and numpy restatement."""
+    fam, cases, params = _kat_batches()
+    for prefer_ref in ([True, False] if ref_available() else [False]):
+        o = matrix_oracle_solve(fam, cases['P'], cases['A'], params['q'], params['l'], params['u'], prefer_ref=prefer_ref, max_iter=1000)
+        assert (o['status'] == 1).all()
+        assert np.abs(o['x'] - cases['x']).max() < 1e-4 and np.abs(o['y']).max() < 1e-4
+        assert np.abs(o['obj'] - cases['obj']).max() < 1e-4
+
+
+def test_osqp_update_matrices_known_answers_on_the_kernel(tmp_path):
+    """... and the matrix-parameter kernel itself (product source on the SIMT emulator) on the same four variants."""
+    from test_simt_emulation import build_emu, run_solve, _rows
+    fam, cases, params = _kat_batches()
+    st, lib, dims = build_emu(fam, ['q', 'l', 'u', 'P', 'A'], str(tmp_path))
+    out = run_solve(lib, 'emu_matpar_solve', dims, _rows(fam, st, params, 4), grid=1)
+    assert (out['status'] == 1).all()
+    assert np.abs(out['x'] - cases['x']).max() < 1e-4 and np.abs(out['y']).max() < 1e-4 and np.abs(out['obj'] - cases['obj']).max() < 1e-4
+
+
+@pytest.mark.gpu
+def test_gpu_osqp_update_matrices_known_answers():
+    fam, cases, params = _kat_batches()
+    res = standard.load('osqp_update_matrices_5_8', device=0).solve_batch(params, return_canonical=True)
+    assert (res.cpg_info.status == 1).all()
+    assert np.abs(res.sol_x - cases['x']).max() < 1e-4 and np.abs(res.sol_y).max() < 1e-4
+    assert np.abs(res.cpg_info.obj_val - cases['obj']).max() < 1e-4
+    ora = matrix_oracle_solve(fam, cases['P'], cases['A'], params['q'], params['l'], params['u'])
+    assert np.array_equal(res.cpg_info.iter, ora['iter']) and np.abs(res.sol_x - ora['x']).max() < 1e-9
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize('name,B', [('mpc_ltv_6_3_10', 300), ('mpc_ltv_12_4_10', 200)])
