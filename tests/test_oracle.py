@@ -107,3 +107,51 @@ def test_reference_library_reproduces_golden():
     s = r.solve_batch(q=g['q'], l=g['l'], u=g['u'])
     assert np.array_equal(s['x'], g['default_x']) and np.array_equal(s['iter'], g['default_iter'])
     assert r.adaptive_rho_interval() == 100       # osqp.c:267-279 without a profiling timer
+
+
+def test_kat_non_convex():
+    """OSQP's non_cvx test (osqp_sources/tests/non_cvx: P indefinite): with the default sigma the SETUP must fail (OSQP_NONCVX_ERROR,
+    test_non_cvx.h:35-36 -- here the offline inertia check of the KKT factor); with sigma = 5 setup succeeds and the SOLVE reports
+    OSQP_NON_CVX with a NaN objective (:53-58) -- restatement, compiled reference (when built) and the main kernel on the emulator."""
+    import scipy.sparse as sp
+    from cvxpygen_b200.ir import CanonFamily
+    from cvxpygen_b200.offline.qp_setup import setup_qp_family
+    from oracle.admm_numpy import AdmmOracle, NON_CVX
+    P = sp.triu(sp.csc_matrix([[2., 5.], [5., 1.]]), format='csc'); q = np.array([3., 4.])
+    A = sp.csc_matrix([[-1., 0.], [0., -1.], [-1., 3.], [2., 5.], [3., 4]])
+    l = -1e30 * np.ones(5); u = np.array([0., 0., -15., 100., 80.])
+    fam = CanonFamily.from_canonical_qp('osqp_non_cvx', P, q, A, l, u, n_eq=0)
+    with pytest.raises(ValueError, match='non-convex'):
+        setup_qp_family(fam, ['q', 'l', 'u'])
+    o = AdmmOracle(P, q, A, l, u, sigma=5.0).solve_batch(B=1)
+    assert o['status'][0] == NON_CVX and np.isnan(o['obj'][0])
+    from helpers import ref_available
+    if ref_available():
+        from oracle.ref_osqp import RefOSQP
+        r = RefOSQP(P, q, A, l, u, sigma=5.0).solve_batch(B=1)
+        assert r['status'][0] == NON_CVX and (np.isnan(r['obj'][0]) or r['obj'][0] == 2143289344.0)    # OSQP_NAN as stored by 0.6.2
+        assert r['iter'][0] == o['iter'][0]
+
+
+def test_kat_non_convex_on_the_kernel(tmp_path):
+    import scipy.sparse as sp
+    from cvxpygen_b200 import codegen
+    from cvxpygen_b200.ir import CanonFamily
+    from cvxpygen_b200.offline.qp_setup import setup_qp_family
+    from oracle.admm_numpy import AdmmOracle, NON_CVX
+    import test_simt_emulation as emu
+    P = sp.triu(sp.csc_matrix([[2., 5.], [5., 1.]]), format='csc'); q = np.array([3., 4.])
+    A = sp.csc_matrix([[-1., 0.], [0., -1.], [-1., 3.], [2., 5.], [3., 4]])
+    l = -1e30 * np.ones(5); u = np.array([0., 0., -15., 100., 80.])
+    fam = CanonFamily.from_canonical_qp('osqp_non_cvx', P, q, A, l, u, n_eq=0)
+    orig = emu.setup_qp_family
+    emu.setup_qp_family = lambda f, b: orig(f, b, sigma=5.0)            # the KAT's sigma_new
+    try:
+        st, lib, dims = emu.build_emu(fam, ['q', 'l', 'u'], str(tmp_path))
+    finally:
+        emu.setup_qp_family = orig
+    rows = np.concatenate([q, l, u])[None, :]
+    out = emu.run_solve(lib, 'emu_main_solve', dims, rows, grid=1)
+    o = AdmmOracle(P, q, A, l, u, sigma=5.0).solve_batch(B=1)
+    assert out['status'][0] == NON_CVX == o['status'][0] and out['iter'][0] == o['iter'][0]
+    assert np.isnan(out['obj'][0]) and np.isnan(out['x']).all()
