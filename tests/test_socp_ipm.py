@@ -318,6 +318,86 @@ def test_gpu_reference_network_lp():
     assert (gap < 1e-6 * np.maximum(1.0, np.abs(r2.cpg_info.obj_val))).all()     # strong duality: w'f = c'z0 - fmin'z1 + fmax'z2
 
 
+def _parse_c_arrays(path):
+    """{name: numpy array or scalar} of the `pfloat` / `idxint` definitions of an ECOS test header"""
+    import re
+    txt = open(path).read()
+    out = {}
+    for m_ in re.finditer(r'(pfloat|idxint)\s+(\w+)\[\d*\]\s*=\s*\{([^}]*)\}', txt):
+        vals = [v for v in re.split(r'[\s,]+', m_.group(3).strip()) if v]
+        out[m_.group(2)] = np.array([float(v) for v in vals]) if m_.group(1) == 'pfloat' else np.array([int(v) for v in vals])
+    for m_ in re.finditer(r'(pfloat|idxint)\s+(\w+)\s*=\s*([-+0-9.eE]+)\s*;', txt):
+        out[m_.group(2)] = float(m_.group(3)) if m_.group(1) == 'pfloat' else int(m_.group(3))
+    return out
+
+
+ECOS_UPDATE_KAT = os.path.join(os.environ.get('CPG_REFERENCE', '/root/reference'), 'cvxpygen', 'solvers', 'ecos', 'test', 'updateData',
+                               'update_data.h')
+
+
+@pytest.mark.skipif(not os.path.exists(ECOS_UPDATE_KAT), reason='reference tree not present')
+def test_ecos_update_data_known_answers(tmp_path):
+    """ECOS's OWN known-answer test for ECOS_updateData (ecos/test/updateData/update_data.h, run by ecostester.c): an LP with
+    n = 20, p = 5, l = 40 solved for (c1, A1, b1, G1, h1) -> optimal value -36.250515, then for the second data set -> -20.011586.
+    The header is parsed where it lies; compiled reference (when built), the numpy restatement and the interior-point kernel's
+    phase logic (host build) must reproduce both values.  Matrices are shared parameters here (one family per data set, the
+    role of update_shared_params); c, b, h are the per-instance vectors."""
+    from cvxpygen_b200.ir import CanonFamily
+    from oracle.ipm_numpy import EcosExact
+    d = _parse_c_arrays(ECOS_UPDATE_KAT)
+    n, m, p, l = d['udd_n'], d['udd_m'], d['udd_p'], d['udd_l']
+    for k, want in (('1', d['udd_optval1']), ('2', d['udd_optval2'])):
+        A = sp.csc_matrix((d[f'udd_A{k}pr'], d['udd_Air'], d['udd_Ajc']), shape=(p, n))
+        G = sp.csc_matrix((d[f'udd_G{k}pr'], d['udd_Gir'], d['udd_Gjc']), shape=(m, n))
+        c, b, h = d[f'udd_c{k}'], d[f'udd_b{k}'], d[f'udd_h{k}']
+        if ref_ecos.available():
+            r = ref_ecos.RefECOS(c, A, b, G, h, l, []).solve_batch()
+            assert r['exitflag'][0] in (0, 10) and abs(r['pcost'][0] - want) < 1e-5
+        e = EcosExact(A, G, l, []).solve(c, b, h)
+        assert e['exitflag'] in (0, 10) and abs(e['pcost'] - want) < 1e-5
+        fam = CanonFamily.from_canonical_conic(f'ecos_update_data_{k}', c, A, b, G, h, l)
+        st = ss.setup_socp_family(fam, ['c', 'b', 'h'])
+        os.makedirs(str(tmp_path / k), exist_ok=True)
+        lib = _build_emu(st, str(tmp_path / k))
+        out = _emu_solve(lib, st, np.concatenate([c, b, h])[None, :])
+        assert out['status'][0] in (0, 10) and abs(out['obj'][0] - want) < 1e-5
+        assert out['iter'][0] == e['iter'] and np.abs(out['x'][0] - e['x']).max() < 1e-7 * max(1.0, np.abs(e['x']).max())
+
+
+ECOS_TESTS = os.path.join(os.environ.get('CPG_REFERENCE', '/root/reference'), 'cvxpygen', 'solvers', 'ecos', 'test')
+
+
+@pytest.mark.skipif(not os.path.isdir(ECOS_TESTS), reason='reference tree not present')
+@pytest.mark.parametrize('rel,prefix,flag', [('infeasibleProblems/infeasible1.h', '', 1), ('infeasibleProblems/infeasible2.h', '', 1),
+                                             ('unboundedProblems/unboundedLP1.h', '', 2), ('LPnetlib/lp_afiro.h', 'lp_afiro_', 0)])
+def test_ecos_own_test_problems(rel, prefix, flag, tmp_path):
+    """Problems of ECOS's own test suite (ecos/test/*, run by ecostester.c) with the exit flag each of them asserts: primal
+    infeasible (with and without equalities), unbounded LP, a netlib LP.  (unboundedMaxSqrt.h is left out: it sits on a
+    numerical knife edge -- the vendored ECOS itself, compiled here, returns ECOS_NUMERICS after 11 iterations from a fresh
+    ECOS_setup and ECOS_DINF after 12 once ECOS_updateData has re-equilibrated the very same data.)  Parsed where they lie; compiled reference (when built), numpy restatement and the kernel's phase logic (host build)."""
+    from cvxpygen_b200.ir import CanonFamily
+    from oracle.ipm_numpy import EcosExact
+    d = _parse_c_arrays(os.path.join(ECOS_TESTS, rel))
+    g = lambda k, default=None: d.get(prefix + k, default)
+    n, m, p, l = g('n'), g('m'), g('p'), g('l')
+    q = [int(v) for v in g('q', [])] if g('ncones', 0) else []
+    G = sp.csc_matrix((g('Gpr'), g('Gir'), g('Gjc')), shape=(m, n))
+    A = sp.csc_matrix((g('Apr'), g('Air'), g('Ajc')), shape=(p, n)) if p else sp.csc_matrix((0, n))
+    c, h, b = g('c'), g('h'), (g('b') if p else np.zeros(0))
+    e = EcosExact(A, G, l, q).solve(c, b, h)
+    assert e['exitflag'] == flag
+    if ref_ecos.available():
+        r = ref_ecos.RefECOS(c, A, b, G, h, l, q).solve_batch()
+        assert r['exitflag'][0] == flag and r['iter'][0] == e['iter']
+    fam = CanonFamily.from_canonical_conic('ecos_kat', c, A, b, G, h, l, q)
+    st = ss.setup_socp_family(fam, [pp.name for pp in fam.params])
+    lib = _build_emu(st, str(tmp_path))
+    out = _emu_solve(lib, st, np.concatenate([c, b, h])[None, :])
+    assert out['status'][0] == flag and out['iter'][0] == e['iter']
+    if flag == 0:
+        assert abs(out['obj'][0] - e['pcost']) < 1e-7 * max(1.0, abs(e['pcost'])) and _rel(out['x'][0], e['x']) < 1e-6
+
+
 def test_generated_directory_and_c_abi():
     d = standard.build(NAME)
     for f in ('cpg_solver.py', 'cpg_module.py', 'cpg_meta.json', 'libcpg_b200.so', 'c/include/cpg_b200_socp.h',
