@@ -21,7 +21,7 @@ extern "C" const unsigned long long CPG_B200_FN(cpg_gblob_words)[];
 extern "C" const unsigned long long CPG_B200_FN(cpg_gS0_words)[];
 extern "C" const unsigned long long CPG_B200_FN(cpg_mblob_words)[];
 
-namespace cpgb200 { alignas(128) uint8_t smem[256 * 1024]; }
+namespace cpgb200 { alignas(128) thread_local uint8_t smem[256 * 1024]; }
 
 namespace {
 struct Fam {

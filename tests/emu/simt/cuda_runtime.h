@@ -25,8 +25,9 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
-#define __shared__          /* `extern __shared__ T smem[]` binds to a host array the driver defines; the only other
-                               __shared__ object of these kernels is the mbarrier word, unused under emulation */
+#define __shared__ thread_local   /* one OS thread runs all fibers, so a thread_local object is shared by every CUDA thread:
+                                     `extern __shared__ T smem[]` binds to a thread_local host array the driver defines, a
+                                     block-scope `__shared__ int x;` becomes one static object per kernel */
 #define __align__(n)
 #define __constant__ static
 
@@ -170,6 +171,18 @@ inline int __any_sync(unsigned, int pred) {
   return acc != 0;
 }
 inline int __all_sync(unsigned m, int pred) { return !__any_sync(m, !pred); }
+template <class T> inline T __reduce_max_sync(unsigned, T v) {
+  for (int o = 16; o; o >>= 1) { const T w = simt::exchange(v, simt::cur()->lane ^ o); v = w > v ? w : v; }
+  return v;
+}
+template <class T> inline T __reduce_min_sync(unsigned, T v) {
+  for (int o = 16; o; o >>= 1) { const T w = simt::exchange(v, simt::cur()->lane ^ o); v = w < v ? w : v; }
+  return v;
+}
+template <class T> inline T __reduce_add_sync(unsigned, T v) {
+  for (int o = 16; o; o >>= 1) v += simt::exchange(v, simt::cur()->lane ^ o);
+  return v;
+}
 inline unsigned __ballot_sync(unsigned, int pred) {
   unsigned v = pred ? (1u << simt::cur()->lane) : 0u;
   for (int o = 16; o; o >>= 1) v |= simt::exchange(v, simt::cur()->lane ^ o);

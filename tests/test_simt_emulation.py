@@ -217,7 +217,7 @@ def test_results_do_not_depend_on_the_thread_schedule(tmp_path):
     st, lib, dims = build_emu(fam, ['x_init'], str(tmp_path / 'mpc'))
     xi = np.random.default_rng(2).uniform(-1.5, 1.5, (21, 4))
     base = None
-    for mode in (0, 1, 2, 3):
+    for mode in (0, 1, 2):
         lib.emu_set_schedule(mode)
         out = run_solve(lib, 'emu_main_solve', dims, xi)
         assert out['rc'] == 0                                  # nothing handed off: the whole solve ran in admm_multi_kernel
@@ -234,7 +234,7 @@ def test_results_do_not_depend_on_the_thread_schedule(tmp_path):
     prim_idx = np.concatenate([v.indices for v in fam.variables])
     dprim = np.random.default_rng(1).standard_normal((B, len(prim_idx)))
     base = None
-    for mode in (0, 1, 2, 3):
+    for mode in (0, 1, 2):
         lib.emu_set_schedule(mode)
         out = run_solve(lib, 'emu_matpar_solve', dims, rows, adaptive_rho_interval=25, eps=1e-5)
         g = _run_grad(lib, dims, rows, out['x'], out['y'], dprim, nnzP=st.nnzP, nnzA=st.nnzA)
@@ -278,3 +278,73 @@ def test_gather_form_factorisation_is_deterministic(tmp_path):
     rv = kkt.rho_vector(st.ctype, 0.37)
     a, b = refactor.emulate_factor(st.refactor, rv), refactor.emulate_factor_gather(st.refactor, rv)
     assert np.abs(a - b).max() < 1e-13 * np.abs(a).max()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# interior-point kernel: the DEVICE code path of csrc/ipm_kernel.cuh (not the CPG_IPM_HOST_EMU branches) on the emulator
+def _build_ipm_simt(st, d):
+    from cvxpygen_b200 import codegen_ipm
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, 'cpg_ipm_family.h'), 'w') as f:
+        f.write(codegen_ipm.family_header(st))
+    so = os.path.join(d, 'libipm_simt.so')
+    res = subprocess.run(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-w', '-DCPG_SIMT_HOST_EMU', '-ffp-contract=off',
+                          '-I', os.path.join(HERE, 'emu', 'simt'), '-I', d, '-I', os.path.join(os.path.dirname(HERE), 'cvxpygen_b200', 'csrc'),
+                          os.path.join(HERE, 'emu', 'ipm_simt.cpp'), '-o', so], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    return C.CDLL(so)
+
+
+def _ipm_simt_solve(lib, st, params, maxit=100, grid=1):
+    D = st.defines
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    B = params.shape[0]
+    out = dict(prim=np.zeros((B, D['NPRIM'])), dual=np.zeros((B, D['NDUAL'])), x=np.zeros((B, D['N'])), y=np.zeros((B, max(D['P'], 1))),
+               z=np.zeros((B, D['M'])), s=np.zeros((B, D['M'])), obj=np.zeros(B), iter=np.zeros(B, np.int32),
+               status=np.zeros(B, np.int32), pres=np.zeros(B), dres=np.zeros(B))
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.ipm_simt_solve(st.smem_blob, st.gmem_blob, B, P(params), *[P(out[k]) for k in
+                       ('prim', 'dual', 'x', 'y', 'z', 's', 'obj', 'iter', 'status', 'pres', 'dres')], maxit, grid)
+    return out
+
+
+@pytest.mark.parametrize('name,B', [('adp_socp_6_3', 2), ('network_lp_50_10', 2), ('portfolio_100_10', 1)])
+def test_interior_point_device_code_on_the_emulator(name, B, tmp_path):
+    """ipm_kernel as the GPU runs it -- one 256-thread CTA per instance, ~118 barrier-separated phases per iteration, gather
+    plans finished with butterfly shuffles, REDUX max reductions, instances pulled from the work counter -- against the
+    golden vectors of the compiled ECOS: identical exit flags and iteration counts, x / s to 1e-7.  portfolio_100_10 is
+    BASELINE config 3's family."""
+    from cvxpygen_b200.offline import socp_setup as ss
+    from helpers import GOLDEN
+    fam, batch = {'adp_socp_6_3': (families.adp_socp(), ['f']), 'network_lp_50_10': (families.network_lp(50, 10), ['c', 'w', 'f_min', 'f_max']),
+                  'portfolio_100_10': (families.portfolio_socp(), ['a', 'w_prev'])}[name]
+    g = np.load(os.path.join(GOLDEN, f'socp_{name}.npz'))
+    st = ss.setup_socp_family(fam, batch)
+    lib = _build_ipm_simt(st, str(tmp_path))
+    P = np.concatenate([g['param_' + k][:B] for k in batch], axis=1)
+    out = _ipm_simt_solve(lib, st, P, grid=2)
+    assert np.array_equal(out['status'], g['exitflag'][:B]) and np.array_equal(out['iter'], g['iter'][:B])
+    assert np.abs(out['x'] - g['x'][:B]).max() < 1e-7 * np.abs(g['x'][:B]).max()
+    assert np.abs(out['s'] - g['s'][:B]).max() < 1e-7 * max(1.0, np.abs(g['s'][:B]).max())
+    sign = -1.0 if fam.is_maximization else 1.0
+    assert np.allclose(out['obj'], sign * g['pcost'][:B], rtol=1e-8, atol=1e-9)
+
+
+def test_interior_point_kernel_is_schedule_independent(tmp_path):
+    """Race check for the kernel with the most barriers: bit-identical iterates and iteration counts whether the emulator resumes
+    the 256 threads of the CTA in ascending, descending or shuffled order (a phase reading what another thread writes in the
+    same phase would break this); DESIGN claims bitwise reproducibility for this kernel -- no atomics, fixed summation order."""
+    from cvxpygen_b200.offline import socp_setup as ss
+    from helpers import GOLDEN
+    fam = families.adp_socp()
+    g = np.load(os.path.join(GOLDEN, 'socp_adp_socp_6_3.npz'))
+    st = ss.setup_socp_family(fam, ['f'])
+    lib = _build_ipm_simt(st, str(tmp_path))
+    base = None
+    for mode in (0, 1, 2):
+        lib.ipm_simt_set_schedule(mode)
+        out = _ipm_simt_solve(lib, st, g['param_f'][:1])
+        cur = tuple(out[k].tobytes() for k in ('x', 'z', 's', 'iter', 'status', 'obj'))
+        base = base or cur
+        assert cur == base, f'schedule {mode} changes the result'
+    lib.ipm_simt_set_schedule(0)
