@@ -4,6 +4,10 @@
 //   -DCPG_SIMT_HOST_EMU -I tests/emu/simt -I <code_dir>/c/include -I <code_dir>/c/solver_code   + <code_dir>/c/src/cpg_blob.c
 // The kernels are the product sources, unchanged; only the launch and the device memory are replaced by host calls.
 #include "cuda_runtime.h"
+// these kernels have no block-scope __shared__ state besides the (unused) mbarrier word: bind `extern __shared__ smem[]` to a
+// plain host array (the interior-point build, ipm_simt.cpp, needs the thread_local form for its `__shared__ int next_inst`)
+#undef __shared__
+#define __shared__
 
 #include "cpg_family.h"
 #include "cpg_b200.h"
@@ -21,7 +25,7 @@ extern "C" const unsigned long long CPG_B200_FN(cpg_gblob_words)[];
 extern "C" const unsigned long long CPG_B200_FN(cpg_gS0_words)[];
 extern "C" const unsigned long long CPG_B200_FN(cpg_mblob_words)[];
 
-namespace cpgb200 { alignas(128) thread_local uint8_t smem[256 * 1024]; }
+namespace cpgb200 { alignas(128) uint8_t smem[256 * 1024]; }
 
 namespace {
 struct Fam {
