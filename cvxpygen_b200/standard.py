@@ -62,7 +62,7 @@ def build_all(force: bool = False, verbose: bool = False, jobs: int = None):
     """Generate + compile every standard family.  The nvcc invocations (minutes of front-end time for the families with
     long generated straight-line solves) run concurrently, one subprocess per family, on the host cores."""
     import concurrent.futures as cf
-    jobs = jobs or max(1, min(len(STANDARD), (os.cpu_count() or 2)))
+    jobs = jobs or max(1, min(len(STANDARD), (os.cpu_count() or 2), 8))      # nvcc's front end takes ~1-2 GB per family
     with cf.ThreadPoolExecutor(jobs) as ex:
         futs = {name: ex.submit(build, name, force, verbose) for name in STANDARD}
         return {name: f.result() for name, f in futs.items()}
