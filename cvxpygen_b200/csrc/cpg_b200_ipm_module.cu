@@ -34,6 +34,8 @@ struct Ctx {
   double *d_obj = nullptr, *d_pri = nullptr, *d_dua = nullptr;
   int *d_iter = nullptr, *d_status = nullptr;
   int launches = 0;
+  cudaEvent_t ev[2] = {nullptr, nullptr};     // around the last ipm_kernel launch
+  bool ev_solve = false;
   char err[256] = {0};
 } g;
 
@@ -44,6 +46,13 @@ struct Ctx {
       snprintf(g.err, sizeof(g.err), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
       return CPG_B200_ERR_CUDA;                                                                   \
     }                                                                                             \
+  } while (0)
+
+// one context per library and process, bound to ONE device (see include/cpg_b200_socp.h)
+#define USE_DEVICE()                                                                              \
+  do {                                                                                            \
+    if (!g.ready) { snprintf(g.err, sizeof(g.err), "cpg_b200_init has not been called"); return CPG_B200_ERR_NOT_INIT; } \
+    CK(cudaSetDevice(g.device));                                                                  \
   } while (0)
 
 template <class T_>
@@ -57,6 +66,7 @@ int grow(T_** p, size_t count) {
 int ensure_staging(int B) {
   if (B <= g.cap_B) return CPG_B200_OK;
   int rc;
+  g.cap_B = 0;                 // a failed allocation below must not leave a stale capacity behind
   if ((rc = grow(&g.d_params, (size_t)B * cpgipm::NPB))) return rc;
   if ((rc = grow(&g.d_prim, (size_t)B * cpgipm::NPRIM))) return rc;
   if ((rc = grow(&g.d_dual, (size_t)B * cpgipm::NDUAL))) return rc;
@@ -78,6 +88,11 @@ int ensure_staging(int B) {
 extern "C" {
 
 int CPG_B200_FN(cpg_b200_init)(int device) {
+  if (g.ready && device != g.device) {
+    snprintf(g.err, sizeof(g.err), "this library is already initialised on device %d: one context per process "
+             "(use one process per GPU, or cpg_b200_free() first)", g.device);
+    return CPG_B200_ERR_BAD_ARG;
+  }
   if (g.ready) return CPG_B200_OK;
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -91,6 +106,7 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
   CK(cudaMalloc(&g.d_best, sizeof(double) * (size_t)g.n_sm * (cpgipm::NK + cpgipm::MT)));
   CK(cudaMalloc(&g.d_counter, sizeof(int)));
   CK(cudaFuncSetAttribute(cpgipm::ipm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cpgipm::SMEM_BYTES));
+  CK(cudaEventCreate(&g.ev[0])); CK(cudaEventCreate(&g.ev[1]));
   g.ready = true;
   return CPG_B200_OK;
 }
@@ -99,7 +115,9 @@ int CPG_B200_FN(cpg_b200_free)(void) {
   if (!g.ready) return CPG_B200_OK;
   void* ptrs[] = {g.d_sblob, g.d_gblob, g.d_best, g.d_counter, g.d_params, g.d_prim, g.d_dual, g.d_x, g.d_y, g.d_z, g.d_s,
                   g.d_obj, g.d_pri, g.d_dua, g.d_iter, g.d_status};
+  cudaSetDevice(g.device);
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (cudaEvent_t e : g.ev) if (e) cudaEventDestroy(e);
   g = Ctx();
   return CPG_B200_OK;
 }
@@ -115,8 +133,20 @@ int CPG_B200_FN(cpg_socp_dims)(CpgB200SocpDims* out) {
   return CPG_B200_OK;
 }
 
+int CPG_B200_FN(cpg_b200_kernel_times)(float* main_ms, float* tail_ms, float* grad_ms) {
+  USE_DEVICE();
+  if (main_ms) *main_ms = -1.f;
+  if (tail_ms) *tail_ms = -1.f;
+  if (grad_ms) *grad_ms = -1.f;
+  if (g.ev_solve && main_ms) {
+    CK(cudaEventSynchronize(g.ev[1]));
+    CK(cudaEventElapsedTime(main_ms, g.ev[0], g.ev[1]));
+  }
+  return CPG_B200_OK;
+}
+
 int CPG_B200_FN(cpg_socp_load_constants)(const void* smem_blob, int smem_nbytes, const void* gmem_blob, int gmem_nbytes) {
-  if (!g.ready) { snprintf(g.err, sizeof(g.err), "cpg_b200_init has not been called"); return CPG_B200_ERR_NOT_INIT; }
+  USE_DEVICE();
   if (!smem_blob || !gmem_blob || smem_nbytes != (int)CPG_B200_FN(cpg_ipm_sblob_nbytes) ||
       gmem_nbytes != (int)CPG_B200_FN(cpg_ipm_gblob_nbytes)) {
     snprintf(g.err, sizeof(g.err), "constant tables of a different layout: regenerate the code");
@@ -139,7 +169,7 @@ int CPG_B200_FN(cpg_socp_solve_batch_device)(int B, const double* params, double
                                              double* sol_x, double* sol_y, double* sol_z, double* sol_s,
                                              double* obj_val, int* iter, int* status, double* pri_res, double* dua_res,
                                              const CpgB200SocpSettings* settings, void* stream) {
-  if (!g.ready) { snprintf(g.err, sizeof(g.err), "cpg_b200_init has not been called"); return CPG_B200_ERR_NOT_INIT; }
+  USE_DEVICE();
   if (B < 0 || (B > 0 && (!prim || !dual || !obj_val || !iter || !status || !pri_res || !dua_res || (cpgipm::NPB > 0 && !params)))) {
     snprintf(g.err, sizeof(g.err), "null output pointer or negative batch size");
     return CPG_B200_ERR_BAD_ARG;
@@ -154,8 +184,11 @@ int CPG_B200_FN(cpg_socp_solve_batch_device)(int B, const double* params, double
   CK(cudaMemsetAsync(g.d_counter, 0, sizeof(int), s));
   IpmIO io{B, params, prim, dual, sol_x, sol_y, sol_z, sol_s, obj_val, iter, status, pri_res, dua_res, g.d_best, g.d_counter};
   const int grid = B < g.n_sm ? B : g.n_sm;
+  CK(cudaEventRecord(g.ev[0], s));
   cpgipm::ipm_kernel<<<grid, cpgipm::T, cpgipm::SMEM_BYTES, s>>>(g.d_sblob, g.d_gblob, ks, io);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[1], s));
+  g.ev_solve = true;
   g.launches = 1;
   return CPG_B200_OK;
 }
@@ -164,7 +197,11 @@ int CPG_B200_FN(cpg_socp_solve_batch_host)(int B, const double* params, double* 
                                            double* sol_x, double* sol_y, double* sol_z, double* sol_s,
                                            double* obj_val, int* iter, int* status, double* pri_res, double* dua_res,
                                            const CpgB200SocpSettings* settings) {
-  if (!g.ready) { snprintf(g.err, sizeof(g.err), "cpg_b200_init has not been called"); return CPG_B200_ERR_NOT_INIT; }
+  USE_DEVICE();
+  if (B < 0 || (B > 0 && (!prim || !dual || !obj_val || !iter || !status || !pri_res || !dua_res || (cpgipm::NPB > 0 && !params)))) {
+    snprintf(g.err, sizeof(g.err), "null output pointer or negative batch size");
+    return CPG_B200_ERR_BAD_ARG;
+  }
   if (B == 0) { g.launches = 0; return CPG_B200_OK; }
   int rc;
   if ((rc = ensure_staging(B))) return rc;

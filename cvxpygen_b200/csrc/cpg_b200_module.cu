@@ -83,6 +83,9 @@ struct Ctx {
   double *d_solx = nullptr, *d_soly = nullptr, *d_obj = nullptr, *d_pri = nullptr, *d_dua = nullptr;
   int *d_iter = nullptr, *d_status = nullptr;
   int launches = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // solve: before / after main / after tail; [3] unused
+  cudaEvent_t gev[2] = {nullptr, nullptr};                   // backward pass: before / after
+  bool ev_solve = false, ev_grad = false;
   char err[256] = {0};
 } g;
 
@@ -93,6 +96,14 @@ struct Ctx {
       snprintf(g.err, sizeof(g.err), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
       return CPG_B200_ERR_CUDA;                                                                   \
     }                                                                                             \
+  } while (0)
+
+// Every entry point runs on the device the context was initialised for (one context per library: the library is a
+// per-process singleton bound to ONE device; a second device needs its own process -- bench.py / torchrun do that).
+#define USE_DEVICE()                                                                              \
+  do {                                                                                            \
+    if (!g.ready) { snprintf(g.err, sizeof(g.err), "cpg_b200_init has not been called"); return CPG_B200_ERR_NOT_INIT; } \
+    CK(cudaSetDevice(g.device));                                                                  \
   } while (0)
 
 int ensure_tail(int B) {
@@ -125,6 +136,7 @@ template <class Tp> Tp* mapped_view(Tp* host) {
 int ensure_staging(int B) {
   if (B <= g.cap_B) return CPG_B200_OK;
   int rc;
+  g.cap_B = 0;                 // a failed allocation below must not leave a stale capacity behind
   const int np = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words))->npb;
   const int npr = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words))->n_prim;
   const int ndu = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words))->n_dual;
@@ -151,6 +163,23 @@ extern "C" {
 const char* CPG_B200_FN(cpg_b200_last_error)(void) { return g.err; }
 int CPG_B200_FN(cpg_b200_launch_count)(void) { return g.launches; }
 
+int CPG_B200_FN(cpg_b200_kernel_times)(float* main_ms, float* tail_ms, float* grad_ms) {
+  USE_DEVICE();
+  if (main_ms) *main_ms = -1.f;
+  if (tail_ms) *tail_ms = -1.f;
+  if (grad_ms) *grad_ms = -1.f;
+  if (g.ev_solve) {
+    CK(cudaEventSynchronize(g.ev[2]));
+    if (main_ms) CK(cudaEventElapsedTime(main_ms, g.ev[0], g.ev[1]));
+    if (tail_ms) CK(cudaEventElapsedTime(tail_ms, g.ev[1], g.ev[2]));
+  }
+  if (g.ev_grad) {
+    CK(cudaEventSynchronize(g.gev[1]));
+    if (grad_ms) CK(cudaEventElapsedTime(grad_ms, g.gev[0], g.gev[1]));
+  }
+  return CPG_B200_OK;
+}
+
 void CPG_B200_FN(cpg_b200_default_settings)(CpgB200Settings* s) {
   if (!s) return;
   s->max_iter = 4000; s->check_termination = 25; s->scaled_termination = 0; s->warm_start = 0;
@@ -168,7 +197,7 @@ int CPG_B200_FN(cpg_b200_dims)(CpgB200Dims* out) {
 }
 
 int CPG_B200_FN(cpg_b200_load_constants)(const void* blob, int nbytes) {
-  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+  USE_DEVICE();
   if (!blob || nbytes <= 0 || nbytes > Fam::BLOB_BYTES_PAD) return CPG_B200_ERR_BAD_ARG;
   const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(blob);
   if (H->n != Fam::N || H->m != Fam::M || (int)H->total_bytes != nbytes || H->n_trail_tiles > Fam::TRAIL)
@@ -180,7 +209,7 @@ int CPG_B200_FN(cpg_b200_load_constants)(const void* blob, int nbytes) {
 int CPG_B200_FN(cpg_b200_load_constants_all)(const void* blob, int nbytes, const void* cblob, int cnbytes,
                                              const void* tail_blob, int tnbytes, const void* gblob, int gnbytes,
                                              const void* gS0, int snbytes) {
-  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+  USE_DEVICE();
   if (!blob || !cblob || !tail_blob || !gblob || !gS0) return CPG_B200_ERR_BAD_ARG;
   if (nbytes != (int)CPG_B200_FN(cpg_blob_nbytes) || cnbytes != (int)CPG_B200_FN(cpg_cblob_nbytes) ||
       tnbytes != (int)CPG_B200_FN(cpg_tail_blob_nbytes) || gnbytes != (int)CPG_B200_FN(cpg_gblob_nbytes) ||
@@ -196,7 +225,7 @@ int CPG_B200_FN(cpg_b200_load_constants_all)(const void* blob, int nbytes, const
 }
 
 int CPG_B200_FN(cpg_b200_load_mat_constants)(const void* mblob, int nbytes) {
-  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+  USE_DEVICE();
 #if CPG_FAM_MATPAR
   if (!mblob || nbytes != (int)CPG_B200_FN(cpg_mblob_nbytes)) return CPG_B200_ERR_BAD_ARG;
   CK(cudaDeviceSynchronize());
@@ -211,6 +240,11 @@ int CPG_B200_FN(cpg_b200_load_mat_constants)(const void* mblob, int nbytes) {
 
 int CPG_B200_FN(cpg_b200_init)(int device) {
   g.err[0] = 0;
+  if (g.ready && device != g.device) {
+    snprintf(g.err, sizeof(g.err), "this library is already initialised on device %d: one context per process "
+             "(use one process per GPU, or cpg_b200_free() first)", g.device);
+    return CPG_B200_ERR_BAD_ARG;
+  }
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
@@ -244,6 +278,8 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
   if (!g.d_counter) CK(cudaMalloc(&g.d_counter, sizeof(unsigned int)));
   if (!g.d_tail_count) CK(cudaMalloc(&g.d_tail_count, sizeof(int)));
   CK(cudaFuncSetAttribute(cpgb200::admm_multi_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  for (int k = 0; k < 4; ++k) if (!g.ev[k]) CK(cudaEventCreate(&g.ev[k]));
+  for (int k = 0; k < 2; ++k) if (!g.gev[k]) CK(cudaEventCreate(&g.gev[k]));
   g.ready = true;
   return CPG_B200_OK;
 }
@@ -251,7 +287,10 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
 int CPG_B200_FN(cpg_b200_free)(void) {
   void* ptrs[] = {g.d_blob, g.d_cblob, g.d_gblob, g.d_gS0, g.d_mblob, g.d_mat_scratch, g.g_soly, g.g_dprim, g.g_dparams, g.g_dq, g.g_dl, g.g_du, g.d_tail_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0,
                   g.d_prim, g.d_dual, g.d_solx, g.d_soly, g.d_obj, g.d_pri, g.d_dua, g.d_iter, g.d_status};
+  if (g.device >= 0) cudaSetDevice(g.device);
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (cudaEvent_t e : g.ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : g.gev) if (e) cudaEventDestroy(e);
   g = Ctx();
   return CPG_B200_OK;
 }
@@ -260,7 +299,7 @@ int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const doubl
                                         double* prim, double* dual, double* sol_x, double* sol_y,
                                         double* obj_val, int* iter, int* status, double* pri_res, double* dua_res,
                                         const CpgB200Settings* settings, void* stream_) {
-  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+  USE_DEVICE();
   if (B < 0 || !obj_val || !iter || !status || !pri_res || !dua_res) return CPG_B200_ERR_BAD_ARG;
   g.launches = 0;
   if (B == 0) return CPG_B200_OK;
@@ -291,9 +330,13 @@ int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const doubl
     int grid = g.n_sm;
     const int need = (B + Fam::MAT_WARPS - 1) / Fam::MAT_WARPS;
     if (grid > need) grid = need;
+    CK(cudaEventRecord(g.ev[0], stream));
     cpgb200::admm_matpar_kernel<Fam><<<grid, Fam::MAT_WARPS * 32, MAT_SMEM_BYTES, stream>>>(g.d_cblob, g.d_tail_blob, g.d_mblob, g.d_mat_scratch, io, st);
     g.launches += 1;
     CK(cudaGetLastError());
+    CK(cudaEventRecord(g.ev[1], stream));
+    CK(cudaEventRecord(g.ev[2], stream));
+    g.ev_solve = true;
     return CPG_B200_OK;
   }
 #endif
@@ -302,14 +345,18 @@ int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const doubl
   int grid = g.n_sm;
   const int need = (B + Fam::NI - 1) / Fam::NI;
   if (grid > need) grid = need;
+  CK(cudaEventRecord(g.ev[0], stream));
   cpgb200::admm_multi_kernel<Fam><<<grid, Fam::WARPS * 32, SMEM_BYTES, stream>>>(g.d_blob, io, st);
   g.launches += 1;
   CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[1], stream));
   // instances that changed rho (or a constraint type) continue with their own factor; the kernel exits at once
   // when the hand-off queue is empty (no host round trip to find out)
   cpgb200::admm_tail_kernel<Fam><<<g.n_sm, Fam::TAIL_WARPS * 32, TAIL_SMEM_BYTES, stream>>>(g.d_cblob, g.d_tail_blob, io, st);
   g.launches += 1;
   CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[2], stream));
+  g.ev_solve = true;
   return CPG_B200_OK;
 }
 
@@ -317,7 +364,7 @@ int CPG_B200_FN(cpg_solve_batch_host)(int B, const double* params, const double*
                                       double* prim, double* dual, double* sol_x, double* sol_y,
                                       double* obj_val, int* iter, int* status, double* pri_res, double* dua_res,
                                       const CpgB200Settings* settings) {
-  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+  USE_DEVICE();
   if (B < 0 || !obj_val || !iter || !status || !pri_res || !dua_res) return CPG_B200_ERR_BAD_ARG;
   if (B == 0) { g.launches = 0; return CPG_B200_OK; }
   const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words));
@@ -361,7 +408,7 @@ int CPG_B200_FN(cpg_solve_batch_host)(int B, const double* params, const double*
 int CPG_B200_FN(cpg_gradient_batch_device)(int B, const double* sol_x, const double* sol_y, const double* dprim,
                                            double* dparams, double* dq, double* dl, double* du, void* stream_) {
   (void)sol_x;   // only enters dP / dA (matrix parameters are shared in this build)
-  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+  USE_DEVICE();
 #if CPG_FAM_MATPAR
   snprintf(g.err, sizeof(g.err), "this family has per-instance matrix parameters: call cpg_gradient_batch_*_mat (it needs the parameter rows)");
   return CPG_B200_ERR_BAD_ARG;
@@ -374,17 +421,20 @@ int CPG_B200_FN(cpg_gradient_batch_device)(int B, const double* sol_x, const dou
   int grid = g.n_sm;
   const int need = (B + Fam::GRAD_WARPS - 1) / Fam::GRAD_WARPS;
   if (grid > need) grid = need;
+  CK(cudaEventRecord(g.gev[0], reinterpret_cast<cudaStream_t>(stream_)));
   cpgb200::qp_grad_kernel<Fam><<<grid, Fam::GRAD_WARPS * 32, GRAD_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream_)>>>(
       g.d_gblob, g.d_tail_blob, io);
   g.launches += 1;
   CK(cudaGetLastError());
+  CK(cudaEventRecord(g.gev[1], reinterpret_cast<cudaStream_t>(stream_)));
+  g.ev_grad = true;
   return CPG_B200_OK;
 }
 
 int CPG_B200_FN(cpg_gradient_batch_device_mat)(int B, const double* params, const double* sol_x, const double* sol_y,
                                                const double* dprim, double* dparams, double* dq, double* dl, double* du,
                                                double* dP, double* dA, void* stream_) {
-  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+  USE_DEVICE();
 #if CPG_FAM_MATPAR
   if (B < 0 || !params || !sol_x || !sol_y || !dprim) return CPG_B200_ERR_BAD_ARG;
   g.launches = 0;
@@ -395,10 +445,13 @@ int CPG_B200_FN(cpg_gradient_batch_device_mat)(int B, const double* params, cons
   int grid = g.n_sm;
   const int need = (B + Fam::GRAD_WARPS - 1) / Fam::GRAD_WARPS;
   if (grid > need) grid = need;
+  CK(cudaEventRecord(g.gev[0], reinterpret_cast<cudaStream_t>(stream_)));
   cpgb200::qp_grad_kernel<Fam, true><<<grid, Fam::GRAD_WARPS * 32, GRAD_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream_)>>>(
       g.d_gblob, g.d_tail_blob, io);
   g.launches += 1;
   CK(cudaGetLastError());
+  CK(cudaEventRecord(g.gev[1], reinterpret_cast<cudaStream_t>(stream_)));
+  g.ev_grad = true;
   return CPG_B200_OK;
 #else
   (void)B; (void)params; (void)sol_x; (void)sol_y; (void)dprim; (void)dparams; (void)dq; (void)dl; (void)du; (void)dP; (void)dA; (void)stream_;
@@ -410,7 +463,7 @@ int CPG_B200_FN(cpg_gradient_batch_device_mat)(int B, const double* params, cons
 int CPG_B200_FN(cpg_gradient_batch_host_mat)(int B, const double* params, const double* sol_x, const double* sol_y,
                                              const double* dprim, double* dparams, double* dq, double* dl, double* du,
                                              double* dP, double* dA) {
-  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+  USE_DEVICE();
 #if CPG_FAM_MATPAR
   if (B < 0 || !params || !sol_x || !sol_y || !dprim) return CPG_B200_ERR_BAD_ARG;
   if (B == 0) { g.launches = 0; return CPG_B200_OK; }
@@ -447,12 +500,13 @@ int CPG_B200_FN(cpg_gradient_batch_host_mat)(int B, const double* params, const 
 
 int CPG_B200_FN(cpg_gradient_batch_host)(int B, const double* sol_x, const double* sol_y, const double* dprim,
                                          double* dparams, double* dq, double* dl, double* du) {
-  if (!g.ready) return CPG_B200_ERR_NOT_INIT;
+  USE_DEVICE();
   if (B < 0 || !sol_y || !dprim) return CPG_B200_ERR_BAD_ARG;
   if (B == 0) { g.launches = 0; return CPG_B200_OK; }
   const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words));
   int rc;
   if (B > g.cap_G) {
+    g.cap_G = 0;
     if ((rc = grow(&g.g_soly, (size_t)B * (Fam::M > 0 ? Fam::M : 1)))) return rc;
     if ((rc = grow(&g.g_dprim, (size_t)B * (H->n_prim > 0 ? H->n_prim : 1)))) return rc;
     if ((rc = grow(&g.g_dparams, (size_t)B * (H->npb > 0 ? H->npb : 1)))) return rc;

@@ -54,6 +54,8 @@ class QPSetup:
     theta_shared: Optional[np.ndarray] = None
     batch_cols: Optional[np.ndarray] = None
     stats: Dict[str, float] = field(default_factory=dict)
+    max_group_rows: int = 32
+    allow_trailing: bool = True
 
 
 def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
@@ -144,7 +146,8 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
                    scaling=scaling, D=sc['D'], E=sc['E'], c=sc['c'], ctype=ctype, P_scaled=sc['P'],
                    A_scaled=sc['A'], factor=F, schedule=S, prim_idx=prim_idx, dual_idx=dual_idx, blob=blob, tail_blob=tail_blob, blob_compact=blob_compact, grad_blob=grad_blob, grad_S0=grad_S0, mat_blob=mat_blob, mat_params=mat_params,
                    nnzP=int(sp.csc_matrix(P).indptr[-1]), nnzA=int(sp.csc_matrix(A).indptr[-1]), refactor=RT, solve_source=solve_source,
-                   theta_shared=theta0, batch_cols=bcols, stats=st)
+                   theta_shared=theta0, batch_cols=bcols, stats=st,
+                   max_group_rows=max_group_rows, allow_trailing=allow_trailing)
 
 
 def unscale_roundtrip(sc, scaling):

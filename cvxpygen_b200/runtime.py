@@ -72,6 +72,13 @@ class Module:
     def _fn(self, name):
         return getattr(self.lib, self.prefix + name)
 
+    @staticmethod
+    def _expect(a, shape, what):
+        """The C entries take raw pointers: a mismatched array would be read past its end.  None in `shape` = any."""
+        got = tuple(a.shape)
+        if len(got) != len(shape) or any(s is not None and s != g for s, g in zip(shape, got)):
+            raise ValueError(f'{what}: expected shape {tuple("B" if s is None else s for s in shape)}, got {got}')
+
     def _check(self, rc):
         if rc != 0:
             msg = self._fn('cpg_b200_last_error')()
@@ -109,7 +116,8 @@ class Module:
                 raise ValueError(f'parameter {name} stores {p.size} entries, got {v.size}')
             self._theta[p.col:p.col + p.size] = v
         st = setup_qp_family(fam, saved['batch_params'], theta=self._theta, rho=saved['rho'], sigma=saved['sigma'],
-                             scaling=saved['scaling'])
+                             scaling=saved['scaling'], max_group_rows=saved.get('max_group_rows', 32),
+                             allow_trailing=saved.get('allow_trailing', True))
         if st.solve_source != saved['solve_source']:
             raise RuntimeError('the new parameter values change the sparsity structure of the KKT factor schedule: '
                                'regenerate the code (cpg.generate_code)')
@@ -124,6 +132,13 @@ class Module:
 
     def launch_count(self):
         return int(self._fn('cpg_b200_launch_count')())
+
+    def kernel_times(self):
+        """Device milliseconds of the kernels of the last solve / gradient call (CUDA events recorded by the library on the
+        caller's stream around each launch): dict(main=, tail=, grad=), None where nothing was launched."""
+        t = [C.c_float(-1.0) for _ in range(3)]
+        self._check(self._fn('cpg_b200_kernel_times')(*[C.byref(v) for v in t]))
+        return {k: (None if v.value < 0 else float(v.value)) for k, v in zip(('main', 'tail', 'grad'), t)}
 
     # ---- settings (b2: cpg_set_solver_default_settings / cpg_set_solver_<name>)
     def set_solver_default_settings(self):
@@ -209,8 +224,9 @@ class Module:
             self.set_solver_setting(k, v)
         P = params if isinstance(params, np.ndarray) else self.pack_params(params)
         P = np.ascontiguousarray(P, dtype=np.float64)
-        B = P.shape[0]
         d = self.dims
+        self._expect(P, (None, d.n_param), 'params')
+        B = P.shape[0]
         prim = np.empty((B, d.n_prim)); dual = np.empty((B, d.n_dual))
         solx = np.empty((B, d.n_var)) if return_canonical else None
         soly = np.empty((B, d.n_con)) if return_canonical else None
@@ -219,6 +235,7 @@ class Module:
         s = self.settings
         if x0 is not None and y0 is not None:
             x0 = np.ascontiguousarray(x0, dtype=np.float64); y0 = np.ascontiguousarray(y0, dtype=np.float64)
+            self._expect(x0, (B, d.n_var), 'x0'); self._expect(y0, (B, d.n_con), 'y0')
             s = CpgB200Settings.from_buffer_copy(bytes(self.settings)); s.warm_start = 1
 
         def p(a, t=C.c_double):
@@ -251,9 +268,15 @@ class Module:
         import torch
         self.init()
         assert params.is_cuda and params.dtype == torch.float64 and params.is_contiguous()
-        B = params.shape[0]
         d = self.dims
+        self._expect(params, (None, d.n_param), 'params')
+        B = params.shape[0]
         dev = params.device
+        if dev.index is not None and dev.index != self.device:
+            raise ValueError(f'params live on cuda:{dev.index}, this library is bound to cuda:{self.device}')
+        for nm, t, w in (('x0', x0, d.n_var), ('y0', y0, d.n_con)):
+            if t is not None:
+                self._expect(t, (B, w), nm)
         if out is None:
             out = SimpleNamespace(
                 prim=torch.empty((B, d.n_prim), dtype=torch.float64, device=dev),
@@ -310,6 +333,8 @@ class Module:
             P = np.ascontiguousarray(np.broadcast_to(P, (B, P.shape[1])))
         D = np.ascontiguousarray(dprim if isinstance(dprim, np.ndarray) else self.pack_dprim(dprim, B), dtype=np.float64)
         d = self.dims
+        self._expect(P, (B, d.n_param), 'params'); self._expect(sol_x, (B, d.n_var), 'sol_x')
+        self._expect(sol_y, (B, d.n_con), 'sol_y'); self._expect(D, (B, d.n_prim), 'dprim')
         dpar = np.empty((B, d.n_param))
         dq = np.empty((B, d.n_var)) if return_canonical else None
         dl = np.empty((B, d.n_con)) if return_canonical else None
@@ -341,6 +366,7 @@ class Module:
         B = sol_y.shape[0]
         D = np.ascontiguousarray(dprim if isinstance(dprim, np.ndarray) else self.pack_dprim(dprim, B), dtype=np.float64)
         d = self.dims
+        self._expect(sol_y, (B, d.n_con), 'sol_y'); self._expect(D, (B, d.n_prim), 'dprim')
         dpar = np.empty((B, d.n_param))
         dq = np.empty((B, d.n_var)) if return_canonical else None
         dl = np.empty((B, d.n_con)) if return_canonical else None
@@ -349,6 +375,17 @@ class Module:
         self._check(self._fn('cpg_gradient_batch_host')(C.c_int(B), None, p(sol_y), p(D), p(dpar), p(dq), p(dl), p(du)))
         res = self.unpack_dparams(dpar)
         return (res, dq, dl, du) if return_canonical else res
+
+    def gradient_batch_pinned(self, sol_y, dprim, dparams):
+        """Host-buffer backward entry on caller-owned (ideally pinned) torch CPU tensors: H2D of sol_y / dprim, the backward
+        kernel, D2H of dparams -- no allocation or copy on the Python side."""
+        self.init()
+        d = self.dims
+        B = sol_y.shape[0]
+        self._expect(sol_y, (B, d.n_con), 'sol_y'); self._expect(dprim, (B, d.n_prim), 'dprim'); self._expect(dparams, (B, d.n_param), 'dparams')
+        ptr = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+        self._check(self._fn('cpg_gradient_batch_host')(C.c_int(B), None, ptr(sol_y), ptr(dprim), ptr(dparams), None, None, None))
+        return dparams
 
     def gradient_batch_device(self, sol_y, dprim, dparams=None):
         import torch
@@ -464,14 +501,20 @@ class SocpModule(Module):
         self._check(self._fn('cpg_socp_load_constants')(*b(st.smem_blob), *b(st.gmem_blob)))
         return st
 
+    def _qp_only(self, *a, **k):
+        raise NotImplementedError('IPM-CUDA libraries carry no QP backward pass / warm start: the conic gradient goes through '
+                                  'cvxpygen_b200.conic_grad (two-stage route, cvxpygen/canonicalizer.py:54-65)')
+    gradient_batch = gradient_batch_device = gradient_batch_mat = gradient_batch_device_mat = _qp_only
+
     def solve_batch(self, params, return_canonical=False, **settings):
         self.init()
         for k, v in settings.items():
             self.set_solver_setting(k, v)
         P = params if isinstance(params, np.ndarray) else self.pack_params(params)
         P = np.ascontiguousarray(P, dtype=np.float64)
-        B = P.shape[0]
         d = self.dims
+        self._expect(P, (None, d.n_param), 'params')
+        B = P.shape[0]
         prim = np.empty((B, d.n_prim)); dual = np.empty((B, d.n_dual))
         x = np.empty((B, d.n_var)) if return_canonical else None
         y = np.empty((B, d.n_eq)) if return_canonical else None

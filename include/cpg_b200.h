@@ -77,12 +77,20 @@ typedef struct {
   int warps_per_cta, smem_bytes;
 } CpgB200Dims;
 
+/* One context per library and process, bound to ONE device: every entry point makes that device current
+ * (cudaSetDevice) before it touches CUDA; a second cpg_b200_init with another device is CPG_B200_ERR_BAD_ARG
+ * (multi-GPU = one process per GPU, or cvxpygen_b200.multi: one library copy per device). */
 int  CPG_B200_FN(cpg_b200_init)(int device);                 /* upload constants, allocate queues  */
 int  CPG_B200_FN(cpg_b200_free)(void);
 int  CPG_B200_FN(cpg_b200_dims)(CpgB200Dims* out);
 void CPG_B200_FN(cpg_b200_default_settings)(CpgB200Settings* s);
 const char* CPG_B200_FN(cpg_b200_last_error)(void);
 int  CPG_B200_FN(cpg_b200_launch_count)(void);               /* kernels launched by the last solve call */
+/* Device time of the kernels of the LAST solve / gradient call, from CUDA events recorded on the caller's stream around
+ * each launch (blocks until they have completed): main solve kernel (admm_multi_kernel or admm_matpar_kernel), the
+ * refactorisation kernel (admm_tail_kernel), the backward kernel (qp_grad_kernel); -1 where nothing was launched.
+ * This is what bench.py's roofline block divides the algorithmic bytes by. */
+int  CPG_B200_FN(cpg_b200_kernel_times)(float* main_ms, float* tail_ms, float* grad_ms);
 /* Replace the constants blob (shared parameters changed => host re-ran the offline setup). */
 int  CPG_B200_FN(cpg_b200_load_constants)(const void* blob, int nbytes);
 /* Replace EVERY constants table after a shared-parameter update (role of osqp_update_data_mat -> re-scale + refactor,

@@ -57,6 +57,10 @@ int  CPG_B200_FN(cpg_b200_init)(int device);                 /* upload the const
 int  CPG_B200_FN(cpg_b200_free)(void);
 const char* CPG_B200_FN(cpg_b200_last_error)(void);
 int  CPG_B200_FN(cpg_b200_launch_count)(void);               /* kernels launched by the last solve call */
+/* Device time of the last ipm_kernel launch from CUDA events on the caller's stream (blocks until it has completed);
+ * tail_ms / grad_ms are -1 (same signature as the QP libraries' entry).  One context per library and process, bound
+ * to one device: every entry point makes it current; a second cpg_b200_init with another device is an error. */
+int  CPG_B200_FN(cpg_b200_kernel_times)(float* main_ms, float* tail_ms, float* grad_ms);
 int  CPG_B200_FN(cpg_socp_dims)(CpgB200SocpDims* out);
 /* Replace the constant tables after a change of SHARED (non-batched) user parameters: the host re-runs the offline setup
  * (equilibration, KKT base image, affine maps) and uploads both images.  Role of ECOS_updateData for data every instance
