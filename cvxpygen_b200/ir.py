@@ -131,8 +131,11 @@ class CanonFamily:
         n, m = P.shape[0], A.shape[0]
         q = np.asarray(q, dtype=float).ravel(); l = np.asarray(l, dtype=float).ravel(); u = np.asarray(u, dtype=float).ravel()
         specs = [('q', (n,), q), ('l', (m,), l), ('u', (m,), u)]
-        if matrix_params:
-            specs += [('P', (P.nnz,), P.data), ('A', (A.nnz,), A.data)]
+        mats = ('P', 'A') if matrix_params is True else tuple(matrix_params or ())     # True = both; or a subset, e.g. ('A',)
+        if 'P' in mats:
+            specs.append(('P', (P.nnz,), P.data))
+        if 'A' in mats:
+            specs.append(('A', (A.nnz,), A.data))
         params, col = [], 0
         for nm, shape, default in specs:
             params.append(UserParam(nm, tuple(shape), int(np.asarray(default).size), col, np.array(default, dtype=float)))
@@ -143,8 +146,8 @@ class CanonFamily:
                                         shape=(len(v), n_theta))
         pc = {p.name: p.col for p in params}
         maps = {'q': ident(n, pc['q']), 'l': ident(m, pc['l']), 'u': ident(m, pc['u']), 'd': sp.csr_matrix((1, n_theta)),
-                'P': ident(P.nnz, pc['P']) if matrix_params else const(P.data),
-                'A': ident(A.nnz, pc['A']) if matrix_params else const(A.data)}
+                'P': ident(P.nnz, pc['P']) if 'P' in mats else const(P.data),
+                'A': ident(A.nnz, pc['A']) if 'A' in mats else const(A.data)}
         if n_eq is None:
             n_eq = int(np.sum(l == u))
         pat = lambda M: (M.indices.astype(np.int32), M.indptr.astype(np.int32), M.shape)

@@ -206,10 +206,9 @@ def _batch_cpp(fam, canon, iface, prefix):
     pc = canon.parameter_canon
     n, m = iface.n_var, iface.n_eq + iface.n_ineq
     setup = iface.setup
-    mats = bool(setup.mat_params)
     lines = []
     off = 0
-    for pid, size in (('q', n), ('l', m), ('u', m)) + ((('P', setup.nnzP), ('A', setup.nnzA)) if mats else ()):
+    for pid, size in (('q', n), ('l', m), ('u', m)) + tuple((k, {'P': setup.nnzP, 'A': setup.nnzA}[k]) for k in ('P', 'A') if k in setup.mat_params):
         acc = '->x' if pid.isupper() else ''
         if pc.p_id_to_changes.get(pid):
             lines.append(f'    apply_map(&{prefix}canon_{pid}_map, {size}, theta.data(), r + {off});')

@@ -220,13 +220,16 @@ class ADMMCUDAInterface(*_BASES):
         from ..shim import write_shim
         pc = canon.parameter_canon
         changes = {k: bool(v) for k, v in pc.p_id_to_changes.items()}
-        mats = bool(changes.get('P')) or bool(changes.get('A'))
+        import numpy as np
+        # a matrix is a per-instance input only if a user parameter enters it: the other one keeps OSQP's semantics of a NULL
+        # argument to osqp_update_data_mat (cvxpygen/solvers/osqp.py:20-33)
+        mats = tuple(k for k in ('P', 'A') if changes.get(k))
         name = getattr(self.family, 'name', None) or os.path.basename(os.path.abspath(code_dir))
-        fam = CanonFamily.from_canonical_qp(name + '_canonical', pc.p['P'], pc.p['q'], pc.p['A'], pc.p['l'], pc.p['u'],
+        clip = lambda v: np.clip(np.asarray(v, dtype=float), -1e30, 1e30)     # the writer emits +-inf as +-1e30 too (utils.replace_inf)
+        fam = CanonFamily.from_canonical_qp(name + '_canonical', pc.p['P'], pc.p['q'], pc.p['A'], clip(pc.p['l']), clip(pc.p['u']),
                                             n_eq=self.n_eq, matrix_params=mats)
         fam.is_maximization = False      # the sign flip is applied by the emitted cpg_retrieve_info (cvxpygen/utils.py:980)
-        batch = ['q', 'l', 'u'] + (['P', 'A'] if mats else [])
-        self.setup = setup_qp_family(fam, batch)
+        self.setup = setup_qp_family(fam, ['q', 'l', 'u'] + list(mats))
         cprefix = prefix or ''
         codegen.write_solver_sources(self.setup, solver_code_dir, prefix=cprefix)
         write_shim(self.setup, solver_code_dir, cprefix, matrices=mats)
