@@ -16,16 +16,24 @@ from .ir import CanonFamily
 SOLVERS = ('ADMM-CUDA', 'IPM-CUDA')
 
 
-def _canonicalize_with_reference(problem, solver_opts, enable_settings):
-    """cvxpy-present path: run the reference's canonicaliser for its OSQP form and convert to the IR."""
+# the reference solver whose canonical form each backend consumes (QP form of OSQP / conic form of ECOS)
+REFERENCE_FORM = {'ADMM-CUDA': 'OSQP', 'IPM-CUDA': 'ECOS'}
+
+
+def _canonicalize_with_reference(problem, solver_opts, enable_settings, solver='ADMM-CUDA'):
+    """cvxpy-present path: run the reference's canonicaliser for the form the backend consumes and convert to the IR."""
     try:
         from cvxpygen.canonicalizer import Canonicalizer      # reference package, if installed
     except ImportError as e:
         raise ImportError('generate_code was given a cvxpy Problem, which needs cvxpy and cvxpygen to be '
                           'importable for canonicalisation; pass a cvxpygen_b200.ir.CanonFamily instead') from e
-    canon, interface = Canonicalizer(solver='OSQP', solver_opts=solver_opts,
+    canon, interface = Canonicalizer(solver=REFERENCE_FORM[solver.upper()], solver_opts=solver_opts,
                                      enable_settings=enable_settings).canonicalize(problem)
-    return CanonFamily.from_reference_canon('problem', canon, interface)
+    fam = CanonFamily.from_reference_canon('problem', canon, interface)
+    if fam.solver_type == 'conic':           # cone sizes: ECOSInterface.canon_constants (cvxpygen/solvers/ecos.py:76-83)
+        cc = interface.canon_constants
+        fam.cone_dims = {'l': int(cc['l']), 'q': [int(v) for v in cc['q']]}
+    return fam
 
 
 def generate_code(problem, code_dir='cpg_code', solver=None, solver_opts=None, enable_settings=[],
@@ -39,7 +47,7 @@ def generate_code(problem, code_dir='cpg_code', solver=None, solver_opts=None, e
     # gradient=True needs nothing extra: every generated library carries the batched backward pass
     # (cpg_gradient_batch_*); the flag is accepted for signature compatibility with the reference.
     sys.stdout.write(f'Generating code with cvxpygen_b200 ({solver.upper()}, sm_100a) ...\n')
-    fam = problem if isinstance(problem, CanonFamily) else _canonicalize_with_reference(problem, solver_opts, enable_settings)
+    fam = problem if isinstance(problem, CanonFamily) else _canonicalize_with_reference(problem, solver_opts, enable_settings, solver)
     if not fam.params:
         raise ValueError('Solution does not depend on parameters. Aborting code generation.')  # canonicalizer.py:98-99
     opts = dict(solver_opts or {})

@@ -164,6 +164,40 @@ class Module:
     def cpg_updated(self):
         return SimpleNamespace(**{p['name']: False for p in self.meta['params']})
 
+    # gradient=True flavour of the pybind module (cvxpygen/utils.py:1272-1328, 1364-1405): cpg_gsol / cpg_vdelta / gradient
+    def cpg_gsol(self):
+        return SimpleNamespace(primal=None, dual=None)
+
+    def cpg_vdelta(self):
+        return SimpleNamespace(**{v['name']: ([0.0] * v['size'] if v['size'] > 1 else 0.0) for v in self.meta['variables']})
+
+    def gradient(self, vdelta, gsol, use_sol):
+        """cpg_module.gradient(vdelta, gsol, use_sol) -> pdelta: the backward pass of ONE instance (a batch of one on the GPU)
+        at the canonical solution in `gsol` (use_sol) or at the last `solve`.  pdelta carries one attribute per user
+        parameter; parameters that are shared by the batch in this generated code (folded into the constants) get None."""
+        if use_sol:
+            sx, sy = np.asarray(gsol.primal, dtype=np.float64)[None, :], np.asarray(gsol.dual, dtype=np.float64)[None, :]
+        else:
+            if getattr(self, '_last', None) is None:
+                raise RuntimeError('cpg_module.gradient: no previous solve and no solution passed (use_sol)')
+            sx, sy = self._last['sol_x'], self._last['sol_y']
+        d = np.zeros((1, self.dims.n_prim))
+        for v in self.meta['variables']:
+            d[0, v['offset']:v['offset'] + v['size']] = np.atleast_1d(np.asarray(getattr(vdelta, v['name']), dtype=np.float64)).ravel()
+        if self.has_matrix_params:
+            if getattr(self, '_last', None) is None:
+                raise RuntimeError('cpg_module.gradient: a family with per-instance matrices needs the parameters of the last solve')
+            res = self.gradient_batch_mat(self._last['params'], sx, sy, d)
+        else:
+            res = self.gradient_batch(sy, d)
+        out = {}
+        for p in self.meta['params']:
+            if p['batched']:
+                out[p['name']] = res[p['name']][0].tolist() if p['size'] > 1 else float(res[p['name']][0, 0])
+            else:
+                out[p['name']] = None
+        return SimpleNamespace(**out)
+
     # ---- packing helpers
     def pack_params(self, params, B=None):
         """dict name -> (B, size) | (B, *shape) | (size,) broadcast  ->  (B, n_param) float64, batched params only.
@@ -407,14 +441,15 @@ class Module:
                 vals[p['name']] = np.atleast_1d(np.asarray(getattr(par, p['name']), dtype=np.float64)).reshape(1, -1)
             elif getattr(upd, p['name'], False):
                 raise ValueError(f"parameter {p['name']} is shared in this generated code; regenerate or use update_shared_params")
-        r = self.solve_batch(vals)
+        r = self.solve_batch(vals, return_canonical=True)
+        self._last = dict(params=self.pack_params(vals), sol_x=r.sol_x, sol_y=r.sol_y)     # what gradient() differentiates at
         prim = SimpleNamespace(**{k: (v[0].flatten(order='F').tolist() if v[0].size > 1 else float(v[0].ravel()[0]))
                                   for k, v in r.cpg_prim.items()})
         dual = SimpleNamespace(**{k: (v[0].tolist() if v[0].size > 1 else float(v[0].ravel()[0])) for k, v in r.cpg_dual.items()})
         info = SimpleNamespace(obj_val=float(r.cpg_info.obj_val[0]), iter=int(r.cpg_info.iter[0]),
                                status=STATUS_STRINGS.get(int(r.cpg_info.status[0]), 'unknown'),
                                pri_res=float(r.cpg_info.pri_res[0]), dua_res=float(r.cpg_info.dua_res[0]),
-                               time=r.cpg_info.time)
+                               time=r.cpg_info.time, gradient_primal=r.sol_x[0].tolist(), gradient_dual=r.sol_y[0].tolist())
         return SimpleNamespace(cpg_prim=prim, cpg_dual=dual, cpg_info=info)
 
 

@@ -134,6 +134,7 @@ class ADMMCUDAInterface(*_BASES):
     stgs_requires_extra_struct_type = False
     stgs_direct_write_ptr = '(&{prefix}cpg_b200_shim_settings)'
     stgs_reset_function = {'name': 'cpg_b200_shim_default_settings', 'ptr': '&{prefix}cpg_b200_shim_settings'}
+    stgs = {n: Setting(t, d, en, cv) for n, t, d, en, cv in _STGS}
     docu = 'DESIGN.md'
 
     def __init__(self, data=None, p_prob=None, enable_settings=(), family=None):

@@ -101,11 +101,17 @@ def test_plugin_classes_carry_the_reference_interface():
     osqp = _class_level_names(os.path.join(sol, 'osqp.py'), 'OSQPInterface') | \
         _class_level_names(os.path.join(sol, '_interface.py'), 'QPCanonMixin')
     ecos = _class_level_names(os.path.join(sol, 'ecos.py'), 'ECOSInterface')
-    cpu_only = {'ws_ptrs', 'get_affine_map', 'augment_vector_parameter', 'cmake_context_extra', 'setup_py_context',
-                'declare_workspace', 'define_workspace', '__init__'}
-    for ours, ref in ((ADMMCUDAInterface, osqp), (IPMCUDAInterface, ecos)):
-        missing = {n for n in ref - cpu_only if not hasattr(ours, n)}
-        assert not missing, (ours.__name__, sorted(missing))
+    # the QP plugin carries EVERYTHING the writer reads (it is driven by the reference's own writer in tests/test_refwriter.py);
+    # only the cvxpy-side affine-map plumbing, which the reference mixin provides when cvxpygen is importable, is left out
+    cvxpy_side = {'get_affine_map', 'augment_vector_parameter', '__init__'}
+    missing = {n for n in osqp - cvxpy_side if not hasattr(ADMMCUDAInterface, n)}
+    assert not missing, sorted(missing)
+    for n in ('ws_ptrs', 'declare_workspace', 'define_workspace', 'cmake_context_extra', 'setup_py_context', 'parameter_update_structure'):
+        assert hasattr(ADMMCUDAInterface, n), n
+    assert set(ADMMCUDAInterface.parameter_update_structure) == {'PA', 'P', 'A', 'qlu', 'ql', 'qu', 'lu', 'q', 'l', 'u'}   # osqp.py:20-61
+    cpu_only = cvxpy_side | {'ws_ptrs', 'cmake_context_extra', 'setup_py_context', 'declare_workspace', 'define_workspace'}
+    missing = {n for n in ecos - cpu_only if not hasattr(IPMCUDAInterface, n)}
+    assert not missing, ('IPMCUDAInterface', sorted(missing))
     assert ADMMCUDAInterface.canon_p_ids == ['P', 'q', 'd', 'A', 'l', 'u'] and IPMCUDAInterface.canon_p_ids == ['c', 'd', 'A', 'b', 'G', 'h']
     assert IPMCUDAInterface.status_is_int and IPMCUDAInterface.dual_var_names == ['y', 'z'] and IPMCUDAInterface.dual_var_split
     i = IPMCUDAInterface(family=families.adp_socp())
