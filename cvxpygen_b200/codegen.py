@@ -48,7 +48,11 @@ def c_ident(prefix: str) -> str:
     return f'{prefix}_' if prefix else ''
 
 
-def _family_header(setup: QPSetup, prefix: str, warps: Optional[int], ni: Optional[int] = None) -> str:
+DMMA_MAX_GROUPS = 3         # 12 warps x <= 170 registers
+
+
+def _family_header(setup: QPSetup, prefix: str, warps: Optional[int], ni: Optional[int] = None, dmma: Optional[bool] = None,
+                   dmma_groups: Optional[int] = None) -> str:
     nk = setup.n + setup.m
     w_stride = nk + (nk % 2)
     blob_pad = (len(setup.blob) + 127) // 128 * 128
@@ -82,6 +86,15 @@ def _family_header(setup: QPSetup, prefix: str, warps: Optional[int], ni: Option
     mat_warps = max(1, min(8, SMEM_BUDGET // (mat_stride * 8)))
     if matpar and mat_stride * 8 > SMEM_BUDGET:
         raise ValueError('one instance of this family (factor + matrices) does not fit in shared memory')
+    # FP64 tensor-core main kernel (admm_dmma_kernel): groups of four warps x eight instances; per group w8 (positions padded to a
+    # multiple of 4, x 8 instances) + the staging buffer; chosen when its tables fit next to the compact blob with >= 2 groups
+    dm_w8 = (nk + 3) // 4 * 4 * 8
+    dm_stage = 4 * max(setup.dmma_rounds, 1) * 64
+    dm_bv = 2 * nb_slots + 2
+    dblob_pad = (len(setup.dmma_blob) + 127) // 128 * 128
+    dm_fixed = cblob_pad + dblob_pad + 64
+    dm_groups = min(dmma_groups or DMMA_MAX_GROUPS, (SMEM_BUDGET - dm_fixed) // ((dm_w8 + dm_stage + 4 * dm_bv) * 8)) if setup.dmma_blob else 0
+    use_dmma = int(bool(setup.dmma_blob) and dm_groups >= 2 and dmma is not False and dm_w8 // 4 >= 2 * w_stride)
     lines = [
         '/* Auto-generated by cvxpygen_b200 %s -- compile-time sizes of problem family "%s". */' % (time.strftime('%Y-%m-%d'), setup.family.name),
         '#ifndef CPG_FAMILY_H', '#define CPG_FAMILY_H',
@@ -98,6 +111,8 @@ def _family_header(setup: QPSetup, prefix: str, warps: Optional[int], ni: Option
         f'#define CPG_FAM_NI {ni}', f'#define CPG_FAM_MULTI_STRIDE {pair_stride}', f'#define CPG_FAM_S_STRIDE {s_stride}', f'#define CPG_FAM_TAIL_WARPS {tail_warps}',
         f'#define CPG_FAM_MATPAR {matpar}', f'#define CPG_FAM_MAT_WARPS {mat_warps}', f'#define CPG_FAM_MAT_STRIDE {mat_stride}',
         f'#define CPG_FAM_MAT_A_STRIDE {mat_a}', f'#define CPG_FAM_MAT_P_STRIDE {mat_p}', f'#define CPG_FAM_MAT_G_STRIDE {mat_g_stride}',
+        f'#define CPG_FAM_DMMA {use_dmma}', f'#define CPG_FAM_DM_GROUPS {max(dm_groups, 1)}', f'#define CPG_FAM_DBLOB_BYTES_PAD {dblob_pad}',
+        f'#define CPG_FAM_DM_W8 {dm_w8}', f'#define CPG_FAM_DM_STAGE {dm_stage}', f'#define CPG_FAM_DM_BV {dm_bv}',
         '#endif', '']
     return '\n'.join(lines)
 
@@ -107,7 +122,7 @@ def _blob_c(setup: QPSetup) -> str:
            '#include "cpg_family.h"', '#include "cpg_b200.h"']
     for sym, data in (('cpg_blob', setup.blob), ('cpg_tail_blob', setup.tail_blob), ('cpg_cblob', setup.blob_compact),
                       ('cpg_gblob', setup.grad_blob), ('cpg_gS0', np.asarray(setup.grad_S0, dtype='<f8').tobytes()),
-                      ('cpg_mblob', setup.mat_blob or b'\0' * 16)):
+                      ('cpg_mblob', setup.mat_blob or b'\0' * 16), ('cpg_dblob', setup.dmma_blob or b'\0' * 32)):
         words = np.frombuffer(data + b'\0' * ((-len(data)) % 8), dtype='<u8')
         out.append(f'const unsigned long long CPG_B200_FN({sym}_words)[] __attribute__((aligned(128))) = {{')
         for i in range(0, len(words), 4):
@@ -117,7 +132,8 @@ def _blob_c(setup: QPSetup) -> str:
     return '\n'.join(out) + '\n'
 
 
-def write_code(setup: QPSetup, code_dir: str, prefix: str = '', warps: Optional[int] = None, ni: Optional[int] = None) -> None:
+def write_code(setup: QPSetup, code_dir: str, prefix: str = '', warps: Optional[int] = None, ni: Optional[int] = None,
+               dmma: Optional[bool] = None, dmma_groups: Optional[int] = None) -> None:
     prefix = c_ident(prefix)
     shutil.rmtree(code_dir, ignore_errors=True)
     for sub in ('c/src', 'c/include', 'c/build', 'c/solver_code'):
@@ -127,7 +143,7 @@ def write_code(setup: QPSetup, code_dir: str, prefix: str = '', warps: Optional[
     for f in ('admm_kernel.cuh', 'admm_multi_kernel.cuh', 'grad_kernel.cuh', 'matpar_kernel.cuh', 'cpg_b200_module.cu'):
         shutil.copyfile(os.path.join(_CSRC, f), os.path.join(sol, f))
     with open(os.path.join(inc, 'cpg_family.h'), 'w') as f:
-        f.write(_family_header(setup, prefix, warps, ni))
+        f.write(_family_header(setup, prefix, warps, ni, dmma, dmma_groups))
     with open(os.path.join(inc, 'cpg_blob_layout.h'), 'w') as f:
         f.write('/* Auto-generated by cvxpygen_b200 from offline/blob.py:HEADER_FIELDS. */\n#pragma once\n' + header_struct_c() + tail_header_struct_c() + grad_header_struct_c() + mat_header_struct_c())
     with open(os.path.join(inc, 'cpg_kkt_solve_gen.cuh'), 'w') as f:

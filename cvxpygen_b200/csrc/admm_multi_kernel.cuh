@@ -46,8 +46,136 @@ template <> struct MultiOps<4> {
 };
 
 }  // namespace cpgb200
+#if !CPG_FAM_DMMA
 #include "cpg_kkt_solve_gen.cuh"     // straight-line schedule of this family, template <int NI>
+#endif
 namespace cpgb200 {
+
+// ================================================================ FP64 tensor-core KKT solve (CPG_FAM_DMMA families)
+// A GROUP of four warps owns eight instances; their work vectors are interleaved, w8[position][instance], so that the
+// operand fragment of mma.sync.m8n8k4.f64 (4 positions x 8 instances) is four 64-byte rows and the 8x8 result fragment is
+// eight.  Schedule and table formats: offline/dmma.py.  The 16-byte pair of instances (2c, 2c+1) of position p sits at
+// column 2c ^ 2*((p >> 2) & 3): the ADMM phases, where a warp touches ONE pair of 32 scattered positions, then spread over
+// all banks instead of four, and the MMA fragments stay conflict-free (the XOR permutes pairs inside one 64-byte row).
+struct DmmaCtx {
+  double* w8;                 // this group's interleaved work vectors
+  double* stage;              // this group's staging buffer: 8x8 partial results, fragment order
+  const uint4* items;         // [stream index][warp of group] -> {mask, value offset, pos0|pos1<<16, pos2|pos3<<16}
+  const double* vals;         // compressed coefficients
+  const int4* tile_hdr;       // {item base, rounds | job rounds << 8, round_len base, job base}
+  const uint16_t* round_len;
+  const uint32_t* jobs;       // [job round][warp of group][8 words]
+  int* gflag;                 // this group's two flag words (bit 0: a warp checks termination this iteration, bit 1: alive)
+  int n_tiles, wg, bar_id;
+};
+
+__device__ __forceinline__ int w8_off(int p, int c) { return p * 8 + (c ^ (((p >> 2) & 3) << 1)); }
+
+#ifdef CPG_SIMT_HOST_EMU
+__device__ inline void group_bar(int id) { simt::named_barrier(id, 128); }
+// D(8x8) += A(8x4) B(4x8): lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4) + {0,1}]  (PTX ISA, mma.m8n8k4 .f64 fragments)
+__device__ inline void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  const int lane = threadIdx.x & 31, row = lane >> 2, kk = lane & 3;
+  for (int j = 0; j < 4; ++j) {
+    const double aj = __shfl_sync(FULL, a, row * 4 + j);
+    const double b0 = __shfl_sync(FULL, b, (2 * kk) * 4 + j), b1 = __shfl_sync(FULL, b, (2 * kk + 1) * 4 + j);
+    d0 = fma(aj, b0, d0); d1 = fma(aj, b1, d1);
+  }
+}
+#else
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+#endif
+
+// Shared-memory accesses of the solve by 32-bit shared-window address: the function is not inlined (its item loop wants its own
+// register allocation -- inlined, the 72 state registers of the ADMM phases squeeze it into rematerialising lane constants), and
+// through generic pointers every access would be a 64-bit LD.E with carry chains.
+#ifdef CPG_SIMT_HOST_EMU
+typedef uintptr_t saddr_t;
+__device__ inline saddr_t s_addr(const void* p) { return reinterpret_cast<uintptr_t>(p); }
+__device__ inline uint4 lds_u4(saddr_t a) { return *reinterpret_cast<const uint4*>(a); }
+__device__ inline int4 lds_i4(saddr_t a) { return *reinterpret_cast<const int4*>(a); }
+__device__ inline unsigned lds_u32(saddr_t a) { return *reinterpret_cast<const unsigned*>(a); }
+__device__ inline unsigned lds_u16(saddr_t a) { return *reinterpret_cast<const uint16_t*>(a); }
+__device__ inline double lds_f64(saddr_t a) { return *reinterpret_cast<const double*>(a); }
+__device__ inline double2 lds_f64x2(saddr_t a) { return *reinterpret_cast<const double2*>(a); }
+__device__ inline void sts_f64x2(saddr_t a, double x, double y) { *reinterpret_cast<double2*>(a) = make_double2(x, y); }
+#else
+typedef uint32_t saddr_t;
+__device__ __forceinline__ saddr_t s_addr(const void* p) { return (saddr_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint4 lds_u4(saddr_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ int4 lds_i4(saddr_t a) { int4 v; asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ unsigned lds_u32(saddr_t a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ unsigned lds_u16(saddr_t a) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double lds_f64(saddr_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double2 lds_f64x2(saddr_t a) { double2 v; asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f64x2(saddr_t a, double x, double y) { asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(x), "d"(y) : "memory"); }
+#endif
+
+#ifndef DMMA_SOLVE_INLINE
+#define DMMA_SOLVE_INLINE __noinline__
+#endif
+// one KKT solve for the group's eight right-hand sides, in place in w8; every warp of the group calls it; ends on a group barrier.
+// The loop is instruction-issue bound (profiles/r2_dmma_v1_ncu_summary.md), so an item costs as few instructions as the table
+// format allows: one broadcast LDS.128 (descriptor), PRMT + 2 LOP3 + IADD + LDS.64 (operand: the descriptor carries the swizzled
+// byte offsets of its four rows, the lane XORs its instance column in), LOP3 + POPC + shift/add + LDS.64 + 2 FSEL (compressed
+// coefficient: rank of the lane's bit in the occupancy mask; loaded unconditionally, then selected), DMMA.
+__device__ DMMA_SOLVE_INLINE void dmma_solve(const DmmaCtx& dc, const int lane) {
+  const int kk = lane & 3, nn = lane >> 2;
+  const unsigned lt = (1u << lane) - 1u, lbit = 1u << lane;
+  const unsigned sel = 0x1010u + 0x2222u * kk;            // byte selector: 16-bit field kk of the pair of words (z, w)
+  const unsigned ncol = (unsigned)nn << 3;
+  const saddr_t vals = s_addr(dc.vals), w8b = s_addr(dc.w8);
+  const saddr_t stage = s_addr(dc.stage) + lane * 16;
+  const saddr_t hdr = s_addr(dc.tile_hdr), rl = s_addr(dc.round_len), jobs = s_addr(dc.jobs), items = s_addr(dc.items);
+  const int wg = dc.wg, bar_id = dc.bar_id, n_tiles = dc.n_tiles;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int4 th = lds_i4(hdr + t * 16);
+    const int n_rounds = th.y & 0xff, n_jr = th.y >> 8;
+    saddr_t it = items + (th.x * 4 + wg) * 16;
+    for (int r = 0; r < n_rounds; ++r) {
+      const int L = (int)lds_u16(rl + (th.z + r) * 2);
+      double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;        // two accumulator chains
+#pragma unroll 2
+      for (int i = 0; i < L; i += 2) {
+        const uint4 d0 = lds_u4(it), d1 = lds_u4(it + 64);
+        it += 128;
+        const double b0 = lds_f64(w8b + ((__byte_perm(d0.z, d0.w, sel) & 0xffffu) ^ ncol));
+        const double b1 = lds_f64(w8b + ((__byte_perm(d1.z, d1.w, sel) & 0xffffu) ^ ncol));
+        // the load is unconditional (a lane without a coefficient reads a neighbour's -- always inside the table) and the
+        // result is selected: a predicated load costs a divergent branch here
+        double a0 = lds_f64(vals + d0.y + 8 * __popc(d0.x & lt));
+        double a1 = lds_f64(vals + d1.y + 8 * __popc(d1.x & lt));
+        a0 = (d0.x & lbit) ? a0 : 0.0;
+        a1 = (d1.x & lbit) ? a1 : 0.0;
+        dmma_8x8x4(c00, c01, a0, b0);
+        dmma_8x8x4(c10, c11, a1, b1);
+      }
+      sts_f64x2(stage + (wg * n_rounds + r) * 512, c00 + c10, c01 + c11);
+    }
+    group_bar(bar_id);                    // every operand of the tile has been read, every partial result is staged
+    saddr_t jb = jobs + (th.w * 4 + wg) * 32;
+    for (int j = 0; j < n_jr; ++j, jb += 128) {
+      const unsigned row = __byte_perm(lds_u32(jb + (nn >> 1) * 4), 0u, (nn & 1) ? 0x4432u : 0x4410u);   // swizzled byte offset of result row lane/4
+      const unsigned sl = lds_u32(jb + 16);
+      const int parts = (int)lds_u32(jb + 20);
+      double2 acc = lds_f64x2(stage + (sl & 0xffu) * 512);
+      if (parts > 1) {
+        const double2 v = lds_f64x2(stage + ((sl >> 8) & 0xffu) * 512);
+        acc.x += v.x; acc.y += v.y;
+        if (parts > 2) {
+          const double2 v2 = lds_f64x2(stage + ((sl >> 16) & 0xffu) * 512);
+          const double2 u2 = lds_f64x2(stage + (sl >> 24) * 512);
+          acc.x += v2.x; acc.y += v2.y; acc.x += u2.x; acc.y += u2.y;
+        }
+      }
+      if (row != 0xffffu) sts_f64x2(w8b + (row ^ ((unsigned)kk << 4)), acc.x, acc.y);
+    }
+    group_bar(bar_id);                    // the rows of this tile are in place before the next tile reads them
+  }
+}
 
 // row-blocked ELL sparse mat-vec on an interleaved multi-vector; returns the result for column 0 only
 template <int NI>
@@ -61,11 +189,15 @@ __device__ __forceinline__ double ell_dot_col0(const int* tab, const double* F64
   return a;
 }
 
-template <class Fam, int NI>
+// DMMA = false: every warp solves for its NI instances on its own (generated straight-line schedule, wN = its work vectors).
+// DMMA = true : NI = 2; the four warps of a group solve their eight right-hand sides together (dmma_solve); wN is then the
+//               warp's PRIVATE scratch for the once-per-check routines (a quarter of the group's w8, free between solves).
+template <class Fam, int NI, bool DMMA = false>
 __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __restrict__ I32,
                             const double* __restrict__ F64, const uint16_t* __restrict__ U16,
                             double* __restrict__ wN, double* __restrict__ bv, const int lane,
-                            const BatchIO& io, const Settings& st) {
+                            const BatchIO& io, const Settings& st, const DmmaCtx* dc = nullptr) {
+  static_assert(!DMMA || NI == 2, "the tensor-core path pairs two instances per warp, eight per group");
   constexpr int N = Fam::N, M = Fam::M, NXL = (N + 31) / 32, NZL = (M + 31) / 32, NZLs = NZL > 0 ? NZL : 1;
   using MO = MultiOps<NI>;
   const double* Dv = F64 + H->f_D;  const double* Dinv = F64 + H->f_Dinv;
@@ -441,22 +573,36 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
   };
 
   // ================================================================ main loop
+  // where an element of the KKT right-hand side / solution lives: the warp's own interleaved vectors, or -- tensor-core
+  // path -- this warp's pair of columns of the group's w8
+  auto wpos = [&](int p) __attribute__((always_inline)) -> double* {
+    if constexpr (DMMA) return dc->w8 + w8_off(p, 2 * dc->wg);
+    else return wN + NI * p;
+  };
+  int par = 0;
+  if constexpr (DMMA) {            // first fill; the group meets before anybody's scratch use can collide with a right-hand side
+#pragma unroll 1
+    for (int r = 0; r < NI; ++r) { refill0(); rotate_state(); }
+    group_bar(dc->bar_id);
+  }
   for (;;) {
-    // All warps of the CTA run the same ~50 KB of straight-line code per iteration; without this barrier they drift
-    // apart and every warp misses the instruction cache on its own (ncu: stall_no_instruction 4.4 cycles/issue).
-    // Iteration counts are multiples of check_termination for every instance, so the warps' check iterations coincide.
     bool any_active = false, any_free = false;
 #pragma unroll
     for (int s = 0; s < NI; ++s) { any_active |= active[s]; any_free |= !active[s]; }
-    if (!__syncthreads_or((int)(!exhausted || any_active))) break;
-    if (any_free && !exhausted) {                        // refill empty slots, one rotation at a time
+    if constexpr (!DMMA) {
+      // All warps of the CTA run the same ~50 KB of straight-line code per iteration; without this barrier they drift
+      // apart and every warp misses the instruction cache on its own (ncu: stall_no_instruction 4.4 cycles/issue).
+      // Iteration counts are multiples of check_termination for every instance, so the warps' check iterations coincide.
+      if (!__syncthreads_or((int)(!exhausted || any_active))) break;
+      if (any_free && !exhausted) {                        // refill empty slots, one rotation at a time
 #pragma unroll 1
-      for (int r = 0; r < NI; ++r) { refill0(); rotate_state(); }
-      any_active = false;
+        for (int r = 0; r < NI; ++r) { refill0(); rotate_state(); }
+        any_active = false;
 #pragma unroll
-      for (int s = 0; s < NI; ++s) any_active |= active[s];
+        for (int s = 0; s < NI; ++s) any_active |= active[s];
+      }
+      if (!any_active) continue;    // nothing left for this warp: keep meeting the others at the barrier
     }
-    if (!any_active) continue;    // nothing left for this warp: keep meeting the others at the barrier
 
     // which slots evaluate their residuals after this iteration
     bool chk[NI], adp[NI];
@@ -469,66 +615,92 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
       chk[s] = active[s] && (can_check || itn == st.max_iter);
       any_chk |= chk[s] || adp[s];
     }
+    if constexpr (DMMA) {           // tell the group: bit 0 = somebody runs the once-per-check routines, bit 1 = somebody is alive
+      const int f = (any_chk ? 1 : 0) | (any_active ? 2 : 0);
+      if (lane == 0 && f) atomicOr(dc->gflag + par, f);
+    }
 
     // ---- one ADMM iteration for all slots (osqp.c:354-372): rhs, KKT solve
-#pragma unroll
-    for (int k = 0; k < NXL; ++k) {
-      const int i = lane + 32 * k;
-      if (i < N) {
-        double qv[NI], r[NI];
-        tabN(AQ, k, qv);
-#pragma unroll
-        for (int s = 0; s < NI; ++s) r[s] = sigma * x[s][k] - qv[s];
-        MO::st(wN + NI * PX[32 * k], r);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < NZL; ++k) {
-      const int j = lane + 32 * k;
-      if (j < M) {
-        const double ri = rinv_of(k);
-        double r[NI];
-#pragma unroll
-        for (int s = 0; s < NI; ++s) r[s] = z[s][k] - ri * y[s][k];
-        MO::st(wN + NI * PZ[32 * k], r);
-      }
-    }
-    __syncwarp();
-    cpg_kkt_solve_gen<NI>(F64, I32, U16, wN, lane);
-
-    if (!any_chk) {
-      // ---- update_x, update_z (+project), update_y (auxil.c:185-225)
+    if (!DMMA || any_active) {
 #pragma unroll
       for (int k = 0; k < NXL; ++k) {
         const int i = lane + 32 * k;
         if (i < N) {
-          double xt[NI];
-          MO::ld(wN + NI * PX[32 * k], xt);
+          double qv[NI], r[NI];
+          tabN(AQ, k, qv);
 #pragma unroll
-          for (int s = 0; s < NI; ++s) x[s][k] = alpha * xt[s] + (1.0 - alpha) * x[s][k];
+          for (int s = 0; s < NI; ++s) r[s] = sigma * x[s][k] - qv[s];
+          MO::st(wpos(PX[32 * k]), r);
         }
       }
 #pragma unroll
       for (int k = 0; k < NZL; ++k) {
         const int j = lane + 32 * k;
         if (j < M) {
-          const double ri = rinv_of(k), r = rho_of(k);
-          double nu[NI], lv[NI], uv[NI];
-          MO::ld(wN + NI * PZ[32 * k], nu);
-          tabN(AL, k, lv); tabN(AU, k, uv);
+          const double ri = rinv_of(k);
+          double r[NI];
 #pragma unroll
-          for (int s = 0; s < NI; ++s) {
-            const double zt = (z[s][k] - ri * y[s][k]) + ri * nu[s];
-            const double v = alpha * zt + (1.0 - alpha) * z[s][k];
-            const double zn = fmin(fmax(v + ri * y[s][k], lv[s]), uv[s]);
-            y[s][k] += r * (v - zn);
-            z[s][k] = zn;
-          }
+          for (int s = 0; s < NI; ++s) r[s] = z[s][k] - ri * y[s][k];
+          MO::st(wpos(PZ[32 * k]), r);
         }
       }
+    }
+    int gflags = 0;
+    if constexpr (DMMA) {
+      group_bar(dc->bar_id);                             // right-hand sides and flags of all four warps are in place
+      gflags = *reinterpret_cast<volatile int*>(dc->gflag + par);
+      if (!(gflags & 2)) break;                          // the whole group is out of work
+      dmma_solve(*dc, lane);
+      if (dc->wg == 0 && lane == 0) dc->gflag[par] = 0;  // everybody read it before the solve's first barrier
+      par ^= 1;
+    } else {
       __syncwarp();
+#if !CPG_FAM_DMMA
+      cpg_kkt_solve_gen<NI>(F64, I32, U16, wN, lane);
+#endif
+    }
+
+    if (!any_chk) {
+      // ---- update_x, update_z (+project), update_y (auxil.c:185-225)
+      if (!DMMA || any_active) {
 #pragma unroll
-      for (int s = 0; s < NI; ++s) it[s] += active[s] ? 1 : 0;
+        for (int k = 0; k < NXL; ++k) {
+          const int i = lane + 32 * k;
+          if (i < N) {
+            double xt[NI];
+            MO::ld(wpos(PX[32 * k]), xt);
+#pragma unroll
+            for (int s = 0; s < NI; ++s) x[s][k] = alpha * xt[s] + (1.0 - alpha) * x[s][k];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < NZL; ++k) {
+          const int j = lane + 32 * k;
+          if (j < M) {
+            const double ri = rinv_of(k), r = rho_of(k);
+            double nu[NI], lv[NI], uv[NI];
+            MO::ld(wpos(PZ[32 * k]), nu);
+            tabN(AL, k, lv); tabN(AU, k, uv);
+#pragma unroll
+            for (int s = 0; s < NI; ++s) {
+              const double zt = (z[s][k] - ri * y[s][k]) + ri * nu[s];
+              const double v = alpha * zt + (1.0 - alpha) * z[s][k];
+              const double zn = fmin(fmax(v + ri * y[s][k], lv[s]), uv[s]);
+              y[s][k] += r * (v - zn);
+              z[s][k] = zn;
+            }
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < NI; ++s) it[s] += active[s] ? 1 : 0;
+      }
+      if constexpr (DMMA) {
+        if (gflags & 1) {            // another warp of the group runs its checks in its scratch: frame them with it
+          group_bar(dc->bar_id);
+          group_bar(dc->bar_id);
+        }
+      }
       continue;
     }
 
@@ -541,7 +713,7 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
       for (int s = 0; s < NI; ++s) dx[s][k] = 0.0;
       if (i < N) {
         double xt[NI];
-        MO::ld(wN + NI * PX[32 * k], xt);
+        MO::ld(wpos(PX[32 * k]), xt);
 #pragma unroll
         for (int s = 0; s < NI; ++s) {
           const double xn = alpha * xt[s] + (1.0 - alpha) * x[s][k];
@@ -558,7 +730,7 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
       if (k < NZL && j < M) {
         const double ri = rinv_of(k), r = rho_of(k);
         double nu[NI], lv[NI], uv[NI];
-        MO::ld(wN + NI * PZ[32 * k], nu);
+        MO::ld(wpos(PZ[32 * k]), nu);
         tabN(AL, k, lv); tabN(AU, k, uv);
 #pragma unroll
         for (int s = 0; s < NI; ++s) {
@@ -575,6 +747,7 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
     __syncwarp();
 #pragma unroll
     for (int s = 0; s < NI; ++s) it[s] += active[s] ? 1 : 0;
+    if constexpr (DMMA) group_bar(dc->bar_id);     // every warp has read its solution: w8 is scratch until the next right-hand side
 
     // ---- residuals, termination, adaptive-rho decision: slot by slot at position 0
 #pragma unroll 1
@@ -615,6 +788,11 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
         for (int s = 0; s + 1 < NI; ++s) dy[s][k] = dy[s + 1][k];
         dy[NI - 1][k] = t; }
     }
+    if constexpr (DMMA) {            // refill what terminated (the other kernel does it at the top of its loop), then release w8
+#pragma unroll 1
+      for (int r = 0; r < NI; ++r) { if (!exhausted) refill0(); rotate_state(); }
+      group_bar(dc->bar_id);
+    }
   }
 }
 
@@ -642,5 +820,57 @@ admm_multi_kernel(const uint8_t* __restrict__ blob_g, const BatchIO io, const Se
   double* bv = wN + Fam::NI * Fam::W_STRIDE;
   solve_multi<Fam, Fam::NI>(H, I32, F64, U16, wN, bv, lane, io, st);
 }
+
+#if CPG_FAM_DMMA
+// Tensor-core variant: DM_GROUPS groups of four warps per CTA, one persistent CTA per SM.  Shared memory: the compact constants
+// blob (no tile schedule) | the DMMA tables (offline/dmma.py, header below) | per group w8 + staging | per warp batched-row
+// table | per group two flag words.  Both blobs are staged by TMA bulk copies.
+struct CpgDmmaHeader { int total_bytes, n_tiles, off_hdr, off_rl, off_items, off_vals, off_jobs, max_rounds; };
+
+template <class Fam>
+__global__ void __launch_bounds__(Fam::DM_GROUPS * 128, 1)
+admm_dmma_kernel(const uint8_t* __restrict__ blob_g, const uint8_t* __restrict__ dblob_g, const BatchIO io, const Settings st) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = warp >> 2;
+  const uint32_t total = reinterpret_cast<const CpgBlobHeader*>(blob_g)->total_bytes;
+  const uint32_t dtotal = reinterpret_cast<const CpgDmmaHeader*>(dblob_g)->total_bytes;
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, total + dtotal);
+    constexpr uint32_t CHUNK = 32768;
+    for (uint32_t off = 0; off < total; off += CHUNK)
+      tma_bulk_g2s(smem + off, blob_g + off, (total - off < CHUNK) ? (total - off) : CHUNK, &bar);
+    for (uint32_t off = 0; off < dtotal; off += CHUNK)
+      tma_bulk_g2s(smem + Fam::CBLOB_BYTES_PAD + off, dblob_g + off, (dtotal - off < CHUNK) ? (dtotal - off) : CHUNK, &bar);
+  }
+  int* gflags = reinterpret_cast<int*>(smem + Fam::CBLOB_BYTES_PAD + Fam::DBLOB_BYTES_PAD +
+                                       (size_t)Fam::DM_GROUPS * (Fam::DM_W8 + Fam::DM_STAGE) * 8 + (size_t)Fam::DM_GROUPS * 4 * Fam::DM_BV * 8);
+  if (tid < 2 * Fam::DM_GROUPS) gflags[tid] = 0;
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(smem);
+  const int* I32 = reinterpret_cast<const int*>(smem + H->off_i32);
+  const double* F64 = reinterpret_cast<const double*>(smem + H->off_f64);
+  const uint16_t* U16 = reinterpret_cast<const uint16_t*>(smem + H->off_u16);
+  const uint8_t* db = smem + Fam::CBLOB_BYTES_PAD;
+  const CpgDmmaHeader* DH = reinterpret_cast<const CpgDmmaHeader*>(db);
+  double* gbase = reinterpret_cast<double*>(smem + Fam::CBLOB_BYTES_PAD + Fam::DBLOB_BYTES_PAD) + (size_t)grp * (Fam::DM_W8 + Fam::DM_STAGE);
+  DmmaCtx dc;
+  dc.w8 = gbase; dc.stage = gbase + Fam::DM_W8;
+  dc.items = reinterpret_cast<const uint4*>(db + DH->off_items);
+  dc.vals = reinterpret_cast<const double*>(db + DH->off_vals);
+  dc.tile_hdr = reinterpret_cast<const int4*>(db + DH->off_hdr);
+  dc.round_len = reinterpret_cast<const uint16_t*>(db + DH->off_rl);
+  dc.jobs = reinterpret_cast<const uint32_t*>(db + DH->off_jobs);
+  dc.gflag = gflags + 2 * grp;
+  dc.n_tiles = DH->n_tiles; dc.wg = warp & 3; dc.bar_id = 1 + grp;
+  double* bv = reinterpret_cast<double*>(smem + Fam::CBLOB_BYTES_PAD + Fam::DBLOB_BYTES_PAD) +
+               (size_t)Fam::DM_GROUPS * (Fam::DM_W8 + Fam::DM_STAGE) + (size_t)warp * Fam::DM_BV;
+  double* scratch = dc.w8 + (size_t)dc.wg * (Fam::DM_W8 / 4);      // >= 2 * W_STRIDE doubles
+  solve_multi<Fam, 2, true>(H, I32, F64, U16, scratch, bv, lane, io, st, &dc);
+}
+#endif
 
 }  // namespace cpgb200

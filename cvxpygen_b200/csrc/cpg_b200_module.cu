@@ -28,6 +28,8 @@ extern "C" const unsigned long long CPG_B200_FN(cpg_gS0_words)[];       // regul
 extern "C" const unsigned int CPG_B200_FN(cpg_gS0_nbytes);
 extern "C" const unsigned long long CPG_B200_FN(cpg_mblob_words)[];     // matrix-parameter tables (global; 16 bytes of zeros when unused)
 extern "C" const unsigned int CPG_B200_FN(cpg_mblob_nbytes);
+extern "C" const unsigned long long CPG_B200_FN(cpg_dblob_words)[];     // tables of the FP64 tensor-core solve (32 bytes of zeros when unused)
+extern "C" const unsigned int CPG_B200_FN(cpg_dblob_nbytes);
 
 namespace {
 
@@ -45,6 +47,9 @@ struct Fam {
   static constexpr int GRAD_STRIDE = CPG_FAM_GRAD_STRIDE;
   static constexpr int NI = CPG_FAM_NI;                     // instances per warp in the main kernel (2 or 4)
   static constexpr int MULTI_STRIDE = CPG_FAM_MULTI_STRIDE; // doubles per warp: interleaved work vectors + batched-row slots
+  static constexpr int DM_GROUPS = CPG_FAM_DM_GROUPS;       // tensor-core main kernel: groups of four warps (eight instances) per CTA
+  static constexpr int DBLOB_BYTES_PAD = CPG_FAM_DBLOB_BYTES_PAD;
+  static constexpr int DM_W8 = CPG_FAM_DM_W8, DM_STAGE = CPG_FAM_DM_STAGE, DM_BV = CPG_FAM_DM_BV;   // doubles
 #if CPG_FAM_MATPAR
   static constexpr int MAT_WARPS = CPG_FAM_MAT_WARPS;       // matrix-parameter kernel: warps per CTA
   static constexpr int MAT_A_STRIDE = CPG_FAM_MAT_A_STRIDE, MAT_P_STRIDE = CPG_FAM_MAT_P_STRIDE;
@@ -56,6 +61,8 @@ struct Fam {
 constexpr int MAT_SMEM_BYTES = Fam::MAT_WARPS * Fam::MAT_STRIDE * 8;
 #endif
 constexpr int SMEM_BYTES = Fam::BLOB_BYTES_PAD + Fam::WARPS * Fam::MULTI_STRIDE * 8;
+constexpr int DMMA_SMEM_BYTES = Fam::CBLOB_BYTES_PAD + Fam::DBLOB_BYTES_PAD +
+                                Fam::DM_GROUPS * ((Fam::DM_W8 + Fam::DM_STAGE) * 8 + 4 * Fam::DM_BV * 8 + 8) + 16;
 constexpr int TAIL_SMEM_BYTES = Fam::CBLOB_BYTES_PAD + Fam::TAIL_WARPS * (Fam::W_STRIDE + Fam::S_STRIDE) * 8;
 constexpr int TAIL_WORDS = Fam::N + 2 * Fam::M + 2;
 constexpr int GRAD_SMEM_BYTES = Fam::GBLOB_BYTES_PAD + Fam::GRAD_WARPS * Fam::GRAD_STRIDE * 8;
@@ -69,6 +76,7 @@ struct Ctx {
   uint8_t* d_gblob = nullptr;
   double* d_gS0 = nullptr;
   uint8_t* d_mblob = nullptr;
+  uint8_t* d_dblob = nullptr;
   double* d_mat_scratch = nullptr;       // per-warp slices for the scaled entries of A (matrix-parameter kernel)
   int cap_G = 0;
   double *g_soly = nullptr, *g_dprim = nullptr, *g_dparams = nullptr, *g_dq = nullptr, *g_dl = nullptr, *g_du = nullptr;
@@ -192,7 +200,12 @@ int CPG_B200_FN(cpg_b200_dims)(CpgB200Dims* out) {
   if (!out) return CPG_B200_ERR_BAD_ARG;
   const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words));
   out->n_var = H->n; out->n_con = H->m; out->n_param = H->npb; out->n_prim = H->n_prim; out->n_dual = H->n_dual;
-  out->blob_bytes = H->total_bytes; out->warps_per_cta = Fam::WARPS; out->smem_bytes = SMEM_BYTES;
+  out->blob_bytes = H->total_bytes;
+#if CPG_FAM_DMMA
+  out->warps_per_cta = Fam::DM_GROUPS * 4; out->smem_bytes = DMMA_SMEM_BYTES;
+#else
+  out->warps_per_cta = Fam::WARPS; out->smem_bytes = SMEM_BYTES;
+#endif
   return CPG_B200_OK;
 }
 
@@ -222,6 +235,20 @@ int CPG_B200_FN(cpg_b200_load_constants_all)(const void* blob, int nbytes, const
   CK(cudaMemcpy(g.d_gblob, gblob, gnbytes, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(g.d_gS0, gS0, snbytes, cudaMemcpyHostToDevice));
   return CPG_B200_OK;
+}
+
+/* tables of the tensor-core solve after a shared-parameter update (same sizes: the sparsity structure is unchanged) */
+int CPG_B200_FN(cpg_b200_load_dmma_constants)(const void* dblob, int nbytes) {
+  USE_DEVICE();
+#if CPG_FAM_DMMA
+  if (!dblob || nbytes != (int)CPG_B200_FN(cpg_dblob_nbytes)) return CPG_B200_ERR_BAD_ARG;
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(g.d_dblob, dblob, nbytes, cudaMemcpyHostToDevice));
+  return CPG_B200_OK;
+#else
+  (void)dblob; (void)nbytes;
+  return CPG_B200_OK;           // this library runs the straight-line schedule of the main blob
+#endif
 }
 
 int CPG_B200_FN(cpg_b200_load_mat_constants)(const void* mblob, int nbytes) {
@@ -277,7 +304,13 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
 #endif
   if (!g.d_counter) CK(cudaMalloc(&g.d_counter, sizeof(unsigned int)));
   if (!g.d_tail_count) CK(cudaMalloc(&g.d_tail_count, sizeof(int)));
+#if CPG_FAM_DMMA
+  if (!g.d_dblob) CK(cudaMalloc(&g.d_dblob, Fam::DBLOB_BYTES_PAD));
+  CK(cudaMemcpy(g.d_dblob, CPG_B200_FN(cpg_dblob_words), CPG_B200_FN(cpg_dblob_nbytes), cudaMemcpyHostToDevice));
+  CK(cudaFuncSetAttribute(cpgb200::admm_dmma_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, DMMA_SMEM_BYTES));
+#else
   CK(cudaFuncSetAttribute(cpgb200::admm_multi_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+#endif
   for (int k = 0; k < 4; ++k) if (!g.ev[k]) CK(cudaEventCreate(&g.ev[k]));
   for (int k = 0; k < 2; ++k) if (!g.gev[k]) CK(cudaEventCreate(&g.gev[k]));
   g.ready = true;
@@ -285,7 +318,7 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
 }
 
 int CPG_B200_FN(cpg_b200_free)(void) {
-  void* ptrs[] = {g.d_blob, g.d_cblob, g.d_gblob, g.d_gS0, g.d_mblob, g.d_mat_scratch, g.g_soly, g.g_dprim, g.g_dparams, g.g_dq, g.g_dl, g.g_du, g.d_tail_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0,
+  void* ptrs[] = {g.d_blob, g.d_cblob, g.d_gblob, g.d_gS0, g.d_mblob, g.d_dblob, g.d_mat_scratch, g.g_soly, g.g_dprim, g.g_dparams, g.g_dq, g.g_dl, g.g_du, g.d_tail_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0,
                   g.d_prim, g.d_dual, g.d_solx, g.d_soly, g.d_obj, g.d_pri, g.d_dua, g.d_iter, g.d_status};
   if (g.device >= 0) cudaSetDevice(g.device);
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -343,10 +376,19 @@ int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const doubl
   // one persistent CTA per SM; a batch smaller than one wave of slots is still spread over all SMs (every warp pulls its
   // instances from the global counter), so that few warps share an SM's shared-memory bandwidth: lower latency
   int grid = g.n_sm;
+#if CPG_FAM_DMMA
+  // tensor-core main kernel: a group of four warps takes eight instances at a time (KKT factor shared by the batch:
+  // the solve is a dense contraction over instances, mma.sync.m8n8k4.f64)
+  const int need = (B + 7) / 8;
+  if (grid > need) grid = need;
+  CK(cudaEventRecord(g.ev[0], stream));
+  cpgb200::admm_dmma_kernel<Fam><<<grid, Fam::DM_GROUPS * 128, DMMA_SMEM_BYTES, stream>>>(g.d_cblob, g.d_dblob, io, st);
+#else
   const int need = (B + Fam::NI - 1) / Fam::NI;
   if (grid > need) grid = need;
   CK(cudaEventRecord(g.ev[0], stream));
   cpgb200::admm_multi_kernel<Fam><<<grid, Fam::WARPS * 32, SMEM_BYTES, stream>>>(g.d_blob, io, st);
+#endif
   g.launches += 1;
   CK(cudaGetLastError());
   CK(cudaEventRecord(g.ev[1], stream));

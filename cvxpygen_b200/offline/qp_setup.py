@@ -56,11 +56,13 @@ class QPSetup:
     stats: Dict[str, float] = field(default_factory=dict)
     max_group_rows: int = 32
     allow_trailing: bool = True
+    dmma_blob: bytes = b''                 # tables of the FP64 tensor-core solve (offline/dmma.py); empty = not generated
+    dmma_rounds: int = 0
 
 
 def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
                     theta: Optional[np.ndarray] = None, rho: float = 0.1, sigma: float = 1e-6,
-                    scaling: int = 10, max_group_rows: int = 32, allow_trailing: bool = True) -> QPSetup:
+                    scaling: int = 10, max_group_rows: int = 32, allow_trailing: bool = True, dmma: bool = True) -> QPSetup:
     if fam.solver_type != 'quadratic':
         raise ValueError('ADMM-CUDA handles the QP canonical form only')
     if batch_params is None:
@@ -125,6 +127,12 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
                              c=sc['c'], sigma=sigma, rho=rho, ctype=ctype, q_base=q_base, l_base=l_base, u_base=u_base,
                              Mq_b=Mq_b, Ml_b=Ml_b, Mu_b=Mu_b, npb=npb, prim_idx=prim_idx, dual_idx=dual_idx,
                              d_const=d_const, is_max=fam.is_maximization, with_tiles=False)
+    dmma_blob, dmma_rounds = b'', 0
+    if dmma and not mat_params:      # shared KKT factor: the solve of eight instances is a dense contraction -> FP64 tensor cores
+        from .dmma import build_dmma_schedule, pack_dmma_blob
+        DS = build_dmma_schedule(F, max_group_rows=max_group_rows)
+        dmma_blob = pack_dmma_blob(DS)
+        dmma_rounds = max(len(t.round_len) for t in DS.tiles)
     RT = build_refactor_tables(F, K, n)
     tail_blob = pack_tail_blob(RT)
     # backward pass (gradient=True): regularised KKT of the UNSCALED problem on the same symbolic pattern
@@ -141,13 +149,13 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
     _hdr = dict(zip([n_ for _, n_ in _HF], _struct.unpack('<' + ''.join('i' if t_ == 'int' else 'd' for t_, _ in _HF),
                                                             blob[:_struct.calcsize('<' + ''.join('i' if t_ == 'int' else 'd' for t_, _ in _HF))])))
     st = dict(nb_slots=int(_hdr['nb_slots']), nnz_L=F.nnz, tail_blob_bytes=len(tail_blob), refactor_ops=len(RT.ops), n_levels=int(F.level.max()) + 1, n_tiles=len(S.tiles), schedule_cost=S.model_cost,
-              schedule_entries=S.n_entries, blob_bytes=len(blob))
+              schedule_entries=S.n_entries, blob_bytes=len(blob), dmma_blob_bytes=len(dmma_blob))
     return QPSetup(family=fam, batch_params=list(batch_params), n=n, m=m, npb=npb, rho=rho, sigma=sigma,
                    scaling=scaling, D=sc['D'], E=sc['E'], c=sc['c'], ctype=ctype, P_scaled=sc['P'],
                    A_scaled=sc['A'], factor=F, schedule=S, prim_idx=prim_idx, dual_idx=dual_idx, blob=blob, tail_blob=tail_blob, blob_compact=blob_compact, grad_blob=grad_blob, grad_S0=grad_S0, mat_blob=mat_blob, mat_params=mat_params,
                    nnzP=int(sp.csc_matrix(P).indptr[-1]), nnzA=int(sp.csc_matrix(A).indptr[-1]), refactor=RT, solve_source=solve_source,
                    theta_shared=theta0, batch_cols=bcols, stats=st,
-                   max_group_rows=max_group_rows, allow_trailing=allow_trailing)
+                   max_group_rows=max_group_rows, allow_trailing=allow_trailing, dmma_blob=dmma_blob, dmma_rounds=dmma_rounds)
 
 
 def unscale_roundtrip(sc, scaling):

@@ -126,6 +126,8 @@ class Module:
         b = lambda x: (C.c_char_p(x), C.c_int(len(x)))
         self._check(self._fn('cpg_b200_load_constants_all')(*b(st.blob), *b(st.blob_compact), *b(st.tail_blob),
                                                            *b(st.grad_blob), *b(gS0)))
+        if getattr(st, 'dmma_blob', b''):      # tensor-core main kernel: its coefficient tables changed with the factor
+            self._check(self._fn('cpg_b200_load_dmma_constants')(*b(st.dmma_blob)))
         if st.mat_blob:       # matrix-parameter family: base values / maps of the P and A entries changed as well
             self._check(self._fn('cpg_b200_load_mat_constants')(*b(st.mat_blob)))
         return st

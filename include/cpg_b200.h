@@ -101,6 +101,11 @@ int  CPG_B200_FN(cpg_b200_load_constants_all)(const void* blob, int nbytes, cons
                                               const void* tail_blob, int tnbytes, const void* gblob, int gnbytes,
                                               const void* gS0, int snbytes);
 
+/* Libraries whose main kernel is the FP64 tensor-core variant (admm_dmma_kernel; chosen at generation time when the factor is
+ * shared by the batch and its tables fit in shared memory): replace the tables of that solve after a shared-parameter update.
+ * No-op (CPG_B200_OK) for the other libraries. */
+int  CPG_B200_FN(cpg_b200_load_dmma_constants)(const void* dblob, int nbytes);
+
 /* Families generated with per-instance MATRIX parameters (a batched parameter enters P or A): replace the
  * tables of the per-instance osqp_update_data_mat path (canonicalisation maps of the P / A entries, KKT slot maps, the
  * round-trip base values) after a SHARED parameter changed.  Error for libraries generated without such parameters.

@@ -24,6 +24,7 @@ extern "C" const unsigned long long CPG_B200_FN(cpg_cblob_words)[];
 extern "C" const unsigned long long CPG_B200_FN(cpg_gblob_words)[];
 extern "C" const unsigned long long CPG_B200_FN(cpg_gS0_words)[];
 extern "C" const unsigned long long CPG_B200_FN(cpg_mblob_words)[];
+extern "C" const unsigned long long CPG_B200_FN(cpg_dblob_words)[];
 
 namespace cpgb200 { alignas(128) uint8_t smem[256 * 1024]; }
 
@@ -37,6 +38,8 @@ struct Fam {
   static constexpr int TAIL_WARPS = CPG_FAM_TAIL_WARPS;
   static constexpr int GBLOB_BYTES_PAD = CPG_FAM_GBLOB_BYTES_PAD;
   static constexpr int GRAD_WARPS = CPG_FAM_GRAD_WARPS, GRAD_STRIDE = CPG_FAM_GRAD_STRIDE;
+  static constexpr int DM_GROUPS = CPG_FAM_DM_GROUPS, DBLOB_BYTES_PAD = CPG_FAM_DBLOB_BYTES_PAD;
+  static constexpr int DM_W8 = CPG_FAM_DM_W8, DM_STAGE = CPG_FAM_DM_STAGE, DM_BV = CPG_FAM_DM_BV;
 #if CPG_FAM_MATPAR
   static constexpr int MAT_WARPS = CPG_FAM_MAT_WARPS;
   static constexpr int MAT_A_STRIDE = CPG_FAM_MAT_A_STRIDE, MAT_P_STRIDE = CPG_FAM_MAT_P_STRIDE;
@@ -108,9 +111,16 @@ int emu_main_solve(int B, const double* params, double* prim, double* dual, doub
   io.status = status; io.pri_res = pri; io.dua_res = dua; io.B = B; io.work_counter = &counter;
   io.tail_count = &count; io.tail_ids = ids.data(); io.tail_state = state.data(); io.tail_capacity = B;
   const cpgb200::Settings st = default_settings(adaptive_rho_interval, eps);
+#if CPG_FAM_DMMA       // the family's main kernel is the tensor-core variant (groups of four warps, DMMA emulated lane by lane)
+  simt::launch(grid, Fam::DM_GROUPS * 128, [&] {
+    cpgb200::admm_dmma_kernel<Fam>(reinterpret_cast<const uint8_t*>(CPG_B200_FN(cpg_cblob_words)),
+                                   reinterpret_cast<const uint8_t*>(CPG_B200_FN(cpg_dblob_words)), io, st);
+  });
+#else
   simt::launch(grid, Fam::WARPS * 32, [&] {
     cpgb200::admm_multi_kernel<Fam>(reinterpret_cast<const uint8_t*>(CPG_B200_FN(cpg_blob_words)), io, st);
   });
+#endif
   const int handed_off = count;
   simt::launch(grid, Fam::TAIL_WARPS * 32, [&] {
     cpgb200::admm_tail_kernel<Fam>(reinterpret_cast<const uint8_t*>(CPG_B200_FN(cpg_cblob_words)),

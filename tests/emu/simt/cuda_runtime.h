@@ -64,6 +64,7 @@ struct Runtime {
   std::vector<Fiber> fibers;
   std::vector<WarpState> warps;
   BlockState block;
+  BlockState named[16];      // bar.sync id, count (named barriers of a subset of the block's warps)
   Fiber* cur = nullptr;
   std::function<void()> body;
   long long n_exchange = 0, n_syncwarp = 0, n_syncthreads = 0;   // per-lane counts of synchronisation points (profiling aid)
@@ -83,6 +84,13 @@ inline void block_barrier() {
   BlockState& b = rt().block;
   const int gen = b.gen;
   if (++b.arrived == b.live) { b.arrived = 0; b.or_result = b.or_acc; b.or_acc = 0; ++b.gen; }
+  else while (b.gen == gen) yield();
+}
+// bar.sync id, count: the first `count` arrivals release each other (no participant leaves the kernel before the others arrive)
+inline void named_barrier(int id, int count) {
+  BlockState& b = rt().named[id & 15];
+  const int gen = b.gen;
+  if (++b.arrived == count) { b.arrived = 0; ++b.gen; }
   else while (b.gen == gen) yield();
 }
 template <class T> inline uint64_t to_bits(T v) { uint64_t u = 0; memcpy(&u, &v, sizeof(T)); return u; }
@@ -115,6 +123,7 @@ inline void launch(int grid, int threads, std::function<void()> body) {
     r.fibers.assign(threads, Fiber());
     r.warps.assign(nw, WarpState());
     r.block = BlockState();
+    for (auto& nb : r.named) nb = BlockState();
     r.block.live = threads;
     for (int t = 0; t < threads; ++t) {
       Fiber& f = r.fibers[t];
@@ -193,6 +202,14 @@ inline void __syncthreads() { ++simt::rt().n_syncthreads; simt::block_barrier();
 inline int __syncthreads_or(int pred) { simt::rt().block.or_acc |= (pred != 0); simt::block_barrier(); const int r = simt::rt().block.or_result; simt::block_barrier(); return r; }
 
 template <class T> inline T atomicAdd(T* p, T v) { const T old = *p; *p = old + v; return old; }
+template <class T> inline T atomicOr(T* p, T v) { const T old = *p; *p = old | v; return old; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {      // PRMT, default mode: result byte i = byte (s >> 4i) & 7 of {x, y}
+  const unsigned long long pool = ((unsigned long long)y << 32) | x;
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) r |= (unsigned)((pool >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+  return r;
+}
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }

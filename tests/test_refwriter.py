@@ -150,11 +150,12 @@ def test_emitted_c_abi_via_ctypes_matrix_family_with_prefix():
     class Result(C.Structure):
         _fields_ = [('prim', C.POINTER(Prim)), ('dual', C.POINTER(Dual)), ('info', C.POINTER(Info))]
     p = 'nnls_'
-    lib[p + 'cpg_update_A'].argtypes = [C.c_int, C.c_double]
-    lib[p + 'cpg_update_b'].argtypes = [C.c_int, C.c_double]
-    lib[p + 'cpg_set_solver_warm_starting'].argtypes = [C.c_int]
-    lib[p + 'cpg_set_solver_default_settings']()
-    lib[p + 'cpg_set_solver_warm_starting'](0)
+    fn = lambda name: getattr(lib, p + name)          # getattr caches the function object (lib[name] does not): argtypes stick
+    fn('cpg_update_A').argtypes = [C.c_int, C.c_double]
+    fn('cpg_update_b').argtypes = [C.c_int, C.c_double]
+    fn('cpg_set_solver_warm_starting').argtypes = [C.c_int]
+    fn('cpg_set_solver_default_settings')()
+    fn('cpg_set_solver_warm_starting')(0)
     rng = np.random.default_rng(12)
     result = Result.in_dll(lib, p + 'CPG_Result')
     from helpers import canon_matrix_batches, matrix_oracle_solve
@@ -162,10 +163,10 @@ def test_emitted_c_abi_via_ctypes_matrix_family_with_prefix():
         Av = fam.param('A').default + 0.2 * rng.standard_normal(fam.param('A').size)
         bv = fam.param('b').default + 0.2 * rng.standard_normal(fam.param('b').size)
         for i, v in enumerate(Av):
-            lib[p + 'cpg_update_A'](i, float(v))
+            fn('cpg_update_A')(i, float(v))
         for i, v in enumerate(bv):
-            lib[p + 'cpg_update_b'](i, float(v))
-        lib[p + 'cpg_solve']()
+            fn('cpg_update_b')(i, float(v))
+        fn('cpg_solve')()
         Px, Ax, (q, l, u) = canon_matrix_batches(fam, {'A': Av[None, :], 'b': bv[None, :]}, 1)
         ora = matrix_oracle_solve(fam, None, Ax, q, l, u)
         info = result.info.contents

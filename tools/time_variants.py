@@ -7,11 +7,13 @@ import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 VDIR = os.path.join(ROOT, 'tools', '_variants')
-VARIANTS = {
+VARIANTS = {      # name -> (family, extra nvcc flags, batch[, solver_opts])
     'ltv_atomic': ('mpc_ltv_12_4_10', '', 20000),
     'ltv_gather': ('mpc_ltv_12_4_10', '-DCPG_TAIL_GATHER_FACTOR=1', 20000),
-    'mpc_atomic': ('mpc_12_4_10', '', 100000),
-    'mpc_gather': ('mpc_12_4_10', '-DCPG_TAIL_GATHER_FACTOR=1', 100000),
+    'mpc_atomic': ('mpc_12_4_10', '', 100000, {'dmma': False}),
+    'mpc_gather': ('mpc_12_4_10', '-DCPG_TAIL_GATHER_FACTOR=1', 100000, {'dmma': False}),
+    'mpc_dmma_g3': ('mpc_12_4_10', '', 100000, {'dmma_groups': 3}),
+    'mpc_dmma_g2': ('mpc_12_4_10', '', 100000, {'dmma_groups': 2}),
 }
 
 
@@ -20,10 +22,11 @@ def build(names):
     from cvxpygen_b200 import standard, cpg
 
     def one(v):
-        famname, flags, _ = VARIANTS[v]
+        famname, flags, _ = VARIANTS[v][:3]
+        opts = VARIANTS[v][3] if len(VARIANTS[v]) > 3 else None
         fam_fn, batch = standard.STANDARD[famname]
         d = os.path.join(VDIR, v)
-        cpg.generate_code(fam_fn(), code_dir=d, batch_params=batch, wrapper=False)
+        cpg.generate_code(fam_fn(), code_dir=d, batch_params=batch, wrapper=False, solver_opts=opts)
         from cvxpygen_b200 import codegen
         codegen.compile_code(d, extra_flags=flags.split())
         return d
@@ -38,7 +41,7 @@ def run(names, reps=3):
     from cvxpygen_b200 import runtime, standard
     from helpers import ltv_batch
     for v in names:
-        famname, flags, B = VARIANTS[v]
+        famname, flags, B = VARIANTS[v][:3]
         d = os.path.join(VDIR, v)
         if not os.path.exists(os.path.join(d, 'libcpg_b200.so')):
             continue
@@ -55,8 +58,18 @@ def run(names, reps=3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); mod.solve_batch_device(P, out=out); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
+        kt = mod.kernel_times()
         rec = dict(variant=v, flags=flags, B=B, fwd_ms=float(np.median(ts)), fwd_inst_per_s=B / (np.median(ts) * 1e-3),
+                   main_ms=kt['main'], tail_ms=kt['tail'], warps=int(mod.dims.warps_per_cta), smem=int(mod.dims.smem_bytes),
                    mean_iter=float(out.iter.float().mean()), frac_solved=float((out.status == 1).float().mean()))
+        if not mod.has_matrix_params and famname == 'mpc_12_4_10' and '--parity' in sys.argv:
+            import bench
+            wl = bench.WORKLOADS['mpc']
+            ph = P[:20000].cpu().numpy()
+            r = mod.solve_batch(ph, return_canonical=True)
+            ora = wl.reference(ph, os.cpu_count())
+            rec['parity'] = dict(iter_equal=float((r.cpg_info.iter == ora['iter']).mean()), status_equal=float((r.cpg_info.status == ora['status']).mean()),
+                                 max_rel_x=bench.relmax_rows(r.sol_x, ora['x']), max_rel_y=bench.relmax_rows(r.sol_y, ora['y']))
         dprim = torch.randn((B, mod.dims.n_prim), dtype=torch.float64, device='cuda')
         g = (lambda dp=None: mod.gradient_batch_device_mat(P, out.sol_x, out.sol_y, dprim, dparams=dp)) if mod.has_matrix_params \
             else (lambda dp=None: mod.gradient_batch_device(out.sol_y, dprim, dparams=dp))
