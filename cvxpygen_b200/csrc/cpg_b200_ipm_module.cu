@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <thread>
+#include <vector>
 
 #include "cpg_ipm_family.h"
 #include "cpg_b200_socp.h"
@@ -37,7 +39,12 @@ struct Ctx {
   cudaEvent_t ev[2] = {nullptr, nullptr};     // around the last ipm_kernel launch
   bool ev_solve = false;
   char err[256] = {0};
-} g;
+};
+// one context per DEVICE; a host thread works on the context it selected last (cpg_b200_init / cpg_b200_use_device)
+constexpr int MAX_DEVICES = 16;
+Ctx ctxs[MAX_DEVICES];
+thread_local Ctx* cur_ctx = &ctxs[0];
+#define g (*cur_ctx)
 
 #define CK(call)                                                                                  \
   do {                                                                                            \
@@ -87,12 +94,16 @@ int ensure_staging(int B) {
 
 extern "C" {
 
+int CPG_B200_FN(cpg_b200_use_device)(int device) {
+  if (device < 0 || device >= MAX_DEVICES) return CPG_B200_ERR_BAD_ARG;
+  if (!ctxs[device].ready) { snprintf(g.err, sizeof(g.err), "cpg_b200_init(%d) has not been called", device); return CPG_B200_ERR_NOT_INIT; }
+  cur_ctx = &ctxs[device];
+  return CPG_B200_OK;
+}
+
 int CPG_B200_FN(cpg_b200_init)(int device) {
-  if (g.ready && device != g.device) {
-    snprintf(g.err, sizeof(g.err), "this library is already initialised on device %d: one context per process "
-             "(use one process per GPU, or cpg_b200_free() first)", g.device);
-    return CPG_B200_ERR_BAD_ARG;
-  }
+  if (device < 0 || device >= MAX_DEVICES) { snprintf(g.err, sizeof(g.err), "device index %d outside [0, %d)", device, MAX_DEVICES); return CPG_B200_ERR_BAD_ARG; }
+  cur_ctx = &ctxs[device];              // this thread now works on the context of `device`
   if (g.ready) return CPG_B200_OK;
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -111,14 +122,19 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
   return CPG_B200_OK;
 }
 
-int CPG_B200_FN(cpg_b200_free)(void) {
-  if (!g.ready) return CPG_B200_OK;
-  void* ptrs[] = {g.d_sblob, g.d_gblob, g.d_best, g.d_counter, g.d_params, g.d_prim, g.d_dual, g.d_x, g.d_y, g.d_z, g.d_s,
-                  g.d_obj, g.d_pri, g.d_dua, g.d_iter, g.d_status};
-  cudaSetDevice(g.device);
-  for (void* p : ptrs) if (p) cudaFree(p);
-  for (cudaEvent_t e : g.ev) if (e) cudaEventDestroy(e);
-  g = Ctx();
+int CPG_B200_FN(cpg_b200_free)(void) {        // releases the context of EVERY device
+  Ctx* keep = cur_ctx;
+  for (int d = 0; d < MAX_DEVICES; ++d) {
+    cur_ctx = &ctxs[d];
+    if (!g.ready) continue;
+    void* ptrs[] = {g.d_sblob, g.d_gblob, g.d_best, g.d_counter, g.d_params, g.d_prim, g.d_dual, g.d_x, g.d_y, g.d_z, g.d_s,
+                    g.d_obj, g.d_pri, g.d_dua, g.d_iter, g.d_status};
+    cudaSetDevice(g.device);
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (cudaEvent_t e : g.ev) if (e) cudaEventDestroy(e);
+    g = Ctx();
+  }
+  cur_ctx = keep;
   return CPG_B200_OK;
 }
 
@@ -222,6 +238,38 @@ int CPG_B200_FN(cpg_socp_solve_batch_host)(int B, const double* params, double* 
   CK(cudaMemcpy(status, g.d_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(pri_res, g.d_pri, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(dua_res, g.d_dua, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost));
+  return CPG_B200_OK;
+}
+
+int CPG_B200_FN(cpg_socp_solve_batch_host_multi)(int n_dev, const int* devices, int B, const double* params, double* prim, double* dual,
+                                                 double* sol_x, double* sol_y, double* sol_z, double* sol_s, double* obj_val, int* iter,
+                                                 int* status, double* pri_res, double* dua_res, const CpgB200SocpSettings* settings) {
+  if (n_dev <= 0 || n_dev > MAX_DEVICES || B < 0) return CPG_B200_ERR_BAD_ARG;
+  std::vector<int> dev(n_dev), rc(n_dev, CPG_B200_OK);
+  for (int k = 0; k < n_dev; ++k) {
+    dev[k] = devices ? devices[k] : k;
+    if (dev[k] < 0 || dev[k] >= MAX_DEVICES) return CPG_B200_ERR_BAD_ARG;
+    for (int j = 0; j < k; ++j) if (dev[j] == dev[k]) return CPG_B200_ERR_BAD_ARG;     // one host thread per context
+  }
+  Ctx* caller = cur_ctx;
+  std::vector<std::thread> th;
+  for (int k = 0; k < n_dev; ++k) {
+    th.emplace_back([&, k] {
+      const long long lo = (long long)B * k / n_dev, hi = (long long)B * (k + 1) / n_dev;     // contiguous shard, nothing exchanged
+      int r = CPG_B200_FN(cpg_b200_init)(dev[k]);
+      if (r == CPG_B200_OK && hi > lo) {
+        auto at = [&](auto* p, size_t w) { return p ? p + (size_t)lo * w : p; };
+        r = CPG_B200_FN(cpg_socp_solve_batch_host)((int)(hi - lo), at(params, (size_t)cpgipm::NPB), at(prim, (size_t)cpgipm::NPRIM),
+                                                   at(dual, (size_t)cpgipm::NDUAL), at(sol_x, (size_t)cpgipm::N), at(sol_y, (size_t)cpgipm::P),
+                                                   at(sol_z, (size_t)cpgipm::M), at(sol_s, (size_t)cpgipm::M), at(obj_val, 1), at(iter, 1),
+                                                   at(status, 1), at(pri_res, 1), at(dua_res, 1), settings);
+      }
+      rc[k] = r;
+      if (r != CPG_B200_OK) snprintf(caller->err, sizeof(caller->err), "device %d: %.200s", dev[k], g.err);
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int k = 0; k < n_dev; ++k) if (rc[k] != CPG_B200_OK) return rc[k];
   return CPG_B200_OK;
 }
 

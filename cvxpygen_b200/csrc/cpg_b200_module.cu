@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <thread>
+#include <vector>
 
 #include "cpg_family.h"
 #include "cpg_b200.h"
@@ -95,7 +97,13 @@ struct Ctx {
   cudaEvent_t gev[2] = {nullptr, nullptr};                   // backward pass: before / after
   bool ev_solve = false, ev_grad = false;
   char err[256] = {0};
-} g;
+};
+// One context per DEVICE; every host thread works on the context it selected last (cpg_b200_init / cpg_b200_use_device), so
+// a multi-GPU caller runs one host thread per device on one loaded library (cpg_solve_batch_host_multi does exactly that).
+constexpr int MAX_DEVICES = 16;
+Ctx ctxs[MAX_DEVICES];
+thread_local Ctx* cur_ctx = &ctxs[0];
+#define g (*cur_ctx)
 
 #define CK(call)                                                                                  \
   do {                                                                                            \
@@ -106,8 +114,7 @@ struct Ctx {
     }                                                                                             \
   } while (0)
 
-// Every entry point runs on the device the context was initialised for (one context per library: the library is a
-// per-process singleton bound to ONE device; a second device needs its own process -- bench.py / torchrun do that).
+// Every entry point runs on the device of the calling thread's context.
 #define USE_DEVICE()                                                                              \
   do {                                                                                            \
     if (!g.ready) { snprintf(g.err, sizeof(g.err), "cpg_b200_init has not been called"); return CPG_B200_ERR_NOT_INIT; } \
@@ -265,13 +272,23 @@ int CPG_B200_FN(cpg_b200_load_mat_constants)(const void* mblob, int nbytes) {
 #endif
 }
 
+int CPG_B200_FN(cpg_b200_use_device)(int device) {
+  if (device < 0 || device >= MAX_DEVICES) return CPG_B200_ERR_BAD_ARG;
+  if (!ctxs[device].ready) {
+    snprintf(g.err, sizeof(g.err), "cpg_b200_init(%d) has not been called", device);
+    return CPG_B200_ERR_NOT_INIT;
+  }
+  cur_ctx = &ctxs[device];
+  return CPG_B200_OK;
+}
+
 int CPG_B200_FN(cpg_b200_init)(int device) {
-  g.err[0] = 0;
-  if (g.ready && device != g.device) {
-    snprintf(g.err, sizeof(g.err), "this library is already initialised on device %d: one context per process "
-             "(use one process per GPU, or cpg_b200_free() first)", g.device);
+  if (device < 0 || device >= MAX_DEVICES) {
+    snprintf(g.err, sizeof(g.err), "device index %d outside [0, %d)", device, MAX_DEVICES);
     return CPG_B200_ERR_BAD_ARG;
   }
+  cur_ctx = &ctxs[device];              // this thread now works on the context of `device`
+  g.err[0] = 0;
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
@@ -317,14 +334,20 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
   return CPG_B200_OK;
 }
 
-int CPG_B200_FN(cpg_b200_free)(void) {
-  void* ptrs[] = {g.d_blob, g.d_cblob, g.d_gblob, g.d_gS0, g.d_mblob, g.d_dblob, g.d_mat_scratch, g.g_soly, g.g_dprim, g.g_dparams, g.g_dq, g.g_dl, g.g_du, g.d_tail_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0,
-                  g.d_prim, g.d_dual, g.d_solx, g.d_soly, g.d_obj, g.d_pri, g.d_dua, g.d_iter, g.d_status};
-  if (g.device >= 0) cudaSetDevice(g.device);
-  for (void* p : ptrs) if (p) cudaFree(p);
-  for (cudaEvent_t e : g.ev) if (e) cudaEventDestroy(e);
-  for (cudaEvent_t e : g.gev) if (e) cudaEventDestroy(e);
-  g = Ctx();
+int CPG_B200_FN(cpg_b200_free)(void) {        // releases the context of EVERY device
+  Ctx* keep = cur_ctx;
+  for (int d = 0; d < MAX_DEVICES; ++d) {
+    cur_ctx = &ctxs[d];
+    if (g.device < 0) continue;
+    void* ptrs[] = {g.d_blob, g.d_cblob, g.d_gblob, g.d_gS0, g.d_mblob, g.d_dblob, g.d_mat_scratch, g.g_soly, g.g_dprim, g.g_dparams, g.g_dq, g.g_dl, g.g_du, g.d_tail_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0,
+                    g.d_prim, g.d_dual, g.d_solx, g.d_soly, g.d_obj, g.d_pri, g.d_dua, g.d_iter, g.d_status};
+    cudaSetDevice(g.device);
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (cudaEvent_t e : g.ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : g.gev) if (e) cudaEventDestroy(e);
+    g = Ctx();
+  }
+  cur_ctx = keep;
   return CPG_B200_OK;
 }
 
@@ -444,6 +467,41 @@ int CPG_B200_FN(cpg_solve_batch_host)(int B, const double* params, const double*
   CK(cudaMemcpyAsync(iter, g.d_iter, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(status, g.d_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return CPG_B200_OK;
+}
+
+int CPG_B200_FN(cpg_solve_batch_host_multi)(int n_dev, const int* devices, int B, const double* params, const double* x0,
+                                            const double* y0, double* prim, double* dual, double* sol_x, double* sol_y,
+                                            double* obj_val, int* iter, int* status, double* pri_res, double* dua_res,
+                                            const CpgB200Settings* settings) {
+  if (n_dev <= 0 || n_dev > MAX_DEVICES || B < 0 || !obj_val || !iter || !status || !pri_res || !dua_res) return CPG_B200_ERR_BAD_ARG;
+  const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words));
+  std::vector<int> dev(n_dev), rc(n_dev, CPG_B200_OK);
+  for (int k = 0; k < n_dev; ++k) {
+    dev[k] = devices ? devices[k] : k;
+    if (dev[k] < 0 || dev[k] >= MAX_DEVICES) return CPG_B200_ERR_BAD_ARG;
+    for (int j = 0; j < k; ++j) if (dev[j] == dev[k]) return CPG_B200_ERR_BAD_ARG;     // one host thread per context
+  }
+  Ctx* caller = cur_ctx;
+  std::vector<std::thread> th;
+  for (int k = 0; k < n_dev; ++k) {
+    th.emplace_back([&, k] {
+      // contiguous shard [lo, hi) of the batch: instances never interact, so nothing is exchanged between the devices
+      const long long lo = (long long)B * k / n_dev, hi = (long long)B * (k + 1) / n_dev;
+      int r = CPG_B200_FN(cpg_b200_init)(dev[k]);      // selects this thread's context; uploads the constants on first use
+      if (r == CPG_B200_OK && hi > lo) {
+        auto at = [&](auto* p, size_t w) { return p ? p + (size_t)lo * w : p; };
+        r = CPG_B200_FN(cpg_solve_batch_host)((int)(hi - lo), at(params, (size_t)H->npb), at(x0, (size_t)Fam::N), at(y0, (size_t)Fam::M),
+                                              at(prim, (size_t)H->n_prim), at(dual, (size_t)H->n_dual), at(sol_x, (size_t)Fam::N),
+                                              at(sol_y, (size_t)Fam::M), at(obj_val, 1), at(iter, 1), at(status, 1), at(pri_res, 1),
+                                              at(dua_res, 1), settings);
+      }
+      rc[k] = r;
+      if (r != CPG_B200_OK) snprintf(caller->err, sizeof(caller->err), "device %d: %.200s", dev[k], g.err);
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int k = 0; k < n_dev; ++k) if (rc[k] != CPG_B200_OK) return rc[k];
   return CPG_B200_OK;
 }
 

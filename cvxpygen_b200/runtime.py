@@ -284,6 +284,45 @@ class Module:
         info = SimpleNamespace(obj_val=obj, iter=it, status=st, pri_res=pri, dua_res=dua, time=t1 - t0)
         return SimpleNamespace(cpg_prim=pr, cpg_dual=du, cpg_info=info, prim=prim, dual=dual, sol_x=solx, sol_y=soly)
 
+    def solve_batch_multi(self, params, devices=None, x0=None, y0=None, return_canonical=False, **settings):
+        """The batch on SEVERAL devices of this node from one call (cpg_solve_batch_host_multi): contiguous shards, one host
+        thread per device inside the library, nothing exchanged between devices.  devices: list of CUDA device indices
+        (default: every visible device).  Same result object as solve_batch."""
+        for k, v in settings.items():
+            self.set_solver_setting(k, v)
+        if devices is None:
+            import torch
+            devices = list(range(torch.cuda.device_count()))
+        if not devices:
+            raise RuntimeError('no CUDA device visible (there is no CPU fallback)')
+        P = params if isinstance(params, np.ndarray) else self.pack_params(params)
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        d = self.dims
+        self._expect(P, (None, d.n_param), 'params')
+        B = P.shape[0]
+        prim = np.empty((B, d.n_prim)); dual = np.empty((B, d.n_dual))
+        solx = np.empty((B, d.n_var)) if return_canonical else None
+        soly = np.empty((B, d.n_con)) if return_canonical else None
+        obj = np.empty(B); pri = np.empty(B); dua = np.empty(B)
+        it = np.empty(B, dtype=np.int32); st = np.empty(B, dtype=np.int32)
+        s = self.settings
+        if x0 is not None and y0 is not None:
+            x0 = np.ascontiguousarray(x0, dtype=np.float64); y0 = np.ascontiguousarray(y0, dtype=np.float64)
+            self._expect(x0, (B, d.n_var), 'x0'); self._expect(y0, (B, d.n_con), 'y0')
+            s = CpgB200Settings.from_buffer_copy(bytes(self.settings)); s.warm_start = 1
+        dev = (C.c_int * len(devices))(*devices)
+
+        def p(a, t=C.c_double):
+            return None if a is None else a.ctypes.data_as(C.POINTER(t))
+        t0 = time.perf_counter()
+        self._check(self._fn('cpg_solve_batch_host_multi')(C.c_int(len(devices)), dev, C.c_int(B), p(P), p(x0), p(y0), p(prim), p(dual),
+                                                           p(solx), p(soly), p(obj), p(it, C.c_int), p(st, C.c_int), p(pri), p(dua),
+                                                           C.byref(s)))
+        t1 = time.perf_counter()
+        pr, du = self.unpack(prim, dual)
+        info = SimpleNamespace(obj_val=obj, iter=it, status=st, pri_res=pri, dua_res=dua, time=t1 - t0)
+        return SimpleNamespace(cpg_prim=pr, cpg_dual=du, cpg_info=info, prim=prim, dual=dual, sol_x=solx, sol_y=soly)
+
     def solve_batch_pinned(self, params, out, x0=None, y0=None):
         """Host-buffer entry on caller-owned (ideally pinned) torch CPU tensors: no allocation, no copies on the
         Python side.  out: dict with prim, dual, obj, pri, dua (float64) and it, st (int32) tensors."""
@@ -565,6 +604,41 @@ class SocpModule(Module):
         t0 = time.perf_counter()
         self._check(self._fn('cpg_socp_solve_batch_host')(C.c_int(B), p(P), p(prim), p(dual), p(x), p(y), p(z), p(s), p(obj),
                                                           p(it, C.c_int), p(st, C.c_int), p(pri), p(dua), C.byref(self.settings)))
+        t1 = time.perf_counter()
+        pr, du = self.unpack(prim, dual)
+        info = SimpleNamespace(obj_val=obj, iter=it, status=st, pri_res=pri, dua_res=dua, time=t1 - t0)
+        return SimpleNamespace(cpg_prim=pr, cpg_dual=du, cpg_info=info, prim=prim, dual=dual, sol_x=x, sol_y=y, sol_z=z, sol_s=s)
+
+    def solve_batch_multi(self, params, devices=None, return_canonical=False, **settings):
+        """The batch on several devices of this node from one call (cpg_socp_solve_batch_host_multi): contiguous shards, one
+        host thread per device inside the library.  Same result object as solve_batch."""
+        for k, v in settings.items():
+            self.set_solver_setting(k, v)
+        if devices is None:
+            import torch
+            devices = list(range(torch.cuda.device_count()))
+        if not devices:
+            raise RuntimeError('no CUDA device visible (there is no CPU fallback)')
+        P = params if isinstance(params, np.ndarray) else self.pack_params(params)
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        d = self.dims
+        self._expect(P, (None, d.n_param), 'params')
+        B = P.shape[0]
+        prim = np.empty((B, d.n_prim)); dual = np.empty((B, d.n_dual))
+        x = np.empty((B, d.n_var)) if return_canonical else None
+        y = np.empty((B, d.n_eq)) if return_canonical else None
+        z = np.empty((B, d.n_ineq)) if return_canonical else None
+        s = np.empty((B, d.n_ineq)) if return_canonical else None
+        obj = np.empty(B); pri = np.empty(B); dua = np.empty(B)
+        it = np.empty(B, dtype=np.int32); st = np.empty(B, dtype=np.int32)
+        dev = (C.c_int * len(devices))(*devices)
+
+        def p(a, t=C.c_double):
+            return None if a is None else a.ctypes.data_as(C.POINTER(t))
+        t0 = time.perf_counter()
+        self._check(self._fn('cpg_socp_solve_batch_host_multi')(C.c_int(len(devices)), dev, C.c_int(B), p(P), p(prim), p(dual), p(x), p(y),
+                                                                p(z), p(s), p(obj), p(it, C.c_int), p(st, C.c_int), p(pri), p(dua),
+                                                                C.byref(self.settings)))
         t1 = time.perf_counter()
         pr, du = self.unpack(prim, dual)
         info = SimpleNamespace(obj_val=obj, iter=it, status=st, pri_res=pri, dua_res=dua, time=t1 - t0)

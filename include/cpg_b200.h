@@ -77,10 +77,13 @@ typedef struct {
   int warps_per_cta, smem_bytes;
 } CpgB200Dims;
 
-/* One context per library and process, bound to ONE device: every entry point makes that device current
- * (cudaSetDevice) before it touches CUDA; a second cpg_b200_init with another device is CPG_B200_ERR_BAD_ARG
- * (multi-GPU = one process per GPU, or cvxpygen_b200.multi: one library copy per device). */
+/* One context per DEVICE (up to 16).  cpg_b200_init(device) creates / refreshes that device's context and makes it the
+ * calling THREAD's current one; every other entry point works on the calling thread's current context and makes its device
+ * current (cudaSetDevice) before it touches CUDA.  cpg_b200_use_device switches a thread to an initialised context.
+ * A multi-GPU caller therefore runs one host thread per device on the same loaded library; cpg_solve_batch_host_multi is
+ * that loop (contiguous shards of the batch, no data exchanged between devices). */
 int  CPG_B200_FN(cpg_b200_init)(int device);                 /* upload constants, allocate queues  */
+int  CPG_B200_FN(cpg_b200_use_device)(int device);
 int  CPG_B200_FN(cpg_b200_free)(void);
 int  CPG_B200_FN(cpg_b200_dims)(CpgB200Dims* out);
 void CPG_B200_FN(cpg_b200_default_settings)(CpgB200Settings* s);
@@ -130,6 +133,14 @@ int CPG_B200_FN(cpg_solve_batch_host)(int B, const double* params, const double*
                                       double* obj_val, int* iter, int* status,
                                       double* pri_res, double* dua_res,
                                       const CpgB200Settings* settings);
+
+/* The same on several devices of one node from ONE call: `devices` lists n_dev distinct device indices (NULL = 0 .. n_dev-1);
+ * instance rows [B k / n_dev, B (k+1) / n_dev) go to devices[k], each from its own host thread (initialising that device's
+ * context on first use).  No collective: instances never interact.  Returns the first non-zero shard code. */
+int CPG_B200_FN(cpg_solve_batch_host_multi)(int n_dev, const int* devices, int B, const double* params, const double* x0,
+                                            const double* y0, double* prim, double* dual, double* sol_x, double* sol_y,
+                                            double* obj_val, int* iter, int* status, double* pri_res, double* dua_res,
+                                            const CpgB200Settings* settings);
 
 /* Batched backward pass (gradient=True): differentiates the QP solution map through its KKT system.
  * Reference counterpart, one instance at a time: <p>cpg_update_d<var>(idx, val) + <p>cpg_gradient()

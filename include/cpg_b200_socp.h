@@ -59,8 +59,10 @@ const char* CPG_B200_FN(cpg_b200_last_error)(void);
 int  CPG_B200_FN(cpg_b200_launch_count)(void);               /* kernels launched by the last solve call */
 /* Device time of the last ipm_kernel launch from CUDA events on the caller's stream (blocks until it has completed);
  * tail_ms / grad_ms are -1 (same signature as the QP libraries' entry).  One context per library and process, bound
- * to one device: every entry point makes it current; a second cpg_b200_init with another device is an error. */
+ * One context per DEVICE; cpg_b200_init(device) makes that device's context the calling thread's current one, every entry
+ * point works on the calling thread's context (cpg_b200_use_device switches). */
 int  CPG_B200_FN(cpg_b200_kernel_times)(float* main_ms, float* tail_ms, float* grad_ms);
+int  CPG_B200_FN(cpg_b200_use_device)(int device);
 int  CPG_B200_FN(cpg_socp_dims)(CpgB200SocpDims* out);
 /* Replace the constant tables after a change of SHARED (non-batched) user parameters: the host re-runs the offline setup
  * (equilibration, KKT base image, affine maps) and uploads both images.  Role of ECOS_updateData for data every instance
@@ -83,6 +85,12 @@ int CPG_B200_FN(cpg_socp_solve_batch_host)(int B, const double* params, double* 
                                            double* sol_x, double* sol_y, double* sol_z, double* sol_s,
                                            double* obj_val, int* iter, int* status, double* pri_res, double* dua_res,
                                            const CpgB200SocpSettings* settings);
+
+/* The same on several devices of one node from ONE call: contiguous shards of the batch, one host thread per device inside the
+ * library (devices = NULL: 0 .. n_dev-1; distinct indices); no collective.  Returns the first non-zero shard code. */
+int CPG_B200_FN(cpg_socp_solve_batch_host_multi)(int n_dev, const int* devices, int B, const double* params, double* prim, double* dual,
+                                                 double* sol_x, double* sol_y, double* sol_z, double* sol_s, double* obj_val, int* iter,
+                                                 int* status, double* pri_res, double* dua_res, const CpgB200SocpSettings* settings);
 
 #ifdef __cplusplus
 }

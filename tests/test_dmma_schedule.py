@@ -101,17 +101,20 @@ def test_tensor_core_path_is_selected_and_fits_shared_memory(tmp_path):
     import re
     for name, builder, batch in (('mpc', lambda: families.mpc(12, 4, 10), ['x_init']), ('pf', lambda: families.portfolio_qp(50, 10), ['a', 'w_prev'])):
         d = str(tmp_path / name)
-        cpg.generate_code(builder(), code_dir=d, batch_params=batch, wrapper=False)
+        cpg.generate_code(builder(), code_dir=d, batch_params=batch, wrapper=False, solver_opts={'dmma': True})
         h = dict(re.findall(r'#define (CPG_FAM_\w+) (\d+)', open(f'{d}/c/include/cpg_family.h').read()))
         h = {k: int(v) for k, v in h.items()}
-        assert name != 'mpc' or h['CPG_FAM_DMMA'] == 1          # the headline family runs on the tensor-core kernel
+        assert name != 'mpc' or h['CPG_FAM_DMMA'] == 1          # opted in: the headline family fits the tensor-core kernel
         if not h['CPG_FAM_DMMA']:                                # too large for two groups next to its tables: straight-line kernel
             continue
         assert 2 <= h['CPG_FAM_DM_GROUPS'] <= 3
         smem = h['CPG_FAM_CBLOB_BYTES_PAD'] + h['CPG_FAM_DBLOB_BYTES_PAD'] + h['CPG_FAM_DM_GROUPS'] * (
             (h['CPG_FAM_DM_W8'] + h['CPG_FAM_DM_STAGE']) * 8 + 4 * h['CPG_FAM_DM_BV'] * 8 + 8) + 16
         assert smem <= 232448 - 1024
-    # a family with per-instance matrices has no shared factor: the tensor-core path is off
+    # a family with per-instance matrices has no shared factor: the tensor-core path stays off even when asked for; so does the default
     d = str(tmp_path / 'ltv')
-    cpg.generate_code(families.mpc_ltv(4, 2, 5), code_dir=d, batch_params=['A', 'B', 'qdiag', 'rdiag', 'x_init'], wrapper=False)
+    cpg.generate_code(families.mpc_ltv(4, 2, 5), code_dir=d, batch_params=['A', 'B', 'qdiag', 'rdiag', 'x_init'], wrapper=False, solver_opts={'dmma': True})
+    assert '#define CPG_FAM_DMMA 0' in open(f'{d}/c/include/cpg_family.h').read()
+    d = str(tmp_path / 'default')
+    cpg.generate_code(families.mpc(4, 2, 6), code_dir=d, batch_params=['x_init'], wrapper=False)
     assert '#define CPG_FAM_DMMA 0' in open(f'{d}/c/include/cpg_family.h').read()

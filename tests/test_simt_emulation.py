@@ -21,9 +21,9 @@ from oracle.grad_numpy import qp_backward, qp_backward_mat, param_gradient, para
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def build_emu(fam, batch, out_dir, flags=()):
+def build_emu(fam, batch, out_dir, flags=(), dmma=None):
     st = setup_qp_family(fam, batch)
-    codegen.write_code(st, out_dir)
+    codegen.write_code(st, out_dir, dmma=dmma)
     inc, sol, src = (os.path.join(out_dir, 'c', d) for d in ('include', 'solver_code', 'src'))
     so = os.path.join(out_dir, 'libadmm_emu.so')
     cmd = ['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-DCPG_SIMT_HOST_EMU', '-w', '-ffp-contract=off', *flags,
@@ -88,11 +88,13 @@ def test_matrix_parameter_kernel_on_the_emulator(tmp_path):
     assert np.array_equal(out2['iter'], ora2['iter']) and rel_err(out2['x'], ora2['x']).max() < 1e-8
 
 
-def test_main_kernel_on_the_emulator(tmp_path):
+@pytest.mark.parametrize('dmma', [False, True])
+def test_main_kernel_on_the_emulator(tmp_path, dmma):
     """The headline path: admm_multi_kernel (two instances per warp, generated straight-line KKT solve, lockstep CTA,
-    persistent slots refilled from the work counter) followed by admm_tail_kernel on the instances it hands off."""
+    persistent slots refilled from the work counter) followed by admm_tail_kernel on the instances it hands off; and its
+    tensor-core variant admm_dmma_kernel (groups of four warps, mma.m8n8k4.f64 emulated lane by lane, named barriers)."""
     fam = families.mpc(4, 2, 6)
-    st, lib, dims = build_emu(fam, ['x_init'], str(tmp_path))
+    st, lib, dims = build_emu(fam, ['x_init'], str(tmp_path), dmma=dmma)
     B = 29                                         # odd: the last warp slot runs half empty
     xi = np.random.default_rng(11).uniform(-1.5, 1.5, (B, 4))
     q, l, u = canon_batches(fam, {'x_init': xi}, B)
@@ -114,9 +116,10 @@ def test_main_kernel_on_the_emulator(tmp_path):
     assert np.array_equal(out2['iter'], ora2['iter']) and rel_err(out2['x'], ora2['x']).max() < 1e-8
 
 
-@pytest.mark.parametrize('name,B', [('nonneg_LS_3_2', 40), ('box_qp_6_8', 96), ('random_qp_20_5_15', 24),
-                                    ('mpc_12_4_10', 12), ('portfolio_qp_50_10', 6)])
-def test_standard_families_on_the_emulator(name, B, tmp_path):
+@pytest.mark.parametrize('name,B,dmma', [('nonneg_LS_3_2', 40, False), ('box_qp_6_8', 96, False), ('random_qp_20_5_15', 24, False),
+                                         ('mpc_12_4_10', 12, False), ('portfolio_qp_50_10', 6, False),
+                                         ('box_qp_6_8', 96, True), ('mpc_12_4_10', 20, True)])
+def test_standard_families_on_the_emulator(name, B, dmma, tmp_path):
     """Main + tail kernels of the standard families -- incl. the headline MPC-12/4/10 family with its 374-step generated solve and
     the 742-row portfolio QP --: unstructured sparsity with q, l, u all batched; box_qp's corner
     cases -- bounds that change a constraint's type (hand-off at iteration 0), primal and dual infeasibility certificates,
@@ -130,7 +133,7 @@ def test_standard_families_on_the_emulator(name, B, tmp_path):
         params, kind = corner_case_batch(fam, B)
         q, l, u = canon_batches(fam, params, B)
     batch = standard.STANDARD[name][1]
-    st, lib, dims = build_emu(fam, batch, str(tmp_path))
+    st, lib, dims = build_emu(fam, batch, str(tmp_path), dmma=dmma)      # dmma: the tensor-core variant of the main kernel
     out = run_solve(lib, 'emu_main_solve', dims, _rows(fam, st, params, B), grid=2)
     ora = oracle_solve(fam, q, l, u)
     info = SimpleNamespace(status=out['status'], iter=out['iter'], obj_val=out['obj'], pri_res=out['pri'], dua_res=out['dua'])

@@ -12,8 +12,8 @@ VARIANTS = {      # name -> (family, extra nvcc flags, batch[, solver_opts])
     'ltv_gather': ('mpc_ltv_12_4_10', '-DCPG_TAIL_GATHER_FACTOR=1', 20000),
     'mpc_atomic': ('mpc_12_4_10', '', 100000, {'dmma': False}),
     'mpc_gather': ('mpc_12_4_10', '-DCPG_TAIL_GATHER_FACTOR=1', 100000, {'dmma': False}),
-    'mpc_dmma_g3': ('mpc_12_4_10', '', 100000, {'dmma_groups': 3}),
-    'mpc_dmma_g2': ('mpc_12_4_10', '', 100000, {'dmma_groups': 2}),
+    'mpc_dmma_g3': ('mpc_12_4_10', '', 100000, {'dmma': True, 'dmma_groups': 3}),
+    'mpc_dmma_g2': ('mpc_12_4_10', '', 100000, {'dmma': True, 'dmma_groups': 2}),
 }
 
 
