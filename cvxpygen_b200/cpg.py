@@ -55,8 +55,18 @@ def generate_code(problem, code_dir='cpg_code', solver=None, solver_opts=None, e
         # SOCP families: Mehrotra interior-point kernel (role of solver='ECOS' in the reference, cvxpygen/solvers/ecos.py)
         from . import codegen_ipm
         from .offline.socp_setup import setup_socp_family
-        if gradient:
-            raise ValueError('gradient=True is generated for the QP path (ADMM-CUDA) only')
+        if fam.solver_type == 'quadratic':
+            # a QP handed to the conic backend (the reference solves QPs with ECOS / SCS / Clarabel too).  With gradient=True this
+            # is the reference's two-stage route (cvxpygen/canonicalizer.py:54-65): conic forward solve, QP backward pass.
+            from . import two_stage
+            if gradient:
+                out = two_stage.generate_two_stage(fam, code_dir, batch_params, prefix=prefix, verbose=verbose, compile=wrapper)
+                sys.stdout.write('cvxpygen_b200 finished generating code (two-stage gradient: IPM-CUDA forward, QP backward).\n')
+                return out
+            fam = two_stage.conic_family_of_qp(fam, batch_params)
+        elif gradient:
+            raise ValueError('gradient=True needs a problem that has a QP canonical form (extended DPP, cvxpygen/canonicalizer.py:338-345): '
+                             'pass the QP family and solver=\'IPM-CUDA\' for the two-stage route')
         from .offline.socp_setup import DEFAULT_THREADS
         setup = setup_socp_family(fam, batch_params, threads=int(opts.get('threads') or DEFAULT_THREADS))
         codegen_ipm.write_ipm_code(setup, code_dir, prefix=prefix, threads=opts.get('threads'))

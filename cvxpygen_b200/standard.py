@@ -33,10 +33,13 @@ STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
     # the reference's network-flow LP (tests/test_E2E_LP.py, solved there with ECOS): vectors per instance, routing matrix shared
     'adp_socp_6_3': (lambda: families.adp_socp(), ['f']),      # the reference's SOCP test problem (tests/test_E2E_SOCP.py), four second-order cones, no LP cone
     'network_lp_50_10': (lambda: families.network_lp(50, 10), ['c', 'w', 'f_min', 'f_max']),
+    # f4: the reference's two-stage gradient (QP family, conic forward solve by IPM-CUDA, QP backward pass): <dir> + <dir>/gradient
+    'mpc_6_3_10_two_stage': (lambda: families.mpc(6, 3, 10), ['x_init']),
 }
+TWO_STAGE_NAMES: List[str] = ['mpc_6_3_10_two_stage']
 
 # families solved by the ADMM (QP) backend / by the interior-point (SOCP) backend
-SOCP_NAMES: List[str] = [n for n in STANDARD if '_socp_' in n or n.startswith('network_lp')]     # conic families (IPM-CUDA)
+SOCP_NAMES: List[str] = [n for n in STANDARD if '_socp_' in n or n.startswith('network_lp') or n.endswith('_two_stage')]     # conic families (IPM-CUDA)
 MATPAR_NAMES: List[str] = ['mpc_ltv_6_3_10', 'mpc_ltv_12_4_10', 'mpc_ref_6_3_10', 'actuator_1_3', 'osqp_update_matrices_5_8',
                            'nonneg_LS_3_2_A']
 QP_NAMES: List[str] = [n for n in STANDARD if n not in SOCP_NAMES and n not in MATPAR_NAMES]
@@ -53,8 +56,9 @@ def build(name: str, force: bool = False, verbose: bool = False) -> str:
     fam_fn, batch = STANDARD[name]
     os.makedirs(GENERATED_DIR, exist_ok=True)
     fam = fam_fn()
-    solver = 'IPM-CUDA' if fam.solver_type == 'conic' else 'ADMM-CUDA'
-    generate_code(fam, code_dir=d, solver=solver, batch_params=batch, prefix='', wrapper=True, verbose=verbose)
+    two_stage = name in TWO_STAGE_NAMES
+    solver = 'IPM-CUDA' if (fam.solver_type == 'conic' or two_stage) else 'ADMM-CUDA'
+    generate_code(fam, code_dir=d, solver=solver, batch_params=batch, prefix='', wrapper=True, verbose=verbose, gradient=two_stage)
     return d
 
 
@@ -70,4 +74,7 @@ def build_all(force: bool = False, verbose: bool = False, jobs: int = None):
 
 def load(name: str, device: int = 0):
     from . import runtime
+    if name in TWO_STAGE_NAMES:
+        from .two_stage import TwoStageModule
+        return TwoStageModule(build(name), device)
     return runtime.load(build(name), device)
