@@ -25,7 +25,7 @@ from typing import Optional
 
 import numpy as np
 
-from .offline.blob import header_struct_c, tail_header_struct_c, grad_header_struct_c, mat_header_struct_c
+from .offline.blob import header_struct_c, tail_header_struct_c, grad_header_struct_c, mat_header_struct_c, TAIL_HEADER_FIELDS
 from .offline.qp_setup import QPSetup
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -52,7 +52,7 @@ DMMA_MAX_GROUPS = 3         # 12 warps x <= 170 registers
 
 
 def _family_header(setup: QPSetup, prefix: str, warps: Optional[int], ni: Optional[int] = None, dmma: Optional[bool] = None,
-                   dmma_groups: Optional[int] = None) -> str:
+                   dmma_groups: Optional[int] = None, force_big: bool = False) -> str:
     nk = setup.n + setup.m
     w_stride = nk + (nk % 2)
     blob_pad = (len(setup.blob) + 127) // 128 * 128
@@ -61,22 +61,28 @@ def _family_header(setup: QPSetup, prefix: str, warps: Optional[int], ni: Option
         ni = DEFAULT_NI
     assert ni in (2, 4)
     pair_stride = ni * w_stride + ni * nb_slots + 2
+    # BIG families: the tile schedule of the main kernel does not fit next to one warp's work vectors (the reference generates
+    # code for any size).  Such a family is solved by the per-instance-factor kernel alone (admm_tail_kernel: every instance is
+    # queued at iteration 0, the warp factors K itself from the family's tables) with the constants read through L1 / L2
+    # instead of being staged, so that shared memory holds only the warps' work vector + factor.
+    big = bool(force_big) or blob_pad + pair_stride * 8 > SMEM_BUDGET       # force_big: exercise the path on small families (tests)
     if warps is None:
         warps = max(1, min(MAX_WARPS[ni], (SMEM_BUDGET - blob_pad) // (pair_stride * 8)))
-    if blob_pad + pair_stride * 8 > SMEM_BUDGET:
-        raise ValueError(f'constants blob of {len(setup.blob)} bytes does not fit in shared memory')
     trail = max(setup.schedule.n_trailing_tiles, 0)
     s_stride = setup.refactor.n_slots + (setup.refactor.n_slots % 2)
     cblob_pad = (len(setup.blob_compact) + 127) // 128 * 128
-    tail_warps = max(1, min(8, (SMEM_BUDGET - cblob_pad) // ((w_stride + s_stride) * 8)))
-    if cblob_pad + (w_stride + s_stride) * 8 > SMEM_BUDGET:
-        raise ValueError('constants blob + one refactorisation workspace do not fit in shared memory')
+    tail_stage = int(not big and cblob_pad + (w_stride + s_stride) * 8 <= SMEM_BUDGET)
+    tail_warps = max(1, min(8, (SMEM_BUDGET - (cblob_pad if tail_stage else 0)) // ((w_stride + s_stride) * 8)))
+    if (w_stride + s_stride) * 8 > SMEM_BUDGET:
+        raise ValueError(f'one instance of this family (work vector + numeric factor = {(w_stride + s_stride) * 8} bytes) does not fit '
+                         f'the {SMEM_BUDGET} bytes of shared memory of one SM')
     gblob_pad = (len(setup.grad_blob) + 127) // 128 * 128
     n_pad, m_pad = (setup.n + 1) // 2 * 2, (setup.m + 1) // 2 * 2
     grad_stride = s_stride + 2 * w_stride + n_pad + m_pad
     if setup.mat_blob:      # matrix-parameter backward pass: + canonical x and the entries of P per warp
         grad_stride += n_pad + (setup.nnzP + 2) // 2 * 2
-    grad_warps = max(1, min(8, (SMEM_BUDGET - gblob_pad) // (grad_stride * 8)))
+    grad_ok = int(gblob_pad + grad_stride * 8 <= SMEM_BUDGET)       # else: the backward kernel is not generated for this size
+    grad_warps = max(1, min(8, (SMEM_BUDGET - gblob_pad) // (grad_stride * 8))) if grad_ok else 1
     # f2: per-instance matrix parameters -- per warp in shared memory: w | S | Pv (nothing staged, tables stay in L2; the
     # scaled entries of A and the scalings D, 1/D, E, 1/E sit in a per-warp slice of a global scratch buffer)
     matpar = 1 if setup.mat_blob else 0
@@ -97,7 +103,11 @@ def _family_header(setup: QPSetup, prefix: str, warps: Optional[int], ni: Option
     # opt-in (solver_opts={'dmma': True}): measured on B200 the tensor-core kernel is correct (identical iteration counts on 100 000
     # instances) but 28 % slower than the straight-line kernel on the MPC family -- its compressed coefficient tables cost as many
     # instructions and shared-memory wavefronts per useful FMA as the dense steps they replace
-    use_dmma = int(bool(setup.dmma_blob) and dm_groups >= 2 and dmma is True and dm_w8 // 4 >= 2 * w_stride)
+    use_dmma = int(bool(setup.dmma_blob) and dm_groups >= 2 and dmma is True and dm_w8 // 4 >= 2 * w_stride and not big)
+    # tile headers of the per-instance triangular solves as a compile-time table (constant memory, admm_kernel.cuh:kTailTiles)
+    th = dict(zip([n_ for _, n_ in TAIL_HEADER_FIELDS], np.frombuffer(setup.tail_blob, dtype='<i4', count=len(TAIL_HEADER_FIELDS))))
+    n_tt = max(int(th['n_fwd_tiles'] + th['n_bwd_tiles']), 1)
+    tail_tiles = np.frombuffer(setup.tail_blob, dtype='<i4', count=8 * n_tt, offset=int(th['off_i32']) + 4 * int(th['i_tiles']))
     lines = [
         '/* Auto-generated by cvxpygen_b200 %s -- compile-time sizes of problem family "%s". */' % (time.strftime('%Y-%m-%d'), setup.family.name),
         '#ifndef CPG_FAMILY_H', '#define CPG_FAMILY_H',
@@ -114,6 +124,8 @@ def _family_header(setup: QPSetup, prefix: str, warps: Optional[int], ni: Option
         f'#define CPG_FAM_NI {ni}', f'#define CPG_FAM_MULTI_STRIDE {pair_stride}', f'#define CPG_FAM_S_STRIDE {s_stride}', f'#define CPG_FAM_TAIL_WARPS {tail_warps}',
         f'#define CPG_FAM_MATPAR {matpar}', f'#define CPG_FAM_MAT_WARPS {mat_warps}', f'#define CPG_FAM_MAT_STRIDE {mat_stride}',
         f'#define CPG_FAM_MAT_A_STRIDE {mat_a}', f'#define CPG_FAM_MAT_P_STRIDE {mat_p}', f'#define CPG_FAM_MAT_G_STRIDE {mat_g_stride}',
+        '#define CPG_FAM_TAIL_TILES {' + ', '.join(str(int(v)) for v in tail_tiles) + '}',
+        f'#define CPG_FAM_BIG {int(big)}', f'#define CPG_FAM_TAIL_STAGE {tail_stage}', f'#define CPG_FAM_GRAD {grad_ok}',
         f'#define CPG_FAM_DMMA {use_dmma}', f'#define CPG_FAM_DM_GROUPS {max(dm_groups, 1)}', f'#define CPG_FAM_DBLOB_BYTES_PAD {dblob_pad}',
         f'#define CPG_FAM_DM_W8 {dm_w8}', f'#define CPG_FAM_DM_STAGE {dm_stage}', f'#define CPG_FAM_DM_BV {dm_bv}',
         '#endif', '']
@@ -136,7 +148,7 @@ def _blob_c(setup: QPSetup) -> str:
 
 
 def write_code(setup: QPSetup, code_dir: str, prefix: str = '', warps: Optional[int] = None, ni: Optional[int] = None,
-               dmma: Optional[bool] = None, dmma_groups: Optional[int] = None) -> None:
+               dmma: Optional[bool] = None, dmma_groups: Optional[int] = None, force_big: bool = False) -> None:
     prefix = c_ident(prefix)
     shutil.rmtree(code_dir, ignore_errors=True)
     for sub in ('c/src', 'c/include', 'c/build', 'c/solver_code'):
@@ -146,11 +158,12 @@ def write_code(setup: QPSetup, code_dir: str, prefix: str = '', warps: Optional[
     for f in ('admm_kernel.cuh', 'admm_multi_kernel.cuh', 'grad_kernel.cuh', 'matpar_kernel.cuh', 'cpg_b200_module.cu'):
         shutil.copyfile(os.path.join(_CSRC, f), os.path.join(sol, f))
     with open(os.path.join(inc, 'cpg_family.h'), 'w') as f:
-        f.write(_family_header(setup, prefix, warps, ni, dmma, dmma_groups))
+        f.write(_family_header(setup, prefix, warps, ni, dmma, dmma_groups, force_big))
     with open(os.path.join(inc, 'cpg_blob_layout.h'), 'w') as f:
         f.write('/* Auto-generated by cvxpygen_b200 from offline/blob.py:HEADER_FIELDS. */\n#pragma once\n' + header_struct_c() + tail_header_struct_c() + grad_header_struct_c() + mat_header_struct_c())
     with open(os.path.join(inc, 'cpg_kkt_solve_gen.cuh'), 'w') as f:
-        f.write(setup.solve_source)
+        f.write(setup.solve_source if '#define CPG_FAM_BIG 0' in open(os.path.join(inc, 'cpg_family.h')).read()
+                else '// BIG family: the straight-line schedule is not compiled (solved by the per-instance-factor kernel)\n')
     with open(os.path.join(src, 'cpg_blob.c'), 'w') as f:
         f.write(_blob_c(setup))
     with open(os.path.join(code_dir, 'cpg_blob.bin'), 'wb') as f:     # same bytes, for cpg_b200_load_constants / NCCL broadcast

@@ -81,7 +81,7 @@ def generate_code(problem, code_dir='cpg_code', solver=None, solver_opts=None, e
     setup = setup_qp_family(fam, batch_params, rho=opts.get('rho', 0.1), sigma=opts.get('sigma', 1e-6),
                             scaling=opts.get('scaling', 10), max_group_rows=opts.get('max_group_rows', 32))
     codegen.write_code(setup, code_dir, prefix=prefix, warps=opts.get('warps'), ni=opts.get('ni'), dmma=opts.get('dmma'),
-                       dmma_groups=opts.get('dmma_groups'))
+                       dmma_groups=opts.get('dmma_groups'), force_big=bool(opts.get('force_big')))
     sys.stdout.write('cvxpygen_b200 finished generating code.\n')
     if wrapper:
         sys.stdout.write('Compiling CUDA solver library (nvcc, sm_100a) ...\n')

@@ -240,46 +240,109 @@ __device__ __forceinline__ double group_sweep(double val, const uint16_t* __rest
 // The same sweep when the group's couplings sit in a packed strict-lower triangle Sg[tri(j) + t] (j = row being swept,
 // t > j its dependents; offline/refactor.py:tri_offset): no index table -- an ascending sweep reads consecutive addresses
 // across the lanes, a descending one reads column t of the triangle at a per-lane base.
+// tri(j) = j (g - 1) - j (j - 1) / 2 - (j + 1);   coupling (t, j), t > j, at tri(j) + t;   tri(j + 1) - tri(j) = g - 2 - j
+//
+// Profile of the first version (profiles/r1_matpar_v2, source page): these sweeps were HALF of the matrix-parameter kernel's
+// instructions -- 18 per row (per-row predicates, address arithmetic, divergence bookkeeping) around the 4 that do the work
+// (two SHFL halves, one LDS, one DFMA).  Now: the coefficient loads are unconditional (a lane that does not depend on row j reads
+// a valid neighbouring slot and discards it -- the update is a predicated DFMA), and a full group (g = 32, the chain groups of the
+// MPC families) runs fully unrolled with every row index, shuffle source and triangle offset an immediate.
+constexpr __host__ __device__ int tri32(int j) { return j * 31 - (j * (j - 1)) / 2 - (j + 1); }
+
 template <bool ASCENDING>
-__device__ __forceinline__ double group_sweep_dense(double val, const double* __restrict__ Sg, const int g, const int lane) {
-  // tri(j) = j (g - 1) - j (j - 1) / 2 - (j + 1);   coupling (t, j), t > j, at tri(j) + t;   tri(j + 1) - tri(j) = g - 2 - j
-  const int nblk = (g + 7) >> 3;
+__device__ __forceinline__ double group_sweep_dense32(double val, const double* __restrict__ Sg, const int lane) {
   if (ASCENDING) {
-    const bool in = lane < g;
-    const double* p = Sg - 1 + lane;            // tri(0) + lane
-    int step = g - 2;                           // tri(j + 1) - tri(j) at j = 0
-    for (int blk = 0; blk < nblk; ++blk) {
-      const int lb = lane - blk * 8;            // dep_u  <=>  lane > blk * 8 + u
+    const double* p = Sg + lane;                       // coupling (lane, j) at Sg[tri(j) + lane]; Sg[-1] exists (slot >= nk)
+#pragma unroll
+    for (int blk = 0; blk < 4; ++blk) {
       double cf[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cf[u] = p[tri32(blk * 8 + u)];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        cf[u] = (in && lb > u) ? *p : 0.0;
-        p += step; --step;
+        const int j = blk * 8 + u;
+        const double vj = __shfl_sync(FULL, val, j);
+        if (lane > j) val = fma(-cf[u], vj, val);
       }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (blk * 8 + u < g) val = fma(-cf[u], __shfl_sync(FULL, val, blk * 8 + u), val);
     }
   } else {
-    const int tl = lane < g ? lane : g - 1;
-    const double* p = Sg + (tl * (g - 1) - (tl * (tl - 1)) / 2 - (tl + 1)) + (g - 1);     // tri(lane) + j at j = g - 1
-    for (int blk = 0; blk < nblk; ++blk) {
-      const int lb = g - 1 - blk * 8 - lane;    // dep_u  <=>  lane < g - 1 - blk * 8 - u
+    const double* p = Sg + (lane * 31 - (lane * (lane - 1)) / 2 - (lane + 1));   // coupling (j, lane), j > lane, at Sg[tri(lane) + j]
+#pragma unroll
+    for (int blk = 0; blk < 4; ++blk) {
       double cf[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) cf[u] = (lb > u) ? p[-u] : 0.0;
-      p -= 8;
+      for (int u = 0; u < 8; ++u) cf[u] = p[31 - blk * 8 - u];      // lane 31 reads up to 31 slots past its (empty) column: inside S
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (blk * 8 + u < g) val = fma(-cf[u], __shfl_sync(FULL, val, g - 1 - blk * 8 - u), val);
+      for (int u = 0; u < 8; ++u) {
+        const int j = 31 - blk * 8 - u;
+        const double vj = __shfl_sync(FULL, val, j);
+        if (lane < j) val = fma(-cf[u], vj, val);
+      }
     }
   }
   return val;
 }
 
+template <bool ASCENDING>
+__device__ __forceinline__ double group_sweep_dense(double val, const double* __restrict__ Sg, const int g, const int lane) {
+  if (g == 32) return group_sweep_dense32<ASCENDING>(val, Sg, lane);
+  const int tl = lane < g ? lane : g - 1;              // lanes beyond the group compute on a copy of the last row (never read)
+  if (ASCENDING) {
+    const double* p = Sg - 1 + tl;                     // tri(0) + lane
+    int step = g - 2;                                  // tri(j + 1) - tri(j) at j = 0
+    int j = 0;
+    for (; j + 4 <= g; j += 4) {
+      double cf[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { cf[u] = *p; p += step; --step; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double vj = __shfl_sync(FULL, val, j + u);
+        if (lane > j + u) val = fma(-cf[u], vj, val);
+      }
+    }
+    for (; j < g; ++j) {
+      const double cf = *p; p += step; --step;
+      const double vj = __shfl_sync(FULL, val, j);
+      if (lane > j) val = fma(-cf, vj, val);
+    }
+  } else {
+    const double* p = Sg + (tl * (g - 1) - (tl * (tl - 1)) / 2 - (tl + 1)) + (g - 1);     // tri(lane) + j at j = g - 1
+    int j = g - 1;
+    for (; j >= 3; j -= 4) {
+      double cf[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cf[u] = p[-u];
+      p -= 4;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double vj = __shfl_sync(FULL, val, j - u);
+        if (lane < j - u) val = fma(-cf[u], vj, val);
+      }
+    }
+    for (; j >= 0; --j) {
+      const double cf = *p; --p;
+      const double vj = __shfl_sync(FULL, val, j);
+      if (lane < j) val = fma(-cf, vj, val);
+    }
+  }
+  return val;
+}
+
+// Tile headers of the triangular solves (8 ints per tile, offline/blob.py:pack_tail_blob).  They are the same for every warp and
+// every instance, so a family's generated header carries them as a compile-time table that lands in CONSTANT memory: one uniform
+// LDC per field instead of dependent global loads behind an L1 that the entry words keep flushing (the header / row-list loads
+// were the three largest stall sites of the first version).  Code generated before this table existed reads them from the blob.
+#ifdef CPG_FAM_TAIL_TILES
+__constant__ const int kTailTiles[] = CPG_FAM_TAIL_TILES;
+#define CPG_TAIL_TILE_PTR(tv) (kTailTiles)
+#else
+#define CPG_TAIL_TILE_PTR(tv) ((tv).I32 + (tv).H->i_tiles)
+#endif
+
 // K x = b with the per-instance factor: grouped level-scheduled L solve, D^{-1}, L' solve (QDLDL_solve, qdldl.c:269-281)
 __device__ __forceinline__ void tail_solve(const TailView& tv, const double* S, double* w, int lane) {
-  const int* T = tv.I32 + tv.H->i_tiles;
+  const int* T = CPG_TAIL_TILE_PTR(tv);
   const int nf = tv.H->n_fwd_tiles, nt = nf + tv.H->n_bwd_tiles, nk = tv.H->nk;
   for (int t = 0; t < nt; ++t) {
     if (t == nf) {
@@ -287,9 +350,9 @@ __device__ __forceinline__ void tail_solve(const TailView& tv, const double* S, 
       __syncwarp();
     }
     const int* h = T + 8 * t;
+    const int row = __ldg(tv.U16 + h[5] + lane);        // issued before the entry words: its latency hides behind them
     const double acc = slot_tile_acc(h, tv.I32, S, w, lane);
     const int nrows = h[4];
-    const int row = tv.U16[h[5] + lane];
     double val = w[row] - acc;
     if (h[7] == 2) val = (t < nf) ? group_sweep_dense<true>(val, S + h[6], nrows, lane)
                                   : group_sweep_dense<false>(val, S + h[6], nrows, lane);
@@ -794,6 +857,18 @@ __device__ void solve_instance(const CpgBlobHeader* __restrict__ H, const int* _
   }
 }
 
+// BIG families: every instance goes to the per-instance-factor kernel from iteration 0 (cold start, the family's rho)
+__global__ void queue_all_kernel(const BatchIO io, int words, int rho_word, double rho) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= io.B) return;
+  double* ts = io.tail_state + (size_t)b * words;
+  for (int k = 0; k < words; ++k) ts[k] = 0.0;
+  ts[rho_word] = rho;
+  io.tail_ids[b] = b;
+  io.status[b] = ST_HANDOFF; io.iter[b] = 0;
+  if (b == 0) *io.tail_count = io.B;
+}
+
 // Tail kernel: instances whose rho changed (or whose bounds changed a constraint type) continue here with their
 // own numeric factor.  One warp per instance; reads the hand-off queue written by admm_batch_kernel.
 template <class Fam>
@@ -805,21 +880,26 @@ admm_tail_kernel(const uint8_t* __restrict__ blob_g, const uint8_t* __restrict__
   const int n_tail = min(*io.tail_count, io.tail_capacity);
   if (n_tail == 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t total = reinterpret_cast<const CpgBlobHeader*>(blob_g)->total_bytes;
-  if (tid == 0) mbar_init(&bar, 1);
-  __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&bar, total);
-    constexpr uint32_t CHUNK = 32768;
-    for (uint32_t off = 0; off < total; off += CHUNK)
-      tma_bulk_g2s(smem + off, blob_g + off, (total - off < CHUNK) ? (total - off) : CHUNK, &bar);
-  }
-  mbar_wait(&bar, 0);
-  const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(smem);
-  const int* I32 = reinterpret_cast<const int*>(smem + H->off_i32);
-  const double* F64 = reinterpret_cast<const double*>(smem + H->off_f64);
-  const uint16_t* U16 = reinterpret_cast<const uint16_t*>(smem + H->off_u16);
-  double* wbase = reinterpret_cast<double*>(smem + Fam::CBLOB_BYTES_PAD) + (size_t)warp * (Fam::W_STRIDE + Fam::S_STRIDE);
+  const uint8_t* base = blob_g;
+  int ws_off = 0;
+  if constexpr (Fam::TAIL_STAGE) {     // the compact constants blob fits next to the warps' workspaces: stage it with TMA
+    const uint32_t total = reinterpret_cast<const CpgBlobHeader*>(blob_g)->total_bytes;
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&bar, total);
+      constexpr uint32_t CHUNK = 32768;
+      for (uint32_t off = 0; off < total; off += CHUNK)
+        tma_bulk_g2s(smem + off, blob_g + off, (total - off < CHUNK) ? (total - off) : CHUNK, &bar);
+    }
+    mbar_wait(&bar, 0);
+    base = smem; ws_off = Fam::CBLOB_BYTES_PAD;
+  }                                    // else (large families): the tables are read through L1 / L2 where they lie
+  const CpgBlobHeader* H = reinterpret_cast<const CpgBlobHeader*>(base);
+  const int* I32 = reinterpret_cast<const int*>(base + H->off_i32);
+  const double* F64 = reinterpret_cast<const double*>(base + H->off_f64);
+  const uint16_t* U16 = reinterpret_cast<const uint16_t*>(base + H->off_u16);
+  double* wbase = reinterpret_cast<double*>(smem + ws_off) + (size_t)warp * (Fam::W_STRIDE + Fam::S_STRIDE);
   TailArgs ta;
   ta.tv = make_tail_view(tail_blob_g);
   ta.S = wbase + Fam::W_STRIDE;

@@ -46,7 +46,17 @@ template <> struct MultiOps<4> {
 };
 
 }  // namespace cpgb200
-#if !CPG_FAM_DMMA
+#ifndef CPG_FAM_BIG
+#define CPG_FAM_BIG 0
+#endif
+#ifndef CPG_FAM_DMMA
+#define CPG_FAM_DMMA 0
+#endif
+// the generated straight-line schedule is compiled only for the kernel that runs it: not for the tensor-core variant and not for
+// BIG families (schedule larger than shared memory: solved by the per-instance-factor kernel alone, nvcc never sees their
+// hundreds of thousands of generated lines)
+#define CPG_FAM_STRAIGHT (!CPG_FAM_DMMA && !CPG_FAM_BIG)
+#if CPG_FAM_STRAIGHT
 #include "cpg_kkt_solve_gen.cuh"     // straight-line schedule of this family, template <int NI>
 #endif
 namespace cpgb200 {
@@ -655,7 +665,7 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
       par ^= 1;
     } else {
       __syncwarp();
-#if !CPG_FAM_DMMA
+#if CPG_FAM_STRAIGHT
       cpg_kkt_solve_gen<NI>(F64, I32, U16, wN, lane);
 #endif
     }

@@ -44,6 +44,7 @@ struct Fam {
   static constexpr int W_STRIDE = CPG_FAM_W_STRIDE;       // doubles per warp work vector
   static constexpr int S_STRIDE = CPG_FAM_S_STRIDE;       // doubles per warp factor storage (tail kernel)
   static constexpr int TAIL_WARPS = CPG_FAM_TAIL_WARPS;
+  static constexpr bool TAIL_STAGE = CPG_FAM_TAIL_STAGE != 0;   // the tail kernel stages the compact blob (else: reads it through L2)
   static constexpr int GBLOB_BYTES_PAD = CPG_FAM_GBLOB_BYTES_PAD;
   static constexpr int GRAD_WARPS = CPG_FAM_GRAD_WARPS;
   static constexpr int GRAD_STRIDE = CPG_FAM_GRAD_STRIDE;
@@ -65,7 +66,7 @@ constexpr int MAT_SMEM_BYTES = Fam::MAT_WARPS * Fam::MAT_STRIDE * 8;
 constexpr int SMEM_BYTES = Fam::BLOB_BYTES_PAD + Fam::WARPS * Fam::MULTI_STRIDE * 8;
 constexpr int DMMA_SMEM_BYTES = Fam::CBLOB_BYTES_PAD + Fam::DBLOB_BYTES_PAD +
                                 Fam::DM_GROUPS * ((Fam::DM_W8 + Fam::DM_STAGE) * 8 + 4 * Fam::DM_BV * 8 + 8) + 16;
-constexpr int TAIL_SMEM_BYTES = Fam::CBLOB_BYTES_PAD + Fam::TAIL_WARPS * (Fam::W_STRIDE + Fam::S_STRIDE) * 8;
+constexpr int TAIL_SMEM_BYTES = (Fam::TAIL_STAGE ? Fam::CBLOB_BYTES_PAD : 0) + Fam::TAIL_WARPS * (Fam::W_STRIDE + Fam::S_STRIDE) * 8;
 constexpr int TAIL_WORDS = Fam::N + 2 * Fam::M + 2;
 constexpr int GRAD_SMEM_BYTES = Fam::GBLOB_BYTES_PAD + Fam::GRAD_WARPS * Fam::GRAD_STRIDE * 8;
 
@@ -305,10 +306,12 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
   CK(cudaMemcpy(g.d_gblob, CPG_B200_FN(cpg_gblob_words), CPG_B200_FN(cpg_gblob_nbytes), cudaMemcpyHostToDevice));
   if (!g.d_gS0) CK(cudaMalloc(&g.d_gS0, CPG_B200_FN(cpg_gS0_nbytes)));
   CK(cudaMemcpy(g.d_gS0, CPG_B200_FN(cpg_gS0_words), CPG_B200_FN(cpg_gS0_nbytes), cudaMemcpyHostToDevice));
+#if CPG_FAM_GRAD
 #if CPG_FAM_MATPAR
   CK(cudaFuncSetAttribute(cpgb200::qp_grad_kernel<Fam, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAD_SMEM_BYTES));
 #else
   CK(cudaFuncSetAttribute(cpgb200::qp_grad_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAD_SMEM_BYTES));
+#endif
 #endif
   if (!g.d_tail_blob) CK(cudaMalloc(&g.d_tail_blob, CPG_B200_FN(cpg_tail_blob_nbytes)));
   CK(cudaMemcpy(g.d_tail_blob, CPG_B200_FN(cpg_tail_blob_words), CPG_B200_FN(cpg_tail_blob_nbytes), cudaMemcpyHostToDevice));
@@ -321,7 +324,9 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
 #endif
   if (!g.d_counter) CK(cudaMalloc(&g.d_counter, sizeof(unsigned int)));
   if (!g.d_tail_count) CK(cudaMalloc(&g.d_tail_count, sizeof(int)));
-#if CPG_FAM_DMMA
+#if CPG_FAM_BIG
+  // nothing to prepare: the main kernel is not part of this library
+#elif CPG_FAM_DMMA
   if (!g.d_dblob) CK(cudaMalloc(&g.d_dblob, Fam::DBLOB_BYTES_PAD));
   CK(cudaMemcpy(g.d_dblob, CPG_B200_FN(cpg_dblob_words), CPG_B200_FN(cpg_dblob_nbytes), cudaMemcpyHostToDevice));
   CK(cudaFuncSetAttribute(cpgb200::admm_dmma_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, DMMA_SMEM_BYTES));
@@ -399,7 +404,16 @@ int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const doubl
   // one persistent CTA per SM; a batch smaller than one wave of slots is still spread over all SMs (every warp pulls its
   // instances from the global counter), so that few warps share an SM's shared-memory bandwidth: lower latency
   int grid = g.n_sm;
-#if CPG_FAM_DMMA
+#if CPG_FAM_BIG
+  // the tile schedule of this family is larger than shared memory: every instance is solved on its own numeric factor by the
+  // per-instance-factor kernel (cold start; x0 / y0 are not used on this path), tables read through L2
+  {
+    const CpgBlobHeader* Hh = reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words));
+    CK(cudaEventRecord(g.ev[0], stream));
+    cpgb200::queue_all_kernel<<<(B + 255) / 256, 256, 0, stream>>>(io, TAIL_WORDS, Fam::N + 2 * Fam::M, Hh->rho);
+    (void)grid;
+  }
+#elif CPG_FAM_DMMA
   // tensor-core main kernel: a group of four warps takes eight instances at a time (KKT factor shared by the batch:
   // the solve is a dense contraction over instances, mma.sync.m8n8k4.f64)
   const int need = (B + 7) / 8;
@@ -511,6 +525,10 @@ int CPG_B200_FN(cpg_gradient_batch_device)(int B, const double* sol_x, const dou
   USE_DEVICE();
 #if CPG_FAM_MATPAR
   snprintf(g.err, sizeof(g.err), "this family has per-instance matrix parameters: call cpg_gradient_batch_*_mat (it needs the parameter rows)");
+  return CPG_B200_ERR_BAD_ARG;
+#endif
+#if !CPG_FAM_GRAD
+  snprintf(g.err, sizeof(g.err), "the backward kernel is not generated for a family of this size (its factor workspace exceeds shared memory)");
   return CPG_B200_ERR_BAD_ARG;
 #endif
   if (B < 0 || !sol_y || !dprim) return CPG_B200_ERR_BAD_ARG;

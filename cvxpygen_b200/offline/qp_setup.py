@@ -128,11 +128,15 @@ def setup_qp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None,
                              Mq_b=Mq_b, Ml_b=Ml_b, Mu_b=Mu_b, npb=npb, prim_idx=prim_idx, dual_idx=dual_idx,
                              d_const=d_const, is_max=fam.is_maximization, with_tiles=False)
     dmma_blob, dmma_rounds = b'', 0
-    if dmma and not mat_params:      # shared KKT factor: the solve of eight instances is a dense contraction -> FP64 tensor cores
+    if dmma and not mat_params and len(blob) <= 227 * 1024:      # (families beyond one SM's shared memory take the per-instance-factor route)
+        # shared KKT factor: the solve of eight instances is a dense contraction -> FP64 tensor cores
         from .dmma import build_dmma_schedule, pack_dmma_blob
-        DS = build_dmma_schedule(F, max_group_rows=max_group_rows)
-        dmma_blob = pack_dmma_blob(DS)
-        dmma_rounds = max(len(t.round_len) for t in DS.tiles)
+        try:
+            DS = build_dmma_schedule(F, max_group_rows=max_group_rows)
+            dmma_blob = pack_dmma_blob(DS)
+            dmma_rounds = max(len(t.round_len) for t in DS.tiles)
+        except AssertionError:      # 16-bit operand offsets: no tensor-core schedule for a family of this size
+            dmma_blob, dmma_rounds = b'', 0
     RT = build_refactor_tables(F, K, n)
     tail_blob = pack_tail_blob(RT)
     # backward pass (gradient=True): regularised KKT of the UNSCALED problem on the same symbolic pattern

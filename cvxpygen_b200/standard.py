@@ -19,6 +19,9 @@ STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
     'random_qp_20_5_15': (lambda: families.random_qp(20, 5, 15), ['q', 'b', 'h']),  # unstructured sparsity, q/l/u all batched
     'portfolio_qp_50_10': (lambda: families.portfolio_qp(50, 10), ['a', 'w_prev']),   # the reference's portfolio test problem (QP form, OSQP)
     'box_qp_6_8': (lambda: families.box_qp(6, 8), ['q', 'l', 'u']),          # corner cases: type changes, infeasibility
+    # f3: a family whose tile schedule (530 KB) is larger than one SM's shared memory -- 1 500-row KKT, nnz(L) = 6 777; solved by the
+    # per-instance-factor kernel alone with its tables read through L2 (codegen.py: CPG_FAM_BIG)
+    'random_qp_700_100_700': (lambda: families.random_qp(700, 100, 700, density=0.002, seed=1), ['q', 'b', 'h']),
     # f2: the MPC family with its matrices as per-instance parameters (dynamics A, B and diagonal stage costs)
     'mpc_ltv_6_3_10': (lambda: families.mpc_ltv(6, 3, 10), ['A', 'B', 'qdiag', 'rdiag', 'x_init']),
     'mpc_ltv_12_4_10': (lambda: families.mpc_ltv(12, 4, 10), ['A', 'B', 'qdiag', 'rdiag', 'x_init']),
@@ -42,7 +45,8 @@ TWO_STAGE_NAMES: List[str] = ['mpc_6_3_10_two_stage']
 SOCP_NAMES: List[str] = [n for n in STANDARD if '_socp_' in n or n.startswith('network_lp') or n.endswith('_two_stage')]     # conic families (IPM-CUDA)
 MATPAR_NAMES: List[str] = ['mpc_ltv_6_3_10', 'mpc_ltv_12_4_10', 'mpc_ref_6_3_10', 'actuator_1_3', 'osqp_update_matrices_5_8',
                            'nonneg_LS_3_2_A']
-QP_NAMES: List[str] = [n for n in STANDARD if n not in SOCP_NAMES and n not in MATPAR_NAMES]
+BIG_NAMES: List[str] = ['random_qp_700_100_700']
+QP_NAMES: List[str] = [n for n in STANDARD if n not in SOCP_NAMES and n not in MATPAR_NAMES and n not in BIG_NAMES]
 
 
 def code_dir(name: str) -> str:

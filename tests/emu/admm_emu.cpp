@@ -36,6 +36,7 @@ struct Fam {
   static constexpr int CBLOB_BYTES_PAD = CPG_FAM_CBLOB_BYTES_PAD;
   static constexpr int W_STRIDE = CPG_FAM_W_STRIDE, S_STRIDE = CPG_FAM_S_STRIDE;
   static constexpr int TAIL_WARPS = CPG_FAM_TAIL_WARPS;
+  static constexpr bool TAIL_STAGE = CPG_FAM_TAIL_STAGE != 0;
   static constexpr int GBLOB_BYTES_PAD = CPG_FAM_GBLOB_BYTES_PAD;
   static constexpr int GRAD_WARPS = CPG_FAM_GRAD_WARPS, GRAD_STRIDE = CPG_FAM_GRAD_STRIDE;
   static constexpr int DM_GROUPS = CPG_FAM_DM_GROUPS, DBLOB_BYTES_PAD = CPG_FAM_DBLOB_BYTES_PAD;
@@ -111,7 +112,10 @@ int emu_main_solve(int B, const double* params, double* prim, double* dual, doub
   io.status = status; io.pri_res = pri; io.dua_res = dua; io.B = B; io.work_counter = &counter;
   io.tail_count = &count; io.tail_ids = ids.data(); io.tail_state = state.data(); io.tail_capacity = B;
   const cpgb200::Settings st = default_settings(adaptive_rho_interval, eps);
-#if CPG_FAM_DMMA       // the family's main kernel is the tensor-core variant (groups of four warps, DMMA emulated lane by lane)
+#if CPG_FAM_BIG        // schedule larger than shared memory: every instance is queued for the per-instance-factor kernel
+  simt::launch((B + 255) / 256, 256, [&] { cpgb200::queue_all_kernel(io, WORDS, Fam::N + 2 * Fam::M,
+                                                                        reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words))->rho); });
+#elif CPG_FAM_DMMA     // the family's main kernel is the tensor-core variant (groups of four warps, DMMA emulated lane by lane)
   simt::launch(grid, Fam::DM_GROUPS * 128, [&] {
     cpgb200::admm_dmma_kernel<Fam>(reinterpret_cast<const uint8_t*>(CPG_B200_FN(cpg_cblob_words)),
                                    reinterpret_cast<const uint8_t*>(CPG_B200_FN(cpg_dblob_words)), io, st);

@@ -25,6 +25,9 @@ def family_and_batch(name, B, seed=1):
             params[pn] = rng.uniform(-1, 1, (B, p.size))
         else:
             params[pn] = np.asarray(p.default)[None, :] + 0.3 * rng.standard_normal((B, p.size))
+    if name in standard.BIG_NAMES:        # keep the 1 500-row family feasible: equalities barely moved, inequalities only loosened
+        params['b'] = np.asarray(fam.param('b').default)[None, :] + 0.002 * rng.standard_normal((B, fam.param('b').size))
+        params['h'] = np.asarray(fam.param('h').default)[None, :] + 0.3 * np.abs(rng.standard_normal((B, fam.param('h').size)))
     if name.startswith('box_qp'):
         params['q'][:, -1] = 0.0          # keep the curvature-less variable free of cost: bounded instances
     return fam, params, canon_batches(fam, params, B)

@@ -21,9 +21,9 @@ from oracle.grad_numpy import qp_backward, qp_backward_mat, param_gradient, para
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def build_emu(fam, batch, out_dir, flags=(), dmma=None):
+def build_emu(fam, batch, out_dir, flags=(), dmma=None, force_big=False):
     st = setup_qp_family(fam, batch)
-    codegen.write_code(st, out_dir, dmma=dmma)
+    codegen.write_code(st, out_dir, dmma=dmma, force_big=force_big)
     inc, sol, src = (os.path.join(out_dir, 'c', d) for d in ('include', 'solver_code', 'src'))
     so = os.path.join(out_dir, 'libadmm_emu.so')
     cmd = ['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-DCPG_SIMT_HOST_EMU', '-w', '-ffp-contract=off', *flags,
@@ -143,6 +143,23 @@ def test_standard_families_on_the_emulator(name, B, dmma, tmp_path):
         assert out['rc'] > 0                                             # some instances went through the tail kernel
         assert set(np.unique(ora['status'])) >= {1, -3, -4} and np.array_equal(out['status'], ora['status'])
         assert (out['obj'][kind == 3] == 1e30).all() and (out['obj'][kind == 4] == -1e30).all()
+
+
+def test_big_family_path_on_the_emulator(tmp_path):
+    """Families whose tile schedule exceeds shared memory (forced here on a small one): no main kernel, every instance queued at
+    iteration 0 for the per-instance-factor kernel, which reads the constants from global memory instead of staging them."""
+    fam = families.mpc(4, 2, 6)
+    st, lib, dims = build_emu(fam, ['x_init'], str(tmp_path), force_big=True)
+    hdr = open(os.path.join(str(tmp_path), 'c', 'include', 'cpg_family.h')).read()
+    assert '#define CPG_FAM_BIG 1' in hdr and '#define CPG_FAM_TAIL_STAGE 0' in hdr
+    B = 11
+    xi = np.random.default_rng(3).uniform(-1.5, 1.5, (B, 4))
+    q, l, u = canon_batches(fam, {'x_init': xi}, B)
+    out = run_solve(lib, 'emu_main_solve', dims, xi, grid=2)
+    ora = oracle_solve(fam, q, l, u)
+    assert out['rc'] == B and (out['status'] != -100).all()            # all of them went through the queue
+    assert np.array_equal(out['iter'], ora['iter']) and np.array_equal(out['status'], ora['status'])
+    assert rel_err(out['x'], ora['x']).max() < 1e-9 and rel_err(out['y'], ora['y']).max() < 1e-9
 
 
 def test_tail_kernel_on_the_emulator(tmp_path):

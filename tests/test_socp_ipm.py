@@ -426,8 +426,11 @@ def test_wrong_solver_for_family_is_rejected(tmp_path):
     from cvxpygen_b200 import cpg
     with pytest.raises(ValueError):
         cpg.generate_code(families.portfolio_socp(), code_dir=str(tmp_path / 'x'), solver='ADMM-CUDA', wrapper=False)
-    with pytest.raises(ValueError):
-        cpg.generate_code(families.mpc(2, 1, 2), code_dir=str(tmp_path / 'y'), solver='IPM-CUDA', wrapper=False)
+    # the other way round is allowed, as in the reference (QPs run under ECOS too): the family is restated in conic form
+    cpg.generate_code(families.mpc(2, 1, 2), code_dir=str(tmp_path / 'y'), solver='IPM-CUDA', wrapper=False)
+    assert os.path.exists(str(tmp_path / 'y' / 'c' / 'include' / 'cpg_ipm_family.h'))
+    with pytest.raises(ValueError):       # a conic family has no QP backward pass (extended DPP, cvxpygen/canonicalizer.py:338-345)
+        cpg.generate_code(families.portfolio_socp(), code_dir=str(tmp_path / 'z'), solver='IPM-CUDA', gradient=True, wrapper=False)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
