@@ -124,6 +124,7 @@ def _family_header(setup: QPSetup, prefix: str, warps: Optional[int], ni: Option
         f'#define CPG_FAM_NI {ni}', f'#define CPG_FAM_MULTI_STRIDE {pair_stride}', f'#define CPG_FAM_S_STRIDE {s_stride}', f'#define CPG_FAM_TAIL_WARPS {tail_warps}',
         f'#define CPG_FAM_MATPAR {matpar}', f'#define CPG_FAM_MAT_WARPS {mat_warps}', f'#define CPG_FAM_MAT_STRIDE {mat_stride}',
         f'#define CPG_FAM_MAT_A_STRIDE {mat_a}', f'#define CPG_FAM_MAT_P_STRIDE {mat_p}', f'#define CPG_FAM_MAT_G_STRIDE {mat_g_stride}',
+        f"#define CPG_FAM_TAIL_WORD_SHIFT {int(th['pad0'])}",
         '#define CPG_FAM_TAIL_TILES {' + ', '.join(str(int(v)) for v in tail_tiles) + '}',
         f'#define CPG_FAM_BIG {int(big)}', f'#define CPG_FAM_TAIL_STAGE {tail_stage}', f'#define CPG_FAM_GRAD {grad_ok}',
         f'#define CPG_FAM_DMMA {use_dmma}', f'#define CPG_FAM_DM_GROUPS {max(dm_groups, 1)}', f'#define CPG_FAM_DBLOB_BYTES_PAD {dblob_pad}',

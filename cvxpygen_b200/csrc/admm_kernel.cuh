@@ -186,7 +186,19 @@ __device__ __forceinline__ void tail_factor(const TailView& tv, double* S, int l
   }
 }
 
-// entries of a tile: one 32-bit word per (k, lane) = slot | position << 16, lane-interleaved (offline/blob.py:pack_tail_blob)
+// entries of a tile: one 32-bit word per (k, lane) = slot | position << 16, lane-interleaved (offline/blob.py:pack_tail_blob);
+// families with fewer than 8192 slots carry both fields as BYTE offsets (CPG_FAM_TAIL_WORD_SHIFT = 3): no shift per operand
+#ifndef CPG_FAM_TAIL_WORD_SHIFT
+#define CPG_FAM_TAIL_WORD_SHIFT 0
+#endif
+__device__ __forceinline__ double tail_entry_fma(const double* S, const double* w, unsigned e, double a) {
+#if CPG_FAM_TAIL_WORD_SHIFT == 3
+  return fma(*reinterpret_cast<const double*>(reinterpret_cast<const char*>(S) + (e & 0xffffu)),
+             *reinterpret_cast<const double*>(reinterpret_cast<const char*>(w) + (e >> 16)), a);
+#else
+  return fma(S[e & 0xffffu], w[e >> 16], a);
+#endif
+}
 __device__ __forceinline__ double slot_tile_acc(const int* h, const int* __restrict__ I32, const double* S,
                                                 const double* w, int lane) {
   const unsigned* wd = reinterpret_cast<const unsigned*>(I32) + h[0] + lane;
@@ -196,12 +208,12 @@ __device__ __forceinline__ double slot_tile_acc(const int* h, const int* __restr
   for (; k + 3 < K; k += 4) {
     const unsigned e0 = __ldg(wd + k * LANES), e1 = __ldg(wd + (k + 1) * LANES);
     const unsigned e2 = __ldg(wd + (k + 2) * LANES), e3 = __ldg(wd + (k + 3) * LANES);
-    a0 = fma(S[e0 & 0xffffu], w[e0 >> 16], a0);
-    a1 = fma(S[e1 & 0xffffu], w[e1 >> 16], a1);
-    a2 = fma(S[e2 & 0xffffu], w[e2 >> 16], a2);
-    a3 = fma(S[e3 & 0xffffu], w[e3 >> 16], a3);
+    a0 = tail_entry_fma(S, w, e0, a0);
+    a1 = tail_entry_fma(S, w, e1, a1);
+    a2 = tail_entry_fma(S, w, e2, a2);
+    a3 = tail_entry_fma(S, w, e3, a3);
   }
-  for (; k < K; ++k) { const unsigned e0 = __ldg(wd + k * LANES); a0 = fma(S[e0 & 0xffffu], w[e0 >> 16], a0); }
+  for (; k < K; ++k) { const unsigned e0 = __ldg(wd + k * LANES); a0 = tail_entry_fma(S, w, e0, a0); }
   double acc = (a0 + a1) + (a2 + a3);
   for (int o = 16; o >= h[3]; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
   return acc;

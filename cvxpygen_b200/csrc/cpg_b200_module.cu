@@ -236,6 +236,20 @@ int CPG_B200_FN(cpg_b200_load_constants_all)(const void* blob, int nbytes, const
       tnbytes != (int)CPG_B200_FN(cpg_tail_blob_nbytes) || gnbytes != (int)CPG_B200_FN(cpg_gblob_nbytes) ||
       snbytes != (int)CPG_B200_FN(cpg_gS0_nbytes))
     return CPG_B200_ERR_BAD_ARG;          // a different layout needs a regenerated library
+  {
+    // the tile headers of the per-instance triangular solves are compiled into this library (constant memory) and the entry words'
+    // format is a compile-time choice: the new tables must carry the same ones
+    const CpgTailHeader* th = reinterpret_cast<const CpgTailHeader*>(tail_blob);
+    const CpgTailHeader* th0 = reinterpret_cast<const CpgTailHeader*>(CPG_B200_FN(cpg_tail_blob_words));
+    const size_t nt = (size_t)th0->n_fwd_tiles + th0->n_bwd_tiles;
+    if (th->pad0 != th0->pad0 || th->n_fwd_tiles != th0->n_fwd_tiles || th->n_bwd_tiles != th0->n_bwd_tiles || th->off_i32 != th0->off_i32 ||
+        th->i_tiles != th0->i_tiles ||
+        memcmp(reinterpret_cast<const char*>(tail_blob) + th->off_i32 + 4 * (size_t)th->i_tiles,
+               reinterpret_cast<const char*>(CPG_B200_FN(cpg_tail_blob_words)) + th0->off_i32 + 4 * (size_t)th0->i_tiles, nt * 32) != 0) {
+      snprintf(g.err, sizeof(g.err), "the new tables have another solve structure than the one compiled into this library: regenerate it");
+      return CPG_B200_ERR_BAD_ARG;
+    }
+  }
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(g.d_blob, blob, nbytes, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(g.d_cblob, cblob, cnbytes, cudaMemcpyHostToDevice));
@@ -315,7 +329,9 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
 #endif
   if (!g.d_tail_blob) CK(cudaMalloc(&g.d_tail_blob, CPG_B200_FN(cpg_tail_blob_nbytes)));
   CK(cudaMemcpy(g.d_tail_blob, CPG_B200_FN(cpg_tail_blob_words), CPG_B200_FN(cpg_tail_blob_nbytes), cudaMemcpyHostToDevice));
+#if !CPG_FAM_MATPAR
   CK(cudaFuncSetAttribute(cpgb200::admm_tail_kernel<Fam>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM_BYTES));
+#endif
 #if CPG_FAM_MATPAR
   if (!g.d_mblob) CK(cudaMalloc(&g.d_mblob, CPG_B200_FN(cpg_mblob_nbytes)));
   CK(cudaMemcpy(g.d_mblob, CPG_B200_FN(cpg_mblob_words), CPG_B200_FN(cpg_mblob_nbytes), cudaMemcpyHostToDevice));
@@ -324,7 +340,7 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
 #endif
   if (!g.d_counter) CK(cudaMalloc(&g.d_counter, sizeof(unsigned int)));
   if (!g.d_tail_count) CK(cudaMalloc(&g.d_tail_count, sizeof(int)));
-#if CPG_FAM_BIG
+#if CPG_FAM_BIG || CPG_FAM_MATPAR
   // nothing to prepare: the main kernel is not part of this library
 #elif CPG_FAM_DMMA
   if (!g.d_dblob) CK(cudaMalloc(&g.d_dblob, Fam::DBLOB_BYTES_PAD));
@@ -400,7 +416,7 @@ int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const doubl
     g.ev_solve = true;
     return CPG_B200_OK;
   }
-#endif
+#else        // (the shared-matrix kernels below are not compiled into a matrix-parameter library)
   // one persistent CTA per SM; a batch smaller than one wave of slots is still spread over all SMs (every warp pulls its
   // instances from the global counter), so that few warps share an SM's shared-memory bandwidth: lower latency
   int grid = g.n_sm;
@@ -437,6 +453,7 @@ int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const doubl
   CK(cudaEventRecord(g.ev[2], stream));
   g.ev_solve = true;
   return CPG_B200_OK;
+#endif
 }
 
 int CPG_B200_FN(cpg_solve_batch_host)(int B, const double* params, const double* x0, const double* y0,

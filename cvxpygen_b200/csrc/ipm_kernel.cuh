@@ -28,6 +28,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #ifdef CPG_IPM_HOST_EMU
 #include <algorithm>
@@ -96,7 +97,7 @@ constexpr int O_XYZ = 0, O_CBH = O_XYZ + NK, O_SV = O_CBH + NK, O_LAM = O_SV + M
               O_RHS = O_S + NS + 1, O_PX = O_RHS + NK, O_E = O_PX + NK, O_SOL1 = O_E + NK, O_RZ = O_SOL1 + NK,
               O_DSW = O_RZ + MT, O_RED = O_DSW + MT, O_CONE = O_RED + 2 * NWARP * 16,
               O_CE = O_CONE + 4 * (NSOC > 0 ? NSOC : 1), O_TW = O_CE + (NCR > 0 ? NCR : 1),
-              O_AG = O_TW + 2 * 32, O_F64_END = O_AG + NNZM + 1;
+              O_AG = (O_TW + 2 * 32 + 1) & ~1, O_F64_END = O_AG + NNZM + 1;      // O_AG even: 16-byte aligned target of the bulk copy
 constexpr int U32_COUNT = (IPM_SB_U16_OFF - IPM_SB_U32_OFF) / 4;
 constexpr int U16_COUNT = (IPM_SB_BYTES - IPM_SB_U16_OFF) / 2;
 constexpr size_t SMEM_BYTES = size_t(O_F64_END) * 8 + size_t(U32_COUNT) * 4 + size_t(U16_COUNT) * 2 + 16;
@@ -1129,19 +1130,42 @@ ipm_kernel(const unsigned char* __restrict__ smem_blob, const unsigned char* __r
   Solver sv;
     sv.gm = make_gm(gmem_blob);
   sv.stg = stg; sv.rb = 0;
-  // stage the constant tables: [f64 ag_val, 0 | u32 plan entries | u16 descriptors and index lists]
+  // stage the constant tables: [f64 ag_val, 0 | u32 plan entries | u16 descriptors and index lists] -- the blob is laid out
+  // exactly like its shared-memory image (O_AG onwards), so it arrives as TMA bulk copies (cp.async.bulk, 32 KB chunks) that
+  // complete on one mbarrier; the null slot of S is set meanwhile
   {
-    const double* src = reinterpret_cast<const double*>(smem_blob);
-    for (int i = threadIdx.x; i < NNZM + 1; i += T) sv.sm.ag()[i] = src[i];
-    const uint32_t* ws = reinterpret_cast<const uint32_t*>(smem_blob + IPM_SB_U32_OFF);
-    uint32_t* wd = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(smem_raw) + O_F64_END);
-    for (int i = threadIdx.x; i < U32_COUNT; i += T) wd[i] = ws[i];
-    const uint16_t* hs = reinterpret_cast<const uint16_t*>(smem_blob + IPM_SB_U16_OFF);
-    uint16_t* hd = reinterpret_cast<uint16_t*>(wd + U32_COUNT);
-    for (int i = threadIdx.x; i < U16_COUNT; i += T) hd[i] = hs[i];
-    if (threadIdx.x == 0) sv.sm.S()[NS] = 0.0;          // the slot every null entry of the plans points at
+    static_assert(IPM_SB_BYTES % 16 == 0 && (O_AG * 8) % 16 == 0, "bulk copies move 16-byte units");
+    static_assert(IPM_SB_U32_OFF == (NNZM + 1) * 8, "the f64 part of the blob is ag_val plus its null entry");
+    unsigned char* dst = smem_raw + size_t(O_AG) * 8;
+#ifdef CPG_SIMT_HOST_EMU
+    if (threadIdx.x == 0) memcpy(dst, smem_blob, IPM_SB_BYTES);
+    if (threadIdx.x == 0) sv.sm.S()[NS] = 0.0;
+    __syncthreads();
+#else
+    __shared__ __align__(8) unsigned long long stage_bar;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)IPM_SB_BYTES) : "memory");
+      constexpr unsigned CHUNK = 32768;
+      for (unsigned off = 0; off < (unsigned)IPM_SB_BYTES; off += CHUNK) {
+        const unsigned n = (unsigned)IPM_SB_BYTES - off < CHUNK ? (unsigned)IPM_SB_BYTES - off : CHUNK;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((unsigned)__cvta_generic_to_shared(dst + off)), "l"(smem_blob + off), "r"(n), "r"(bar) : "memory");
+      }
+      sv.sm.S()[NS] = 0.0;          // the slot every null entry of the plans points at
+    }
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(bar), "r"(0) : "memory");
+    __syncthreads();
+#endif
   }
-  __syncthreads();
   double* best = io.best + size_t(blockIdx.x) * (NK + MT);
   for (;;) {
     if (threadIdx.x == 0) next_inst = atomicAdd(io.counter, 1);

@@ -268,9 +268,13 @@ def pack_tail_blob(T) -> bytes:
     # tile header (8 ints): [i32 offset of the packed entries (slot | position << 16, lane-interleaved), 0, K, r_pad, rows,
     #                        u16 offset of the row list, inside: u16 offset of the slot table | first slot of the packed triangle,
     #                        0 no couplings inside / 1 slot table / 2 packed triangle]
+    # pad0 = 3: both fields of an entry word are BYTE offsets (index * 8; needs n_slots, nk < 8192), the kernel then spends no
+    # shift on them; 0: plain indices (larger families)
+    shift = 3 if (T.n_slots < 8192 and T.nk < 8192) else 0
+    hv['pad0'] = shift
     tab = []
     for t in list(T.fwd_tiles) + list(T.bwd_tiles):
-        words = (t.slots.astype(np.uint32) | (t.cols.astype(np.uint32) << 16)).astype(np.uint32).view(np.int32)
+        words = ((t.slots.astype(np.uint32) << shift) | ((t.cols.astype(np.uint32) << shift) << 16)).astype(np.uint32).view(np.int32)
         hw = ar.add_i32(words)
         hr = ar.add_u16(np.concatenate([t.rows, np.zeros(LANES - len(t.rows), dtype=np.uint16)]))
         if t.inside is None:
