@@ -199,12 +199,32 @@ __device__ __forceinline__ double tail_entry_fma(const double* S, const double* 
   return fma(S[e & 0xffffu], w[e >> 16], a);
 #endif
 }
+// The first TAIL_PRE words per lane of a tile are fetched ONE TILE AHEAD (tail_prefetch, issued before the previous tile's
+// in-register sweep): the words are static addresses behind an L2 latency -- shared memory is carved out for the factors, L1
+// keeps ~28 KB that the words of one solve (29 KB for mpc_ltv_12_4_10) flush -- and were the kernel's largest stall
+// (long_scoreboard 2.9 cycles per issue, profiles/r2_matpar_v5_ncu_summary.md).  Slots beyond the tile's K hold `zero_word`
+// (S[zero slot] * w[0] = 0).  Entry k accumulates into chain k mod 4.
+constexpr int TAIL_PRE = 8;
+__device__ __forceinline__ void tail_prefetch(unsigned (&pre)[TAIL_PRE], const int* h, const int* __restrict__ I32, int lane,
+                                              unsigned zero_word) {
+  const unsigned* wd = reinterpret_cast<const unsigned*>(I32) + h[0] + lane;
+  const int K = h[2];
+#pragma unroll
+  for (int u = 0; u < TAIL_PRE; ++u) pre[u] = (u < K) ? __ldg(wd + u * LANES) : zero_word;
+}
 __device__ __forceinline__ double slot_tile_acc(const int* h, const int* __restrict__ I32, const double* S,
-                                                const double* w, int lane) {
+                                                const double* w, int lane, const unsigned (&pre)[TAIL_PRE]) {
   const unsigned* wd = reinterpret_cast<const unsigned*>(I32) + h[0] + lane;
   const int K = h[2];
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int k = 0;
+#pragma unroll
+  for (int u = 0; u < TAIL_PRE; u += 4) {
+    a0 = tail_entry_fma(S, w, pre[u], a0);
+    a1 = tail_entry_fma(S, w, pre[u + 1], a1);
+    a2 = tail_entry_fma(S, w, pre[u + 2], a2);
+    a3 = tail_entry_fma(S, w, pre[u + 3], a3);
+  }
+  int k = TAIL_PRE;
   for (; k + 3 < K; k += 4) {
     const unsigned e0 = __ldg(wd + k * LANES), e1 = __ldg(wd + (k + 1) * LANES);
     const unsigned e2 = __ldg(wd + (k + 2) * LANES), e3 = __ldg(wd + (k + 3) * LANES);
@@ -213,7 +233,11 @@ __device__ __forceinline__ double slot_tile_acc(const int* h, const int* __restr
     a2 = tail_entry_fma(S, w, e2, a2);
     a3 = tail_entry_fma(S, w, e3, a3);
   }
-  for (; k < K; ++k) { const unsigned e0 = __ldg(wd + k * LANES); a0 = tail_entry_fma(S, w, e0, a0); }
+  if (k < K) {
+    a0 = tail_entry_fma(S, w, __ldg(wd + k * LANES), a0);
+    if (k + 1 < K) a1 = tail_entry_fma(S, w, __ldg(wd + (k + 1) * LANES), a1);
+    if (k + 2 < K) a2 = tail_entry_fma(S, w, __ldg(wd + (k + 2) * LANES), a2);
+  }
   double acc = (a0 + a1) + (a2 + a3);
   for (int o = 16; o >= h[3]; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
   return acc;
@@ -259,6 +283,22 @@ __device__ __forceinline__ double group_sweep(double val, const uint16_t* __rest
 // (two SHFL halves, one LDS, one DFMA).  Now: the coefficient loads are unconditional (a lane that does not depend on row j reads
 // a valid neighbouring slot and discards it -- the update is a predicated DFMA), and a full group (g = 32, the chain groups of the
 // MPC families) runs fully unrolled with every row index, shuffle source and triangle offset an immediate.
+// val -= cf * vj on the lanes where `on` holds: one ISETP (folded by the compiler when `on` compares against an immediate) and a
+// PREDICATED DFMA.  Written as `if (on) val = fma(..)` the compiler computes the product everywhere and selects with two FSEL,
+// and packs the 32 predicates of an unrolled sweep into a register with a LOP3 each (profiles/r2_matpar_v5: 10 instructions
+// per row instead of 5).
+template <bool GT>      // GT: lanes above row j take the update (ascending sweep); else the lanes below it
+__device__ __forceinline__ void fnma_if(double& val, const double cf, const double vj, const int lane, const int j) {
+#ifdef CPG_SIMT_HOST_EMU
+  if (GT ? lane > j : lane < j) val = fma(-cf, vj, val);
+#else
+  if (GT) asm("{\n .reg .pred p;\n .reg .f64 n;\n setp.gt.s32 p, %3, %4;\n neg.f64 n, %1;\n @p fma.rn.f64 %0, n, %2, %0;\n}"
+              : "+d"(val) : "d"(cf), "d"(vj), "r"(lane), "r"(j));
+  else asm("{\n .reg .pred p;\n .reg .f64 n;\n setp.lt.s32 p, %3, %4;\n neg.f64 n, %1;\n @p fma.rn.f64 %0, n, %2, %0;\n}"
+           : "+d"(val) : "d"(cf), "d"(vj), "r"(lane), "r"(j));
+#endif
+}
+
 constexpr __host__ __device__ int tri32(int j) { return j * 31 - (j * (j - 1)) / 2 - (j + 1); }
 
 template <bool ASCENDING>
@@ -274,7 +314,7 @@ __device__ __forceinline__ double group_sweep_dense32(double val, const double* 
       for (int u = 0; u < 8; ++u) {
         const int j = blk * 8 + u;
         const double vj = __shfl_sync(FULL, val, j);
-        if (lane > j) val = fma(-cf[u], vj, val);
+        fnma_if<true>(val, cf[u], vj, lane, j);
       }
     }
   } else {
@@ -288,7 +328,7 @@ __device__ __forceinline__ double group_sweep_dense32(double val, const double* 
       for (int u = 0; u < 8; ++u) {
         const int j = 31 - blk * 8 - u;
         const double vj = __shfl_sync(FULL, val, j);
-        if (lane < j) val = fma(-cf[u], vj, val);
+        fnma_if<false>(val, cf[u], vj, lane, j);
       }
     }
   }
@@ -310,13 +350,13 @@ __device__ __forceinline__ double group_sweep_dense(double val, const double* __
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const double vj = __shfl_sync(FULL, val, j + u);
-        if (lane > j + u) val = fma(-cf[u], vj, val);
+        fnma_if<true>(val, cf[u], vj, lane, j + u);
       }
     }
     for (; j < g; ++j) {
       const double cf = *p; p += step; --step;
       const double vj = __shfl_sync(FULL, val, j);
-      if (lane > j) val = fma(-cf, vj, val);
+      fnma_if<true>(val, cf, vj, lane, j);
     }
   } else {
     const double* p = Sg + (tl * (g - 1) - (tl * (tl - 1)) / 2 - (tl + 1)) + (g - 1);     // tri(lane) + j at j = g - 1
@@ -329,13 +369,13 @@ __device__ __forceinline__ double group_sweep_dense(double val, const double* __
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const double vj = __shfl_sync(FULL, val, j - u);
-        if (lane < j - u) val = fma(-cf[u], vj, val);
+        fnma_if<false>(val, cf[u], vj, lane, j - u);
       }
     }
     for (; j >= 0; --j) {
       const double cf = *p; --p;
       const double vj = __shfl_sync(FULL, val, j);
-      if (lane < j) val = fma(-cf, vj, val);
+      fnma_if<false>(val, cf, vj, lane, j);
     }
   }
   return val;
@@ -356,6 +396,9 @@ __constant__ const int kTailTiles[] = CPG_FAM_TAIL_TILES;
 __device__ __forceinline__ void tail_solve(const TailView& tv, const double* S, double* w, int lane) {
   const int* T = CPG_TAIL_TILE_PTR(tv);
   const int nf = tv.H->n_fwd_tiles, nt = nf + tv.H->n_bwd_tiles, nk = tv.H->nk;
+  const unsigned zero_word = (unsigned)(tv.H->n_slots - 1) << CPG_FAM_TAIL_WORD_SHIFT;
+  unsigned pre[TAIL_PRE];
+  if (nt > 0) tail_prefetch(pre, T, tv.I32, lane, zero_word);
   for (int t = 0; t < nt; ++t) {
     if (t == nf) {
       for (int i = lane; i < nk; i += LANES) w[i] *= S[i];
@@ -363,7 +406,8 @@ __device__ __forceinline__ void tail_solve(const TailView& tv, const double* S, 
     }
     const int* h = T + 8 * t;
     const int row = __ldg(tv.U16 + h[5] + lane);        // issued before the entry words: its latency hides behind them
-    const double acc = slot_tile_acc(h, tv.I32, S, w, lane);
+    const double acc = slot_tile_acc(h, tv.I32, S, w, lane, pre);
+    if (t + 1 < nt) tail_prefetch(pre, h + 8, tv.I32, lane, zero_word);     // in flight during this tile's sweep
     const int nrows = h[4];
     double val = w[row] - acc;
     if (h[7] == 2) val = (t < nf) ? group_sweep_dense<true>(val, S + h[6], nrows, lane)
