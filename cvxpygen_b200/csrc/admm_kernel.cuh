@@ -63,6 +63,7 @@ struct BatchIO {
   double* tail_state;           // per handed-off instance: x(n) z(m) y(m) rho_new iter   (scaled iterates)
   int B;
   int tail_capacity;
+  double* ws;                   // warm start only: per instance z0 = A x0 (m) | y0 / rho (m), the start point of the main kernel
 };
 
 // ---------------------------------------------------------------- TMA bulk copy + mbarrier helpers

@@ -21,6 +21,7 @@
 // Reference functions restated: same list as admm_kernel.cuh (a1-a12); the per-instance arithmetic and its order are
 // those of the single-instance path, so iterates agree with it bit for bit.
 #pragma once
+#include <type_traits>
 #include "admm_kernel.cuh"
 
 namespace cpgb200 {
@@ -251,36 +252,54 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
   auto rho_of = [&](int k) __attribute__((always_inline)) -> double {
     return ((loosemask >> k) & 1u) ? RHO_MIN : (((eqmask >> k) & 1u) ? rho_eq : rho_in); };
 
-  // ---- per-slot state
-  double x[NI][NXL], z[NI][NZLs], y[NI][NZLs];
+  // ---- per-slot state: x and the PRE-PROJECTION vector t = alpha z~ + (1 - alpha) z_prev + y_prev / rho of the last update
+  // (auxil.c:197-213 computes exactly this value before projecting it).  z and y are functions of it,
+  //     z = clip(t, l, u),      y = rho (t - z)
+  // so one vector per instance stays in registers instead of two (profile of the (x, z, y) version: 87 M spilled loads per
+  // 100 000 instances).  The start point of an instance is not of that form (z0 = 0 or A x0 need not lie in [l, u]): until its
+  // first update a slot is flagged `first` and its (z0, y0 / rho) are 0 (cold start) or read from the instance's scratch rows
+  // io.ws (warm start).
+  double x[NI][NXL], t[NI][NZLs];
   int inst[NI], it[NI];
-  bool active[NI];
+  bool active[NI], first[NI];
   bool exhausted = false;
+  const bool warm = st.warm_start && io.x0 != nullptr && io.y0 != nullptr;
 #pragma unroll
   for (int s = 0; s < NI; ++s) {
-    inst[s] = -1; it[s] = 0; active[s] = false;
+    inst[s] = -1; it[s] = 0; active[s] = false; first[s] = true;
 #pragma unroll
     for (int k = 0; k < NXL; ++k) x[s][k] = 0.0;
 #pragma unroll
-    for (int k = 0; k < NZLs; ++k) { z[s][k] = 0.0; y[s][k] = 0.0; }
+    for (int k = 0; k < NZLs; ++k) t[s][k] = 0.0;
   }
+  // z and d = y / rho of slot s, row lane + 32 k, given the row's bounds
+  auto zd_of = [&](int s, int k, double lv, double uv, double& zv, double& dv) __attribute__((always_inline)) {
+    zv = fmin(fmax(t[s][k], lv), uv); dv = t[s][k] - zv;
+  };
+  auto zd_first = [&](int s, int k, double lv, double uv, double& zv, double& dv) __attribute__((always_inline)) {
+    if (first[s]) {
+      zv = 0.0; dv = 0.0;
+      const int j = lane + 32 * k;
+      if (warm && inst[s] >= 0 && j < M) { const double* wr = io.ws + (size_t)inst[s] * (2 * M); zv = wr[j]; dv = wr[M + j]; }
+    } else zd_of(s, k, lv, uv, zv, dv);
+  };
 
   // bring slot s+1 to position s (cyclically) -- registers and the per-warp batched-row table
   auto rotate_state = [&]() __attribute__((always_inline)) {
 #pragma unroll
-    for (int k = 0; k < NXL; ++k) { const double t = x[0][k];
+    for (int k = 0; k < NXL; ++k) { const double v = x[0][k];
 #pragma unroll
       for (int s = 0; s + 1 < NI; ++s) x[s][k] = x[s + 1][k];
-      x[NI - 1][k] = t; }
+      x[NI - 1][k] = v; }
 #pragma unroll
-    for (int k = 0; k < NZLs; ++k) { const double t = z[0][k], u = y[0][k];
+    for (int k = 0; k < NZLs; ++k) { const double v = t[0][k];
 #pragma unroll
-      for (int s = 0; s + 1 < NI; ++s) { z[s][k] = z[s + 1][k]; y[s][k] = y[s + 1][k]; }
-      z[NI - 1][k] = t; y[NI - 1][k] = u; }
-    { const int t = inst[0], u = it[0]; const bool a = active[0];
+      for (int s = 0; s + 1 < NI; ++s) t[s][k] = t[s + 1][k];
+      t[NI - 1][k] = v; }
+    { const int v = inst[0], u = it[0]; const bool a = active[0], f = first[0];
 #pragma unroll
-      for (int s = 0; s + 1 < NI; ++s) { inst[s] = inst[s + 1]; it[s] = it[s + 1]; active[s] = active[s + 1]; }
-      inst[NI - 1] = t; it[NI - 1] = u; active[NI - 1] = a; }
+      for (int s = 0; s + 1 < NI; ++s) { inst[s] = inst[s + 1]; it[s] = it[s + 1]; active[s] = active[s + 1]; first[s] = first[s + 1]; }
+      inst[NI - 1] = v; it[NI - 1] = u; active[NI - 1] = a; first[NI - 1] = f; }
     const int nb = H->nb_slots;
     for (int r = lane; r < nb; r += LANES) {
       double v[NI], w[NI];
@@ -324,13 +343,26 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
     return __any_sync(FULL, mismatch);
   };
 
+  // z and y of slot 0 (start values while the slot is `first`)
+  auto zy0 = [&](double (&zc)[NZLs], double (&yc)[NZLs]) __attribute__((always_inline)) {
+#pragma unroll
+    for (int k = 0; k < NZLs; ++k) {
+      zc[k] = 0.0; yc[k] = 0.0;
+      if (k < NZL && lane + 32 * k < M) {
+        double dv;
+        zd_first(0, k, tab0(AL, k), tab0(AU, k), zc[k], dv);
+        yc[k] = rho_of(k) * dv;
+      }
+    }
+  };
+
   // residuals + norms of slot 0's current iterate (update_info, auxil.c:564-629)
   double pri_res, dua_res, xPx, qx, nrm_z, nrm_Ax, nrm_q, nrm_Aty, nrm_Px, s_rp, s_rd, s_z, s_Ax, s_q, s_Aty, s_Px;
-  auto update_info0 = [&]() __attribute__((always_inline)) {
+  auto update_info0 = [&](const double (&zc)[NZLs], const double (&yc)[NZLs]) __attribute__((always_inline)) {
 #pragma unroll
     for (int k = 0; k < NXL; ++k) { const int i = lane + 32 * k; if (i < N) wN[NI * i] = x[0][k]; }
 #pragma unroll
-    for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) wN[NI * (N + j)] = y[0][k]; }
+    for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) wN[NI * (N + j)] = yc[k]; }
     __syncwarp();
     double m_rp = 0, m_z = 0, m_Ax = 0, ms_rp = 0, ms_z = 0, ms_Ax = 0;
 #pragma unroll
@@ -338,10 +370,10 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
       const int j = lane + 32 * k;
       if (j < M) {
         const double Ax = ell_dot_col0<NI>(I32 + H->i_ellA + 3 * k, F64, U16, wN, lane);
-        const double rp = Ax - z[0][k];
+        const double rp = Ax - zc[k];
         const double e = unscale ? Einv[j] : 1.0;
-        m_rp = fmax(m_rp, fabs(e * rp)); m_z = fmax(m_z, fabs(e * z[0][k])); m_Ax = fmax(m_Ax, fabs(e * Ax));
-        ms_rp = fmax(ms_rp, fabs(rp)); ms_z = fmax(ms_z, fabs(z[0][k])); ms_Ax = fmax(ms_Ax, fabs(Ax));
+        m_rp = fmax(m_rp, fabs(e * rp)); m_z = fmax(m_z, fabs(e * zc[k])); m_Ax = fmax(m_Ax, fabs(e * Ax));
+        ms_rp = fmax(ms_rp, fabs(rp)); ms_z = fmax(ms_z, fabs(zc[k])); ms_Ax = fmax(ms_Ax, fabs(Ax));
       }
     }
     double m_rd = 0, m_q = 0, m_Aty = 0, m_Px = 0, ms_rd = 0, ms_q = 0, ms_Aty = 0, ms_Px = 0, a_xPx = 0, a_qx = 0;
@@ -475,7 +507,7 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
   };
 
   // hand slot 0 to the tail kernel (own KKT factor needed)
-  auto hand_off0 = [&](double rho_new) __attribute__((always_inline)) {
+  auto hand_off0 = [&](double rho_new, const double (&zc)[NZLs], const double (&yc)[NZLs]) __attribute__((always_inline)) {
     const int b = inst[0];
     int slot = -1;
     if (lane == 0) slot = atomicAdd(io.tail_count, 1);
@@ -486,13 +518,13 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
 #pragma unroll
       for (int k = 0; k < NXL; ++k) { const int i = lane + 32 * k; if (i < N) ts[i] = x[0][k]; }
 #pragma unroll
-      for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) { ts[N + j] = z[0][k]; ts[N + M + j] = y[0][k]; } }
+      for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) { ts[N + j] = zc[k]; ts[N + M + j] = yc[k]; } }
       if (lane == 0) { ts[N + 2 * M] = rho_new; ts[N + 2 * M + 1] = (double)it[0]; io.tail_ids[slot] = b; }
     }
   };
 
   // store_solution / unscale / retrieval for slot 0 (a11, a12)
-  auto finish0 = [&](int status) __attribute__((always_inline)) {
+  auto finish0 = [&](int status, const double (&yc)[NZLs]) __attribute__((always_inline)) {
     const int b = inst[0];
     const bool has_sol = !(status == ST_PINF || status == ST_PINF_INACC || status == ST_DINF ||
                            status == ST_DINF_INACC || status == ST_NONCVX);
@@ -510,7 +542,7 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
     for (int k = 0; k < NZL; ++k) {
       const int j = lane + 32 * k;
       if (j < M) {
-        const double yv = has_sol ? (Ev[j] * y[0][k]) * cinv : qnan;
+        const double yv = has_sol ? (Ev[j] * yc[k]) * cinv : qnan;
         wN[NI * (N + j)] = yv;
         if (io.sol_y) io.sol_y[(size_t)b * M + j] = yv;
       }
@@ -538,44 +570,50 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
   };
 
   // fetch instances into slot 0 until one is accepted (or the queue is empty)
+  bool need_rhs = true;            // the work vector does not hold the slots' right-hand sides (after a refill / a check iteration)
   auto refill0 = [&]() __attribute__((always_inline)) {
     while (!active[0] && !exhausted) {
       unsigned b = 0;
       if (lane == 0) b = atomicAdd(io.work_counter, 1u);
       b = __shfl_sync(FULL, b, 0);
       if (b >= (unsigned)io.B) { exhausted = true; break; }
-      inst[0] = (int)b; it[0] = 0;
+      inst[0] = (int)b; it[0] = 0; first[0] = true; need_rhs = true;
       const bool mismatch = load_instance0((int)b);
       // cold start (auxil.c:155-159) or warm start (osqp.c:929-953)
-      if (st.warm_start && io.x0 != nullptr && io.y0 != nullptr) {
+      if (warm) {
 #pragma unroll
         for (int k = 0; k < NXL; ++k) {
           const int i = lane + 32 * k;
           if (i < N) { x[0][k] = Dinv[i] * io.x0[(size_t)b * N + i]; wN[NI * i] = x[0][k]; }
         }
-#pragma unroll
-        for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) y[0][k] = (Einv[j] * io.y0[(size_t)b * M + j]) * c; }
         __syncwarp();
+        double* wr = io.ws + (size_t)b * (2 * M);        // start values of this instance: z0 = A x0, y0 / rho
 #pragma unroll
-        for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) z[0][k] = ell_dot_col0<NI>(I32 + H->i_ellA + 3 * k, F64, U16, wN, lane); }
+        for (int k = 0; k < NZL; ++k) {
+          const int j = lane + 32 * k;
+          if (j < M) {
+            wr[j] = ell_dot_col0<NI>(I32 + H->i_ellA + 3 * k, F64, U16, wN, lane);
+            wr[M + j] = rinv_of(k) * ((Einv[j] * io.y0[(size_t)b * M + j]) * c);
+          }
+        }
         __syncwarp();
       } else {
 #pragma unroll
         for (int k = 0; k < NXL; ++k) x[0][k] = 0.0;
-#pragma unroll
-        for (int k = 0; k < NZLs; ++k) { z[0][k] = 0.0; y[0][k] = 0.0; }
       }
-      if (mismatch) { hand_off0(rho_in); continue; }     // a constraint changed type: needs its own factor
-      if (st.max_iter <= 0) {                             // degenerate setting: report the start point
-        double dx0[NXL], dy0[NZLs];
+      if (mismatch || st.max_iter <= 0) {
+        double zc[NZLs], yc[NZLs];
+        zy0(zc, yc);
+        if (mismatch) { hand_off0(rho_in, zc, yc); continue; }     // a constraint changed type: needs its own factor
+        double dx0[NXL], dy0[NZLs];                         // degenerate setting: report the start point
 #pragma unroll
         for (int k = 0; k < NXL; ++k) dx0[k] = 0.0;
 #pragma unroll
         for (int k = 0; k < NZLs; ++k) dy0[k] = 0.0;
-        update_info0();
+        update_info0(zc, yc);
         int status = check_termination0(dx0, dy0, false);
         if (status == ST_UNSOLVED) { status = check_termination0(dx0, dy0, true); if (status == ST_UNSOLVED) status = ST_MAXITER; }
-        finish0(status);
+        finish0(status, yc);
         continue;
       }
       active[0] = true;
@@ -589,6 +627,80 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
     if constexpr (DMMA) return dc->w8 + w8_off(p, 2 * dc->wg);
     else return wN + NI * p;
   };
+  // right-hand side of the next solve from the slots' state (osqp.c:354-358): sigma x - q | z - y / rho
+  auto write_rhs = [&]() __attribute__((always_inline)) {
+#pragma unroll
+    for (int k = 0; k < NXL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < N) {
+        double qv[NI], r[NI];
+        tabN(AQ, k, qv);
+#pragma unroll
+        for (int s = 0; s < NI; ++s) r[s] = sigma * x[s][k] - qv[s];
+        MO::st(wpos(PX[32 * k]), r);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NZL; ++k) {
+      const int j = lane + 32 * k;
+      if (j < M) {
+        double lv[NI], uv[NI], r[NI];
+        tabN(AL, k, lv); tabN(AU, k, uv);
+#pragma unroll
+        for (int s = 0; s < NI; ++s) { double zv, dv; zd_first(s, k, lv[s], uv[s], zv, dv); r[s] = zv - dv; }
+        MO::st(wpos(PZ[32 * k]), r);
+      }
+    }
+  };
+  // update_x, update_z (+project), update_y (auxil.c:185-225) on the state (x, t), FUSED with the right-hand side of the next
+  // solve when RHS (the solution of this one has just been read from the same positions).  FIRST: some slot still holds its
+  // start point.
+  auto update_all = [&](auto first_tag, auto rhs_tag) __attribute__((always_inline)) {
+    constexpr bool FIRST = decltype(first_tag)::value, RHS = decltype(rhs_tag)::value;
+#pragma unroll
+    for (int k = 0; k < NXL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < N) {
+        double xt[NI], qv[NI], r[NI];
+        double* pw = wpos(PX[32 * k]);
+        MO::ld(pw, xt);
+        if (RHS) tabN(AQ, k, qv);
+#pragma unroll
+        for (int s = 0; s < NI; ++s) {
+          x[s][k] = alpha * xt[s] + (1.0 - alpha) * x[s][k];
+          if (RHS) r[s] = sigma * x[s][k] - qv[s];
+        }
+        if (RHS) MO::st(pw, r);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NZL; ++k) {
+      const int j = lane + 32 * k;
+      if (j < M) {
+        const double ri = rinv_of(k);
+        double nu[NI], lv[NI], uv[NI], r[NI];
+        double* pw = wpos(PZ[32 * k]);
+        MO::ld(pw, nu);
+        tabN(AL, k, lv); tabN(AU, k, uv);
+#pragma unroll
+        for (int s = 0; s < NI; ++s) {
+          double zv, dv;
+          if (FIRST) zd_first(s, k, lv[s], uv[s], zv, dv); else zd_of(s, k, lv[s], uv[s], zv, dv);
+          const double zt = (zv - dv) + ri * nu[s];
+          const double v = alpha * zt + (1.0 - alpha) * zv;
+          t[s][k] = v + dv;
+          if (RHS) { double zn, dn; zd_of(s, k, lv[s], uv[s], zn, dn); r[s] = zn - dn; }
+        }
+        if (RHS) MO::st(pw, r);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < NI; ++s) { it[s] += active[s] ? 1 : 0; first[s] = false; }
+  };
+  using TrueT = std::integral_constant<bool, true>;
+  using FalseT = std::integral_constant<bool, false>;
+
   int par = 0;
   if constexpr (DMMA) {            // first fill; the group meets before anybody's scratch use can collide with a right-hand side
 #pragma unroll 1
@@ -616,7 +728,7 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
 
     // which slots evaluate their residuals after this iteration
     bool chk[NI], adp[NI];
-    bool any_chk = false;
+    bool any_chk = false, any_first = false;
 #pragma unroll
     for (int s = 0; s < NI; ++s) {
       const int itn = it[s] + 1;
@@ -624,37 +736,15 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
       adp[s] = active[s] && st.adaptive_rho && st.adaptive_rho_interval && (itn % st.adaptive_rho_interval == 0);
       chk[s] = active[s] && (can_check || itn == st.max_iter);
       any_chk |= chk[s] || adp[s];
+      any_first |= first[s];
     }
     if constexpr (DMMA) {           // tell the group: bit 0 = somebody runs the once-per-check routines, bit 1 = somebody is alive
       const int f = (any_chk ? 1 : 0) | (any_active ? 2 : 0);
       if (lane == 0 && f) atomicOr(dc->gflag + par, f);
     }
 
-    // ---- one ADMM iteration for all slots (osqp.c:354-372): rhs, KKT solve
-    if (!DMMA || any_active) {
-#pragma unroll
-      for (int k = 0; k < NXL; ++k) {
-        const int i = lane + 32 * k;
-        if (i < N) {
-          double qv[NI], r[NI];
-          tabN(AQ, k, qv);
-#pragma unroll
-          for (int s = 0; s < NI; ++s) r[s] = sigma * x[s][k] - qv[s];
-          MO::st(wpos(PX[32 * k]), r);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < NZL; ++k) {
-        const int j = lane + 32 * k;
-        if (j < M) {
-          const double ri = rinv_of(k);
-          double r[NI];
-#pragma unroll
-          for (int s = 0; s < NI; ++s) r[s] = z[s][k] - ri * y[s][k];
-          MO::st(wpos(PZ[32 * k]), r);
-        }
-      }
-    }
+    // ---- one ADMM iteration for all slots (osqp.c:354-372): rhs (unless the last update left it in place), KKT solve
+    if ((DMMA && any_active) || (!DMMA && need_rhs)) write_rhs();
     int gflags = 0;
     if constexpr (DMMA) {
       group_bar(dc->bar_id);                             // right-hand sides and flags of all four warps are in place
@@ -671,45 +761,15 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
     }
 
     if (!any_chk) {
-      // ---- update_x, update_z (+project), update_y (auxil.c:185-225)
-      if (!DMMA || any_active) {
-#pragma unroll
-        for (int k = 0; k < NXL; ++k) {
-          const int i = lane + 32 * k;
-          if (i < N) {
-            double xt[NI];
-            MO::ld(wpos(PX[32 * k]), xt);
-#pragma unroll
-            for (int s = 0; s < NI; ++s) x[s][k] = alpha * xt[s] + (1.0 - alpha) * x[s][k];
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < NZL; ++k) {
-          const int j = lane + 32 * k;
-          if (j < M) {
-            const double ri = rinv_of(k), r = rho_of(k);
-            double nu[NI], lv[NI], uv[NI];
-            MO::ld(wpos(PZ[32 * k]), nu);
-            tabN(AL, k, lv); tabN(AU, k, uv);
-#pragma unroll
-            for (int s = 0; s < NI; ++s) {
-              const double zt = (z[s][k] - ri * y[s][k]) + ri * nu[s];
-              const double v = alpha * zt + (1.0 - alpha) * z[s][k];
-              const double zn = fmin(fmax(v + ri * y[s][k], lv[s]), uv[s]);
-              y[s][k] += r * (v - zn);
-              z[s][k] = zn;
-            }
-          }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int s = 0; s < NI; ++s) it[s] += active[s] ? 1 : 0;
-      }
       if constexpr (DMMA) {
+        if (any_active) { if (any_first) update_all(TrueT{}, FalseT{}); else update_all(FalseT{}, FalseT{}); }
         if (gflags & 1) {            // another warp of the group runs its checks in its scratch: frame them with it
           group_bar(dc->bar_id);
           group_bar(dc->bar_id);
         }
+      } else {
+        if (any_first) update_all(TrueT{}, TrueT{}); else update_all(FalseT{}, TrueT{});
+        need_rhs = false;
       }
       continue;
     }
@@ -744,40 +804,43 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
         tabN(AL, k, lv); tabN(AU, k, uv);
 #pragma unroll
         for (int s = 0; s < NI; ++s) {
-          const double zt = (z[s][k] - ri * y[s][k]) + ri * nu[s];
-          const double v = alpha * zt + (1.0 - alpha) * z[s][k];
-          const double zn = fmin(fmax(v + ri * y[s][k], lv[s]), uv[s]);
-          const double d = r * (v - zn);
-          dy[s][k] = d;
-          y[s][k] += d;
-          z[s][k] = zn;
+          double zv, dv;
+          zd_first(s, k, lv[s], uv[s], zv, dv);
+          const double zt = (zv - dv) + ri * nu[s];
+          const double v = alpha * zt + (1.0 - alpha) * zv;
+          t[s][k] = v + dv;
+          const double zn = fmin(fmax(t[s][k], lv[s]), uv[s]);
+          dy[s][k] = r * (v - zn);                         // delta_y of update_y (auxil.c:215-225)
         }
       }
     }
     __syncwarp();
 #pragma unroll
-    for (int s = 0; s < NI; ++s) it[s] += active[s] ? 1 : 0;
+    for (int s = 0; s < NI; ++s) { it[s] += active[s] ? 1 : 0; first[s] = false; }
+    need_rhs = true;
     if constexpr (DMMA) group_bar(dc->bar_id);     // every warp has read its solution: w8 is scratch until the next right-hand side
 
     // ---- residuals, termination, adaptive-rho decision: slot by slot at position 0
 #pragma unroll 1
     for (int r = 0; r < NI; ++r) {
       if (chk[0] || adp[0]) {
-        update_info0();
+        double zc[NZLs], yc[NZLs];
+        zy0(zc, yc);
+        update_info0(zc, yc);
         int status = ST_UNSOLVED;
         if (chk[0]) status = check_termination0(dx[0], dy[0], false);
         if (status == ST_UNSOLVED && it[0] >= st.max_iter) {          // osqp.c:563-568
           status = check_termination0(dx[0], dy[0], true);
           if (status == ST_UNSOLVED) status = ST_MAXITER;
         }
-        if (status != ST_UNSOLVED) { finish0(status); active[0] = false; }
+        if (status != ST_UNSOLVED) { finish0(status, yc); active[0] = false; }
         else if (adp[0]) {                                            // adapt_rho decision (auxil.c:13-74)
           const double pn = s_rp / (fmax(s_z, s_Ax) + DIVISION_TOL);
           const double dn = s_rd / (fmax(fmax(s_q, s_Aty), s_Px) + DIVISION_TOL);
           double rr = rho_in * sqrt(pn / dn);
           rr = fmin(fmax(rr, RHO_MIN), RHO_MAX);
           if (rr > rho_in * st.adaptive_rho_tolerance || rr < rho_in / st.adaptive_rho_tolerance) {
-            hand_off0(rr); active[0] = false;
+            hand_off0(rr, zc, yc); active[0] = false;
           }
         }
       }
@@ -788,15 +851,15 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
         for (int s = 0; s + 1 < NI; ++s) { chk[s] = chk[s + 1]; adp[s] = adp[s + 1]; }
         chk[NI - 1] = c0; adp[NI - 1] = a0; }
 #pragma unroll
-      for (int k = 0; k < NXL; ++k) { const double t = dx[0][k];
+      for (int k = 0; k < NXL; ++k) { const double v = dx[0][k];
 #pragma unroll
         for (int s = 0; s + 1 < NI; ++s) dx[s][k] = dx[s + 1][k];
-        dx[NI - 1][k] = t; }
+        dx[NI - 1][k] = v; }
 #pragma unroll
-      for (int k = 0; k < NZLs; ++k) { const double t = dy[0][k];
+      for (int k = 0; k < NZLs; ++k) { const double v = dy[0][k];
 #pragma unroll
         for (int s = 0; s + 1 < NI; ++s) dy[s][k] = dy[s + 1][k];
-        dy[NI - 1][k] = t; }
+        dy[NI - 1][k] = v; }
     }
     if constexpr (DMMA) {            // refill what terminated (the other kernel does it at the top of its loop), then release w8
 #pragma unroll 1

@@ -90,6 +90,8 @@ struct Ctx {
   int tail_cap = 0;
   // staging for the host-buffer entry point
   int cap_B = 0;
+  double* d_ws = nullptr;      // warm-start scratch of the main kernel (BatchIO::ws)
+  int cap_ws = 0;
   double *d_params = nullptr, *d_x0 = nullptr, *d_y0 = nullptr, *d_prim = nullptr, *d_dual = nullptr;
   double *d_solx = nullptr, *d_soly = nullptr, *d_obj = nullptr, *d_pri = nullptr, *d_dua = nullptr;
   int *d_iter = nullptr, *d_status = nullptr;
@@ -360,7 +362,7 @@ int CPG_B200_FN(cpg_b200_free)(void) {        // releases the context of EVERY d
   for (int d = 0; d < MAX_DEVICES; ++d) {
     cur_ctx = &ctxs[d];
     if (g.device < 0) continue;
-    void* ptrs[] = {g.d_blob, g.d_cblob, g.d_gblob, g.d_gS0, g.d_mblob, g.d_dblob, g.d_mat_scratch, g.g_soly, g.g_dprim, g.g_dparams, g.g_dq, g.g_dl, g.g_du, g.d_tail_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0,
+    void* ptrs[] = {g.d_blob, g.d_cblob, g.d_gblob, g.d_gS0, g.d_mblob, g.d_dblob, g.d_mat_scratch, g.g_soly, g.g_dprim, g.g_dparams, g.g_dq, g.g_dl, g.g_du, g.d_tail_blob, g.d_counter, g.d_tail_count, g.d_tail_ids, g.d_tail_state, g.d_params, g.d_x0, g.d_y0, g.d_ws,
                     g.d_prim, g.d_dual, g.d_solx, g.d_soly, g.d_obj, g.d_pri, g.d_dua, g.d_iter, g.d_status};
     cudaSetDevice(g.device);
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -399,6 +401,17 @@ int CPG_B200_FN(cpg_solve_batch_device)(int B, const double* params, const doubl
   io.obj_val = obj_val; io.iter = iter; io.status = status; io.pri_res = pri_res; io.dua_res = dua_res;
   io.work_counter = g.d_counter; io.tail_count = g.d_tail_count; io.tail_ids = g.d_tail_ids;
   io.tail_state = g.d_tail_state; io.B = B; io.tail_capacity = g.tail_cap;
+  io.ws = nullptr;
+  if (st.warm_start && Fam::M > 0) {        // start points (z0 = A x0, y0 / rho) of the warm-started instances, main kernel only
+    if (B > g.cap_ws) {
+      g.cap_ws = 0;
+      CK(cudaStreamSynchronize(stream));
+      int rc = grow(&g.d_ws, (size_t)B * 2 * Fam::M);
+      if (rc) return rc;
+      g.cap_ws = B;
+    }
+    io.ws = g.d_ws;
+  }
   CK(cudaMemsetAsync(g.d_counter, 0, sizeof(unsigned int), stream));
   CK(cudaMemsetAsync(g.d_tail_count, 0, sizeof(int), stream));
 #if CPG_FAM_MATPAR
