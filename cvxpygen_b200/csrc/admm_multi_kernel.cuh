@@ -869,8 +869,10 @@ __device__ void solve_multi(const CpgBlobHeader* __restrict__ H, const int* __re
   }
 }
 
+// registers per thread: the whole register file divided among the CTA's warps, stated as __maxnreg__ (from __launch_bounds__
+// alone ptxas settles on 128 for 13 and 14 warps, far below the 152 / 144 that fit)
 template <class Fam>
-__global__ void __launch_bounds__(Fam::WARPS * 32, 1)
+__global__ void __maxnreg__(Fam::MAXREG)
 admm_multi_kernel(const uint8_t* __restrict__ blob_g, const BatchIO io, const Settings st) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;

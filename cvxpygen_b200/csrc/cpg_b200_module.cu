@@ -41,6 +41,9 @@ struct Fam {
   static constexpr int WARPS = CPG_FAM_WARPS;
   static constexpr int BLOB_BYTES_PAD = CPG_FAM_BLOB_BYTES_PAD;
   static constexpr int CBLOB_BYTES_PAD = CPG_FAM_CBLOB_BYTES_PAD;
+  // registers are allocated to warps four at a time: the file (65 536) is divided among ceil(WARPS / 4) * 4 warps
+  static constexpr int WARPS_ALLOC = (CPG_FAM_WARPS + 3) / 4 * 4;
+  static constexpr int MAXREG = (65536 / (WARPS_ALLOC * 32)) / 8 * 8 > 255 ? 255 : (65536 / (WARPS_ALLOC * 32)) / 8 * 8;
   static constexpr int W_STRIDE = CPG_FAM_W_STRIDE;       // doubles per warp work vector
   static constexpr int S_STRIDE = CPG_FAM_S_STRIDE;       // doubles per warp factor storage (tail kernel)
   static constexpr int TAIL_WARPS = CPG_FAM_TAIL_WARPS;

@@ -180,20 +180,44 @@ class SolveSchedule:
         return w
 
 
-def build_schedule(F: LDLFactor, max_group_rows: int = 64, allow_trailing: bool = True) -> SolveSchedule:
+import os as _os
+ENCODED_TILE_OVERHEAD = float(_os.environ.get('CPG_TILE_OVERHEAD', 12.0))     # per tile, in wavefront units: result stores, the shuffle-add stages, the hazard on the next tile
+
+
+def _encoded_cost(tiles: List['Tile'], nk: int) -> float:
+    """Modelled shared-memory wavefronts of a group's tiles in their cheaper device encoding (the quantity the kernel is bound by)."""
+    c = 0.0
+    for t in tiles:
+        sp_ = encode_sparse(t, conflict_aware=False)       # the conflict-aware deal removes ~3/4 of the counted conflicts
+        de = encode_dense(t)
+        ok = max(c0 + (LANES // t.r_pad) * Kp for c0, Kp in de['segs']) <= nk
+        c += min(sp_['K'] * SPARSE_STEP_WF + 0.25 * sp_['conflicts'], de['cost'] if ok else float('inf')) + ENCODED_TILE_OVERHEAD
+    return c
+
+
+def build_schedule(F: LDLFactor, max_group_rows: int = 64, allow_trailing: bool = True, cost: str = 'encoded') -> SolveSchedule:
+    """Group boundaries by dynamic programming.  cost = 'encoded': a group costs the modelled wavefronts of its tiles as the kernel
+    will execute them (round 2; MPC-12/4/10: 1 760 -> 1 435 wavefronts per solve against the step-count model of round 1, which
+    remains available as cost = 'count')."""
     level = F.level
     n = len(level)
     bounds = [0] + [k for k in range(1, n) if level[k] != level[k - 1]] + [n]
     nb = len(bounds)
+    if cost == 'encoded' and nb * min(nb, max_group_rows) > 20000:
+        cost = 'count'                                     # very deep elimination trees: keep the set-up time bounded
 
     def cost_f(i, j):
-        rows, M, _ = _forward_group(F, bounds[i], bounds[j])
+        rows, M, cp = _forward_group(F, bounds[i], bounds[j])
         if not len(rows):
             return 0.0
+        if cost == 'encoded':
+            return _encoded_cost(_make_tiles(rows, M, cp, decreasing=True), n)
         return _group_cost(np.count_nonzero(M, axis=1)[::-1])
 
     def cost_b(i, j):
-        rows, M, _ = _backward_group(F, bounds[i], bounds[j])
+        rows, M, cp = _backward_group(F, bounds[i], bounds[j])
+        if cost == 'encoded':
+            return _encoded_cost(_make_tiles(rows, M, cp, decreasing=False), n)
         return _group_cost(np.count_nonzero(M, axis=1))
 
     INF = float('inf')
@@ -216,8 +240,9 @@ def build_schedule(F: LDLFactor, max_group_rows: int = 64, allow_trailing: bool 
             r = n - bounds[j]
             if r > 160:
                 continue
-            _, Mt, _ = _trailing_block(F, bounds[j])
-            dense = _group_cost(np.count_nonzero(Mt, axis=1))
+            rt, Mt, cpt = _trailing_block(F, bounds[j])
+            dense = (_encoded_cost(_make_tiles(rt, Mt, cpt, decreasing=False), n) if cost == 'encoded'
+                     else _group_cost(np.count_nonzero(Mt, axis=1)))
             tot = Ff[j] + Bb[j] + dense
             if tot < best:
                 best, best_j = tot, j
@@ -255,9 +280,13 @@ def build_schedule(F: LDLFactor, max_group_rows: int = 64, allow_trailing: bool 
 #   sparse: lane-interleaved ELL, column indices packed two per 32-bit word; every lane gathers its own w entry
 #   dense : the union of the rows' columns is covered by a few contiguous column segments; all lanes of a
 #           row-part read the SAME w address at each step (shared-memory broadcast), no index loads at all.
-SPARSE_STEP_WF = 9.0     # shared-memory wavefronts per inner step (2 val + 0.5 idx + ~6.5 gather of 16-byte pairs)
-DENSE_STEP_WF = 3.0      # 2 val + 1 broadcast
-DENSE_SEG_OVERHEAD = 1.0
+# Shared-memory wavefronts per inner step, MEASURED per instruction on B200 (ncu source page of the MPC kernel, round 2,
+# profiles/r2_multi_v8_ncu_summary.md): a coefficient LDS.64 is 2 wavefronts, a broadcast LDS.128 of the operand pair is 2 (not 1),
+# a 16-byte gather is 4 plus its bank conflicts, the packed index word 0.5.  (Round 1 assumed 9 / 3, which encoded four tiles of
+# the MPC schedule dense although their gather form is cheaper: 1 760 -> 1 618 modelled wavefronts per solve.)
+SPARSE_STEP_WF = 6.5
+DENSE_STEP_WF = 4.0
+DENSE_SEG_OVERHEAD = 0.5
 
 
 def _quarter_conflicts(cols_k: np.ndarray) -> int:
@@ -325,8 +354,8 @@ def encode_sparse(t: Tile, conflict_aware: bool = True):
             fill = cols[k][sl][real][0] if real.any() else (used_all[0] if len(used_all) else int(t.rows[0]))
             cq = cols[k][sl]; cq[~real] = fill
     packed = (cols[0::2] | (cols[1::2] << 16)).astype(np.uint32)
-    return dict(kind=0, K=K, vals=vals, cols32=packed, cost=K * SPARSE_STEP_WF,
-                conflicts=sum(_quarter_conflicts(cols[k]) for k in range(K)))
+    conflicts = sum(_quarter_conflicts(cols[k]) for k in range(K))
+    return dict(kind=0, K=K, vals=vals, cols32=packed, cost=K * SPARSE_STEP_WF + conflicts, conflicts=conflicts)
 
 
 def encode_dense(t: Tile, max_gap: int = 3):

@@ -34,6 +34,7 @@ struct Fam {
   static constexpr int TRAIL = CPG_FAM_TRAIL_TILES, WARPS = CPG_FAM_WARPS, NI = CPG_FAM_NI, MULTI_STRIDE = CPG_FAM_MULTI_STRIDE;
   static constexpr int BLOB_BYTES_PAD = CPG_FAM_BLOB_BYTES_PAD;
   static constexpr int CBLOB_BYTES_PAD = CPG_FAM_CBLOB_BYTES_PAD;
+  static constexpr int MAXREG = 255;
   static constexpr int W_STRIDE = CPG_FAM_W_STRIDE, S_STRIDE = CPG_FAM_S_STRIDE;
   static constexpr int TAIL_WARPS = CPG_FAM_TAIL_WARPS;
   static constexpr bool TAIL_STAGE = CPG_FAM_TAIL_STAGE != 0;

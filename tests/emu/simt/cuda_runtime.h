@@ -25,6 +25,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __shared__ thread_local   /* one OS thread runs all fibers, so a thread_local object is shared by every CUDA thread:
                                      `extern __shared__ T smem[]` binds to a thread_local host array the driver defines, a
                                      block-scope `__shared__ int x;` becomes one static object per kernel */
