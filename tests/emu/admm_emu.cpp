@@ -100,6 +100,8 @@ int emu_matpar_solve(int B, const double* params, double* prim, double* dual, do
 
 // The two launches of cpg_solve_batch_device for shared-matrix families: admm_multi_kernel (NI instances per warp, generated
 // straight-line KKT solve, lockstep CTA) and then admm_tail_kernel on whatever it handed off (rho updates, type changes)
+static const double* g_warm_x0 = nullptr;     // set by emu_main_solve_warm for the duration of one solve
+static const double* g_warm_y0 = nullptr;
 int emu_main_solve(int B, const double* params, double* prim, double* dual, double* sol_x, double* sol_y, double* obj,
                    int* iter, int* status, double* pri, double* dua, int grid, int adaptive_rho_interval, double eps) {
   constexpr int WORDS = Fam::N + 2 * Fam::M + 2;
@@ -112,7 +114,13 @@ int emu_main_solve(int B, const double* params, double* prim, double* dual, doub
   io.params = params; io.prim = prim; io.dual = dual; io.sol_x = sol_x; io.sol_y = sol_y; io.obj_val = obj; io.iter = iter;
   io.status = status; io.pri_res = pri; io.dua_res = dua; io.B = B; io.work_counter = &counter;
   io.tail_count = &count; io.tail_ids = ids.data(); io.tail_state = state.data(); io.tail_capacity = B;
-  const cpgb200::Settings st = default_settings(adaptive_rho_interval, eps);
+  cpgb200::Settings st = default_settings(adaptive_rho_interval, eps);
+  std::vector<double> ws;
+  if (g_warm_x0 && g_warm_y0) {          // warm start (osqp_warm_start): start points of the main kernel live in io.ws
+    io.x0 = g_warm_x0; io.y0 = g_warm_y0; st.warm_start = 1;
+    ws.assign((size_t)B * 2 * (Fam::M > 0 ? Fam::M : 1), 0.0);
+    io.ws = ws.data();
+  }
 #if CPG_FAM_BIG        // schedule larger than shared memory: every instance is queued for the per-instance-factor kernel
   simt::launch((B + 255) / 256, 256, [&] { cpgb200::queue_all_kernel(io, WORDS, Fam::N + 2 * Fam::M,
                                                                         reinterpret_cast<const CpgBlobHeader*>(CPG_B200_FN(cpg_blob_words))->rho); });
@@ -132,6 +140,15 @@ int emu_main_solve(int B, const double* params, double* prim, double* dual, doub
                                    reinterpret_cast<const uint8_t*>(CPG_B200_FN(cpg_tail_blob_words)), io, st);
   });
   return handed_off;
+}
+
+int emu_main_solve_warm(int B, const double* params, const double* x0, const double* y0, double* prim, double* dual, double* sol_x,
+                        double* sol_y, double* obj, int* iter, int* status, double* pri, double* dua, int grid,
+                        int adaptive_rho_interval, double eps) {
+  g_warm_x0 = x0; g_warm_y0 = y0;
+  const int rc = emu_main_solve(B, params, prim, dual, sol_x, sol_y, obj, iter, status, pri, dua, grid, adaptive_rho_interval, eps);
+  g_warm_x0 = g_warm_y0 = nullptr;
+  return rc;
 }
 
 // admm_tail_kernel: every instance is queued at iteration 0 with the family's rho (the route an instance whose bounds

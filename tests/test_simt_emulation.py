@@ -116,6 +116,34 @@ def test_main_kernel_on_the_emulator(tmp_path, dmma):
     assert np.array_equal(out2['iter'], ora2['iter']) and rel_err(out2['x'], ora2['x']).max() < 1e-8
 
 
+def test_main_kernel_warm_start_on_the_emulator(tmp_path):
+    """Warm start (osqp_warm_start, osqp.c:929-953) through the main kernel: its per-instance state is the pre-projection vector
+    t, which cannot represent a start point (z0 = A x0 need not lie in [l, u]); the first iteration reads (z0, y0 / rho) from the
+    instance's scratch rows instead.  Same iteration counts as the reference warm-started from the same point."""
+    fam = families.mpc(4, 2, 6)
+    st, lib, dims = build_emu(fam, ['x_init'], str(tmp_path))
+    n, m = dims[0], dims[1]
+    B = 13
+    rng = np.random.default_rng(5)
+    xi = rng.uniform(-1.5, 1.5, (B, 4))
+    q, l, u = canon_batches(fam, {'x_init': xi}, B)
+    cold = oracle_solve(fam, q, l, u)
+    # start from the solution of a neighbouring instance, perturbed: z0 = A x0 violates the bounds of most rows
+    x0 = np.ascontiguousarray(np.roll(cold['x'], 1, axis=0) + 0.05 * rng.standard_normal((B, n)))
+    y0 = np.ascontiguousarray(np.roll(cold['y'], 1, axis=0) + 0.05 * rng.standard_normal((B, m)))
+    out = dict(prim=np.zeros((B, dims[3])), dual=np.zeros((B, dims[4])), x=np.zeros((B, n)), y=np.zeros((B, m)), obj=np.zeros(B),
+               iter=np.zeros(B, np.int32), status=np.zeros(B, np.int32), pri=np.zeros(B), dua=np.zeros(B))
+    rows = np.ascontiguousarray(xi)
+    rc = lib.emu_main_solve_warm(C.c_int(B), _ptr(rows), _ptr(x0), _ptr(y0), _ptr(out['prim']), _ptr(out['dual']), _ptr(out['x']),
+                                 _ptr(out['y']), _ptr(out['obj']), _ptr(out['iter'], C.c_int), _ptr(out['status'], C.c_int),
+                                 _ptr(out['pri']), _ptr(out['dua']), C.c_int(2), C.c_int(0), C.c_double(1e-3))
+    assert rc >= 0
+    ora = oracle_solve(fam, q, l, u, x0=x0, y0=y0)
+    assert np.array_equal(out['iter'], ora['iter']) and np.array_equal(out['status'], ora['status'])
+    assert rel_err(out['x'], ora['x']).max() < 1e-9 and rel_err(out['y'], ora['y']).max() < 1e-9
+    assert not np.array_equal(ora['iter'], cold['iter'])          # the start point mattered
+
+
 @pytest.mark.parametrize('name,B,dmma', [('nonneg_LS_3_2', 40, False), ('box_qp_6_8', 96, False), ('random_qp_20_5_15', 24, False),
                                          ('mpc_12_4_10', 12, False), ('portfolio_qp_50_10', 6, False),
                                          ('box_qp_6_8', 96, True), ('mpc_12_4_10', 20, True)])
