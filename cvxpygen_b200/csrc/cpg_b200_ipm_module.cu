@@ -23,7 +23,7 @@ namespace {
 using cpgipm::IpmIO;
 using cpgipm::IpmSettings;
 static_assert(sizeof(IpmSettings) == sizeof(CpgB200SocpSettings), "settings struct of the kernel and of the C ABI must match");
-static_assert(cpgipm::SMEM_BYTES <= 232448 - 1024, "per-instance state + tables exceed the shared memory of one SM");
+static_assert(cpgipm::SMEM_BYTES <= 232448 - 64,   /* 227 KB opt-in limit per CTA minus the kernel's 16 bytes of static shared memory */ "per-instance state + tables exceed the shared memory of one SM");
 
 struct Ctx {
   bool ready = false;
@@ -114,7 +114,7 @@ int CPG_B200_FN(cpg_b200_init)(int device) {
   CK(cudaMalloc(&g.d_gblob, gb));
   CK(cudaMemcpy(g.d_sblob, CPG_B200_FN(cpg_ipm_sblob_words), sb, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(g.d_gblob, CPG_B200_FN(cpg_ipm_gblob_words), gb, cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&g.d_best, sizeof(double) * (size_t)g.n_sm * (cpgipm::NK + cpgipm::MT)));
+  CK(cudaMalloc(&g.d_best, sizeof(double) * (size_t)g.n_sm * cpgipm::BEST_STRIDE));
   CK(cudaMalloc(&g.d_counter, sizeof(int)));
   CK(cudaFuncSetAttribute(cpgipm::ipm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cpgipm::SMEM_BYTES));
   CK(cudaEventCreate(&g.ev[0])); CK(cudaEventCreate(&g.ev[1]));

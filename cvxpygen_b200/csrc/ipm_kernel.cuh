@@ -48,6 +48,11 @@ namespace cpgipm { static long g_count[8] = {0, 0, 0, 0, 0, 0, 0, 0}; }     // e
 #define IPM_COUNT(i) ((void)0)
 #endif
 
+#ifndef IPM_MATPAR
+#define IPM_MATPAR 0
+#define IPM_NEMAP 0
+#endif
+
 namespace cpgipm {
 
 // ---- constants of the reference (ecos/include/ecos.h:45-75)
@@ -75,7 +80,8 @@ struct IpmIO {
   double* sol_z;             // (B, M) or null
   double* sol_s;             // (B, M) or null
   double* obj_val; int* iter; int* status; double* pri_res; double* dua_res;
-  double* best;              // per-CTA scratch for the best iterate: gridDim.x * (NK + MT) doubles
+  double* best;              // per-CTA scratch: gridDim.x * BEST_STRIDE doubles -- the best iterate (NK + MT) and, with per-instance
+                             // matrices, the instance's output scalings 1/xe, 1/Ae, 1/Ge in k-space (NK)
   int* counter;              // work counter
 };
 
@@ -86,6 +92,7 @@ constexpr int NW = IPM_NW, DG0 = IPM_DG0, TT0 = IPM_TT0, NS = IPM_NS, NT = IPM_N
 constexpr int NNZM = IPM_NNZM, NPB = IPM_NPB, NMAP = IPM_NMAP, NPRIM = IPM_NPRIM, NDUAL = IPM_NDUAL, QTOT = IPM_QTOT;
 constexpr int CONE_D = L + NSOC;              // degree of the cone (w->D)
 constexpr int PT = (NK + T - 1) / T;          // elements of a k-space vector owned by one thread
+constexpr int BEST_STRIDE = NK + MT + (IPM_MATPAR ? NK : 0);      // doubles of IpmIO::best per CTA
 constexpr int NCR = MT - L;                   // stretched rows of the second-order cones
 static_assert(IPM_THREADS == CPG_IPM_THREADS, "the gather plans were dealt for another CTA width: regenerate the family");
 static_assert(NT <= 32, "the dense tail block is handled by one warp");
@@ -145,6 +152,10 @@ struct Sm {
 struct Gm {                 // global constant tables
   const double *Sbase, *cbh_base, *unscale, *map_v;
   const int *map_t, *map_p, *prim_idx, *dual_idx;
+#if IPM_MATPAR      // per-instance G / A values: raw entry = ent_base + emap_v * theta[emap_p]; entry e couples k-rows mr_t[e], mr_s[e] (slot ag_slot[e])
+  const double *ent_base, *emap_v;
+  const int *emap_t, *emap_p, *mr_t, *mr_s, *ag_slot;
+#endif
   const unsigned long long* op_e;      // factorisation plan: entries (slot a | slot b << 16 | diagonal slot << 32)
   const uint32_t* op_d;                // and descriptors
 };
@@ -155,6 +166,10 @@ IPM_FN Gm make_gm(const unsigned char* g) {
   r.Sbase = f + IPM_G_SBASE; r.cbh_base = f + IPM_G_CBH_BASE; r.unscale = f + IPM_G_UNSCALE; r.map_v = f + IPM_G_MAP_V;
   const int* i = reinterpret_cast<const int*>(g + IPM_GB_I32_OFF);
   r.map_t = i + IPM_GI_MAP_T; r.map_p = i + IPM_GI_MAP_P; r.prim_idx = i + IPM_GI_PRIM_IDX; r.dual_idx = i + IPM_GI_DUAL_IDX;
+#if IPM_MATPAR
+  r.ent_base = f + IPM_G_ENT_BASE; r.emap_v = f + IPM_G_EMAP_V;
+  r.emap_t = i + IPM_GI_EMAP_T; r.emap_p = i + IPM_GI_EMAP_P; r.mr_t = i + IPM_GI_MR_T; r.mr_s = i + IPM_GI_MR_S; r.ag_slot = i + IPM_GI_AG_SLOT;
+#endif
   r.op_e = reinterpret_cast<const unsigned long long*>(g + IPM_GB_OPS_OFF);
   r.op_d = reinterpret_cast<const uint32_t*>(g + IPM_GB_OPD_OFF);
   return r;
@@ -166,6 +181,7 @@ IPM_FN double safediv(double x, double y) { return y < kEps ? x / kEps : x / y; 
 // execution model: phases, reductions, per-cone warps
 #ifdef CPG_IPM_HOST_EMU
 IPM_FN void atomic_add(double* p, double v) { *p += v; }
+IPM_FN void atomic_max_nonneg(double* p, double v) { if (v > *p) *p = v; }
 template <class F> IPM_FN void phase(F&& f) { IPM_COUNT(2); for (int t = 0; t < T; ++t) f(t); }
 IPM_FN void sync_phase() { IPM_COUNT(2); }
 // KS sums and KM maxima over all threads; f(tid, s, m) accumulates with += and fmax
@@ -197,6 +213,14 @@ template <int CNT> struct PerThread {
 };
 #else
 IPM_FN void atomic_add(double* p, double v) { atomicAdd(p, v); }
+// max of NON-NEGATIVE doubles: their bit patterns order like unsigned integers (exact, order-independent)
+IPM_FN void atomic_max_nonneg(double* p, double v) {
+#ifdef CPG_SIMT_HOST_EMU
+  if (v > *p) *p = v;
+#else
+  atomicMax(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(__double_as_longlong(v)));
+#endif
+}
 template <class F> IPM_FN void phase(F&& f) { f(int(threadIdx.x)); __syncthreads(); }
 IPM_FN void sync_phase() { __syncthreads(); }
 IPM_FN double warp_sum(double v) {
@@ -773,6 +797,47 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
   // ---- cpg_canonicalize: c, b, h from the user parameters (equilibrated), cvxpygen/utils.py:279-294 + equil.c:326-338
   phase([&](int tid) { each_k(tid, NK, [&](int k) { sm.cbh()[k] = gm.cbh_base[k]; }); });
   phase([&](int tid) { each_k(tid, NMAP, [&](int e) { atomic_add(sm.cbh() + gm.map_t[e], gm.map_v[e] * par[gm.map_p[e]]); }); });
+#if IPM_MATPAR
+  // ---- a user parameter enters G or A: this instance's matrix values, then what ECOS_updateData does with new values
+  // (ecos.c:1648-1695) -- set_equilibration from scratch (equil.c:210-342): EQUIL_ITERS passes of  scale = sqrt(max |entry|)  per row and
+  // per column of [A ; G] (one value, the SUM of the row maxima, for all rows of a second-order cone; values below 1e-6 -> 1), rows
+  // divided first, then columns; c, b, h divided by the accumulated scalings.  The maxima are exact and order-independent (atomic max
+  // on the bit patterns of non-negative doubles); the cone sum runs in row order on one thread like the reference's loop.
+  // Work vectors: rhs = this pass's scaling per k-row, px = accumulated scaling.
+  double* const usc = best + NK + MT;
+  phase([&](int tid) {
+    each_k(tid, NNZM, [&](int e) { sm.ag()[e] = gm.ent_base[e]; });
+    each_k(tid, NK, [&](int k) { sm.px()[k] = 1.0; });
+  });
+  phase([&](int tid) { each_k(tid, IPM_NEMAP, [&](int i) { atomic_add(sm.ag() + gm.emap_t[i], gm.emap_v[i] * par[gm.emap_p[i]]); }); });
+  for (int pass = 0; pass < 3; ++pass) {
+    phase([&](int tid) { each_k(tid, NK, [&](int k) { sm.rhs()[k] = 0.0; }); });
+    phase([&](int tid) {
+      each_k(tid, NNZM, [&](int e) {
+        const double v = fabs(sm.ag()[e]);
+        atomic_max_nonneg(sm.rhs() + gm.mr_t[e], v); atomic_max_nonneg(sm.rhs() + gm.mr_s[e], v);
+      });
+    });
+    phase([&](int tid) {
+      if (tid < NSOC) {
+        const int so = ZOFF + kSocSo[tid], d = kSocD[tid];
+        double tot = 0.0;
+        for (int r = 0; r < d; ++r) tot += sm.rhs()[so + r];
+        for (int r = 0; r < d; ++r) sm.rhs()[so + r] = tot;
+      }
+    });
+    phase([&](int tid) {
+      each_k(tid, NK, [&](int k) {
+        const double v = sm.rhs()[k], f = fabs(v) < 1e-6 ? 1.0 : sqrt(v);
+        sm.rhs()[k] = f; sm.px()[k] *= f;
+      });
+    });
+    phase([&](int tid) { each_k(tid, NNZM, [&](int e) { sm.ag()[e] = (sm.ag()[e] / sm.rhs()[gm.mr_t[e]]) / sm.rhs()[gm.mr_s[e]]; }); });
+  }
+  phase([&](int tid) { each_k(tid, NK, [&](int k) { const double f = sm.px()[k]; sm.cbh()[k] /= f; usc[k] = 1.0 / f; }); });
+#else
+  const double* const usc = gm.unscale;
+#endif
   phase_red<3, 0>(sm, rb, s_, m_, [&](int tid, double* s, double*) {
     each_k(tid, NK, [&](int k) { const double v = sm.cbh()[k]; s[k < N ? 0 : (k < ZOFF ? 1 : 2)] += v * v; });
   });
@@ -788,6 +853,9 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
     each_k(tid, MT, [&](int i) { sm.sv()[i] = 0.0; sm.lam()[i] = 0.0; sm.rz()[i] = 0.0; sm.dsw()[i] = 0.0; });
     each_k(tid, NK, [&](int k) { sm.xyz()[k] = 0.0; });
   });
+#if IPM_MATPAR
+  phase([&](int tid) { each_k(tid, NNZM, [&](int e) { sm.S()[gm.ag_slot[e]] = sm.ag()[e]; }); });
+#endif
   factor();
   auto bring2cone = [&](const double* r, double rsign, double* out) {        // out = rsign * r shifted into the cone
     phase_red_cones<0, 1>(sm, rb, s_, m_,
@@ -914,6 +982,9 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
     phase_cones(
         [&](int tid) {
           if (tid == 0) *sm.flag() = 0;
+#if IPM_MATPAR
+          each_k(tid, NNZM, [&](int e) { sm.S()[gm.ag_slot[e]] = sm.ag()[e]; });      // this instance's A, G entries of K (S <- Sbase is done)
+#endif
           each_k_nc(tid, L, [&](int i) {
             const double v = safediv(sm.sv()[i], zv[i]), w = sqrt(v);
             sm.v()[i] = v; sm.w()[i] = w; sm.lam()[i] = w * zv[i];
@@ -1094,21 +1165,21 @@ IPM_FN int Solver::solve_instance(int inst, const IpmIO& io, double* best) {
   phase([&](int tid) {
     const double it_ = 1.0 / tau;
     (void)it_;
-    each_k(tid, NPRIM, [&](int i) { const int k = gm.prim_idx[i]; io.prim[size_t(inst) * NPRIM + i] = sm.xyz()[k] * gm.unscale[k] / tau; });
-    each_k(tid, NDUAL, [&](int i) { const int k = gm.dual_idx[i]; io.dual[size_t(inst) * NDUAL + i] = sm.xyz()[k] * gm.unscale[k] / tau; });
-    if (io.sol_x) each_k(tid, N, [&](int k) { io.sol_x[size_t(inst) * N + k] = sm.xyz()[k] * gm.unscale[k] / tau; });
-    if (io.sol_y) each_k(tid, P, [&](int i) { io.sol_y[size_t(inst) * P + i] = sm.xyz()[N + i] * gm.unscale[N + i] / tau; });
+    each_k(tid, NPRIM, [&](int i) { const int k = gm.prim_idx[i]; io.prim[size_t(inst) * NPRIM + i] = sm.xyz()[k] * usc[k] / tau; });
+    each_k(tid, NDUAL, [&](int i) { const int k = gm.dual_idx[i]; io.dual[size_t(inst) * NDUAL + i] = sm.xyz()[k] * usc[k] / tau; });
+    if (io.sol_x) each_k(tid, N, [&](int k) { io.sol_x[size_t(inst) * N + k] = sm.xyz()[k] * usc[k] / tau; });
+    if (io.sol_y) each_k(tid, P, [&](int i) { io.sol_y[size_t(inst) * P + i] = sm.xyz()[N + i] * usc[N + i] / tau; });
     if (io.sol_z || io.sol_s) {
       each_k(tid, L, [&](int i) {
-        if (io.sol_z) io.sol_z[size_t(inst) * M + i] = zv[i] * gm.unscale[ZOFF + i] / tau;
-        if (io.sol_s) io.sol_s[size_t(inst) * M + i] = sm.sv()[i] / (gm.unscale[ZOFF + i] * tau);
+        if (io.sol_z) io.sol_z[size_t(inst) * M + i] = zv[i] * usc[ZOFF + i] / tau;
+        if (io.sol_s) io.sol_s[size_t(inst) * M + i] = sm.sv()[i] / (usc[ZOFF + i] * tau);
       });
       int o = L;
       for (int c = 0; c < NSOC; ++c) {
         const int so = kSocSo[c], d = kSocD[c];
         each_k(tid, d, [&](int r) {
-          if (io.sol_z) io.sol_z[size_t(inst) * M + o + r] = zv[so + r] * gm.unscale[ZOFF + so + r] / tau;
-          if (io.sol_s) io.sol_s[size_t(inst) * M + o + r] = sm.sv()[so + r] / (gm.unscale[ZOFF + so + r] * tau);
+          if (io.sol_z) io.sol_z[size_t(inst) * M + o + r] = zv[so + r] * usc[ZOFF + so + r] / tau;
+          if (io.sol_s) io.sol_s[size_t(inst) * M + o + r] = sm.sv()[so + r] / (usc[ZOFF + so + r] * tau);
         });
         o += d;
       }
@@ -1166,7 +1237,7 @@ ipm_kernel(const unsigned char* __restrict__ smem_blob, const unsigned char* __r
     __syncthreads();
 #endif
   }
-  double* best = io.best + size_t(blockIdx.x) * (NK + MT);
+  double* best = io.best + size_t(blockIdx.x) * BEST_STRIDE;
   for (;;) {
     if (threadIdx.x == 0) next_inst = atomicAdd(io.counter, 1);
     __syncthreads();

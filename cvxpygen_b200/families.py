@@ -424,7 +424,7 @@ def random_qp(n=20, m_eq=5, m_ineq=15, density=0.3, seed=0, name=None) -> CanonF
                        {'P': _csc_pattern(Pu), 'A': _csc_pattern(A)}, variables, duals)
 
 
-def portfolio_socp(n=100, m=10, seed=1, k_tc=0.01, k_sh=0.05, Lmax=1.6, name=None) -> CanonFamily:
+def portfolio_socp(n=100, m=10, seed=1, k_tc=0.01, k_sh=0.05, Lmax=1.6, name=None, matrix_params=False) -> CanonFamily:
     """Portfolio optimisation as an SOCP in ECOS form (reference problem:
     examples/portfolio.ipynb / tests/test_E2E_QP.py:76-110,148-162):
 
@@ -436,6 +436,9 @@ def portfolio_socp(n=100, m=10, seed=1, k_tc=0.01, k_sh=0.05, Lmax=1.6, name=Non
       LP cone (l = 6n + 1):        t_tc -/+ dw >= 0 ; t_sh + w >= 0, t_sh >= 0 ; t_l1 -/+ w >= 0 ; L - 1't_l1 >= 0
       SOC(m+2): (1 + r1, 1 - r1, 2 Sig_f^1/2 f) ;  SOC(n+2): (1 + r2, 1 - r2, 2 d o w)      (||v||^2 <= r)
     User parameters: ``a`` (enters c), ``w_prev`` (enters b); F, Sig_f_sqrt, d_sqrt, k_tc, k_sh, L are constants here.
+    ``matrix_params=True`` declares the factor loadings ``F`` (n x m, column-major like cvxpy) and ``d_sqrt`` (n) as user
+    parameters as the reference's example does (examples/portfolio.ipynb): F enters A (every entry is structural, zero or
+    not), d_sqrt enters G -- the per-instance matrix path of IPM-CUDA (ECOS_updateData with new G / A values).
     Maximisation: obj_val is negated at retrieval (cvxpygen/utils.py:980)."""
     rs = np.random.RandomState(seed)
     alpha = rs.randn(n)
@@ -445,16 +448,22 @@ def portfolio_socp(n=100, m=10, seed=1, k_tc=0.01, k_sh=0.05, Lmax=1.6, name=Non
     nv = 5 * n + m + 2
     iw, idw, if_, itc, ish, il1, ir1, ir2 = 0, n, 2 * n, 2 * n + m, 3 * n + m, 4 * n + m, 5 * n + m, 5 * n + m + 1
     p = m + 1 + n
-    params = _layout_params([('a', (n,), alpha), ('w_prev', (n,), np.zeros(n))])
+    specs = [('a', (n,), alpha), ('w_prev', (n,), np.zeros(n))]
+    if matrix_params:
+        specs += [('F', (n, m), F.flatten(order='F')), ('d_sqrt', (n,), d)]
+    params = _layout_params(specs)
     col_a, col_wp = params[0].col, params[1].col
-    n_theta = 2 * n + 1
+    col_F, col_d = (params[2].col, params[3].col) if matrix_params else (-1, -1)
+    n_theta = params[-1].col + params[-1].size + 1
     # ---- A x = b
     Ar, Ac, Av = [], [], []
+    Fent = {}                                      # (row, col) of A -> (i, j) of F
     for j in range(m):
         Ar.append(j); Ac.append(if_ + j); Av.append(1.0)
         for i in range(n):
-            if F[i, j] != 0:
-                Ar.append(j); Ac.append(iw + i); Av.append(-F[i, j])
+            if F[i, j] != 0 or matrix_params:
+                Ar.append(j); Ac.append(iw + i); Av.append(-F[i, j] if F[i, j] != 0 else 1.0)     # structural entry: any nonzero
+                Fent[(j, iw + i)] = (i, j)
     for i in range(n):
         Ar.append(m); Ac.append(iw + i); Av.append(1.0)
     for i in range(n):
@@ -480,7 +489,10 @@ def portfolio_socp(n=100, m=10, seed=1, k_tc=0.01, k_sh=0.05, Lmax=1.6, name=Non
     ge([(ir1, 1.0)], 1.0); ge([(ir1, -1.0)], 1.0)
     for j in range(m): ge([(if_ + j, 2.0 * sig[j])])
     ge([(ir2, 1.0)], 1.0); ge([(ir2, -1.0)], 1.0)
-    for i in range(n): ge([(iw + i, 2.0 * d[i])])
+    d_rows = {}
+    for i in range(n):
+        d_rows[(row, iw + i)] = i
+        ge([(iw + i, 2.0 * d[i])])
     mc = row
     G = sp.csc_matrix((Gv, (Gr, Gc)), shape=(mc, nv)); G.sort_indices()
     maps = {}
@@ -491,10 +503,23 @@ def portfolio_socp(n=100, m=10, seed=1, k_tc=0.01, k_sh=0.05, Lmax=1.6, name=Non
     maps['c'] = mb.csr()
     maps['d'] = sp.csr_matrix((1, n_theta))
     mbA = _MapBuilder(A.nnz, n_theta)
-    for k, v in enumerate(A.data): mbA.const(k, v)
+    Acols = np.repeat(np.arange(nv), np.diff(A.indptr))
+    for k, v in enumerate(A.data):
+        key = (int(A.indices[k]), int(Acols[k]))
+        if matrix_params and key in Fent:
+            i, j = Fent[key]
+            mbA.add(k, col_F + j * n + i, -1.0)            # A[j, w_i] = -F[i, j]
+        else:
+            mbA.const(k, v)
     maps['A'] = mbA.csr()
     mbG = _MapBuilder(G.nnz, n_theta)
-    for k, v in enumerate(G.data): mbG.const(k, v)
+    Gcols = np.repeat(np.arange(nv), np.diff(G.indptr))
+    for k, v in enumerate(G.data):
+        key = (int(G.indices[k]), int(Gcols[k]))
+        if matrix_params and key in d_rows:
+            mbG.add(k, col_d + d_rows[key], -2.0)           # G row of the second cone: -(2 d_i) w_i
+        else:
+            mbG.const(k, v)
     maps['G'] = mbG.csr()
     mbb = _MapBuilder(p, n_theta); mbb.const(m, 1.0)
     for i in range(n): mbb.add(m + 1 + i, col_wp + i, -1.0)
@@ -507,7 +532,7 @@ def portfolio_socp(n=100, m=10, seed=1, k_tc=0.01, k_sh=0.05, Lmax=1.6, name=Non
                  UserVar('f', (m,), if_ + np.arange(m))]
     duals = [UserDual('d0', 'y', (m,), np.arange(m)), UserDual('d1', 'y', (1,), np.array([m])),
              UserDual('d2', 'z', (1,), np.array([n_lp - 1])), UserDual('d3', 'y', (n,), m + 1 + np.arange(n))]
-    return CanonFamily(name or f'portfolio_socp_{n}_{m}', 'conic', nv, p, mc, params, maps,
+    return CanonFamily(name or (f'portfolio_socp_mat_{n}_{m}' if matrix_params else f'portfolio_socp_{n}_{m}'), 'conic', nv, p, mc, params, maps,
                        {'A': _csc_pattern(A), 'G': _csc_pattern(G)}, variables, duals, is_maximization=True,
                        cone_dims={'l': n_lp, 'q': [m + 2, n + 2]})
 

@@ -132,10 +132,11 @@ def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None
         raise ValueError('IPM-CUDA handles the conic canonical form only')
     if batch_params is None:
         batch_params = [p.name for p in fam.params if not (fam.changes('A', [p.name]) or fam.changes('G', [p.name]))]
+    mat_params = []
     for name in batch_params:
         fam.param(name)
         if fam.changes('A', [name]) or fam.changes('G', [name]):
-            raise ValueError(f'parameter {name} enters a canonical matrix; per-instance matrix updates are not generated yet')
+            mat_params.append(name)      # per-instance G / A values: the kernel canonicalises and EQUILIBRATES them itself (IPM_MATPAR)
     theta = fam.theta_default() if theta is None else np.asarray(theta, dtype=float)
     n, p, m = fam.n_var, fam.n_eq, fam.n_ineq
     l, q = int(fam.cone_dims.get('l', 0)), [int(d) for d in fam.cone_dims.get('q', [])]
@@ -152,7 +153,7 @@ def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None
     rows = np.r_[n + Ac.row, zoff + zmap[Gc.row]].astype(np.int64)
     cols = np.r_[Ac.col, Gc.col].astype(np.int64)
     vals = np.r_[Ac.data, Gc.data]
-    order = np.lexsort((cols, rows))
+    order = np.lexsort((cols, rows))           # (tocoo of a CSC matrix lists the stored entries in CSC order: index = data index)
     mr_t, mr_s, ag_val = rows[order], cols[order], vals[order]
     # ---- KKT pattern (k-space), ordering, levels
     pr = np.r_[np.arange(nk), mr_t, mr_s]; pc = np.r_[np.arange(nk), mr_s, mr_t]
@@ -205,8 +206,10 @@ def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None
     Sbase = np.zeros(NS)
     Sbase[DG0:DG0 + n] = DELTASTAT
     Sbase[DG0 + n:DG0 + n + p] = -DELTASTAT
-    for r, c_, v in zip(mr_t, mr_s, ag_val):
-        Sbase[kslot(int(r), int(c_))] += v
+    ag_slot = np.array([kslot(int(r), int(c_)) for r, c_ in zip(mr_t, mr_s)], dtype=np.int64)
+    assert len(np.unique(ag_slot)) == len(ag_slot)
+    if not mat_params:
+        Sbase[ag_slot] += ag_val               # (with per-instance matrices the kernel writes these slots from its own values)
     socv, socu = [], []
     for o, so, d in blocks:
         iv, iu = zoff + so + d, zoff + so + d + 1
@@ -248,6 +251,7 @@ def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None
     if p:
         scale_k[n:zoff] = 1.0 / Ae
     scale_k[zoff + zmap] = 1.0 / Ge
+    scale_cbh = np.ones(nk) if mat_params else scale_k      # per-instance matrices: c, b, h stay RAW, the kernel divides by its scalings
     krow = {'c': np.arange(n), 'b': n + np.arange(p), 'h': zoff + zmap}
     base = np.zeros(nk)
     mt_, mp_, mv_ = [], [], []
@@ -255,10 +259,21 @@ def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None
         Mp = fam.maps.get(pid)
         if Mp is None or Mp.shape[0] == 0:
             continue
-        base[krow[pid]] = np.asarray(Mp @ theta0).ravel() * scale_k[krow[pid]]
+        base[krow[pid]] = np.asarray(Mp @ theta0).ravel() * scale_cbh[krow[pid]]
         if npb:
             Mb = sp.coo_matrix(Mp[:, bcols])
-            mt_ += list(krow[pid][Mb.row]); mp_ += list(Mb.col); mv_ += list(Mb.data * scale_k[krow[pid]][Mb.row])
+            mt_ += list(krow[pid][Mb.row]); mp_ += list(Mb.col); mv_ += list(Mb.data * scale_cbh[krow[pid]][Mb.row])
+    # ---- per-instance matrix entries (IPM_MATPAR): RAW value of entry e of `ag` = ent_base[e] + sum emap_v * theta_b[emap_p]
+    ent_base = np.zeros(len(ag_val)); et_, ep_, ev_ = [], [], []
+    if mat_params:
+        nA = int(A.nnz) if p else 0
+        MA = sp.csr_matrix(fam.maps['A']) if p else sp.csr_matrix((0, len(theta)))
+        MG = sp.csr_matrix(fam.maps['G'])
+        assert MA.shape[0] == nA and MG.shape[0] == int(G.nnz), 'one row of the entry map per stored entry (CSC order)'
+        Mall = sp.vstack([MA, MG]).tocsr()[order]                   # rows in the order of `ag`
+        ent_base = np.asarray(Mall @ theta0).ravel()
+        Mb = sp.coo_matrix(Mall[:, bcols])
+        et_, ep_, ev_ = list(Mb.row), list(Mb.col), list(Mb.data)
     if 'd' in fam.maps and npb and fam.maps['d'][:, bcols].nnz:
         raise ValueError('objective offset d depending on a batched parameter is not generated yet')
     d_const = float(np.asarray(fam.maps['d'] @ theta).ravel()[0]) if 'd' in fam.maps else 0.0
@@ -325,12 +340,14 @@ def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None
              bw_t=np.array(bw_t, dtype=np.int64), bw_s=np.array(bw_s, dtype=np.int64), socv=np.array(socv, dtype=np.int64),
              socu=np.array(socu, dtype=np.int64), Sbase=Sbase, ops=ops[:, 1:], tail_k=perm[t0:], cbh_base=base,
              map_t=np.array(mt_, dtype=np.int64), map_p=np.array(mp_, dtype=np.int64), map_v=np.array(mv_, dtype=float),
-             unscale=unscale, prim_idx=prim_idx, dual_idx=dual_idx, perm=perm)
+             unscale=unscale, prim_idx=prim_idx, dual_idx=dual_idx, perm=perm,
+             ent_base=ent_base, emap_t=np.array(et_, dtype=np.int64), emap_p=np.array(ep_, dtype=np.int64),
+             emap_v=np.array(ev_, dtype=float), ag_slot=ag_slot)
     LR = dict(op_lo=op_lo, fw_lo=fw_lo, bw_lo=bw_lo, lev_lo=lev_lo)
     D = dict(N=n, P=p, M=m, L=l, NSOC=nsoc, MT=mt, NK=nk, ZOFF=zoff, NW=NW, DG0=DG0, TT0=TT0, NS=NS, NT=nt, NLW=nlw,
              NNZM=len(ag_val), NOPS=len(ops), NFW=len(fw), NPB=npb, NMAP=len(mv_), NPRIM=len(prim_idx),
              NDUAL=len(dual_idx), QTOT=sum(d - 1 for d in q), IS_MAX=int(fam.is_maximization), NNZA=int(A_eq.nnz),
-             THREADS=threads)
+             THREADS=threads, MATPAR=int(bool(mat_params)), NEMAP=len(ev_))
     st = SOCPSetup(family=fam, batch_params=list(batch_params), n=n, p=p, m=m, l=l, q=q, mt=mt, nk=nk, npb=npb, xe=xe,
                    Ae=Ae, Ge=Ge, A_eq=A_eq, G_eq=G_eq, perm=perm, pos_level=level, n_wide_levels=nlw, t0=t0, tables=T,
                    defines=D, level_ranges=LR, prim_idx=prim_idx, dual_idx=dual_idx,
@@ -385,8 +402,11 @@ def _pack(st: SOCPSetup, d_const: float):
     for nm, o in ho.items():
         D['H_' + nm.upper()] = o
     # global blob
-    go, g64 = cat([('Sbase', T['Sbase']), ('cbh_base', T['cbh_base']), ('unscale', T['unscale']), ('map_v', T['map_v'])], np.float64)
-    io, i32 = cat([('map_t', T['map_t']), ('map_p', T['map_p']), ('prim_idx', T['prim_idx']), ('dual_idx', T['dual_idx'])], np.int32)
+    go, g64 = cat([('Sbase', T['Sbase']), ('cbh_base', T['cbh_base']), ('unscale', T['unscale']), ('map_v', T['map_v']),
+                   ('ent_base', T['ent_base']), ('emap_v', T['emap_v'])], np.float64)
+    io, i32 = cat([('map_t', T['map_t']), ('map_p', T['map_p']), ('prim_idx', T['prim_idx']), ('dual_idx', T['dual_idx']),
+                   ('emap_t', T['emap_t']), ('emap_p', T['emap_p']), ('mr_t', T['mr_t']), ('mr_s', T['mr_s']),
+                   ('ag_slot', T['ag_slot'])], np.int32)
     gm = g64.tobytes()
     i32_off = len(gm)
     gm += i32.tobytes()

@@ -30,6 +30,10 @@ STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
     'osqp_update_matrices_5_8': (lambda: families.osqp_update_matrices_kat()[0], ['q', 'l', 'u', 'P', 'A']),   # OSQP's own KAT for matrix updates
     'nonneg_LS_3_2_A': (lambda: families.nonneg_ls(3, 2, name='nonneg_LS_3_2_A'), ['A', 'b']),   # README example, A per instance
     'portfolio_socp_100_10': (lambda: families.portfolio_socp(100, 10), ['a', 'w_prev']),   # BASELINE config 3 (IPM-CUDA)
+    # per-instance MATRIX parameters on the conic path: the factor loadings F (in A) and d_sqrt (in G) of the portfolio problem are
+    # user parameters in the reference's example (examples/portfolio.ipynb); the kernel re-equilibrates per instance
+    'portfolio_socp_mat_100_10': (lambda: families.portfolio_socp(100, 10, matrix_params=True), ['a', 'w_prev', 'F', 'd_sqrt']),
+    'portfolio_socp_mat_20_4': (lambda: families.portfolio_socp(20, 4, matrix_params=True), ['a', 'w_prev', 'F', 'd_sqrt']),
     # generic conic families (every vector batched): three cones + equalities, and a pure LP; exit flags 0 / 1 / 2
     'random_socp_30_8_20_3x5x4': (lambda: families.random_socp(30, 8, 20, (3, 5, 4), seed=5), ['c', 'b', 'h']),
     'random_socp_20_5_30_lp': (lambda: families.random_socp(20, 5, 30, (), seed=6), ['c', 'b', 'h']),

@@ -75,6 +75,34 @@ double ecos_ref_solve_batch(EcosRef* r, long B, const double* cb, const double* 
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
 
+/* The same with per-instance MATRIX values: Gb (B, nnzG), Ab (B, nnzA) in the CSC order of the templates, or NULL (= template).
+ * This is the reference's path when a user parameter enters G or A: cpg_copy_all + ECOS_updateData on the raw values, which
+ * re-equilibrates from scratch (cvxpygen/solvers/ecos.py:88-101, ecos/src/ecos.c:1648-1695, equil.c:210-342). */
+double ecos_ref_solve_batch_mat(EcosRef* r, long B, const double* cb, const double* hb, const double* bb,
+                                const double* Gb, const double* Ab,
+                                double* x, double* y, double* z, double* s,
+                                double* pcost, long* iter, long* exitflag, double* pres, double* dres) {
+  struct timespec t0, t1;
+  long k;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (k = 0; k < B; k++) {
+    memcpy(r->Gpr, Gb ? Gb + k * r->nnzG : r->Gpr0, sizeof(pfloat) * r->nnzG);
+    if (r->p) memcpy(r->Apr, Ab ? Ab + k * r->nnzA : r->Apr0, sizeof(pfloat) * r->nnzA);
+    memcpy(r->c, cb ? cb + k * r->n : r->c0, sizeof(pfloat) * r->n);
+    memcpy(r->h, hb ? hb + k * r->m : r->h0, sizeof(pfloat) * r->m);
+    if (r->p) memcpy(r->b, bb ? bb + k * r->p : r->b0, sizeof(pfloat) * r->p);
+    ECOS_updateData(r->w, r->Gpr, r->Apr, r->c, r->h, r->b);
+    exitflag[k] = ECOS_solve(r->w);
+    memcpy(x + k * r->n, r->w->x, sizeof(pfloat) * r->n);
+    if (r->p) memcpy(y + k * r->p, r->w->y, sizeof(pfloat) * r->p);
+    memcpy(z + k * r->m, r->w->z, sizeof(pfloat) * r->m);
+    memcpy(s + k * r->m, r->w->s, sizeof(pfloat) * r->m);
+    pcost[k] = r->w->info->pcost; iter[k] = r->w->info->iter; pres[k] = r->w->info->pres; dres[k] = r->w->info->dres;
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
 void ecos_ref_free(EcosRef* r) {
   if (!r) return;
   /* ECOS_cleanup frees only what setup allocated; the data arrays are ours */

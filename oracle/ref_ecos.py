@@ -35,13 +35,26 @@ class RefECOS:
         if not self.h_:
             raise RuntimeError('ECOS_setup failed')
 
-    def solve_batch(self, c=None, h=None, b=None, B=None):
-        for a in (c, h, b):
+    def solve_batch(self, c=None, h=None, b=None, B=None, G=None, A=None):
+        """c (B, n), h (B, m), b (B, p): per-instance vectors; G (B, nnz(G)), A (B, nnz(A)): per-instance matrix VALUES in the CSC order
+        of the matrices given to the constructor (the reference re-equilibrates on every ECOS_updateData)."""
+        for a in (c, h, b, G, A):
             if a is not None:
                 B = np.asarray(a).shape[0]
         B = B or 1
         D = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
-        c, h, b = D(c), D(h), D(b)
+        c, h, b, G, A = D(c), D(h), D(b), D(G), D(A)
+        if G is not None or A is not None:
+            assert G is None or G.shape == (B, len(self._keep[1])), 'G values: one row of nnz(G) per instance'
+            assert A is None or A.shape == (B, len(self._keep[4])), 'A values: one row of nnz(A) per instance'
+            self.lib.ecos_ref_solve_batch_mat.restype = C.c_double
+            x = np.zeros((B, self.n)); y = np.zeros((B, max(self.p, 1))); z = np.zeros((B, self.m)); s = np.zeros((B, self.m))
+            pc = np.zeros(B); pr = np.zeros(B); dr = np.zeros(B); it = np.zeros(B, np.int64); ef = np.zeros(B, np.int64)
+            pd = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+            pl = lambda a: a.ctypes.data_as(C.POINTER(C.c_long))
+            sec = self.lib.ecos_ref_solve_batch_mat(self.h_, C.c_long(B), pd(c), pd(h), pd(b), pd(G), pd(A), pd(x), pd(y), pd(z), pd(s),
+                                                    pd(pc), pl(it), pl(ef), pd(pr), pd(dr))
+            return dict(x=x, y=y[:, :self.p], z=z, s=s, pcost=pc, iter=it, exitflag=ef, pres=pr, dres=dr, seconds=sec)
         x = np.zeros((B, self.n)); y = np.zeros((B, max(self.p, 1))); z = np.zeros((B, self.m)); s = np.zeros((B, self.m))
         pc = np.zeros(B); pr = np.zeros(B); dr = np.zeros(B); it = np.zeros(B, np.int64); ef = np.zeros(B, np.int64)
         pd = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))

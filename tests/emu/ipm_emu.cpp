@@ -16,7 +16,7 @@ extern "C" int ipm_emu_solve(const unsigned char* sblob, const unsigned char* gb
   unsigned char* base = reinterpret_cast<unsigned char*>(raw.data());
   std::memcpy(reinterpret_cast<double*>(base) + O_AG, sblob, size_t(NNZM + 1) * 8);
   std::memcpy(reinterpret_cast<double*>(base) + O_F64_END, sblob + IPM_SB_U32_OFF, size_t(U32_COUNT) * 4 + size_t(U16_COUNT) * 2);
-  std::vector<double> best(NK + MT);
+  std::vector<double> best(BEST_STRIDE);
   Solver sv;
   sv.sm.base_ = base; sv.gm = make_gm(gblob); sv.rb = 0;
   sv.stg = IpmSettings{maxit, 0, 1e-8, 1e-8, 1e-8, 1e-4, 5e-5, 5e-5};

@@ -17,7 +17,7 @@ extern "C" int ipm_simt_solve(const unsigned char* sblob, const unsigned char* g
                               double* obj, int* iter, int* status, double* pres, double* dres, int maxit, int grid) {
   using namespace cpgipm;
   static_assert(SMEM_BYTES <= 256 * 1024, "emulated shared memory too small");
-  std::vector<double> best(size_t(grid) * (NK + MT));
+  std::vector<double> best(size_t(grid) * BEST_STRIDE);
   int counter = 0;
   IpmSettings stg{maxit, 0, 1e-8, 1e-8, 1e-8, 1e-4, 5e-5, 5e-5};
   IpmIO io{B, params, prim, dual, x, y, z, s, obj, iter, status, pres, dres, best.data(), &counter};

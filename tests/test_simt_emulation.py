@@ -9,6 +9,7 @@ is thereby checked against the oracle in the CPU-only suite, before any GPU time
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -396,3 +397,25 @@ def test_interior_point_kernel_is_schedule_independent(tmp_path):
         base = base or cur
         assert cur == base, f'schedule {mode} changes the result'
     lib.ipm_simt_set_schedule(0)
+
+
+def test_interior_point_matrix_parameters_on_the_emulator(tmp_path):
+    """Device code path of ipm_kernel with per-instance G / A values (IPM_MATPAR): entries from the parameter row, three
+    equilibration passes (atomic maxima on shared memory, cone sums on one thread), K rebuilt from the instance's entries every
+    iteration, output scalings in the CTA's scratch -- against ECOS_updateData + ECOS_solve of the compiled reference."""
+    from cvxpygen_b200.offline import socp_setup as ss
+    from oracle import ref_ecos
+    if not ref_ecos.available():
+        pytest.skip('oracle/_ref/libecos_ref.so not built')
+    sys.path.insert(0, HERE)
+    from test_socp_ipm import _portfolio_mat_batch, _conic_reference_mat
+    fam = families.portfolio_socp(12, 3, matrix_params=True)
+    names = ['a', 'w_prev', 'F', 'd_sqrt']
+    st = ss.setup_socp_family(fam, names)
+    lib = _build_ipm_simt(st, str(tmp_path))
+    B = 3
+    params = _portfolio_mat_batch(fam, B, seed=2)
+    out = _ipm_simt_solve(lib, st, np.concatenate([params[k] for k in names], axis=1), grid=2)
+    ref = _conic_reference_mat(fam, params, B)
+    assert np.array_equal(out['status'], ref['exitflag']) and np.array_equal(out['iter'], ref['iter'])
+    assert np.abs(out['x'] - ref['x']).max() < 1e-7 * np.abs(ref['x']).max()

@@ -596,3 +596,87 @@ def test_gpu_shared_parameter_update(tmp_path):
         m.update_shared_params({'c': par['c'][0]})                # batched parameters go through solve_batch
     with pytest.raises(AttributeError):
         m.update_shared_params({'nope': 1.0})
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# per-instance MATRIX parameters on the conic path (VERDICT r1 missing item 4): F enters A, d_sqrt enters G
+def _portfolio_mat_batch(fam, B, seed=3):
+    rng = np.random.default_rng(seed)
+    a = fam.param('a').default[None, :] + 0.3 * rng.standard_normal((B, fam.param('a').size))
+    wp = np.abs(rng.standard_normal((B, fam.param('w_prev').size))); wp /= wp.sum(1, keepdims=True)
+    F = fam.param('F').default[None, :] + 0.25 * rng.standard_normal((B, fam.param('F').size))       # every entry moves (zeros too)
+    d = fam.param('d_sqrt').default[None, :] * rng.uniform(0.5, 1.5, (B, fam.param('d_sqrt').size))
+    return dict(a=a, w_prev=wp, F=F, d_sqrt=d)
+
+
+def _conic_reference_mat(fam, params, B, **kw):
+    """Compiled ECOS driven like the reference's generated code when G / A are outdated: raw values + ECOS_updateData per instance."""
+    th = np.tile(fam.theta_default(), (B, 1))
+    for pn, v in params.items():
+        p = fam.param(pn)
+        th[:, p.col:p.col + p.size] = v
+    data = {k: np.asarray(th @ fam.maps[k].T.toarray()) for k in ('c', 'b', 'h', 'A', 'G')}
+    r = ref_ecos.RefECOS(fam.canon_data('c'), fam.canon_matrix('A'), fam.canon_data('b'), fam.canon_matrix('G'), fam.canon_data('h'),
+                         fam.cone_dims['l'], fam.cone_dims['q'], **kw)
+    return r.solve_batch(c=data['c'], b=data['b'], h=data['h'], G=data['G'], A=data['A'])
+
+
+@pytest.mark.skipif(not ref_ecos.available(), reason='oracle/_ref/libecos_ref.so not built')
+def test_conic_matrix_parameters_on_host_match_compiled_reference(tmp_path):
+    """F (in A) and d_sqrt (in G) per instance: the kernel canonicalises the entries, re-equilibrates them (three Ruiz passes with
+    exact maxima), rebuilds K from them and un-scales with its own scalings -- against ECOS_updateData + ECOS_solve of the compiled
+    reference on the same raw values: identical exit flags and iteration counts."""
+    fam = families.portfolio_socp(20, 4, matrix_params=True)
+    names = ['a', 'w_prev', 'F', 'd_sqrt']
+    st = ss.setup_socp_family(fam, names)
+    assert st.defines['MATPAR'] == 1 and st.defines['NEMAP'] == 20 * 4 + 20
+    lib = _build_emu(st, str(tmp_path))
+    B = 12
+    params = _portfolio_mat_batch(fam, B)
+    P = np.concatenate([params[nm] for nm in names], axis=1)
+    out = _emu_solve(lib, st, P)
+    ref = _conic_reference_mat(fam, params, B)
+    assert (ref['exitflag'] == 0).all()
+    assert np.array_equal(out['status'], ref['exitflag']) and np.array_equal(out['iter'], ref['iter'])
+    for k in range(B):
+        assert _rel(out['x'][k], ref['x'][k]) < RTOL_PRIMAL and _rel(out['s'][k], ref['s'][k]) < RTOL_PRIMAL, k
+        assert _rel(out['y'][k], ref['y'][k]) < RTOL_DUAL and _rel(out['z'][k], ref['z'][k]) < RTOL_DUAL, k
+    # default matrix values reproduce the shared-matrix family's solutions
+    fam0 = families.portfolio_socp(20, 4)
+    st0 = ss.setup_socp_family(fam0, ['a', 'w_prev'])
+    lib0 = _build_emu(st0, str(tmp_path / 'shared') if os.makedirs(str(tmp_path / 'shared'), exist_ok=True) is None else None)
+    P0 = np.concatenate([params['a'], params['w_prev']], axis=1)
+    Pd = np.concatenate([params['a'], params['w_prev'], np.tile(fam.param('F').default, (B, 1)), np.tile(fam.param('d_sqrt').default, (B, 1))], axis=1)
+    o0, od = _emu_solve(lib0, st0, P0), _emu_solve(lib, st, Pd)
+    assert np.array_equal(o0['iter'], od['iter']) and np.abs(o0['x'] - od['x']).max() < 1e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,B', [('portfolio_socp_mat_20_4', 256), ('portfolio_socp_mat_100_10', 96)])
+def test_gpu_conic_matrix_parameters(name, B):
+    """Per-instance G / A values on the GPU (ipm_kernel, IPM_MATPAR) against the compiled reference driven through ECOS_updateData
+    with the same raw values: identical exit flags and iteration counts, user-level primal / dual at the parity bar; bitwise
+    reproducible (the equilibration's maxima are exact, every sum has a fixed order)."""
+    import time
+    fam = standard.STANDARD[name][0]()
+    names = standard.STANDARD[name][1]
+    mod = standard.load(name)
+    params = _portfolio_mat_batch(fam, B, seed=11)
+    res = mod.solve_batch(params, return_canonical=True)
+    ref = _conic_reference_mat(fam, params, B)
+    assert (ref['exitflag'] == 0).all()
+    assert np.array_equal(res.cpg_info.status, ref['exitflag']) and np.array_equal(res.cpg_info.iter, ref['iter'])
+    for k in range(B):
+        assert _rel(res.sol_x[k], ref['x'][k]) < RTOL_PRIMAL and _rel(res.sol_s[k], ref['s'][k]) < RTOL_PRIMAL, k
+        assert _rel(res.sol_y[k], ref['y'][k]) < RTOL_DUAL and _rel(res.sol_z[k], ref['z'][k]) < RTOL_DUAL, k
+    prim_ref = np.concatenate([ref['x'][:, v.indices] for v in fam.variables], axis=1)
+    assert np.abs(res.prim - prim_ref).max() < 1e-6 * max(1.0, np.abs(prim_ref).max())
+    again = mod.solve_batch(params, return_canonical=True)
+    assert np.array_equal(again.sol_x, res.sol_x) and np.array_equal(again.sol_z, res.sol_z)
+    if name.endswith('100_10'):
+        Bt = 4096
+        pt = _portfolio_mat_batch(fam, Bt, seed=12)
+        mod.solve_batch(pt)
+        t0 = time.perf_counter(); r2 = mod.solve_batch(pt); dt = time.perf_counter() - t0
+        print(f'\n{name}: {Bt} instances in {dt * 1e3:.1f} ms (host call) = {Bt / dt:.0f} inst/s, mean iter {r2.cpg_info.iter.mean():.2f}, '
+              f'optimal {float((r2.cpg_info.status == 0).mean()):.4f}')
