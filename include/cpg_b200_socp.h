@@ -11,6 +11,11 @@
  *     cpg_retrieve_prim / cpg_retrieve_dual / cpg_retrieve_info                cvxpygen/utils.py:950-985
  * and the settings table  feastol, abstol, reltol, feastol_inacc, abstol_inacc, reltol_inacc, maxit
  * (cvxpygen/solvers/ecos.py:60-68).
+ *
+ * A batched user parameter may enter c, b, h AND the matrices G, A: a library generated with such a parameter in `batch_params`
+ * canonicalises every instance's G / A values from its parameter row and does what ECOS_updateData does with new values --
+ * set_equilibration from scratch (ecos/src/equil.c:210-342) -- inside the kernel; nothing changes in this interface (the rows
+ * of `params` are simply longer: matrix parameters in column-major order, like cvxpy's).
  */
 #ifndef CPG_B200_SOCP_H
 #define CPG_B200_SOCP_H
