@@ -427,7 +427,66 @@ class SocpWorkload(Workload):
                 'status_equal_frac': float((res.cpg_info.status == ora['exitflag']).mean())}
 
 
-WORKLOADS = {w.key: w for w in (MpcWorkload(), SocpWorkload(), GradWorkload(), LtvWorkload())}
+class SocpMatWorkload(SocpWorkload):
+    """Config 3's problem with the reference example's MATRIX parameters batched too: F (in A) and d_sqrt (in G) per instance."""
+    key, family, kernel = 'portfolio_socp_mat', 'portfolio_socp_mat_100_10', 'ipm_kernel'
+    metric = 'SOCP instances/sec (portfolio n=100 assets, per-instance F and d_sqrt)'
+    default_batch, cpu_sample, ref_sample, parity_sample, sub_steps = 20000, 2048, 2048, 2048, 3
+    note = ('ipm_kernel with IPM_MATPAR: per instance the G / A entries are canonicalised, re-equilibrated (ECOS set_equilibration) and '
+            'written into the KKT image inside the kernel; 10.4 KB of parameters per instance in')
+
+    def describe(self, B):
+        return ('portfolio SOCP (n=100 assets, 10 factors) with per-instance factor loadings F (100x10, in A) and d_sqrt (in G), '
+                'batch=%d per GPU, IPM-CUDA backend, ECOS default settings (tol 1e-8)' % B)
+
+    def _fam(self):
+        from cvxpygen_b200 import families
+        return families.portfolio_socp(100, 10, matrix_params=True)
+
+    def host_params(self, B, seed):
+        fam = self._fam()
+        rng = np.random.default_rng(5 + seed)
+        a = rng.standard_normal((B, 100))
+        wp = np.abs(1 / 100 + 0.01 * rng.standard_normal((B, 100)))
+        F = fam.param('F').default[None, :] + 0.25 * rng.standard_normal((B, 1000))
+        d = fam.param('d_sqrt').default[None, :] * rng.uniform(0.5, 1.5, (B, 100))
+        return np.ascontiguousarray(np.c_[a, wp, F, d])
+
+    def bytes_per_instance(self, d):
+        return 1300 * 8 + (210 + 112) * 8 + 40
+
+    def reference(self, P_host, threads):
+        """vendored ECOS 2.0.8: raw G / A / c / b / h of every instance through ECOS_updateData (re-equilibration) + ECOS_solve"""
+        import concurrent.futures as cf
+        from oracle import ref_ecos
+        if not ref_ecos.available():
+            raise RuntimeError('oracle/_ref/libecos_ref.so missing (run `make -C oracle ref` where /root/reference exists)')
+        fam = self._fam()
+        n = P_host.shape[0]
+        th = np.tile(fam.theta_default(), (n, 1))
+        col = 0
+        for nm in ('a', 'w_prev', 'F', 'd_sqrt'):
+            p_ = fam.param(nm)
+            th[:, p_.col:p_.col + p_.size] = P_host[:, col:col + p_.size]; col += p_.size
+        data = {k: np.asarray((fam.maps[k] @ th.T).T) for k in ('c', 'b', 'h', 'A', 'G')}
+        nw = max(1, min(threads, n))
+        refs = [ref_ecos.RefECOS(fam.canon_data('c'), fam.canon_matrix('A'), fam.canon_data('b'), fam.canon_matrix('G'),
+                                 fam.canon_data('h'), 601, [12, 102]) for _ in range(nw)]
+        sl = [slice(k * n // nw, (k + 1) * n // nw) for k in range(nw)]
+        t0 = time.perf_counter()
+        with cf.ThreadPoolExecutor(nw) as ex:
+            parts = list(ex.map(lambda k: refs[k].solve_batch(c=data['c'][sl[k]], b=data['b'][sl[k]], h=data['h'][sl[k]],
+                                                              G=data['G'][sl[k]], A=data['A'][sl[k]]), range(nw)))
+        sec = time.perf_counter() - t0
+        out = {k: np.concatenate([p_[k] for p_ in parts]) for k in ('x', 'y', 'z', 's', 'iter', 'exitflag', 'pcost')}
+        out['seconds'] = sec
+        return fam, out
+
+    def reference_note(self, cores):
+        return f'vendored ECOS 2.0.8 (oracle/_ref), {cores} host threads, per-instance G / A values: ECOS_updateData (re-equilibration) + ECOS_solve'
+
+
+WORKLOADS = {w.key: w for w in (MpcWorkload(), SocpWorkload(), GradWorkload(), LtvWorkload(), SocpMatWorkload())}
 
 
 # =====================================================================================================================
@@ -580,7 +639,7 @@ def main():
     cores = os.cpu_count() or 1
     head = WORKLOADS[args.workload]
     B = args.batch or head.default_batch
-    others = [] if (args.no_workloads or args.workload != 'mpc') else [WORKLOADS[k] for k in ('portfolio_socp', 'mpc_grad', 'mpc_ltv')]
+    others = [] if (args.no_workloads or args.workload != 'mpc') else [WORKLOADS[k] for k in ('portfolio_socp', 'mpc_grad', 'mpc_ltv', 'portfolio_socp_mat')]
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
     if args.impl == 'reference':
@@ -608,7 +667,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     from cvxpygen_b200 import standard
     # e(multi-GPU): the only collective of the path -- one NCCL broadcast of the family constants blob
-    if world > 1 and head.key != 'portfolio_socp':
+    if world > 1 and not head.key.startswith('portfolio_socp'):
         mod = standard.load(head.family, device=local_rank).init()
         blob = open(os.path.join(standard.code_dir(head.family), 'cpg_blob.bin'), 'rb').read()
         tb = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
