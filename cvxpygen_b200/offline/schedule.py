@@ -284,7 +284,7 @@ def build_schedule(F: LDLFactor, max_group_rows: int = 64, allow_trailing: bool 
 # profiles/r2_multi_v8_ncu_summary.md): a coefficient LDS.64 is 2 wavefronts, a broadcast LDS.128 of the operand pair is 2 (not 1),
 # a 16-byte gather is 4 plus its bank conflicts, the packed index word 0.5.  (Round 1 assumed 9 / 3, which encoded four tiles of
 # the MPC schedule dense although their gather form is cheaper: 1 760 -> 1 618 modelled wavefronts per solve.)
-SPARSE_STEP_WF = 6.5
+SPARSE_STEP_WF = float(__import__('os').environ.get('CPG_SPARSE_WF', 6.5))      # (environment overrides: A/B sweeps only)
 DENSE_STEP_WF = 4.0
 DENSE_SEG_OVERHEAD = 0.5
 
