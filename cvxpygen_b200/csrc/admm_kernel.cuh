@@ -141,11 +141,20 @@ __device__ __forceinline__ TailView make_tail_view(const uint8_t* blob) {
   return tv;
 }
 
-// CPG_TAIL_GATHER_FACTOR = 1 selects the owner-writes (atomics-free, deterministic) form of the update phase; the default is
-// the push form with shared-memory atomicAdd(double).  Both are checked on the SIMT emulator (tests/test_simt_emulation.py);
-// the gather form has not been timed on the GPU yet, which is why it is not the default.
-#ifndef CPG_TAIL_GATHER_FACTOR
-#define CPG_TAIL_GATHER_FACTOR 0
+// Forms of the factorisation's update phase (all checked on the SIMT emulator, tests/test_simt_emulation.py):
+//   CPG_TAIL_FACTOR_FORM 2 (default)  COLOURED ROUNDS: the ops of a level are dealt offline to rounds of 32 with pairwise distinct
+//       targets (offline/refactor.py: greedy, reaches ceil(ops / 32) rounds on the MPC families); a round is a plain read-modify-
+//       write per lane + __syncwarp -- no atomics, one fixed order per target (bit-reproducible), balanced lanes;
+//   0  push form with shared-memory atomicAdd(double) -- a CAS loop on sm_100 (13 % of the matrix-parameter kernel's samples,
+//       profiles/r2_matpar_v7_ncu_summary.md), run-to-run differences in the last bits;
+//   1  owner-writes: a target's ops summed by ONE lane (deterministic, but unbalanced: measured 1 - 8 % slower than the atomics,
+//       profiles/r2_tail_gather_factor_ab.jsonl).  (CPG_TAIL_GATHER_FACTOR=1 is the older spelling of form 1.)
+#ifndef CPG_TAIL_FACTOR_FORM
+#if defined(CPG_TAIL_GATHER_FACTOR) && CPG_TAIL_GATHER_FACTOR
+#define CPG_TAIL_FACTOR_FORM 1
+#else
+#define CPG_TAIL_FACTOR_FORM 2
+#endif
 #endif
 // Numeric factorisation of K(rho_vec) on the family's symbolic pattern (role of QDLDL_factor, qdldl.c:72-233,
 // after update_KKT_param2, kkt.c:214-222).  S holds K's lower triangle in slot order with -1/rho_vec already
@@ -153,20 +162,42 @@ __device__ __forceinline__ TailView make_tail_view(const uint8_t* blob) {
 __device__ __forceinline__ void tail_factor(const TailView& tv, double* S, int lane) {
   const int nl = tv.H->n_levels;
   const int* lp = tv.I32 + tv.H->i_level_ptr;
-  const int* op = tv.I32 + tv.H->i_op_ptr;
   const int* sp = tv.I32 + tv.H->i_scale_ptr;
   const uint16_t* lc = tv.U16 + tv.H->h_level_cols;
-  const ushort4* ops = reinterpret_cast<const ushort4*>(tv.U16 + tv.H->h_ops);
   const ushort2* scl = reinterpret_cast<const ushort2*>(tv.U16 + tv.H->h_scale);
-#if CPG_TAIL_GATHER_FACTOR
+#if CPG_TAIL_FACTOR_FORM == 2
+  const int* lg = tv.I32 + tv.H->i_clevel_group;
+  const int* gp = tv.I32 + tv.H->i_cgroup_ptr;
+  const ushort4* cops = reinterpret_cast<const ushort4*>(tv.U16 + tv.H->h_cops) + lane;
+#elif CPG_TAIL_FACTOR_FORM == 1
   const int* gtp = tv.I32 + tv.H->i_gtgt_ptr;
   const int* gsg = tv.I32 + tv.H->i_gseg;
   const ushort4* gops = reinterpret_cast<const ushort4*>(tv.U16 + tv.H->h_gops);
+#else
+  const int* op = tv.I32 + tv.H->i_op_ptr;
+  const ushort4* ops = reinterpret_cast<const ushort4*>(tv.U16 + tv.H->h_ops);
 #endif
   for (int lv = 0; lv < nl; ++lv) {
     for (int c = lp[lv] + lane; c < lp[lv + 1]; c += LANES) { const int j = lc[c]; S[j] = 1.0 / S[j]; }
     __syncwarp();
-#if CPG_TAIL_GATHER_FACTOR
+#if CPG_TAIL_FACTOR_FORM == 2
+    // rounds of one SYNC GROUP touch pairwise distinct targets: no barrier between them, so their table words and operands are in
+    // flight together (a level that eliminates one column is a single group)
+    for (int g = lg[lv]; g < lg[lv + 1]; ++g) {
+      const int r1 = gp[g + 1];
+      int r = gp[g];
+      for (; r + 3 < r1; r += 4) {
+        const ushort4 q0 = __ldg(cops + (size_t)r * LANES), q1 = __ldg(cops + (size_t)(r + 1) * LANES);
+        const ushort4 q2 = __ldg(cops + (size_t)(r + 2) * LANES), q3 = __ldg(cops + (size_t)(r + 3) * LANES);
+        const double u0 = S[q0.y] * S[q0.z] * S[q0.w], u1 = S[q1.y] * S[q1.z] * S[q1.w];
+        const double u2 = S[q2.y] * S[q2.z] * S[q2.w], u3 = S[q3.y] * S[q3.z] * S[q3.w];
+        // the zero slot is the only target that may repeat inside a group (padding): it only ever receives 0 - 0
+        S[q0.x] -= u0; S[q1.x] -= u1; S[q2.x] -= u2; S[q3.x] -= u3;
+      }
+      for (; r < r1; ++r) { const ushort4 q = __ldg(cops + (size_t)r * LANES); S[q.x] -= S[q.y] * S[q.z] * S[q.w]; }
+      __syncwarp();
+    }
+#elif CPG_TAIL_FACTOR_FORM == 1
     // owner-writes form: a target's ops are contiguous and summed by ONE lane in table order (no atomics, deterministic)
     for (int ti = gtp[lv] + lane; ti < gtp[lv + 1]; ti += LANES) {
       const int o0 = __ldg(gsg + ti), o1 = __ldg(gsg + ti + 1);
@@ -175,13 +206,14 @@ __device__ __forceinline__ void tail_factor(const TailView& tv, double* S, int l
       for (int o = o0 + 1; o < o1; ++o) { q = __ldg(gops + o); acc += S[q.y] * S[q.z] * S[q.w]; }
       S[q.x] -= acc;
     }
+    __syncwarp();
 #else
     for (int o = op[lv] + lane; o < op[lv + 1]; o += LANES) {
       const ushort4 q = __ldg(ops + o);
       atomicAdd(&S[q.x], -(S[q.y] * S[q.z] * S[q.w]));
     }
-#endif
     __syncwarp();
+#endif
     for (int o = sp[lv] + lane; o < sp[lv + 1]; o += LANES) { const ushort2 q = __ldg(scl + o); S[q.x] *= S[q.y]; }
     __syncwarp();
   }
@@ -465,9 +497,17 @@ __device__ __forceinline__ double ellx_absmax(const int* __restrict__ tab, const
                                               const double* vals, int lane) {
   const int K = __ldg(tab);
   const uint16_t* ix = U16 + __ldg(tab + 1) + lane;
-  double a = 0.0;
-  for (int k = 0; k < K; ++k) a = fmax(a, fabs(vals[__ldg(ix + k * LANES)]));
-  return a;
+  // index and value both sit behind an L2 latency (the entries of A live in the warp's global scratch slice): four independent
+  // chains in flight; a maximum does not depend on the order
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int k = 0;
+  for (; k + 3 < K; k += 4) {
+    const int i0 = __ldg(ix + k * LANES), i1 = __ldg(ix + (k + 1) * LANES), i2 = __ldg(ix + (k + 2) * LANES), i3 = __ldg(ix + (k + 3) * LANES);
+    const double v0 = vals[i0], v1 = vals[i1], v2 = vals[i2], v3 = vals[i3];
+    a0 = fmax(a0, fabs(v0)); a1 = fmax(a1, fabs(v1)); a2 = fmax(a2, fabs(v2)); a3 = fmax(a3, fabs(v3));
+  }
+  for (; k < K; ++k) a0 = fmax(a0, fabs(vals[__ldg(ix + k * LANES)]));
+  return fmax(fmax(a0, a1), fmax(a2, a3));
 }
 
 struct TailArgs {

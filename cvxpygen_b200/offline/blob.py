@@ -235,6 +235,7 @@ TAIL_HEADER_FIELDS: List[Tuple[str, str]] = [
     ('int', 'i_level_ptr'), ('int', 'i_op_ptr'), ('int', 'i_scale_ptr'), ('int', 'i_tiles'),
     ('int', 'f_S0'), ('int', 'h_rho_slot'), ('int', 'h_level_cols'), ('int', 'h_ops'),
     ('int', 'h_scale'), ('int', 'i_gtgt_ptr'), ('int', 'i_gseg'), ('int', 'h_gops'),     # owner-writes form of the update ops
+    ('int', 'i_cround_ptr'), ('int', 'h_cops'), ('int', 'i_cgroup_ptr'), ('int', 'i_clevel_group'),     # coloured-rounds form
 ]
 
 
@@ -265,6 +266,11 @@ def pack_tail_blob(T) -> bytes:
     hv['i_gseg'] = ar.add_i32(T.g_seg)
     align_u16(4)
     hv['h_gops'] = ar.add_u16(T.g_ops)
+    hv['i_cround_ptr'] = ar.add_i32(T.c_round_ptr)
+    hv['i_cgroup_ptr'] = ar.add_i32(T.c_group_ptr)
+    hv['i_clevel_group'] = ar.add_i32(T.c_level_group)
+    align_u16(4)
+    hv['h_cops'] = ar.add_u16(T.c_ops)
     # tile header (8 ints): [i32 offset of the packed entries (slot | position << 16, lane-interleaved), 0, K, r_pad, rows,
     #                        u16 offset of the row list, inside: u16 offset of the slot table | first slot of the packed triangle,
     #                        0 no couplings inside / 1 slot table / 2 packed triangle]

@@ -69,6 +69,13 @@ class RefactorTables:
     g_tgt_ptr: np.ndarray = None  # (n_levels+1,) into the target list
     g_seg: np.ndarray = None      # (n_targets+1,) first op of every target
     g_ops: np.ndarray = None      # (n_ops, 4): t, a, b, j -- the ops of `ops`, level by level, grouped by target
+    # "coloured rounds" form: per level the ops dealt to rounds of 32 with pairwise DISTINCT targets (padded with a no-op on the zero
+    # slot), so a warp applies a round with plain read-modify-writes and one __syncwarp: no atomics, a fixed order per target
+    # (bit-reproducible), lanes balanced.  Kernel path: tail_factor, CPG_TAIL_FACTOR_FORM = 2 (default).
+    c_round_ptr: np.ndarray = None   # (n_levels+1,) first round of every level
+    c_ops: np.ndarray = None         # (n_rounds * 32, 4): t, a, b, j
+    c_group_ptr: np.ndarray = None   # sync groups: rounds between two warp barriers (no target twice inside a group)
+    c_level_group: np.ndarray = None  # (n_levels+1,) first group of every level
 
     def slot_of(self, i: int, j: int) -> int:
         if i == j:
@@ -262,7 +269,37 @@ def build_refactor_tables(F: LDLFactor, K: sp.csc_matrix, n_var: int) -> Refacto
         g_tgt_ptr.append(len(g_seg) - 1)
     g_ops = np.concatenate(g_ops).reshape(-1, 4) if g_ops else np.zeros((0, 4), dtype=np.int64)
     assert len(g_ops) == len(ops_arr)
+    c_round_ptr, c_ops = [0], []
+    c_group_ptr, c_level_group = [0], [0]       # group g = rounds c_group_ptr[g] .. c_group_ptr[g+1]; level lv = groups c_level_group[lv] .. [lv+1]
+    zs = n_slots - 1
+    for lv in range(n_levels):
+        o = ops_arr[op_ptr[lv]:op_ptr[lv + 1]]
+        rounds, first_open = [], 0                      # [set of targets, list of ops]
+        for op in o:
+            t = int(op[0])
+            for r in range(first_open, len(rounds)):
+                if len(rounds[r][1]) < LANES and t not in rounds[r][0]:
+                    rounds[r][0].add(t); rounds[r][1].append(op); break
+            else:
+                rounds.append([{t}, [op]])
+            while first_open < len(rounds) and len(rounds[first_open][1]) >= LANES:
+                first_open += 1
+        # rounds whose targets are all new since the last barrier need none between them: SYNC GROUPS (a level that eliminates one
+        # column -- the chain of the MPC families -- is a single group: its targets are pairwise distinct)
+        seen = set()
+        for tg, lst in rounds:
+            if seen & tg:
+                c_group_ptr.append(len(c_ops) // LANES); seen = set()
+            seen |= tg
+            c_ops += [tuple(int(v) for v in op) for op in lst] + [(zs, zs, zs, zs)] * (LANES - len(lst))
+        c_round_ptr.append(c_round_ptr[-1] + len(rounds))
+        if len(rounds):
+            c_group_ptr.append(len(c_ops) // LANES)
+        c_level_group.append(len(c_group_ptr) - 1)
+    c_ops = np.asarray(c_ops, dtype=np.int64).reshape(-1, 4)
     return RefactorTables(g_tgt_ptr=np.asarray(g_tgt_ptr), g_seg=np.asarray(g_seg), g_ops=g_ops,
+                          c_round_ptr=np.asarray(c_round_ptr), c_ops=c_ops,
+                          c_group_ptr=np.asarray(c_group_ptr), c_level_group=np.asarray(c_level_group),
                           nk=nk, n_slots=n_slots, S0=S0, rho_slot=rho_slot.astype(np.int64),
                           level_ptr=np.asarray(level_ptr), level_cols=np.asarray(level_cols),
                           op_ptr=np.asarray(op_ptr), ops=np.asarray(ops, dtype=np.int64).reshape(-1, 4),
@@ -344,3 +381,21 @@ def emulate_solve(T: RefactorTables, S: np.ndarray, w: np.ndarray) -> np.ndarray
     for t in T.bwd_tiles:
         run(t, False)
     return w
+
+
+def emulate_factor_coloured(T: RefactorTables, rho_vec: np.ndarray) -> np.ndarray:
+    """The coloured-rounds form (tail_factor, CPG_TAIL_FACTOR_FORM = 2): rounds of 32 ops with pairwise distinct targets."""
+    S = T.S0.copy()
+    S[T.rho_slot] = -1.0 / rho_vec
+    for lv in range(len(T.level_ptr) - 1):
+        cols = T.level_cols[T.level_ptr[lv]:T.level_ptr[lv + 1]]
+        S[cols] = 1.0 / S[cols]
+        for g in range(T.c_level_group[lv], T.c_level_group[lv + 1]):
+            o = T.c_ops[T.c_group_ptr[g] * LANES:T.c_group_ptr[g + 1] * LANES]
+            real = o[:, 0] != T.zero_slot
+            assert len(np.unique(o[real, 0])) == real.sum()                 # distinct targets inside a sync group
+            S[o[:, 0]] = S[o[:, 0]] - S[o[:, 1]] * S[o[:, 2]] * S[o[:, 3]]      # plain read-modify-writes, the whole group at once
+        sc = T.scale[T.scale_ptr[lv]:T.scale_ptr[lv + 1]]
+        if len(sc):
+            S[sc[:, 0]] *= S[sc[:, 1]]
+    return S

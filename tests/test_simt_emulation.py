@@ -296,13 +296,14 @@ def test_results_do_not_depend_on_the_thread_schedule(tmp_path):
     lib.emu_set_schedule(0)
 
 
-def test_gather_form_factorisation_is_deterministic(tmp_path):
-    """tail_factor under CPG_TAIL_GATHER_FACTOR (owner-writes update phase, no atomics; not the default build until it has
-    been timed on the GPU): same answers as the reference, and -- with no atomic left on the path -- bit-identical results
-    under every thread schedule, for the solve and for the backward pass."""
+@pytest.mark.parametrize('form', [2, 1])
+def test_atomics_free_factorisation_is_deterministic(form, tmp_path):
+    """tail_factor without atomics -- form 2, the default: coloured rounds (32 ops with pairwise distinct targets per round, plain
+    read-modify-writes); form 1: owner-writes (one lane sums a target's ops) -- gives the reference's answers and, with no atomic
+    left on the path, bit-identical results under every thread schedule, for the solve and for the backward pass."""
     fam = families.mpc_ltv(4, 2, 5)
     batch = ['A', 'B', 'qdiag', 'rdiag', 'x_init']
-    st, lib, dims = build_emu(fam, batch, str(tmp_path), flags=('-DCPG_TAIL_GATHER_FACTOR=1',))
+    st, lib, dims = build_emu(fam, batch, str(tmp_path), flags=(f'-DCPG_TAIL_FACTOR_FORM={form}',))
     B = 6
     params = families.mpc_ltv_batch(fam, B, seed=33)
     rows = _rows(fam, st, params, B)
@@ -325,8 +326,10 @@ def test_gather_form_factorisation_is_deterministic(tmp_path):
     # the tables themselves: owner-writes == push form up to rounding
     from cvxpygen_b200.offline import kkt, refactor
     rv = kkt.rho_vector(st.ctype, 0.37)
-    a, b = refactor.emulate_factor(st.refactor, rv), refactor.emulate_factor_gather(st.refactor, rv)
-    assert np.abs(a - b).max() < 1e-13 * np.abs(a).max()
+    a, b, c = (f(st.refactor, rv) for f in (refactor.emulate_factor, refactor.emulate_factor_gather, refactor.emulate_factor_coloured))
+    assert np.abs(a - b).max() < 1e-13 * np.abs(a).max() and np.abs(a - c).max() < 1e-13 * np.abs(a).max()
+    nr = st.refactor.c_round_ptr[-1]
+    assert nr * 32 >= len(st.refactor.ops) and nr <= sum(-(-(b_ - a_) // 32) for a_, b_ in zip(st.refactor.op_ptr[:-1], st.refactor.op_ptr[1:])) * 1.25
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@ def run(B=100000, reps=5):
     import numpy as np, torch
     from cvxpygen_b200 import runtime
     xi = torch.from_numpy(np.random.default_rng(1).uniform(-1, 1, (B, 12))).cuda()
-    for name in VARIANTS:
+    for name in sorted(os.listdir(VDIR)):          # every built variant directory (also those built by hand for a sweep)
         d = os.path.join(VDIR, name)
         if not os.path.exists(os.path.join(d, 'libcpg_b200.so')):
             continue
