@@ -108,6 +108,9 @@ def _family_header(setup: QPSetup, prefix: str, warps: Optional[int], ni: Option
     th = dict(zip([n_ for _, n_ in TAIL_HEADER_FIELDS], np.frombuffer(setup.tail_blob, dtype='<i4', count=len(TAIL_HEADER_FIELDS))))
     n_tt = max(int(th['n_fwd_tiles'] + th['n_bwd_tiles']), 1)
     tail_tiles = np.frombuffer(setup.tail_blob, dtype='<i4', count=8 * n_tt, offset=int(th['off_i32']) + 4 * int(th['i_tiles']))
+    nlv = int(th['n_levels']) + 1
+    tail_levels = np.concatenate([np.frombuffer(setup.tail_blob, dtype='<i4', count=nlv, offset=int(th['off_i32']) + 4 * int(th[k]))
+                                  for k in ('i_level_ptr', 'i_cround_ptr', 'i_scale_ptr')])
     lines = [
         '/* Auto-generated by cvxpygen_b200 %s -- compile-time sizes of problem family "%s". */' % (time.strftime('%Y-%m-%d'), setup.family.name),
         '#ifndef CPG_FAMILY_H', '#define CPG_FAMILY_H',
@@ -125,6 +128,7 @@ def _family_header(setup: QPSetup, prefix: str, warps: Optional[int], ni: Option
         f'#define CPG_FAM_MATPAR {matpar}', f'#define CPG_FAM_MAT_WARPS {mat_warps}', f'#define CPG_FAM_MAT_STRIDE {mat_stride}',
         f'#define CPG_FAM_MAT_A_STRIDE {mat_a}', f'#define CPG_FAM_MAT_P_STRIDE {mat_p}', f'#define CPG_FAM_MAT_G_STRIDE {mat_g_stride}',
         f"#define CPG_FAM_TAIL_WORD_SHIFT {int(th['pad0'])}",
+        '#define CPG_FAM_TAIL_LEVELS {' + ', '.join(str(int(v)) for v in tail_levels) + '}',
         '#define CPG_FAM_TAIL_TILES {' + ', '.join(str(int(v)) for v in tail_tiles) + '}',
         f'#define CPG_FAM_BIG {int(big)}', f'#define CPG_FAM_TAIL_STAGE {tail_stage}', f'#define CPG_FAM_GRAD {grad_ok}',
         f'#define CPG_FAM_DMMA {use_dmma}', f'#define CPG_FAM_DM_GROUPS {max(dm_groups, 1)}', f'#define CPG_FAM_DBLOB_BYTES_PAD {dblob_pad}',

@@ -141,6 +141,15 @@ __device__ __forceinline__ TailView make_tail_view(const uint8_t* blob) {
   return tv;
 }
 
+// Per-level pointers of the factorisation (level_ptr | coloured round_ptr | scale_ptr, n_levels + 1 entries each): a compile-time
+// table in constant memory when the family header carries it -- a uniform LDC instead of a dependent global load in front of
+// every level's loops (pointer chasing behind an L2 latency, 134 levels x 3 loops for mpc_ltv_12_4_10).
+#ifdef CPG_FAM_TAIL_LEVELS
+__constant__ const int kTailLevels[] = CPG_FAM_TAIL_LEVELS;
+#define CPG_TAIL_LEVEL_PTR(tv, which, off) (kTailLevels + (which) * ((tv).H->n_levels + 1))
+#else
+#define CPG_TAIL_LEVEL_PTR(tv, which, off) ((tv).I32 + (off))
+#endif
 // Forms of the factorisation's update phase (all checked on the SIMT emulator, tests/test_simt_emulation.py):
 //   CPG_TAIL_FACTOR_FORM 2 (default)  COLOURED ROUNDS: the ops of a level are dealt offline to rounds of 32 with pairwise distinct
 //       targets (offline/refactor.py: greedy, reaches ceil(ops / 32) rounds on the MPC families); a round is a plain read-modify-
@@ -161,13 +170,12 @@ __device__ __forceinline__ TailView make_tail_view(const uint8_t* blob) {
 // written; on exit S[j] = 1/D_j and the other slots hold L.  Right-looking, one elimination-tree level at a time.
 __device__ __forceinline__ void tail_factor(const TailView& tv, double* S, int lane) {
   const int nl = tv.H->n_levels;
-  const int* lp = tv.I32 + tv.H->i_level_ptr;
-  const int* sp = tv.I32 + tv.H->i_scale_ptr;
+  const int* lp = CPG_TAIL_LEVEL_PTR(tv, 0, tv.H->i_level_ptr);
+  const int* sp = CPG_TAIL_LEVEL_PTR(tv, 2, tv.H->i_scale_ptr);
   const uint16_t* lc = tv.U16 + tv.H->h_level_cols;
   const ushort2* scl = reinterpret_cast<const ushort2*>(tv.U16 + tv.H->h_scale);
 #if CPG_TAIL_FACTOR_FORM == 2
-  const int* lg = tv.I32 + tv.H->i_clevel_group;
-  const int* gp = tv.I32 + tv.H->i_cgroup_ptr;
+  const int* rp = CPG_TAIL_LEVEL_PTR(tv, 1, tv.H->i_cround_ptr);
   const ushort4* cops = reinterpret_cast<const ushort4*>(tv.U16 + tv.H->h_cops) + lane;
 #elif CPG_TAIL_FACTOR_FORM == 1
   const int* gtp = tv.I32 + tv.H->i_gtgt_ptr;
@@ -181,21 +189,21 @@ __device__ __forceinline__ void tail_factor(const TailView& tv, double* S, int l
     for (int c = lp[lv] + lane; c < lp[lv + 1]; c += LANES) { const int j = lc[c]; S[j] = 1.0 / S[j]; }
     __syncwarp();
 #if CPG_TAIL_FACTOR_FORM == 2
-    // rounds of one SYNC GROUP touch pairwise distinct targets: no barrier between them, so their table words and operands are in
-    // flight together (a level that eliminates one column is a single group)
-    for (int g = lg[lv]; g < lg[lv + 1]; ++g) {
-      const int r1 = gp[g + 1];
-      int r = gp[g];
-      for (; r + 3 < r1; r += 4) {
-        const ushort4 q0 = __ldg(cops + (size_t)r * LANES), q1 = __ldg(cops + (size_t)(r + 1) * LANES);
-        const ushort4 q2 = __ldg(cops + (size_t)(r + 2) * LANES), q3 = __ldg(cops + (size_t)(r + 3) * LANES);
-        const double u0 = S[q0.y] * S[q0.z] * S[q0.w], u1 = S[q1.y] * S[q1.z] * S[q1.w];
-        const double u2 = S[q2.y] * S[q2.z] * S[q2.w], u3 = S[q3.y] * S[q3.z] * S[q3.w];
-        // the zero slot is the only target that may repeat inside a group (padding): it only ever receives 0 - 0
-        S[q0.x] -= u0; S[q1.x] -= u1; S[q2.x] -= u2; S[q3.x] -= u3;
+    // rounds of one SYNC GROUP touch pairwise distinct targets: no barrier between them (bit 15 of the op's last field marks the
+    // round a barrier follows; a level that eliminates one column is a single group); the table words run two rounds ahead
+    {
+      const int r1 = rp[lv + 1];
+      int r = rp[lv];
+      if (r < r1) {
+        ushort4 q = __ldg(cops + (size_t)r * LANES);
+        ushort4 qn = (r + 1 < r1) ? __ldg(cops + (size_t)(r + 1) * LANES) : q;
+        for (; r < r1; ++r) {
+          const ushort4 qnn = (r + 2 < r1) ? __ldg(cops + (size_t)(r + 2) * LANES) : qn;
+          S[q.x] -= S[q.y] * S[q.z] * S[q.w & 0x7fffu];
+          if (q.w & 0x8000u) __syncwarp();
+          q = qn; qn = qnn;
+        }
       }
-      for (; r < r1; ++r) { const ushort4 q = __ldg(cops + (size_t)r * LANES); S[q.x] -= S[q.y] * S[q.z] * S[q.w]; }
-      __syncwarp();
     }
 #elif CPG_TAIL_FACTOR_FORM == 1
     // owner-writes form: a target's ops are contiguous and summed by ONE lane in table order (no atomics, deterministic)
@@ -493,6 +501,12 @@ __device__ __forceinline__ double ellx_dot(const int* __restrict__ tab, const ui
   if (k < K) a0 = fma(vals[__ldg(ix + k * LANES)], vec[__ldg(c + k * LANES)], a0);
   return a0 + a1;
 }
+// CPG_EQ_UNROLL = 1 keeps four (index, value) loads of the equilibration's norm / scaling loops in flight per lane.  Measured on
+// B200 it is SLOWER (mpc_ltv_12_4_10, 20 000 instances: 105.6 vs 94.8 ms, profiles/r2_matpar_factor_unroll_ab.jsonl) -- the kernel
+// sits at 255 registers and pays for the extra live values elsewhere -- so it is off.
+#ifndef CPG_EQ_UNROLL
+#define CPG_EQ_UNROLL 0
+#endif
 __device__ __forceinline__ double ellx_absmax(const int* __restrict__ tab, const uint16_t* __restrict__ U16,
                                               const double* vals, int lane) {
   const int K = __ldg(tab);
@@ -501,11 +515,13 @@ __device__ __forceinline__ double ellx_absmax(const int* __restrict__ tab, const
   // chains in flight; a maximum does not depend on the order
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   int k = 0;
+#if CPG_EQ_UNROLL
   for (; k + 3 < K; k += 4) {
     const int i0 = __ldg(ix + k * LANES), i1 = __ldg(ix + (k + 1) * LANES), i2 = __ldg(ix + (k + 2) * LANES), i3 = __ldg(ix + (k + 3) * LANES);
     const double v0 = vals[i0], v1 = vals[i1], v2 = vals[i2], v3 = vals[i3];
     a0 = fmax(a0, fabs(v0)); a1 = fmax(a1, fabs(v1)); a2 = fmax(a2, fabs(v2)); a3 = fmax(a3, fabs(v3));
   }
+#endif
   for (; k < K; ++k) a0 = fmax(a0, fabs(vals[__ldg(ix + k * LANES)]));
   return fmax(fmax(a0, a1), fmax(a2, a3));
 }

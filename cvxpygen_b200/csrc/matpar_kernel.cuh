@@ -91,10 +91,14 @@ __device__ void matpar_prepare(MatCtx& mc, const double* __restrict__ th, double
     }
     __syncwarp();
     // P <- Dt P Dt, A <- Et A Dt (mat_premult_diag then mat_postmult_diag)
+#if CPG_EQ_UNROLL
 #pragma unroll 2
+#endif
     for (int e = lane; e < nnzP; e += LANES)
       mc.Pv[e] = (mc.Pv[e] * w[__ldg(U16 + H->h_Prow + e)]) * w[__ldg(U16 + H->h_Pcol + e)];
+#if CPG_EQ_UNROLL
 #pragma unroll 4                 // (entries and indices come from L2: several elements in flight per lane)
+#endif
     for (int e = lane; e < nnzA; e += LANES)
       mc.Av[e] = (mc.Av[e] * w[N + __ldg(U16 + H->h_Arow + e)]) * w[__ldg(U16 + H->h_Acol + e)];
     __syncwarp();

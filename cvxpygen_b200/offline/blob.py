@@ -270,7 +270,14 @@ def pack_tail_blob(T) -> bytes:
     hv['i_cgroup_ptr'] = ar.add_i32(T.c_group_ptr)
     hv['i_clevel_group'] = ar.add_i32(T.c_level_group)
     align_u16(4)
-    hv['h_cops'] = ar.add_u16(T.c_ops)
+    # bit 15 of an op's 4th field (the pivot position j < 32768) = "a warp barrier follows this round" (last round of a sync group)
+    cops = np.array(T.c_ops, dtype=np.int64, copy=True).reshape(-1, 4)
+    assert T.nk < 32768
+    for g in range(len(T.c_group_ptr) - 1):
+        last = int(T.c_group_ptr[g + 1]) - 1
+        if last >= int(T.c_group_ptr[g]):
+            cops[last * LANES:(last + 1) * LANES, 3] |= 0x8000
+    hv['h_cops'] = ar.add_u16(cops)
     # tile header (8 ints): [i32 offset of the packed entries (slot | position << 16, lane-interleaved), 0, K, r_pad, rows,
     #                        u16 offset of the row list, inside: u16 offset of the slot table | first slot of the packed triangle,
     #                        0 no couplings inside / 1 slot table / 2 packed triangle]

@@ -8,6 +8,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 VDIR = os.path.join(ROOT, 'tools', '_variants')
 VARIANTS = {      # name -> (family, extra nvcc flags, batch[, solver_opts])
+    'ltv_cur': ('mpc_ltv_12_4_10', '', 20000),
+    'ltv_form0': ('mpc_ltv_12_4_10', '-DCPG_TAIL_FACTOR_FORM=0', 20000),
+    'ltv_nounroll': ('mpc_ltv_12_4_10', '-DCPG_EQ_UNROLL=0', 20000),
+    'ltv_form0_nounroll': ('mpc_ltv_12_4_10', '-DCPG_TAIL_FACTOR_FORM=0 -DCPG_EQ_UNROLL=0', 20000),
     'ltv_atomic': ('mpc_ltv_12_4_10', '', 20000),
     'ltv_gather': ('mpc_ltv_12_4_10', '-DCPG_TAIL_GATHER_FACTOR=1', 20000),
     'mpc_atomic': ('mpc_12_4_10', '', 100000, {'dmma': False}),
