@@ -155,13 +155,18 @@ class CanonFamily:
                    [UserVar('x', (n,), np.arange(n))], [UserDual('y', 'y', (m,), np.arange(m))])
 
     @classmethod
-    def from_canonical_conic(cls, name, c, A, b, G, h, l, q=()) -> 'CanonFamily':
+    def from_canonical_conic(cls, name, c, A, b, G, h, l, q=(), matrix_params=()) -> 'CanonFamily':
         """min c'x  s.t.  Ax = b,  h - Gx in R+^l x SOC(q_1) x ...  (ECOS form) with the canonical vectors ``c``, ``b``, ``h`` as
         the user parameters and A, G constant: the conic counterpart of from_canonical_qp.  Variables: ``x``; duals ``y`` (if
         there are equalities) and ``z``."""
         A = sp.csc_matrix(A); A.sort_indices(); G = sp.csc_matrix(G); G.sort_indices()
         n, p, m = G.shape[1], A.shape[0], G.shape[0]
         specs = [('c', (n,), c)] + ([('b', (p,), b)] if p else []) + [('h', (m,), h)]
+        mats = ('G', 'A') if matrix_params is True else tuple(matrix_params or ())    # stored entries (CSC order) as parameters ``G`` / ``A``
+        if 'G' in mats:
+            specs.append(('G', (G.nnz,), G.data))
+        if 'A' in mats and p:
+            specs.append(('A', (A.nnz,), A.data))
         params, col = [], 0
         for nm, shape, default in specs:
             d = np.asarray(default, dtype=float).ravel()
@@ -173,7 +178,8 @@ class CanonFamily:
         const = lambda v: sp.csr_matrix((np.asarray(v, dtype=float), (np.arange(len(v)), np.full(len(v), n_theta - 1))),
                                         shape=(len(v), n_theta))
         maps = {'c': ident(n, pc['c']), 'b': ident(p, pc['b']) if p else sp.csr_matrix((0, n_theta)), 'h': ident(m, pc['h']),
-                'd': sp.csr_matrix((1, n_theta)), 'A': const(A.data), 'G': const(G.data)}
+                'd': sp.csr_matrix((1, n_theta)), 'A': ident(A.nnz, pc['A']) if 'A' in pc else const(A.data),
+                'G': ident(G.nnz, pc['G']) if 'G' in pc else const(G.data)}
         pat = lambda M: (M.indices.astype(np.int32), M.indptr.astype(np.int32), M.shape)
         duals = ([UserDual('y', 'y', (p,), np.arange(p))] if p else []) + [UserDual('z', 'z', (m,), np.arange(m))]
         return cls(name, 'conic', n, p, m, params, maps, {'A': pat(A), 'G': pat(G)}, [UserVar('x', (n,), np.arange(n))], duals,

@@ -233,22 +233,27 @@ def write_reference_layout(fam, code_dir, prefix='', enable_settings=(), ref_roo
     """generator.py:65-95 minus canonicalisation and compilation, with the reference's own emitters.  Returns
     (canon, interface, configuration)."""
     from .solvers.admm_cuda import ADMMCUDAInterface
-    if fam.solver_type != 'quadratic':
-        raise ValueError('write_reference_layout drives the QP plugin (ADMM-CUDA)')
+    from .solvers.ipm_cuda import IPMCUDAInterface
+    conic = fam.solver_type != 'quadratic'
+    if conic and gradient:
+        raise ValueError('gradient code is emitted for the QP plugin (ADMM-CUDA)')
     U, M = reference_modules(ref_root)
     if prefix and not prefix[0].isalpha():       # generator.py:175-182
         prefix = f'_{prefix}'
     prefix = f'{prefix}_' if prefix else ''
-    cfg = M.Configuration(code_dir, 'ADMM-CUDA', prefix, bool(gradient), False, 0)
+    cfg = M.Configuration(code_dir, 'IPM-CUDA' if conic else 'ADMM-CUDA', prefix, bool(gradient), False, 0)
     canon = canon_from_family(fam, M)
-    iface = ADMMCUDAInterface(family=fam, enable_settings=enable_settings)
+    iface = (IPMCUDAInterface if conic else ADMMCUDAInterface)(family=fam, enable_settings=enable_settings)
     # _setup_folder (generator.py:99-108)
     shutil.rmtree(code_dir, ignore_errors=True)
     for sub in ('c/src', 'c/include', 'c/build', 'cpp/src', 'cpp/include'):
         os.makedirs(os.path.join(code_dir, sub))
     solver_code_dir = os.path.join(code_dir, 'c', 'solver_code')
     # _run_solver_code_generation (generator.py:124-146)
-    iface.generate_code(cfg, code_dir, solver_code_dir, os.path.join(ref_root, 'cvxpygen'), canon, gradient, prefix)
+    if conic:
+        iface.generate_reference_layout_code(code_dir, solver_code_dir, canon, prefix)
+    else:
+        iface.generate_code(cfg, code_dir, solver_code_dir, os.path.join(ref_root, 'cvxpygen'), canon, gradient, prefix)
     # CCodeWriter._write_workspace / _write_solve / _write_python_module (writer.py:96-139, 596-609)
     pvi, dvi, pi, pc = canon.prim_variable_info, canon.dual_variable_info, canon.parameter_info, canon.parameter_canon
     inc, src = os.path.join(code_dir, 'c', 'include'), os.path.join(code_dir, 'c', 'src')
@@ -261,14 +266,16 @@ def write_reference_layout(fam, code_dir, prefix='', enable_settings=(), ref_roo
     buf = io.StringIO()
     U.write_module_def(buf, cfg, pvi, dvi, pi, iface, iface)
     txt = buf.getvalue()
-    # the one-line patch to write_module_def a maintainer would make for the batched entry
-    txt = txt.replace('namespace py = pybind11;\n', f'namespace py = pybind11;\nvoid {prefix}cpg_b200_register_batch(py::module_& m);\n', 1)
-    k = txt.rindex('\n}')
-    txt = txt[:k] + f'\n    {prefix}cpg_b200_register_batch(m);\n' + txt[k:]
+    if not conic:
+        # the one-line patch to write_module_def a maintainer would make for the batched entry
+        txt = txt.replace('namespace py = pybind11;\n', f'namespace py = pybind11;\nvoid {prefix}cpg_b200_register_batch(py::module_& m);\n', 1)
+        k = txt.rindex('\n}')
+        txt = txt[:k] + f'\n    {prefix}cpg_b200_register_batch(m);\n' + txt[k:]
     with open(os.path.join(code_dir, 'cpp', 'src', 'cpg_module.cpp'), 'w') as f:
         f.write(txt)
-    with open(os.path.join(code_dir, 'cpp', 'src', 'cpg_module_batch.cpp'), 'w') as f:
-        f.write(_batch_cpp(fam, canon, iface, prefix))
+    if not conic:
+        with open(os.path.join(code_dir, 'cpp', 'src', 'cpg_module_batch.cpp'), 'w') as f:
+            f.write(_batch_cpp(fam, canon, iface, prefix))
     with open(os.path.join(code_dir, '__init__.py'), 'w') as f:
         f.write('')
     return canon, iface, cfg
@@ -278,14 +285,18 @@ def compile_reference_layout(code_dir, verbose=False):
     """Role of the reference's build (cmake -> libcpg.a, then setup.py build_ext; cvxpygen/compiler.py:24-31,
     templates/setup.py.jinja2:74-117) without cmake: nvcc for the CUDA library, gcc for the emitted C, g++ + pybind11 for the
     emitted module; everything in-tree.  Returns the path of the built cpg_module extension."""
-    from . import codegen
+    from . import codegen, codegen_ipm
     import pybind11
     sol = os.path.join(code_dir, 'c', 'solver_code')
-    lib = codegen.compile_solver_sources(sol, os.path.join(code_dir, 'libcpg_b200.so'), verbose=verbose)
+    conic = os.path.exists(os.path.join(sol, 'cpg_b200_socp_shim.c'))
+    if conic:
+        lib = codegen_ipm.compile_ipm_solver_sources(sol, os.path.join(code_dir, 'libcpg_b200.so'), verbose=verbose)
+    else:
+        lib = codegen.compile_solver_sources(sol, os.path.join(code_dir, 'libcpg_b200.so'), verbose=verbose)
     inc = os.path.join(code_dir, 'c', 'include')
     objs = []
     for c in (os.path.join(code_dir, 'c', 'src', 'cpg_workspace.c'), os.path.join(code_dir, 'c', 'src', 'cpg_solve.c'),
-              os.path.join(sol, 'cpg_b200_shim.c')):
+              os.path.join(sol, 'cpg_b200_socp_shim.c' if conic else 'cpg_b200_shim.c')):
         o = os.path.join(code_dir, 'c', 'build', os.path.basename(c)[:-2] + '.o')
         cmd = ['gcc', '-O2', '-fPIC', '-std=c99', '-I', inc, '-I', sol, '-c', c, '-o', o]
         res = subprocess.run(cmd, capture_output=True, text=True)
@@ -296,7 +307,8 @@ def compile_reference_layout(code_dir, verbose=False):
     cmd = ['g++', '-O2', '-fPIC', '-shared', '-std=c++17', '-fvisibility=hidden',
            '-I', pybind11.get_include(), '-I', sysconfig.get_paths()['include'], '-I', os.path.join(code_dir, 'cpp', 'include'),
            '-I', os.path.join(code_dir, 'c'), '-I', inc, '-I', sol,
-           os.path.join(code_dir, 'cpp', 'src', 'cpg_module.cpp'), os.path.join(code_dir, 'cpp', 'src', 'cpg_module_batch.cpp')] + objs + \
+           os.path.join(code_dir, 'cpp', 'src', 'cpg_module.cpp')] + \
+          ([] if conic else [os.path.join(code_dir, 'cpp', 'src', 'cpg_module_batch.cpp')]) + objs + \
           [lib, '-Wl,-rpath,$ORIGIN', '-o', ext]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode:
@@ -323,6 +335,9 @@ def standard_layouts():
     return {
         'refwriter_mpc_6_3_10': (lambda: families.mpc(6, 3, 10), ''),                   # vectors only (l, u change): the 'lu' branch
         'refwriter_nonneg_LS_3_2_A': (lambda: families.nonneg_ls(3, 2, name='nonneg_LS_3_2_A'), 'nnls'),   # A + l/u change; prefix
+        # the conic plugin (IPM-CUDA, role of ECOSInterface): c / b change ('AbcGh' and 'c' branches), and F / d_sqrt in A / G
+        'refwriter_portfolio_socp_20_4': (lambda: families.portfolio_socp(20, 4), ''),
+        'refwriter_portfolio_socp_mat_20_4': (lambda: families.portfolio_socp(20, 4, matrix_params=True), 'pf'),
     }
 
 

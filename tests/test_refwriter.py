@@ -174,3 +174,96 @@ def test_emitted_c_abi_via_ctypes_matrix_family_with_prefix():
         x = np.array([result.prim.contents.x[i] for i in range(2)])
         assert np.allclose(x, ora['x'][0, fam.variables[0].indices], rtol=1e-5, atol=1e-9)
         assert abs(info.obj_val - ora['obj'][0]) < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the conic plugin (IPMCUDAInterface, role of ECOSInterface) under the reference's writer
+@pytest.mark.skipif(not refwriter.reference_available(), reason='reference tree not present')
+def test_reference_writer_emits_the_conic_update_tree(tmp_path):
+    """What the reference's emitters produce from IPMCUDAInterface's attribute values: ECOS's decision tree ('AbcGh' when anything of
+    A, b, G is outdated, else 'c' / 'h' alone; cvxpygen/solvers/ecos.py:88-117) calling the shim, integer status, duals split into
+    y and z, the settings table written through cpg_set_solver_<name>."""
+    fam = families.portfolio_socp(20, 4, matrix_params=True)
+    d = str(tmp_path / 'code')
+    canon, iface, cfg = refwriter.write_reference_layout(fam, d, prefix='pf')
+    solve_c = open(os.path.join(d, 'c', 'src', 'cpg_solve.c')).read()
+    assert 'pf_cpg_b200_socp_shim_update(pf_Canon_Params.G->x, pf_Canon_Params.A->x, pf_Canon_Params.c, pf_Canon_Params.h, pf_Canon_Params.b);' in solve_c
+    assert 'pf_cpg_b200_socp_shim_update(0, 0, pf_Canon_Params.c, 0, 0);' in solve_c
+    assert 'pf_cpg_b200_socp_shim_solve();' in solve_c and 'pf_CPG_Info.status = pf_cpg_b200_socp_shim_info.status;' in solve_c
+    assert 'pf_sol_z[' in solve_c and 'pf_sol_y[' in solve_c
+    assert '(&pf_cpg_b200_socp_shim_settings)->maxit = maxit_new;' in solve_c
+    ws_h = open(os.path.join(d, 'c', 'include', 'cpg_workspace.h')).read()
+    assert 'extern CpgB200SocpShimInfo pf_cpg_b200_socp_shim_info;' in ws_h and '#include "cpg_b200_socp_shim.h"' in ws_h
+    shim_h = open(os.path.join(d, 'c', 'solver_code', 'cpg_b200_socp_shim.h')).read()
+    assert '#define CPG_SSHIM_HAS_G 1' in shim_h and '#define CPG_SSHIM_HAS_A 1' in shim_h
+    # the emitted C compiles against the shim's declarations (no nvcc here)
+    import subprocess
+    for c in ('cpg_workspace.c', 'cpg_solve.c'):
+        r = subprocess.run(['gcc', '-std=c99', '-fsyntax-only', '-I', os.path.join(d, 'c', 'include'), '-I', os.path.join(d, 'c', 'solver_code'),
+                            os.path.join(d, 'c', 'src', c)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,mat', [('refwriter_portfolio_socp_20_4', False), ('refwriter_portfolio_socp_mat_20_4', True)])
+def test_pybind_conic_solve_equals_compiled_ecos(name, mat):
+    """cpg_module.solve(upd, par) through the reference-emitted pybind module of the CONIC plugin: the emitted cpg_solve canonicalises
+    on the host, hands c / b / h (and G / A values when F, d_sqrt are parameters) to the shim, the kernel solves a batch of one;
+    compared with the compiled ECOS driven the reference's way (ECOS_updateData + ECOS_solve on the same canonical data).
+    Runs in a fresh interpreter: every emitted module registers pybind classes of the same C++ names (cpg_params, ...), so a second
+    cpg_module in one process shadows the first -- the reference has the same property (one generated module per process)."""
+    import subprocess, sys
+    from oracle import ref_ecos
+    if not ref_ecos.available():
+        pytest.skip('oracle/_ref/libecos_ref.so not built')
+    d = _dir(name)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), d, str(int(mat))], capture_output=True, text=True,
+                       env={**os.environ, 'PYTHONPATH': root + os.pathsep + os.path.join(root, 'tests')})
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def _conic_pybind_check(d, mat):
+    from oracle import ref_ecos
+    m = refwriter.load_module(d)
+    fam = families.portfolio_socp(20, 4, matrix_params=mat)
+    r = ref_ecos.RefECOS(fam.canon_data('c'), fam.canon_matrix('A'), fam.canon_data('b'), fam.canon_matrix('G'), fam.canon_data('h'),
+                         fam.cone_dims['l'], fam.cone_dims['q'])
+    rng = np.random.default_rng(8)
+    m.set_solver_default_settings()
+    for trial in range(4):
+        vals = {'a': fam.param('a').default + 0.3 * rng.standard_normal(20), 'w_prev': np.full(20, 1 / 20)}
+        if mat:
+            vals['F'] = fam.param('F').default + 0.25 * rng.standard_normal(80)
+            vals['d_sqrt'] = fam.param('d_sqrt').default * rng.uniform(0.5, 1.5, 20)
+        pre = 'pf_' if mat else ''                     # classes carry the code-generation prefix, functions do not
+        par = getattr(m, pre + 'cpg_params')(); upd = getattr(m, pre + 'cpg_updated')()
+        for k, v in vals.items():
+            if trial == 3 and k != 'a':
+                continue                              # last trial: only `a` is marked outdated -> the 'c' branch of the tree
+            setattr(par, k, list(np.asarray(v, dtype=float)))      # matrices: flat, column-major (what cpg_solver.py hands over)
+            setattr(upd, k, True)
+        if trial == 3:
+            vals = {**prev, 'a': vals['a']}
+        prev = vals
+        res = m.solve(upd, par)
+        th = fam.theta_default().copy()
+        for k, v in vals.items():
+            p_ = fam.param(k); th[p_.col:p_.col + p_.size] = v
+        data = {k: np.asarray(fam.maps[k] @ th).ravel()[None, :] for k in ('c', 'b', 'h', 'A', 'G')}
+        ora = r.solve_batch(c=data['c'], b=data['b'], h=data['h'], G=data['G'], A=data['A'])
+        assert res.cpg_info.status == int(ora['exitflag'][0]) == 0 and res.cpg_info.iter == int(ora['iter'][0])
+        for v in fam.variables:
+            assert np.allclose(np.asarray(getattr(res.cpg_prim, v.name)), ora['x'][0, v.indices], rtol=1e-5, atol=1e-7), v.name
+        for dv in fam.duals:
+            assert np.allclose(np.asarray(getattr(res.cpg_dual, dv.name)).ravel(), ora[dv.vec][0, dv.indices], rtol=1e-4, atol=1e-6), dv.name
+        assert abs(res.cpg_info.obj_val + ora['pcost'][0]) < 1e-7            # maximisation: cpg reports -(pcost)
+    m.set_solver_maxit(3)
+    assert m.solve(upd, par).cpg_info.iter == 3
+    m.set_solver_default_settings()
+
+
+if __name__ == '__main__':
+    import sys
+    _conic_pybind_check(sys.argv[1], bool(int(sys.argv[2])))
+    print('ok')
