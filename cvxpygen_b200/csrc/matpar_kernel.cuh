@@ -56,11 +56,18 @@ __device__ __forceinline__ void matpar_canon(MatCtx& mc, const double* __restric
 // steps 1-2; on exit mc.Av / mc.Pv hold the scaled matrices, mc.D/Dinv/E/Einv/c/cinv the scalings.  w: >= n+m doubles scratch.
 template <class Fam>
 __device__ void matpar_prepare(MatCtx& mc, const double* __restrict__ th, double* __restrict__ w, const int lane,
-                               const int scaling) {
+                               const int scaling, double* __restrict__ S) {
   constexpr int N = Fam::N, M = Fam::M, NXL = (N + 31) / 32, NZL = (M + 31) / 32, NZLs = NZL > 0 ? NZL : 1;
   const CpgMatHeader* H = mc.mv.H;
   const int* I32 = mc.mv.I32; const double* F64 = mc.mv.F64; const uint16_t* U16 = mc.mv.U16;
   const int nnzP = H->nnzP, nnzA = H->nnzA;
+  // The ten Ruiz passes read every entry of A twice and rewrite it once per pass.  Their home is the warp's slice of the global
+  // scratch (an L2 round trip per access, behind an index that is itself an L2 load: 13 % of the kernel's stall samples for 5 %
+  // of its instructions, profiles/r2_matpar_v8_ncu_summary.md); the factor storage S is idle until the assembly, so the entries
+  // are equilibrated THERE and copied to their home once at the end.
+  double* const Ahome = mc.Av;
+  constexpr bool STAGE_A = Fam::MAT_A_STRIDE <= Fam::S_STRIDE;
+  if (STAGE_A) mc.Av = S;
   matpar_canon(mc, th, lane);
   // ---- 2. scale_data
   double d[NXL], e_[NZLs], q[NXL];
@@ -127,6 +134,10 @@ __device__ void matpar_prepare(MatCtx& mc, const double* __restrict__ th, double
 #pragma unroll
   for (int k = 0; k < NZL; ++k) { const int j = lane + 32 * k; if (j < M) { mc.E[j] = e_[k]; mc.Einv[j] = 1.0 / e_[k]; } }
   mc.c = c; mc.cinv = 1.0 / c;
+  if (STAGE_A) {
+    for (int e = lane; e <= nnzA; e += LANES) Ahome[e] = S[e];
+    mc.Av = Ahome;
+  }
   __syncwarp();
 }
 
@@ -164,7 +175,7 @@ admm_matpar_kernel(const uint8_t* __restrict__ cblob_g, const uint8_t* __restric
     if (lane == 0) b = (int)atomicAdd(io.work_counter, 1u);
     b = __shfl_sync(FULL, b, 0);
     if (b >= io.B) break;
-    matpar_prepare<Fam>(mc, io.params + (size_t)b * H->npb, wbase, lane, st.scaling);
+    matpar_prepare<Fam>(mc, io.params + (size_t)b * H->npb, wbase, lane, st.scaling, ta.S);
     solve_instance<Fam, 2>(H, I32, F64, U16, wbase, lane, b, io, st, &ta);
     __syncwarp();
   }
