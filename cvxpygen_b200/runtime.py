@@ -284,10 +284,12 @@ class Module:
         info = SimpleNamespace(obj_val=obj, iter=it, status=st, pri_res=pri, dua_res=dua, time=t1 - t0)
         return SimpleNamespace(cpg_prim=pr, cpg_dual=du, cpg_info=info, prim=prim, dual=dual, sol_x=solx, sol_y=soly)
 
-    def solve_batch_multi(self, params, devices=None, x0=None, y0=None, return_canonical=False, **settings):
+    def solve_batch_multi(self, params, devices=None, x0=None, y0=None, return_canonical=False, out=None, **settings):
         """The batch on SEVERAL devices of this node from one call (cpg_solve_batch_host_multi): contiguous shards, one host
         thread per device inside the library, nothing exchanged between devices.  devices: list of CUDA device indices
-        (default: every visible device).  Same result object as solve_batch."""
+        (default: every visible device).  Same result object as solve_batch.  out: optional dict of caller-owned float64 arrays
+        `prim` (B, n_prim), `dual` (B, n_dual), `obj`, `pri`, `dua` (B) and int32 `it`, `st` (B) -- numpy views of PINNED buffers
+        (e.g. torch.empty(..., pin_memory=True).numpy()) let every device store its result rows straight into host memory."""
         for k, v in settings.items():
             self.set_solver_setting(k, v)
         if devices is None:
@@ -300,11 +302,18 @@ class Module:
         d = self.dims
         self._expect(P, (None, d.n_param), 'params')
         B = P.shape[0]
-        prim = np.empty((B, d.n_prim)); dual = np.empty((B, d.n_dual))
+        if out is not None:
+            prim, dual, obj, pri, dua, it, st = (out[k] for k in ('prim', 'dual', 'obj', 'pri', 'dua', 'it', 'st'))
+            self._expect(prim, (B, d.n_prim), 'out[prim]'); self._expect(dual, (B, d.n_dual), 'out[dual]')
+            for a, nm in ((obj, 'obj'), (pri, 'pri'), (dua, 'dua'), (it, 'it'), (st, 'st')):
+                if a.shape != (B,) or not a.flags.c_contiguous or a.dtype != (np.int32 if nm in ('it', 'st') else np.float64):
+                    raise ValueError(f'out[{nm}]: expected a contiguous ({B},) array of the right dtype')
+        else:
+            prim = np.empty((B, d.n_prim)); dual = np.empty((B, d.n_dual))
+            obj = np.empty(B); pri = np.empty(B); dua = np.empty(B)
+            it = np.empty(B, dtype=np.int32); st = np.empty(B, dtype=np.int32)
         solx = np.empty((B, d.n_var)) if return_canonical else None
         soly = np.empty((B, d.n_con)) if return_canonical else None
-        obj = np.empty(B); pri = np.empty(B); dua = np.empty(B)
-        it = np.empty(B, dtype=np.int32); st = np.empty(B, dtype=np.int32)
         s = self.settings
         if x0 is not None and y0 is not None:
             x0 = np.ascontiguousarray(x0, dtype=np.float64); y0 = np.ascontiguousarray(y0, dtype=np.float64)

@@ -57,3 +57,23 @@ def test_multi_entry_equals_single_device_entry():
         assert lib.cpg_b200_use_device(C.c_int(0)) == 0
         again = mod.solve_batch({'x_init': xi[:64]}, return_canonical=True)
         assert np.array_equal(again.sol_x, one.sol_x[:64])
+
+
+@pytest.mark.gpu
+def test_multi_entry_with_caller_owned_pinned_outputs():
+    """solve_batch_multi(out=...) on numpy views of pinned buffers: same numbers as the allocating call, written in place."""
+    import torch
+    from cvxpygen_b200 import standard
+    mod = standard.load('mpc_6_3_10')
+    B = 300
+    xi = np.random.default_rng(2).uniform(-1, 1, (B, 6))
+    d = mod.dims
+    pin = lambda shape, dt=torch.float64: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+    out = dict(prim=pin((B, d.n_prim)), dual=pin((B, d.n_dual)), obj=pin(B), pri=pin(B), dua=pin(B), it=pin(B, torch.int32), st=pin(B, torch.int32))
+    devs = list(range(min(2, torch.cuda.device_count())))
+    r = mod.solve_batch_multi(xi, devices=devs, out=out)
+    ref = mod.solve_batch(xi)
+    assert r.prim is out['prim'] and np.array_equal(out['prim'], ref.prim) and np.array_equal(out['dual'], ref.dual)
+    assert np.array_equal(out['it'], ref.cpg_info.iter) and np.array_equal(out['st'], ref.cpg_info.status)
+    with pytest.raises(ValueError):
+        mod.solve_batch_multi(xi, devices=devs, out={**out, 'it': np.zeros(B)})

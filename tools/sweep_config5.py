@@ -10,18 +10,25 @@ import numpy as np, torch
 from cvxpygen_b200 import standard
 mod = standard.load('mpc_12_4_10').init()
 ndev = torch.cuda.device_count()
+PINNED = '--pinned' in sys.argv        # caller-owned pinned host buffers in and out (the devices store their result rows directly)
+d = mod.dims
 for B in (1000, 10000, 100000, 1000000):
     xi = np.random.default_rng(1).uniform(-1, 1, (B, 12))
+    out = None
+    if PINNED:
+        pin = lambda shape, dt=torch.float64: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+        xp = pin((B, 12)); xp[:] = xi; xi = xp
+        out = dict(prim=pin((B, d.n_prim)), dual=pin((B, d.n_dual)), obj=pin(B), pri=pin(B), dua=pin(B), it=pin(B, torch.int32), st=pin(B, torch.int32))
     for N in (1, 2, 4, 8):
         if N > ndev:
             continue
         devs = list(range(N))
-        mod.solve_batch_multi(xi, devices=devs)           # warm-up: contexts, staging buffers
+        mod.solve_batch_multi(xi, devices=devs, out=out)           # warm-up: contexts, staging buffers
         ts = []
         for _ in range(3):
-            t0 = time.perf_counter(); r = mod.solve_batch_multi(xi, devices=devs); ts.append(time.perf_counter() - t0)
+            t0 = time.perf_counter(); r = mod.solve_batch_multi(xi, devices=devs, out=out); ts.append(time.perf_counter() - t0)
         t = float(np.median(ts))
-        rec = dict(config='MPC QP (12,4,10) strong scaling through cpg_solve_batch_host_multi (pageable host buffers)', n_gpus=N, batch=B,
+        rec = dict(config='MPC QP (12,4,10) strong scaling through cpg_solve_batch_host_multi (%s host buffers)' % ('pinned' if PINNED else 'pageable'), n_gpus=N, batch=B,
                    ms=round(t * 1e3, 3), inst_per_s=round(B / t), frac_solved=float((r.cpg_info.status == 1).mean()))
         if N == 1:
             P = torch.from_numpy(xi).cuda(); out = mod.solve_batch_device(P); torch.cuda.synchronize()
