@@ -256,7 +256,7 @@ int CPG_B200_FN(cpg_socp_solve_batch_host_multi)(int n_dev, const int* devices, 
   for (int k = 0; k < n_dev; ++k) {
     th.emplace_back([&, k] {
       const long long lo = (long long)B * k / n_dev, hi = (long long)B * (k + 1) / n_dev;     // contiguous shard, nothing exchanged
-      int r = CPG_B200_FN(cpg_b200_init)(dev[k]);
+      int r = ctxs[dev[k]].ready ? CPG_B200_FN(cpg_b200_use_device)(dev[k]) : CPG_B200_FN(cpg_b200_init)(dev[k]);     // (init only on first use)
       if (r == CPG_B200_OK && hi > lo) {
         auto at = [&](auto* p, size_t w) { return p ? p + (size_t)lo * w : p; };
         r = CPG_B200_FN(cpg_socp_solve_batch_host)((int)(hi - lo), at(params, (size_t)cpgipm::NPB), at(prim, (size_t)cpgipm::NPRIM),

@@ -535,7 +535,9 @@ int CPG_B200_FN(cpg_solve_batch_host_multi)(int n_dev, const int* devices, int B
     th.emplace_back([&, k] {
       // contiguous shard [lo, hi) of the batch: instances never interact, so nothing is exchanged between the devices
       const long long lo = (long long)B * k / n_dev, hi = (long long)B * (k + 1) / n_dev;
-      int r = CPG_B200_FN(cpg_b200_init)(dev[k]);      // selects this thread's context; uploads the constants on first use
+      // select this thread's context; the first use of a device uploads the constants (later calls must not: cpg_b200_init queries
+      // the device properties and re-uploads every table -- ~2 ms per device, and it would undo a cpg_b200_load_constants_all)
+      int r = ctxs[dev[k]].ready ? CPG_B200_FN(cpg_b200_use_device)(dev[k]) : CPG_B200_FN(cpg_b200_init)(dev[k]);
       if (r == CPG_B200_OK && hi > lo) {
         auto at = [&](auto* p, size_t w) { return p ? p + (size_t)lo * w : p; };
         r = CPG_B200_FN(cpg_solve_batch_host)((int)(hi - lo), at(params, (size_t)H->npb), at(x0, (size_t)Fam::N), at(y0, (size_t)Fam::M),

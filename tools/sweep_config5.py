@@ -31,8 +31,8 @@ for B in (1000, 10000, 100000, 1000000):
         rec = dict(config='MPC QP (12,4,10) strong scaling through cpg_solve_batch_host_multi (%s host buffers)' % ('pinned' if PINNED else 'pageable'), n_gpus=N, batch=B,
                    ms=round(t * 1e3, 3), inst_per_s=round(B / t), frac_solved=float((r.cpg_info.status == 1).mean()))
         if N == 1:
-            P = torch.from_numpy(xi).cuda(); out = mod.solve_batch_device(P); torch.cuda.synchronize()
+            P = torch.from_numpy(np.ascontiguousarray(xi)).cuda(); dout = mod.solve_batch_device(P); torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); mod.solve_batch_device(P, out=out); e1.record(); torch.cuda.synchronize()
+            e0.record(); mod.solve_batch_device(P, out=dout); e1.record(); torch.cuda.synchronize()
             rec['device_resident_ms'] = round(e0.elapsed_time(e1), 3)
         print(json.dumps(rec), flush=True)
