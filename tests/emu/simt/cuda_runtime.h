@@ -35,6 +35,7 @@
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3() {} dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct ushort2 { unsigned short x, y; };
 struct ushort4 { unsigned short x, y, z, w; };
+inline ushort2 make_ushort2(unsigned short x, unsigned short y) { ushort2 r; r.x = x; r.y = y; return r; }
 struct int4 { int x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
 struct alignas(16) double2 { double x, y; };
