@@ -10,7 +10,7 @@
 //
 // The NI slots of a warp are independent instances: each has its own iteration counter, termination check and
 // epilogue; when one terminates its slot is refilled from the global instance queue at once.
-// State per slot in registers: x, z, y (lane i%32 owns element i).  q, l, u are NOT kept in registers: rows that do
+// State per slot in registers: x and the pre-projection vector t, of which z and y are functions (lane i%32 owns element i).  q, l, u are NOT kept in registers: rows that do
 // not depend on a batched parameter are read from the constants blob (already scaled), rows that do are read from a
 // small per-warp table written by the slot's prologue.
 // Everything that happens once per instance or once per check_termination iterations (prologue, residuals,
@@ -19,7 +19,7 @@
 // loop shares the instruction cache with it) at the cost of ~100 register moves per rotation.
 //
 // Reference functions restated: same list as admm_kernel.cuh (a1-a12); the per-instance arithmetic and its order are
-// those of the single-instance path, so iterates agree with it bit for bit.
+// those of the single-instance path except that z, y are recomputed from t (agreement to ~1e-14, identical iteration counts).
 #pragma once
 #include <type_traits>
 #include "admm_kernel.cuh"
