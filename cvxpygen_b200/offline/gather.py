@@ -105,6 +105,65 @@ def _cost(cells, nwarp, c_fixed=10.0, c_entry=1.0, c_shuf=3.0):
     return max(per_warp)
 
 
+# Deal a lane's entries to the steps so that half-warps hit distinct bank pairs (_order_steps).  OFF: with cells this short there is
+# little freedom -- the bank model counts 3 404 -> 2 566 extra passes per iteration for portfolio_socp_100_10 (-25 % of the excess,
+# ~ -8 % of the operand wavefronts of a kernel whose shared-memory pipe is 31 % busy) -- not worth a different summation order.
+CONFLICT_AWARE = False
+
+
+def _order_steps(lists, ln, nfields, null_entry):
+    """The ORDER in which a lane walks the entries of its cell is free (a sum).  An 8-byte shared-memory load of a warp is served
+    in two passes, one per half-warp, iff the distinct addresses of a half fall into distinct bank pairs (index mod 16); every
+    extra address in a pair costs a pass (ncu, round 2: 22 % of ipm_kernel's shared wavefronts were such conflicts, half of
+    the operand gathers').  Greedy, step by step and half by half: the lanes with the most entries left choose first, each takes
+    the entry that adds the fewest conflicts over all operand fields; a lane with slack may wait (its step is a null entry).
+    Returns ln lists of 32 entries (None = null)."""
+    rem = [list(l) for l in lists]
+    out = []
+    nf = nfields
+    for j in range(ln):
+        left = ln - j
+        step = [None] * 32
+        for h in (0, 16):
+            used = [dict() for _ in range(nf)]       # per field: bank pair -> set of addresses
+            lanes = sorted(range(h, h + 16), key=lambda l: -len(rem[l]))
+            for l in lanes:
+                if not rem[l]:
+                    continue
+                best_i, best_c = -1, None
+                for i, e in enumerate(rem[l]):
+                    c = 0
+                    for f in range(nf):
+                        a = e[f]; cls = used[f].get(a & 15)
+                        if cls and a not in cls:
+                            c += 1
+                    if best_c is None or c < best_c:
+                        best_i, best_c = i, c
+                        if c == 0:
+                            break
+                if best_c and len(rem[l]) < left:
+                    continue                       # would conflict and the lane has slack: wait for a later step
+                e = rem[l].pop(best_i)
+                for f in range(nf):
+                    used[f].setdefault(e[f] & 15, set()).add(e[f])
+                step[l] = e
+        out.append(step)
+    assert not any(rem)
+    return out
+
+
+def plan_conflicts(plan: GatherPlan) -> int:
+    """Extra shared-memory passes of the plan's operand loads under the bank model above (diagnostic / tests)."""
+    E = plan.entry_array().astype(np.int64).reshape(-1, 32, plan.nfields)
+    extra = 0
+    for step in E:
+        for h in (0, 16):
+            for f in range(plan.nfields):
+                a = np.unique(step[h:h + 16, f])
+                extra += int(np.bincount(a & 15, minlength=16).max()) - 1
+    return extra
+
+
 def add_phase(plan: GatherPlan, rows: Sequence[Tuple[int, int, Sequence[Tuple[int, ...]]]], use_warps: int = 0) -> None:
     """rows: (target, flag, entries).  Appends one phase (possibly of zero rounds) to the plan.  use_warps > 0 deals the
     cells to the first use_warps warps only (the others are busy with something else during this phase)."""
@@ -136,12 +195,17 @@ def add_phase(plan: GatherPlan, rows: Sequence[Tuple[int, int, Sequence[Tuple[in
             shuf = max([c[0] for c in chunk], default=1).bit_length() - 1
             plan.wr_base.append(len(plan.entries)); plan.wr_len.append(ln); plan.wr_shuf.append(shuf)
             ent = [plan.null_entry] * (ln * 32)
+            lists = [[] for _ in range(32)]
             for lane, (g, clen, ri, part) in enumerate(chunk):
                 assert lane % g == part                   # the group is aligned to its size inside the warp
                 tgt, flag, e = rows[ri]
-                for j, v in enumerate(e[part * clen:(part + 1) * clen]):
-                    ent[j * 32 + lane] = v
+                lists[lane] = list(e[part * clen:(part + 1) * clen])
                 desc[r * T + w * 32 + lane] = tgt | ((g.bit_length() - 1) << plan.gshift) | (1 << plan.vshift) | (flag << plan.fshift)
+            for j, step in enumerate(_order_steps(lists, ln, plan.nfields, plan.null_entry) if CONFLICT_AWARE else
+                                     [[lst[j] if j < len(lst) else None for lst in lists] for j in range(ln)]):
+                for lane, v in enumerate(step):
+                    if v is not None:
+                        ent[j * 32 + lane] = v
             plan.entries += ent
     plan.desc += desc
     plan.phases.append(Phase(lo, lo + n_rounds))
