@@ -147,7 +147,7 @@ def test_main_kernel_warm_start_on_the_emulator(tmp_path):
 
 @pytest.mark.parametrize('name,B,dmma', [('nonneg_LS_3_2', 40, False), ('box_qp_6_8', 96, False), ('random_qp_20_5_15', 24, False),
                                          ('mpc_12_4_10', 12, False), ('portfolio_qp_50_10', 6, False),
-                                         ('box_qp_6_8', 96, True), ('mpc_12_4_10', 20, True)])
+                                         ('box_qp_6_8', 96, True)])      # (the tensor-core variant on mpc: test_main_kernel_on_the_emulator[True] and the GPU suite)
 def test_standard_families_on_the_emulator(name, B, dmma, tmp_path):
     """Main + tail kernels of the standard families -- incl. the headline MPC-12/4/10 family with its 374-step generated solve and
     the 742-row portfolio QP --: unstructured sparsity with q, l, u all batched; box_qp's corner
