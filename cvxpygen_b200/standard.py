@@ -15,6 +15,7 @@ GENERATED_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_gener
 STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
     'mpc_12_4_10': (lambda: families.mpc(12, 4, 10), ['x_init']),          # BASELINE config 2 / 5 (headline)
     'mpc_6_3_10': (lambda: families.mpc(6, 3, 10), ['x_init']),             # the reference test's MPC size
+    'mpc_6_3_10_dmma': (lambda: families.mpc(6, 3, 10), ['x_init']),        # the same through the opt-in FP64 tensor-core main kernel
     'nonneg_LS_3_2': (lambda: families.nonneg_ls(3, 2), ['b']),             # BASELINE config 1 (README example)
     'random_qp_20_5_15': (lambda: families.random_qp(20, 5, 15), ['q', 'b', 'h']),  # unstructured sparsity, q/l/u all batched
     'portfolio_qp_50_10': (lambda: families.portfolio_qp(50, 10), ['a', 'w_prev']),   # the reference's portfolio test problem (QP form, OSQP)
@@ -44,13 +45,14 @@ STANDARD: Dict[str, Tuple[Callable, List[str]]] = {
     'mpc_6_3_10_two_stage': (lambda: families.mpc(6, 3, 10), ['x_init']),
 }
 TWO_STAGE_NAMES: List[str] = ['mpc_6_3_10_two_stage']
+SOLVER_OPTS: Dict[str, dict] = {'mpc_6_3_10_dmma': {'dmma': True}}      # non-default code-generation options of a standard family
 
 # families solved by the ADMM (QP) backend / by the interior-point (SOCP) backend
 SOCP_NAMES: List[str] = [n for n in STANDARD if '_socp_' in n or n.startswith('network_lp') or n.endswith('_two_stage')]     # conic families (IPM-CUDA)
 MATPAR_NAMES: List[str] = ['mpc_ltv_6_3_10', 'mpc_ltv_12_4_10', 'mpc_ref_6_3_10', 'actuator_1_3', 'osqp_update_matrices_5_8',
                            'nonneg_LS_3_2_A']
 BIG_NAMES: List[str] = ['random_qp_700_100_700']
-QP_NAMES: List[str] = [n for n in STANDARD if n not in SOCP_NAMES and n not in MATPAR_NAMES and n not in BIG_NAMES]
+QP_NAMES: List[str] = [n for n in STANDARD if n not in SOCP_NAMES and n not in MATPAR_NAMES and n not in BIG_NAMES and n not in SOLVER_OPTS]
 
 
 def code_dir(name: str) -> str:
@@ -66,7 +68,8 @@ def build(name: str, force: bool = False, verbose: bool = False) -> str:
     fam = fam_fn()
     two_stage = name in TWO_STAGE_NAMES
     solver = 'IPM-CUDA' if (fam.solver_type == 'conic' or two_stage) else 'ADMM-CUDA'
-    generate_code(fam, code_dir=d, solver=solver, batch_params=batch, prefix='', wrapper=True, verbose=verbose, gradient=two_stage)
+    generate_code(fam, code_dir=d, solver=solver, batch_params=batch, prefix='', wrapper=True, verbose=verbose, gradient=two_stage,
+                  solver_opts=SOLVER_OPTS.get(name))
     return d
 
 

@@ -244,3 +244,19 @@ def test_big_family_parity(adaptive_rho):
     assert_batch_parity(res.sol_x, res.sol_y, res.cpg_info, ora, TOL)
     assert mod.launch_count() == 2          # queue_all_kernel + admm_tail_kernel, no main kernel
     print(f'\nbig family {name}: B={B} host-call {dt * 1e3:.1f} ms = {B / dt:.0f} inst/s, mean iter {res.cpg_info.iter.mean():.1f}')
+
+
+@pytest.mark.gpu
+def test_tensor_core_main_kernel_parity():
+    """The opt-in FP64 tensor-core main kernel (admm_dmma_kernel: mma.sync.m8n8k4.f64, eight instances per group of four warps;
+    DESIGN 4.7) against the compiled reference: identical iteration counts and statuses, incl. rho updates handed to the tail kernel."""
+    name, B = 'mpc_6_3_10_dmma', 700
+    fam, params, (q, l, u) = family_and_batch(name, B, seed=9)
+    mod = standard.load(name)
+    hdr = open(__import__('os').path.join(standard.code_dir(name), 'c', 'include', 'cpg_family.h')).read()
+    assert '#define CPG_FAM_DMMA 1' in hdr
+    for kw in ({}, dict(adaptive_rho_interval=25, eps_abs=1e-5, eps_rel=1e-5)):
+        res = mod.solve_batch(params, return_canonical=True, **kw)
+        mod.set_solver_default_settings()
+        ora = oracle_solve(fam, q, l, u, **kw)
+        assert_batch_parity(res.sol_x, res.sol_y, res.cpg_info, ora, TOL, eps_abs=kw.get('eps_abs', 1e-3))
