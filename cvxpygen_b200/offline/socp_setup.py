@@ -301,7 +301,12 @@ def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None
     fw_rows = {}
     for t_, s_, sl in zip(fw[:, 1], fw[:, 2], fw[:, 3]):
         fw_rows.setdefault(int(t_), []).append((int(sl), int(s_)))
-    plan_fw = _gather.GatherPlan(T=threads, nfields=2, tbits=11, null_entry=(NS, 0))
+    # a null entry multiplies the always-zero slot S[NS] by SOME element of the vector being solved for: it must be one that no
+    # thread writes during the phase (compute-sanitizer racecheck flagged the read of u[0] next to its owner's write -- harmless, the
+    # product is 0 either way, but a hazard all the same).  Forward phases never write a leaf, backward phases never write a tail row.
+    null_fw = int(perm[lev_lo[0]]) if nlw else 0
+    null_bw = int(perm[t0]) if nt else int(perm[nk - 1])
+    plan_fw = _gather.GatherPlan(T=threads, nfields=2, tbits=11, null_entry=(NS, null_fw))
     _gather.add_phase(plan_fw, [])      # level 0: the leaves are scaled by whoever writes the right-hand side (l0mask)
     for lv in range(1, nlw):
         ks = [int(perm[pos]) for pos in range(lev_lo[lv], lev_lo[lv + 1])]
@@ -311,7 +316,7 @@ def setup_socp_family(fam: CanonFamily, batch_params: Optional[List[str]] = None
     bw_cols = {}
     for sl, (t_, s_) in enumerate(zip(bw_t, bw_s)):
         bw_cols.setdefault(int(t_), []).append((sl, int(s_)))
-    plan_bw = _gather.GatherPlan(T=threads, nfields=2, tbits=11, null_entry=(NS, 0))
+    plan_bw = _gather.GatherPlan(T=threads, nfields=2, tbits=11, null_entry=(NS, null_bw))
     for lv in range(nlw - 1, -1, -1):
         ks = [int(perm[pos]) for pos in range(lev_lo[lv], lev_lo[lv + 1])]
         _gather.add_phase(plan_bw, [(k, 0, sorted(bw_cols[k], key=lambda x: inv[x[1]])) for k in ks if k in bw_cols])
