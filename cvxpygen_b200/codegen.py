@@ -69,7 +69,7 @@ def _family_header(setup: QPSetup, prefix: str, warps: Optional[int], ni: Option
     if warps is None:
         warps = max(1, min(MAX_WARPS[ni], (SMEM_BUDGET - blob_pad) // (pair_stride * 8)))
     trail = max(setup.schedule.n_trailing_tiles, 0)
-    s_stride = setup.refactor.n_slots + (setup.refactor.n_slots % 2)
+    s_stride = setup.refactor.n_slots + 32 + (setup.refactor.n_slots % 2)      # + one dummy slot per lane (padding ops of the factorisation)
     cblob_pad = (len(setup.blob_compact) + 127) // 128 * 128
     tail_stage = int(not big and cblob_pad + (w_stride + s_stride) * 8 <= SMEM_BUDGET)
     tail_warps = max(1, min(8, (SMEM_BUDGET - (cblob_pad if tail_stage else 0)) // ((w_stride + s_stride) * 8)))

@@ -177,7 +177,6 @@ __device__ __forceinline__ void tail_factor(const TailView& tv, double* S, int l
 #if CPG_TAIL_FACTOR_FORM == 2
   const int* rp = CPG_TAIL_LEVEL_PTR(tv, 1, tv.H->i_cround_ptr);
   const ushort4* cops = reinterpret_cast<const ushort4*>(tv.U16 + tv.H->h_cops) + lane;
-  const unsigned zs = (unsigned)(tv.H->n_slots - 1);
 #elif CPG_TAIL_FACTOR_FORM == 1
   const int* gtp = tv.I32 + tv.H->i_gtgt_ptr;
   const int* gsg = tv.I32 + tv.H->i_gseg;
@@ -200,8 +199,7 @@ __device__ __forceinline__ void tail_factor(const TailView& tv, double* S, int l
         ushort4 qn = (r + 1 < r1) ? __ldg(cops + (size_t)(r + 1) * LANES) : q;
         for (; r < r1; ++r) {
           const ushort4 qnn = (r + 2 < r1) ? __ldg(cops + (size_t)(r + 2) * LANES) : qn;
-          const double upd = S[q.x] - S[q.y] * S[q.z] * S[q.w & 0x7fffu];
-          if (q.x != zs) S[q.x] = upd;          // (padding ops aim at the zero slot: they only read it -- no write, no hazard)
+          S[q.x] -= S[q.y] * S[q.z] * S[q.w & 0x7fffu];      // (a padding op subtracts 0 from the lane's own dummy slot beyond n_slots)
           if (q.w & 0x8000u) __syncwarp();
           q = qn; qn = qnn;
         }

@@ -272,7 +272,7 @@ def pack_tail_blob(T) -> bytes:
     align_u16(4)
     # bit 15 of an op's 4th field (the pivot position j < 32768) = "a warp barrier follows this round" (last round of a sync group)
     cops = np.array(T.c_ops, dtype=np.int64, copy=True).reshape(-1, 4)
-    assert T.nk < 32768
+    assert T.nk < 32768 and T.n_slots + LANES < 65536
     for g in range(len(T.c_group_ptr) - 1):
         last = int(T.c_group_ptr[g + 1]) - 1
         if last >= int(T.c_group_ptr[g]):

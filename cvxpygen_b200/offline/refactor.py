@@ -291,7 +291,9 @@ def build_refactor_tables(F: LDLFactor, K: sp.csc_matrix, n_var: int) -> Refacto
             if seen & tg:
                 c_group_ptr.append(len(c_ops) // LANES); seen = set()
             seen |= tg
-            c_ops += [tuple(int(v) for v in op) for op in lst] + [(zs, zs, zs, zs)] * (LANES - len(lst))
+            # padding: lane l subtracts S[zs]^3 = 0 from ITS OWN dummy slot n_slots + l (the factor storage has 32 slots of slack):
+            # no lane ever writes what another lane touches, so a round needs no predicate and racecheck sees no hazard
+            c_ops += [tuple(int(v) for v in op) for op in lst] + [(n_slots + l, zs, zs, zs) for l in range(len(lst), LANES)]
         c_round_ptr.append(c_round_ptr[-1] + len(rounds))
         if len(rounds):
             c_group_ptr.append(len(c_ops) // LANES)
@@ -392,8 +394,9 @@ def emulate_factor_coloured(T: RefactorTables, rho_vec: np.ndarray) -> np.ndarra
         S[cols] = 1.0 / S[cols]
         for g in range(T.c_level_group[lv], T.c_level_group[lv + 1]):
             o = T.c_ops[T.c_group_ptr[g] * LANES:T.c_group_ptr[g + 1] * LANES]
-            real = o[:, 0] != T.zero_slot
+            real = o[:, 0] < T.n_slots                                          # (padding aims at the lanes' dummy slots beyond S)
             assert len(np.unique(o[real, 0])) == real.sum()                 # distinct targets inside a sync group
+            o = o[real]
             S[o[:, 0]] = S[o[:, 0]] - S[o[:, 1]] * S[o[:, 2]] * S[o[:, 3]]      # plain read-modify-writes, the whole group at once
         sc = T.scale[T.scale_ptr[lv]:T.scale_ptr[lv + 1]]
         if len(sc):
