@@ -245,7 +245,16 @@ __device__ __forceinline__ double tail_entry_fma(const double* S, const double* 
 // keeps ~28 KB that the words of one solve (29 KB for mpc_ltv_12_4_10) flush -- and were the kernel's largest stall
 // (long_scoreboard 2.9 cycles per issue, profiles/r2_matpar_v5_ncu_summary.md).  Slots beyond the tile's K hold `zero_word`
 // (S[zero slot] * w[0] = 0).  Entry k accumulates into chain k mod 4.
-constexpr int TAIL_PRE = 8;
+// Depth measured on B200 (profiles/r2_tail_prefetch_ab.jsonl): the matrix-parameter kernel gains 7.7 % from 12 words instead of 8
+// (86.3 -> 79.7 ms per 20 000; 4: 88.7, 16: 81.7, 20: 79.6), the tail and backward kernels of shared-matrix families do not (+-1 %).
+#ifndef CPG_TAIL_PRE
+#if defined(CPG_FAM_MATPAR) && CPG_FAM_MATPAR
+#define CPG_TAIL_PRE 12
+#else
+#define CPG_TAIL_PRE 8
+#endif
+#endif
+constexpr int TAIL_PRE = CPG_TAIL_PRE;
 __device__ __forceinline__ void tail_prefetch(unsigned (&pre)[TAIL_PRE], const int* h, const int* __restrict__ I32, int lane,
                                               unsigned zero_word) {
   const unsigned* wd = reinterpret_cast<const unsigned*>(I32) + h[0] + lane;

@@ -9,6 +9,14 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 VDIR = os.path.join(ROOT, 'tools', '_variants')
 VARIANTS = {      # name -> (family, extra nvcc flags, batch[, solver_opts])
     'ltv_cur': ('mpc_ltv_12_4_10', '', 20000),
+    'ltv_pre4': ('mpc_ltv_12_4_10', '-DCPG_TAIL_PRE=4', 20000),
+    'ltv_pre12': ('mpc_ltv_12_4_10', '-DCPG_TAIL_PRE=12', 20000),
+    'ltv_pre16': ('mpc_ltv_12_4_10', '-DCPG_TAIL_PRE=16', 20000),
+    'ltv_pre20': ('mpc_ltv_12_4_10', '-DCPG_TAIL_PRE=20', 20000),
+    'mpc_pre12': ('mpc_12_4_10', '-DCPG_TAIL_PRE=12', 100000, {'dmma': False}),
+    'mpc_pre16': ('mpc_12_4_10', '-DCPG_TAIL_PRE=16', 100000, {'dmma': False}),
+    'mpc_pre4': ('mpc_12_4_10', '-DCPG_TAIL_PRE=4', 100000, {'dmma': False}),
+    'mpc_cur': ('mpc_12_4_10', '', 100000, {'dmma': False}),
     'ltv_form0': ('mpc_ltv_12_4_10', '-DCPG_TAIL_FACTOR_FORM=0', 20000),
     'ltv_nounroll': ('mpc_ltv_12_4_10', '-DCPG_EQ_UNROLL=0', 20000),
     'ltv_form0_nounroll': ('mpc_ltv_12_4_10', '-DCPG_TAIL_FACTOR_FORM=0 -DCPG_EQ_UNROLL=0', 20000),
