@@ -8,6 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 VDIR = os.path.join(ROOT, 'tools', '_variants')
 VARIANTS = {      # name -> (family, extra nvcc flags, batch[, solver_opts])
+    'big_pre8': ('random_qp_700_100_700', '-DCPG_TAIL_PRE=8', 4000),
+    'big_pre16': ('random_qp_700_100_700', '-DCPG_TAIL_PRE=16', 4000),
     'ltv_cur': ('mpc_ltv_12_4_10', '', 20000),
     'ltv_pre4': ('mpc_ltv_12_4_10', '-DCPG_TAIL_PRE=4', 20000),
     'ltv_pre12': ('mpc_ltv_12_4_10', '-DCPG_TAIL_PRE=12', 20000),
@@ -85,13 +87,16 @@ def run(names, reps=3):
         dprim = torch.randn((B, mod.dims.n_prim), dtype=torch.float64, device='cuda')
         g = (lambda dp=None: mod.gradient_batch_device_mat(P, out.sol_x, out.sol_y, dprim, dparams=dp)) if mod.has_matrix_params \
             else (lambda dp=None: mod.gradient_batch_device(out.sol_y, dprim, dparams=dp))
-        dp = g(); torch.cuda.synchronize()
-        ts = []
-        for _ in range(reps):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); g(dp); e1.record(); torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        rec.update(bwd_ms=float(np.median(ts)), bwd_inst_per_s=B / (np.median(ts) * 1e-3))
+        try:
+            dp = g(); torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); g(dp); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            rec.update(bwd_ms=float(np.median(ts)), bwd_inst_per_s=B / (np.median(ts) * 1e-3))
+        except Exception as e:          # e.g. a family without a generated backward kernel
+            rec.update(bwd_ms=None, bwd_note=str(e)[:80])
         print(json.dumps(rec), flush=True)
 
 
