@@ -98,7 +98,12 @@ def _deal(cells, nwarp):
     return out
 
 
-def _cost(cells, nwarp, c_fixed=10.0, c_entry=1.0, c_shuf=3.0):
+import os as _os
+_C_FIXED = float(_os.environ.get('CPG_GATHER_C_FIXED', 10.0))      # (environment overrides: A/B sweeps of the cell-size model only)
+_C_SHUF = float(_os.environ.get('CPG_GATHER_C_SHUF', 3.0))
+
+
+def _cost(cells, nwarp, c_fixed=_C_FIXED, c_entry=1.0, c_shuf=_C_SHUF):
     per_warp = [0.0] * nwarp
     for r, w, chunk in _deal(cells, nwarp):
         per_warp[w] += c_fixed + c_entry * max(c[1] for c in chunk) + c_shuf * (max(c[0] for c in chunk).bit_length() - 1)
