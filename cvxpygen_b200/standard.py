@@ -79,8 +79,9 @@ def build_all(force: bool = False, verbose: bool = False, jobs: int = None):
     import concurrent.futures as cf
     jobs = jobs or max(1, min(len(STANDARD), (os.cpu_count() or 2), 8))      # nvcc's front end takes ~1-2 GB per family
     with cf.ThreadPoolExecutor(jobs) as ex:
-        futs = {name: ex.submit(build, name, force, verbose) for name in STANDARD}
-        return {name: f.result() for name, f in futs.items()}
+        order = sorted(STANDARD, key=lambda n: (n not in BIG_NAMES, n not in ('mpc_ltv_12_4_10', 'mpc_12_4_10', 'portfolio_qp_50_10')))   # longest compiles first
+        futs = {name: ex.submit(build, name, force, verbose) for name in order}
+        return {name: futs[name].result() for name in STANDARD}
 
 
 def load(name: str, device: int = 0):
